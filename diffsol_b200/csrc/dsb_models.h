@@ -1,0 +1,199 @@
+// dsb_models.h -- the user-equation side of the boundary: rhs / jac_mul / mass / init functors.
+//
+// These play the role of the Rust closures a diffsol user hands to
+// `OdeBuilder::rhs_implicit(f, jac_mul).mass(m).init(i, n)` (crates/diffsol/src/ode_solver/builder.rs:192-200):
+//   rhs     (x, p, t, y)        y = f(x, p, t)                 Fn(&V,&V,T,&mut V)
+//   jac_mul (x, p, t, v, y)     y = df/dx(x, p, t) . v         Fn(&V,&V,T,&V,&mut V)
+//   mass    (x, p, t, beta, y)  y = M x + beta y               Fn(&V,&V,T,T,&mut V)
+//   init    (p, t, y)           y = y0(p, t)                   Fn(&V,T,&mut V)
+// They are written once as __host__ __device__ code so the sm_100a kernels and the CPU oracle
+// integrate *the same equations with the same floating-point expression trees*; the expression
+// order follows the reference closures literally (file:line cited on each model).
+#pragma once
+#include "dsb_math.h"
+
+enum dsb_model_id {
+    DSB_MODEL_EXP_DECAY = 0,            // n=2  np=2   test_models/exponential_decay.rs:14-21,54-61,75-84
+    DSB_MODEL_EXP_DECAY_ALGEBRAIC = 1,  // n=3  np=1   test_models/exponential_decay_with_algebraic.rs:18-23,59-71,94-106,122-126
+    DSB_MODEL_ROBERTSON_DAE = 2,        // n=3  np=3   test_models/robertson.rs:59-90
+    DSB_MODEL_ROBERTSON_ODE = 3,        // n=3  np=3   test_models/robertson_ode.rs:46-104 (ngroups=1)
+    DSB_MODEL_ROBERTSON_ODE_G3 = 4,     // n=9  np=3   same, ngroups=3
+    DSB_MODEL_DYDT_Y2 = 5,              // n=10 np=0   test_models/dydt_y2.rs:9-19
+    DSB_MODEL_GAUSSIAN_DECAY = 6,       // n=10 np=10  test_models/gaussian_decay.rs:12-23
+    DSB_MODEL_VAN_DER_POL = 7,          // n=2  np=1   (not in the reference; BASELINE.json config 3)
+    DSB_MODEL_COUNT
+};
+
+// dy/dt = -k y, p = [k, y0]
+struct ModelExpDecay {
+    static constexpr int N = 2, NP = 2;
+    static constexpr bool HAS_MASS = false;
+    DSB_HD static void rhs(const double* x, const double* p, double, double* y) {
+        const double mk = -p[0];
+        for (int i = 0; i < N; ++i) y[i] = x[i] * mk;
+    }
+    DSB_HD static void jac_mul(const double*, const double* p, double, const double* v, double* y) {
+        const double mk = -p[0];
+        for (int i = 0; i < N; ++i) y[i] = v[i] * mk;
+    }
+    DSB_HD static void mass(const double* x, const double*, double, double beta, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = x[i] + beta * y[i];
+    }
+    DSB_HD static void init(const double* p, double, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = p[1];
+    }
+};
+
+// dy/dt = -a y ; 0 = z - y ; p = [a]; inconsistent IC [1,1,0]
+struct ModelExpDecayAlgebraic {
+    static constexpr int N = 3, NP = 1;
+    static constexpr bool HAS_MASS = true;
+    DSB_HD static void rhs(const double* x, const double* p, double, double* y) {
+        const double ma = -p[0];
+        for (int i = 0; i < N; ++i) y[i] = x[i] * ma;
+        y[N - 1] = x[N - 1] - x[N - 2];
+    }
+    DSB_HD static void jac_mul(const double*, const double* p, double, const double* v, double* y) {
+        const double ma = -p[0];
+        for (int i = 0; i < N; ++i) y[i] = v[i] * ma;
+        y[N - 1] = v[N - 1] - v[N - 2];
+    }
+    DSB_HD static void mass(const double* x, const double*, double, double beta, double* y) {
+        const double yn = beta * y[N - 1];
+        for (int i = 0; i < N; ++i) y[i] = x[i] + beta * y[i];
+        y[N - 1] = yn;
+    }
+    DSB_HD static void init(const double*, double, double* y) {
+        y[0] = 1.0; y[1] = 1.0; y[2] = 0.0;
+    }
+};
+
+// Robertson chemical kinetics as an index-1 DAE, p = [k1, k2, k3]
+struct ModelRobertsonDae {
+    static constexpr int N = 3, NP = 3;
+    static constexpr bool HAS_MASS = true;
+    DSB_HD static void rhs(const double* x, const double* p, double, double* y) {
+        y[0] = -p[0] * x[0] + p[1] * x[1] * x[2];
+        y[1] = p[0] * x[0] - p[1] * x[1] * x[2] - p[2] * x[1] * x[1];
+        y[2] = x[0] + x[1] + x[2] - 1.0;
+    }
+    DSB_HD static void jac_mul(const double* x, const double* p, double, const double* v, double* y) {
+        y[0] = -p[0] * v[0] + p[1] * v[1] * x[2] + p[1] * x[1] * v[2];
+        y[1] = p[0] * v[0] - p[1] * v[1] * x[2] - p[1] * x[1] * v[2] - 2.0 * p[2] * x[1] * v[1];
+        y[2] = v[0] + v[1] + v[2];
+    }
+    DSB_HD static void mass(const double* x, const double*, double, double beta, double* y) {
+        y[0] = x[0] + beta * y[0];
+        y[1] = x[1] + beta * y[1];
+        y[2] = beta * y[2];
+    }
+    DSB_HD static void init(const double*, double, double* y) {
+        y[0] = 1.0; y[1] = 0.0; y[2] = 0.0;
+    }
+};
+
+// Robertson as a pure ODE, NG decoupled copies (robertson_ode.rs `ngroups`)
+template <int NG>
+struct ModelRobertsonOde {
+    static constexpr int N = 3 * NG, NP = 3;
+    static constexpr bool HAS_MASS = false;
+    DSB_HD static void rhs(const double* x, const double* p, double, double* y) {
+        for (int ig = 0; ig < NG; ++ig) {
+            const int i = ig * 3;
+            y[i] = -p[0] * x[i] + p[1] * x[i + 1] * x[i + 2];
+            y[i + 1] = p[0] * x[i] - p[1] * x[i + 1] * x[i + 2] - p[2] * x[i + 1] * x[i + 1];
+            y[i + 2] = p[2] * x[i + 1] * x[i + 1];
+        }
+    }
+    DSB_HD static void jac_mul(const double* x, const double* p, double, const double* v, double* y) {
+        for (int ig = 0; ig < NG; ++ig) {
+            const int i = ig * 3;
+            y[i] = -p[0] * v[i] + p[1] * v[i + 1] * x[i + 2] + p[1] * x[i + 1] * v[i + 2];
+            y[i + 1] = p[0] * v[i] - p[1] * v[i + 1] * x[i + 2] - p[1] * x[i + 1] * v[i + 2]
+                       - 2.0 * p[2] * x[i + 1] * v[i + 1];
+            y[i + 2] = 2.0 * p[2] * x[i + 1] * v[i + 1];
+        }
+    }
+    DSB_HD static void mass(const double* x, const double*, double, double beta, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = x[i] + beta * y[i];
+    }
+    DSB_HD static void init(const double*, double, double* y) {
+        for (int ig = 0; ig < NG; ++ig) { y[3 * ig] = 1.0; y[3 * ig + 1] = 0.0; y[3 * ig + 2] = 0.0; }
+    }
+};
+
+// dy/dt = y^2, y0 = -200
+template <int NS>
+struct ModelDydtY2 {
+    static constexpr int N = NS, NP = 0;
+    static constexpr bool HAS_MASS = false;
+    DSB_HD static void rhs(const double* x, const double*, double, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = x[i] * x[i];
+    }
+    DSB_HD static void jac_mul(const double* x, const double*, double, const double* v, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = v[i] * x[i] * 2.0;
+    }
+    DSB_HD static void mass(const double* x, const double*, double, double beta, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = x[i] + beta * y[i];
+    }
+    DSB_HD static void init(const double*, double, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = -200.0;
+    }
+};
+
+// dy/dt = -a t y, p = [a_0..a_{n-1}]
+template <int NS>
+struct ModelGaussianDecay {
+    static constexpr int N = NS, NP = NS;
+    static constexpr bool HAS_MASS = false;
+    DSB_HD static void rhs(const double* x, const double* p, double t, double* y) {
+        const double mt = -t;
+        for (int i = 0; i < N; ++i) y[i] = x[i] * p[i] * mt;
+    }
+    DSB_HD static void jac_mul(const double*, const double* p, double t, const double* v, double* y) {
+        const double mt = -t;
+        for (int i = 0; i < N; ++i) y[i] = v[i] * p[i] * mt;
+    }
+    DSB_HD static void mass(const double* x, const double*, double, double beta, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = x[i] + beta * y[i];
+    }
+    DSB_HD static void init(const double*, double, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = 1.0;
+    }
+};
+
+// Van der Pol oscillator y1' = y2, y2' = mu (1 - y1^2) y2 - y1, p = [mu], y0 = [2, 0]
+struct ModelVanDerPol {
+    static constexpr int N = 2, NP = 1;
+    static constexpr bool HAS_MASS = false;
+    DSB_HD static void rhs(const double* x, const double* p, double, double* y) {
+        y[0] = x[1];
+        y[1] = p[0] * (1.0 - x[0] * x[0]) * x[1] - x[0];
+    }
+    DSB_HD static void jac_mul(const double* x, const double* p, double, const double* v, double* y) {
+        y[0] = v[1];
+        y[1] = p[0] * (-2.0 * x[0] * v[0]) * x[1] + p[0] * (1.0 - x[0] * x[0]) * v[1] - v[0];
+    }
+    DSB_HD static void mass(const double* x, const double*, double, double beta, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = x[i] + beta * y[i];
+    }
+    DSB_HD static void init(const double*, double, double* y) {
+        y[0] = 2.0; y[1] = 0.0;
+    }
+};
+
+// Compile-time dispatch over the registry: calls f.template operator()<Model>() for `id`.
+template <class F>
+inline bool dsb_dispatch_model(int id, F&& f) {
+    switch (id) {
+        case DSB_MODEL_EXP_DECAY: f.template operator()<ModelExpDecay>(); return true;
+        case DSB_MODEL_EXP_DECAY_ALGEBRAIC: f.template operator()<ModelExpDecayAlgebraic>(); return true;
+        case DSB_MODEL_ROBERTSON_DAE: f.template operator()<ModelRobertsonDae>(); return true;
+        case DSB_MODEL_ROBERTSON_ODE: f.template operator()<ModelRobertsonOde<1>>(); return true;
+        case DSB_MODEL_ROBERTSON_ODE_G3: f.template operator()<ModelRobertsonOde<3>>(); return true;
+        case DSB_MODEL_DYDT_Y2: f.template operator()<ModelDydtY2<10>>(); return true;
+        case DSB_MODEL_GAUSSIAN_DECAY: f.template operator()<ModelGaussianDecay<10>>(); return true;
+        case DSB_MODEL_VAN_DER_POL: f.template operator()<ModelVanDerPol>(); return true;
+        default: return false;
+    }
+}

@@ -1,0 +1,212 @@
+// oracle/dsb_oracle_capi.cpp -- TEST INFRASTRUCTURE (see dsb_oracle.hpp).
+// extern "C" entry points used through ctypes by tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs.
+#include "dsb_oracle.hpp"
+
+#include <atomic>
+#include <memory>
+#include <thread>
+
+using namespace orc;
+
+// Flat problem description; mirrors what OdeBuilder collects (builder.rs:112-140).
+struct orc_problem_desc {
+    int32_t model_id;
+    int32_t method;        // 0 = Bdf, 1 = Sdirk(tr_bdf2), 2 = Sdirk(esdirk34)
+    int32_t use_coloring;
+    int32_t powmode;       // 0 = libm pow (reference-literal), 1 = dsb_pow (shared with CUDA)
+    double rtol;
+    double t0, h0;
+    int32_t natol;         // 1 => broadcast (builder default), else == n
+    int32_t has_options;   // 0 => OdeSolverOptions::default()
+    double atol[64];
+    // option overrides (only read when has_options != 0), same order as orc::Options
+    int32_t max_nonlinear_solver_iterations, max_error_test_failures, max_nonlinear_solver_failures;
+    int32_t update_jacobian_after_steps, update_rhs_jacobian_after_steps, pad0;
+    double nonlinear_solver_tolerance, min_timestep;
+    double max_timestep_growth, min_timestep_growth, max_timestep_shrink, min_timestep_shrink;
+    double threshold_to_update_jacobian, threshold_to_update_rhs_jacobian;
+    double pi_control_proportional, pi_control_integral;
+};
+
+static int build_problem(const orc_problem_desc* d, const double* p, int np, Problem* pr) {
+    if (!model_by_id(d->model_id, &pr->model)) return ST_BAD_ARG;
+    const int n = pr->model.n;
+    if (np != pr->model.np) return ST_BAD_ARG;
+    pr->p.assign(p, p + np);
+    pr->rtol = d->rtol; pr->t0 = d->t0; pr->h0 = d->h0;
+    pr->atol.resize(n);
+    if (d->natol == 1) for (int i = 0; i < n; ++i) pr->atol[i] = d->atol[0];
+    else if (d->natol == n && n <= 64) for (int i = 0; i < n; ++i) pr->atol[i] = d->atol[i];
+    else return ST_BAD_ARG;
+    pr->math.powmode = d->powmode;
+    if (d->has_options) {
+        Options& o = pr->opt;
+        o.max_nonlinear_solver_iterations = d->max_nonlinear_solver_iterations;
+        o.max_error_test_failures = d->max_error_test_failures;
+        o.max_nonlinear_solver_failures = d->max_nonlinear_solver_failures;
+        o.update_jacobian_after_steps = d->update_jacobian_after_steps;
+        o.update_rhs_jacobian_after_steps = d->update_rhs_jacobian_after_steps;
+        o.nonlinear_solver_tolerance = d->nonlinear_solver_tolerance;
+        o.min_timestep = d->min_timestep;
+        o.max_timestep_growth = d->max_timestep_growth; o.min_timestep_growth = d->min_timestep_growth;
+        o.max_timestep_shrink = d->max_timestep_shrink; o.min_timestep_shrink = d->min_timestep_shrink;
+        o.threshold_to_update_jacobian = d->threshold_to_update_jacobian;
+        o.threshold_to_update_rhs_jacobian = d->threshold_to_update_rhs_jacobian;
+        o.pi_control_proportional = d->pi_control_proportional;
+        o.pi_control_integral = d->pi_control_integral;
+    }
+    pr->use_coloring = d->use_coloring != 0;
+    if (pr->use_coloring) pr->build_coloring();
+    return ST_OK;
+}
+
+static Method* make_method(const Problem& pr, int method, int* err) {
+    switch (method) {
+        case 0: return new_bdf(pr, err);
+        case 1: return new_sdirk(pr, 0, err);
+        case 2: return new_sdirk(pr, 1, err);
+    }
+    *err = ST_BAD_ARG;
+    return nullptr;
+}
+
+static void export_stats(const Problem& pr, const Method* m, int64_t* stats) {
+    if (!stats) return;
+    for (int i = 0; i < S_COUNT; ++i) stats[i] = m ? m->stats().v[i] : 0;
+    stats[S_RHS_CALLS] = pr.n_calls;
+    stats[S_RHS_JAC_MULS] = pr.n_jac_muls;
+    stats[S_RHS_MATRIX_EVALS] = pr.n_matrix_evals;
+}
+
+extern "C" {
+
+int orc_model_dims(int model_id, int* n, int* np, int* has_mass) {
+    Model m;
+    if (!model_by_id(model_id, &m)) return ST_BAD_ARG;
+    *n = m.n; *np = m.np; *has_mass = m.has_mass ? 1 : 0;
+    return ST_OK;
+}
+
+// `problem.bdf::<LS>()?.solve_dense(t_eval)`: out is n x nt column-major; fin = {t, h, order}
+int orc_solve_dense(const orc_problem_desc* d, const double* p, int np, const double* t_eval, int nt,
+                    double* out, int64_t* stats, double* fin) {
+    Problem pr;
+    int err = build_problem(d, p, np, &pr);
+    if (err) return err;
+    std::unique_ptr<Method> m(make_method(pr, d->method, &err));
+    if (!m) { export_stats(pr, nullptr, stats); return err; }
+    err = solve_dense(*m, t_eval, nt, pr.n(), out);
+    export_stats(pr, m.get(), stats);
+    if (fin) { fin[0] = m->t(); fin[1] = m->h(); fin[2] = (double)m->cur_order(); }
+    return err;
+}
+
+// The reference's test harness `test_ode_solver(.., use_tstop = false)` (ode_solver/mod.rs:104-194):
+// for each point: step while |t| < |t_point|, then interpolate(t_point).  out is n x npts.
+int orc_harness(const orc_problem_desc* d, const double* p, int np, const double* t_points, int npts,
+                double* out, int64_t* stats, double* fin) {
+    Problem pr;
+    int err = build_problem(d, p, np, &pr);
+    if (err) return err;
+    std::unique_ptr<Method> m(make_method(pr, d->method, &err));
+    if (!m) { export_stats(pr, nullptr, stats); return err; }
+    const int n = pr.n();
+    for (int k = 0; k < npts && !err; ++k) {
+        while (std::fabs(m->t()) < std::fabs(t_points[k])) {
+            StopReason r = m->step(&err);
+            if (r == STEP_ERROR) break;
+        }
+        if (err) break;
+        err = m->interpolate(t_points[k], out + (size_t)k * n);
+    }
+    export_stats(pr, m.get(), stats);
+    if (fin) { fin[0] = m->t(); fin[1] = m->h(); fin[2] = (double)m->cur_order(); }
+    return err;
+}
+
+// The same with `use_tstop = true`: set_stop_time(point) then step until TstopReached; the solution
+// is state().y (which for Bdf is the predictor).  out is n x npts.
+int orc_harness_tstop(const orc_problem_desc* d, const double* p, int np, const double* t_points, int npts,
+                      double* out, int64_t* stats, double* fin) {
+    Problem pr;
+    int err = build_problem(d, p, np, &pr);
+    if (err) return err;
+    std::unique_ptr<Method> m(make_method(pr, d->method, &err));
+    if (!m) { export_stats(pr, nullptr, stats); return err; }
+    const int n = pr.n();
+    for (int k = 0; k < npts && !err; ++k) {
+        int e = m->set_stop_time(t_points[k]);
+        if (e == ST_OK) {
+            while (true) {
+                StopReason r = m->step(&err);
+                if (r == STEP_ERROR || r == TSTOP_REACHED) break;
+            }
+        }
+        for (int i = 0; i < n; ++i) out[(size_t)k * n + i] = m->y()[i];
+    }
+    export_stats(pr, m.get(), stats);
+    if (fin) { fin[0] = m->t(); fin[1] = m->h(); fin[2] = (double)m->cur_order(); }
+    return err;
+}
+
+// Batched driver: instance b uses params[b*np .. (b+1)*np) (instance-major, as the reference lays
+// out batched parameters, test_models/exponential_decay.rs:297-304).  out[b] is n x nt col-major,
+// stats[b] the 16 counters, status[b] the error code.  threads over instances = the CPU baseline.
+int orc_batch_solve_dense(const orc_problem_desc* d, const double* params, int np, int64_t nbatch,
+                          const double* t_eval, int nt, int nthreads,
+                          double* out, int64_t* stats, int32_t* status) {
+    Model mm;
+    if (!model_by_id(d->model_id, &mm)) return ST_BAD_ARG;
+    const int n = mm.n;
+    // std::thread pool with a shared work counter (dynamic schedule, 16 instances per grab);
+    // libgomp is not usable in this image.
+    int nt_use = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
+    if (nt_use < 1) nt_use = 1;
+    std::atomic<int64_t> next(0);
+    auto worker = [&]() {
+        const int64_t chunk = 16;
+        while (true) {
+            int64_t b0 = next.fetch_add(chunk);
+            if (b0 >= nbatch) break;
+            int64_t b1 = b0 + chunk < nbatch ? b0 + chunk : nbatch;
+            for (int64_t b = b0; b < b1; ++b) {
+                int err = orc_solve_dense(d, params + (size_t)b * np, np, t_eval, nt,
+                                          out ? out + (size_t)b * n * nt : nullptr,
+                                          stats ? stats + (size_t)b * S_COUNT : nullptr, nullptr);
+                if (status) status[b] = err;
+            }
+        }
+    };
+    if (nt_use == 1) worker();
+    else {
+        std::vector<std::thread> pool;
+        for (int i = 0; i < nt_use; ++i) pool.emplace_back(worker);
+        for (auto& th : pool) th.join();
+    }
+    return ST_OK;
+}
+
+int orc_num_threads() { return (int)std::thread::hardware_concurrency(); }
+
+double orc_pow(double x, double y, int powmode) { Math m; m.powmode = powmode; return m.pow(x, y); }
+double orc_powi(double x, int n) { return dsb_powi(x, n); }
+
+// Known-answer hooks for the reference's unit tests of the building blocks.
+double orc_squared_norm(const double* x, const double* y, const double* atol, double rtol, int n) {
+    return squared_norm(x, y, atol, rtol, n);
+}
+int orc_lu_solve(const double* A, int n, double* b) {
+    DenseLU lu; lu.factor(A, n);
+    return lu.solve(b) ? 0 : ST_LU_SOLVE_FAILED;
+}
+int orc_lu_factor(const double* A, int n, double* lu_out, int32_t* piv_out) {
+    DenseLU lu; lu.factor(A, n);
+    for (size_t i = 0; i < (size_t)n * n; ++i) lu_out[i] = lu.lu[i];
+    // expand the permutation sequence into LAPACK-style ipiv (row i swapped with piv[i])
+    for (int i = 0; i < n; ++i) piv_out[i] = i;
+    for (auto& pq : lu.perm) piv_out[pq.first] = pq.second;
+    return 0;
+}
+
+}  // extern "C"

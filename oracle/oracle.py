@@ -1,0 +1,205 @@
+"""ctypes wrapper around oracle/_ref/libdsb_oracle.so -- TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  The product package (diffsol_b200) never does.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_ref", "libdsb_oracle.so")
+
+S_NAMES = [
+    "number_of_linear_solver_setups",
+    "number_of_linear_solver_setups_from_checkpoint",
+    "number_of_linear_solver_setups_from_first_convergence_fail",
+    "number_of_linear_solver_setups_from_second_convergence_fail",
+    "number_of_linear_solver_setups_from_error_test_fail",
+    "number_of_linear_solver_setups_from_step_success",
+    "number_of_steps",
+    "number_of_error_test_failures",
+    "number_of_nonlinear_solver_iterations",
+    "number_of_nonlinear_solver_fails",
+    "rhs_number_of_calls",
+    "rhs_number_of_jac_muls",
+    "rhs_number_of_matrix_evals",
+]
+S_COUNT = 16
+
+METHODS = {"bdf": 0, "tr_bdf2": 1, "esdirk34": 2}
+MODELS = {
+    "exp_decay": 0,
+    "exp_decay_algebraic": 1,
+    "robertson_dae": 2,
+    "robertson_ode": 3,
+    "robertson_ode_g3": 4,
+    "dydt_y2": 5,
+    "gaussian_decay": 6,
+    "van_der_pol": 7,
+}
+
+
+class ProblemDesc(ctypes.Structure):
+    _fields_ = [
+        ("model_id", ctypes.c_int32),
+        ("method", ctypes.c_int32),
+        ("use_coloring", ctypes.c_int32),
+        ("powmode", ctypes.c_int32),
+        ("rtol", ctypes.c_double),
+        ("t0", ctypes.c_double),
+        ("h0", ctypes.c_double),
+        ("natol", ctypes.c_int32),
+        ("has_options", ctypes.c_int32),
+        ("atol", ctypes.c_double * 64),
+        ("max_nonlinear_solver_iterations", ctypes.c_int32),
+        ("max_error_test_failures", ctypes.c_int32),
+        ("max_nonlinear_solver_failures", ctypes.c_int32),
+        ("update_jacobian_after_steps", ctypes.c_int32),
+        ("update_rhs_jacobian_after_steps", ctypes.c_int32),
+        ("pad0", ctypes.c_int32),
+        ("nonlinear_solver_tolerance", ctypes.c_double),
+        ("min_timestep", ctypes.c_double),
+        ("max_timestep_growth", ctypes.c_double),
+        ("min_timestep_growth", ctypes.c_double),
+        ("max_timestep_shrink", ctypes.c_double),
+        ("min_timestep_shrink", ctypes.c_double),
+        ("threshold_to_update_jacobian", ctypes.c_double),
+        ("threshold_to_update_rhs_jacobian", ctypes.c_double),
+        ("pi_control_proportional", ctypes.c_double),
+        ("pi_control_integral", ctypes.c_double),
+    ]
+
+
+def build(force=False):
+    """Compile the oracle with the recipe committed in oracle/Makefile."""
+    if force or not os.path.exists(_LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        dp = ctypes.POINTER(ctypes.c_double)
+        ip = ctypes.POINTER(ctypes.c_int64)
+        for name in ("orc_solve_dense", "orc_harness", "orc_harness_tstop"):
+            f = getattr(L, name)
+            f.restype = ctypes.c_int
+            f.argtypes = [ctypes.POINTER(ProblemDesc), dp, ctypes.c_int, dp, ctypes.c_int, dp, ip, dp]
+        L.orc_batch_solve_dense.restype = ctypes.c_int
+        L.orc_batch_solve_dense.argtypes = [
+            ctypes.POINTER(ProblemDesc), dp, ctypes.c_int, ctypes.c_int64, dp, ctypes.c_int, ctypes.c_int,
+            dp, ip, ctypes.POINTER(ctypes.c_int32)]
+        L.orc_model_dims.argtypes = [ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 3
+        L.orc_pow.restype = ctypes.c_double
+        L.orc_pow.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_int]
+        L.orc_powi.restype = ctypes.c_double
+        L.orc_powi.argtypes = [ctypes.c_double, ctypes.c_int]
+        L.orc_squared_norm.restype = ctypes.c_double
+        L.orc_squared_norm.argtypes = [dp, dp, dp, ctypes.c_double, ctypes.c_int]
+        L.orc_lu_solve.argtypes = [dp, ctypes.c_int, dp]
+        L.orc_lu_factor.argtypes = [dp, ctypes.c_int, dp, ctypes.POINTER(ctypes.c_int32)]
+        L.orc_num_threads.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def model_dims(model):
+    n, np_, hm = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = lib().orc_model_dims(MODELS[model], ctypes.byref(n), ctypes.byref(np_), ctypes.byref(hm))
+    assert rc == 0
+    return n.value, np_.value, bool(hm.value)
+
+
+def make_desc(model, method="bdf", rtol=1e-6, atol=1e-6, t0=0.0, h0=1.0, use_coloring=False,
+              powmode=0, options=None):
+    d = ProblemDesc()
+    d.model_id = MODELS[model] if isinstance(model, str) else int(model)
+    d.method = METHODS[method] if isinstance(method, str) else int(method)
+    d.use_coloring = int(use_coloring)
+    d.powmode = int(powmode)
+    d.rtol, d.t0, d.h0 = float(rtol), float(t0), float(h0)
+    atol = np.atleast_1d(np.asarray(atol, dtype=np.float64))
+    d.natol = len(atol)
+    for i, a in enumerate(atol):
+        d.atol[i] = a
+    if options:
+        d.has_options = 1
+        defaults = dict(
+            max_nonlinear_solver_iterations=10, max_error_test_failures=40, max_nonlinear_solver_failures=50,
+            update_jacobian_after_steps=20, update_rhs_jacobian_after_steps=50,
+            nonlinear_solver_tolerance=0.2, min_timestep=1e-13, max_timestep_growth=2.0,
+            min_timestep_growth=2.0, max_timestep_shrink=0.9, min_timestep_shrink=0.5,
+            threshold_to_update_jacobian=0.3, threshold_to_update_rhs_jacobian=0.2,
+            pi_control_proportional=0.0, pi_control_integral=0.5)
+        defaults.update(options)
+        for k, v in defaults.items():
+            setattr(d, k, v)
+    return d
+
+
+def _stats_dict(stats):
+    return {name: int(stats[i]) for i, name in enumerate(S_NAMES)}
+
+
+def _run(fn, desc, p, ts):
+    n, np_, _ = model_dims(desc.model_id) if False else _dims_by_id(desc.model_id)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    assert p.size == np_, (p.size, np_)
+    ts = np.ascontiguousarray(ts, dtype=np.float64)
+    out = np.full((len(ts), n), np.nan)
+    stats = np.zeros(S_COUNT, dtype=np.int64)
+    fin = np.zeros(3)
+    rc = fn(ctypes.byref(desc), _dp(p), int(p.size), _dp(ts), len(ts), _dp(out),
+            stats.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _dp(fin))
+    return rc, out, _stats_dict(stats), dict(t=fin[0], h=fin[1], order=int(fin[2]))
+
+
+def _dims_by_id(model_id):
+    n, np_, hm = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = lib().orc_model_dims(int(model_id), ctypes.byref(n), ctypes.byref(np_), ctypes.byref(hm))
+    assert rc == 0
+    return n.value, np_.value, bool(hm.value)
+
+
+def solve_dense(desc, p, t_eval):
+    """problem.<method>().solve_dense(t_eval) -> (rc, ys[nt, n], stats, final)"""
+    return _run(lib().orc_solve_dense, desc, p, t_eval)
+
+
+def harness(desc, p, t_points, use_tstop=False):
+    """The reference's test_ode_solver() loop -> (rc, ys[npts, n], stats, final)"""
+    return _run(lib().orc_harness_tstop if use_tstop else lib().orc_harness, desc, p, t_points)
+
+
+def batch_solve_dense(desc, params, t_eval, nthreads=0):
+    """params[B, np] instance-major -> (ys[B, nt, n], stats[B, 16], status[B])"""
+    n, np_, _ = _dims_by_id(desc.model_id)
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, max(np_, 1))
+    B = params.shape[0]
+    t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
+    out = np.full((B, len(t_eval), n), np.nan)
+    stats = np.zeros((B, S_COUNT), dtype=np.int64)
+    status = np.zeros(B, dtype=np.int32)
+    rc = lib().orc_batch_solve_dense(
+        ctypes.byref(desc), _dp(params), np_, B, _dp(t_eval), len(t_eval), int(nthreads), _dp(out),
+        stats.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+        status.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    assert rc == 0
+    return out, stats, status
+
+
+def num_threads():
+    return lib().orc_num_threads()
