@@ -1,0 +1,177 @@
+/* diffsol_b200.h -- C ABI of the B200-native batched implicit ODE/DAE integrator.
+ *
+ * This is the drop-in boundary for ONE hot path of martinjrobins/diffsol: the implicit step loop
+ * (`Bdf::step`, `Sdirk::step`) driven by `solve_dense`, run over a BATCH of independent problem
+ * instances, each with its own adaptive step size / order / Newton state.  The reference reaches
+ * that path through Rust traits, not an FFI; the entry points below are what
+ * a Rust shim crate (`impl OdeSolverMethod for BatchedBdf`, `impl LinearSolver<BatchMat>`) or the
+ * reference's own C layer (crates/diffsol-c) would bind.  Conventions follow crates/diffsol-c:
+ * opaque handles, every call returns an int (0 = OK, crates/diffsol-c/src/c_api_utils.rs:3-5),
+ * message in a thread-local last-error string (crates/diffsol-c/src/error_c.rs:12-46), enums as int.
+ *
+ * Paths in comments are relative to /root/reference/crates/ (diffsol @ ad3477a).
+ * All pointers are plain host or device pointers; there are no torch types in this ABI.
+ */
+#ifndef DIFFSOL_B200_H
+#define DIFFSOL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return codes (crates/diffsol-c/src/c_api_utils.rs:3-5) ------------------------------------ */
+#define DSB_OK 0
+#define DSB_ERR (-1)
+#define DSB_BAD_ARG (-2)
+
+/* ---- per-instance status: an instance that fails must not abort the batch.  Values mirror the
+ * variants of OdeSolverError (diffsol/src/error.rs:40-93) the hot path can raise. ------------------ */
+enum dsb_status {
+    DSB_STATUS_OK = 0,
+    DSB_STATUS_STEP_SIZE_TOO_SMALL = 1,            /* OdeSolverError::StepSizeTooSmall            bdf.rs:559-563 */
+    DSB_STATUS_TOO_MANY_ERROR_TEST_FAILURES = 2,   /* OdeSolverError::TooManyErrorTestFailures   bdf.rs:1456-1464 */
+    DSB_STATUS_TOO_MANY_NONLINEAR_FAILURES = 3,    /* OdeSolverError::TooManyNonlinearSolverFailures bdf.rs:1366-1375 */
+    DSB_STATUS_STOP_TIME_BEFORE_CURRENT = 4,       /* OdeSolverError::StopTimeBeforeCurrentTime  bdf.rs:706-716 */
+    DSB_STATUS_STOP_TIME_AT_CURRENT = 5,           /* OdeSolverError::StopTimeAtCurrentTime      bdf.rs:1593-1597 */
+    DSB_STATUS_INITIAL_CONDITION_DID_NOT_CONVERGE = 6, /* NonLinearSolverError::InitialConditionDidNotConverge state.rs:152-154 */
+    DSB_STATUS_LINESEARCH_FAILED = 7,
+    DSB_STATUS_INTERPOLATION_TIME_AFTER_CURRENT = 8,
+    DSB_STATUS_LU_SOLVE_FAILED = 9
+};
+
+/* ---- OdeSolverType (crates/diffsol-c: OdeSolverType{Bdf,Esdirk34,TrBdf2,Tsit45}) ------------------ */
+enum dsb_method {
+    DSB_METHOD_BDF = 0,        /* problem.bdf::<LS>()       ode_solver/problem.rs:649-655 */
+    DSB_METHOD_TR_BDF2 = 1,    /* problem.tr_bdf2::<LS>()   ode_solver/problem.rs:320-328 */
+    DSB_METHOD_ESDIRK34 = 2    /* problem.esdirk34::<LS>() */
+};
+
+/* ---- built-in equation sets (device functors; diffsol_b200/csrc/dsb_models.h) -------------------- */
+enum dsb_model {
+    DSB_EXP_DECAY = 0, DSB_EXP_DECAY_ALGEBRAIC = 1, DSB_ROBERTSON_DAE = 2, DSB_ROBERTSON_ODE = 3,
+    DSB_ROBERTSON_ODE_G3 = 4, DSB_DYDT_Y2 = 5, DSB_GAUSSIAN_DECAY = 6, DSB_VAN_DER_POL = 7
+};
+
+/* ---- statistics: one row of DSB_NSTATS int64 per instance.  Indices 0-9 are the fields of
+ * OdeSolverStatistics (ode_solver/mod.rs:27-49), 10-12 the rhs OpStatistics (op/mod.rs:108-145). --- */
+enum dsb_stat {
+    DSB_STAT_LINEAR_SOLVER_SETUPS = 0,
+    DSB_STAT_SETUPS_FROM_CHECKPOINT = 1,
+    DSB_STAT_SETUPS_FROM_FIRST_CONVERGENCE_FAIL = 2,
+    DSB_STAT_SETUPS_FROM_SECOND_CONVERGENCE_FAIL = 3,
+    DSB_STAT_SETUPS_FROM_ERROR_TEST_FAIL = 4,
+    DSB_STAT_SETUPS_FROM_STEP_SUCCESS = 5,
+    DSB_STAT_STEPS = 6,
+    DSB_STAT_ERROR_TEST_FAILURES = 7,
+    DSB_STAT_NONLINEAR_SOLVER_ITERATIONS = 8,
+    DSB_STAT_NONLINEAR_SOLVER_FAILS = 9,
+    DSB_STAT_RHS_CALLS = 10,
+    DSB_STAT_RHS_JAC_MULS = 11,
+    DSB_STAT_RHS_MATRIX_EVALS = 12,
+    DSB_NSTATS = 16
+};
+
+/* ---- OdeSolverOptions + InitialConditionSolverOptions (ode_solver/problem.rs:15-152) and the
+ * BdfConfig / SdirkConfig growth clamps (ode_solver/config.rs:54-110); same names, same defaults. --- */
+typedef struct dsb_options {
+    int32_t max_nonlinear_solver_iterations;   /* 10 */
+    int32_t max_error_test_failures;           /* 40, per step */
+    int32_t max_nonlinear_solver_failures;     /* 50, cumulative */
+    int32_t update_jacobian_after_steps;       /* 20 */
+    int32_t update_rhs_jacobian_after_steps;   /* 50 */
+    int32_t ic_max_linesearch_iterations;      /* 10 */
+    int32_t ic_max_newton_iterations;          /* 10 */
+    int32_t ic_max_linear_solver_setups;       /* 4 */
+    int32_t ic_use_linesearch;                 /* 1 */
+    int32_t reserved0;
+    double nonlinear_solver_tolerance;         /* 0.2 */
+    double min_timestep;                       /* 1e-13 */
+    double max_timestep_growth;                /* 2.0 */
+    double min_timestep_growth;                /* 2.0 */
+    double max_timestep_shrink;                /* 0.9 */
+    double min_timestep_shrink;                /* 0.5 */
+    double threshold_to_update_jacobian;       /* 0.3 */
+    double threshold_to_update_rhs_jacobian;   /* 0.2 */
+    double pi_control_proportional;            /* 0.0 */
+    double pi_control_integral;                /* 0.5 */
+    double ic_step_reduction_factor;           /* 0.5 */
+    double ic_armijo_constant;                 /* 1e-4 */
+} dsb_options;
+
+void dsb_options_default(dsb_options* opt);
+
+const char* dsb_last_error(void);               /* thread-local, crates/diffsol-c/src/error_c.rs */
+const char* dsb_version(void);
+int dsb_device_count(int* count);               /* DSB_ERR when the CUDA runtime reports none */
+
+/* ---- problem = what OdeBuilder::new()...build() returns (ode_solver/builder.rs:112-140,1447-1626) --
+ * Defaults: t0 = 0, h0 = 1, rtol = 1e-6, atol = [1e-6] broadcast. */
+typedef struct dsb_problem dsb_problem;
+int dsb_problem_new(int model, dsb_problem** out);
+int dsb_problem_free(dsb_problem* p);
+int dsb_problem_dims(const dsb_problem* p, int32_t* nstates, int32_t* nparams, int32_t* has_mass);
+int dsb_problem_set_rtol(dsb_problem* p, double rtol);                      /* OdeBuilder::rtol */
+int dsb_problem_set_atol(dsb_problem* p, const double* atol, int32_t n);    /* OdeBuilder::atol; n == 1 broadcasts */
+int dsb_problem_set_t0(dsb_problem* p, double t0);                          /* OdeBuilder::t0 */
+int dsb_problem_set_h0(dsb_problem* p, double h0);                          /* OdeBuilder::h0 */
+int dsb_problem_set_options(dsb_problem* p, const dsb_options* opt);        /* OdeBuilder::ode_options / ic_options */
+int dsb_problem_get_options(const dsb_problem* p, dsb_options* opt);
+
+/* ---- batch = Context::nbatch (diffsol-la/src/context/mod.rs:27) + per-instance parameters + all
+ * device state of the batched solver, resident on ONE GPU.  Not thread-safe; all work is enqueued on
+ * the stream given to the solve call; only the get_* / *_host calls synchronise. */
+typedef struct dsb_batch dsb_batch;
+int dsb_batch_new(const dsb_problem* p, int64_t nbatch, int32_t device, dsb_batch** out);
+int dsb_batch_free(dsb_batch* b);
+int64_t dsb_batch_size(const dsb_batch* b);
+
+/* Parameters, instance-major: params[b*nparams + j], exactly how the reference concatenates batched
+ * parameters (diffsol/src/ode_equations/test_models/exponential_decay.rs:297-304). */
+int dsb_batch_set_params_host(dsb_batch* b, const double* params, int64_t nbatch, int32_t nparams);
+int dsb_batch_set_params_device(dsb_batch* b, const double* params_dev, int64_t nbatch, int32_t nparams, void* stream);
+
+/* `problem.<method>::<LS>()?.solve_dense(t_eval)` for every instance (ode_solver/method.rs:467-505,
+ * 721-848; Bdf::step ode_solver/bdf.rs:1277-1589; Sdirk::step ode_solver/sdirk.rs:409-543).
+ * t_eval is a HOST array of nt increasing times shared by the batch; t_eval[nt-1] is the stop time.
+ * ys_dev: DEVICE buffer of nt*nstates*nbatch doubles, batch-major: ys[(k*nstates + i)*nbatch + b].
+ * Asynchronous on `stream` (a cudaStream_t, NULL = default stream). */
+int dsb_batch_solve_dense(dsb_batch* b, int32_t method, const double* t_eval, int32_t nt, double* ys_dev, void* stream);
+
+/* Same call with HOST buffers: copies parameters in, runs, copies results back, synchronises.
+ * ys_host layout is instance-major [nbatch][nt][nstates] (each instance's block is the column-major
+ * nstates x nt matrix `solve_dense` returns).  stats_host ([nbatch][DSB_NSTATS]) and status_host
+ * ([nbatch]) may be NULL. */
+int dsb_batch_solve_dense_host(dsb_batch* b, int32_t method, const double* params_host, int32_t nparams,
+                               const double* t_eval, int32_t nt,
+                               double* ys_host, int64_t* stats_host, int32_t* status_host);
+
+/* Per-instance results of the last solve (device -> host copy, synchronises). */
+int dsb_batch_get_stats(dsb_batch* b, int64_t* stats_host /* [nbatch][DSB_NSTATS] */);
+int dsb_batch_get_status(dsb_batch* b, int32_t* status_host /* [nbatch] */);
+int dsb_batch_get_final_state(dsb_batch* b, double* t_host, double* h_host, int32_t* order_host /* each [nbatch] or NULL */);
+/* Device views (valid until the next solve / free): stats [DSB_NSTATS][nbatch] int32, status [nbatch] int32. */
+int dsb_batch_device_views(dsb_batch* b, const int32_t** stats_dev, const int32_t** status_dev);
+
+/* Sum over the batch of one statistic of the last solve (device reduction; synchronises). */
+int dsb_batch_sum_stat(dsb_batch* b, int32_t stat, int64_t* total);
+
+/* Device time of the last solve's kernels in milliseconds (CUDA events on the solve's stream). */
+int dsb_batch_last_kernel_ms(dsb_batch* b, float* ms);
+/* Number of kernels this library launched for the last solve. */
+int dsb_batch_last_launch_count(dsb_batch* b, int32_t* launches);
+
+/* ---- the LinearSolver<M> pair a Rust `impl LinearSolver<BatchMat>` would call
+ * (diffsol-la/src/linear_solver/mod.rs:19-42; replaces NalgebraLU nalgebra/lu.rs:31-51 and the
+ * per-instance cuSOLVER loop of linear_solver/cuda/lu.rs:80-95,127-145).
+ * a_dev: nbatch column-major n x n matrices, batch-major: a[(j*n + i)*nbatch + b]; overwritten by LU.
+ * piv_dev: [n][nbatch] int32 row swaps (row i swapped with piv[i]); info_dev[b] != 0 => zero pivot. */
+int dsb_lu_factor_batched(double* a_dev, int32_t n, int64_t nbatch, int32_t* piv_dev, int32_t* info_dev, void* stream);
+int dsb_lu_solve_batched(const double* lu_dev, const int32_t* piv_dev, double* b_dev, int32_t n, int64_t nbatch,
+                         int32_t* info_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFSOL_B200_H */
