@@ -1,0 +1,65 @@
+// dsb_args.h -- plain-old-data blocks handed to the sm_100a kernels by value (constant bank).
+//
+// `DsbProblemArgs` is the device-side image of what `OdeBuilder::build()` returns in the reference
+// (crates/diffsol/src/ode_solver/builder.rs:112-140, problem.rs:98-193): tolerances, t0, h0, the
+// solver options, plus the order-dependent BDF constant tables (bdf.rs:253-276, 433-463) which the
+// host evaluates once with the same IEEE operations the oracle uses.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/diffsol_b200.h"
+
+#define DSB_MAX_STATES 64      // register/local-memory lane kernels; larger n uses the block-cooperative path
+#define DSB_MAX_ORDER 5        // bdf_state.rs:44
+#define DSB_NDIFF (DSB_MAX_ORDER + 3)
+#define DSB_LANE_THREADS 128   // block size of the one-thread-per-instance kernels
+
+// Lane-kernel statistics are int32 in device memory, one array per counter (batch-major).
+enum dsb_solver_state {        // ode_solver/jacobian_update.rs:3-10
+    DSB_STEP_SUCCESS = 0, DSB_FIRST_CONVERGENCE_FAIL = 1, DSB_SECOND_CONVERGENCE_FAIL = 2,
+    DSB_ERROR_TEST_FAIL = 3, DSB_CHECKPOINT = 4
+};
+
+struct DsbBdfTables {
+    double alpha[DSB_MAX_ORDER + 1];
+    double gamma[DSB_MAX_ORDER + 1];
+    double error_const2[DSB_MAX_ORDER + 1];
+    // U = R(order, 1) for order = 1..5, each (order+1)^2 column-major, compact (leading dimension order+1)
+    double u[DSB_MAX_ORDER + 1][36];
+    double eta_reset;              // 20^1.25   convergence.rs:36-38
+    double eta_reset_timestep;     // 100^1.25  convergence.rs:40-42
+    double ic_steptol;             // eps^(2/3) line_search.rs:126
+};
+
+struct DsbProblemArgs {
+    int64_t nbatch;
+    int32_t nt;
+    int32_t use_coloring;
+    int32_t free_running;      // 1: no stop time; step until t passes each point, then interpolate (the
+                               // `while t < t_k { step() }; interpolate(t_k)` loop of ode_solver/mod.rs:132-141)
+    int32_t reserved;
+    int32_t ncolors;
+    int32_t color_of_col[DSB_MAX_STATES];      // colour index of every column
+    uint64_t nz_rows_of_col[DSB_MAX_STATES];   // bit i set <=> (i, col) is in the sparsity pattern
+    double rtol;
+    double atol[DSB_MAX_STATES];
+    double t0, h0;
+    dsb_options opt;
+    DsbBdfTables tab;
+};
+
+// Device buffers of one batch, all batch-major (instance index fastest) so that a warp's 32 lanes
+// touch 32 consecutive doubles.
+struct DsbBatchBuffers {
+    const double* params;    // [np][B]
+    const double* t_eval;    // [nt]
+    double* y0;              // [n][B]   state after `new_and_consistent` (state.rs:969-997)
+    double* dy0;             // [n][B]
+    double* h0;              // [B]
+    double* ys;              // [nt][n][B]  solve_dense output
+    int32_t* stats;          // [DSB_NSTATS][B]
+    int32_t* status;         // [B]
+    double* fin_t;           // [B]
+    double* fin_h;           // [B]
+    int32_t* fin_order;      // [B]
+};

@@ -1,0 +1,579 @@
+// dsb_capi.cu -- the extern "C" boundary declared in include/diffsol_b200.h.
+//
+// Host side of the batched integrator: problem description (what `OdeBuilder::build()` collects,
+// crates/diffsol/src/ode_solver/builder.rs), device buffers of a batch, kernel launches, and the
+// host<->device copies of the `*_host` entry points.  There is NO CPU fallback: every solve runs
+// the sm_100a kernels; without a CUDA device the calls fail with DSB_ERR.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/diffsol_b200.h"
+#include "dsb_args.h"
+#include "dsb_launch.h"
+#include "dsb_lu_kernels.cuh"
+#include "dsb_models.h"
+
+// ---- thread-local last error (crates/diffsol-c/src/error_c.rs:12-46) -----------------------------------
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+#define DSB_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(DSB_ERR, std::string(#call) + ": " + cudaGetErrorString(e_));               \
+    } while (0)
+
+struct dsb_problem {
+    int model;
+    int n, np, has_mass;
+    double rtol;
+    std::vector<double> atol;
+    double t0, h0;
+    int use_coloring;
+    dsb_options opt;
+};
+
+struct dsb_batch {
+    dsb_problem prob;           // snapshot: the batch outlives edits of the problem
+    int64_t B;
+    int device;
+    double* params = nullptr;   // [np][B]
+    double* y0 = nullptr;
+    double* dy0 = nullptr;
+    double* h0 = nullptr;
+    double* fin_t = nullptr;
+    double* fin_h = nullptr;
+    int32_t* fin_order = nullptr;
+    int32_t* stats = nullptr;   // [DSB_NSTATS][B]
+    int32_t* status = nullptr;
+    double* t_eval = nullptr; int t_eval_cap = 0;
+    double* ys_own = nullptr; size_t ys_own_bytes = 0;       // used by the *_host entry point
+    void* stage = nullptr; size_t stage_bytes = 0;           // instance-major staging for host copies
+    cudaEvent_t ev0 = nullptr, ev_mid = nullptr, ev1 = nullptr;
+    int last_launches = 0;
+    bool have_timing = false;
+    int sparsity_probe_jac_muls = 0;
+};
+
+namespace {
+
+struct DimsOf {
+    int *n, *np, *hm;
+    template <class M> void operator()() { *n = M::N; *np = M::NP; *hm = M::HAS_MASS ? 1 : 0; }
+};
+
+// bdf.rs:253-276 (kappa, gamma, alpha, error_const2), bdf.rs:433-463 (U = R(order, 1)),
+// convergence.rs:36-42 (eta resets), line_search.rs:126 (steptol).  Host code of this file is compiled
+// with -ffp-contract=off so these are the same doubles the oracle computes.
+void build_tables(DsbBdfTables* tb) {
+    const double kappa[6] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
+    tb->alpha[0] = 0.0; tb->gamma[0] = 0.0; tb->error_const2[0] = 1.0;
+    for (int i = 1; i <= DSB_MAX_ORDER; ++i) {
+        const double i_t = (double)i;
+        const double one_over_i = 1.0 / i_t;
+        const double one_over_i_plus_one = 1.0 / (i_t + 1.0);
+        tb->gamma[i] = tb->gamma[i - 1] + one_over_i;
+        tb->alpha[i] = 1.0 / ((1.0 - kappa[i]) * tb->gamma[i]);
+        const double e = kappa[i] * tb->gamma[i] + one_over_i_plus_one;
+        tb->error_const2[i] = e * e;
+    }
+    std::memset(tb->u, 0, sizeof(tb->u));
+    for (int order = 1; order <= DSB_MAX_ORDER; ++order) {
+        const int nr = order + 1;
+        double* r = tb->u[order];
+        for (int j = 0; j < nr; ++j) r[j * nr] = 1.0;
+        for (int j = 1; j < nr; ++j) {
+            const double j_t = (double)j;
+            for (int i = 1; i < nr; ++i) {
+                const double i_t = (double)i;
+                const int idx = j * nr + i;
+                r[idx] = r[idx - 1] * (i_t - 1.0 - 1.0 * j_t) / i_t;
+            }
+        }
+    }
+    tb->eta_reset = dsb_pow(20.0, 1.25);
+    tb->eta_reset_timestep = dsb_pow(100.0, 1.25);
+    tb->ic_steptol = dsb_pow(std::numeric_limits<double>::epsilon(), 2.0 / 3.0);
+}
+
+// jacobian/mod.rs:16-48 (NaN probe), coloring.rs:27-47 (graph), greedy_coloring.rs:14-34.
+// The pattern is a property of the equations, not of the instance ("assume every batch has the same
+// non-zeros", jacobian/mod.rs:32), so it is found once on the host with the model's own functor.
+struct ColoringOf {
+    const dsb_problem* pr; DsbProblemArgs* pa; int* probes;
+    template <class M> void operator()() {
+        constexpr int N = M::N;
+        constexpr int NP = M::NP;
+        double p[NP > 0 ? NP : 1];
+        for (int j = 0; j < NP; ++j) p[j] = 1.0;
+        double y0[N], v[N], col[N];
+        M::init(p, pr->t0, y0);
+        std::vector<std::pair<int, int>> non_zeros;
+        for (int i = 0; i < N; ++i) { v[i] = 0.0; col[i] = 0.0; }
+        for (int j = 0; j < N; ++j) {
+            v[j] = std::numeric_limits<double>::quiet_NaN();
+            M::jac_mul(y0, p, pr->t0, v, col);
+            for (int i = 0; i < N; ++i) if (std::isnan(col[i])) non_zeros.push_back({i, j});
+            for (int i = 0; i < N; ++i) col[i] = 0.0;
+            v[j] = 0.0;
+        }
+        *probes = N;
+        std::vector<std::vector<int>> cols_by_rows(N), adj(N);
+        for (auto& ij : non_zeros) cols_by_rows[ij.first].push_back(ij.second);
+        for (auto& ij : non_zeros)
+            for (int next_col : cols_by_rows[ij.first])
+                if (next_col < ij.second) { adj[ij.second].push_back(next_col); adj[next_col].push_back(ij.second); }
+        std::vector<int> result(N, 0);
+        if (N > 0) result[0] = 1;
+        std::vector<char> available(N, 0);
+        for (int ii = 1; ii < N; ++ii) {
+            for (int j : adj[ii]) if (result[j] != 0) available[result[j] - 1] = 1;
+            for (int i = 0; i < N; ++i) if (!available[i]) { result[ii] = i + 1; break; }
+            std::fill(available.begin(), available.end(), 0);
+        }
+        int max_color = 0;
+        for (int c : result) if (c > max_color) max_color = c;
+        pa->ncolors = max_color;
+        for (int j = 0; j < N; ++j) { pa->color_of_col[j] = result[j] - 1; pa->nz_rows_of_col[j] = 0; }
+        for (auto& ij : non_zeros) pa->nz_rows_of_col[ij.second] |= (1ull << ij.first);
+    }
+};
+
+int fill_problem_args(const dsb_problem& pr, int64_t B, int nt, DsbProblemArgs* pa, int* probes) {
+    std::memset(pa, 0, sizeof(*pa));
+    pa->nbatch = B; pa->nt = nt;
+    pa->rtol = pr.rtol; pa->t0 = pr.t0; pa->h0 = pr.h0;
+    for (int i = 0; i < pr.n; ++i) pa->atol[i] = pr.atol.size() == 1 ? pr.atol[0] : pr.atol[i];
+    pa->opt = pr.opt;
+    build_tables(&pa->tab);
+    pa->use_coloring = pr.use_coloring;
+    *probes = 0;
+    if (pr.use_coloring) {
+        ColoringOf f{&pr, pa, probes};
+        if (!dsb_dispatch_model(pr.model, f)) return DSB_BAD_ARG;
+    }
+    return DSB_OK;
+}
+
+const dsb_launch_fn g_launch_table[DSB_MODEL_COUNT] = {
+    dsb_launch_model_0, dsb_launch_model_1, dsb_launch_model_2, dsb_launch_model_3,
+    dsb_launch_model_4, dsb_launch_model_5, dsb_launch_model_6, dsb_launch_model_7,
+};
+
+// instance-major <-> batch-major re-layout on the device (the host-facing layouts follow the
+// reference: parameters concatenated per instance, each instance's solve_dense block column-major)
+__global__ void dsb_to_batch_major_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t B, int m) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*m, dst index
+    if (idx >= B * m) return;
+    const int64_t j = idx / B, b = idx - j * B;
+    dst[idx] = src[b * m + j];
+}
+__global__ void dsb_to_instance_major_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t B, int m) {
+    __shared__ double tile[32][33];
+    // src [m][B] -> dst [B][m], 32x32 tiles through shared memory so both sides are coalesced
+    const int64_t b0 = (int64_t)blockIdx.x * 32;
+    const int j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int r = ty; r < 32; r += blockDim.y) {
+        const int j = j0 + r; const int64_t b = b0 + tx;
+        if (j < m && b < B) tile[r][tx] = src[(int64_t)j * B + b];
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += blockDim.y) {
+        const int64_t b = b0 + r; const int j = j0 + tx;
+        if (j < m && b < B) dst[b * m + j] = tile[tx][r];
+    }
+}
+__global__ void dsb_stats_to_host_layout_kernel(const int32_t* __restrict__ src, int64_t* __restrict__ dst, int64_t B,
+                                                int probe_jac_muls) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*DSB_NSTATS, dst index
+    if (idx >= B * DSB_NSTATS) return;
+    const int64_t b = idx / DSB_NSTATS; const int s = (int)(idx - b * DSB_NSTATS);
+    int64_t v = src[(int64_t)s * B + b];
+    if (s == DSB_STAT_RHS_JAC_MULS) v += probe_jac_muls;
+    dst[idx] = v;
+}
+__global__ void dsb_sum_stat_kernel(const int32_t* __restrict__ src, int64_t B, unsigned long long* out) {
+    unsigned long long acc = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x)
+        acc += (unsigned long long)src[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+int ensure_stage(dsb_batch* b, size_t bytes) {
+    if (b->stage_bytes >= bytes) return DSB_OK;
+    if (b->stage) cudaFree(b->stage);
+    b->stage = nullptr; b->stage_bytes = 0;
+    DSB_CUDA(cudaMalloc(&b->stage, bytes));
+    b->stage_bytes = bytes;
+    return DSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void dsb_options_default(dsb_options* o) {
+    std::memset(o, 0, sizeof(*o));
+    o->max_nonlinear_solver_iterations = 10;
+    o->max_error_test_failures = 40;
+    o->max_nonlinear_solver_failures = 50;
+    o->update_jacobian_after_steps = 20;
+    o->update_rhs_jacobian_after_steps = 50;
+    o->ic_max_linesearch_iterations = 10;
+    o->ic_max_newton_iterations = 10;
+    o->ic_max_linear_solver_setups = 4;
+    o->ic_use_linesearch = 1;
+    o->nonlinear_solver_tolerance = 0.2;
+    o->min_timestep = 1e-13;
+    o->max_timestep_growth = 2.0;
+    o->min_timestep_growth = 2.0;
+    o->max_timestep_shrink = 0.9;
+    o->min_timestep_shrink = 0.5;
+    o->threshold_to_update_jacobian = 0.3;
+    o->threshold_to_update_rhs_jacobian = 0.2;
+    o->pi_control_proportional = 0.0;
+    o->pi_control_integral = 0.5;
+    o->ic_step_reduction_factor = 0.5;
+    o->ic_armijo_constant = 1e-4;
+}
+
+const char* dsb_last_error(void) { return g_last_error.c_str(); }
+const char* dsb_version(void) { return "diffsol_b200 0.1 (sm_100a)"; }
+
+int dsb_device_count(int* count) {
+    if (!count) return fail(DSB_BAD_ARG, "count is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess || c == 0) {
+        *count = 0;
+        return fail(DSB_ERR, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    }
+    *count = c;
+    return DSB_OK;
+}
+
+int dsb_problem_new(int model, dsb_problem** out) {
+    if (!out) return fail(DSB_BAD_ARG, "out is NULL");
+    int n = 0, np = 0, hm = 0;
+    DimsOf f{&n, &np, &hm};
+    if (!dsb_dispatch_model(model, f)) return fail(DSB_BAD_ARG, "unknown model id");
+    dsb_problem* p = new (std::nothrow) dsb_problem();
+    if (!p) return fail(DSB_ERR, "out of memory");
+    p->model = model; p->n = n; p->np = np; p->has_mass = hm;
+    p->rtol = 1e-6; p->atol.assign(1, 1e-6); p->t0 = 0.0; p->h0 = 1.0; p->use_coloring = 0;   // builder.rs:112-140
+    dsb_options_default(&p->opt);
+    *out = p;
+    return DSB_OK;
+}
+int dsb_problem_free(dsb_problem* p) { delete p; return DSB_OK; }
+int dsb_problem_dims(const dsb_problem* p, int32_t* nstates, int32_t* nparams, int32_t* has_mass) {
+    if (!p) return fail(DSB_BAD_ARG, "problem is NULL");
+    if (nstates) *nstates = p->n;
+    if (nparams) *nparams = p->np;
+    if (has_mass) *has_mass = p->has_mass;
+    return DSB_OK;
+}
+int dsb_problem_set_rtol(dsb_problem* p, double rtol) {
+    if (!p || !(rtol > 0.0)) return fail(DSB_BAD_ARG, "rtol must be positive");
+    p->rtol = rtol; return DSB_OK;
+}
+int dsb_problem_set_atol(dsb_problem* p, const double* atol, int32_t n) {
+    if (!p || !atol || (n != 1 && n != p->n)) return fail(DSB_BAD_ARG, "atol must have 1 or nstates entries");
+    p->atol.assign(atol, atol + n); return DSB_OK;
+}
+int dsb_problem_set_t0(dsb_problem* p, double t0) { if (!p) return fail(DSB_BAD_ARG, "problem is NULL"); p->t0 = t0; return DSB_OK; }
+int dsb_problem_set_h0(dsb_problem* p, double h0) {
+    if (!p || h0 == 0.0) return fail(DSB_BAD_ARG, "h0 must be non-zero");
+    p->h0 = h0; return DSB_OK;
+}
+int dsb_problem_set_use_coloring(dsb_problem* p, int32_t use_coloring) {
+    if (!p) return fail(DSB_BAD_ARG, "problem is NULL");
+    p->use_coloring = use_coloring ? 1 : 0; return DSB_OK;
+}
+int dsb_problem_set_options(dsb_problem* p, const dsb_options* opt) {
+    if (!p || !opt) return fail(DSB_BAD_ARG, "NULL argument");
+    if (opt->max_nonlinear_solver_iterations < 1) return fail(DSB_BAD_ARG, "max_nonlinear_solver_iterations < 1");
+    p->opt = *opt; return DSB_OK;
+}
+int dsb_problem_get_options(const dsb_problem* p, dsb_options* opt) {
+    if (!p || !opt) return fail(DSB_BAD_ARG, "NULL argument");
+    *opt = p->opt; return DSB_OK;
+}
+
+int dsb_batch_new(const dsb_problem* p, int64_t nbatch, int32_t device, dsb_batch** out) {
+    if (!p || !out || nbatch < 1) return fail(DSB_BAD_ARG, "bad argument to dsb_batch_new");
+    if (nbatch > 0x7fffffffll * 64) return fail(DSB_BAD_ARG, "nbatch too large");
+    int count = 0;
+    if (dsb_device_count(&count) != DSB_OK) return DSB_ERR;
+    if (device < 0 || device >= count) return fail(DSB_BAD_ARG, "no such CUDA device");
+    DSB_CUDA(cudaSetDevice(device));
+    dsb_batch* b = new (std::nothrow) dsb_batch();
+    if (!b) return fail(DSB_ERR, "out of memory");
+    b->prob = *p; b->B = nbatch; b->device = device;
+    const size_t B = (size_t)nbatch, n = (size_t)p->n, np = (size_t)(p->np > 0 ? p->np : 1);
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes); };
+    alloc((void**)&b->params, np * B * 8);
+    alloc((void**)&b->y0, n * B * 8);
+    alloc((void**)&b->dy0, n * B * 8);
+    alloc((void**)&b->h0, B * 8);
+    alloc((void**)&b->fin_t, B * 8);
+    alloc((void**)&b->fin_h, B * 8);
+    alloc((void**)&b->fin_order, B * 4);
+    alloc((void**)&b->stats, (size_t)DSB_NSTATS * B * 4);
+    alloc((void**)&b->status, B * 4);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev_mid);
+    if (e != cudaSuccess) {
+        dsb_batch_free(b);
+        return fail(DSB_ERR, std::string("dsb_batch_new: ") + cudaGetErrorString(e));
+    }
+    cudaMemset(b->params, 0, np * B * 8);
+    cudaMemset(b->stats, 0, (size_t)DSB_NSTATS * B * 4);
+    cudaMemset(b->status, 0, B * 4);
+    *out = b;
+    return DSB_OK;
+}
+
+int dsb_batch_free(dsb_batch* b) {
+    if (!b) return DSB_OK;
+    cudaSetDevice(b->device);
+    cudaFree(b->params); cudaFree(b->y0); cudaFree(b->dy0); cudaFree(b->h0);
+    cudaFree(b->fin_t); cudaFree(b->fin_h); cudaFree(b->fin_order);
+    cudaFree(b->stats); cudaFree(b->status); cudaFree(b->t_eval); cudaFree(b->ys_own); cudaFree(b->stage);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->ev_mid) cudaEventDestroy(b->ev_mid);
+    delete b;
+    return DSB_OK;
+}
+int64_t dsb_batch_size(const dsb_batch* b) { return b ? b->B : 0; }
+
+int dsb_batch_set_params_device(dsb_batch* b, const double* params_dev, int64_t nbatch, int32_t nparams, void* stream) {
+    if (!b || nbatch != b->B || nparams != b->prob.np) return fail(DSB_BAD_ARG, "parameter shape mismatch");
+    if (nparams == 0) return DSB_OK;
+    if (!params_dev) return fail(DSB_BAD_ARG, "params is NULL");
+    DSB_CUDA(cudaSetDevice(b->device));
+    const int64_t total = nbatch * nparams;
+    dsb_to_batch_major_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params_dev, b->params, nbatch, nparams);
+    DSB_CUDA(cudaGetLastError());
+    return DSB_OK;
+}
+
+int dsb_batch_set_params_host(dsb_batch* b, const double* params, int64_t nbatch, int32_t nparams) {
+    if (!b || nbatch != b->B || nparams != b->prob.np) return fail(DSB_BAD_ARG, "parameter shape mismatch");
+    if (nparams == 0) return DSB_OK;
+    if (!params) return fail(DSB_BAD_ARG, "params is NULL");
+    DSB_CUDA(cudaSetDevice(b->device));
+    const size_t bytes = (size_t)nbatch * nparams * 8;
+    if (ensure_stage(b, bytes) != DSB_OK) return DSB_ERR;
+    DSB_CUDA(cudaMemcpyAsync(b->stage, params, bytes, cudaMemcpyHostToDevice, 0));
+    int rc = dsb_batch_set_params_device(b, (const double*)b->stage, nbatch, nparams, nullptr);
+    if (rc != DSB_OK) return rc;
+    DSB_CUDA(cudaStreamSynchronize(0));
+    return DSB_OK;
+}
+
+static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_t nt, double* ys_dev, void* stream_,
+                      int free_running) {
+    if (!b || !t_eval || nt < 1 || !ys_dev) return fail(DSB_BAD_ARG, "bad argument to dsb_batch_solve_dense");
+    if (method != DSB_METHOD_BDF && method != DSB_METHOD_TR_BDF2 && method != DSB_METHOD_ESDIRK34)
+        return fail(DSB_BAD_ARG, "unknown method");
+    if (method != DSB_METHOD_BDF) return fail(DSB_ERR, "SDIRK kernels are not built into this library yet");
+    for (int k = 1; k < nt; ++k)
+        if (!(t_eval[k] >= t_eval[k - 1])) return fail(DSB_BAD_ARG, "t_eval must be increasing");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DSB_CUDA(cudaSetDevice(b->device));
+    if (b->t_eval_cap < nt) {
+        cudaFree(b->t_eval); b->t_eval = nullptr; b->t_eval_cap = 0;
+        DSB_CUDA(cudaMalloc((void**)&b->t_eval, (size_t)nt * 8));
+        b->t_eval_cap = nt;
+    }
+    DSB_CUDA(cudaMemcpyAsync(b->t_eval, t_eval, (size_t)nt * 8, cudaMemcpyHostToDevice, stream));
+    DsbProblemArgs pa;
+    int probes = 0;
+    if (fill_problem_args(b->prob, b->B, nt, &pa, &probes) != DSB_OK) return fail(DSB_BAD_ARG, "unknown model id");
+    b->sparsity_probe_jac_muls = probes;
+    pa.free_running = free_running;
+    DsbBatchBuffers bb;
+    bb.params = b->params; bb.t_eval = b->t_eval; bb.y0 = b->y0; bb.dy0 = b->dy0; bb.h0 = b->h0;
+    bb.ys = ys_dev; bb.stats = b->stats; bb.status = b->status;
+    bb.fin_t = b->fin_t; bb.fin_h = b->fin_h; bb.fin_order = b->fin_order;
+    // outputs never reached stay NaN (all-ones bit pattern)
+    DSB_CUDA(cudaMemsetAsync(ys_dev, 0xFF, (size_t)nt * b->prob.n * b->B * 8, stream));
+    b->last_launches = 0;
+    DSB_CUDA(cudaEventRecord(b->ev0, stream));
+    if (b->prob.model < 0 || b->prob.model >= DSB_MODEL_COUNT) return fail(DSB_BAD_ARG, "unknown model id");
+    cudaError_t lerr = g_launch_table[b->prob.model](&pa, &bb, method, stream, b->ev_mid, &b->last_launches);
+    if (lerr != cudaSuccess) return fail(DSB_ERR, std::string("kernel launch: ") + cudaGetErrorString(lerr));
+    DSB_CUDA(cudaEventRecord(b->ev1, stream));
+    b->have_timing = true;
+    return DSB_OK;
+}
+
+int dsb_batch_solve_dense(dsb_batch* b, int32_t method, const double* t_eval, int32_t nt, double* ys_dev, void* stream) {
+    return solve_impl(b, method, t_eval, nt, ys_dev, stream, 0);
+}
+int dsb_batch_step_and_interpolate(dsb_batch* b, int32_t method, const double* t_points, int32_t npts, double* ys_dev,
+                                   void* stream) {
+    return solve_impl(b, method, t_points, npts, ys_dev, stream, 1);
+}
+
+int dsb_batch_get_stats_device(dsb_batch* b, int64_t* stats_dev, void* stream) {
+    if (!b || !stats_dev) return fail(DSB_BAD_ARG, "NULL argument");
+    const int64_t total = b->B * DSB_NSTATS;
+    dsb_stats_to_host_layout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        b->stats, stats_dev, b->B, b->sparsity_probe_jac_muls);
+    DSB_CUDA(cudaGetLastError());
+    return DSB_OK;
+}
+
+int dsb_batch_get_stats(dsb_batch* b, int64_t* stats_host) {
+    if (!b || !stats_host) return fail(DSB_BAD_ARG, "NULL argument");
+    DSB_CUDA(cudaSetDevice(b->device));
+    const size_t bytes = (size_t)b->B * DSB_NSTATS * 8;
+    if (ensure_stage(b, bytes) != DSB_OK) return DSB_ERR;
+    DSB_CUDA(cudaDeviceSynchronize());
+    if (dsb_batch_get_stats_device(b, (int64_t*)b->stage, nullptr) != DSB_OK) return DSB_ERR;
+    DSB_CUDA(cudaMemcpy(stats_host, b->stage, bytes, cudaMemcpyDeviceToHost));
+    return DSB_OK;
+}
+int dsb_batch_get_status(dsb_batch* b, int32_t* status_host) {
+    if (!b || !status_host) return fail(DSB_BAD_ARG, "NULL argument");
+    DSB_CUDA(cudaSetDevice(b->device));
+    DSB_CUDA(cudaDeviceSynchronize());
+    DSB_CUDA(cudaMemcpy(status_host, b->status, (size_t)b->B * 4, cudaMemcpyDeviceToHost));
+    return DSB_OK;
+}
+int dsb_batch_get_final_state(dsb_batch* b, double* t_host, double* h_host, int32_t* order_host) {
+    if (!b) return fail(DSB_BAD_ARG, "NULL argument");
+    DSB_CUDA(cudaSetDevice(b->device));
+    DSB_CUDA(cudaDeviceSynchronize());
+    if (t_host) DSB_CUDA(cudaMemcpy(t_host, b->fin_t, (size_t)b->B * 8, cudaMemcpyDeviceToHost));
+    if (h_host) DSB_CUDA(cudaMemcpy(h_host, b->fin_h, (size_t)b->B * 8, cudaMemcpyDeviceToHost));
+    if (order_host) DSB_CUDA(cudaMemcpy(order_host, b->fin_order, (size_t)b->B * 4, cudaMemcpyDeviceToHost));
+    return DSB_OK;
+}
+int dsb_batch_device_views(dsb_batch* b, const int32_t** stats_dev, const int32_t** status_dev) {
+    if (!b) return fail(DSB_BAD_ARG, "NULL argument");
+    if (stats_dev) *stats_dev = b->stats;
+    if (status_dev) *status_dev = b->status;
+    return DSB_OK;
+}
+
+int dsb_batch_sum_stat(dsb_batch* b, int32_t stat, int64_t* total) {
+    if (!b || !total || stat < 0 || stat >= DSB_NSTATS) return fail(DSB_BAD_ARG, "bad argument");
+    DSB_CUDA(cudaSetDevice(b->device));
+    if (ensure_stage(b, 8) != DSB_OK) return DSB_ERR;
+    DSB_CUDA(cudaDeviceSynchronize());
+    DSB_CUDA(cudaMemset(b->stage, 0, 8));
+    dsb_sum_stat_kernel<<<296, 256>>>(b->stats + (size_t)stat * b->B, b->B, (unsigned long long*)b->stage);
+    DSB_CUDA(cudaGetLastError());
+    unsigned long long v = 0;
+    DSB_CUDA(cudaMemcpy(&v, b->stage, 8, cudaMemcpyDeviceToHost));
+    if (stat == DSB_STAT_RHS_JAC_MULS) v += (unsigned long long)b->sparsity_probe_jac_muls * (unsigned long long)b->B;
+    *total = (int64_t)v;
+    return DSB_OK;
+}
+
+int dsb_batch_last_kernel_ms(dsb_batch* b, float* ms) {
+    if (!b || !ms || !b->have_timing) return fail(DSB_BAD_ARG, "no solve has been timed");
+    DSB_CUDA(cudaSetDevice(b->device));
+    DSB_CUDA(cudaEventSynchronize(b->ev1));
+    DSB_CUDA(cudaEventElapsedTime(ms, b->ev0, b->ev1));
+    return DSB_OK;
+}
+int dsb_batch_last_integrator_ms(dsb_batch* b, float* ms) {
+    if (!b || !ms || !b->have_timing) return fail(DSB_BAD_ARG, "no solve has been timed");
+    DSB_CUDA(cudaSetDevice(b->device));
+    DSB_CUDA(cudaEventSynchronize(b->ev1));
+    DSB_CUDA(cudaEventElapsedTime(ms, b->ev_mid, b->ev1));
+    return DSB_OK;
+}
+int dsb_batch_last_launch_count(dsb_batch* b, int32_t* launches) {
+    if (!b || !launches) return fail(DSB_BAD_ARG, "NULL argument");
+    *launches = b->last_launches;
+    return DSB_OK;
+}
+
+static int solve_host_impl(dsb_batch* b, int32_t method, const double* params_host, int32_t nparams,
+                           const double* t_eval, int32_t nt, double* ys_host, int64_t* stats_host,
+                           int32_t* status_host, int free_running) {
+    if (!b || !ys_host) return fail(DSB_BAD_ARG, "NULL argument");
+    DSB_CUDA(cudaSetDevice(b->device));
+    const int n = b->prob.n;
+    const size_t ys_bytes = (size_t)nt * n * b->B * 8;
+    size_t stage_need = ys_bytes;
+    if ((size_t)b->B * DSB_NSTATS * 8 > stage_need) stage_need = (size_t)b->B * DSB_NSTATS * 8;
+    if ((size_t)b->B * (nparams > 0 ? nparams : 1) * 8 > stage_need) stage_need = (size_t)b->B * nparams * 8;
+    if (ensure_stage(b, stage_need) != DSB_OK) return DSB_ERR;
+    if (b->ys_own_bytes < ys_bytes) {
+        cudaFree(b->ys_own); b->ys_own = nullptr; b->ys_own_bytes = 0;
+        DSB_CUDA(cudaMalloc((void**)&b->ys_own, ys_bytes));
+        b->ys_own_bytes = ys_bytes;
+    }
+    int extra = 0;
+    if (nparams > 0) {
+        if (!params_host || nparams != b->prob.np) return fail(DSB_BAD_ARG, "parameter shape mismatch");
+        DSB_CUDA(cudaMemcpyAsync(b->stage, params_host, (size_t)b->B * nparams * 8, cudaMemcpyHostToDevice, 0));
+        int rc = dsb_batch_set_params_device(b, (const double*)b->stage, b->B, nparams, nullptr);
+        if (rc != DSB_OK) return rc;
+        ++extra;
+    }
+    int rc = solve_impl(b, method, t_eval, nt, b->ys_own, nullptr, free_running);
+    if (rc != DSB_OK) return rc;
+    {
+        const int m = nt * n;
+        dim3 grid((unsigned)((b->B + 31) / 32), (unsigned)((m + 31) / 32)), block(32, 8);
+        dsb_to_instance_major_kernel<<<grid, block>>>(b->ys_own, (double*)b->stage, b->B, m);
+        DSB_CUDA(cudaGetLastError());
+        ++extra;
+        DSB_CUDA(cudaMemcpyAsync(ys_host, b->stage, ys_bytes, cudaMemcpyDeviceToHost, 0));
+    }
+    if (stats_host) {
+        if (dsb_batch_get_stats_device(b, (int64_t*)b->stage, nullptr) != DSB_OK) return DSB_ERR;
+        ++extra;
+        DSB_CUDA(cudaMemcpyAsync(stats_host, b->stage, (size_t)b->B * DSB_NSTATS * 8, cudaMemcpyDeviceToHost, 0));
+    }
+    if (status_host) DSB_CUDA(cudaMemcpyAsync(status_host, b->status, (size_t)b->B * 4, cudaMemcpyDeviceToHost, 0));
+    DSB_CUDA(cudaStreamSynchronize(0));
+    b->last_launches += extra;
+    return DSB_OK;
+}
+
+int dsb_batch_solve_dense_host(dsb_batch* b, int32_t method, const double* params_host, int32_t nparams,
+                               const double* t_eval, int32_t nt, double* ys_host, int64_t* stats_host,
+                               int32_t* status_host) {
+    return solve_host_impl(b, method, params_host, nparams, t_eval, nt, ys_host, stats_host, status_host, 0);
+}
+int dsb_batch_step_and_interpolate_host(dsb_batch* b, int32_t method, const double* params_host, int32_t nparams,
+                                        const double* t_points, int32_t npts, double* ys_host, int64_t* stats_host,
+                                        int32_t* status_host) {
+    return solve_host_impl(b, method, params_host, nparams, t_points, npts, ys_host, stats_host, status_host, 1);
+}
+
+int dsb_lu_factor_batched(double* a_dev, int32_t n, int64_t nbatch, int32_t* piv_dev, int32_t* info_dev, void* stream) {
+    if (!a_dev || !piv_dev || !info_dev || n < 1 || nbatch < 1) return fail(DSB_BAD_ARG, "bad argument to dsb_lu_factor_batched");
+    cudaError_t e = dsb_launch_lu_factor(a_dev, n, nbatch, piv_dev, info_dev, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(DSB_ERR, std::string("dsb_lu_factor_batched: ") + cudaGetErrorString(e));
+    return DSB_OK;
+}
+int dsb_lu_solve_batched(const double* lu_dev, const int32_t* piv_dev, double* b_dev, int32_t n, int64_t nbatch,
+                         int32_t* info_dev, void* stream) {
+    if (!lu_dev || !piv_dev || !b_dev || !info_dev || n < 1 || nbatch < 1) return fail(DSB_BAD_ARG, "bad argument to dsb_lu_solve_batched");
+    cudaError_t e = dsb_launch_lu_solve(lu_dev, piv_dev, b_dev, n, nbatch, info_dev, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(DSB_ERR, std::string("dsb_lu_solve_batched: ") + cudaGetErrorString(e));
+    return DSB_OK;
+}
+
+}  // extern "C"

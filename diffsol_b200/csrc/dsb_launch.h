@@ -1,0 +1,16 @@
+// dsb_launch.h -- one launcher per built-in equation set; each lives in its own translation unit
+// (dsb_inst.cu compiled with -DDSB_INST=<model id>) so the heavily unrolled lane kernels build in parallel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "dsb_args.h"
+
+// `mid` (may be NULL) is recorded between the initialisation kernel and the integrator kernel so the
+// integrator's own duration can be read back.
+typedef cudaError_t (*dsb_launch_fn)(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method,
+                                     cudaStream_t stream, cudaEvent_t mid, int* launches);
+
+#define DSB_DECLARE_LAUNCH(id) cudaError_t dsb_launch_model_##id(const DsbProblemArgs*, const DsbBatchBuffers*, int, cudaStream_t, cudaEvent_t, int*);
+DSB_DECLARE_LAUNCH(0) DSB_DECLARE_LAUNCH(1) DSB_DECLARE_LAUNCH(2) DSB_DECLARE_LAUNCH(3)
+DSB_DECLARE_LAUNCH(4) DSB_DECLARE_LAUNCH(5) DSB_DECLARE_LAUNCH(6) DSB_DECLARE_LAUNCH(7)
+#undef DSB_DECLARE_LAUNCH

@@ -19,7 +19,7 @@
 
 #if defined(__CUDACC__)
 #define DSB_HD __host__ __device__ __forceinline__
-#define DSB_HD_NOINLINE __host__ __device__ __noinline__
+#define DSB_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define DSB_HD inline
 #define DSB_HD_NOINLINE inline

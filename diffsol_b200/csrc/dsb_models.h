@@ -182,6 +182,17 @@ struct ModelVanDerPol {
     }
 };
 
+// id -> functor type
+template <int ID> struct dsb_model_by_id;
+template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY> { typedef ModelExpDecay type; };
+template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY_ALGEBRAIC> { typedef ModelExpDecayAlgebraic type; };
+template <> struct dsb_model_by_id<DSB_MODEL_ROBERTSON_DAE> { typedef ModelRobertsonDae type; };
+template <> struct dsb_model_by_id<DSB_MODEL_ROBERTSON_ODE> { typedef ModelRobertsonOde<1> type; };
+template <> struct dsb_model_by_id<DSB_MODEL_ROBERTSON_ODE_G3> { typedef ModelRobertsonOde<3> type; };
+template <> struct dsb_model_by_id<DSB_MODEL_DYDT_Y2> { typedef ModelDydtY2<10> type; };
+template <> struct dsb_model_by_id<DSB_MODEL_GAUSSIAN_DECAY> { typedef ModelGaussianDecay<10> type; };
+template <> struct dsb_model_by_id<DSB_MODEL_VAN_DER_POL> { typedef ModelVanDerPol type; };
+
 // Compile-time dispatch over the registry: calls f.template operator()<Model>() for `id`.
 template <class F>
 inline bool dsb_dispatch_model(int id, F&& f) {

@@ -1,0 +1,247 @@
+"""Host-side mirror of the reference interface for the batched implicit path.
+
+Names and argument meaning follow diffsol (paths relative to /root/reference/crates/diffsol/src):
+
+    OdeBuilder().p(...).rtol(..).atol(..).t0(..).h0(..).use_coloring(..)      ode_solver/builder.rs:1447-1626
+        .rhs_implicit(model).nbatch(B).build()          -> OdeSolverProblem    ode_solver/problem.rs:98-193
+    problem.bdf() / problem.tr_bdf2() / problem.esdirk34() -> solver           ode_solver/problem.rs:320-328,649-655
+    solver.solve_dense(t_eval) -> ys                                           ode_solver/method.rs:467-505
+    solver.get_statistics()                                                    ode_solver/mod.rs:27-69
+
+Differences that the batch imposes: the equations are one of the library's device functors (a Rust
+closure or a DiffSL CPU JIT module cannot run inside a kernel; `rhs_implicit` takes the functor's
+name), `p` is [nbatch, nparams] (instance-major, as the reference concatenates batched parameters,
+test_models/exponential_decay.rs:297-304), results carry a leading batch axis, and an instance that
+fails does not raise: it gets a per-instance status (the variant name of the reference's error enum)
+and NaN outputs past the failure.
+"""
+import ctypes
+
+import numpy as np
+
+from . import capi
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class OdeSolverProblem:
+    def __init__(self, handle, model, n, nparams, has_mass, nbatch, params, device):
+        self._h = handle
+        self.model = model
+        self.nstates, self.nparams, self.has_mass = n, nparams, has_mass
+        self.nbatch = nbatch
+        self.p = params
+        self.device = device
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            capi.lib().dsb_problem_free(self._h)
+            self._h = None
+
+    def _solver(self, method):
+        return BatchedSolver(self, method)
+
+    def bdf(self):
+        return self._solver("bdf")
+
+    def tr_bdf2(self):
+        return self._solver("tr_bdf2")
+
+    def esdirk34(self):
+        return self._solver("esdirk34")
+
+
+class OdeBuilder:
+    """Fluent builder; defaults are the reference's (builder.rs:112-140): t0=0, h0=1, rtol=1e-6, atol=[1e-6]."""
+
+    def __init__(self):
+        self._model = None
+        self._p = None
+        self._rtol, self._atol, self._t0, self._h0 = 1e-6, [1e-6], 0.0, 1.0
+        self._coloring = False
+        self._nbatch = None
+        self._device = 0
+        self._opts = {}
+
+    def rhs_implicit(self, model):
+        if model not in capi.MODELS:
+            raise ValueError("unknown equation set %r; available: %s" % (model, sorted(capi.MODELS)))
+        self._model = model
+        return self
+
+    def p(self, p):
+        self._p = np.asarray(p, dtype=np.float64)
+        return self
+
+    def rtol(self, v):
+        self._rtol = float(v); return self
+
+    def atol(self, v):
+        self._atol = [float(x) for x in np.atleast_1d(v)]; return self
+
+    def t0(self, v):
+        self._t0 = float(v); return self
+
+    def h0(self, v):
+        self._h0 = float(v); return self
+
+    def use_coloring(self, v):
+        self._coloring = bool(v); return self
+
+    def nbatch(self, b):
+        self._nbatch = int(b); return self
+
+    def device(self, d):
+        self._device = int(d); return self
+
+    def ode_options(self, **kw):
+        """Fields of OdeSolverOptions / BdfConfig / SdirkConfig / InitialConditionSolverOptions by name."""
+        self._opts.update(kw); return self
+
+    def build(self):
+        if self._model is None:
+            raise ValueError("rhs_implicit(model) is required")
+        L = capi.lib()
+        h = ctypes.c_void_p()
+        capi.check(L.dsb_problem_new(capi.MODELS[self._model], ctypes.byref(h)))
+        n, npar, hm = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        capi.check(L.dsb_problem_dims(h, ctypes.byref(n), ctypes.byref(npar), ctypes.byref(hm)))
+        try:
+            capi.check(L.dsb_problem_set_rtol(h, self._rtol))
+            atol = np.asarray(self._atol, dtype=np.float64)
+            capi.check(L.dsb_problem_set_atol(h, _ptr(atol), len(atol)))
+            capi.check(L.dsb_problem_set_t0(h, self._t0))
+            capi.check(L.dsb_problem_set_h0(h, self._h0))
+            capi.check(L.dsb_problem_set_use_coloring(h, int(self._coloring)))
+            if self._opts:
+                o = capi.Options()
+                capi.check(L.dsb_problem_get_options(h, ctypes.byref(o)))
+                for k, v in self._opts.items():
+                    if not hasattr(o, k):
+                        raise ValueError("unknown option %r" % k)
+                    setattr(o, k, v)
+                capi.check(L.dsb_problem_set_options(h, ctypes.byref(o)))
+            p = self._p if self._p is not None else np.zeros((0,))
+            if npar.value == 0:
+                nb = self._nbatch or 1
+                p = np.zeros((nb, 0))
+            else:
+                p = np.ascontiguousarray(p, dtype=np.float64)
+                if p.ndim == 1:
+                    if p.size != npar.value:
+                        raise ValueError("p has %d entries, the equations take %d" % (p.size, npar.value))
+                    p = np.tile(p, (self._nbatch or 1, 1))
+                if p.ndim != 2 or p.shape[1] != npar.value:
+                    raise ValueError("p must be [nbatch, %d]" % npar.value)
+                if self._nbatch is not None and p.shape[0] != self._nbatch:
+                    raise ValueError("p has %d rows, nbatch is %d" % (p.shape[0], self._nbatch))
+        except Exception:
+            L.dsb_problem_free(h)
+            raise
+        return OdeSolverProblem(h, self._model, n.value, npar.value, bool(hm.value), p.shape[0],
+                                np.ascontiguousarray(p), self._device)
+
+
+class BatchedSolver:
+    """`problem.<method>::<LS>()` over the batch; owns the device state (dsb_batch)."""
+
+    def __init__(self, problem, method):
+        self.problem = problem
+        self.method = capi.METHODS[method]
+        capi.require_device()
+        L = capi.lib()
+        b = ctypes.c_void_p()
+        capi.check(L.dsb_batch_new(problem._h, problem.nbatch, problem.device, ctypes.byref(b)))
+        self._b = b
+        self._stats = None
+        self._status = None
+
+    def __del__(self):
+        if getattr(self, "_b", None):
+            capi.lib().dsb_batch_free(self._b)
+            self._b = None
+
+    def step_and_interpolate(self, t_points):
+        """The stepping loop of the reference's tests (ode_solver/mod.rs:132-141), no stop time:
+        for each point: while |t| < |t_k|: step(); then interpolate(t_k).  -> ys[nbatch, npts, nstates]."""
+        return self._solve_host(t_points, "dsb_batch_step_and_interpolate_host")
+
+    def solve_dense(self, t_eval):
+        """-> ys[nbatch, nt, nstates] (host).  Per-instance statistics/status via get_statistics()/status()."""
+        return self._solve_host(t_eval, "dsb_batch_solve_dense_host")
+
+    def _solve_host(self, t_eval, entry):
+        pr = self.problem
+        t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
+        nt = len(t_eval)
+        ys = np.empty((pr.nbatch, nt, pr.nstates))
+        stats = np.empty((pr.nbatch, capi.DSB_NSTATS), dtype=np.int64)
+        status = np.empty(pr.nbatch, dtype=np.int32)
+        capi.check(getattr(capi.lib(), entry)(
+            self._b, self.method, _ptr(pr.p) if pr.nparams else None, pr.nparams, _ptr(t_eval), nt,
+            _ptr(ys), _ptr(stats), _ptr(status)))
+        self._stats, self._status = stats, status
+        return ys
+
+    def solve_dense_device(self, t_eval, ys_dev_ptr, stream=None, params_dev_ptr=None):
+        """Device-resident variant: ys_dev_ptr -> [nt][nstates][nbatch] doubles (batch-major), asynchronous."""
+        pr = self.problem
+        L = capi.lib()
+        if params_dev_ptr is not None:
+            capi.check(L.dsb_batch_set_params_device(self._b, ctypes.c_void_p(params_dev_ptr), pr.nbatch, pr.nparams,
+                                                     ctypes.c_void_p(stream or 0)))
+        t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
+        capi.check(L.dsb_batch_solve_dense(self._b, self.method, _ptr(t_eval), len(t_eval),
+                                           ctypes.c_void_p(ys_dev_ptr), ctypes.c_void_p(stream or 0)))
+        self._stats = self._status = None
+
+    def set_params(self):
+        pr = self.problem
+        if pr.nparams:
+            capi.check(capi.lib().dsb_batch_set_params_host(self._b, _ptr(pr.p), pr.nbatch, pr.nparams))
+
+    def statistics_array(self):
+        if self._stats is None:
+            s = np.empty((self.problem.nbatch, capi.DSB_NSTATS), dtype=np.int64)
+            capi.check(capi.lib().dsb_batch_get_stats(self._b, _ptr(s)))
+            self._stats = s
+        return self._stats
+
+    def get_statistics(self, b=0):
+        s = self.statistics_array()[b]
+        return {name: int(s[i]) for i, name in enumerate(capi.STAT_NAMES)}
+
+    def status(self):
+        if self._status is None:
+            s = np.empty(self.problem.nbatch, dtype=np.int32)
+            capi.check(capi.lib().dsb_batch_get_status(self._b, _ptr(s)))
+            self._status = s
+        return self._status
+
+    def final_state(self):
+        B = self.problem.nbatch
+        t, h, o = np.empty(B), np.empty(B), np.empty(B, dtype=np.int32)
+        capi.check(capi.lib().dsb_batch_get_final_state(self._b, _ptr(t), _ptr(h), _ptr(o)))
+        return t, h, o
+
+    def sum_statistic(self, name):
+        tot = ctypes.c_int64()
+        capi.check(capi.lib().dsb_batch_sum_stat(self._b, capi.STAT_NAMES.index(name), ctypes.byref(tot)))
+        return tot.value
+
+    def last_kernel_ms(self):
+        ms = ctypes.c_float()
+        capi.check(capi.lib().dsb_batch_last_kernel_ms(self._b, ctypes.byref(ms)))
+        return ms.value
+
+    def last_integrator_ms(self):
+        ms = ctypes.c_float()
+        capi.check(capi.lib().dsb_batch_last_integrator_ms(self._b, ctypes.byref(ms)))
+        return ms.value
+
+    def last_launch_count(self):
+        n = ctypes.c_int32()
+        capi.check(capi.lib().dsb_batch_last_launch_count(self._b, ctypes.byref(n)))
+        return n.value

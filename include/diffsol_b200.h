@@ -116,6 +116,7 @@ int dsb_problem_set_rtol(dsb_problem* p, double rtol);                      /* O
 int dsb_problem_set_atol(dsb_problem* p, const double* atol, int32_t n);    /* OdeBuilder::atol; n == 1 broadcasts */
 int dsb_problem_set_t0(dsb_problem* p, double t0);                          /* OdeBuilder::t0 */
 int dsb_problem_set_h0(dsb_problem* p, double h0);                          /* OdeBuilder::h0 */
+int dsb_problem_set_use_coloring(dsb_problem* p, int32_t use_coloring);      /* OdeBuilder::use_coloring  builder.rs:1852-1857 */
 int dsb_problem_set_options(dsb_problem* p, const dsb_options* opt);        /* OdeBuilder::ode_options / ic_options */
 int dsb_problem_get_options(const dsb_problem* p, dsb_options* opt);
 
@@ -139,6 +140,12 @@ int dsb_batch_set_params_device(dsb_batch* b, const double* params_dev, int64_t 
  * Asynchronous on `stream` (a cudaStream_t, NULL = default stream). */
 int dsb_batch_solve_dense(dsb_batch* b, int32_t method, const double* t_eval, int32_t nt, double* ys_dev, void* stream);
 
+/* The user-level stepping loop of the reference's own tests (ode_solver/mod.rs:132-141), for every instance:
+ *   for each k: while |solver.state().t| < |t_points[k]| { solver.step()? }; ys[k] = solver.interpolate(t_points[k])?
+ * i.e. OdeSolverMethod::step (method.rs:99) + interpolate (method.rs:106) with NO stop time.  Same
+ * layouts as dsb_batch_solve_dense.  This is the call that reproduces the reference's statistics snapshots. */
+int dsb_batch_step_and_interpolate(dsb_batch* b, int32_t method, const double* t_points, int32_t npts, double* ys_dev, void* stream);
+
 /* Same call with HOST buffers: copies parameters in, runs, copies results back, synchronises.
  * ys_host layout is instance-major [nbatch][nt][nstates] (each instance's block is the column-major
  * nstates x nt matrix `solve_dense` returns).  stats_host ([nbatch][DSB_NSTATS]) and status_host
@@ -147,9 +154,15 @@ int dsb_batch_solve_dense_host(dsb_batch* b, int32_t method, const double* param
                                const double* t_eval, int32_t nt,
                                double* ys_host, int64_t* stats_host, int32_t* status_host);
 
+int dsb_batch_step_and_interpolate_host(dsb_batch* b, int32_t method, const double* params_host, int32_t nparams,
+                                        const double* t_points, int32_t npts,
+                                        double* ys_host, int64_t* stats_host, int32_t* status_host);
+
 /* Per-instance results of the last solve (device -> host copy, synchronises). */
 int dsb_batch_get_stats(dsb_batch* b, int64_t* stats_host /* [nbatch][DSB_NSTATS] */);
 int dsb_batch_get_status(dsb_batch* b, int32_t* status_host /* [nbatch] */);
+/* The same statistics written to a DEVICE buffer [nbatch][DSB_NSTATS] int64, asynchronously on `stream`. */
+int dsb_batch_get_stats_device(dsb_batch* b, int64_t* stats_dev, void* stream);
 int dsb_batch_get_final_state(dsb_batch* b, double* t_host, double* h_host, int32_t* order_host /* each [nbatch] or NULL */);
 /* Device views (valid until the next solve / free): stats [DSB_NSTATS][nbatch] int32, status [nbatch] int32. */
 int dsb_batch_device_views(dsb_batch* b, const int32_t** stats_dev, const int32_t** status_dev);
@@ -159,6 +172,8 @@ int dsb_batch_sum_stat(dsb_batch* b, int32_t stat, int64_t* total);
 
 /* Device time of the last solve's kernels in milliseconds (CUDA events on the solve's stream). */
 int dsb_batch_last_kernel_ms(dsb_batch* b, float* ms);
+/* Device time of the integrator kernel alone (without the initialisation kernel). */
+int dsb_batch_last_integrator_ms(dsb_batch* b, float* ms);
 /* Number of kernels this library launched for the last solve. */
 int dsb_batch_last_launch_count(dsb_batch* b, int32_t* launches);
 
