@@ -1,14 +1,40 @@
-// dsb_bdf_kernel.cuh -- `problem.bdf::<LS>()?.solve_dense(t_eval)` for every instance of a batch,
-// one CUDA thread per instance, the whole integration inside one kernel.
+// dsb_bdf_kernel.cuh -- `problem.bdf::<LS>()?.solve_dense(t_eval)` for every instance of a batch.
 //
-// Restates (paths relative to /root/reference/crates/diffsol/src):
+// Execution model (B200-first, not the reference's): one CUDA thread ("lane") integrates one instance
+// at a time, with its OWN step size, order, Newton state and counters.  The reference's nested loops
+// (step -> retry loop -> Newton loop) are flattened into a per-lane STATE MACHINE whose blocks each
+// appear exactly once in the kernel:
+//
+//     FETCH -> JAC(construct) -> TSTOP(first) -> PREDICT -> NEWTON* -> POST -> [SELECT] -> [RESCALE -> JAC]
+//           -> TSTOP -> OUTPUT -> PREDICT -> ...                  \-> (retry) JAC / RESCALE -> PREDICT
+//
+// In the loop body the rarely needed blocks come first and POST last, so that a lane flows
+// [SELECT -> RESCALE -> JAC ->] TSTOP -> OUTPUT -> PREDICT -> NEWTON -> POST in ONE trip and the blocks
+// every trip needs are contiguous in the instruction cache.
+//
+// so that (a) the 32 lanes of a warp, which are at different points of their own integrations, still
+// execute the hot block (one Newton iteration) together instead of serialising whole retry loops,
+// (b) the code stays small enough for the instruction cache (the nested-loop version inlined the
+// rescale / refactor blocks at every call site: 13 k SASS instructions, 70 % of issue slots stalled on
+// instruction fetch, ncu profiles/r1_v1_*), and (c) a lane that finishes its instance fetches the next
+// one from a global work counter, so a warp never waits for its slowest instance.
+//
+// Storage: Newton work vectors and controller scalars in registers; the difference array D (n x 8),
+// df/dy, M (DAEs), the LU factors, state.y, the predictor and the parameters in shared memory, one
+// column per thread (word w of thread t at smem[w * blockDim + t]: conflict-free, indexable by the
+// run-time order).  Global memory is touched only to fetch an instance and to write its outputs.
+//
+// Arithmetic: every floating-point expression keeps the operation order of the reference's CPU path so
+// that a build with --fmad=false reproduces its controller decisions bit for bit (checked against the
+// oracle in tests/).  Restated functions (paths relative to /root/reference/crates/diffsol/src):
 //   Bdf::_new                    ode_solver/bdf.rs:230-368
 //   Bdf::step                    ode_solver/bdf.rs:1277-1589   (retry loop, order/step selection)
 //   _predict_forward / set_psi   ode_solver/bdf.rs:667-692, op/bdf.rs:182-210
 //   BdfCallable::call_inplace    op/bdf.rs:240-256             F(y) = M (y - y0 + psi) - c f(y)
 //   BdfCallable::jacobian_inplace op/bdf.rs:273-300            A = M - c J
 //   newton_iteration + NoLineSearch  crates/diffsol-nl/src/newton.rs:13-36, line_search.rs:48-69
-//   _jacobian_updates            ode_solver/bdf.rs:465-506
+//   Convergence                  crates/diffsol-nl/src/convergence.rs:64-139
+//   _jacobian_updates            ode_solver/bdf.rs:465-506, jacobian_update.rs
 //   _update_step_size, _compute_r ode_solver/bdf.rs:433-463, 508-577
 //   _update_diff                 ode_solver/bdf.rs:646-664
 //   error_control, predict_error_control   ode_solver/bdf.rs:812-932
@@ -16,456 +42,584 @@
 //   handle_tstop, set_stop_time  ode_solver/bdf.rs:694-731, 1591-1599
 //   interpolate                  ode_solver/bdf.rs:767-782, 1080-1106
 //   fn solve_dense               ode_solver/method.rs:721-848
-// Every instance keeps its own h / order / Newton state / counters: the result for instance b is
-// what the reference's CPU path returns for that instance alone (SURVEY.md section 3.6 quirks
-// Q1-Q8 included).  LU, the Newton work vectors and all controller scalars are registers; the
-// difference array D (n x 8) and df/dy (and M for DAEs), which are only touched between Newton
-// solves, live in shared memory as one column per thread (word index * blockDim + tid: conflict-free),
-// which also lets them be indexed by the run-time order.
 #pragma once
 #include "dsb_lane.cuh"
 
+enum dsb_lane_state {
+    L_FETCH = 0, L_POST, L_SELECT, L_RESCALE, L_JAC, L_TSTOP, L_OUTPUT, L_PREDICT, L_NEWTON, L_FINISH, L_IDLE
+};
+#define DSB_KIND_CONSTRUCT 5      // Bdf::_new's reset_jacobian (counted as a checkpoint setup, bdf.rs:351-359)
+
 template <class M>
-struct BdfLane {
-    static constexpr int N = M::N;
-    static constexpr int NP = M::NP;
+struct BdfLayout {
+    static constexpr int N = M::N, NP = M::NP;
+    static constexpr int O_D = 0;                                   // D[DSB_NDIFF][N]
+    static constexpr int O_J = O_D + DSB_NDIFF * N;                 // rhs_jac[col][row]
+    static constexpr int O_M = O_J + N * N;                         // mass_jac[col][row] (DAE only)
+    static constexpr int O_LU = O_M + (M::HAS_MASS ? N * N : 0);    // LU factors [col][row]
+    static constexpr int O_Y = O_LU + N * N;                        // state.y
+    static constexpr int O_YP = O_Y + N;                            // y_predict
+    static constexpr int O_P = O_YP + N;                            // parameters
+    static constexpr int WORDS = O_P + (NP > 0 ? NP : 1);
+    // threads per block: the per-thread column must leave room for >= 2 blocks per SM (227 KB)
+    static constexpr int THREADS = (WORDS * 8 * 128 <= 75 * 1024) ? 128 : (WORDS * 8 * 64 <= 110 * 1024) ? 64 : 32;
+};
 
-    const DsbProblemArgs& pa;
-    double p[NP > 0 ? NP : 1];
-    // shared-memory column of this thread: D[j][i] at (j*N + i), then rhs_jac[j][i], then mass_jac[j][i]
-    double* sm;
-    static constexpr int SM_D = 0, SM_J = DSB_NDIFF * N, SM_M = SM_J + N * N;
-    static constexpr int SM_WORDS = SM_M + (M::HAS_MASS ? N * N : 0);
-    DSB_DEV double& D(int j, int i) { return sm[(SM_D + j * N + i) * DSB_LANE_THREADS]; }
-    DSB_DEV const double& D(int j, int i) const { return sm[(SM_D + j * N + i) * DSB_LANE_THREADS]; }
-    DSB_DEV double& Jm(int j, int i) { return sm[(SM_J + j * N + i) * DSB_LANE_THREADS]; }
-    DSB_DEV double& Mm(int j, int i) { return sm[(SM_M + j * N + i) * DSB_LANE_THREADS]; }
-    // BdfState
-    int order;
-    double y[N];
-    double t, h;
-    // Bdf
+template <class M>
+__global__ void __launch_bounds__(BdfLayout<M>::THREADS) dsb_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa,
+                                                                              const __grid_constant__ DsbBatchBuffers bb,
+                                                                              unsigned long long* __restrict__ work_counter) {
+    constexpr int N = M::N;
+    constexpr int NP = M::NP;
+    static_assert(N <= 16, "pivots are packed 4 bits per row");
+    typedef BdfLayout<M> Lay;
+    extern __shared__ double dsb_lane_smem[];
+    double* const sm = dsb_lane_smem + threadIdx.x;
+#define SM(w) sm[(w) * Lay::THREADS]
+#define SD(j, i) SM(Lay::O_D + (j) * N + (i))
+#define SJ(j, i) SM(Lay::O_J + (j) * N + (i))
+#define SMM(j, i) SM(Lay::O_M + (j) * N + (i))
+#define SLU(j, i) SM(Lay::O_LU + (j) * N + (i))
+#define SY(i) SM(Lay::O_Y + (i))
+#define SYP(i) SM(Lay::O_YP + (i))
+#define SP(i) SM(Lay::O_P + (i))
+
+    const int64_t B = pa.nbatch;
+    const int nt = pa.nt;
+    const bool free_running = pa.free_running != 0;
+    const int quorum = pa.quorum;
+    const double eps = 2.220446049250313e-16;
+
+    // ---- per-lane registers -----------------------------------------------------------------------
+    int state = L_FETCH;
+    int64_t inst = 0;
+    // BdfState / Bdf scalars
+    int order = 1, n_equal_steps = 0;
+    double t = 0.0, h = 0.0, c = 0.0, t_predict = 0.0;
+    bool has_tstop = false, has_prev_error = false, jacobian_is_stale = true;
+    double tstop = 0.0, prev_error_norm = 0.0;
+    LaneJacobianUpdate ju; ju.init(1.0);
     LaneConvergence conv;
-    LaneLU<N> lu;
-    int n_equal_steps;
-    double y_delta[N], y_predict[N];
-    double t_predict;
-    LaneStats st;
-    bool has_tstop; double tstop;
-    LaneJacobianUpdate ju;
-    bool has_prev_error; double prev_error_norm;
-    // BdfCallable
-    double psi_neg_y0[N];
-    double c;
-    bool jacobian_is_stale;
+    conv.tol = pa.opt.nonlinear_solver_tolerance; conv.max_iter = pa.opt.max_nonlinear_solver_iterations;
+    conv.eta = pa.tab.eta_reset; conv.old_norm = 0.0; conv.reset();
+    LaneStats st; st.clear();
+    unsigned long long piv_packed = 0;         // 4 bits per row
+    // Newton work vectors
+    double y_cur[N], psi_neg_y0[N], wt[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { y_cur[i] = 0.0; psi_neg_y0[i] = 0.0; wt[i] = 1.0; }
+    // step()-local state
+    bool convergence_fail = false, newton_ok = false, first = true, reached = false, accepted = false;
+    bool repredict = true, pending_etf = false, rs_ignore_small = false;
+    int old_num_error_test_failures = 0, col = 0;
+    double safety = 0.0, error_norm = 0.0;
+    // pending control transfers
+    int after_rescale = L_JAC, after_jac = L_TSTOP, jac_kind = DSB_CHECKPOINT;
+    double rescale_factor = 1.0;
 
-    DSB_DEV BdfLane(const DsbProblemArgs& a, double* sm_) : pa(a), sm(sm_) {}
-
-    DSB_DEV void set_c(double hh, double a) { c = hh * a; }
-
-    DSB_DEV void reset_jacobian(const double (&x)[N], double tt) {
-        if (jacobian_is_stale) {
-            // the fresh Jacobian goes through lu.a (about to be overwritten anyway) on its way to shared memory
-            lane_jacobian<M>(pa, x, p, tt, lu.a, st);
-#pragma unroll
-            for (int j = 0; j < N; ++j)
-#pragma unroll
-                for (int i = 0; i < N; ++i) Jm(j, i) = lu.a[j][i];
-            if (M::HAS_MASS) {
-                lane_mass_matrix<M>(p, tt, lu.a);
-#pragma unroll
-                for (int j = 0; j < N; ++j)
-#pragma unroll
-                    for (int i = 0; i < N; ++i) Mm(j, i) = lu.a[j][i];
-            }
-            jacobian_is_stale = false;
-        }
-        const double mc = -c;
-#pragma unroll
-        for (int j = 0; j < N; ++j)
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                // identity mass when the model has none (op/bdf.rs:141-143)
-                const double m_ji = M::HAS_MASS ? Mm(j, i) : ((i == j) ? 1.0 : 0.0);
-                lu.a[j][i] = Jm(j, i) * mc + m_ji;
-            }
-        lu.factor();
-    }
-
-    DSB_DEV void jacobian_updates(double cc, int state) {
-        bool did_update = false;
-        if (ju.check_rhs_jacobian_update(pa.opt, cc, state)) {
-            jacobian_is_stale = true;
-            reset_jacobian(y, t);
-            ju.update_rhs_jacobian(cc);
-            ju.update_jacobian(cc);
-            conv.eta = pa.tab.eta_reset;
-            did_update = true;
-        } else if (ju.check_jacobian_update(pa.opt, cc, state)) {
-            reset_jacobian(y, t);
-            ju.update_jacobian(cc);
-            conv.eta = pa.tab.eta_reset;
-            did_update = true;
-        }
-        if (did_update) st.record_linear_solver_setup(state);
-    }
-
-    // D[:, 0..=K] <- D[:, 0..=K] * (R(K, factor) * U(K)).  Every product is accumulated in the order of
-    // nalgebra's gemm (first term assigned, the rest added one by one: bdf.rs:521, 568-577), but R and
-    // RU are produced one ROW at a time and folded into the new columns at once, so that only
-    // 2 (K+1) coefficients are live instead of 2 (K+1)^2.
-    template <int K>
-    DSB_DEV void rescale_diff(double factor) {
-        constexpr int NR = K + 1;
-        const double* u = pa.tab.u[K];     // U = R(K, 1), column-major, leading dimension NR
-        double rrow[NR];                   // R[i, l] for the current row i
-        double nd[NR][N];
-#pragma unroll
-        for (int l = 0; l < NR; ++l) rrow[l] = 1.0;
-#pragma unroll
-        for (int i = 0; i < NR; ++i) {
-            if (i > 0) {
-                const double i_t = (double)i;
-                rrow[0] = 0.0;
-#pragma unroll
-                for (int l = 1; l < NR; ++l) rrow[l] = rrow[l] * (i_t - 1.0 - factor * (double)l) / i_t;
-            }
-#pragma unroll
-            for (int j = 0; j < NR; ++j) {
-                double ru_ij = rrow[0] * u[j * NR + 0];          // RU[i, j] = sum_l R[i, l] U[l, j]
-#pragma unroll
-                for (int l = 1; l < NR; ++l) ru_ij = rrow[l] * u[j * NR + l] + ru_ij;
-#pragma unroll
-                for (int s = 0; s < N; ++s) {
-                    if (i == 0) nd[j][s] = D(i, s) * ru_ij;
-                    else nd[j][s] = D(i, s) * ru_ij + nd[j][s];
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < NR; ++j)
-#pragma unroll
-            for (int s = 0; s < N; ++s) D(j, s) = nd[j][s];
-    }
-
-    DSB_DEV int update_step_size(double factor, double* new_h_out) {
-        const double new_h = factor * h;
-        n_equal_steps = 0;
-        switch (order) {
-            case 1: rescale_diff<1>(factor); break;
-            case 2: rescale_diff<2>(factor); break;
-            case 3: rescale_diff<3>(factor); break;
-            case 4: rescale_diff<4>(factor); break;
-            default: rescale_diff<5>(factor); break;
-        }
-        set_c(new_h, pa.tab.alpha[order]);
-        h = new_h;
-        conv.eta = pa.tab.eta_reset_timestep;
-        if (new_h_out) *new_h_out = new_h;
-        if (dsb_abs(h) < pa.opt.min_timestep) return DSB_STATUS_STEP_SIZE_TOO_SMALL;
-        return DSB_STATUS_OK;
-    }
-
-    DSB_DEV void update_diff(int ord, const double (&d)[N]) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            D(ord + 2, i) = d[i] - D(ord + 1, i);
-            D(ord + 1, i) = d[i];
-        }
-        for (int j = ord; j >= 0; --j) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) D(j, i) = D(j, i) + 1.0 * D(j + 1, i);
-        }
-    }
-
-    DSB_DEV void predict_forward() {
-#pragma unroll
-        for (int i = 0; i < N; ++i) y_predict[i] = 0.0;
-        for (int j = 0; j <= order; ++j) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) y_predict[i] += D(j, i);
-        }
-#pragma unroll
-        for (int i = 0; i < N; ++i) psi_neg_y0[i] = pa.tab.gamma[1] * D(1, i);
-        for (int j = 2; j <= order; ++j) {
-            const double g = pa.tab.gamma[j];
-#pragma unroll
-            for (int i = 0; i < N; ++i) psi_neg_y0[i] = g * D(j, i) + psi_neg_y0[i];
-        }
-        const double a = pa.tab.alpha[order];
-#pragma unroll
-        for (int i = 0; i < N; ++i) psi_neg_y0[i] *= a;
-#pragma unroll
-        for (int i = 0; i < N; ++i) psi_neg_y0[i] -= y_predict[i];
-        t_predict = t + h;
-    }
-
-    DSB_DEV void callable(const double (&x)[N], double tt, double (&out)[N]) {
-        M::rhs(x, p, tt, out);
-        st.v[DSB_STAT_RHS_CALLS] += 1;
-        double tmp[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) tmp[i] = x[i] + psi_neg_y0[i];
-        const double mc = -c;
-        if (M::HAS_MASS) {
-            M::mass(tmp, p, tt, mc, out);
-        } else {
-#pragma unroll
-            for (int i = 0; i < N; ++i) out[i] = tmp[i] + mc * out[i];
-        }
-    }
-
-    DSB_DEV bool newton_solve(double (&xn)[N], double tt, const double (&error_y)[N]) {
-        conv.reset();
-        for (int it = 0; it < conv.max_iter; ++it) {
-            double delta[N];
-            callable(xn, tt, delta);
-            if (!lu.solve(delta)) return false;
-#pragma unroll
-            for (int i = 0; i < N; ++i) xn[i] -= delta[i];
-            const double norm = dsb_sqrt(lane_squared_norm<N>(delta, error_y, pa.atol, pa.rtol));
-            const int s = conv.check_new_iteration(norm);
-            if (s == LANE_CONVERGED) return true;
-            if (s == LANE_DIVERGED) return false;
-        }
-        return false;
-    }
-
-    // 0 = nothing, 1 = TstopReached, < 0 = -status
-    DSB_DEV int handle_tstop(double ts) {
-        const double troundoff = 100.0 * 2.220446049250313e-16 * (dsb_abs(t) + dsb_abs(h));
+    int fin_status = DSB_STATUS_OK;
+    auto finish = [&](int status) { fin_status = status; state = L_FINISH; };
+    // bdf.rs:694-731.  0 = nothing, 1 = TstopReached, 2 = step size must be clipped (rescale_factor set), < 0 = -status
+    auto handle_tstop = [&](double ts) -> int {
+        const double troundoff = 100.0 * eps * (dsb_abs(t) + dsb_abs(h));
         if (dsb_abs(t - ts) <= troundoff) { has_tstop = false; return 1; }
         if ((h > 0.0 && ts < t - troundoff) || (h < 0.0 && ts > t + troundoff)) {
             has_tstop = false;
             return -DSB_STATUS_STOP_TIME_BEFORE_CURRENT;
         }
         if ((h > 0.0 && t + h > ts + troundoff) || (h < 0.0 && t + h < ts - troundoff)) {
-            const double factor = (ts - t) / h;
-            (void)update_step_size(factor, nullptr);
+            rescale_factor = (ts - t) / h;
+            return 2;
         }
         return 0;
-    }
-
-    DSB_DEV double error_control() const {
-        const double err = lane_squared_norm<N>(y_delta, y, pa.atol, pa.rtol) * pa.tab.error_const2[order - 1];
-        return (0.0 < err) ? err : 0.0;
-    }
-    // squared norm of D[:, ord + 1] scaled by error_const2[ord]
-    DSB_DEV double predict_error_control(int ord) const {
-        double col[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) col[i] = D(ord + 1, i);
-        const double err = lane_squared_norm<N>(col, y, pa.atol, pa.rtol) * pa.tab.error_const2[ord];
-        return (0.0 < err) ? err : 0.0;
-    }
-    DSB_DEV double pi_controller_raw(double error_norm, int eff_order) const {
+    };
+    // runge_kutta.rs:1313-1335
+    auto pi_controller_raw = [&](double err, int eff_order) -> double {
         const double order_f = (double)eff_order;
         const double ki = pa.opt.pi_control_integral / order_f;
-        if (pa.opt.pi_control_proportional == 0.0 || !has_prev_error) return dsb_pow(error_norm, -ki);
-        const double kp = pa.opt.pi_control_proportional / order_f;
-        return dsb_pow(error_norm, -(ki + kp)) * dsb_pow(prev_error_norm, kp);
-    }
-
-    // Bdf::_new from the state the init kernel produced
-    DSB_DEV void construct(const double (&y_init)[N], const double (&dy_init)[N], double h_init) {
-        order = 1;
-        t = pa.t0; h = h_init;
-        conv.tol = pa.opt.nonlinear_solver_tolerance;
-        conv.max_iter = pa.opt.max_nonlinear_solver_iterations;
-        conv.eta = pa.tab.eta_reset;
-        conv.reset();
-        conv.old_norm = 0.0;
+        const bool p_only = pa.opt.pi_control_proportional == 0.0 || !has_prev_error;
+        const double kp = p_only ? 0.0 : pa.opt.pi_control_proportional / order_f;
+        double v = dsb_pow(err, p_only ? -ki : -(ki + kp));
+        if (!p_only) v = v * dsb_pow(prev_error_norm, kp);
+        return v;
+    };
+    // ||D[:, j]||^2_w(state.y) (vector/nalgebra_serial.rs:395-408)
+    auto diff_col_norm = [&](int j) -> double {
+        double acc = 0.0;
 #pragma unroll
-        for (int i = 0; i < N; ++i) { y[i] = y_init[i]; psi_neg_y0[i] = 0.0; y_delta[i] = 0.0; y_predict[i] = 0.0; }
-        jacobian_is_stale = true;
-        set_c(h, pa.tab.alpha[order]);
-        reset_jacobian(y, t);
-#pragma unroll
-        for (int j = 0; j < DSB_NDIFF; ++j)
-#pragma unroll
-            for (int i = 0; i < N; ++i) D(j, i) = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) { D(0, i) = y[i]; D(1, i) = dy_init[i] * h; }
-        st.v[DSB_STAT_LINEAR_SOLVER_SETUPS] += 1;
-        st.v[DSB_STAT_SETUPS_FROM_CHECKPOINT] += 1;
-        ju.init(1.0);                 // jacobian_update.rs:27 -- h_at_last starts at ONE
-        n_equal_steps = 0;
-        has_tstop = false; tstop = 0.0;
-        has_prev_error = false; prev_error_norm = 0.0;
-        t_predict = t;
-    }
-
-    // returns 0 = InternalTimestep, 1 = TstopReached, < 0 = -status
-    DSB_DEV int step() {
-        double safety = 0.0, error_norm = 0.0;
-        const int old_num_error_test_failures = st.v[DSB_STAT_ERROR_TEST_FAILURES];
-        bool convergence_fail = false;
-        double new_h = 0.0;
-        predict_forward();
-        while (true) {
-            const int ord = order;
-#pragma unroll
-            for (int i = 0; i < N; ++i) y_delta[i] = y_predict[i];
-            const bool ok = newton_solve(y_delta, t_predict, y_predict);
-            st.v[DSB_STAT_NONLINEAR_SOLVER_ITERATIONS] += conv.niter;
-            if (ok) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) y_delta[i] -= y_predict[i];
-            } else {
-                st.v[DSB_STAT_NONLINEAR_SOLVER_FAILS] += 1;
-                if (st.v[DSB_STAT_NONLINEAR_SOLVER_FAILS] > pa.opt.max_nonlinear_solver_failures)
-                    return -DSB_STATUS_TOO_MANY_NONLINEAR_FAILURES;
-                if (convergence_fail) {
-                    has_prev_error = false;
-                    const int e = update_step_size(0.3, &new_h);
-                    if (e) return -e;
-                    jacobian_updates(new_h * pa.tab.alpha[ord], DSB_SECOND_CONVERGENCE_FAIL);
-                    predict_forward();
-                } else {
-                    has_prev_error = false;
-                    jacobian_updates(h * pa.tab.alpha[ord], DSB_FIRST_CONVERGENCE_FAIL);
-                    convergence_fail = true;
-                }
-                continue;
-            }
-            error_norm = error_control();
-            const double maxiter = (double)conv.max_iter;
-            const double niter = (double)conv.niter;
-            safety = 0.9 * (2.0 * maxiter + 1.0) / (2.0 * maxiter + niter);
-            if (error_norm <= 1.0) break;
-            double factor = safety * pi_controller_raw(error_norm, ord + 1);
-            has_prev_error = false;
-            if (factor < pa.opt.min_timestep_shrink) factor = pa.opt.min_timestep_shrink;
-            const int e = update_step_size(factor, &new_h);
-            if (e) return -e;
-            jacobian_updates(new_h * pa.tab.alpha[ord], DSB_ERROR_TEST_FAIL);
-            predict_forward();
-            st.v[DSB_STAT_ERROR_TEST_FAILURES] += 1;
-            if (st.v[DSB_STAT_ERROR_TEST_FAILURES] - old_num_error_test_failures >= pa.opt.max_error_test_failures)
-                return -DSB_STATUS_TOO_MANY_ERROR_TEST_FAILURES;
+        for (int i = 0; i < N; ++i) {
+            const double term = SD(j, i) / (dsb_abs(SY(i)) * pa.rtol + pa.atol[i]);
+            acc += term * term;
         }
-        // accepted
-        update_diff(order, y_delta);
+        return acc / (double)N;
+    };
+
+    while (true) {
+        // ---- warp-level block scheduler ---------------------------------------------------------------
+        // The lanes of a warp are in different states.  The blocks every lane passes through once per
+        // Newton iteration or step (POST, TSTOP, OUTPUT, PREDICT, NEWTON) run whenever a lane needs them;
+        // a lane flows through all of them within one trip of this loop.  The heavy blocks only a few lanes
+        // need at a time (SELECT: order/step selection with its three pow()s; RESCALE + JAC: step-size
+        // change and refactorisation) would run with a handful of active lanes on every trip, so a lane
+        // that needs one WAITS until pa.quorum lanes (or half of the active ones) want the same group.
+        // Waiting never changes a lane's arithmetic, only when it runs.
+        const unsigned m_idle = __ballot_sync(0xffffffffu, state == L_IDLE);
+        if (m_idle == 0xffffffffu) break;
+        const int n_active = 32 - __popc(m_idle);
+        const int n_select = __popc(__ballot_sync(0xffffffffu, state == L_SELECT));
+        const int n_setup = __popc(__ballot_sync(0xffffffffu, state == L_RESCALE || state == L_JAC));
+        const bool none_running = (n_select + n_setup) == n_active;
+        const bool run_select = n_select > 0 && (n_select >= quorum || 2 * n_select >= n_active || none_running);
+        const bool run_setup = n_setup > 0 && (n_setup >= quorum || 2 * n_setup >= n_active || none_running);
+
+        // ================= FINISH: write the instance's results, then fetch the next one =====================
+        if (__any_sync(0xffffffffu, state == L_FINISH) && state == L_FINISH) {
+            bb.status[inst] = fin_status;
+            bb.fin_t[inst] = t; bb.fin_h[inst] = h; bb.fin_order[inst] = order;
 #pragma unroll
-        for (int i = 0; i < N; ++i) y[i] = y_predict[i];        // Q1: the PREDICTOR
-        t = t_predict;
-        st.v[DSB_STAT_STEPS] += 1;
-        ju.step();
-        has_prev_error = true; prev_error_norm = error_norm;
-        n_equal_steps += 1;
-        if (n_equal_steps > order) {
+            for (int k = 0; k < DSB_NSTATS; ++k) bb.stats[(int64_t)k * B + inst] = st.v[k];
+            state = L_FETCH;
+        }
+        // ================= FETCH: next instance from the work counter; Bdf::_new part 1 ==================
+        if (__any_sync(0xffffffffu, state == L_FETCH) && state == L_FETCH) {
+            inst = (int64_t)atomicAdd(work_counter, 1ull);
+            if (inst >= B) {
+                state = L_IDLE;
+            } else if (bb.status[inst] == DSB_STATUS_OK) {      // else: initialisation failed, keep its status
+#pragma unroll
+                for (int j = 0; j < NP; ++j) SP(j) = bb.params[(int64_t)j * B + inst];
+#pragma unroll
+                for (int k = 0; k < DSB_NSTATS; ++k) st.v[k] = bb.stats[(int64_t)k * B + inst];
+                order = 1; n_equal_steps = 0;
+                t = pa.t0; h = bb.h0[inst];
+                conv.eta = pa.tab.eta_reset; conv.old_norm = 0.0; conv.reset();
+#pragma unroll
+                for (int j = 0; j < DSB_NDIFF; ++j)
+#pragma unroll
+                    for (int i = 0; i < N; ++i) SD(j, i) = 0.0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double yi = bb.y0[(int64_t)i * B + inst];
+                    SY(i) = yi; SD(0, i) = yi; SD(1, i) = bb.dy0[(int64_t)i * B + inst] * h;
+                }
+                c = h * pa.tab.alpha[1];
+                jacobian_is_stale = true;
+                ju.init(1.0);                                   // jacobian_update.rs:27 -- h_at_last starts at ONE
+                has_tstop = false; tstop = 0.0; has_prev_error = false; prev_error_norm = 0.0;
+                convergence_fail = false; first = true; reached = false; pending_etf = false; col = 0;
+                t_predict = t;
+                jac_kind = DSB_KIND_CONSTRUCT;
+                state = L_JAC;
+            }
+        }
+        // ================= SELECT: order / step-size selection after an accepted step (bdf.rs:1489-1563), ==
+        // or the shrink factor after a failed error test (bdf.rs:1431-1442).  Every pow() of the controller
+        // is issued from ONE call site inside a rolled loop so that the lanes of the warp share it.
+        if (run_select && state == L_SELECT) {
             const int ord = order;
             const double inf = dsb_from_bits(0x7ff0000000000000ULL);
-            const double error_m_norm = ord > 1 ? predict_error_control(ord - 1) : inf;
-            const double error_p_norm = ord < DSB_MAX_ORDER ? predict_error_control(ord + 1) : inf;
-            const double f0 = pi_controller_raw(error_m_norm, ord);
-            const double f1 = pi_controller_raw(error_norm, ord + 1);
-            const double f2 = pi_controller_raw(error_p_norm, ord + 2);
-            // Iterator::max_by keeps the LAST maximum
-            int max_index = 0;
-            double fmax = f0;
-            if (!(fmax > f1)) { max_index = 1; fmax = f1; }
-            if (!(fmax > f2)) { max_index = 2; fmax = f2; }
-            const int new_order = ord + (max_index - 1);
-            order = new_order;
-            double factor = safety * fmax;
-            if (factor > pa.opt.max_timestep_growth) factor = pa.opt.max_timestep_growth;
-            if (factor < pa.opt.min_timestep_shrink) factor = pa.opt.min_timestep_shrink;
-            if (factor >= pa.opt.min_timestep_growth || factor <= pa.opt.max_timestep_shrink
-                || max_index == 0 || max_index == 2) {
-                const int e = update_step_size(factor, &new_h);
-                if (e) return -e;
-                jacobian_updates(new_h * pa.tab.alpha[new_order], DSB_STEP_SUCCESS);
+            double e0 = inf, e2 = inf;
+            if (accepted) {
+                if (ord > 1) {
+                    const double e = diff_col_norm(ord) * pa.tab.error_const2[ord - 1];
+                    e0 = (0.0 < e) ? e : 0.0;
+                }
+                if (ord < DSB_MAX_ORDER) {
+                    const double e = diff_col_norm(ord + 2) * pa.tab.error_const2[ord + 1];
+                    e2 = (0.0 < e) ? e : 0.0;
+                }
+            }
+            double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+#pragma unroll 1
+            for (int q = 0; q < 3; ++q) {
+                if (accepted || q == 1) {
+                    const double err = (q == 0) ? e0 : (q == 1) ? error_norm : e2;
+                    const double v = pi_controller_raw(err, ord + q);
+                    if (q == 0) f0 = v; else if (q == 1) f1 = v; else f2 = v;
+                }
+            }
+            if (accepted) {
+                int max_index = 0;                      // Iterator::max_by keeps the LAST maximum
+                double fmax = f0;
+                if (!(fmax > f1)) { max_index = 1; fmax = f1; }
+                if (!(fmax > f2)) { max_index = 2; fmax = f2; }
+                order = ord + (max_index - 1);
+                double factor = safety * fmax;
+                if (factor > pa.opt.max_timestep_growth) factor = pa.opt.max_timestep_growth;
+                if (factor < pa.opt.min_timestep_shrink) factor = pa.opt.min_timestep_shrink;
+                state = L_TSTOP;
+                if (factor >= pa.opt.min_timestep_growth || factor <= pa.opt.max_timestep_shrink || max_index != 1) {
+                    rescale_factor = factor; rs_ignore_small = false;
+                    state = L_RESCALE; after_rescale = L_JAC;
+                    jac_kind = DSB_STEP_SUCCESS; after_jac = L_TSTOP;
+                }
+            } else {
+                double factor = safety * f1;
+                has_prev_error = false;
+                if (factor < pa.opt.min_timestep_shrink) factor = pa.opt.min_timestep_shrink;
+                rescale_factor = factor; rs_ignore_small = false;
+                state = L_RESCALE; after_rescale = L_JAC;
+                jac_kind = DSB_ERROR_TEST_FAIL; after_jac = L_PREDICT;
+                repredict = true; pending_etf = true;
             }
         }
-        if (has_tstop) {
-            const int r = handle_tstop(tstop);
-            if (r == 1) return 1;
-            if (r < 0) return r;
+
+        // ================= RESCALE: _update_step_size(factor) (bdf.rs:508-577) ============================
+        // D[:, 0..=k] <- D[:, 0..=k] * (R(k, factor) * U(k)).  R and RU are produced one ROW at a time and
+        // folded into the new columns at once.  Terms that are exactly zero in the reference's gemm
+        // (U is upper triangular with U[l, j] = (-1)^l C(j, l); R[i, 0] = RU[i, 0] = RU[0, i] = delta_i0, so
+        // column 0 is unchanged) are skipped: adding an exact zero never changes a non-zero partial sum.
+        if (run_setup && state == L_RESCALE) {
+            const double factor = rescale_factor;
+            const double new_h = factor * h;
+            n_equal_steps = 0;
+            const int k = order;
+            const double* __restrict__ u = pa.tab.u[DSB_MAX_ORDER];         // leading dimension 6
+            double rrow[DSB_MAX_ORDER + 1];
+            double nd[DSB_MAX_ORDER + 1][N];
+#pragma unroll
+            for (int l = 1; l <= DSB_MAX_ORDER; ++l) rrow[l] = 1.0;
+#pragma unroll
+            for (int i = 1; i <= DSB_MAX_ORDER; ++i) {
+                if (i <= k) {
+                    const double i_t = (double)i;
+#pragma unroll
+                    for (int l = 1; l <= DSB_MAX_ORDER; ++l) {
+                        const double num = rrow[l] * (i_t - 1.0 - factor * (double)l);
+                        // x / 1, x / 2, x / 4 are exact scalings
+                        rrow[l] = (i == 1) ? num : (i == 2) ? num * 0.5 : (i == 4) ? num * 0.25 : num / i_t;
+                    }
+#pragma unroll
+                    for (int j = 1; j <= DSB_MAX_ORDER; ++j) {
+                        if (j <= k) {
+                            double ru_ij = rrow[1] * u[j * 6 + 1];              // RU[i, j] = sum_{l <= j} R[i, l] U[l, j]
+#pragma unroll
+                            for (int l = 2; l <= j; ++l) ru_ij = rrow[l] * u[j * 6 + l] + ru_ij;
+#pragma unroll
+                            for (int s = 0; s < N; ++s) {
+                                if (i == 1) nd[j][s] = SD(i, s) * ru_ij;
+                                else nd[j][s] = SD(i, s) * ru_ij + nd[j][s];
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 1; j <= DSB_MAX_ORDER; ++j) {
+                if (j <= k) {
+#pragma unroll
+                    for (int s = 0; s < N; ++s) SD(j, s) = nd[j][s];
+                }
+            }
+            c = new_h * pa.tab.alpha[k];
+            h = new_h;
+            conv.eta = pa.tab.eta_reset_timestep;
+            if (!rs_ignore_small && dsb_abs(h) < pa.opt.min_timestep) finish(DSB_STATUS_STEP_SIZE_TOO_SMALL);
+            else state = after_rescale;
         }
-        return 0;
-    }
 
-    DSB_DEV int set_stop_time(double ts) {
-        has_tstop = true; tstop = ts;
-        const int r = handle_tstop(ts);
-        if (r == 1) { has_tstop = false; return DSB_STATUS_STOP_TIME_AT_CURRENT; }
-        if (r < 0) return -r;
-        return DSB_STATUS_OK;
-    }
-
-    DSB_DEV int interpolate(double tq, double (&yo)[N]) const {
-        const bool is_forward = h > 0.0;
-        if ((is_forward && tq > t) || (!is_forward && tq < t)) return DSB_STATUS_INTERPOLATION_TIME_AFTER_CURRENT;
-        double time_factor = 1.0;
+        // ================= JAC: _jacobian_updates(c, kind) / Bdf::_new's reset_jacobian ===================
+        if (run_setup && state == L_JAC) {
+            bool do_factor = false;
+            if (jac_kind == DSB_KIND_CONSTRUCT) {
+                do_factor = true;
+                st.v[DSB_STAT_LINEAR_SOLVER_SETUPS] += 1;
+                st.v[DSB_STAT_SETUPS_FROM_CHECKPOINT] += 1;
+                after_jac = L_TSTOP;
+            } else if (ju.check_rhs_jacobian_update(pa.opt, c, jac_kind)) {
+                jacobian_is_stale = true;
+                ju.update_rhs_jacobian(c);
+                ju.update_jacobian(c);
+                do_factor = true;
+            } else if (ju.check_jacobian_update(pa.opt, c, jac_kind)) {
+                ju.update_jacobian(c);
+                do_factor = true;
+            }
+            if (do_factor) {
+                if (jac_kind != DSB_KIND_CONSTRUCT) {
+                    conv.eta = pa.tab.eta_reset;
+                    st.record_linear_solver_setup(jac_kind);
+                }
+                LaneLU<N> lu;
+                double pl[NP > 0 ? NP : 1];
 #pragma unroll
-        for (int i = 0; i < N; ++i) yo[i] = D(0, i);
-        for (int j = 0; j < order; ++j) {
-            const double j_t = (double)j;
-            time_factor *= (tq - (t - h * j_t)) / (h * (1.0 + j_t));
+                for (int j = 0; j < NP; ++j) pl[j] = SP(j);
+                if (jacobian_is_stale) {
+                    // df/dy at (state.y, state.t) (quirk Q6); passes through lu.a on its way to shared memory
+                    double yl[N];
 #pragma unroll
-            for (int i = 0; i < N; ++i) yo[i] = time_factor * D(j + 1, i) + yo[i];
+                    for (int i = 0; i < N; ++i) yl[i] = SY(i);
+                    lane_jacobian<M>(pa, yl, pl, t, lu.a, st);
+#pragma unroll
+                    for (int j = 0; j < N; ++j)
+#pragma unroll
+                        for (int i = 0; i < N; ++i) SJ(j, i) = lu.a[j][i];
+                    if (M::HAS_MASS) {
+                        lane_mass_matrix<M>(pl, t, lu.a);
+#pragma unroll
+                        for (int j = 0; j < N; ++j)
+#pragma unroll
+                            for (int i = 0; i < N; ++i) SMM(j, i) = lu.a[j][i];
+                    }
+                    jacobian_is_stale = false;
+                }
+                const double mc = -c;
+#pragma unroll
+                for (int j = 0; j < N; ++j)
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        // identity mass when the model has none (op/bdf.rs:141-143)
+                        const double m_ji = M::HAS_MASS ? SMM(j, i) : ((i == j) ? 1.0 : 0.0);
+                        lu.a[j][i] = SJ(j, i) * mc + m_ji;
+                    }
+                lu.factor();
+                piv_packed = 0;
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    piv_packed |= (unsigned long long)lu.piv[j] << (4 * j);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) SLU(j, i) = lu.a[j][i];
+                }
+            }
+            state = after_jac;
         }
-        return DSB_STATUS_OK;
-    }
-};
 
-// One thread per instance: Bdf::new + solve_dense (method.rs:721-818).
-template <class M>
-__global__ void __launch_bounds__(DSB_LANE_THREADS) dsb_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa,
-                                                                  const __grid_constant__ DsbBatchBuffers bb) {
-    constexpr int N = M::N;
-    constexpr int NP = M::NP;
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= pa.nbatch) return;
-    const int64_t B = pa.nbatch;
-    int status = bb.status[b];            // set by the init kernel
-    if (status != DSB_STATUS_OK) return;
+        // ================= TSTOP: set_stop_time (first) / handle_tstop after an accepted step =============
+        if (__any_sync(0xffffffffu, state == L_TSTOP) && state == L_TSTOP) {
+            int next = first ? L_PREDICT : L_OUTPUT;
+            int r = 0;
+            if (first) {
+                if (free_running) next = L_OUTPUT;
+                else {
+                    has_tstop = true; tstop = bb.t_eval[nt - 1];
+                    r = handle_tstop(tstop);
+                    if (r == 1) r = -DSB_STATUS_STOP_TIME_AT_CURRENT;
+                }
+            } else if (has_tstop) {
+                r = handle_tstop(tstop);
+                if (r == 1) reached = true;
+            }
+            if (r < 0) {
+                finish(-r);
+            } else if (r == 2) {
+                rs_ignore_small = true;            // "step size too small" is ignored here (bdf.rs:726-728)
+                state = L_RESCALE; after_rescale = next;
+            } else {
+                state = next;
+            }
+            if (first && state != L_FETCH) {       // start of the first step()
+                old_num_error_test_failures = st.v[DSB_STAT_ERROR_TEST_FAILURES];
+                convergence_fail = false; repredict = true;
+            }
+            first = false;
+        }
 
-    extern __shared__ double dsb_lane_smem[];
-    BdfLane<M> s(pa, dsb_lane_smem + threadIdx.x);
-#pragma unroll
-    for (int j = 0; j < NP; ++j) s.p[j] = bb.params[(int64_t)j * B + b];
-#pragma unroll
-    for (int k = 0; k < DSB_NSTATS; ++k) s.st.v[k] = bb.stats[(int64_t)k * B + b];
-    {
-        double y_init[N], dy_init[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) { y_init[i] = bb.y0[(int64_t)i * B + b]; dy_init[i] = bb.dy0[(int64_t)i * B + b]; }
-        s.construct(y_init, dy_init, bb.h0[b]);
-    }
-    const int nt = pa.nt;
-    const bool free_running = pa.free_running != 0;
-    if (!free_running) status = s.set_stop_time(bb.t_eval[nt - 1]);
-    int col = 0;
-    while (status == DSB_STATUS_OK && col < nt) {
-        if (free_running) {
-            while (col < nt && !(dsb_abs(s.t) < dsb_abs(bb.t_eval[col]))) {
+        // ================= OUTPUT: dense output at every t_eval passed (method.rs:761-764, 822-848) =======
+        if (__any_sync(0xffffffffu, state == L_OUTPUT) && state == L_OUTPUT) {
+            int status = DSB_STATUS_OK;
+            while (col < nt) {
+                const double tq = bb.t_eval[col];
+                if (free_running ? (dsb_abs(t) < dsb_abs(tq)) : !(tq <= t)) break;
+                // interpolate (bdf.rs:767-782, 1080-1106)
+                const bool is_forward = h > 0.0;
+                if ((is_forward && tq > t) || (!is_forward && tq < t)) { status = DSB_STATUS_INTERPOLATION_TIME_AFTER_CURRENT; break; }
                 double yo[N];
-                const int e = s.interpolate(bb.t_eval[col], yo);
-                if (e) { status = e; break; }
+                double time_factor = 1.0;
 #pragma unroll
-                for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + b] = yo[i];
+                for (int i = 0; i < N; ++i) yo[i] = SD(0, i);
+#pragma unroll 1
+                for (int j = 0; j < order; ++j) {
+                    const double j_t = (double)j;
+                    time_factor *= (tq - (t - h * j_t)) / (h * (1.0 + j_t));
+#pragma unroll
+                    for (int i = 0; i < N; ++i) yo[i] = time_factor * SD(j + 1, i) + yo[i];
+                }
+#pragma unroll
+                for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
                 ++col;
             }
-            if (col >= nt || status != DSB_STATUS_OK) break;
-        }
-        const int r = s.step();
-        if (r < 0) { status = -r; break; }
-        if (!free_running) {
-            while (col < nt && bb.t_eval[col] <= s.t) {
-                double yo[N];
-                const int e = s.interpolate(bb.t_eval[col], yo);
-                if (e) { status = e; break; }
-#pragma unroll
-                for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + b] = yo[i];
-                ++col;
+            if (status != DSB_STATUS_OK) finish(status);
+            else if (free_running ? (col >= nt) : reached) finish(DSB_STATUS_OK);
+            else {                                  // start of the next step()
+                old_num_error_test_failures = st.v[DSB_STAT_ERROR_TEST_FAILURES];
+                convergence_fail = false; repredict = true;
+                state = L_PREDICT;
             }
-            if (r == 1) break;
         }
-    }
-    bb.status[b] = status;
-    bb.fin_t[b] = s.t; bb.fin_h[b] = s.h; bb.fin_order[b] = s.order;
+
+        // ================= PREDICT: _predict_forward + start of a Newton solve ============================
+        if (__any_sync(0xffffffffu, state == L_PREDICT) && state == L_PREDICT) {
+            if (repredict) {
+                double yp[N];
 #pragma unroll
-    for (int k = 0; k < DSB_NSTATS; ++k) bb.stats[(int64_t)k * B + b] = s.st.v[k];
+                for (int i = 0; i < N; ++i) yp[i] = 0.0;
+#pragma unroll 1
+                for (int j = 0; j <= order; ++j) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) yp[i] += SD(j, i);
+                }
+#pragma unroll
+                for (int i = 0; i < N; ++i) psi_neg_y0[i] = pa.tab.gamma[1] * SD(1, i);
+#pragma unroll 1
+                for (int j = 2; j <= order; ++j) {
+                    const double g = pa.tab.gamma[j];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) psi_neg_y0[i] = g * SD(j, i) + psi_neg_y0[i];
+                }
+                const double a = pa.tab.alpha[order];
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    psi_neg_y0[i] *= a;
+                    psi_neg_y0[i] -= yp[i];
+                    SYP(i) = yp[i];
+                    wt[i] = dsb_abs(yp[i]) * pa.rtol + pa.atol[i];     // Newton norm weights use the predictor
+                }
+                t_predict = t + h;
+            }
+            state = L_NEWTON;
+            if (pending_etf) {
+                pending_etf = false;
+                st.v[DSB_STAT_ERROR_TEST_FAILURES] += 1;
+                if (st.v[DSB_STAT_ERROR_TEST_FAILURES] - old_num_error_test_failures >= pa.opt.max_error_test_failures)
+                    finish(DSB_STATUS_TOO_MANY_ERROR_TEST_FAILURES);
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) y_cur[i] = SYP(i);
+            conv.reset();
+        }
+
+        // ================= NEWTON: one iteration (newton.rs:13-36, line_search.rs:48-69) ==================
+        if (__any_sync(0xffffffffu, state == L_NEWTON) && state == L_NEWTON) {
+            double pl[NP > 0 ? NP : 1];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) pl[j] = SP(j);
+            double delta[N];
+            M::rhs(y_cur, pl, t_predict, delta);
+            st.v[DSB_STAT_RHS_CALLS] += 1;
+            {
+                double tmp[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) tmp[i] = y_cur[i] + psi_neg_y0[i];
+                const double mc = -c;
+                if (M::HAS_MASS) {
+                    M::mass(tmp, pl, t_predict, mc, delta);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) delta[i] = tmp[i] + mc * delta[i];
+                }
+            }
+            LaneLU<N> lu;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                lu.piv[j] = (int)((piv_packed >> (4 * j)) & 15ull);
+#pragma unroll
+                for (int i = 0; i < N; ++i) lu.a[j][i] = SLU(j, i);
+            }
+            if (!lu.solve(delta)) {
+                newton_ok = false; state = L_POST;              // LuSolveFailed
+            } else {
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    y_cur[i] -= delta[i];
+                    const double term = delta[i] / wt[i];
+                    acc += term * term;
+                }
+                const double norm = dsb_sqrt(acc / (double)N);
+                // Convergence::check_new_iteration (convergence.rs:68-139) with its pow() hoisted to one call site
+                conv.niter += 1;
+                const bool have_rate = conv.has_old_norm;
+                double px, py;
+                if (have_rate) { px = norm / conv.old_norm; py = 1.0 / (double)(conv.niter - 1); }
+                else { const double min_eta = 1e4 * eps; px = (conv.eta < min_eta) ? min_eta : conv.eta; py = 0.8; }
+                const double pw = dsb_pow(px, py);
+                int s = LANE_CONTINUE;
+                if (have_rate) {
+                    const double rate = pw;
+                    if (rate > 0.9) s = LANE_DIVERGED;
+                    else if (dsb_powi(rate, conv.max_iter - conv.niter) / (1.0 - rate) * norm > conv.tol) s = LANE_DIVERGED;
+                    else conv.eta = rate / (1.0 - rate);
+                } else {
+                    conv.eta = pw;
+                }
+                if (s != LANE_DIVERGED && conv.eta * norm < conv.tol) s = LANE_CONVERGED;
+                if (conv.niter == 1) { conv.has_old_norm = true; conv.old_norm = norm; }   // frozen at the FIRST norm (quirk Q3)
+                if (s == LANE_CONVERGED) { newton_ok = true; state = L_POST; }
+                else if (s == LANE_DIVERGED || conv.niter >= conv.max_iter) { newton_ok = false; state = L_POST; }
+            }
+        }
+        // ================= POST: a Newton solve ended (bdf.rs:1338-1563) ==================================
+        if (__any_sync(0xffffffffu, state == L_POST) && state == L_POST) {
+            st.v[DSB_STAT_NONLINEAR_SOLVER_ITERATIONS] += conv.niter;
+            if (newton_ok) {
+                const int ord = order;
+                double d[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) d[i] = y_cur[i] - SYP(i);
+                {   // error_control: ||d||^2_w(state.y) * error_const2[order - 1]
+                    double acc = 0.0;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const double term = d[i] / (dsb_abs(SY(i)) * pa.rtol + pa.atol[i]);
+                        acc += term * term;
+                    }
+                    const double err = acc / (double)N * pa.tab.error_const2[ord - 1];
+                    error_norm = (0.0 < err) ? err : 0.0;
+                }
+                const double maxiter = (double)conv.max_iter;
+                const double niter = (double)conv.niter;
+                safety = 0.9 * (2.0 * maxiter + 1.0) / (2.0 * maxiter + niter);
+                if (error_norm <= 1.0) {
+                    // ---- accepted: _update_diff, state.y <- PREDICTOR (quirk Q1) ----
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        SD(ord + 2, i) = d[i] - SD(ord + 1, i);
+                        SD(ord + 1, i) = d[i];
+                    }
+#pragma unroll 1
+                    for (int j = ord; j >= 0; --j) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) SD(j, i) = SD(j, i) + 1.0 * SD(j + 1, i);
+                    }
+#pragma unroll
+                    for (int i = 0; i < N; ++i) SY(i) = SYP(i);
+                    t = t_predict;
+                    st.v[DSB_STAT_STEPS] += 1;
+                    ju.step();
+                    has_prev_error = true; prev_error_norm = error_norm;
+                    n_equal_steps += 1;
+                    accepted = true;
+                    state = (n_equal_steps > ord) ? L_SELECT : L_TSTOP;
+                } else {
+                    accepted = false;               // error test failed: the new step size needs a pow(), see SELECT
+                    state = L_SELECT;
+                }
+            } else {
+                // ---- Newton failed ----
+                st.v[DSB_STAT_NONLINEAR_SOLVER_FAILS] += 1;
+                has_prev_error = false;
+                if (st.v[DSB_STAT_NONLINEAR_SOLVER_FAILS] > pa.opt.max_nonlinear_solver_failures) {
+                    finish(DSB_STATUS_TOO_MANY_NONLINEAR_FAILURES);
+                } else if (convergence_fail) {
+                    rescale_factor = 0.3; rs_ignore_small = false;
+                    state = L_RESCALE; after_rescale = L_JAC;
+                    jac_kind = DSB_SECOND_CONVERGENCE_FAIL; after_jac = L_PREDICT;
+                    repredict = true;
+                } else {
+                    convergence_fail = true;
+                    state = L_JAC; jac_kind = DSB_FIRST_CONVERGENCE_FAIL; after_jac = L_PREDICT;
+                    repredict = false;                          // retry from the SAME predictor
+                }
+            }
+        }
+
+    }
+#undef SM
+#undef SD
+#undef SJ
+#undef SMM
+#undef SLU
+#undef SY
+#undef SYP
+#undef SP
 }

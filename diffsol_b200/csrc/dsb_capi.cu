@@ -8,6 +8,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -53,6 +54,7 @@ struct dsb_batch {
     int32_t* fin_order = nullptr;
     int32_t* stats = nullptr;   // [DSB_NSTATS][B]
     int32_t* status = nullptr;
+    unsigned long long* work_counter = nullptr;
     double* t_eval = nullptr; int t_eval_cap = 0;
     double* ys_own = nullptr; size_t ys_own_bytes = 0;       // used by the *_host entry point
     void* stage = nullptr; size_t stage_bytes = 0;           // instance-major staging for host copies
@@ -331,6 +333,7 @@ int dsb_batch_new(const dsb_problem* p, int64_t nbatch, int32_t device, dsb_batc
     alloc((void**)&b->fin_order, B * 4);
     alloc((void**)&b->stats, (size_t)DSB_NSTATS * B * 4);
     alloc((void**)&b->status, B * 4);
+    alloc((void**)&b->work_counter, 8);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_mid);
@@ -341,6 +344,7 @@ int dsb_batch_new(const dsb_problem* p, int64_t nbatch, int32_t device, dsb_batc
     cudaMemset(b->params, 0, np * B * 8);
     cudaMemset(b->stats, 0, (size_t)DSB_NSTATS * B * 4);
     cudaMemset(b->status, 0, B * 4);
+    cudaMemset(b->fin_t, 0, B * 8); cudaMemset(b->fin_h, 0, B * 8); cudaMemset(b->fin_order, 0, B * 4);
     *out = b;
     return DSB_OK;
 }
@@ -350,7 +354,7 @@ int dsb_batch_free(dsb_batch* b) {
     cudaSetDevice(b->device);
     cudaFree(b->params); cudaFree(b->y0); cudaFree(b->dy0); cudaFree(b->h0);
     cudaFree(b->fin_t); cudaFree(b->fin_h); cudaFree(b->fin_order);
-    cudaFree(b->stats); cudaFree(b->status); cudaFree(b->t_eval); cudaFree(b->ys_own); cudaFree(b->stage);
+    cudaFree(b->stats); cudaFree(b->status); cudaFree(b->work_counter); cudaFree(b->t_eval); cudaFree(b->ys_own); cudaFree(b->stage);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->ev_mid) cudaEventDestroy(b->ev_mid);
@@ -405,6 +409,8 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     if (fill_problem_args(b->prob, b->B, nt, &pa, &probes) != DSB_OK) return fail(DSB_BAD_ARG, "unknown model id");
     b->sparsity_probe_jac_muls = probes;
     pa.free_running = free_running;
+    pa.quorum = DSB_DEFAULT_QUORUM;
+    if (const char* q = getenv("DSB_QUORUM")) { int v = atoi(q); if (v >= 1 && v <= 33) pa.quorum = v; }   // tuning knob
     DsbBatchBuffers bb;
     bb.params = b->params; bb.t_eval = b->t_eval; bb.y0 = b->y0; bb.dy0 = b->dy0; bb.h0 = b->h0;
     bb.ys = ys_dev; bb.stats = b->stats; bb.status = b->status;
@@ -414,7 +420,7 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     b->last_launches = 0;
     DSB_CUDA(cudaEventRecord(b->ev0, stream));
     if (b->prob.model < 0 || b->prob.model >= DSB_MODEL_COUNT) return fail(DSB_BAD_ARG, "unknown model id");
-    cudaError_t lerr = g_launch_table[b->prob.model](&pa, &bb, method, stream, b->ev_mid, &b->last_launches);
+    cudaError_t lerr = g_launch_table[b->prob.model](&pa, &bb, method, stream, b->ev_mid, b->work_counter, &b->last_launches);
     if (lerr != cudaSuccess) return fail(DSB_ERR, std::string("kernel launch: ") + cudaGetErrorString(lerr));
     DSB_CUDA(cudaEventRecord(b->ev1, stream));
     b->have_timing = true;

@@ -13,17 +13,33 @@
 typedef dsb_model_by_id<DSB_INST>::type InstModel;
 
 cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method,
-                                                 cudaStream_t stream, cudaEvent_t mid, int* launches) {
-    const int threads = DSB_LANE_THREADS;
-    const unsigned blocks = (unsigned)((pa->nbatch + threads - 1) / threads);
+                                                 cudaStream_t stream, cudaEvent_t mid, unsigned long long* work_counter,
+                                                 int* launches) {
+    const int init_threads = DSB_LANE_THREADS;
+    const unsigned init_blocks = (unsigned)((pa->nbatch + init_threads - 1) / init_threads);
     if (method == DSB_METHOD_BDF) {
-        const size_t smem = (size_t)BdfLane<InstModel>::SM_WORDS * threads * sizeof(double);
-        cudaError_t e = cudaFuncSetAttribute(dsb_bdf_solve_dense_kernel<InstModel>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int threads = BdfLayout<InstModel>::THREADS;
+        const unsigned blocks = (unsigned)((pa->nbatch + threads - 1) / threads);
+        const size_t smem = (size_t)BdfLayout<InstModel>::WORDS * threads * sizeof(double);
+        static int resident_blocks = 0;      // persistent grid: as many blocks as fit on the device at once
+        if (resident_blocks == 0) {
+            cudaError_t e = cudaFuncSetAttribute(dsb_bdf_solve_dense_kernel<InstModel>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            int dev = 0, sms = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dsb_bdf_solve_dense_kernel<InstModel>, threads, smem);
+            if (e != cudaSuccess) return e;
+            if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+            resident_blocks = sms * per_sm;
+        }
+        cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return e;
-        dsb_init_kernel<InstModel><<<blocks, threads, 0, stream>>>(*pa, *bb, 1);
+        dsb_init_kernel<InstModel><<<init_blocks, init_threads, 0, stream>>>(*pa, *bb, 1);
         if (mid) cudaEventRecord(mid, stream);
-        dsb_bdf_solve_dense_kernel<InstModel><<<blocks, threads, smem, stream>>>(*pa, *bb);
+        const unsigned grid = blocks < (unsigned)resident_blocks ? blocks : (unsigned)resident_blocks;
+        dsb_bdf_solve_dense_kernel<InstModel><<<grid, threads, smem, stream>>>(*pa, *bb, work_counter);
         *launches += 2;
     } else {
         return cudaErrorNotSupported;

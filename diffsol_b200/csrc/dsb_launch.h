@@ -6,11 +6,13 @@
 #include "dsb_args.h"
 
 // `mid` (may be NULL) is recorded between the initialisation kernel and the integrator kernel so the
-// integrator's own duration can be read back.
+// integrator's own duration can be read back; `work_counter` is the device word the persistent integrator
+// kernel draws instance indices from (zeroed by the launcher).
 typedef cudaError_t (*dsb_launch_fn)(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method,
-                                     cudaStream_t stream, cudaEvent_t mid, int* launches);
+                                     cudaStream_t stream, cudaEvent_t mid, unsigned long long* work_counter,
+                                     int* launches);
 
-#define DSB_DECLARE_LAUNCH(id) cudaError_t dsb_launch_model_##id(const DsbProblemArgs*, const DsbBatchBuffers*, int, cudaStream_t, cudaEvent_t, int*);
+#define DSB_DECLARE_LAUNCH(id) cudaError_t dsb_launch_model_##id(const DsbProblemArgs*, const DsbBatchBuffers*, int, cudaStream_t, cudaEvent_t, unsigned long long*, int*);
 DSB_DECLARE_LAUNCH(0) DSB_DECLARE_LAUNCH(1) DSB_DECLARE_LAUNCH(2) DSB_DECLARE_LAUNCH(3)
 DSB_DECLARE_LAUNCH(4) DSB_DECLARE_LAUNCH(5) DSB_DECLARE_LAUNCH(6) DSB_DECLARE_LAUNCH(7)
 #undef DSB_DECLARE_LAUNCH

@@ -82,6 +82,8 @@ DSB_HD_NOINLINE double dsb_pow(double x, double y) {
     if (y == 0.0) return 1.0;
     if (dsb_isnan(x) || dsb_isnan(y)) return nan;
     if (x < 0.0) return nan;
+    if (y == 1.0) return x;                     // exact, and the most frequent call (Newton rate at the 2nd iteration)
+    if (y == 0.5) return dsb_sqrt(x);           // correctly rounded (x >= 0 here)
     if (x == 0.0) return y > 0.0 ? 0.0 : inf;
     if (x == inf) return y > 0.0 ? inf : 0.0;
     if (x == 1.0) return 1.0;
