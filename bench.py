@@ -103,7 +103,7 @@ def run_reference(args):
     orc.build()
     threads = orc.num_threads()
     desc = orc.make_desc("robertson_ode", powmode=0, **sweeps.ROBERTSON_ODE_TOL)
-    sample = args.cpu_sample or 16384
+    sample = args.cpu_sample or (1 << 20)
     p = sweeps.robertson_sweep(np.arange(sample))
     for _ in range(max(args.warmup, 1)):
         orc.batch_solve_dense(desc, p[: max(256, sample // 16)], sweeps.ROBERTSON_T_EVAL, nthreads=threads)
@@ -128,7 +128,7 @@ def run_reference(args):
     return 0
 
 
-def cpu_baseline(seconds_target=12.0):
+def cpu_baseline(seconds_target=10.0):
     from oracle import oracle as orc
     from diffsol_b200 import sweeps
     orc.build()
@@ -139,7 +139,7 @@ def cpu_baseline(seconds_target=12.0):
     t0 = time.perf_counter()
     orc.batch_solve_dense(desc, p, sweeps.ROBERTSON_T_EVAL, nthreads=threads)
     rate = probe / (time.perf_counter() - t0)
-    sample = int(min(max(rate * seconds_target, probe), 1 << 18))
+    sample = int(min(max(rate * seconds_target, probe), 1 << 22))
     p = sweeps.robertson_sweep(np.arange(sample))
     t0 = time.perf_counter()
     _, stats, _ = orc.batch_solve_dense(desc, p, sweeps.ROBERTSON_T_EVAL, nthreads=threads)

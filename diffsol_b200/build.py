@@ -13,14 +13,16 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT_DIR = os.path.join(HERE, "_lib")
+# DSB_LIB_TAG / DSB_NVCC_EXTRA: build and load an alternative variant side by side (kernel tuning experiments)
+_TAG = os.environ.get("DSB_LIB_TAG", "")
+OUT_DIR = os.path.join(HERE, "_lib" + ("_" + _TAG if _TAG else ""))
 LIB = os.path.join(OUT_DIR, "libdiffsol_b200.so")
 N_MODELS = 8
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "-diag-suppress", "128",
-]
+] + os.environ.get("DSB_NVCC_EXTRA", "").split()
 
 
 def _nvcc():

@@ -63,10 +63,15 @@ struct BdfLayout {
     static constexpr int WORDS = O_P + (NP > 0 ? NP : 1);
     // threads per block: the per-thread column must leave room for >= 2 blocks per SM (227 KB)
     static constexpr int THREADS = (WORDS * 8 * 128 <= 75 * 1024) ? 128 : (WORDS * 8 * 64 <= 110 * 1024) ? 64 : 32;
+    // resident blocks per SM the register allocation is asked to allow (shared memory permitting)
+#ifndef DSB_MIN_BLOCKS
+#define DSB_MIN_BLOCKS 3
+#endif
+    static constexpr int MIN_BLOCKS = (WORDS * 8 * THREADS * DSB_MIN_BLOCKS <= 226 * 1024) ? DSB_MIN_BLOCKS : 1;
 };
 
 template <class M>
-__global__ void __launch_bounds__(BdfLayout<M>::THREADS) dsb_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa,
+__global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCKS) dsb_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa,
                                                                               const __grid_constant__ DsbBatchBuffers bb,
                                                                               unsigned long long* __restrict__ work_counter) {
     constexpr int N = M::N;
@@ -168,9 +173,20 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS) dsb_bdf_solve_dense_ker
         const int n_active = 32 - __popc(m_idle);
         const int n_select = __popc(__ballot_sync(0xffffffffu, state == L_SELECT));
         const int n_setup = __popc(__ballot_sync(0xffffffffu, state == L_RESCALE || state == L_JAC));
-        const bool none_running = (n_select + n_setup) == n_active;
-        const bool run_select = n_select > 0 && (n_select >= quorum || 2 * n_select >= n_active || none_running);
-        const bool run_setup = n_setup > 0 && (n_setup >= quorum || 2 * n_setup >= n_active || none_running);
+        const int n_post = __popc(__ballot_sync(0xffffffffu, state == L_POST));
+        const int n_slow = n_select + n_setup;
+        bool run_select, run_setup;
+        if (pa.sched_mode == 0) {        // separate pools
+            const bool none_running = n_slow == n_active;
+            run_select = n_select > 0 && (n_select >= quorum || 2 * n_select >= n_active || none_running);
+            run_setup = n_setup > 0 && (n_setup >= quorum || 2 * n_setup >= n_active || none_running);
+        } else {                         // one pool: SELECT -> RESCALE -> JAC flow through together
+            run_select = run_setup = n_slow > 0 && (n_slow >= quorum || 2 * n_slow >= n_active);
+        }
+        // POST (and the per-step chain behind it) may also wait for company: lanes whose Newton solve ended
+        // early idle a trip so that the chain runs once with more lanes
+        const int n_hot = n_active - n_slow;
+        const bool run_post = n_post > 0 && (n_post >= pa.quorum_post || n_post * pa.post_den >= n_hot * pa.post_num);
 
         // ================= FINISH: write the instance's results, then fetch the next one =====================
         if (__any_sync(0xffffffffu, state == L_FINISH) && state == L_FINISH) {
@@ -549,7 +565,7 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS) dsb_bdf_solve_dense_ker
             }
         }
         // ================= POST: a Newton solve ended (bdf.rs:1338-1563) ==================================
-        if (__any_sync(0xffffffffu, state == L_POST) && state == L_POST) {
+        if (run_post && state == L_POST) {
             st.v[DSB_STAT_NONLINEAR_SOLVER_ITERATIONS] += conv.niter;
             if (newton_ok) {
                 const int ord = order;

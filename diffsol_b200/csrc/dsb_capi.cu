@@ -410,6 +410,11 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     b->sparsity_probe_jac_muls = probes;
     pa.free_running = free_running;
     pa.quorum = DSB_DEFAULT_QUORUM;
+    pa.sched_mode = 1; pa.quorum_post = 1; pa.post_num = 0; pa.post_den = 1;
+    if (const char* q = getenv("DSB_SCHED_MODE")) pa.sched_mode = atoi(q);
+    if (const char* q = getenv("DSB_Q_POST")) pa.quorum_post = atoi(q);
+    if (const char* q = getenv("DSB_POST_NUM")) pa.post_num = atoi(q);
+    if (const char* q = getenv("DSB_POST_DEN")) pa.post_den = atoi(q);
     if (const char* q = getenv("DSB_QUORUM")) { int v = atoi(q); if (v >= 1 && v <= 33) pa.quorum = v; }   // tuning knob
     DsbBatchBuffers bb;
     bb.params = b->params; bb.t_eval = b->t_eval; bb.y0 = b->y0; bb.dy0 = b->dy0; bb.h0 = b->h0;

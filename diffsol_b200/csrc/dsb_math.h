@@ -75,28 +75,11 @@ DSB_HD double dsb_sqrt(double a) {
 DSB_HD double dsb_abs(double a) { return dsb_from_bits(dsb_bits(a) & 0x7fffffffffffffffULL); }
 DSB_HD bool dsb_isnan(double a) { return a != a; }
 
-// x^y for x >= 0 (x < 0 returns NaN: the hot path never raises a negative base to a power).
-DSB_HD_NOINLINE double dsb_pow(double x, double y) {
+// Core of dsb_pow for a positive, finite, NORMAL x (bits ix) and finite y: exp(y * log(x)) with log(x) as
+// a double-double (table of 128 sub-intervals, Tang-style) and a 128-entry 2^(j/128) table for exp.
+DSB_HD double dsb_pow_core(uint64_t ix, int sub, double y) {
     const double inf = dsb_from_bits(0x7ff0000000000000ULL);
-    const double nan = dsb_from_bits(0x7ff8000000000000ULL);
-    if (y == 0.0) return 1.0;
-    if (dsb_isnan(x) || dsb_isnan(y)) return nan;
-    if (x < 0.0) return nan;
-    if (y == 1.0) return x;                     // exact, and the most frequent call (Newton rate at the 2nd iteration)
-    if (y == 0.5) return dsb_sqrt(x);           // correctly rounded (x >= 0 here)
-    if (x == 0.0) return y > 0.0 ? 0.0 : inf;
-    if (x == inf) return y > 0.0 ? inf : 0.0;
-    if (x == 1.0) return 1.0;
-    if (y == inf) return x > 1.0 ? inf : 0.0;
-    if (y == -inf) return x > 1.0 ? 0.0 : inf;
-
     // ---- log(x) = k ln2 + log(c_i) + log1p(r),  r = z/c_i - 1, as hi + lo ----
-    uint64_t ix = dsb_bits(x);
-    int sub = 0;
-    if (ix < 0x0010000000000000ULL) {           // subnormal: scale by 2^52
-        ix = dsb_bits(x * 4503599627370496.0);
-        sub = 52;
-    }
     const uint64_t OFF = 0x3FE6955500000000ULL;
     uint64_t tmp = ix - OFF;
     int i = (int)((tmp >> 45) & 127);
@@ -173,6 +156,40 @@ DSB_HD_NOINLINE double dsb_pow(double x, double y) {
     double sc1 = dsb_from_bits((uint64_t)(k1 + 1023) << 52);
     double sc2 = dsb_from_bits((uint64_t)(k2 + 1023) << 52);
     return (val * sc1) * sc2;
+}
+
+// Everything that is not (positive normal x, finite y): zeros, infinities, NaNs, negative and subnormal x.
+DSB_HD_NOINLINE double dsb_pow_special(double x, double y) {
+    const double inf = dsb_from_bits(0x7ff0000000000000ULL);
+    const double nan = dsb_from_bits(0x7ff8000000000000ULL);
+    if (y == 0.0) return 1.0;
+    if (dsb_isnan(x) || dsb_isnan(y)) return nan;
+    if (x < 0.0) return nan;
+    if (x == 0.0) return y > 0.0 ? 0.0 : inf;
+    if (x == inf) return y > 0.0 ? inf : 0.0;
+    if (x == 1.0) return 1.0;
+    if (y == inf) return x > 1.0 ? inf : 0.0;
+    if (y == -inf) return x > 1.0 ? 0.0 : inf;
+    uint64_t ix = dsb_bits(x);
+    int sub = 0;
+    if (ix < 0x0010000000000000ULL) {           // subnormal: scale by 2^52
+        ix = dsb_bits(x * 4503599627370496.0);
+        sub = 52;
+    }
+    return dsb_pow_core(ix, sub, y);
+}
+
+// x^y for x >= 0 (x < 0 returns NaN: the hot path never raises a negative base to a power).
+DSB_HD_NOINLINE double dsb_pow(double x, double y) {
+    if (y == 1.0) return x;                     // exact, and the most frequent call (Newton rate at the 2nd iteration)
+    const uint64_t ix = dsb_bits(x);
+    const uint64_t iy = dsb_bits(y) & 0x7fffffffffffffffULL;
+    // fast path: x positive, finite and normal; y finite and non-zero
+    const bool x_ok = (ix - 0x0010000000000000ULL) < (0x7ff0000000000000ULL - 0x0010000000000000ULL);
+    const bool y_ok = (iy - 1ULL) < (0x7ff0000000000000ULL - 1ULL);
+    if (!(x_ok && y_ok)) return dsb_pow_special(x, y);
+    if (y == 0.5) return dsb_sqrt(x);           // correctly rounded
+    return dsb_pow_core(ix, 0, y);
 }
 
 // f64::powi as lowered by LLVM on the reference's targets: compiler-rt / compiler_builtins
