@@ -32,6 +32,14 @@ struct DsbBdfTables {
     double ic_steptol;             // eps^(2/3) line_search.rs:126
 };
 
+// Butcher tableau of an (E)SDIRK method (ode_solver/tableau.rs:41-159), evaluated on the host
+struct DsbSdirkTableau {
+    int32_t s, order, has_beta, reserved;
+    double a[16];        // s x s column-major: a(i, j) = a[j * s + i]
+    double b[4], c[4], d[4];
+    double beta[8];      // s x 2 column-major (dense-output coefficients), when has_beta
+};
+
 struct DsbProblemArgs {
     int64_t nbatch;
     int32_t nt;
@@ -48,6 +56,7 @@ struct DsbProblemArgs {
     double t0, h0;
     dsb_options opt;
     DsbBdfTables tab;
+    DsbSdirkTableau rk;
 };
 
 // Device buffers of one batch, all batch-major (instance index fastest) so that a warp's 32 lanes

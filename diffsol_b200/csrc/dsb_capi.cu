@@ -105,6 +105,37 @@ void build_tables(DsbBdfTables* tb) {
     tb->ic_steptol = dsb_pow(std::numeric_limits<double>::epsilon(), 2.0 / 3.0);
 }
 
+// ode_solver/tableau.rs:41-97 (tr_bdf2) and :101-159 (esdirk34); same expressions as the reference
+void build_tableau(int method, DsbSdirkTableau* t) {
+    std::memset(t, 0, sizeof(*t));
+    if (method == DSB_METHOD_TR_BDF2) {
+        t->s = 3; t->order = 2; t->has_beta = 1;
+        const double gamma = 2.0 - std::sqrt(2.0);
+        const double d = gamma / 2.0;
+        const double w = std::sqrt(2.0) / 4.0;
+        const double a[9] = {0.0, d, w, 0.0, d, w, 0.0, 0.0, d};
+        for (int i = 0; i < 9; ++i) t->a[i] = a[i];
+        t->b[0] = w; t->b[1] = w; t->b[2] = d;
+        const double b_hat[3] = {(1.0 - w) / 3.0, (3.0 * w + 1.0) / 3.0, d / 3.0};
+        for (int i = 0; i < 3; ++i) t->d[i] = t->b[i] - b_hat[i];
+        const double beta[6] = {2.0 * w, 2.0 * w, gamma - 1.0, -w, -w, 2.0 * w};
+        for (int i = 0; i < 6; ++i) t->beta[i] = beta[i];
+        t->c[0] = 0.0; t->c[1] = gamma; t->c[2] = 1.0;
+    } else if (method == DSB_METHOD_ESDIRK34) {
+        t->s = 4; t->order = 3; t->has_beta = 0;
+        const double g = 0.435866521508459;
+        const double a[16] = {0.0, g, 0.1407377747247062, 0.102399400619911,
+                              0.0, g, -0.1083655513813208, -0.3768784522555561,
+                              0.0, 0.0, g, 0.8386125301271861,
+                              0.0, 0.0, 0.0, g};
+        for (int i = 0; i < 16; ++i) t->a[i] = a[i];
+        for (int j = 0; j < 4; ++j) t->b[j] = a[j * 4 + 3];
+        const double c[4] = {0.0, 0.871733043016918, 0.4682387448518444, 1.0};
+        const double d[4] = {-0.05462549724041394, -0.49420889362599496, 0.22193449973506466, 0.32689989113134427};
+        for (int i = 0; i < 4; ++i) { t->c[i] = c[i]; t->d[i] = d[i]; }
+    }
+}
+
 // jacobian/mod.rs:16-48 (NaN probe), coloring.rs:27-47 (graph), greedy_coloring.rs:14-34.
 // The pattern is a property of the equations, not of the instance ("assume every batch has the same
 // non-zeros", jacobian/mod.rs:32), so it is found once on the host with the model's own functor.
@@ -167,6 +198,7 @@ int fill_problem_args(const dsb_problem& pr, int64_t B, int nt, DsbProblemArgs* 
 const dsb_launch_fn g_launch_table[DSB_MODEL_COUNT] = {
     dsb_launch_model_0, dsb_launch_model_1, dsb_launch_model_2, dsb_launch_model_3,
     dsb_launch_model_4, dsb_launch_model_5, dsb_launch_model_6, dsb_launch_model_7,
+    dsb_launch_model_8,
 };
 
 // instance-major <-> batch-major re-layout on the device (the host-facing layouts follow the
@@ -393,7 +425,6 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     if (!b || !t_eval || nt < 1 || !ys_dev) return fail(DSB_BAD_ARG, "bad argument to dsb_batch_solve_dense");
     if (method != DSB_METHOD_BDF && method != DSB_METHOD_TR_BDF2 && method != DSB_METHOD_ESDIRK34)
         return fail(DSB_BAD_ARG, "unknown method");
-    if (method != DSB_METHOD_BDF) return fail(DSB_ERR, "SDIRK kernels are not built into this library yet");
     for (int k = 1; k < nt; ++k)
         if (!(t_eval[k] >= t_eval[k - 1])) return fail(DSB_BAD_ARG, "t_eval must be increasing");
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -409,6 +440,7 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     if (fill_problem_args(b->prob, b->B, nt, &pa, &probes) != DSB_OK) return fail(DSB_BAD_ARG, "unknown model id");
     b->sparsity_probe_jac_muls = probes;
     pa.free_running = free_running;
+    build_tableau(method, &pa.rk);
     pa.quorum = DSB_DEFAULT_QUORUM;
     pa.sched_mode = 1; pa.quorum_post = 1; pa.post_num = 0; pa.post_den = 1;
     if (const char* q = getenv("DSB_SCHED_MODE")) pa.sched_mode = atoi(q);

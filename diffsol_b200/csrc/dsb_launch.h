@@ -15,4 +15,5 @@ typedef cudaError_t (*dsb_launch_fn)(const DsbProblemArgs* pa, const DsbBatchBuf
 #define DSB_DECLARE_LAUNCH(id) cudaError_t dsb_launch_model_##id(const DsbProblemArgs*, const DsbBatchBuffers*, int, cudaStream_t, cudaEvent_t, unsigned long long*, int*);
 DSB_DECLARE_LAUNCH(0) DSB_DECLARE_LAUNCH(1) DSB_DECLARE_LAUNCH(2) DSB_DECLARE_LAUNCH(3)
 DSB_DECLARE_LAUNCH(4) DSB_DECLARE_LAUNCH(5) DSB_DECLARE_LAUNCH(6) DSB_DECLARE_LAUNCH(7)
+DSB_DECLARE_LAUNCH(8)
 #undef DSB_DECLARE_LAUNCH

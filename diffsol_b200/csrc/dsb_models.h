@@ -21,6 +21,7 @@ enum dsb_model_id {
     DSB_MODEL_DYDT_Y2 = 5,              // n=10 np=0   test_models/dydt_y2.rs:9-19
     DSB_MODEL_GAUSSIAN_DECAY = 6,       // n=10 np=10  test_models/gaussian_decay.rs:12-23
     DSB_MODEL_VAN_DER_POL = 7,          // n=2  np=1   (not in the reference; BASELINE.json config 3)
+    DSB_MODEL_VAN_DER_POL_SCALED = 8,   // n=2  np=2   the same in scaled time tau = t / T, p = [mu, T]
     DSB_MODEL_COUNT
 };
 
@@ -182,6 +183,27 @@ struct ModelVanDerPol {
     }
 };
 
+// Van der Pol in scaled time tau = t / T: dy/dtau = T f(y; mu), p = [mu, T].  Lets a batch whose instances
+// need different end times T_i (BASELINE config 3: T = max(20, 2 mu)) share one t_eval grid on [0, 1].
+struct ModelVanDerPolScaled {
+    static constexpr int N = 2, NP = 2;
+    static constexpr bool HAS_MASS = false;
+    DSB_HD static void rhs(const double* x, const double* p, double, double* y) {
+        y[0] = p[1] * x[1];
+        y[1] = p[1] * (p[0] * (1.0 - x[0] * x[0]) * x[1] - x[0]);
+    }
+    DSB_HD static void jac_mul(const double* x, const double* p, double, const double* v, double* y) {
+        y[0] = p[1] * v[1];
+        y[1] = p[1] * (p[0] * (-2.0 * x[0] * v[0]) * x[1] + p[0] * (1.0 - x[0] * x[0]) * v[1] - v[0]);
+    }
+    DSB_HD static void mass(const double* x, const double*, double, double beta, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = x[i] + beta * y[i];
+    }
+    DSB_HD static void init(const double*, double, double* y) {
+        y[0] = 2.0; y[1] = 0.0;
+    }
+};
+
 // id -> functor type
 template <int ID> struct dsb_model_by_id;
 template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY> { typedef ModelExpDecay type; };
@@ -192,6 +214,7 @@ template <> struct dsb_model_by_id<DSB_MODEL_ROBERTSON_ODE_G3> { typedef ModelRo
 template <> struct dsb_model_by_id<DSB_MODEL_DYDT_Y2> { typedef ModelDydtY2<10> type; };
 template <> struct dsb_model_by_id<DSB_MODEL_GAUSSIAN_DECAY> { typedef ModelGaussianDecay<10> type; };
 template <> struct dsb_model_by_id<DSB_MODEL_VAN_DER_POL> { typedef ModelVanDerPol type; };
+template <> struct dsb_model_by_id<DSB_MODEL_VAN_DER_POL_SCALED> { typedef ModelVanDerPolScaled type; };
 
 // Compile-time dispatch over the registry: calls f.template operator()<Model>() for `id`.
 template <class F>
@@ -205,6 +228,7 @@ inline bool dsb_dispatch_model(int id, F&& f) {
         case DSB_MODEL_DYDT_Y2: f.template operator()<ModelDydtY2<10>>(); return true;
         case DSB_MODEL_GAUSSIAN_DECAY: f.template operator()<ModelGaussianDecay<10>>(); return true;
         case DSB_MODEL_VAN_DER_POL: f.template operator()<ModelVanDerPol>(); return true;
+        case DSB_MODEL_VAN_DER_POL_SCALED: f.template operator()<ModelVanDerPolScaled>(); return true;
         default: return false;
     }
 }

@@ -1,0 +1,553 @@
+// dsb_sdirk_kernel.cuh -- `problem.tr_bdf2::<LS>()?.solve_dense(t_eval)` / `esdirk34` for every instance
+// of a batch: the same execution model as dsb_bdf_kernel.cuh (one lane per instance, per-lane state
+// machine, warp-level block scheduler, persistent work-fetching grid), applied to the (E)SDIRK loop.
+//
+//   FETCH -> TSTOP(first) -> STEP -> ATTEMPT -> STAGE(i) -> [JAC lazily] -> NEWTON* -> POST
+//         -> STAGE(i+1) ... -> ERRTEST -> (accept) JAC(StepSuccess) -> ACCEPT -> TSTOP -> OUTPUT -> STEP ...
+//                                      -> (reject) JAC(ErrorTestFail) -> ATTEMPT ...
+//         POST (Newton failed) -> JAC(First/SecondConvergenceFail) -> ATTEMPT ...
+//
+// Restated functions (paths relative to /root/reference/crates/diffsol/src):
+//   Sdirk::_new, jacobian_updates, step     ode_solver/sdirk.rs:178-304, 409-543
+//   Rk::_new, start_step_attempt, do_stage_sdirk, predict_stage_sdirk, error_norm, factor, solve_fail,
+//   error_test_fail, step_accepted, handle_tstop, set_stop_time, interpolate_inplace
+//                                            ode_solver/runge_kutta.rs:100-175, 431-441, 466-535, 610-981, 1080-1127
+//   pi_controller_raw                        ode_solver/runge_kutta.rs:1313-1335
+//   SdirkCallable (set_phi, call_inplace, jacobian_inplace, get_f_eval)   op/sdirk.rs:157-292
+//   newton_iteration + NoLineSearch, Convergence   crates/diffsol-nl/src/newton.rs:13-36, line_search.rs:48-69,
+//                                            convergence.rs:64-139
+// Reference quirks kept on purpose: df/dy is evaluated at phi + c * state.y with the phi left over from
+// the last stage (op/sdirk.rs:265-276); JacobianUpdate is fed h, not a_d * h; the first LU is set up lazily
+// inside the first stage and counted as a Checkpoint; the accept test is strict; the safety factor uses the
+// Newton iteration count of the last stage only; the error estimate is filtered through the LU.
+#pragma once
+#include "dsb_lane.cuh"
+
+enum dsb_rk_lane_state {
+    R_FETCH = 0, R_FINISH, R_ERRTEST, R_JAC, R_ACCEPT, R_TSTOP, R_OUTPUT, R_STEP, R_ATTEMPT, R_STAGE, R_NEWTON, R_POST, R_IDLE
+};
+#define DSB_KIND_LAZY 5          // the first reset_jacobian, inside do_stage_sdirk (runge_kutta.rs:661-665)
+#define DSB_RK_MAX_STAGES 4
+
+template <class M>
+struct SdirkLayout {
+    static constexpr int N = M::N, NP = M::NP;
+    static constexpr int O_DIFF = 0;                                // diff[DSB_RK_MAX_STAGES][N]: x_i = h k_i
+    static constexpr int O_J = O_DIFF + DSB_RK_MAX_STAGES * N;      // rhs_jac[col][row]
+    static constexpr int O_M = O_J + N * N;                         // mass_jac[col][row] (DAE only)
+    static constexpr int O_LU = O_M + (M::HAS_MASS ? N * N : 0);    // LU factors
+    static constexpr int O_Y = O_LU + N * N;                        // state.y
+    static constexpr int O_DY = O_Y + N;                            // state.dy
+    static constexpr int O_OY = O_DY + N;                           // old_state.y (last stage value / previous step)
+    static constexpr int O_PHI = O_OY + N;                          // SdirkCallable.phi
+    static constexpr int O_P = O_PHI + N;                           // parameters
+    static constexpr int WORDS = O_P + (NP > 0 ? NP : 1);
+    static constexpr int THREADS = (WORDS * 8 * 128 <= 75 * 1024) ? 128 : (WORDS * 8 * 64 <= 110 * 1024) ? 64 : 32;
+    static constexpr int MIN_BLOCKS = (WORDS * 8 * THREADS * 3 <= 226 * 1024) ? 3 : 1;
+};
+
+template <class M>
+__global__ void __launch_bounds__(SdirkLayout<M>::THREADS, SdirkLayout<M>::MIN_BLOCKS)
+dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __grid_constant__ DsbBatchBuffers bb,
+                             unsigned long long* __restrict__ work_counter) {
+    constexpr int N = M::N;
+    constexpr int NP = M::NP;
+    static_assert(N <= 16, "pivots are packed 4 bits per row");
+    typedef SdirkLayout<M> Lay;
+    extern __shared__ double dsb_lane_smem[];
+    double* const sm = dsb_lane_smem + threadIdx.x;
+#define SM(w) sm[(w) * Lay::THREADS]
+#define SDF(j, i) SM(Lay::O_DIFF + (j) * N + (i))
+#define SJ(j, i) SM(Lay::O_J + (j) * N + (i))
+#define SMM(j, i) SM(Lay::O_M + (j) * N + (i))
+#define SLU(j, i) SM(Lay::O_LU + (j) * N + (i))
+#define SY(i) SM(Lay::O_Y + (i))
+#define SDY(i) SM(Lay::O_DY + (i))
+#define SOY(i) SM(Lay::O_OY + (i))
+#define SPHI(i) SM(Lay::O_PHI + (i))
+#define SP(i) SM(Lay::O_P + (i))
+
+    const int64_t B = pa.nbatch;
+    const int nt = pa.nt;
+    const bool free_running = pa.free_running != 0;
+    const int quorum = pa.quorum;
+    const double eps = 2.220446049250313e-16;
+    const int ns = pa.rk.s;
+    const int start = (pa.rk.a[0] == 0.0) ? 1 : 0;        // skip_first_stage (runge_kutta.rs:286-288)
+    const double cg = pa.rk.a[1 * ns + 1];                // Sdirk::gamma() = a(1, 1)
+
+    // ---- per-lane registers ---------------------------------------------------------------------------
+    int state = R_FETCH;
+    int64_t inst = 0;
+    double t = 0.0, h_state = 0.0, old_t = 0.0;           // state.t, state.h, old_state.t
+    double h = 0.0, op_h = 0.0;                            // step()'s local h, SdirkCallable.h
+    bool has_tstop = false, has_prev_error = false, jacobian_is_stale = true, is_jacobian_set = false;
+    double tstop = 0.0, prev_error_norm = 0.0;
+    LaneJacobianUpdate ju; ju.init(1.0);
+    LaneConvergence conv;
+    conv.tol = pa.opt.nonlinear_solver_tolerance; conv.max_iter = pa.opt.max_nonlinear_solver_iterations;
+    conv.eta = pa.tab.eta_reset; conv.old_norm = 0.0; conv.reset();
+    LaneStats st; st.clear();
+    unsigned long long piv_packed = 0;
+    double x_cur[N], wt[N];                                // Newton iterate (old_state.dy), norm weights from state.y
+#pragma unroll
+    for (int i = 0; i < N; ++i) { x_cur[i] = 0.0; wt[i] = 1.0; }
+    int stage = 0, nattempts = 0, col = 0;
+    bool updated_jacobian = false, newton_ok = false, first = true, reached = false;
+    double t_stage = 0.0, factor = 1.0, error_norm = 0.0;
+    int after_jac = R_NEWTON, jac_kind = DSB_CHECKPOINT;
+    double jac_h = 0.0;
+    int fin_status = DSB_STATUS_OK;
+    auto finish = [&](int status) { fin_status = status; state = R_FINISH; };
+
+    // runge_kutta.rs:752-781.  0 = nothing, 1 = TstopReached, < 0 = -status
+    auto handle_tstop = [&](double ts) -> int {
+        const double troundoff = 100.0 * eps * (dsb_abs(t) + dsb_abs(h_state));
+        if (dsb_abs(t - ts) <= troundoff) return 1;
+        if ((h_state > 0.0 && ts < t - troundoff) || (h_state < 0.0 && ts > t + troundoff)) return -DSB_STATUS_STOP_TIME_BEFORE_CURRENT;
+        if ((h_state > 0.0 && t + h_state > ts + troundoff) || (h_state < 0.0 && t + h_state < ts - troundoff)) {
+            const double f = (ts - t) / h_state;
+            h_state *= f;
+        }
+        return 0;
+    };
+
+    while (true) {
+        // ---- warp-level block scheduler (see dsb_bdf_kernel.cuh) ------------------------------------------
+        const unsigned m_idle = __ballot_sync(0xffffffffu, state == R_IDLE);
+        if (m_idle == 0xffffffffu) break;
+        const int n_active = 32 - __popc(m_idle);
+        const int n_slow = __popc(__ballot_sync(0xffffffffu, state == R_ERRTEST || state == R_JAC || state == R_ACCEPT));
+        const bool run_slow = n_slow > 0 && (n_slow >= quorum || 2 * n_slow >= n_active);
+
+        // ================= FINISH ===============================================================================
+        if (__any_sync(0xffffffffu, state == R_FINISH) && state == R_FINISH) {
+            bb.status[inst] = fin_status;
+            bb.fin_t[inst] = t; bb.fin_h[inst] = h_state; bb.fin_order[inst] = pa.rk.order;
+#pragma unroll
+            for (int k = 0; k < DSB_NSTATS; ++k) bb.stats[(int64_t)k * B + inst] = st.v[k];
+            state = R_FETCH;
+        }
+        // ================= FETCH: next instance; Rk::_new + Sdirk::_new =========================================
+        if (__any_sync(0xffffffffu, state == R_FETCH) && state == R_FETCH) {
+            inst = (int64_t)atomicAdd(work_counter, 1ull);
+            if (inst >= B) {
+                state = R_IDLE;
+            } else if (bb.status[inst] == DSB_STATUS_OK) {
+#pragma unroll
+                for (int j = 0; j < NP; ++j) SP(j) = bb.params[(int64_t)j * B + inst];
+#pragma unroll
+                for (int k = 0; k < DSB_NSTATS; ++k) st.v[k] = bb.stats[(int64_t)k * B + inst];
+                t = pa.t0; h_state = bb.h0[inst]; old_t = t;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double yi = bb.y0[(int64_t)i * B + inst];
+                    SY(i) = yi; SOY(i) = yi; SDY(i) = bb.dy0[(int64_t)i * B + inst]; SPHI(i) = 0.0;
+                    wt[i] = dsb_abs(yi) * pa.rtol + pa.atol[i];
+                }
+#pragma unroll
+                for (int j = 0; j < DSB_RK_MAX_STAGES; ++j)
+#pragma unroll
+                    for (int i = 0; i < N; ++i) SDF(j, i) = 0.0;
+                ju.init(1.0);
+                ju.update_jacobian(h_state);
+                ju.update_rhs_jacobian(h_state);
+                conv.eta = pa.tab.eta_reset; conv.old_norm = 0.0; conv.reset();
+                op_h = h_state;
+                jacobian_is_stale = true; is_jacobian_set = false;
+                has_tstop = false; tstop = 0.0; has_prev_error = false; prev_error_norm = 0.0;
+                first = true; reached = false; col = 0;
+                state = R_TSTOP;
+            }
+        }
+
+        // ================= ERRTEST: embedded error estimate, step-size factor, accept / reject ==================
+        // (sdirk.rs:474-529, runge_kutta.rs:783-800, 466-495)
+        if (run_slow && state == R_ERRTEST) {
+            double err[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) err[k] = SDF(0, k) * pa.rk.d[0];
+#pragma unroll 1
+            for (int j = 1; j < ns; ++j) {
+                const double dj = pa.rk.d[j];
+#pragma unroll
+                for (int k = 0; k < N; ++k) err[k] = SDF(j, k) * dj + err[k];
+            }
+            if (M::HAS_MASS) {
+                double nx[N];
+#pragma unroll
+                for (int k = 0; k < N; ++k) nx[k] = err[k];
+#pragma unroll
+                for (int k = 0; k < N; ++k) err[k] = SMM(0, k) * nx[0];
+#pragma unroll
+                for (int j = 1; j < N; ++j)
+#pragma unroll
+                    for (int k = 0; k < N; ++k) err[k] = SMM(j, k) * nx[j] + err[k];
+            }
+            LaneLU<N> lu;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                lu.piv[j] = (int)((piv_packed >> (4 * j)) & 15ull);
+#pragma unroll
+                for (int i = 0; i < N; ++i) lu.a[j][i] = SLU(j, i);
+            }
+            if (!lu.solve(err)) {
+                finish(DSB_STATUS_LU_SOLVE_FAILED);
+            } else {
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double term = err[i] / wt[i];                 // weights from state.y
+                    acc += term * term;
+                }
+                const double e = acc / (double)N;
+                error_norm = (0.0 < e) ? e : 0.0;
+                const double maxiter = (double)conv.max_iter;
+                const double niter = (double)conv.niter;
+                const double safety_factor = (2.0 * maxiter + 1.0) / (2.0 * maxiter + niter);
+                const double safety = 0.9 * safety_factor;
+                const double order_f = (double)(pa.rk.order + 1);
+                const double ki = pa.opt.pi_control_integral / order_f;
+                const bool p_only = pa.opt.pi_control_proportional == 0.0 || !has_prev_error;
+                const double kp = p_only ? 0.0 : pa.opt.pi_control_proportional / order_f;
+                double raw = dsb_pow(error_norm, p_only ? -ki : -(ki + kp));
+                if (!p_only) raw = raw * dsb_pow(prev_error_norm, kp);
+                double f = safety * raw;
+                if (f > pa.opt.max_timestep_shrink && f < pa.opt.min_timestep_growth) f = 1.0;
+                if (f < pa.opt.min_timestep_shrink) f = pa.opt.min_timestep_shrink;
+                if (f > pa.opt.max_timestep_growth) f = pa.opt.max_timestep_growth;
+                factor = f;
+                if (error_norm < 1.0) {
+                    const double new_h = h * factor;
+                    if (factor != 1.0) conv.eta = pa.tab.eta_reset_timestep;
+                    op_h = new_h;
+                    jac_h = new_h; jac_kind = DSB_STEP_SUCCESS; after_jac = R_ACCEPT;
+                    state = R_JAC;
+                } else {
+                    h *= factor;
+                    conv.eta = pa.tab.eta_reset_timestep;
+                    op_h = h;
+                    jac_h = h; jac_kind = DSB_ERROR_TEST_FAIL; after_jac = R_ATTEMPT;
+                    state = R_JAC;
+                }
+            }
+        }
+
+        // ================= JAC: Sdirk::jacobian_updates(h, kind) / the lazy first reset_jacobian ================
+        if (run_slow && state == R_JAC) {
+            bool do_factor = false;
+            double t_jac = t;
+            if (jac_kind == DSB_KIND_LAZY) {
+                do_factor = true;
+                t_jac = t_stage;
+                st.record_linear_solver_setup(DSB_CHECKPOINT);
+            } else if (ju.check_rhs_jacobian_update(pa.opt, jac_h, jac_kind)) {
+                jacobian_is_stale = true;
+                ju.update_rhs_jacobian(jac_h);
+                ju.update_jacobian(jac_h);
+                do_factor = true;
+            } else if (ju.check_jacobian_update(pa.opt, jac_h, jac_kind)) {
+                ju.update_jacobian(jac_h);
+                do_factor = true;
+            }
+            if (do_factor) {
+                if (jac_kind != DSB_KIND_LAZY) {
+                    conv.eta = pa.tab.eta_reset;
+                    st.record_linear_solver_setup(jac_kind);
+                }
+                LaneLU<N> lu;
+                double pl[NP > 0 ? NP : 1];
+#pragma unroll
+                for (int j = 0; j < NP; ++j) pl[j] = SP(j);
+                if (jacobian_is_stale) {
+                    double tmpv[N];                                      // set_tmp: phi + c * x with x = state.y
+#pragma unroll
+                    for (int i = 0; i < N; ++i) tmpv[i] = cg * SY(i) + SPHI(i);
+                    lane_jacobian<M>(pa, tmpv, pl, t_jac, lu.a, st);
+#pragma unroll
+                    for (int j = 0; j < N; ++j)
+#pragma unroll
+                        for (int i = 0; i < N; ++i) SJ(j, i) = lu.a[j][i];
+                    if (M::HAS_MASS) {
+                        lane_mass_matrix<M>(pl, t_jac, lu.a);
+#pragma unroll
+                        for (int j = 0; j < N; ++j)
+#pragma unroll
+                            for (int i = 0; i < N; ++i) SMM(j, i) = lu.a[j][i];
+                    }
+                    jacobian_is_stale = false;
+                }
+                const double beta = -(cg * op_h);
+#pragma unroll
+                for (int j = 0; j < N; ++j)
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const double m_ji = M::HAS_MASS ? SMM(j, i) : ((i == j) ? 1.0 : 0.0);
+                        lu.a[j][i] = SJ(j, i) * beta + m_ji;
+                    }
+                lu.factor();
+                piv_packed = 0;
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    piv_packed |= (unsigned long long)lu.piv[j] << (4 * j);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) SLU(j, i) = lu.a[j][i];
+                }
+                is_jacobian_set = true;
+            }
+            state = after_jac;
+            if (jac_kind != DSB_KIND_LAZY && jac_kind != DSB_STEP_SUCCESS) {
+                // the failure paths continue after jacobian_updates (sdirk.rs:464-471, 524-529)
+                has_prev_error = false;
+                if (jac_kind == DSB_ERROR_TEST_FAIL) {
+                    nattempts += 1;
+                    st.v[DSB_STAT_ERROR_TEST_FAILURES] += 1;
+                    if (nattempts >= pa.opt.max_error_test_failures) finish(DSB_STATUS_TOO_MANY_ERROR_TEST_FAILURES);
+                    else if (dsb_abs(h) < pa.opt.min_timestep) finish(DSB_STATUS_STEP_SIZE_TOO_SMALL);
+                } else {
+                    st.v[DSB_STAT_NONLINEAR_SOLVER_FAILS] += 1;
+                    if (st.v[DSB_STAT_NONLINEAR_SOLVER_FAILS] > pa.opt.max_nonlinear_solver_failures)
+                        finish(DSB_STATUS_TOO_MANY_NONLINEAR_FAILURES);
+                    else if (dsb_abs(h) < pa.opt.min_timestep) finish(DSB_STATUS_STEP_SIZE_TOO_SMALL);
+                }
+            }
+        }
+
+        // ================= ACCEPT: rest of the accepted path + Rk::step_accepted (runge_kutta.rs:894-960) ========
+        if (run_slow && state == R_ACCEPT) {
+            ju.step();
+            has_prev_error = true; prev_error_norm = error_norm;
+            const double new_h = h * factor;
+            const double inv_h = 1.0 / h;
+            old_t = t;
+            t = t + h;
+            h_state = new_h;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double y_new = SOY(i);                 // old_state.y held the last stage value
+                SOY(i) = SY(i);                              // swap: old_state <- previous state
+                SY(i) = y_new;
+                SDY(i) = x_cur[i] * inv_h;                   // old_state.dy *= 1/h, then swapped in
+                wt[i] = dsb_abs(y_new) * pa.rtol + pa.atol[i];
+            }
+            st.v[DSB_STAT_STEPS] += 1;
+            state = R_TSTOP;
+        }
+
+        // ================= TSTOP: set_stop_time (first) / handle_tstop after an accepted step ===================
+        if (__any_sync(0xffffffffu, state == R_TSTOP) && state == R_TSTOP) {
+            int r = 0;
+            int next = first ? R_STEP : R_OUTPUT;
+            if (first) {
+                if (free_running) next = R_OUTPUT;
+                else {
+                    has_tstop = true; tstop = bb.t_eval[nt - 1];
+                    r = handle_tstop(tstop);
+                    if (r == 1) r = -DSB_STATUS_STOP_TIME_AT_CURRENT;
+                }
+            } else if (has_tstop) {
+                r = handle_tstop(tstop);
+                if (r == 1) { reached = true; has_tstop = false; }
+            }
+            if (r < 0) finish(-r);
+            else state = next;
+            first = false;
+        }
+
+        // ================= OUTPUT: dense output (method.rs:761-764, 822-848; runge_kutta.rs:1080-1127) ==========
+        if (__any_sync(0xffffffffu, state == R_OUTPUT) && state == R_OUTPUT) {
+            int status = DSB_STATUS_OK;
+            while (col < nt) {
+                const double tq = bb.t_eval[col];
+                if (free_running ? (dsb_abs(t) < dsb_abs(tq)) : !(tq <= t)) break;
+                const bool is_forward = h_state > 0.0;
+                if ((is_forward && (tq > t || tq < old_t)) || (!is_forward && (tq < t || tq > old_t))) {
+                    status = DSB_STATUS_INTERPOLATION_TIME_AFTER_CURRENT; break;
+                }
+                const double dt = t - old_t;
+                const double theta = (dt == 0.0) ? 1.0 : (tq - old_t) / dt;
+                double yo[N];
+                if (pa.rk.has_beta) {
+                    const double th2 = theta * theta;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) yo[i] = SOY(i);
+#pragma unroll 1
+                    for (int j = 0; j < ns; ++j) {
+                        double bf = pa.rk.beta[j] * theta;
+                        bf = pa.rk.beta[ns + j] * th2 + bf;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) yo[i] = SDF(j, i) * bf + yo[i];
+                    }
+                } else {
+                    const double al1 = theta - 1.0, be1 = 1.0 - 2.0 * theta;
+                    const double al2 = 1.0 - theta, be2 = theta * (theta - 1.0);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const double u0 = SOY(i), u1 = SY(i);
+                        double v = u1;
+                        v -= u0;
+                        v = al1 * SDF(0, i) + be1 * v;
+                        v = theta * SDF(ns - 1, i) + v;
+                        v = al2 * u0 + be2 * v;
+                        v = theta * u1 + v;
+                        yo[i] = v;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
+                ++col;
+            }
+            if (status != DSB_STATUS_OK) finish(status);
+            else if (free_running ? (col >= nt) : reached) finish(DSB_STATUS_OK);
+            else state = R_STEP;
+        }
+
+        // ================= STEP: start of Sdirk::step (sdirk.rs:415-431) ========================================
+        if (__any_sync(0xffffffffu, state == R_STEP) && state == R_STEP) {
+            h = h_state;
+            if (dsb_abs(h) < pa.opt.min_timestep) finish(DSB_STATUS_STEP_SIZE_TOO_SMALL);
+            else {
+                op_h = h;
+                nattempts = 0; updated_jacobian = false;
+                state = R_ATTEMPT;
+            }
+        }
+        // ================= ATTEMPT: start_step_attempt (runge_kutta.rs:505-535) =================================
+        if (__any_sync(0xffffffffu, state == R_ATTEMPT) && state == R_ATTEMPT) {
+            if (start == 1) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) SDF(0, k) = h * SDY(k);
+            }
+            stage = start;
+            state = R_STAGE;
+        }
+        // ================= STAGE: set_phi + predict_stage_sdirk (runge_kutta.rs:645-665) ========================
+        if (__any_sync(0xffffffffu, state == R_STAGE) && state == R_STAGE) {
+            const int i = stage;
+            t_stage = t + pa.rk.c[i] * h;
+            double ph[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) ph[k] = SY(k);
+#pragma unroll 1
+            for (int j = 0; j < i; ++j) {
+                const double aij = pa.rk.a[j * ns + i];
+#pragma unroll
+                for (int k = 0; k < N; ++k) ph[k] = SDF(j, k) * aij + ph[k];
+            }
+#pragma unroll
+            for (int k = 0; k < N; ++k) SPHI(k) = ph[k];
+            if (i == 0) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) x_cur[k] = h * SDY(k);
+            } else if (i == 1) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) x_cur[k] = SDF(0, k);
+            } else {
+                const double cc = (pa.rk.c[i] - pa.rk.c[i - 2]) / (pa.rk.c[i - 1] - pa.rk.c[i - 2]);
+                const double al = -cc, be = 1.0 + cc;
+#pragma unroll
+                for (int k = 0; k < N; ++k) x_cur[k] = al * SDF(i - 2, k) + be * SDF(i - 1, k);
+            }
+            conv.reset();
+            if (!is_jacobian_set) { jac_kind = DSB_KIND_LAZY; after_jac = R_NEWTON; state = R_JAC; }
+            else state = R_NEWTON;
+        }
+
+        // ================= NEWTON: one iteration on F(x) = M x - h f(phi + c x) =================================
+        if (__any_sync(0xffffffffu, state == R_NEWTON) && state == R_NEWTON) {
+            double pl[NP > 0 ? NP : 1];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) pl[j] = SP(j);
+            double delta[N];
+            {
+                double tmpv[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) tmpv[i] = cg * x_cur[i] + SPHI(i);
+                M::rhs(tmpv, pl, t_stage, delta);
+                st.v[DSB_STAT_RHS_CALLS] += 1;
+                const double beta = -op_h;
+                if (M::HAS_MASS) {
+                    M::mass(x_cur, pl, t_stage, beta, delta);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) delta[i] = x_cur[i] + beta * delta[i];
+                }
+            }
+            LaneLU<N> lu;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                lu.piv[j] = (int)((piv_packed >> (4 * j)) & 15ull);
+#pragma unroll
+                for (int i = 0; i < N; ++i) lu.a[j][i] = SLU(j, i);
+            }
+            if (!lu.solve(delta)) {
+                newton_ok = false; state = R_POST;
+            } else {
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    x_cur[i] -= delta[i];
+                    const double term = delta[i] / wt[i];
+                    acc += term * term;
+                }
+                const double norm = dsb_sqrt(acc / (double)N);
+                conv.niter += 1;
+                const bool have_rate = conv.has_old_norm;
+                double px, py;
+                if (have_rate) { px = norm / conv.old_norm; py = 1.0 / (double)(conv.niter - 1); }
+                else { const double min_eta = 1e4 * eps; px = (conv.eta < min_eta) ? min_eta : conv.eta; py = 0.8; }
+                const double pw = dsb_pow(px, py);
+                int s = LANE_CONTINUE;
+                if (have_rate) {
+                    const double rate = pw;
+                    if (rate > 0.9) s = LANE_DIVERGED;
+                    else if (dsb_powi(rate, conv.max_iter - conv.niter) / (1.0 - rate) * norm > conv.tol) s = LANE_DIVERGED;
+                    else conv.eta = rate / (1.0 - rate);
+                } else {
+                    conv.eta = pw;
+                }
+                if (s != LANE_DIVERGED && conv.eta * norm < conv.tol) s = LANE_CONVERGED;
+                if (conv.niter == 1) { conv.has_old_norm = true; conv.old_norm = norm; }
+                if (s == LANE_CONVERGED) { newton_ok = true; state = R_POST; }
+                else if (s == LANE_DIVERGED || conv.niter >= conv.max_iter) { newton_ok = false; state = R_POST; }
+            }
+        }
+
+        // ================= POST: a stage's Newton solve ended (runge_kutta.rs:674-679, sdirk.rs:436-472) ========
+        if (__any_sync(0xffffffffu, state == R_POST) && state == R_POST) {
+            st.v[DSB_STAT_NONLINEAR_SOLVER_ITERATIONS] += conv.niter;
+            if (newton_ok) {
+                const int i = stage;
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    SOY(k) = cg * x_cur[k] + SPHI(k);          // get_f_eval: stage value
+                    SDF(i, k) = x_cur[k];
+                }
+                stage = i + 1;
+                state = (stage < ns) ? R_STAGE : R_ERRTEST;
+            } else {
+                if (!updated_jacobian) {
+                    updated_jacobian = true;
+                    jac_kind = DSB_FIRST_CONVERGENCE_FAIL;
+                } else {
+                    h *= 0.3;
+                    conv.eta = pa.tab.eta_reset_timestep;
+                    op_h = h;
+                    jac_kind = DSB_SECOND_CONVERGENCE_FAIL;
+                }
+                jac_h = h; after_jac = R_ATTEMPT;
+                state = R_JAC;
+            }
+        }
+    }
+#undef SM
+#undef SDF
+#undef SJ
+#undef SMM
+#undef SLU
+#undef SY
+#undef SDY
+#undef SOY
+#undef SPHI
+#undef SP
+}

@@ -47,6 +47,17 @@ def van_der_pol_sweep(indices):
     return (10.0 ** (6.0 * uniform(idx, 0))).reshape(-1, 1)
 
 
+def van_der_pol_scaled_sweep(indices):
+    """Config 3 with per-instance end time T = max(20, 2 mu) folded into the equations (model
+    van_der_pol_scaled, scaled time tau = t / T in [0, 1]) -> params[len, 2] = [mu, T]."""
+    mu = van_der_pol_sweep(indices)[:, 0]
+    return np.stack([mu, np.maximum(20.0, 2.0 * mu)], axis=1)
+
+
+VAN_DER_POL_T_EVAL = np.arange(1, 9) / 8.0            # 8 equally spaced points in scaled time
+VAN_DER_POL_TOL = dict(rtol=1e-4, atol=[1e-6])
+
+
 def shard_indices(nbatch, rank, world):
     """Instance i -> rank i mod world (interleaved keeps a parameter-sorted sweep balanced)."""
     return np.arange(rank, nbatch, world, dtype=np.int64)

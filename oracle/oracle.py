@@ -39,6 +39,7 @@ MODELS = {
     "dydt_y2": 5,
     "gaussian_decay": 6,
     "van_der_pol": 7,
+    "van_der_pol_scaled": 8,
 }
 
 
