@@ -33,8 +33,11 @@ def all_gather_batch_major(local, nbatch):
         padded = local.new_zeros(lead + (bmax,))
         padded[..., : local.shape[-1]] = local
     padded = padded.contiguous()
-    out = padded.new_empty((G,) + tuple(padded.shape))
-    dist.all_gather_into_tensor(out, padded)
+    # concatenation along dim 0 is the one output layout every backend (NCCL, gloo) accepts
+    flat = padded.reshape(-1)
+    out = flat.new_empty(G * flat.numel())
+    dist.all_gather_into_tensor(out, flat)
+    out = out.view((G,) + tuple(padded.shape))
     # out[r, ..., k] is global instance r + G k  ->  [..., k, r] -> flatten
     out = out.movedim(0, -1).reshape(lead + (bmax * G,))
     return out[..., :nbatch]
