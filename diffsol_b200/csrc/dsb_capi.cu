@@ -619,4 +619,18 @@ int dsb_lu_solve_batched(const double* lu_dev, const int32_t* piv_dev, double* b
     return DSB_OK;
 }
 
+int dsb_lu_factor_instance_major(double* a_dev, int32_t n, int64_t nbatch, int32_t* piv_dev, int32_t* info_dev, void* stream) {
+    if (!a_dev || !piv_dev || !info_dev || n < 1 || nbatch < 1) return fail(DSB_BAD_ARG, "bad argument to dsb_lu_factor_instance_major");
+    cudaError_t e = dsb_launch_lu_factor_im(a_dev, n, nbatch, piv_dev, info_dev, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(DSB_ERR, std::string("dsb_lu_factor_instance_major: ") + cudaGetErrorString(e));
+    return DSB_OK;
+}
+int dsb_lu_solve_instance_major(const double* lu_dev, const int32_t* piv_dev, double* b_dev, int32_t n, int64_t nbatch,
+                                int32_t* info_dev, void* stream) {
+    if (!lu_dev || !piv_dev || !b_dev || !info_dev || n < 1 || nbatch < 1) return fail(DSB_BAD_ARG, "bad argument to dsb_lu_solve_instance_major");
+    cudaError_t e = dsb_launch_lu_solve_im(lu_dev, piv_dev, b_dev, n, nbatch, info_dev, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(DSB_ERR, std::string("dsb_lu_solve_instance_major: ") + cudaGetErrorString(e));
+    return DSB_OK;
+}
+
 }  // extern "C"

@@ -1,0 +1,257 @@
+// dsb_coop.cuh -- block-cooperative (one thread block per instance) building blocks for systems too large
+// for the one-thread-per-instance kernels (n > 16): dense LU with partial pivoting and the two triangular
+// solves, with the matrix in global memory (column-major, leading dimension n: 512 KB at n = 256 does not
+// fit in shared memory) and panels staged through shared memory.
+//
+// Arithmetic is the nalgebra 0.35 LU the reference calls (diffsol-la/src/linear_solver/nalgebra/lu.rs:31-51):
+// first maximum as pivot, reciprocal-pivot scaling of the sub-column, rank-1 updates `a = (-u) * l + a`
+// applied to every element in ascending pivot order, column-axpy substitutions.  The factorisation is
+// BLOCKED (panel width 32: the trailing matrix is streamed through the SM once per panel instead of once
+// per column) but every element still receives exactly the same sequence of unfused multiply / add
+// operations as in the unblocked right-looking algorithm, so factors, pivots and solutions are bit-identical
+// to the CPU path.  (Deferring a panel's row swaps for the columns outside the panel moves elements before
+// they are updated instead of after; the multiplier and the pivot-row entry an element meets at step i are
+// the same either way.)  FP64 tensor-core MMA is deliberately NOT used for the trailing update: DMMA fuses
+// the multiply-add and would change the rounding of every element.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dsb_math.h"
+
+#define DSB_COOP_NB 32            // panel width
+#define DSB_COOP_MAX_N 512
+
+// Shared-memory scratch of one block: a panel of up to n x NB doubles + reduction scratch.
+struct CoopScratch {
+    double* panel;     // [NB][m] column-major, m = rows below and including the panel's first row
+    double* redv;      // [32] per-warp partial maxima
+    int* redi;         // [32]
+    int* bcast;        // [4] broadcast words
+};
+
+__device__ __forceinline__ size_t coop_lu_smem_bytes(int n) {
+    return (size_t)n * DSB_COOP_NB * sizeof(double) + 32 * sizeof(double) + 32 * sizeof(int) + 4 * sizeof(int);
+}
+inline size_t coop_lu_smem_bytes_host(int n) {
+    return (size_t)n * DSB_COOP_NB * sizeof(double) + 32 * sizeof(double) + 32 * sizeof(int) + 4 * sizeof(int);
+}
+
+__device__ __forceinline__ CoopScratch coop_carve(void* smem, int n) {
+    CoopScratch s;
+    s.panel = (double*)smem;
+    s.redv = s.panel + (size_t)n * DSB_COOP_NB;
+    s.redi = (int*)(s.redv + 32);
+    s.bcast = s.redi + 32;
+    return s;
+}
+
+// In-place LU of the n x n column-major matrix A (global memory, leading dimension n) by the whole block.
+// piv[i] = row swapped with row i (== i: no swap).  Returns (to every thread) 0, or k+1 for the first
+// zero pivot column k (nalgebra leaves that column untouched and continues).
+__device__ int coop_lu_factor(double* __restrict__ A, int n, int* __restrict__ piv, const CoopScratch& sc) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int lane = tid & 31, wid = tid >> 5, nwarps = (T + 31) >> 5;
+    int first_bad = 0;
+    for (int k0 = 0; k0 < n; k0 += DSB_COOP_NB) {
+        const int kb = (n - k0 < DSB_COOP_NB) ? (n - k0) : DSB_COOP_NB;
+        const int m = n - k0;                        // panel rows
+        double* P = sc.panel;                        // P[c * m + lr]
+        // ---- 1. stage the panel ----
+        for (int c = 0; c < kb; ++c)
+            for (int lr = tid; lr < m; lr += T) P[(size_t)c * m + lr] = A[(size_t)(k0 + c) * n + k0 + lr];
+        __syncthreads();
+        // ---- 2. factor the panel (unblocked, in shared memory) ----
+        for (int i = 0; i < kb; ++i) {
+            // pivot = first maximum of |P[i][lr]|, lr >= i (NaNs below the diagonal never win; a NaN on the
+            // diagonal keeps the diagonal, as `val > the_max` is false for every candidate)
+            double bv = -1.0; int bi = 0x7fffffff;
+            for (int lr = i + tid; lr < m; lr += T) {
+                const double v = dsb_abs(P[(size_t)i * m + lr]);
+                if (v > bv) { bv = v; bi = lr; }        // ascending lr per thread: keeps the first maximum
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) { sc.redv[wid] = bv; sc.redi[wid] = bi; }
+            __syncthreads();
+            if (wid == 0) {
+                bv = (lane < nwarps) ? sc.redv[lane] : -1.0;
+                bi = (lane < nwarps) ? sc.redi[lane] : 0x7fffffff;
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                if (lane == 0) {
+                    const double dii = P[(size_t)i * m + i];
+                    int p = bi;
+                    if (dii != dii) p = i;                             // NaN diagonal: the_max = NaN, never replaced
+                    const double diag = P[(size_t)i * m + p];
+                    const int ok = (diag == 0.0) ? 0 : 1;
+                    if (!ok) p = i;
+                    sc.bcast[0] = p; sc.bcast[1] = ok;
+                    piv[k0 + i] = k0 + p;
+                }
+            }
+            __syncthreads();
+            const int p = sc.bcast[0];
+            const int ok = sc.bcast[1];
+            if (!ok) { if (first_bad == 0) first_bad = k0 + i + 1; __syncthreads(); continue; }
+            if (p != i) {
+                for (int c = tid; c < kb; c += T) {
+                    const double tmp = P[(size_t)c * m + i]; P[(size_t)c * m + i] = P[(size_t)c * m + p]; P[(size_t)c * m + p] = tmp;
+                }
+            }
+            __syncthreads();
+            const double inv_diag = 1.0 / P[(size_t)i * m + i];
+            for (int lr = i + 1 + tid; lr < m; lr += T) P[(size_t)i * m + lr] *= inv_diag;
+            __syncthreads();
+            // rank-1 update of the remaining panel columns
+            const int ncols = kb - i - 1, nrows = m - i - 1;
+            for (int e = tid; e < ncols * nrows; e += T) {
+                const int c = i + 1 + e / nrows, lr = i + 1 + e % nrows;
+                const double mpk = -P[(size_t)c * m + i];
+                P[(size_t)c * m + lr] = mpk * P[(size_t)i * m + lr] + P[(size_t)c * m + lr];
+            }
+            __syncthreads();
+        }
+        // ---- 3. write the panel back ----
+        for (int c = 0; c < kb; ++c)
+            for (int lr = tid; lr < m; lr += T) A[(size_t)(k0 + c) * n + k0 + lr] = P[(size_t)c * m + lr];
+        // ---- 4. row swaps for the columns outside the panel; U12 = L11^-1 A12 (one thread per column) ----
+        for (int c = tid; c < n; c += T) {
+            if (c >= k0 && c < k0 + kb) continue;
+            double* col = A + (size_t)c * n;
+            for (int i = 0; i < kb; ++i) {
+                const int p = piv[k0 + i];
+                if (p != k0 + i) { const double tmp = col[k0 + i]; col[k0 + i] = col[p]; col[p] = tmp; }
+            }
+            if (c >= k0 + kb) {
+                for (int i = 0; i < kb; ++i) {
+                    const double mpk = -col[k0 + i];
+                    for (int r = i + 1; r < kb; ++r) col[k0 + r] = mpk * P[(size_t)i * m + r] + col[k0 + r];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 5. trailing update A22[r][c] = sum_i (-U[i][c]) * L[r][i] + A22[r][c], i ascending ----
+        const int r0 = k0 + kb;
+        const int m2 = n - r0;
+        if (m2 > 0) {
+            // warps own columns; lanes own rows in chunks of 32; L21 rows are read from the staged panel
+            for (int rc = 0; rc < m2; rc += 32) {
+                const int r = r0 + rc + lane;
+                const bool live = r < n;
+                double l[DSB_COOP_NB];
+#pragma unroll
+                for (int i = 0; i < DSB_COOP_NB; ++i) l[i] = (live && i < kb) ? P[(size_t)i * m + (r - k0)] : 0.0;
+                for (int c = r0 + wid; c < n; c += nwarps) {
+                    double* col = A + (size_t)c * n;
+                    double a = live ? col[r] : 0.0;
+                    if (kb == DSB_COOP_NB) {
+#pragma unroll
+                        for (int i = 0; i < DSB_COOP_NB; ++i) { const double mpk = -col[k0 + i]; a = mpk * l[i] + a; }
+                    } else {
+                        for (int i = 0; i < kb; ++i) { const double mpk = -col[k0 + i]; a = mpk * l[i] + a; }
+                    }
+                    if (live) col[r] = a;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    return first_bad;
+}
+
+// Solve with the factors of coop_lu_factor; b lives in SHARED memory (n doubles).  Returns false (to every
+// thread) when U has a zero on its diagonal (nalgebra's solve_mut returns false; b is then unspecified).
+__device__ bool coop_lu_solve(const double* __restrict__ LU, int n, const int* __restrict__ piv, double* b,
+                              const CoopScratch& sc) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    if (tid == 0) {
+        for (int i = 0; i < n; ++i) { const int p = piv[i]; if (p != i) { const double tmp = b[i]; b[i] = b[p]; b[p] = tmp; } }
+        sc.bcast[2] = 1;
+    }
+    __syncthreads();
+    // forward substitution with the unit lower triangle, column-axpy form, in blocks of 32 columns
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int kb = (n - k0 < 32) ? (n - k0) : 32;
+        if (tid < 32) {                                   // diagonal block: one warp, lane = row within the block
+            const int r = k0 + tid;
+            double br = (tid < kb) ? b[r] : 0.0;
+            for (int i = 0; i < kb; ++i) {
+                const double coeff = __shfl_sync(0xffffffffu, br, i);
+                if (tid > i && tid < kb) br = (-coeff) * LU[(size_t)(k0 + i) * n + r] + br;
+            }
+            if (tid < kb) b[r] = br;
+        }
+        __syncthreads();
+        for (int r = k0 + kb + tid; r < n; r += T) {      // rows below: each row accumulates in ascending i
+            double br = b[r];
+            for (int i = 0; i < kb; ++i) br = (-b[k0 + i]) * LU[(size_t)(k0 + i) * n + r] + br;
+            b[r] = br;
+        }
+        __syncthreads();
+    }
+    // back substitution with U, column-axpy form, blocks of 32 columns from the bottom
+    const int nblk = (n + 31) / 32;
+    for (int kbk = nblk - 1; kbk >= 0; --kbk) {
+        const int k0 = kbk * 32;
+        const int kb = (n - k0 < 32) ? (n - k0) : 32;
+        if (tid < 32) {
+            const int r = k0 + tid;
+            double br = (tid < kb) ? b[r] : 0.0;
+            bool ok = true;
+            for (int i = kb - 1; i >= 0; --i) {
+                const double diag = LU[(size_t)(k0 + i) * n + k0 + i];
+                if (diag == 0.0) { ok = false; break; }           // uniform across the warp
+                double coeff = 0.0;
+                if (tid == i) { coeff = br / diag; br = coeff; }
+                coeff = __shfl_sync(0xffffffffu, coeff, i);
+                if (tid < i) br = (-coeff) * LU[(size_t)(k0 + i) * n + r] + br;
+            }
+            if (tid < kb) b[r] = br;
+            if (!ok && tid == 0) sc.bcast[2] = 0;
+        }
+        __syncthreads();
+        if (sc.bcast[2] == 0) return false;
+        for (int r = tid; r < k0; r += T) {               // rows above: ascending order of application is i DESCENDING
+            double br = b[r];
+            for (int i = kb - 1; i >= 0; --i) br = (-b[k0 + i]) * LU[(size_t)(k0 + i) * n + r] + br;
+            b[r] = br;
+        }
+        __syncthreads();
+    }
+    return true;
+}
+
+// ---- stand-alone kernels: the LinearSolver pair for instance-major storage ------------------------------
+// a: [nbatch][n*n] column-major per instance (the layout of the reference's CUDA matrices,
+// diffsol-la/src/matrix/cuda.rs), piv: [nbatch][n], rhs: [nbatch][n].
+__global__ void dsb_lu_factor_coop_kernel(double* __restrict__ a, int n, int64_t B, int32_t* __restrict__ piv,
+                                          int32_t* __restrict__ info) {
+    extern __shared__ unsigned char dsb_coop_smem[];
+    const CoopScratch sc = coop_carve(dsb_coop_smem, n);
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        const int bad = coop_lu_factor(a + (size_t)b * n * n, n, piv + (size_t)b * n, sc);
+        if (threadIdx.x == 0) info[b] = bad;
+        __syncthreads();
+    }
+}
+__global__ void dsb_lu_solve_coop_kernel(const double* __restrict__ a, const int32_t* __restrict__ piv,
+                                         double* __restrict__ rhs, int n, int64_t B, int32_t* __restrict__ info) {
+    extern __shared__ unsigned char dsb_coop_smem[];
+    const CoopScratch sc = coop_carve(dsb_coop_smem, n);
+    double* bs = sc.panel;                               // the panel area doubles as the right-hand side buffer
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) bs[i] = rhs[(size_t)b * n + i];
+        __syncthreads();
+        const bool ok = coop_lu_solve(a + (size_t)b * n * n, n, piv + (size_t)b * n, bs, sc);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) rhs[(size_t)b * n + i] = bs[i];
+        if (threadIdx.x == 0) info[b] = ok ? 0 : 1;
+        __syncthreads();
+    }
+}

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dsb_coop.cuh"
 #include "dsb_lane.cuh"
 
 // Small systems: the whole matrix in registers (static indices after unrolling).
@@ -143,5 +144,42 @@ inline cudaError_t dsb_launch_lu_solve(const double* a, const int32_t* piv, doub
         case 8: dsb_lu_solve_reg_kernel<8><<<blocks, threads, 0, s>>>(a, piv, rhs, B, info); break;
         default: dsb_lu_solve_gmem_kernel<<<blocks, threads, 0, s>>>(a, piv, rhs, n, B, info); break;
     }
+    return cudaGetLastError();
+}
+
+// ---- instance-major storage (each instance's n x n column-major matrix contiguous): block-cooperative LU ----
+inline int dsb_coop_threads(int n) { int t = ((n + 31) / 32) * 32; return t > 256 ? 256 : t; }
+inline cudaError_t dsb_coop_grid(const void* kernel, int threads, size_t smem, int64_t B, unsigned* grid) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const int64_t resident = (int64_t)sms * per_sm;
+    *grid = (unsigned)(B < resident ? B : resident);
+    return cudaSuccess;
+}
+inline cudaError_t dsb_launch_lu_factor_im(double* a, int n, int64_t B, int32_t* piv, int32_t* info, cudaStream_t s) {
+    if (n > DSB_COOP_MAX_N) return cudaErrorInvalidValue;
+    const int threads = dsb_coop_threads(n);
+    const size_t smem = coop_lu_smem_bytes_host(n);
+    unsigned grid = 1;
+    cudaError_t e = dsb_coop_grid((const void*)dsb_lu_factor_coop_kernel, threads, smem, B, &grid);
+    if (e != cudaSuccess) return e;
+    dsb_lu_factor_coop_kernel<<<grid, threads, smem, s>>>(a, n, B, piv, info);
+    return cudaGetLastError();
+}
+inline cudaError_t dsb_launch_lu_solve_im(const double* a, const int32_t* piv, double* rhs, int n, int64_t B, int32_t* info,
+                                          cudaStream_t s) {
+    if (n > DSB_COOP_MAX_N) return cudaErrorInvalidValue;
+    const int threads = dsb_coop_threads(n);
+    const size_t smem = coop_lu_smem_bytes_host(n);
+    unsigned grid = 1;
+    cudaError_t e = dsb_coop_grid((const void*)dsb_lu_solve_coop_kernel, threads, smem, B, &grid);
+    if (e != cudaSuccess) return e;
+    dsb_lu_solve_coop_kernel<<<grid, threads, smem, s>>>(a, piv, rhs, n, B, info);
     return cudaGetLastError();
 }

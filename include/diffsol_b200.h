@@ -187,6 +187,14 @@ int dsb_lu_factor_batched(double* a_dev, int32_t n, int64_t nbatch, int32_t* piv
 int dsb_lu_solve_batched(const double* lu_dev, const int32_t* piv_dev, double* b_dev, int32_t n, int64_t nbatch,
                          int32_t* info_dev, void* stream);
 
+/* The same pair for INSTANCE-major storage, the layout of the reference's own CUDA matrices
+ * (diffsol-la/src/matrix/cuda.rs: instance b's column-major n x n block at a + b*n*n; vectors at b*n,
+ * diffsol-la/src/vector/cuda.rs:119-130): one thread block per instance, panels of 32 columns staged
+ * through shared memory, n <= 512.  piv_dev: [nbatch][n]; b_dev: [nbatch][n]. */
+int dsb_lu_factor_instance_major(double* a_dev, int32_t n, int64_t nbatch, int32_t* piv_dev, int32_t* info_dev, void* stream);
+int dsb_lu_solve_instance_major(const double* lu_dev, const int32_t* piv_dev, double* b_dev, int32_t n, int64_t nbatch,
+                                int32_t* info_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

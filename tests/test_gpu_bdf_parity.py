@@ -200,3 +200,48 @@ def test_batched_lu_matches_nalgebra_restatement(dsb, oracle, n):
         assert (rc != 0) == (info2[b] != 0), b
         if rc == 0:
             assert np.array_equal(x_g[b], x_o), b
+
+
+@pytest.mark.parametrize("n", [9, 17, 32, 33, 64, 100, 200, 256])
+def test_cooperative_lu_matches_nalgebra_restatement(dsb, oracle, n):
+    """dsb_lu_factor_instance_major / dsb_lu_solve_instance_major (one thread block per instance, blocked
+    with 32-column panels) still give nalgebra's factors, pivots and solutions bit for bit."""
+    import torch
+    from diffsol_b200 import capi
+    rng = np.random.default_rng(1000 + n)
+    B = 37
+    A = rng.standard_normal((B, n, n))               # A[b][i][j]
+    A[3] = 0.0                                       # singular
+    A[4, :, 0] = 0.0                                 # zero first column: skipped by nalgebra
+    A[5, :, n // 2] = 0.0                            # zero column in the middle (becomes zero after elimination only if...)
+    A[6] = np.triu(A[6])                             # already upper triangular: no swaps needed below diagonal
+    A[7] = A[7] * (10.0 ** rng.uniform(-8, 8, size=(n, 1)))   # badly scaled rows: lots of pivoting
+    rhs = rng.standard_normal((B, n))
+    dev = torch.device("cuda:0")
+    a_dev = torch.from_numpy(np.ascontiguousarray(A.transpose(0, 2, 1))).to(dev)      # [b][j][i] = column-major per instance
+    b_dev = torch.from_numpy(rhs.copy()).to(dev)
+    piv = torch.zeros((B, n), dtype=torch.int32, device=dev)
+    info = torch.zeros(B, dtype=torch.int32, device=dev)
+    info2 = torch.zeros(B, dtype=torch.int32, device=dev)
+    L = capi.lib()
+    vp = ctypes.c_void_p
+    capi.check(L.dsb_lu_factor_instance_major(vp(a_dev.data_ptr()), n, B, vp(piv.data_ptr()), vp(info.data_ptr()), None))
+    capi.check(L.dsb_lu_solve_instance_major(vp(a_dev.data_ptr()), vp(piv.data_ptr()), vp(b_dev.data_ptr()), n, B,
+                                             vp(info2.data_ptr()), None))
+    torch.cuda.synchronize()
+    lu_g = a_dev.cpu().numpy()                       # [b][j][i]
+    piv_g = piv.cpu().numpy()
+    x_g = b_dev.cpu().numpy()
+    info2 = info2.cpu().numpy()
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    for b in range(B):
+        Af = np.ascontiguousarray(A[b].T).ravel()
+        lu_o = np.empty(n * n); piv_o = np.empty(n, dtype=np.int32)
+        oracle.lib().orc_lu_factor(dp(Af), n, dp(lu_o), piv_o.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+        assert np.array_equal(piv_g[b], piv_o), b
+        assert np.array_equal(lu_g[b].ravel(), lu_o, equal_nan=True), b
+        x_o = rhs[b].copy()
+        rc = oracle.lib().orc_lu_solve(dp(Af), n, dp(x_o))
+        assert (rc != 0) == (info2[b] != 0), b
+        if rc == 0:
+            assert np.array_equal(x_g[b], x_o), b

@@ -1,5 +1,2 @@
-run() { echo "$@"; env "$@" python bench.py --steps 3 --warmup 2 --batch 500000 --no-cpu-baseline 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('   inst/s %.4g  ms %.2f' % (d['instances_per_sec'], d['ms_per_step']))"; }
-run DSB_LIB_TAG=mb3
-run DSB_LIB_TAG=
-run DSB_LIB_TAG=mb3
-run DSB_LIB_TAG=
+run() { echo "$@"; env "$@" python bench.py --steps 3 --warmup 2 --batch 500000 --no-cpu-baseline 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('   inst/s %.4g  ms %.2f  nli %d' % (d['instances_per_sec'], d['ms_per_step'], d['newton_iters_per_step']))"; }
+for tag in $TAGS; do run DSB_LIB_TAG=$tag; done
