@@ -15,6 +15,7 @@ METHODS = {"bdf": 0, "tr_bdf2": 1, "esdirk34": 2}
 MODELS = {
     "exp_decay": 0, "exp_decay_algebraic": 1, "robertson_dae": 2, "robertson_ode": 3,
     "robertson_ode_g3": 4, "dydt_y2": 5, "gaussian_decay": 6, "van_der_pol": 7, "van_der_pol_scaled": 8,
+    "heat1d_dae_256": 9, "heat1d_dae_32": 10,
 }
 STAT_NAMES = [
     "number_of_linear_solver_setups",
@@ -92,6 +93,7 @@ SIGNATURES = {
     "dsb_batch_new": (ctypes.c_int, [_vp, _i64, _i32, ctypes.POINTER(_vp)]),
     "dsb_batch_free": (ctypes.c_int, [_vp]),
     "dsb_batch_size": (_i64, [_vp]),
+    "dsb_batch_set_execution": (ctypes.c_int, [_vp, _i32]),
     "dsb_batch_set_params_host": (ctypes.c_int, [_vp, _vp, _i64, _i32]),
     "dsb_batch_set_params_device": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "dsb_batch_solve_dense": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),

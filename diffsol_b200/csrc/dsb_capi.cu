@@ -62,6 +62,7 @@ struct dsb_batch {
     int last_launches = 0;
     bool have_timing = false;
     int sparsity_probe_jac_muls = 0;
+    DsbCoopState coop = {0, nullptr, 0, nullptr, 0};
 };
 
 namespace {
@@ -183,7 +184,7 @@ int fill_problem_args(const dsb_problem& pr, int64_t B, int nt, DsbProblemArgs* 
     std::memset(pa, 0, sizeof(*pa));
     pa->nbatch = B; pa->nt = nt;
     pa->rtol = pr.rtol; pa->t0 = pr.t0; pa->h0 = pr.h0;
-    for (int i = 0; i < pr.n; ++i) pa->atol[i] = pr.atol.size() == 1 ? pr.atol[0] : pr.atol[i];
+    for (int i = 0; i < pr.n && i < DSB_MAX_STATES; ++i) pa->atol[i] = pr.atol.size() == 1 ? pr.atol[0] : pr.atol[i];
     pa->opt = pr.opt;
     build_tables(&pa->tab);
     pa->use_coloring = pr.use_coloring;
@@ -198,7 +199,7 @@ int fill_problem_args(const dsb_problem& pr, int64_t B, int nt, DsbProblemArgs* 
 const dsb_launch_fn g_launch_table[DSB_MODEL_COUNT] = {
     dsb_launch_model_0, dsb_launch_model_1, dsb_launch_model_2, dsb_launch_model_3,
     dsb_launch_model_4, dsb_launch_model_5, dsb_launch_model_6, dsb_launch_model_7,
-    dsb_launch_model_8,
+    dsb_launch_model_8, dsb_launch_model_9, dsb_launch_model_10,
 };
 
 // instance-major <-> batch-major re-layout on the device (the host-facing layouts follow the
@@ -386,7 +387,7 @@ int dsb_batch_free(dsb_batch* b) {
     cudaSetDevice(b->device);
     cudaFree(b->params); cudaFree(b->y0); cudaFree(b->dy0); cudaFree(b->h0);
     cudaFree(b->fin_t); cudaFree(b->fin_h); cudaFree(b->fin_order);
-    cudaFree(b->stats); cudaFree(b->status); cudaFree(b->work_counter); cudaFree(b->t_eval); cudaFree(b->ys_own); cudaFree(b->stage);
+    cudaFree(b->stats); cudaFree(b->status); cudaFree(b->work_counter); cudaFree(b->coop.ws_mem); cudaFree(b->coop.atol_dev); cudaFree(b->t_eval); cudaFree(b->ys_own); cudaFree(b->stage);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->ev_mid) cudaEventDestroy(b->ev_mid);
@@ -457,7 +458,12 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     b->last_launches = 0;
     DSB_CUDA(cudaEventRecord(b->ev0, stream));
     if (b->prob.model < 0 || b->prob.model >= DSB_MODEL_COUNT) return fail(DSB_BAD_ARG, "unknown model id");
-    cudaError_t lerr = g_launch_table[b->prob.model](&pa, &bb, method, stream, b->ev_mid, b->work_counter, &b->last_launches);
+    std::vector<double> atol_full((size_t)b->prob.n);
+    for (int i = 0; i < b->prob.n; ++i) atol_full[i] = b->prob.atol.size() == 1 ? b->prob.atol[0] : b->prob.atol[i];
+    if (const char* q = getenv("DSB_EXEC_MODE")) b->coop.exec_mode = atoi(q);      // test hook: 1 = lane kernels, 2 = cooperative
+    cudaError_t lerr = g_launch_table[b->prob.model](&pa, &bb, method, stream, b->ev_mid, b->work_counter, &b->coop,
+                                                     atol_full.data(), &b->last_launches);
+    if (lerr == cudaErrorNotSupported) return fail(DSB_ERR, "this method / option is not available for this system size (cooperative path: BDF with dense Jacobian only)");
     if (lerr != cudaSuccess) return fail(DSB_ERR, std::string("kernel launch: ") + cudaGetErrorString(lerr));
     DSB_CUDA(cudaEventRecord(b->ev1, stream));
     b->have_timing = true;
@@ -470,6 +476,12 @@ int dsb_batch_solve_dense(dsb_batch* b, int32_t method, const double* t_eval, in
 int dsb_batch_step_and_interpolate(dsb_batch* b, int32_t method, const double* t_points, int32_t npts, double* ys_dev,
                                    void* stream) {
     return solve_impl(b, method, t_points, npts, ys_dev, stream, 1);
+}
+
+int dsb_batch_set_execution(dsb_batch* b, int32_t mode) {
+    if (!b || mode < 0 || mode > 2) return fail(DSB_BAD_ARG, "mode must be 0 (automatic), 1 (thread per instance) or 2 (block per instance)");
+    b->coop.exec_mode = mode;
+    return DSB_OK;
 }
 
 int dsb_batch_get_stats_device(dsb_batch* b, int64_t* stats_dev, void* stream) {

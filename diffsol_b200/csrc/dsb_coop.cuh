@@ -49,7 +49,7 @@ __device__ __forceinline__ CoopScratch coop_carve(void* smem, int n) {
 // In-place LU of the n x n column-major matrix A (global memory, leading dimension n) by the whole block.
 // piv[i] = row swapped with row i (== i: no swap).  Returns (to every thread) 0, or k+1 for the first
 // zero pivot column k (nalgebra leaves that column untouched and continues).
-__device__ int coop_lu_factor(double* __restrict__ A, int n, int* __restrict__ piv, const CoopScratch& sc) {
+static __device__ int coop_lu_factor(double* __restrict__ A, int n, int* __restrict__ piv, const CoopScratch& sc) {
     const int tid = threadIdx.x, T = blockDim.x;
     const int lane = tid & 31, wid = tid >> 5, nwarps = (T + 31) >> 5;
     int first_bad = 0;
@@ -168,7 +168,7 @@ __device__ int coop_lu_factor(double* __restrict__ A, int n, int* __restrict__ p
 
 // Solve with the factors of coop_lu_factor; b lives in SHARED memory (n doubles).  Returns false (to every
 // thread) when U has a zero on its diagonal (nalgebra's solve_mut returns false; b is then unspecified).
-__device__ bool coop_lu_solve(const double* __restrict__ LU, int n, const int* __restrict__ piv, double* b,
+static __device__ bool coop_lu_solve(const double* __restrict__ LU, int n, const int* __restrict__ piv, double* b,
                               const CoopScratch& sc) {
     const int tid = threadIdx.x, T = blockDim.x;
     if (tid == 0) {
@@ -228,30 +228,3 @@ __device__ bool coop_lu_solve(const double* __restrict__ LU, int n, const int* _
     return true;
 }
 
-// ---- stand-alone kernels: the LinearSolver pair for instance-major storage ------------------------------
-// a: [nbatch][n*n] column-major per instance (the layout of the reference's CUDA matrices,
-// diffsol-la/src/matrix/cuda.rs), piv: [nbatch][n], rhs: [nbatch][n].
-__global__ void dsb_lu_factor_coop_kernel(double* __restrict__ a, int n, int64_t B, int32_t* __restrict__ piv,
-                                          int32_t* __restrict__ info) {
-    extern __shared__ unsigned char dsb_coop_smem[];
-    const CoopScratch sc = coop_carve(dsb_coop_smem, n);
-    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-        const int bad = coop_lu_factor(a + (size_t)b * n * n, n, piv + (size_t)b * n, sc);
-        if (threadIdx.x == 0) info[b] = bad;
-        __syncthreads();
-    }
-}
-__global__ void dsb_lu_solve_coop_kernel(const double* __restrict__ a, const int32_t* __restrict__ piv,
-                                         double* __restrict__ rhs, int n, int64_t B, int32_t* __restrict__ info) {
-    extern __shared__ unsigned char dsb_coop_smem[];
-    const CoopScratch sc = coop_carve(dsb_coop_smem, n);
-    double* bs = sc.panel;                               // the panel area doubles as the right-hand side buffer
-    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) bs[i] = rhs[(size_t)b * n + i];
-        __syncthreads();
-        const bool ok = coop_lu_solve(a + (size_t)b * n * n, n, piv + (size_t)b * n, bs, sc);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) rhs[(size_t)b * n + i] = bs[i];
-        if (threadIdx.x == 0) info[b] = ok ? 0 : 1;
-        __syncthreads();
-    }
-}

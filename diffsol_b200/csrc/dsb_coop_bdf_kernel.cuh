@@ -1,0 +1,637 @@
+// dsb_coop_bdf_kernel.cuh -- the BDF path for systems too large for one thread per instance (n > 16):
+// ONE THREAD BLOCK per instance, one thread per state component.  Control flow is uniform over the block
+// (every thread carries the controller scalars and takes the same decisions from the same shared-memory
+// data), so the reference's nested loops are kept as they are; what is parallel is every vector / matrix
+// operation inside them.  Vectors (the difference array D, y, predictor, Newton iterate, ...) live in shared
+// memory; J, M and the LU factors (n^2 doubles each: 512 KB at n = 256) live in global memory and are
+// streamed through the blocked LU of dsb_coop.cuh.  Blocks are persistent and draw instances from a global
+// work counter.
+//
+// Bit-exactness: element-wise operations are order-free; everything the reference sums sequentially
+// (squared_norm: nalgebra_serial.rs:395-408; LU; substitutions) is summed in the same order here (the norm's
+// terms are computed in parallel and added up by one thread).
+//
+// Restated functions: the same list as dsb_bdf_kernel.cuh and dsb_init_kernel.cuh (Bdf::_new, Bdf::step and
+// everything it calls, new_and_consistent with InitOp, set_step_size, solve_dense), paths relative to
+// /root/reference/crates/diffsol/src.
+#pragma once
+#include <type_traits>
+
+#include "dsb_coop.cuh"
+#include "dsb_lane.cuh"
+
+template <class M, class = void> struct dsb_is_componentwise : std::false_type {};
+template <class M> struct dsb_is_componentwise<M, std::void_t<decltype(M::COMPONENTWISE)>> : std::bool_constant<M::COMPONENTWISE> {};
+
+// Component-wise view of the equations.  Models written component-wise (dsb_models.h: `*_i`) are used
+// directly; for the small whole-vector models the component is picked out of a full evaluation (O(n) per
+// component: only used to run the reference's small test problems through this kernel).
+template <class M, bool CW = dsb_is_componentwise<M>::value> struct CoopEval;
+template <class M> struct CoopEval<M, true> {
+    static __device__ __forceinline__ double rhs_i(int i, const double* x, const double* p, double t) { return M::rhs_i(i, x, p, t); }
+    template <class V>
+    static __device__ __forceinline__ double jac_mul_i(int i, const double* x, const double* p, double t, const V& v) { return M::jac_mul_i(i, x, p, t, v); }
+    static __device__ __forceinline__ double mass_i(int i, const double* x, const double* p, double t, double beta, double yi) { return M::mass_i(i, x, p, t, beta, yi); }
+    static __device__ __forceinline__ double init_i(int i, const double* p, double t) { return M::init_i(i, p, t); }
+};
+template <class M> struct CoopEval<M, false> {
+    static __device__ double rhs_i(int i, const double* x, const double* p, double t) {
+        double xl[M::N], yl[M::N];
+        for (int k = 0; k < M::N; ++k) { xl[k] = x[k]; yl[k] = 0.0; }
+        M::rhs(xl, p, t, yl);
+        return yl[i];
+    }
+    template <class V>
+    static __device__ double jac_mul_i(int i, const double* x, const double* p, double t, const V& v) {
+        double xl[M::N], vl[M::N], yl[M::N];
+        for (int k = 0; k < M::N; ++k) { xl[k] = x[k]; vl[k] = v[k]; yl[k] = 0.0; }
+        M::jac_mul(xl, p, t, vl, yl);
+        return yl[i];
+    }
+    static __device__ double mass_i(int i, const double* x, const double* p, double t, double beta, double yi) {
+        double xl[M::N], yl[M::N];
+        for (int k = 0; k < M::N; ++k) { xl[k] = x[k]; yl[k] = 0.0; }
+        yl[i] = yi;
+        M::mass(xl, p, t, beta, yl);
+        return yl[i];
+    }
+    static __device__ double init_i(int i, const double* p, double t) {
+        double yl[M::N];
+        M::init(p, t, yl);
+        return yl[i];
+    }
+};
+
+// unit vector e_j as an indexable object (seed of one Jacobian / mass column)
+struct CoopUnitVec {
+    int j;
+    __device__ __forceinline__ double operator[](int k) const { return k == j ? 1.0 : 0.0; }
+};
+
+// Global-memory workspace of one resident block (instance in flight)
+struct DsbCoopWorkspace {
+    double* jac;      // [nblocks][n*n]  df/dy
+    double* mass;     // [nblocks][n*n]  M (DAE only)
+    double* lu;       // [nblocks][n*n]  factors of M - cJ
+    int32_t* piv;     // [nblocks][n]
+    const double* atol;   // [n]
+};
+
+template <class M>
+struct CoopBdfLayout {
+    static constexpr int N = M::N;
+    static constexpr int NVEC = DSB_NDIFF + 9;          // D[8], y, yp, ycur, psi, dlt, tmp, scr, atol, dy
+    static constexpr int THREADS = (N + 31) / 32 * 32 > 256 ? 256 : (N + 31) / 32 * 32;
+    static size_t smem_bytes() { return (size_t)NVEC * N * sizeof(double) + coop_lu_smem_bytes_host(N) + 64; }
+};
+
+template <class M>
+__global__ void __launch_bounds__(CoopBdfLayout<M>::THREADS)
+dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __grid_constant__ DsbBatchBuffers bb,
+                                const __grid_constant__ DsbCoopWorkspace ws, unsigned long long* __restrict__ work_counter) {
+    constexpr int N = M::N;
+    constexpr int NP = M::NP;
+    typedef CoopEval<M> E;
+    extern __shared__ unsigned char dsb_coop_bdf_smem[];
+    double* const vec = (double*)dsb_coop_bdf_smem;
+    double* const Dm = vec;                              // D[j][i] at Dm[j * N + i]
+    double* const ys = vec + DSB_NDIFF * N;              // state.y
+    double* const yp = ys + N;                           // y_predict
+    double* const yc = yp + N;                           // Newton iterate / y_delta
+    double* const psi = yc + N;                          // psi - y_predict
+    double* const dlt = psi + N;                         // Newton residual / update
+    double* const tmpv = dlt + N;
+    double* const scr = tmpv + N;                        // per-component terms of a norm
+    double* const atolv = scr + N;
+    double* const dys = atolv + N;                       // state.dy (initialisation only)
+    const CoopScratch sc = coop_carve(dys + N, N);
+    __shared__ double s_red;                             // broadcast of a sequential reduction
+    __shared__ long long s_inst;
+    __shared__ double s_p[NP > 0 ? NP : 1];
+
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int64_t B = pa.nbatch;
+    const int nt = pa.nt;
+    const bool free_running = pa.free_running != 0;
+    const double eps = 2.220446049250313e-16;
+    double* const Jg = ws.jac + (size_t)blockIdx.x * N * N;
+    double* const Mg = M::HAS_MASS ? ws.mass + (size_t)blockIdx.x * N * N : nullptr;
+    double* const LUg = ws.lu + (size_t)blockIdx.x * N * N;
+    int32_t* const pivg = ws.piv + (size_t)blockIdx.x * N;
+
+    for (int i = tid; i < N; i += T) atolv[i] = ws.atol[i];
+
+    // sum_i term_i / n with term_i = (x_i / (|y_i| rtol + atol_i))^2, terms in parallel, the sum sequential
+    auto squared_norm = [&](const double* x, const double* yref) -> double {
+        __syncthreads();
+        for (int i = tid; i < N; i += T) {
+            const double term = x[i] / (dsb_abs(yref[i]) * pa.rtol + atolv[i]);
+            scr[i] = term * term;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double acc = 0.0;
+            for (int i = 0; i < N; ++i) acc += scr[i];
+            s_red = acc / (double)N;
+        }
+        __syncthreads();
+        return s_red;
+    };
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_inst = (long long)atomicAdd(work_counter, 1ull);
+        __syncthreads();
+        const int64_t inst = s_inst;
+        if (inst >= B) break;
+
+        LaneStats st; st.clear();
+        if (tid < NP) s_p[tid] = bb.params[(int64_t)tid * B + inst];
+        __syncthreads();
+        const double* p = s_p;
+        int status = DSB_STATUS_OK;
+
+        // ================= new_and_consistent (state.rs:969-997, 1086-1124) =================
+        double t = pa.t0, h = pa.h0;
+        for (int i = tid; i < N; i += T) ys[i] = E::init_i(i, p, pa.t0);
+        __syncthreads();
+        for (int i = tid; i < N; i += T) dys[i] = E::rhs_i(i, ys, p, pa.t0);
+        st.v[DSB_STAT_RHS_CALLS] += 1;
+        __syncthreads();
+
+        // df/dy at (x, tt) into Jg, column by column (op/nonlinear_op.rs:211-220); colouring is not
+        // supported on this path
+        auto eval_jacobian = [&](const double* x, double tt) {
+            st.v[DSB_STAT_RHS_MATRIX_EVALS] += 1;
+            st.v[DSB_STAT_RHS_JAC_MULS] += N;
+            for (int j = 0; j < N; ++j) {
+                const CoopUnitVec v{j};
+                for (int i = tid; i < N; i += T) Jg[(size_t)j * N + i] = E::jac_mul_i(i, x, p, tt, v);
+            }
+        };
+        // ---- set_consistent (state.rs:84-162, op/init.rs:14-131) ----
+        if (M::HAS_MASS) {
+            // mass matrix at t0: column j = M e_j, with beta = 0
+            for (int j = 0; j < N; ++j) {
+                __syncthreads();
+                for (int i = tid; i < N; i += T) tmpv[i] = (i == j) ? 1.0 : 0.0;
+                __syncthreads();
+                for (int i = tid; i < N; i += T) Mg[(size_t)j * N + i] = E::mass_i(i, tmpv, p, pa.t0, 0.0, 0.0);
+            }
+            __syncthreads();
+            // algebraic indices: zero diagonal; flags kept in scr as 0/1 is not possible (scr is norm scratch),
+            // so they are recomputed from Mg where needed
+            __shared__ int s_nalg;
+            if (tid == 0) {
+                int c = 0;
+                for (int i = 0; i < N; ++i) c += (Mg[(size_t)i * N + i] == 0.0) ? 1 : 0;
+                s_nalg = c;
+            }
+            __syncthreads();
+            if (s_nalg > 0) {
+                auto is_alg = [&](int i) -> bool { return Mg[(size_t)i * N + i] == 0.0; };
+                eval_jacobian(ys, pa.t0);
+                __syncthreads();
+                // InitOp jac = (-M_u | f_v ; 0 | g_v) into LUg; neg_mass = (-M_u | 0 ; 0 | 0) overwrites Jg
+                for (int e = tid; e < N * N; e += T) {
+                    const int j = e / N, i = e % N;
+                    double jv = 0.0, nm = 0.0;
+                    if (!is_alg(j)) { if (!is_alg(i)) { const double m_u = Mg[e] * -1.0; jv = m_u; nm = m_u; } }
+                    else jv = Jg[e];
+                    LUg[e] = jv; Jg[e] = nm;
+                }
+                __syncthreads();
+                // the InitOp Jacobian is constant: factor once, keep a copy is unnecessary because LU setups
+                // beyond the first only re-factor the same matrix (bitwise the same factors)
+                coop_lu_factor(LUg, N, pivg, sc);
+                __syncthreads();
+                // y_tmp (yc) = (dy at differential idx, y at algebraic idx); yerr (yp) = y_tmp; y0 copy in psi
+                for (int i = tid; i < N; i += T) { yc[i] = is_alg(i) ? ys[i] : dys[i]; yp[i] = yc[i]; psi[i] = ys[i]; }
+                __syncthreads();
+                // fun(x) -> dlt: y0[alg] = x[alg]; out = f(y0); out = neg_mass * x + out (column sweep)
+                auto fun = [&](const double* x) {
+                    __syncthreads();
+                    for (int i = tid; i < N; i += T) if (is_alg(i)) psi[i] = x[i];
+                    __syncthreads();
+                    for (int i = tid; i < N; i += T) {
+                        double o = E::rhs_i(i, psi, p, pa.t0);
+                        for (int j = 0; j < N; ++j) o = Jg[(size_t)j * N + i] * x[j] + o;
+                        dlt[i] = o;
+                    }
+                    st.v[DSB_STAT_RHS_CALLS] += 1;
+                    __syncthreads();
+                };
+                LaneConvergence conv;
+                conv.tol = pa.opt.nonlinear_solver_tolerance; conv.eta = pa.tab.eta_reset;
+                conv.max_iter = pa.opt.ic_max_newton_iterations; conv.old_norm = 0.0; conv.reset();
+                const double tau = pa.opt.ic_step_reduction_factor, c_armijo = pa.opt.ic_armijo_constant;
+                const double steptol = pa.tab.ic_steptol;
+                bool ok = false;
+                for (int setup = 0; setup < pa.opt.ic_max_linear_solver_setups && status == DSB_STATUS_OK && !ok; ++setup) {
+                    conv.reset();
+                    double ls_norm = 1.0;
+                    int result = -1;
+                    for (int i = tid; i < N; i += T) dlt[i] = 0.0;
+                    for (int it = 0; it < conv.max_iter && result < 0; ++it) {
+                        int res = LANE_CONTINUE;
+                        bool have_res = false;
+                        if (pa.opt.ic_use_linesearch) {
+                            if (conv.niter == 0) {
+                                fun(yc);
+                                if (!coop_lu_solve(LUg, N, pivg, dlt, sc)) { result = 2; break; }
+                                ls_norm = dsb_sqrt(squared_norm(dlt, yp));
+                                if (conv.check_norm(ls_norm) == LANE_CONVERGED) {
+                                    for (int i = tid; i < N; i += T) yc[i] -= dlt[i];
+                                    __syncthreads();
+                                    res = LANE_CONVERGED; have_res = true;
+                                }
+                            }
+                            if (!have_res) {
+                                // x0 -> tmpv, delta0 -> Dm row 0 (D is not in use yet)
+                                __syncthreads();
+                                for (int i = tid; i < N; i += T) { tmpv[i] = yc[i]; Dm[i] = dlt[i]; }
+                                __syncthreads();
+                                const double norm = ls_norm;
+                                const double phi0 = norm * norm * 0.5, two_phi0 = norm * norm;
+                                const double min_alpha = steptol / norm;
+                                double alpha = 1.0;
+                                int ls_status = 1;
+                                for (int li = 0; li < pa.opt.ic_max_linesearch_iterations; ++li) {
+                                    for (int q = tid; q < N; q += T) yc[q] = (-alpha) * Dm[q] + yc[q];
+                                    fun(yc);
+                                    if (!coop_lu_solve(LUg, N, pivg, dlt, sc)) { ls_status = 2; break; }
+                                    const double new_norm = dsb_sqrt(squared_norm(dlt, yp));
+                                    const double phi1 = new_norm * new_norm * 0.5;
+                                    if (phi1 <= phi0 - c_armijo * alpha * two_phi0) {
+                                        ls_norm = new_norm;
+                                        res = conv.check_norm(new_norm); have_res = true; ls_status = 0;
+                                        break;
+                                    }
+                                    if (alpha < min_alpha) { ls_status = 2; break; }
+                                    alpha *= tau;
+                                    __syncthreads();
+                                    for (int q = tid; q < N; q += T) yc[q] = tmpv[q];
+                                    __syncthreads();
+                                }
+                                if (ls_status != 0) { result = 2; break; }
+                            }
+                        } else {
+                            fun(yc);
+                            if (!coop_lu_solve(LUg, N, pivg, dlt, sc)) { result = 2; break; }
+                            for (int i = tid; i < N; i += T) yc[i] -= dlt[i];
+                            res = conv.check_new_iteration(dsb_sqrt(squared_norm(dlt, yp)));
+                        }
+                        if (res == LANE_CONVERGED) result = 0;
+                        else if (res == LANE_DIVERGED) result = 2;
+                    }
+                    if (result < 0) result = 1;
+                    if (result == 0) ok = true;
+                    else if (result == 2) status = DSB_STATUS_INITIAL_CONDITION_DID_NOT_CONVERGE;
+                    else {
+                        __syncthreads();
+                        for (int i = tid; i < N; i += T) yp[i] = yc[i];
+                        __syncthreads();
+                    }
+                }
+                if (!ok && status == DSB_STATUS_OK) status = DSB_STATUS_INITIAL_CONDITION_DID_NOT_CONVERGE;
+                __syncthreads();
+                if (status == DSB_STATUS_OK) {
+                    for (int i = tid; i < N; i += T) {
+                        if (is_alg(i)) { ys[i] = yc[i]; dys[i] = 0.0; }
+                        else dys[i] = yc[i];
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---- set_step_size (state.rs:1209-1277) ----
+        if (status == DSB_STATUS_OK) {
+            const bool is_neg_h = pa.h0 < 0.0;
+            const double d0 = dsb_sqrt(squared_norm(ys, ys));
+            const double d1 = dsb_sqrt(squared_norm(dys, ys));
+            const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+            __syncthreads();
+            for (int i = tid; i < N; i += T) tmpv[i] = is_neg_h ? (dys[i] * (-h0) + ys[i]) : (dys[i] * h0 + ys[i]);
+            __syncthreads();
+            const double t1 = is_neg_h ? pa.t0 - h0 : pa.t0 + h0;
+            for (int i = tid; i < N; i += T) dlt[i] = E::rhs_i(i, tmpv, p, t1) - dys[i];
+            st.v[DSB_STAT_RHS_CALLS] += 1;
+            const double d2 = dsb_sqrt(squared_norm(dlt, ys)) / dsb_abs(h0);
+            double max_d = d2;
+            if (max_d < d1) max_d = d1;
+            double h1;
+            if (max_d < 1e-15) { h1 = h0 * 1e-3; if (h1 < 1e-6) h1 = 1e-6; }
+            else h1 = dsb_pow(0.01 / max_d, 1.0 / (1.0 + 1.0));        // solver_order = 1 for Bdf
+            h = 100.0 * h0;
+            if (h > h1) h = h1;
+            if (is_neg_h) h = -h;
+        }
+
+        // ================= Bdf::_new (bdf.rs:230-368) =================
+        int order = 1, n_equal_steps = 0;
+        double c = h * pa.tab.alpha[1], t_predict = t;
+        bool has_tstop = false, has_prev_error = false, jacobian_is_stale = true;
+        double tstop = 0.0, prev_error_norm = 0.0;
+        LaneJacobianUpdate ju; ju.init(1.0);
+        LaneConvergence conv;
+        conv.tol = pa.opt.nonlinear_solver_tolerance; conv.max_iter = pa.opt.max_nonlinear_solver_iterations;
+        conv.eta = pa.tab.eta_reset; conv.old_norm = 0.0; conv.reset();
+
+        // BdfCallable::jacobian_inplace + NalgebraLU::set_linearisation: (re)evaluate J, M when stale; A = M - cJ; LU
+        auto reset_jacobian = [&]() {
+            __syncthreads();
+            if (jacobian_is_stale) {
+                eval_jacobian(ys, t);
+                if (M::HAS_MASS) {
+                    for (int j = 0; j < N; ++j) {
+                        __syncthreads();
+                        for (int i = tid; i < N; i += T) tmpv[i] = (i == j) ? 1.0 : 0.0;
+                        __syncthreads();
+                        for (int i = tid; i < N; i += T) Mg[(size_t)j * N + i] = E::mass_i(i, tmpv, p, t, 0.0, 0.0);
+                    }
+                }
+                jacobian_is_stale = false;
+                __syncthreads();
+            }
+            const double mc = -c;
+            for (int e = tid; e < N * N; e += T) {
+                const int j = e / N, i = e % N;
+                const double m_ji = M::HAS_MASS ? Mg[e] : ((i == j) ? 1.0 : 0.0);
+                LUg[e] = Jg[e] * mc + m_ji;
+            }
+            __syncthreads();
+            coop_lu_factor(LUg, N, pivg, sc);
+            __syncthreads();
+        };
+        auto jacobian_updates = [&](double cc, int kind) {
+            bool did_update = false;
+            if (ju.check_rhs_jacobian_update(pa.opt, cc, kind)) {
+                jacobian_is_stale = true;
+                reset_jacobian();
+                ju.update_rhs_jacobian(cc);
+                ju.update_jacobian(cc);
+                conv.eta = pa.tab.eta_reset;
+                did_update = true;
+            } else if (ju.check_jacobian_update(pa.opt, cc, kind)) {
+                reset_jacobian();
+                ju.update_jacobian(cc);
+                conv.eta = pa.tab.eta_reset;
+                did_update = true;
+            }
+            if (did_update) st.record_linear_solver_setup(kind);
+        };
+        // _update_step_size (bdf.rs:508-577): RU = R(order, factor) U; D[:, 0..=order] <- D[:, 0..=order] RU
+        auto update_step_size = [&](double factor, double* new_h_out) -> int {
+            const double new_h = factor * h;
+            n_equal_steps = 0;
+            const int nr = order + 1;
+            double r[36], ru[36];
+            for (int q = 0; q < nr * nr; ++q) r[q] = 0.0;
+            for (int j = 0; j < nr; ++j) r[j * nr] = 1.0;
+            for (int j = 1; j < nr; ++j) {
+                const double j_t = (double)j;
+                for (int i = 1; i < nr; ++i) {
+                    const double i_t = (double)i;
+                    r[j * nr + i] = r[j * nr + i - 1] * (i_t - 1.0 - factor * j_t) / i_t;
+                }
+            }
+            const double* u = pa.tab.u[order];
+            for (int j = 0; j < nr; ++j)
+                for (int l = 0; l < nr; ++l) {
+                    const double ulj = u[j * nr + l];
+                    for (int i = 0; i < nr; ++i) {
+                        if (l == 0) ru[j * nr + i] = r[l * nr + i] * ulj;
+                        else ru[j * nr + i] = r[l * nr + i] * ulj + ru[j * nr + i];
+                    }
+                }
+            __syncthreads();
+            for (int i = tid; i < N; i += T) {
+                double row[DSB_MAX_ORDER + 1];
+                for (int j = 0; j < nr; ++j) {
+                    double acc = Dm[0 * N + i] * ru[j * nr + 0];
+                    for (int l = 1; l < nr; ++l) acc = Dm[l * N + i] * ru[j * nr + l] + acc;
+                    row[j] = acc;
+                }
+                for (int j = 0; j < nr; ++j) Dm[j * N + i] = row[j];
+            }
+            __syncthreads();
+            c = new_h * pa.tab.alpha[order];
+            h = new_h;
+            conv.eta = pa.tab.eta_reset_timestep;
+            if (new_h_out) *new_h_out = new_h;
+            if (dsb_abs(h) < pa.opt.min_timestep) return DSB_STATUS_STEP_SIZE_TOO_SMALL;
+            return DSB_STATUS_OK;
+        };
+        auto predict_forward = [&]() {
+            __syncthreads();
+            for (int i = tid; i < N; i += T) {
+                double a = 0.0;
+                for (int j = 0; j <= order; ++j) a += Dm[j * N + i];
+                double ps = pa.tab.gamma[1] * Dm[1 * N + i];
+                for (int j = 2; j <= order; ++j) ps = pa.tab.gamma[j] * Dm[j * N + i] + ps;
+                ps *= pa.tab.alpha[order];
+                ps -= a;
+                yp[i] = a; psi[i] = ps;
+            }
+            t_predict = t + h;
+            __syncthreads();
+        };
+        auto handle_tstop = [&](double ts) -> int {
+            const double troundoff = 100.0 * eps * (dsb_abs(t) + dsb_abs(h));
+            if (dsb_abs(t - ts) <= troundoff) { has_tstop = false; return 1; }
+            if ((h > 0.0 && ts < t - troundoff) || (h < 0.0 && ts > t + troundoff)) { has_tstop = false; return -DSB_STATUS_STOP_TIME_BEFORE_CURRENT; }
+            if ((h > 0.0 && t + h > ts + troundoff) || (h < 0.0 && t + h < ts - troundoff)) {
+                const double factor = (ts - t) / h;
+                (void)update_step_size(factor, nullptr);
+            }
+            return 0;
+        };
+        auto pi_controller_raw = [&](double err, int eff_order) -> double {
+            const double order_f = (double)eff_order;
+            const double ki = pa.opt.pi_control_integral / order_f;
+            if (pa.opt.pi_control_proportional == 0.0 || !has_prev_error) return dsb_pow(err, -ki);
+            const double kp = pa.opt.pi_control_proportional / order_f;
+            return dsb_pow(err, -(ki + kp)) * dsb_pow(prev_error_norm, kp);
+        };
+        auto interpolate_and_write = [&](double tq, int col) -> int {
+            const bool is_forward = h > 0.0;
+            if ((is_forward && tq > t) || (!is_forward && tq < t)) return DSB_STATUS_INTERPOLATION_TIME_AFTER_CURRENT;
+            __syncthreads();
+            for (int i = tid; i < N; i += T) {
+                double time_factor = 1.0;
+                double yo = Dm[i];
+                for (int j = 0; j < order; ++j) {
+                    const double j_t = (double)j;
+                    time_factor *= (tq - (t - h * j_t)) / (h * (1.0 + j_t));
+                    yo = time_factor * Dm[(j + 1) * N + i] + yo;
+                }
+                bb.ys[((int64_t)col * N + i) * B + inst] = yo;
+            }
+            return DSB_STATUS_OK;
+        };
+
+        int col = 0;
+        if (status == DSB_STATUS_OK) {
+            reset_jacobian();
+            st.v[DSB_STAT_LINEAR_SOLVER_SETUPS] += 1;
+            st.v[DSB_STAT_SETUPS_FROM_CHECKPOINT] += 1;
+            for (int i = tid; i < N; i += T) {
+                for (int j = 0; j < DSB_NDIFF; ++j) Dm[j * N + i] = 0.0;
+                Dm[i] = ys[i]; Dm[N + i] = dys[i] * h;
+            }
+            __syncthreads();
+            if (!free_running) {
+                has_tstop = true; tstop = bb.t_eval[nt - 1];
+                const int r = handle_tstop(tstop);
+                if (r == 1) { has_tstop = false; status = DSB_STATUS_STOP_TIME_AT_CURRENT; }
+                else if (r < 0) status = -r;
+            }
+        }
+
+        // ================= solve_dense loop (method.rs:721-818) around Bdf::step (bdf.rs:1277-1589) =================
+        while (status == DSB_STATUS_OK && col < nt) {
+            if (free_running) {
+                while (col < nt && !(dsb_abs(t) < dsb_abs(bb.t_eval[col]))) {
+                    const int e = interpolate_and_write(bb.t_eval[col], col);
+                    if (e) { status = e; break; }
+                    ++col;
+                }
+                if (col >= nt || status != DSB_STATUS_OK) break;
+            }
+            // ---- step() ----
+            int step_result = 0;                                    // 0 internal, 1 tstop reached
+            {
+                double safety = 0.0, error_norm = 0.0, new_h = 0.0;
+                const int old_etf = st.v[DSB_STAT_ERROR_TEST_FAILURES];
+                bool convergence_fail = false;
+                predict_forward();
+                while (true) {
+                    const int ord = order;
+                    __syncthreads();
+                    for (int i = tid; i < N; i += T) yc[i] = yp[i];
+                    __syncthreads();
+                    // newton_iteration + NoLineSearch
+                    bool ok = false;
+                    conv.reset();
+                    for (int it = 0; it < conv.max_iter; ++it) {
+                        __syncthreads();
+                        for (int i = tid; i < N; i += T) {
+                            const double f = E::rhs_i(i, yc, p, t_predict);
+                            tmpv[i] = yc[i] + psi[i];
+                            dlt[i] = f;
+                        }
+                        st.v[DSB_STAT_RHS_CALLS] += 1;
+                        __syncthreads();
+                        const double mc = -c;
+                        for (int i = tid; i < N; i += T) {
+                            dlt[i] = M::HAS_MASS ? E::mass_i(i, tmpv, p, t_predict, mc, dlt[i]) : (tmpv[i] + mc * dlt[i]);
+                        }
+                        __syncthreads();
+                        if (!coop_lu_solve(LUg, N, pivg, dlt, sc)) break;
+                        for (int i = tid; i < N; i += T) yc[i] -= dlt[i];
+                        const double norm = dsb_sqrt(squared_norm(dlt, yp));
+                        const int s = conv.check_new_iteration(norm);
+                        if (s == LANE_CONVERGED) { ok = true; break; }
+                        if (s == LANE_DIVERGED) break;
+                    }
+                    st.v[DSB_STAT_NONLINEAR_SOLVER_ITERATIONS] += conv.niter;
+                    if (ok) {
+                        __syncthreads();
+                        for (int i = tid; i < N; i += T) yc[i] -= yp[i];
+                        __syncthreads();
+                    } else {
+                        st.v[DSB_STAT_NONLINEAR_SOLVER_FAILS] += 1;
+                        if (st.v[DSB_STAT_NONLINEAR_SOLVER_FAILS] > pa.opt.max_nonlinear_solver_failures) { status = DSB_STATUS_TOO_MANY_NONLINEAR_FAILURES; break; }
+                        has_prev_error = false;
+                        if (convergence_fail) {
+                            const int e = update_step_size(0.3, &new_h);
+                            if (e) { status = e; break; }
+                            jacobian_updates(new_h * pa.tab.alpha[ord], DSB_SECOND_CONVERGENCE_FAIL);
+                            predict_forward();
+                        } else {
+                            jacobian_updates(h * pa.tab.alpha[ord], DSB_FIRST_CONVERGENCE_FAIL);
+                            convergence_fail = true;
+                        }
+                        continue;
+                    }
+                    {
+                        const double err = squared_norm(yc, ys) * pa.tab.error_const2[order - 1];
+                        error_norm = (0.0 < err) ? err : 0.0;
+                    }
+                    const double maxiter = (double)conv.max_iter;
+                    const double niter = (double)conv.niter;
+                    safety = 0.9 * (2.0 * maxiter + 1.0) / (2.0 * maxiter + niter);
+                    if (error_norm <= 1.0) break;
+                    double factor = safety * pi_controller_raw(error_norm, ord + 1);
+                    has_prev_error = false;
+                    if (factor < pa.opt.min_timestep_shrink) factor = pa.opt.min_timestep_shrink;
+                    const int e = update_step_size(factor, &new_h);
+                    if (e) { status = e; break; }
+                    jacobian_updates(new_h * pa.tab.alpha[ord], DSB_ERROR_TEST_FAIL);
+                    predict_forward();
+                    st.v[DSB_STAT_ERROR_TEST_FAILURES] += 1;
+                    if (st.v[DSB_STAT_ERROR_TEST_FAILURES] - old_etf >= pa.opt.max_error_test_failures) { status = DSB_STATUS_TOO_MANY_ERROR_TEST_FAILURES; break; }
+                }
+                if (status != DSB_STATUS_OK) break;
+                // accepted: _update_diff, state.y <- predictor
+                __syncthreads();
+                for (int i = tid; i < N; i += T) {
+                    const double d = yc[i];
+                    Dm[(order + 2) * N + i] = d - Dm[(order + 1) * N + i];
+                    Dm[(order + 1) * N + i] = d;
+                    for (int j = order; j >= 0; --j) Dm[j * N + i] = Dm[j * N + i] + 1.0 * Dm[(j + 1) * N + i];
+                    ys[i] = yp[i];
+                }
+                __syncthreads();
+                t = t_predict;
+                st.v[DSB_STAT_STEPS] += 1;
+                ju.step();
+                has_prev_error = true; prev_error_norm = error_norm;
+                n_equal_steps += 1;
+                if (n_equal_steps > order) {
+                    const int ord = order;
+                    const double inf = dsb_from_bits(0x7ff0000000000000ULL);
+                    double error_m_norm = inf, error_p_norm = inf;
+                    if (ord > 1) { const double e = squared_norm(Dm + ord * N, ys) * pa.tab.error_const2[ord - 1]; error_m_norm = (0.0 < e) ? e : 0.0; }
+                    if (ord < DSB_MAX_ORDER) { const double e = squared_norm(Dm + (ord + 2) * N, ys) * pa.tab.error_const2[ord + 1]; error_p_norm = (0.0 < e) ? e : 0.0; }
+                    const double f0 = pi_controller_raw(error_m_norm, ord);
+                    const double f1 = pi_controller_raw(error_norm, ord + 1);
+                    const double f2 = pi_controller_raw(error_p_norm, ord + 2);
+                    int max_index = 0;
+                    double fmax = f0;
+                    if (!(fmax > f1)) { max_index = 1; fmax = f1; }
+                    if (!(fmax > f2)) { max_index = 2; fmax = f2; }
+                    order = ord + (max_index - 1);
+                    double factor = safety * fmax;
+                    if (factor > pa.opt.max_timestep_growth) factor = pa.opt.max_timestep_growth;
+                    if (factor < pa.opt.min_timestep_shrink) factor = pa.opt.min_timestep_shrink;
+                    if (factor >= pa.opt.min_timestep_growth || factor <= pa.opt.max_timestep_shrink || max_index != 1) {
+                        const int e = update_step_size(factor, &new_h);
+                        if (e) { status = e; break; }
+                        jacobian_updates(new_h * pa.tab.alpha[order], DSB_STEP_SUCCESS);
+                    }
+                }
+                if (has_tstop) {
+                    const int r = handle_tstop(tstop);
+                    if (r == 1) step_result = 1;
+                    else if (r < 0) { status = -r; break; }
+                }
+            }
+            if (!free_running) {
+                while (col < nt && bb.t_eval[col] <= t) {
+                    const int e = interpolate_and_write(bb.t_eval[col], col);
+                    if (e) { status = e; break; }
+                    ++col;
+                }
+                if (step_result == 1) break;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            bb.status[inst] = status;
+            bb.fin_t[inst] = t; bb.fin_h[inst] = h; bb.fin_order[inst] = order;
+            for (int k = 0; k < DSB_NSTATS; ++k) bb.stats[(int64_t)k * B + inst] = st.v[k];
+        }
+    }
+}

@@ -1,5 +1,6 @@
 // dsb_inst.cu -- instantiates the lane kernels for ONE equation set: compile with -DDSB_INST=<model id>.
 #include "dsb_bdf_kernel.cuh"
+#include "dsb_coop_bdf_kernel.cuh"
 #include "dsb_init_kernel.cuh"
 #include "dsb_launch.h"
 #include "dsb_models.h"
@@ -13,60 +14,133 @@
 
 typedef dsb_model_by_id<DSB_INST>::type InstModel;
 
-cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method,
-                                                 cudaStream_t stream, cudaEvent_t mid, unsigned long long* work_counter,
-                                                 int* launches) {
+constexpr bool kLaneCapable = InstModel::N <= 16;
+
+template <class M>
+static cudaError_t launch_coop_bdf(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, cudaStream_t stream,
+                                   cudaEvent_t mid, unsigned long long* work_counter, DsbCoopState* coop,
+                                   const double* atol_host, int* launches) {
+    constexpr int N = M::N;
+    const int threads = CoopBdfLayout<M>::THREADS;
+    const size_t smem = CoopBdfLayout<M>::smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(dsb_coop_bdf_solve_dense_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dsb_coop_bdf_solve_dense_kernel<M>, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const int64_t resident = (int64_t)sms * per_sm;
+    const unsigned grid = (unsigned)(pa->nbatch < resident ? pa->nbatch : resident);
+    // workspace: per resident block J, [M], LU (n^2 doubles each) and n pivots
+    const size_t nn = (size_t)N * N;
+    const size_t per_block = (M::HAS_MASS ? 3 : 2) * nn * sizeof(double) + (size_t)N * sizeof(int32_t);
+    const size_t need = per_block * grid + 256;
+    if (coop->ws_bytes < need) {
+        if (coop->ws_mem) cudaFree(coop->ws_mem);
+        coop->ws_mem = nullptr; coop->ws_bytes = 0;
+        e = cudaMalloc(&coop->ws_mem, need);
+        if (e != cudaSuccess) return e;
+        coop->ws_bytes = need;
+    }
+    if (coop->atol_n < N) {
+        if (coop->atol_dev) cudaFree(coop->atol_dev);
+        coop->atol_dev = nullptr; coop->atol_n = 0;
+        e = cudaMalloc((void**)&coop->atol_dev, (size_t)N * sizeof(double));
+        if (e != cudaSuccess) return e;
+        coop->atol_n = N;
+    }
+    e = cudaMemcpyAsync(coop->atol_dev, atol_host, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    DsbCoopWorkspace ws;
+    char* base = (char*)coop->ws_mem;
+    ws.jac = (double*)base; base += nn * sizeof(double) * grid;
+    ws.mass = nullptr;
+    if (M::HAS_MASS) { ws.mass = (double*)base; base += nn * sizeof(double) * grid; }
+    ws.lu = (double*)base; base += nn * sizeof(double) * grid;
+    ws.piv = (int32_t*)base;
+    ws.atol = coop->atol_dev;
+    e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    if (mid) cudaEventRecord(mid, stream);
+    dsb_coop_bdf_solve_dense_kernel<M><<<grid, threads, smem, stream>>>(*pa, *bb, ws, work_counter);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+// lane kernels (one thread per instance): only instantiated for n <= 16
+template <class M, bool LANE> struct LaneLauncher {
+    static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, int, cudaStream_t, cudaEvent_t, unsigned long long*, int*) {
+        return cudaErrorNotSupported;
+    }
+};
+template <class M> struct LaneLauncher<M, true> {
+    static cudaError_t run(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method, cudaStream_t stream, cudaEvent_t mid,
+                           unsigned long long* work_counter, int* launches) {
     const int init_threads = DSB_LANE_THREADS;
     const unsigned init_blocks = (unsigned)((pa->nbatch + init_threads - 1) / init_threads);
     if (method == DSB_METHOD_BDF) {
-        const int threads = BdfLayout<InstModel>::THREADS;
+        const int threads = BdfLayout<M>::THREADS;
         const unsigned blocks = (unsigned)((pa->nbatch + threads - 1) / threads);
-        const size_t smem = (size_t)BdfLayout<InstModel>::WORDS * threads * sizeof(double);
+        const size_t smem = (size_t)BdfLayout<M>::WORDS * threads * sizeof(double);
         static int resident_blocks = 0;      // persistent grid: as many blocks as fit on the device at once
         if (resident_blocks == 0) {
-            cudaError_t e = cudaFuncSetAttribute(dsb_bdf_solve_dense_kernel<InstModel>,
+            cudaError_t e = cudaFuncSetAttribute(dsb_bdf_solve_dense_kernel<M>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             int dev = 0, sms = 0, per_sm = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dsb_bdf_solve_dense_kernel<InstModel>, threads, smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dsb_bdf_solve_dense_kernel<M>, threads, smem);
             if (e != cudaSuccess) return e;
             if (per_sm < 1) return cudaErrorLaunchOutOfResources;
             resident_blocks = sms * per_sm;
         }
         cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return e;
-        dsb_init_kernel<InstModel><<<init_blocks, init_threads, 0, stream>>>(*pa, *bb, 1);
+        dsb_init_kernel<M><<<init_blocks, init_threads, 0, stream>>>(*pa, *bb, 1);
         if (mid) cudaEventRecord(mid, stream);
         const unsigned grid = blocks < (unsigned)resident_blocks ? blocks : (unsigned)resident_blocks;
-        dsb_bdf_solve_dense_kernel<InstModel><<<grid, threads, smem, stream>>>(*pa, *bb, work_counter);
+        dsb_bdf_solve_dense_kernel<M><<<grid, threads, smem, stream>>>(*pa, *bb, work_counter);
         *launches += 2;
     } else {
         // (E)SDIRK: the tableau travels in pa->rk; RkState::new_and_consistent uses the tableau order
-        const int threads = SdirkLayout<InstModel>::THREADS;
+        const int threads = SdirkLayout<M>::THREADS;
         const unsigned blocks = (unsigned)((pa->nbatch + threads - 1) / threads);
-        const size_t smem = (size_t)SdirkLayout<InstModel>::WORDS * threads * sizeof(double);
+        const size_t smem = (size_t)SdirkLayout<M>::WORDS * threads * sizeof(double);
         static int resident_blocks = 0;
         if (resident_blocks == 0) {
-            cudaError_t e = cudaFuncSetAttribute(dsb_sdirk_solve_dense_kernel<InstModel>,
+            cudaError_t e = cudaFuncSetAttribute(dsb_sdirk_solve_dense_kernel<M>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             int dev = 0, sms = 0, per_sm = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dsb_sdirk_solve_dense_kernel<InstModel>, threads, smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dsb_sdirk_solve_dense_kernel<M>, threads, smem);
             if (e != cudaSuccess) return e;
             if (per_sm < 1) return cudaErrorLaunchOutOfResources;
             resident_blocks = sms * per_sm;
         }
         cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return e;
-        dsb_init_kernel<InstModel><<<init_blocks, init_threads, 0, stream>>>(*pa, *bb, pa->rk.order);
+        dsb_init_kernel<M><<<init_blocks, init_threads, 0, stream>>>(*pa, *bb, pa->rk.order);
         if (mid) cudaEventRecord(mid, stream);
         const unsigned grid = blocks < (unsigned)resident_blocks ? blocks : (unsigned)resident_blocks;
-        dsb_sdirk_solve_dense_kernel<InstModel><<<grid, threads, smem, stream>>>(*pa, *bb, work_counter);
+        dsb_sdirk_solve_dense_kernel<M><<<grid, threads, smem, stream>>>(*pa, *bb, work_counter);
         *launches += 2;
     }
     return cudaGetLastError();
+    }
+};
+
+cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method,
+                                                 cudaStream_t stream, cudaEvent_t mid, unsigned long long* work_counter,
+                                                 DsbCoopState* coop, const double* atol_host, int* launches) {
+    const bool use_coop = coop->exec_mode == 2 || (coop->exec_mode == 0 && !kLaneCapable);
+    if (use_coop) {
+        if (method != DSB_METHOD_BDF || pa->use_coloring) return cudaErrorNotSupported;   // cooperative path: BDF, dense Jacobian
+        return launch_coop_bdf<InstModel>(pa, bb, stream, mid, work_counter, coop, atol_host, launches);
+    }
+    return LaneLauncher<InstModel, kLaneCapable>::run(pa, bb, method, stream, mid, work_counter, launches);
 }

@@ -8,12 +8,19 @@
 // `mid` (may be NULL) is recorded between the initialisation kernel and the integrator kernel so the
 // integrator's own duration can be read back; `work_counter` is the device word the persistent integrator
 // kernel draws instance indices from (zeroed by the launcher).
+// `coop` describes the block-per-instance path: exec_mode (0 = automatic: lane kernels for n <= 16, cooperative
+// kernel above; 1 = lane; 2 = cooperative) and its global-memory workspace (grown on demand by the launcher).
+struct DsbCoopState {
+    int exec_mode;
+    void* ws_mem; size_t ws_bytes;
+    double* atol_dev; int atol_n;
+};
 typedef cudaError_t (*dsb_launch_fn)(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method,
                                      cudaStream_t stream, cudaEvent_t mid, unsigned long long* work_counter,
-                                     int* launches);
+                                     DsbCoopState* coop, const double* atol_host, int* launches);
 
-#define DSB_DECLARE_LAUNCH(id) cudaError_t dsb_launch_model_##id(const DsbProblemArgs*, const DsbBatchBuffers*, int, cudaStream_t, cudaEvent_t, unsigned long long*, int*);
+#define DSB_DECLARE_LAUNCH(id) cudaError_t dsb_launch_model_##id(const DsbProblemArgs*, const DsbBatchBuffers*, int, cudaStream_t, cudaEvent_t, unsigned long long*, DsbCoopState*, const double*, int*);
 DSB_DECLARE_LAUNCH(0) DSB_DECLARE_LAUNCH(1) DSB_DECLARE_LAUNCH(2) DSB_DECLARE_LAUNCH(3)
 DSB_DECLARE_LAUNCH(4) DSB_DECLARE_LAUNCH(5) DSB_DECLARE_LAUNCH(6) DSB_DECLARE_LAUNCH(7)
-DSB_DECLARE_LAUNCH(8)
+DSB_DECLARE_LAUNCH(8) DSB_DECLARE_LAUNCH(9) DSB_DECLARE_LAUNCH(10)
 #undef DSB_DECLARE_LAUNCH

@@ -147,7 +147,35 @@ inline cudaError_t dsb_launch_lu_solve(const double* a, const int32_t* piv, doub
     return cudaGetLastError();
 }
 
-// ---- instance-major storage (each instance's n x n column-major matrix contiguous): block-cooperative LU ----
+// ---- stand-alone kernels: the LinearSolver pair for instance-major storage ------------------------------
+// a: [nbatch][n*n] column-major per instance (the layout of the reference's CUDA matrices,
+// diffsol-la/src/matrix/cuda.rs), piv: [nbatch][n], rhs: [nbatch][n].
+__global__ void dsb_lu_factor_coop_kernel(double* __restrict__ a, int n, int64_t B, int32_t* __restrict__ piv,
+                                          int32_t* __restrict__ info) {
+    extern __shared__ unsigned char dsb_coop_smem[];
+    const CoopScratch sc = coop_carve(dsb_coop_smem, n);
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        const int bad = coop_lu_factor(a + (size_t)b * n * n, n, piv + (size_t)b * n, sc);
+        if (threadIdx.x == 0) info[b] = bad;
+        __syncthreads();
+    }
+}
+__global__ void dsb_lu_solve_coop_kernel(const double* __restrict__ a, const int32_t* __restrict__ piv,
+                                         double* __restrict__ rhs, int n, int64_t B, int32_t* __restrict__ info) {
+    extern __shared__ unsigned char dsb_coop_smem[];
+    const CoopScratch sc = coop_carve(dsb_coop_smem, n);
+    double* bs = sc.panel;                               // the panel area doubles as the right-hand side buffer
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) bs[i] = rhs[(size_t)b * n + i];
+        __syncthreads();
+        const bool ok = coop_lu_solve(a + (size_t)b * n * n, n, piv + (size_t)b * n, bs, sc);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) rhs[(size_t)b * n + i] = bs[i];
+        if (threadIdx.x == 0) info[b] = ok ? 0 : 1;
+        __syncthreads();
+    }
+}
+
+// ---- launchers for the instance-major kernels ----
 inline int dsb_coop_threads(int n) { int t = ((n + 31) / 32) * 32; return t > 256 ? 256 : t; }
 inline cudaError_t dsb_coop_grid(const void* kernel, int threads, size_t smem, int64_t B, unsigned* grid) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -22,6 +22,8 @@ enum dsb_model_id {
     DSB_MODEL_GAUSSIAN_DECAY = 6,       // n=10 np=10  test_models/gaussian_decay.rs:12-23
     DSB_MODEL_VAN_DER_POL = 7,          // n=2  np=1   (not in the reference; BASELINE.json config 3)
     DSB_MODEL_VAN_DER_POL_SCALED = 8,   // n=2  np=2   the same in scaled time tau = t / T, p = [mu, T]
+    DSB_MODEL_HEAT1D_DAE_256 = 9,       // n=256 np=3  1-D heat equation, boundary rows algebraic (BASELINE.json config 4)
+    DSB_MODEL_HEAT1D_DAE_32 = 10,       // n=32  np=3  the same on a coarse grid (test size)
     DSB_MODEL_COUNT
 };
 
@@ -204,6 +206,51 @@ struct ModelVanDerPolScaled {
     }
 };
 
+// 1-D heat equation u_t = D u_xx on [0, 1] with NS grid points, D = 0.1 (examples/pde-heat/src/main.rs:18),
+// as an index-1 DAE in the style of test_models/heat2d.rs: the two boundary rows are algebraic (0 = u - 0,
+// M = diag(0, 1, .., 1, 0)).  p = [height, x_left, x_right]: the initial condition is a plateau of that height
+// on [x_left, x_right] (BASELINE.json config 4: an initial-condition sweep).  Written component-wise
+// (`*_i`) so that the block-cooperative kernels evaluate one component per thread; the whole-vector closures
+// used by the CPU oracle call the same functions, so both sides share every expression.
+template <int NS>
+struct ModelHeat1dDae {
+    static constexpr int N = NS, NP = 3;
+    static constexpr bool HAS_MASS = true;
+    static constexpr bool COMPONENTWISE = true;
+    DSB_HD static double coef() { return 0.1 * (double)((NS - 1) * (NS - 1)); }
+    template <class X>
+    DSB_HD static double rhs_i(int i, const X& x, const double*, double) {
+        if (i == 0 || i == NS - 1) return x[i];
+        return coef() * (x[i - 1] - 2.0 * x[i] + x[i + 1]);
+    }
+    template <class X, class V>
+    DSB_HD static double jac_mul_i(int i, const X&, const double*, double, const V& v) {
+        if (i == 0 || i == NS - 1) return v[i];
+        return coef() * (v[i - 1] - 2.0 * v[i] + v[i + 1]);
+    }
+    template <class X>
+    DSB_HD static double mass_i(int i, const X& x, const double*, double, double beta, double yi) {
+        if (i == 0 || i == NS - 1) return beta * yi;
+        return x[i] + beta * yi;
+    }
+    DSB_HD static double init_i(int i, const double* p, double) {
+        const double xi = (double)i / (double)(NS - 1);
+        return (xi >= p[1] && xi <= p[2]) ? p[0] : 0.0;
+    }
+    DSB_HD static void rhs(const double* x, const double* p, double t, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = rhs_i(i, x, p, t);
+    }
+    DSB_HD static void jac_mul(const double* x, const double* p, double t, const double* v, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = jac_mul_i(i, x, p, t, v);
+    }
+    DSB_HD static void mass(const double* x, const double* p, double t, double beta, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = mass_i(i, x, p, t, beta, y[i]);
+    }
+    DSB_HD static void init(const double* p, double t, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = init_i(i, p, t);
+    }
+};
+
 // id -> functor type
 template <int ID> struct dsb_model_by_id;
 template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY> { typedef ModelExpDecay type; };
@@ -215,6 +262,8 @@ template <> struct dsb_model_by_id<DSB_MODEL_DYDT_Y2> { typedef ModelDydtY2<10> 
 template <> struct dsb_model_by_id<DSB_MODEL_GAUSSIAN_DECAY> { typedef ModelGaussianDecay<10> type; };
 template <> struct dsb_model_by_id<DSB_MODEL_VAN_DER_POL> { typedef ModelVanDerPol type; };
 template <> struct dsb_model_by_id<DSB_MODEL_VAN_DER_POL_SCALED> { typedef ModelVanDerPolScaled type; };
+template <> struct dsb_model_by_id<DSB_MODEL_HEAT1D_DAE_256> { typedef ModelHeat1dDae<256> type; };
+template <> struct dsb_model_by_id<DSB_MODEL_HEAT1D_DAE_32> { typedef ModelHeat1dDae<32> type; };
 
 // Compile-time dispatch over the registry: calls f.template operator()<Model>() for `id`.
 template <class F>
@@ -229,6 +278,8 @@ inline bool dsb_dispatch_model(int id, F&& f) {
         case DSB_MODEL_GAUSSIAN_DECAY: f.template operator()<ModelGaussianDecay<10>>(); return true;
         case DSB_MODEL_VAN_DER_POL: f.template operator()<ModelVanDerPol>(); return true;
         case DSB_MODEL_VAN_DER_POL_SCALED: f.template operator()<ModelVanDerPolScaled>(); return true;
+        case DSB_MODEL_HEAT1D_DAE_256: f.template operator()<ModelHeat1dDae<256>>(); return true;
+        case DSB_MODEL_HEAT1D_DAE_32: f.template operator()<ModelHeat1dDae<32>>(); return true;
         default: return false;
     }
 }

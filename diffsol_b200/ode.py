@@ -197,6 +197,11 @@ class BatchedSolver:
                                            ctypes.c_void_p(ys_dev_ptr), ctypes.c_void_p(stream or 0)))
         self._stats = self._status = None
 
+    def set_execution(self, mode):
+        """'auto' | 'lane' (one thread per instance, n <= 16) | 'block' (one thread block per instance)."""
+        capi.check(capi.lib().dsb_batch_set_execution(self._b, {"auto": 0, "lane": 1, "block": 2}[mode]))
+        return self
+
     def set_params(self):
         pr = self.problem
         if pr.nparams:

@@ -52,7 +52,7 @@ enum dsb_method {
 enum dsb_model {
     DSB_EXP_DECAY = 0, DSB_EXP_DECAY_ALGEBRAIC = 1, DSB_ROBERTSON_DAE = 2, DSB_ROBERTSON_ODE = 3,
     DSB_ROBERTSON_ODE_G3 = 4, DSB_DYDT_Y2 = 5, DSB_GAUSSIAN_DECAY = 6, DSB_VAN_DER_POL = 7,
-    DSB_VAN_DER_POL_SCALED = 8
+    DSB_VAN_DER_POL_SCALED = 8, DSB_HEAT1D_DAE_256 = 9, DSB_HEAT1D_DAE_32 = 10
 };
 
 /* ---- statistics: one row of DSB_NSTATS int64 per instance.  Indices 0-9 are the fields of
@@ -128,6 +128,10 @@ typedef struct dsb_batch dsb_batch;
 int dsb_batch_new(const dsb_problem* p, int64_t nbatch, int32_t device, dsb_batch** out);
 int dsb_batch_free(dsb_batch* b);
 int64_t dsb_batch_size(const dsb_batch* b);
+
+/* Execution model of the integrator kernels: 0 = automatic (one thread per instance for n <= 16, one thread
+ * block per instance above), 1 = thread per instance, 2 = block per instance.  Results are identical. */
+int dsb_batch_set_execution(dsb_batch* b, int32_t mode);
 
 /* Parameters, instance-major: params[b*nparams + j], exactly how the reference concatenates batched
  * parameters (diffsol/src/ode_equations/test_models/exponential_decay.rs:297-304). */

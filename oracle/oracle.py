@@ -40,6 +40,8 @@ MODELS = {
     "gaussian_decay": 6,
     "van_der_pol": 7,
     "van_der_pol_scaled": 8,
+    "heat1d_dae_256": 9,
+    "heat1d_dae_32": 10,
 }
 
 

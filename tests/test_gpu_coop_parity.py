@@ -1,0 +1,94 @@
+"""GPU parity tests of the block-per-instance (cooperative) BDF path: the reference's small test problems
+forced through it, and the heat-equation DAE (BASELINE config 4) at n = 32 and n = 256."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "reference_snapshots.json")) as f:
+    GOLD = json.load(f)
+BDF_CASES = [c for c in GOLD["cases"] if c["method"] == "bdf" and not c["coloring"]]
+
+
+@pytest.fixture(scope="module")
+def dsb():
+    import diffsol_b200
+    from diffsol_b200 import capi
+    capi.require_device()
+    return diffsol_b200
+
+
+def heat_params(idx):
+    from diffsol_b200 import sweeps
+    return np.stack([1.0 + sweeps.uniform(idx, 0), 0.1 + 0.3 * sweeps.uniform(idx, 1), 0.6 + 0.3 * sweeps.uniform(idx, 2)], axis=1)
+
+
+HEAT_T_EVAL = np.arange(1, 101) / 100.0 * 0.99
+
+
+@pytest.mark.parametrize("case", BDF_CASES, ids=[c["name"] for c in BDF_CASES])
+def test_reference_snapshots_block_per_instance(dsb, oracle, case):
+    from test_oracle_golden import expected_stats, solution_points
+    t, ystar = solution_points(case["points"])
+    nb = 3
+    b = dsb.OdeBuilder().rhs_implicit(case["model"]).rtol(case["rtol"]).atol(case["atol"]).nbatch(nb)
+    if len(case["p"]):
+        b = b.p(case["p"])
+    solver = b.build().bdf().set_execution("block")
+    ys = solver.step_and_interpolate(t)
+    assert (solver.status() == 0).all()
+    for k in range(nb):
+        assert solver.get_statistics(k) == expected_stats(case), case["cite"]
+    desc = oracle.make_desc(case["model"], rtol=case["rtol"], atol=case["atol"], powmode=1)
+    rc, ys_o, stats_o, fin = oracle.harness(desc, case["p"], t)
+    assert rc == 0
+    for k in range(nb):
+        assert np.array_equal(ys[k], ys_o), case["name"]
+
+
+@pytest.mark.parametrize("model,tol", [("robertson_ode", "ROBERTSON_ODE_TOL"), ("robertson_dae", "ROBERTSON_DAE_TOL")])
+def test_robertson_sweep_block_equals_lane_equals_oracle(dsb, oracle, model, tol):
+    from diffsol_b200 import sweeps
+    B = 600
+    tolkw = getattr(sweeps, tol)
+    p = sweeps.robertson_sweep(np.arange(B))
+    prob = dsb.OdeBuilder().rhs_implicit(model).p(p).rtol(tolkw["rtol"]).atol(tolkw["atol"]).build()
+    s_block = prob.bdf().set_execution("block")
+    ys_b = s_block.solve_dense(sweeps.ROBERTSON_T_EVAL)
+    s_lane = prob.bdf().set_execution("lane")
+    ys_l = s_lane.solve_dense(sweeps.ROBERTSON_T_EVAL)
+    desc = oracle.make_desc(model, powmode=1, **tolkw)
+    ys_o, stats_o, status_o = oracle.batch_solve_dense(desc, p, sweeps.ROBERTSON_T_EVAL)
+    for s, ys in ((s_block, ys_b), (s_lane, ys_l)):
+        assert np.array_equal(s.status(), status_o)
+        assert np.array_equal(s.statistics_array()[:, :13], stats_o[:, :13])
+        assert np.array_equal(ys, ys_o)
+
+
+@pytest.mark.parametrize("model,B", [("heat1d_dae_32", 96), ("heat1d_dae_256", 12)])
+def test_heat_dae_sweep_bit_exact(dsb, oracle, model, B):
+    """BASELINE config 4 (1-D heat equation, boundary rows algebraic, initial-condition sweep) at sizes the
+    oracle finishes in seconds: counters, status and all 100 dense-output columns bitwise."""
+    p = heat_params(np.arange(B))
+    solver = dsb.OdeBuilder().rhs_implicit(model).p(p).rtol(1e-6).atol(1e-6).build().bdf()
+    ys = solver.solve_dense(HEAT_T_EVAL)
+    desc = oracle.make_desc(model, powmode=1, rtol=1e-6, atol=1e-6)
+    ys_o, stats_o, status_o = oracle.batch_solve_dense(desc, p, HEAT_T_EVAL)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o)
+    # physics sanity: heat is lost through the cold boundaries, nothing grows
+    assert (ys[:, -1].max(axis=1) < p[:, 0]).all()
+
+
+def test_unsupported_combinations_fail_loudly(dsb):
+    p = heat_params(np.arange(2))
+    prob = dsb.OdeBuilder().rhs_implicit("heat1d_dae_32").p(p).build()
+    with pytest.raises(dsb.DiffsolB200Error):
+        prob.tr_bdf2().solve_dense([0.5])           # SDIRK has no block-per-instance kernel yet
+    with pytest.raises(dsb.DiffsolB200Error):
+        prob.bdf().set_execution("lane").solve_dense([0.5])
