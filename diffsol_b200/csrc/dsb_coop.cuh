@@ -49,7 +49,7 @@ __device__ __forceinline__ CoopScratch coop_carve(void* smem, int n) {
 // In-place LU of the n x n column-major matrix A (global memory, leading dimension n) by the whole block.
 // piv[i] = row swapped with row i (== i: no swap).  Returns (to every thread) 0, or k+1 for the first
 // zero pivot column k (nalgebra leaves that column untouched and continues).
-static __device__ int coop_lu_factor(double* __restrict__ A, int n, int* __restrict__ piv, const CoopScratch& sc) {
+static __device__ __noinline__ int coop_lu_factor(double* __restrict__ A, int n, int* __restrict__ piv, const CoopScratch& sc) {
     const int tid = threadIdx.x, T = blockDim.x;
     const int lane = tid & 31, wid = tid >> 5, nwarps = (T + 31) >> 5;
     int first_bad = 0;
@@ -109,19 +109,21 @@ static __device__ int coop_lu_factor(double* __restrict__ A, int n, int* __restr
             const double inv_diag = 1.0 / P[(size_t)i * m + i];
             for (int lr = i + 1 + tid; lr < m; lr += T) P[(size_t)i * m + lr] *= inv_diag;
             __syncthreads();
-            // rank-1 update of the remaining panel columns
-            const int ncols = kb - i - 1, nrows = m - i - 1;
-            for (int e = tid; e < ncols * nrows; e += T) {
-                const int c = i + 1 + e / nrows, lr = i + 1 + e % nrows;
-                const double mpk = -P[(size_t)c * m + i];
-                P[(size_t)c * m + lr] = mpk * P[(size_t)i * m + lr] + P[(size_t)c * m + lr];
+            // rank-1 update of the remaining panel columns: a thread owns rows, walks the columns
+            for (int lr = i + 1 + tid; lr < m; lr += T) {
+                const double l = P[(size_t)i * m + lr];
+                for (int c = i + 1; c < kb; ++c) {
+                    const double mpk = -P[(size_t)c * m + i];
+                    P[(size_t)c * m + lr] = mpk * l + P[(size_t)c * m + lr];
+                }
             }
             __syncthreads();
         }
         // ---- 3. write the panel back ----
         for (int c = 0; c < kb; ++c)
             for (int lr = tid; lr < m; lr += T) A[(size_t)(k0 + c) * n + k0 + lr] = P[(size_t)c * m + lr];
-        // ---- 4. row swaps for the columns outside the panel; U12 = L11^-1 A12 (one thread per column) ----
+        // ---- 4. row swaps for the columns outside the panel; U12 = L11^-1 A12 (one thread per column, the
+        //         kb-long column segment held in registers) ----
         for (int c = tid; c < n; c += T) {
             if (c >= k0 && c < k0 + kb) continue;
             double* col = A + (size_t)c * n;
@@ -130,34 +132,70 @@ static __device__ int coop_lu_factor(double* __restrict__ A, int n, int* __restr
                 if (p != k0 + i) { const double tmp = col[k0 + i]; col[k0 + i] = col[p]; col[p] = tmp; }
             }
             if (c >= k0 + kb) {
-                for (int i = 0; i < kb; ++i) {
-                    const double mpk = -col[k0 + i];
-                    for (int r = i + 1; r < kb; ++r) col[k0 + r] = mpk * P[(size_t)i * m + r] + col[k0 + r];
+                if (kb == DSB_COOP_NB) {
+                    double seg[DSB_COOP_NB];
+#pragma unroll
+                    for (int r = 0; r < DSB_COOP_NB; ++r) seg[r] = col[k0 + r];
+#pragma unroll
+                    for (int i = 0; i < DSB_COOP_NB; ++i) {
+                        const double mpk = -seg[i];
+#pragma unroll
+                        for (int r = i + 1; r < DSB_COOP_NB; ++r) seg[r] = mpk * P[(size_t)i * m + r] + seg[r];
+                    }
+#pragma unroll
+                    for (int r = 0; r < DSB_COOP_NB; ++r) col[k0 + r] = seg[r];
+                } else {
+                    for (int i = 0; i < kb; ++i) {
+                        const double mpk = -col[k0 + i];
+                        for (int r = i + 1; r < kb; ++r) col[k0 + r] = mpk * P[(size_t)i * m + r] + col[k0 + r];
+                    }
                 }
             }
         }
         __syncthreads();
         // ---- 5. trailing update A22[r][c] = sum_i (-U[i][c]) * L[r][i] + A22[r][c], i ascending ----
+        // warps own groups of 4 columns (4 independent accumulation chains per lane); lanes own rows in chunks
+        // of 32; L21 rows come from the staged panel, U12 entries are warp-uniform (broadcast) loads
         const int r0 = k0 + kb;
         const int m2 = n - r0;
         if (m2 > 0) {
-            // warps own columns; lanes own rows in chunks of 32; L21 rows are read from the staged panel
             for (int rc = 0; rc < m2; rc += 32) {
                 const int r = r0 + rc + lane;
                 const bool live = r < n;
                 double l[DSB_COOP_NB];
 #pragma unroll
                 for (int i = 0; i < DSB_COOP_NB; ++i) l[i] = (live && i < kb) ? P[(size_t)i * m + (r - k0)] : 0.0;
-                for (int c = r0 + wid; c < n; c += nwarps) {
-                    double* col = A + (size_t)c * n;
-                    double a = live ? col[r] : 0.0;
+                for (int c = r0 + 4 * wid; c < n; c += 4 * nwarps) {
+                    const int nc = (n - c < 4) ? (n - c) : 4;
+                    double* col0 = A + (size_t)c * n;
+                    double* col1 = A + (size_t)(c + (nc > 1 ? 1 : 0)) * n;
+                    double* col2 = A + (size_t)(c + (nc > 2 ? 2 : 0)) * n;
+                    double* col3 = A + (size_t)(c + (nc > 3 ? 3 : 0)) * n;
+                    double a0 = live ? col0[r] : 0.0, a1 = live ? col1[r] : 0.0, a2 = live ? col2[r] : 0.0, a3 = live ? col3[r] : 0.0;
                     if (kb == DSB_COOP_NB) {
 #pragma unroll
-                        for (int i = 0; i < DSB_COOP_NB; ++i) { const double mpk = -col[k0 + i]; a = mpk * l[i] + a; }
+                        for (int i = 0; i < DSB_COOP_NB; ++i) {
+                            const double li = l[i];
+                            a0 = (-col0[k0 + i]) * li + a0;
+                            a1 = (-col1[k0 + i]) * li + a1;
+                            a2 = (-col2[k0 + i]) * li + a2;
+                            a3 = (-col3[k0 + i]) * li + a3;
+                        }
                     } else {
-                        for (int i = 0; i < kb; ++i) { const double mpk = -col[k0 + i]; a = mpk * l[i] + a; }
+                        for (int i = 0; i < kb; ++i) {
+                            const double li = l[i];
+                            a0 = (-col0[k0 + i]) * li + a0;
+                            a1 = (-col1[k0 + i]) * li + a1;
+                            a2 = (-col2[k0 + i]) * li + a2;
+                            a3 = (-col3[k0 + i]) * li + a3;
+                        }
                     }
-                    if (live) col[r] = a;
+                    if (live) {
+                        col0[r] = a0;
+                        if (nc > 1) col1[r] = a1;
+                        if (nc > 2) col2[r] = a2;
+                        if (nc > 3) col3[r] = a3;
+                    }
                 }
             }
         }
@@ -168,7 +206,7 @@ static __device__ int coop_lu_factor(double* __restrict__ A, int n, int* __restr
 
 // Solve with the factors of coop_lu_factor; b lives in SHARED memory (n doubles).  Returns false (to every
 // thread) when U has a zero on its diagonal (nalgebra's solve_mut returns false; b is then unspecified).
-static __device__ bool coop_lu_solve(const double* __restrict__ LU, int n, const int* __restrict__ piv, double* b,
+static __device__ __noinline__ bool coop_lu_solve(const double* __restrict__ LU, int n, const int* __restrict__ piv, double* b,
                               const CoopScratch& sc) {
     const int tid = threadIdx.x, T = blockDim.x;
     if (tid == 0) {
@@ -176,20 +214,38 @@ static __device__ bool coop_lu_solve(const double* __restrict__ LU, int n, const
         sc.bcast[2] = 1;
     }
     __syncthreads();
-    // forward substitution with the unit lower triangle, column-axpy form, in blocks of 32 columns
+    // forward substitution with the unit lower triangle, column-axpy form, in blocks of 32 columns.  Every
+    // thread first loads the (up to) 32 factor entries its row needs (independent loads in flight together),
+    // then runs the dependent multiply-add chain out of registers.
     for (int k0 = 0; k0 < n; k0 += 32) {
         const int kb = (n - k0 < 32) ? (n - k0) : 32;
+        double lv[32];
+        const int rb = k0 + kb + tid;                     // this thread's row below the block (if any)
         if (tid < 32) {                                   // diagonal block: one warp, lane = row within the block
             const int r = k0 + tid;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) lv[i] = (i < kb && tid < kb) ? LU[(size_t)(k0 + i) * n + r] : 0.0;
             double br = (tid < kb) ? b[r] : 0.0;
-            for (int i = 0; i < kb; ++i) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
                 const double coeff = __shfl_sync(0xffffffffu, br, i);
-                if (tid > i && tid < kb) br = (-coeff) * LU[(size_t)(k0 + i) * n + r] + br;
+                if (i < kb && tid > i && tid < kb) br = (-coeff) * lv[i] + br;
             }
             if (tid < kb) b[r] = br;
         }
+        // (rows below are one per thread for n <= 32 + blockDim; the generic loop handles larger n)
+        if (rb < n) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) lv[i] = (i < kb) ? LU[(size_t)(k0 + i) * n + rb] : 0.0;
+        }
         __syncthreads();
-        for (int r = k0 + kb + tid; r < n; r += T) {      // rows below: each row accumulates in ascending i
+        if (rb < n) {
+            double br = b[rb];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (i < kb) br = (-b[k0 + i]) * lv[i] + br;
+            b[rb] = br;
+        }
+        for (int r = rb + T; r < n; r += T) {
             double br = b[r];
             for (int i = 0; i < kb; ++i) br = (-b[k0 + i]) * LU[(size_t)(k0 + i) * n + r] + br;
             b[r] = br;
@@ -201,24 +257,42 @@ static __device__ bool coop_lu_solve(const double* __restrict__ LU, int n, const
     for (int kbk = nblk - 1; kbk >= 0; --kbk) {
         const int k0 = kbk * 32;
         const int kb = (n - k0 < 32) ? (n - k0) : 32;
+        double lv[32];
         if (tid < 32) {
             const int r = k0 + tid;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) lv[i] = (i < kb && tid < kb) ? LU[(size_t)(k0 + i) * n + r] : 0.0;
             double br = (tid < kb) ? b[r] : 0.0;
             bool ok = true;
-            for (int i = kb - 1; i >= 0; --i) {
-                const double diag = LU[(size_t)(k0 + i) * n + k0 + i];
-                if (diag == 0.0) { ok = false; break; }           // uniform across the warp
-                double coeff = 0.0;
-                if (tid == i) { coeff = br / diag; br = coeff; }
-                coeff = __shfl_sync(0xffffffffu, coeff, i);
-                if (tid < i) br = (-coeff) * LU[(size_t)(k0 + i) * n + r] + br;
+#pragma unroll
+            for (int i = 31; i >= 0; --i) {
+                if (i < kb && ok) {
+                    const double diag = __shfl_sync(0xffffffffu, lv[i], i);       // U[i][i] lives in lane i
+                    if (diag == 0.0) ok = false;                                    // uniform across the warp
+                    else {
+                        double coeff = 0.0;
+                        if (tid == i) { coeff = br / diag; br = coeff; }
+                        coeff = __shfl_sync(0xffffffffu, coeff, i);
+                        if (tid < i) br = (-coeff) * lv[i] + br;
+                    }
+                }
             }
             if (tid < kb) b[r] = br;
             if (!ok && tid == 0) sc.bcast[2] = 0;
         }
+        if (tid < k0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) lv[i] = (i < kb) ? LU[(size_t)(k0 + i) * n + tid] : 0.0;
+        }
         __syncthreads();
         if (sc.bcast[2] == 0) return false;
-        for (int r = tid; r < k0; r += T) {               // rows above: ascending order of application is i DESCENDING
+        if (tid < k0) {                                    // rows above: contributions in DESCENDING i
+            double br = b[tid];
+#pragma unroll
+            for (int i = 31; i >= 0; --i) if (i < kb) br = (-b[k0 + i]) * lv[i] + br;
+            b[tid] = br;
+        }
+        for (int r = tid + T; r < k0; r += T) {
             double br = b[r];
             for (int i = kb - 1; i >= 0; --i) br = (-b[k0 + i]) * LU[(size_t)(k0 + i) * n + r] + br;
             b[r] = br;

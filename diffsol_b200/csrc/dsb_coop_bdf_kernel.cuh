@@ -81,12 +81,12 @@ template <class M>
 struct CoopBdfLayout {
     static constexpr int N = M::N;
     static constexpr int NVEC = DSB_NDIFF + 9;          // D[8], y, yp, ycur, psi, dlt, tmp, scr, atol, dy
-    static constexpr int THREADS = (N + 31) / 32 * 32 > 256 ? 256 : (N + 31) / 32 * 32;
+    static constexpr int THREADS = (N + 31) / 32 * 32 > 128 ? 128 : (N + 31) / 32 * 32;
     static size_t smem_bytes() { return (size_t)NVEC * N * sizeof(double) + coop_lu_smem_bytes_host(N) + 64; }
 };
 
 template <class M>
-__global__ void __launch_bounds__(CoopBdfLayout<M>::THREADS)
+__global__ void __launch_bounds__(CoopBdfLayout<M>::THREADS, 2)
 dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __grid_constant__ DsbBatchBuffers bb,
                                 const __grid_constant__ DsbCoopWorkspace ws, unsigned long long* __restrict__ work_counter) {
     constexpr int N = M::N;

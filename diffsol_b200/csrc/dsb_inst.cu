@@ -25,6 +25,8 @@ static cudaError_t launch_coop_bdf(const DsbProblemArgs* pa, const DsbBatchBuffe
     const size_t smem = CoopBdfLayout<M>::smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(dsb_coop_bdf_solve_dense_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(dsb_coop_bdf_solve_dense_kernel<M>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

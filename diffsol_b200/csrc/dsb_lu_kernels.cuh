@@ -150,7 +150,7 @@ inline cudaError_t dsb_launch_lu_solve(const double* a, const int32_t* piv, doub
 // ---- stand-alone kernels: the LinearSolver pair for instance-major storage ------------------------------
 // a: [nbatch][n*n] column-major per instance (the layout of the reference's CUDA matrices,
 // diffsol-la/src/matrix/cuda.rs), piv: [nbatch][n], rhs: [nbatch][n].
-__global__ void dsb_lu_factor_coop_kernel(double* __restrict__ a, int n, int64_t B, int32_t* __restrict__ piv,
+__global__ void __launch_bounds__(128, 3) dsb_lu_factor_coop_kernel(double* __restrict__ a, int n, int64_t B, int32_t* __restrict__ piv,
                                           int32_t* __restrict__ info) {
     extern __shared__ unsigned char dsb_coop_smem[];
     const CoopScratch sc = coop_carve(dsb_coop_smem, n);
@@ -160,11 +160,13 @@ __global__ void dsb_lu_factor_coop_kernel(double* __restrict__ a, int n, int64_t
         __syncthreads();
     }
 }
-__global__ void dsb_lu_solve_coop_kernel(const double* __restrict__ a, const int32_t* __restrict__ piv,
+__global__ void __launch_bounds__(128, 4) dsb_lu_solve_coop_kernel(const double* __restrict__ a, const int32_t* __restrict__ piv,
                                          double* __restrict__ rhs, int n, int64_t B, int32_t* __restrict__ info) {
     extern __shared__ unsigned char dsb_coop_smem[];
-    const CoopScratch sc = coop_carve(dsb_coop_smem, n);
-    double* bs = sc.panel;                               // the panel area doubles as the right-hand side buffer
+    CoopScratch sc;                                      // no panel here: [b (n doubles) | reduction scratch]
+    sc.panel = (double*)dsb_coop_smem;
+    sc.redv = sc.panel + n; sc.redi = (int*)(sc.redv + 32); sc.bcast = sc.redi + 32;
+    double* bs = sc.panel;
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) bs[i] = rhs[(size_t)b * n + i];
         __syncthreads();
@@ -176,9 +178,11 @@ __global__ void dsb_lu_solve_coop_kernel(const double* __restrict__ a, const int
 }
 
 // ---- launchers for the instance-major kernels ----
-inline int dsb_coop_threads(int n) { int t = ((n + 31) / 32) * 32; return t > 256 ? 256 : t; }
+inline int dsb_coop_threads(int n) { int t = ((n + 31) / 32) * 32; return t > 128 ? 128 : t; }
 inline cudaError_t dsb_coop_grid(const void* kernel, int threads, size_t smem, int64_t B, unsigned* grid) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
@@ -204,7 +208,7 @@ inline cudaError_t dsb_launch_lu_solve_im(const double* a, const int32_t* piv, d
                                           cudaStream_t s) {
     if (n > DSB_COOP_MAX_N) return cudaErrorInvalidValue;
     const int threads = dsb_coop_threads(n);
-    const size_t smem = coop_lu_smem_bytes_host(n);
+    const size_t smem = coop_lu_smem_bytes_host(n) - (size_t)n * (DSB_COOP_NB - 1) * sizeof(double);   // only b, no panel
     unsigned grid = 1;
     cudaError_t e = dsb_coop_grid((const void*)dsb_lu_solve_coop_kernel, threads, smem, B, &grid);
     if (e != cudaSuccess) return e;

@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Time one BASELINE.json configuration other than the headline one (which bench.py owns) on one GPU:
+   python tools/bench_config.py heat256 [batch]   |  vdp [batch]  |  robertson_dae [batch]
+Prints ms per pass, instances/s, Newton-it/s and the algorithmic-byte HBM roofline fraction."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import diffsol_b200 as ds  # noqa: E402
+from diffsol_b200 import capi, sweeps  # noqa: E402
+
+capi.require_device()
+which = sys.argv[1]
+peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+if which.startswith("heat"):
+    n = int(which[4:])
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
+    idx = np.arange(B)
+    p = np.stack([1.0 + sweeps.uniform(idx, 0), 0.1 + 0.3 * sweeps.uniform(idx, 1), 0.6 + 0.3 * sweeps.uniform(idx, 2)], axis=1)
+    t_eval = np.arange(1, 101) / 100.0 * 0.99
+    prob = ds.OdeBuilder().rhs_implicit("heat1d_dae_%d" % n).p(p).rtol(1e-6).atol(1e-6).build()
+    solver, npar, mass_words = prob.bdf(), 3, n * n
+elif which == "vdp":
+    n, npar, mass_words = 2, 2, 0
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 4000000
+    p = sweeps.van_der_pol_scaled_sweep(np.arange(B))
+    t_eval = sweeps.VAN_DER_POL_T_EVAL
+    prob = ds.OdeBuilder().rhs_implicit("van_der_pol_scaled").p(p).rtol(1e-4).atol([1e-6]).build()
+    solver = prob.tr_bdf2()
+elif which == "robertson_dae":
+    n, npar, mass_words = 3, 3, 3
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 1000000
+    p = sweeps.robertson_sweep(np.arange(B))
+    t_eval = sweeps.ROBERTSON_T_EVAL
+    prob = ds.OdeBuilder().rhs_implicit("robertson_dae").p(p).rtol(1e-4).atol([1e-8, 1e-6, 1e-6]).build()
+    solver = prob.bdf()
+else:
+    raise SystemExit("unknown configuration")
+
+times = []
+for it in range(3):
+    t0 = time.perf_counter()
+    ys = solver.solve_dense(t_eval)
+    times.append((time.perf_counter() - t0, solver.last_kernel_ms()))
+st = solver.statistics_array()
+status = solver.status()
+kms = min(k for _, k in times[1:])
+nli, setups, me = int(st[:, 8].sum()), int(st[:, 0].sum()), int(st[:, 12].sum())
+attempts = int(st[:, 6].sum() + st[:, 7].sum() + st[:, 9].sum())
+nt = len(t_eval)
+alg = (nli * (8 * (n * n + 4 * n + npar) + 4 * n) + setups * (8 * (2 * n * n + mass_words) + 4 * n)
+       + me * 8 * (n * n + n + npar) + attempts * 8 * 19 * n + B * nt * 8 * n)
+print(json.dumps({"config": which, "n": n, "batch": B, "kernel_ms": kms, "e2e_ms": min(t for t, _ in times[1:]) * 1e3,
+                  "instances_per_s": B / kms * 1e3, "newton_iters_per_s": nli / kms * 1e3,
+                  "steps_mean": float(st[:, 6].mean()), "nli_mean": float(st[:, 8].mean()), "setups_mean": float(st[:, 0].mean()),
+                  "failed": int((status != 0).sum()), "algorithmic_GB": alg / 1e9,
+                  "achieved_GBps": alg / kms / 1e6, "frac_hbm": alg / kms / 1e6 / peak}))
