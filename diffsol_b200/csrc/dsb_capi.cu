@@ -444,6 +444,7 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     build_tableau(method, &pa.rk);
     pa.quorum = DSB_DEFAULT_QUORUM;
     pa.sched_mode = 1; pa.quorum_post = 1; pa.post_num = 0; pa.post_den = 1;
+    if (const char* q = getenv("DSB_COOP_DENSE_ONLY")) pa.coop_dense_only = atoi(q);
     if (const char* q = getenv("DSB_SCHED_MODE")) pa.sched_mode = atoi(q);
     if (const char* q = getenv("DSB_Q_POST")) pa.quorum_post = atoi(q);
     if (const char* q = getenv("DSB_POST_NUM")) pa.post_num = atoi(q);

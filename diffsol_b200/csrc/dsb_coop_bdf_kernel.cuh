@@ -82,7 +82,7 @@ struct CoopBdfLayout {
     static constexpr int N = M::N;
     static constexpr int NVEC = DSB_NDIFF + 9;          // D[8], y, yp, ycur, psi, dlt, tmp, scr, atol, dy
     static constexpr int THREADS = (N + 31) / 32 * 32 > 128 ? 128 : (N + 31) / 32 * 32;
-    static size_t smem_bytes() { return (size_t)NVEC * N * sizeof(double) + coop_lu_smem_bytes_host(N) + 64; }
+    static size_t smem_bytes() { return (size_t)NVEC * N * sizeof(double) + coop_lu_smem_bytes_host(N) + 4 * (size_t)N * sizeof(int) + 64; }
 };
 
 template <class M>
@@ -105,6 +105,9 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
     double* const atolv = scr + N;
     double* const dys = atolv + N;                       // state.dy (initialisation only)
     const CoopScratch sc = coop_carve(dys + N, N);
+    CoopExtents ex;                                      // non-zero ranges of the current LU (structure-adaptive path)
+    ex.rfirst = sc.bcast + 4; ex.rlast = ex.rfirst + N; ex.cfirst = ex.rlast + N; ex.clast = ex.cfirst + N;
+    __shared__ int s_adaptive, s_packed;
     __shared__ double s_red;                             // broadcast of a sequential reduction
     __shared__ long long s_inst;
     __shared__ double s_p[NP > 0 ? NP : 1];
@@ -136,6 +139,38 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
         }
         __syncthreads();
         return s_red;
+    };
+
+    // LU of LUg: banded structure (lower + upper bandwidth <= 32) takes the structure-adaptive warp routine, anything
+    // else the blocked dense one.  Both give the same bits; the choice is remembered for the solves.
+    auto lu_factor = [&]() {
+        __syncthreads();
+        const int band = coop_scan_structure(LUg, N, ex, sc.bcast);
+        if (tid == 0) s_adaptive = (pa.coop_dense_only == 0 && band <= 32 && N > 32) ? 1 : 0;
+        __syncthreads();
+        if (s_adaptive) {
+            if (tid < 32) warp_lu_factor_adaptive(LUg, N, pivg, ex);
+            __syncthreads();
+            const int code = coop_pack_band(LUg, N, ex, sc.panel, sc.bcast);     // the panel scratch is free on this path
+            if (tid == 0) s_packed = code;
+            __syncthreads();
+        } else {
+            coop_lu_factor(LUg, N, pivg, sc);
+            __syncthreads();
+        }
+    };
+    auto lu_solve = [&](double* b) -> bool {
+        if (s_adaptive) {
+            __syncthreads();
+            if (tid < 32) {
+                const bool ok = s_packed ? warp_lu_solve_packed(sc.panel, s_packed, N, pivg, b)
+                                         : warp_lu_solve_adaptive(LUg, N, pivg, b, ex);
+                if (tid == 0) sc.bcast[2] = ok ? 1 : 0;
+            }
+            __syncthreads();
+            return sc.bcast[2] != 0;
+        }
+        return coop_lu_solve(LUg, N, pivg, b, sc);
     };
 
     while (true) {
@@ -203,8 +238,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                 __syncthreads();
                 // the InitOp Jacobian is constant: factor once, keep a copy is unnecessary because LU setups
                 // beyond the first only re-factor the same matrix (bitwise the same factors)
-                coop_lu_factor(LUg, N, pivg, sc);
-                __syncthreads();
+                lu_factor();
                 // y_tmp (yc) = (dy at differential idx, y at algebraic idx); yerr (yp) = y_tmp; y0 copy in psi
                 for (int i = tid; i < N; i += T) { yc[i] = is_alg(i) ? ys[i] : dys[i]; yp[i] = yc[i]; psi[i] = ys[i]; }
                 __syncthreads();
@@ -238,7 +272,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                         if (pa.opt.ic_use_linesearch) {
                             if (conv.niter == 0) {
                                 fun(yc);
-                                if (!coop_lu_solve(LUg, N, pivg, dlt, sc)) { result = 2; break; }
+                                if (!lu_solve(dlt)) { result = 2; break; }
                                 ls_norm = dsb_sqrt(squared_norm(dlt, yp));
                                 if (conv.check_norm(ls_norm) == LANE_CONVERGED) {
                                     for (int i = tid; i < N; i += T) yc[i] -= dlt[i];
@@ -259,7 +293,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                                 for (int li = 0; li < pa.opt.ic_max_linesearch_iterations; ++li) {
                                     for (int q = tid; q < N; q += T) yc[q] = (-alpha) * Dm[q] + yc[q];
                                     fun(yc);
-                                    if (!coop_lu_solve(LUg, N, pivg, dlt, sc)) { ls_status = 2; break; }
+                                    if (!lu_solve(dlt)) { ls_status = 2; break; }
                                     const double new_norm = dsb_sqrt(squared_norm(dlt, yp));
                                     const double phi1 = new_norm * new_norm * 0.5;
                                     if (phi1 <= phi0 - c_armijo * alpha * two_phi0) {
@@ -277,7 +311,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                             }
                         } else {
                             fun(yc);
-                            if (!coop_lu_solve(LUg, N, pivg, dlt, sc)) { result = 2; break; }
+                            if (!lu_solve(dlt)) { result = 2; break; }
                             for (int i = tid; i < N; i += T) yc[i] -= dlt[i];
                             res = conv.check_new_iteration(dsb_sqrt(squared_norm(dlt, yp)));
                         }
@@ -361,8 +395,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                 LUg[e] = Jg[e] * mc + m_ji;
             }
             __syncthreads();
-            coop_lu_factor(LUg, N, pivg, sc);
-            __syncthreads();
+            lu_factor();
         };
         auto jacobian_updates = [&](double cc, int kind) {
             bool did_update = false;
@@ -528,7 +561,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                             dlt[i] = M::HAS_MASS ? E::mass_i(i, tmpv, p, t_predict, mc, dlt[i]) : (tmpv[i] + mc * dlt[i]);
                         }
                         __syncthreads();
-                        if (!coop_lu_solve(LUg, N, pivg, dlt, sc)) break;
+                        if (!lu_solve(dlt)) break;
                         for (int i = tid; i < N; i += T) yc[i] -= dlt[i];
                         const double norm = dsb_sqrt(squared_norm(dlt, yp));
                         const int s = conv.check_new_iteration(norm);
