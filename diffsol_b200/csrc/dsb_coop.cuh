@@ -303,198 +303,107 @@ static __device__ __noinline__ bool coop_lu_solve(const double* __restrict__ LU,
 }
 
 
-// ---- structure-adaptive variant --------------------------------------------------------------------------
+// ---- banded variant -------------------------------------------------------------------------------------------
 // PDE-type systems (BASELINE configs 4 and 5) have banded Jacobians: almost every multiplier and pivot-row
-// entry of the dense elimination is an exact zero, and `a = (-0) * l + a` leaves `a` untouched.  The routines
-// below run the SAME unblocked right-looking elimination and the same column-axpy substitutions, but only
-// over the index ranges that can hold non-zeros.  The ranges (per column: first / last non-zero row, per row:
-// first / last non-zero column) are conservative upper bounds maintained through the row swaps and the
-// fill-in of every elimination step, so every skipped operation is one whose multiplier or pivot-row entry is
-// exactly zero: factors, pivots and solutions stay bit-identical to the dense algorithm (and to nalgebra's),
-// at O(n b^2) instead of O(n^3) work and O(n b) instead of O(n^2) bytes per solve.  They are executed by the
-// first warp of the block (the per-column work is a handful of elements; block-wide barriers would dominate).
-struct CoopExtents {
-    int* rfirst;   // [n] first non-zero row of each column
-    int* rlast;    // [n] last non-zero row of each column
-    int* cfirst;   // [n] first non-zero column of each row
-    int* clast;    // [n] last non-zero column of each row
-};
+// entry of the dense elimination is an exact zero, and `a = (-0) * l + a` leaves `a` untouched.  When the
+// iteration matrix has lower / upper bandwidths kl / ku with 2 kl + ku + 1 <= 32 it is factored in LAPACK band
+// storage held in SHARED memory (ab[j * 32 + kv + r - j], kv = kl + ku: room for the fill-in of partial
+// pivoting), by the first warp of the block, at O(n kl (kl + ku)) work, and the substitutions of every Newton
+// iteration read the band at shared-memory latency: O(n (2 kl + ku)) instead of O(n^2) bytes from HBM.
+//
+// Same arithmetic as the dense algorithm: first maximum as pivot, reciprocal-pivot scaling, updates
+// `a = (-u) * l + a` in ascending pivot order, column-axpy substitutions; every operation that is skipped has an
+// exactly zero multiplier or pivot-row entry.  Unlike nalgebra, the row interchanges are not applied to the
+// multipliers of earlier columns (the dgbtf2 convention); the forward substitution therefore interleaves the
+// interchanges with the column updates.  Every right-hand-side entry still meets the same multipliers in the
+// same order, so the solutions are bit-identical to nalgebra's.
 
-// Scan A (n x n, column-major, global) for its non-zero ranges; every thread of the block takes part.
-// Returns (to every thread) lower + upper bandwidth.
-static __device__ __noinline__ int coop_scan_structure(const double* __restrict__ A, int n, const CoopExtents& ex, int* bcast) {
+// kl, ku of the union of the non-zero patterns of J and (optionally) M; every thread of the block takes part.
+static __device__ __noinline__ void coop_band_scan(const double* __restrict__ J, const double* __restrict__ Mm, int n, int* kl_ku) {
     const int tid = threadIdx.x, T = blockDim.x;
-    for (int i = tid; i < n; i += T) { ex.rfirst[i] = n; ex.rlast[i] = -1; ex.cfirst[i] = n; ex.clast[i] = -1; }
+    if (tid == 0) { kl_ku[0] = 0; kl_ku[1] = 0; }
     __syncthreads();
-    for (int r = tid; r < n; r += T) {                   // a thread owns a row: loads are coalesced across the warp
-        int cf = n, cl = -1;
+    int kl = 0, ku = 0;
+    for (int r = tid; r < n; r += T) {                    // a thread owns a row: loads are coalesced across the warp
         for (int c = 0; c < n; ++c) {
-            if (A[(size_t)c * n + r] != 0.0) {
-                if (c < cf) cf = c;
-                cl = c;
-                atomicMin(&ex.rfirst[c], r);
-                atomicMax(&ex.rlast[c], r);
-            }
+            const bool nz = J[(size_t)c * n + r] != 0.0 || (Mm != nullptr && Mm[(size_t)c * n + r] != 0.0);
+            if (nz) { if (r - c > kl) kl = r - c; if (c - r > ku) ku = c - r; }
         }
-        ex.cfirst[r] = cf; ex.clast[r] = cl;
     }
+    atomicMax(&kl_ku[0], kl);
+    atomicMax(&kl_ku[1], ku);
     __syncthreads();
-    if (tid == 0) {
-        int kl = 0, ku = 0;
-        for (int i = 0; i < n; ++i) {
-            if (ex.rlast[i] - i > kl) kl = ex.rlast[i] - i;
-            if (ex.clast[i] - i > ku) ku = ex.clast[i] - i;
-        }
-        bcast[3] = kl + ku;
-    }
-    __syncthreads();
-    return bcast[3];
 }
 
-// Executed by warp 0 only.  Same contract as coop_lu_factor.
-static __device__ __noinline__ int warp_lu_factor_adaptive(double* __restrict__ A, int n, int* __restrict__ piv, const CoopExtents& ex) {
+// dgbtf2-style band LU in shared memory; executed by warp 0 only.  piv[j] = row interchanged with row j.
+static __device__ __noinline__ int warp_band_factor(double* ab, int n, int kl, int ku, int* __restrict__ piv) {
     const int lane = threadIdx.x & 31;
+    const int kv = kl + ku;
     int first_bad = 0;
-    for (int i = 0; i < n; ++i) {
-        const int re = ex.rlast[i];
+    int ju = 0;                                            // last column touched by the fill-in so far
+    for (int j = 0; j < n; ++j) {
+        const int km = (kl < n - 1 - j) ? kl : (n - 1 - j);
+        // pivot: first maximum of |A[j + d][j]|, d = 0 .. km
         double bv = -1.0; int bi = 0x7fffffff;
-        for (int r = i + lane; r <= re; r += 32) {
-            const double v = dsb_abs(A[(size_t)i * n + r]);
-            if (v > bv) { bv = v; bi = r; }
-        }
+        if (lane <= km) { bv = dsb_abs(ab[j * 32 + kv + lane]); bi = lane; if (!(bv == bv)) { bv = -1.0; bi = 0x7fffffff; } }
         for (int o = 16; o > 0; o >>= 1) {
             const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
-        const double dii = A[(size_t)i * n + i];
-        int p = (bi == 0x7fffffff) ? i : bi;
-        if (dii != dii) p = i;                               // NaN diagonal keeps the diagonal
-        const double diag = A[(size_t)i * n + p];
-        if (diag == 0.0) { if (lane == 0) piv[i] = i; if (first_bad == 0) first_bad = i + 1; __syncwarp(); continue; }
-        if (lane == 0) piv[i] = p;
-        if (p != i) {
-            const int cmin = min(ex.cfirst[i], ex.cfirst[p]);
-            const int cmax = max(ex.clast[i], ex.clast[p]);
-            __syncwarp();
-            for (int c = cmin + lane; c <= cmax; c += 32) {
-                const double vi = A[(size_t)c * n + i], vp = A[(size_t)c * n + p];
-                A[(size_t)c * n + i] = vp; A[(size_t)c * n + p] = vi;
-                if (vi != 0.0) atomicMax(&ex.rlast[c], p);       // a non-zero moved down to row p
-                if (vp != 0.0) atomicMin(&ex.rfirst[c], i);      // a non-zero moved up to row i
-            }
-            __syncwarp();
-            if (lane == 0) {
-                const int a = ex.cfirst[i], b = ex.clast[i];
-                ex.cfirst[i] = ex.cfirst[p]; ex.clast[i] = ex.clast[p];
-                ex.cfirst[p] = a; ex.clast[p] = b;
+        const double dii = ab[j * 32 + kv];
+        int jp = (bi == 0x7fffffff) ? 0 : bi;
+        if (dii != dii) jp = 0;                            // NaN diagonal keeps the diagonal
+        const double diag = ab[j * 32 + kv + jp];
+        if (diag == 0.0) { if (lane == 0) piv[j] = j; if (first_bad == 0) first_bad = j + 1; __syncwarp(); continue; }
+        if (lane == 0) piv[j] = j + jp;
+        { const int cand = (j + ku + jp < n - 1) ? (j + ku + jp) : (n - 1); if (cand > ju) ju = cand; }
+        if (jp != 0) {
+            const int c = j + lane;                         // columns j .. ju (at most kv + 1 <= 32 of them)
+            if (c <= ju) {
+                const double a = ab[c * 32 + kv + j - c], b = ab[c * 32 + kv + j + jp - c];
+                ab[c * 32 + kv + j - c] = b; ab[c * 32 + kv + j + jp - c] = a;
             }
             __syncwarp();
         }
-        const int rend = ex.rlast[i];                        // rows (i, rend] hold the multipliers
-        const int cend = ex.clast[i];                        // columns (i, cend] hold the pivot row
-        const double inv_diag = 1.0 / A[(size_t)i * n + i];
-        for (int r = i + 1 + lane; r <= rend; r += 32) A[(size_t)i * n + r] *= inv_diag;
-        __syncwarp();
-        const int nrows = rend - i, ncols = cend - i;
-        if (nrows > 0 && ncols > 0) {
-            for (int e = lane; e < nrows * ncols; e += 32) {
-                const int c = i + 1 + e / nrows, r = i + 1 + e % nrows;
-                const double mpk = -A[(size_t)c * n + i];
-                A[(size_t)c * n + r] = mpk * A[(size_t)i * n + r] + A[(size_t)c * n + r];
+        if (km > 0) {
+            const double inv_diag = 1.0 / ab[j * 32 + kv];
+            if (lane >= 1 && lane <= km) ab[j * 32 + kv + lane] *= inv_diag;
+            __syncwarp();
+            const int ncols = ju - j;                       // columns j+1 .. ju
+            for (int e = lane; e < ncols * km; e += 32) {
+                const int c = j + 1 + e / km, d = 1 + e % km;       // row j + d
+                const double mpk = -ab[c * 32 + kv + j - c];
+                ab[c * 32 + kv + j + d - c] = mpk * ab[j * 32 + kv + d] + ab[c * 32 + kv + j + d - c];
             }
-            // fill-in: the touched rows may now reach column cend, the touched columns row rend
-            for (int r = i + 1 + lane; r <= rend; r += 32) atomicMax(&ex.clast[r], cend);
-            for (int c = i + 1 + lane; c <= cend; c += 32) atomicMax(&ex.rlast[c], rend);
+            __syncwarp();
         }
-        __syncwarp();
     }
     return first_bad;
 }
 
-// Executed by warp 0 only; b in shared memory.  Same contract as coop_lu_solve.
-static __device__ __noinline__ bool warp_lu_solve_adaptive(const double* __restrict__ LU, int n, const int* __restrict__ piv, double* b,
-                                                           const CoopExtents& ex) {
+// dgbtrs-style substitutions on the shared-memory band; executed by warp 0 only; b in shared memory.
+static __device__ __noinline__ bool warp_band_solve(const double* ab, int n, int kl, int ku, const int* __restrict__ piv, double* b) {
     const int lane = threadIdx.x & 31;
-    if (lane == 0) {
-        for (int i = 0; i < n; ++i) { const int p = piv[i]; if (p != i) { const double tmp = b[i]; b[i] = b[p]; b[p] = tmp; } }
-    }
-    __syncwarp();
-    for (int i = 0; i + 1 < n; ++i) {
-        const int re = ex.rlast[i];
-        if (re > i) {
-            const double mc = -b[i];
-            for (int r = i + 1 + lane; r <= re; r += 32) b[r] = mc * LU[(size_t)i * n + r] + b[r];
+    const int kv = kl + ku;
+    if (kl > 0) {
+        for (int j = 0; j + 1 < n; ++j) {
+            const int lm = (kl < n - 1 - j) ? kl : (n - 1 - j);
+            const int l = piv[j];
+            if (l != j) { __syncwarp(); if (lane == 0) { const double tmp = b[l]; b[l] = b[j]; b[j] = tmp; } __syncwarp(); }
+            const double mc = -b[j];
+            if (lane >= 1 && lane <= lm) b[j + lane] = mc * ab[j * 32 + kv + lane] + b[j + lane];
             __syncwarp();
         }
     }
     for (int i = n - 1; i >= 0; --i) {
-        const double diag = LU[(size_t)i * n + i];
+        const double diag = ab[i * 32 + kv];
         if (diag == 0.0) return false;
         const double coeff = b[i] / diag;
         __syncwarp();
         if (lane == 0) b[i] = coeff;
-        const double mc = -coeff;
-        for (int r = ex.rfirst[i] + lane; r < i; r += 32) b[r] = mc * LU[(size_t)i * n + r] + b[r];
-        __syncwarp();
-    }
-    return true;
-}
-
-// Pack the factors' non-zero band into shared memory after an adaptive factorisation, so that the two
-// substitutions of every Newton iteration read it at shared-memory latency instead of one L2 round trip per
-// column: pk[i * 32 + d], d < wl: L[i + 1 + d][i];  pk[i * 32 + wl + e], e < wu: U[i - e][i] (e = 0: diagonal).
-// Returns (to every thread) wl | (wu << 8), or 0 when the band does not fit (wl + wu > 32).
-static __device__ __noinline__ int coop_pack_band(const double* __restrict__ LU, int n, const CoopExtents& ex, double* pk, int* bcast) {
-    const int tid = threadIdx.x, T = blockDim.x;
-    if (tid == 0) {
-        int wl = 0, wu = 1;
-        for (int i = 0; i < n; ++i) {
-            if (ex.rlast[i] - i > wl) wl = ex.rlast[i] - i;
-            if (i - ex.rfirst[i] + 1 > wu) wu = i - ex.rfirst[i] + 1;
-        }
-        bcast[3] = (wl + wu <= 32) ? (wl | (wu << 8)) : 0;
-    }
-    __syncthreads();
-    const int code = bcast[3];
-    if (code == 0) return 0;
-    const int wl = code & 255, wu = code >> 8;
-    for (int e = tid; e < n * 32; e += T) {
-        const int i = e >> 5, d = e & 31;
-        double v = 0.0;
-        if (d < wl) { const int r = i + 1 + d; if (r < n) v = LU[(size_t)i * n + r]; }
-        else if (d < wl + wu) { const int r = i - (d - wl); if (r >= 0) v = LU[(size_t)i * n + r]; }
-        pk[e] = v;
-    }
-    __syncthreads();
-    return code;
-}
-
-// The substitutions on the packed band (warp 0 only).  Entries inside the packed width but outside a
-// column's own range are exact zeros of the factors: `b = (-c) * 0 + b` leaves b unchanged.
-static __device__ __noinline__ bool warp_lu_solve_packed(const double* pk, int code, int n, const int* __restrict__ piv, double* b) {
-    const int lane = threadIdx.x & 31;
-    const int wl = code & 255, wu = code >> 8;
-    if (lane == 0) {
-        for (int i = 0; i < n; ++i) { const int p = piv[i]; if (p != i) { const double tmp = b[i]; b[i] = b[p]; b[p] = tmp; } }
-    }
-    __syncwarp();
-    if (wl > 0) {
-        for (int i = 0; i + 1 < n; ++i) {
-            const double mc = -b[i];
-            const int r = i + 1 + lane;
-            if (lane < wl && r < n) b[r] = mc * pk[i * 32 + lane] + b[r];
-            __syncwarp();
-        }
-    }
-    for (int i = n - 1; i >= 0; --i) {
-        const double diag = pk[i * 32 + wl];
-        if (diag == 0.0) return false;
-        const double coeff = b[i] / diag;
-        __syncwarp();
-        if (lane == 0) b[i] = coeff;
-        const int r = i - 1 - lane;                       // lane e - 1 handles U[i - e][i], e = 1 .. wu - 1
-        if (lane + 1 < wu && r >= 0) b[r] = (-coeff) * pk[i * 32 + wl + 1 + lane] + b[r];
+        const int r = i - 1 - lane;                         // lane e - 1 handles U[i - e][i], e = 1 .. kv
+        if (lane < kv && r >= 0) b[r] = (-coeff) * ab[i * 32 + kv - 1 - lane] + b[r];
         __syncwarp();
     }
     return true;

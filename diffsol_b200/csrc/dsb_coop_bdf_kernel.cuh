@@ -82,7 +82,7 @@ struct CoopBdfLayout {
     static constexpr int N = M::N;
     static constexpr int NVEC = DSB_NDIFF + 9;          // D[8], y, yp, ycur, psi, dlt, tmp, scr, atol, dy
     static constexpr int THREADS = (N + 31) / 32 * 32 > 128 ? 128 : (N + 31) / 32 * 32;
-    static size_t smem_bytes() { return (size_t)NVEC * N * sizeof(double) + coop_lu_smem_bytes_host(N) + 4 * (size_t)N * sizeof(int) + 64; }
+    static size_t smem_bytes() { return (size_t)NVEC * N * sizeof(double) + coop_lu_smem_bytes_host(N) + 64; }
 };
 
 template <class M>
@@ -105,9 +105,8 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
     double* const atolv = scr + N;
     double* const dys = atolv + N;                       // state.dy (initialisation only)
     const CoopScratch sc = coop_carve(dys + N, N);
-    CoopExtents ex;                                      // non-zero ranges of the current LU (structure-adaptive path)
-    ex.rfirst = sc.bcast + 4; ex.rlast = ex.rfirst + N; ex.cfirst = ex.rlast + N; ex.clast = ex.cfirst + N;
-    __shared__ int s_adaptive, s_packed;
+    __shared__ int s_band[2];                            // kl, ku of the current J / M
+    __shared__ int s_banded;                             // 1: the current factors are the shared-memory band factors
     __shared__ double s_red;                             // broadcast of a sequential reduction
     __shared__ long long s_inst;
     __shared__ double s_p[NP > 0 ? NP : 1];
@@ -141,32 +140,17 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
         return s_red;
     };
 
-    // LU of LUg: banded structure (lower + upper bandwidth <= 32) takes the structure-adaptive warp routine, anything
-    // else the blocked dense one.  Both give the same bits; the choice is remembered for the solves.
+    // dense path: LU of LUg (global memory, blocked); banded path: see reset_jacobian
     auto lu_factor = [&]() {
         __syncthreads();
-        const int band = coop_scan_structure(LUg, N, ex, sc.bcast);
-        if (tid == 0) s_adaptive = (pa.coop_dense_only == 0 && band <= 32 && N > 32) ? 1 : 0;
+        if (tid == 0) s_banded = 0;
+        coop_lu_factor(LUg, N, pivg, sc);
         __syncthreads();
-        if (s_adaptive) {
-            if (tid < 32) warp_lu_factor_adaptive(LUg, N, pivg, ex);
-            __syncthreads();
-            const int code = coop_pack_band(LUg, N, ex, sc.panel, sc.bcast);     // the panel scratch is free on this path
-            if (tid == 0) s_packed = code;
-            __syncthreads();
-        } else {
-            coop_lu_factor(LUg, N, pivg, sc);
-            __syncthreads();
-        }
     };
     auto lu_solve = [&](double* b) -> bool {
-        if (s_adaptive) {
+        if (s_banded) {
             __syncthreads();
-            if (tid < 32) {
-                const bool ok = s_packed ? warp_lu_solve_packed(sc.panel, s_packed, N, pivg, b)
-                                         : warp_lu_solve_adaptive(LUg, N, pivg, b, ex);
-                if (tid == 0) sc.bcast[2] = ok ? 1 : 0;
-            }
+            if (tid < 32) { const bool ok = warp_band_solve(sc.panel, N, s_band[0], s_band[1], pivg, b); if (tid == 0) sc.bcast[2] = ok ? 1 : 0; }
             __syncthreads();
             return sc.bcast[2] != 0;
         }
@@ -387,15 +371,38 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                 }
                 jacobian_is_stale = false;
                 __syncthreads();
+                coop_band_scan(Jg, M::HAS_MASS ? Mg : nullptr, N, s_band);       // structure only changes when J / M do
             }
             const double mc = -c;
-            for (int e = tid; e < N * N; e += T) {
-                const int j = e / N, i = e % N;
-                const double m_ji = M::HAS_MASS ? Mg[e] : ((i == j) ? 1.0 : 0.0);
-                LUg[e] = Jg[e] * mc + m_ji;
+            const int kl = s_band[0], ku = s_band[1];
+            if (pa.coop_dense_only == 0 && N > 32 && 2 * kl + ku + 1 <= 32) {
+                // banded: build A = M - cJ directly in LAPACK band storage in shared memory, factor there
+                const int kv = kl + ku;
+                double* ab = sc.panel;
+                __syncthreads();
+                for (int e = tid; e < N * 32; e += T) {
+                    const int j = e >> 5, d = e & 31;
+                    const int r = j - kv + d;
+                    double v = 0.0;
+                    if (d <= kv + kl && r >= 0 && r < N && r >= j - ku) {
+                        const double m_ji = M::HAS_MASS ? Mg[(size_t)j * N + r] : ((r == j) ? 1.0 : 0.0);
+                        v = Jg[(size_t)j * N + r] * mc + m_ji;
+                    }
+                    ab[e] = v;
+                }
+                __syncthreads();
+                if (tid < 32) warp_band_factor(ab, N, kl, ku, pivg);
+                if (tid == 0) s_banded = 1;
+                __syncthreads();
+            } else {
+                for (int e = tid; e < N * N; e += T) {
+                    const int j = e / N, i = e % N;
+                    const double m_ji = M::HAS_MASS ? Mg[e] : ((i == j) ? 1.0 : 0.0);
+                    LUg[e] = Jg[e] * mc + m_ji;
+                }
+                __syncthreads();
+                lu_factor();
             }
-            __syncthreads();
-            lu_factor();
         };
         auto jacobian_updates = [&](double cc, int kind) {
             bool did_update = false;
