@@ -199,7 +199,7 @@ int fill_problem_args(const dsb_problem& pr, int64_t B, int nt, DsbProblemArgs* 
 const dsb_launch_fn g_launch_table[DSB_MODEL_COUNT] = {
     dsb_launch_model_0, dsb_launch_model_1, dsb_launch_model_2, dsb_launch_model_3,
     dsb_launch_model_4, dsb_launch_model_5, dsb_launch_model_6, dsb_launch_model_7,
-    dsb_launch_model_8, dsb_launch_model_9, dsb_launch_model_10,
+    dsb_launch_model_8, dsb_launch_model_9, dsb_launch_model_10, dsb_launch_model_11,
 };
 
 // instance-major <-> batch-major re-layout on the device (the host-facing layouts follow the

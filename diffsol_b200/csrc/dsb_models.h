@@ -24,6 +24,7 @@ enum dsb_model_id {
     DSB_MODEL_VAN_DER_POL_SCALED = 8,   // n=2  np=2   the same in scaled time tau = t / T, p = [mu, T]
     DSB_MODEL_HEAT1D_DAE_256 = 9,       // n=256 np=3  1-D heat equation, boundary rows algebraic (BASELINE.json config 4)
     DSB_MODEL_HEAT1D_DAE_32 = 10,       // n=32  np=3  the same on a coarse grid (test size)
+    DSB_MODEL_SPM = 11,                 // n=42  np=1  single-particle battery model, book/src/primer/src/spm.ds (BASELINE config 5)
     DSB_MODEL_COUNT
 };
 
@@ -251,6 +252,66 @@ struct ModelHeat1dDae {
     }
 };
 
+// Single-particle battery model (SPM) of the reference's battery example
+// (examples/physics-based-battery-simulation/src/main.rs, model text book/src/primer/src/spm.ds), states only:
+// u = [discharge capacity, throughput capacity, 20 negative-particle concentrations, 20 positive-particle
+// concentrations]; p = [applied current I].  F is linear: two tridiagonal radial-diffusion operators plus a flux
+// forcing on the surface node.  (The model's `out` / `stop` functions -- terminal voltage and its cut-offs --
+// are not part of the implicit step loop and are not built.)  Products are summed in the order the model text
+// lists the non-zeros of a row: super-diagonal, diagonal, sub-diagonal.
+#include "dsb_spm_tables.inc"
+struct dsb_spm_row { double sub, diag, sup; };
+static const dsb_spm_row dsb_spm_neg_host[20] = { DSB_SPM_NEG_ROWS };
+static const dsb_spm_row dsb_spm_pos_host[20] = { DSB_SPM_POS_ROWS };
+#if defined(__CUDACC__)
+static __device__ const dsb_spm_row dsb_spm_neg_dev[20] = { DSB_SPM_NEG_ROWS };
+static __device__ const dsb_spm_row dsb_spm_pos_dev[20] = { DSB_SPM_POS_ROWS };
+#endif
+struct ModelSpm {
+    static constexpr int N = 42, NP = 1;
+    static constexpr bool HAS_MASS = false;
+    static constexpr bool COMPONENTWISE = true;
+    DSB_HD static dsb_spm_row row(int i) {        // i in 2 .. 41
+#if defined(__CUDA_ARCH__)
+        return i < 22 ? dsb_spm_neg_dev[i - 2] : dsb_spm_pos_dev[i - 22];
+#else
+        return i < 22 ? dsb_spm_neg_host[i - 2] : dsb_spm_pos_host[i - 22];
+#endif
+    }
+    template <class X>
+    DSB_HD static double diffusion_i(int i, const X& x) {
+        const dsb_spm_row c = row(i);
+        const int k = (i < 22) ? i - 2 : i - 22;
+        double acc = 0.0;
+        if (k < 19) acc = c.sup * x[i + 1];
+        acc = (k < 19) ? (c.diag * x[i] + acc) : (c.diag * x[i]);
+        if (k > 0) acc = c.sub * x[i - 1] + acc;
+        return acc;
+    }
+    template <class X>
+    DSB_HD static double rhs_i(int i, const X& x, const double* p, double) {
+        if (i == 0) return 0.0002777777777777778 * p[0];
+        if (i == 1) return 0.0002777777777777778 * dsb_abs(p[0]);
+        const double flux = (i == 21) ? DSB_SPM_NEG_FLUX * (-520607810.21082705 * p[0])
+                          : (i == 41) ? DSB_SPM_POS_FLUX * (243644455.17866704 * p[0]) : 0.0;
+        return diffusion_i(i, x) + flux;
+    }
+    template <class X, class V>
+    DSB_HD static double jac_mul_i(int i, const X&, const double*, double, const V& v) {
+        if (i < 2) return 0.0;
+        return diffusion_i(i, v);
+    }
+    template <class X>
+    DSB_HD static double mass_i(int i, const X& x, const double*, double, double beta, double yi) { return x[i] + beta * yi; }
+    DSB_HD static double init_i(int i, const double*, double) {
+        return i < 2 ? 0.0 : (i < 22 ? 0.8000000000000016 : 0.6000000000000001);
+    }
+    DSB_HD static void rhs(const double* x, const double* p, double t, double* y) { for (int i = 0; i < N; ++i) y[i] = rhs_i(i, x, p, t); }
+    DSB_HD static void jac_mul(const double* x, const double* p, double t, const double* v, double* y) { for (int i = 0; i < N; ++i) y[i] = jac_mul_i(i, x, p, t, v); }
+    DSB_HD static void mass(const double* x, const double* p, double t, double beta, double* y) { for (int i = 0; i < N; ++i) y[i] = mass_i(i, x, p, t, beta, y[i]); }
+    DSB_HD static void init(const double* p, double t, double* y) { for (int i = 0; i < N; ++i) y[i] = init_i(i, p, t); }
+};
+
 // id -> functor type
 template <int ID> struct dsb_model_by_id;
 template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY> { typedef ModelExpDecay type; };
@@ -264,6 +325,7 @@ template <> struct dsb_model_by_id<DSB_MODEL_VAN_DER_POL> { typedef ModelVanDerP
 template <> struct dsb_model_by_id<DSB_MODEL_VAN_DER_POL_SCALED> { typedef ModelVanDerPolScaled type; };
 template <> struct dsb_model_by_id<DSB_MODEL_HEAT1D_DAE_256> { typedef ModelHeat1dDae<256> type; };
 template <> struct dsb_model_by_id<DSB_MODEL_HEAT1D_DAE_32> { typedef ModelHeat1dDae<32> type; };
+template <> struct dsb_model_by_id<DSB_MODEL_SPM> { typedef ModelSpm type; };
 
 // Compile-time dispatch over the registry: calls f.template operator()<Model>() for `id`.
 template <class F>
@@ -280,6 +342,7 @@ inline bool dsb_dispatch_model(int id, F&& f) {
         case DSB_MODEL_VAN_DER_POL_SCALED: f.template operator()<ModelVanDerPolScaled>(); return true;
         case DSB_MODEL_HEAT1D_DAE_256: f.template operator()<ModelHeat1dDae<256>>(); return true;
         case DSB_MODEL_HEAT1D_DAE_32: f.template operator()<ModelHeat1dDae<32>>(); return true;
+        case DSB_MODEL_SPM: f.template operator()<ModelSpm>(); return true;
         default: return false;
     }
 }

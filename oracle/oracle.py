@@ -42,6 +42,7 @@ MODELS = {
     "van_der_pol_scaled": 8,
     "heat1d_dae_256": 9,
     "heat1d_dae_32": 10,
+    "spm": 11,
 }
 
 

@@ -92,3 +92,22 @@ def test_unsupported_combinations_fail_loudly(dsb):
         prob.tr_bdf2().solve_dense([0.5])           # SDIRK has no block-per-instance kernel yet
     with pytest.raises(dsb.DiffsolB200Error):
         prob.bdf().set_execution("lane").solve_dense([0.5])
+
+
+def test_spm_battery_sweep_bit_exact(dsb, oracle):
+    """BASELINE config 5 (single-particle battery model of the reference's battery example, n = 42, applied
+    current sweep I = 0.6 + 0.8 u) at a size the oracle finishes in seconds.  States only: the model's
+    output / stop functions are outside the implicit step loop."""
+    from diffsol_b200 import sweeps
+    B = 300
+    current = (0.6 + 0.8 * sweeps.uniform(np.arange(B), 0)).reshape(-1, 1)
+    t_eval = np.arange(1, 13) * 300.0
+    solver = dsb.OdeBuilder().rhs_implicit("spm").p(current).build().bdf()
+    ys = solver.solve_dense(t_eval)
+    desc = oracle.make_desc("spm", powmode=1)
+    ys_o, stats_o, status_o = oracle.batch_solve_dense(desc, current, t_eval)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o)
+    # discharge capacity is I t / 3600 exactly up to the integration tolerance
+    assert np.allclose(ys[:, -1, 0], current[:, 0] * 3600.0 / 3600.0, rtol=1e-5)
