@@ -299,7 +299,10 @@ def main():
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
             "gpu_launches": c[8],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "dsb_bdf_solve_dense_kernel<ModelRobertsonOde<1>>",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
+                         # (profiles/r1_v5_bdf_kernel_ncu_summary.txt: 31.4 MB for a 200 000-instance launch), per instance
+                         "traffic": 157.0 * B, "traffic_source": "ncu capture profiles/r1_v5 (157 B/instance), scaled to this launch",
+                         "kernel": "dsb_bdf_solve_dense_kernel<ModelRobertsonOde<1>>",
                          "kernel_ms": integ_mean_ms, "algorithmic_bytes_per_launch": alg,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "note": "state is register/shared-memory resident; the kernel is FP64-issue/latency bound, not HBM bound"},
