@@ -62,7 +62,7 @@ struct dsb_batch {
     int last_launches = 0;
     bool have_timing = false;
     int sparsity_probe_jac_muls = 0;
-    DsbCoopState coop = {0, nullptr, 0, nullptr, 0};
+    DsbCoopState coop = {0, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, 0};
 };
 
 namespace {
@@ -142,12 +142,14 @@ void build_tableau(int method, DsbSdirkTableau* t) {
 // non-zeros", jacobian/mod.rs:32), so it is found once on the host with the model's own functor.
 struct ColoringOf {
     const dsb_problem* pr; DsbProblemArgs* pa; int* probes;
+    std::vector<int32_t>* color_full; std::vector<uint8_t>* nz_full;      // any n: for the block-per-instance path
     template <class M> void operator()() {
         constexpr int N = M::N;
         constexpr int NP = M::NP;
         double p[NP > 0 ? NP : 1];
         for (int j = 0; j < NP; ++j) p[j] = 1.0;
-        double y0[N], v[N], col[N];
+        std::vector<double> y0v(N), vv(N), colv(N);
+        double* y0 = y0v.data(); double* v = vv.data(); double* col = colv.data();
         M::init(p, pr->t0, y0);
         std::vector<std::pair<int, int>> non_zeros;
         for (int i = 0; i < N; ++i) { v[i] = 0.0; col[i] = 0.0; }
@@ -175,12 +177,19 @@ struct ColoringOf {
         int max_color = 0;
         for (int c : result) if (c > max_color) max_color = c;
         pa->ncolors = max_color;
-        for (int j = 0; j < N; ++j) { pa->color_of_col[j] = result[j] - 1; pa->nz_rows_of_col[j] = 0; }
-        for (auto& ij : non_zeros) pa->nz_rows_of_col[ij.second] |= (1ull << ij.first);
+        if (N <= DSB_MAX_STATES) {
+            for (int j = 0; j < N; ++j) { pa->color_of_col[j] = result[j] - 1; pa->nz_rows_of_col[j] = 0; }
+            for (auto& ij : non_zeros) pa->nz_rows_of_col[ij.second] |= (1ull << ij.first);
+        }
+        // dense form: colour of every column (-1: the column has no non-zero and is never seeded), pattern bytes
+        color_full->assign(N, -1);
+        nz_full->assign((size_t)N * N, 0);
+        for (auto& ij : non_zeros) { (*nz_full)[(size_t)ij.second * N + ij.first] = 1; (*color_full)[ij.second] = result[ij.second] - 1; }
     }
 };
 
-int fill_problem_args(const dsb_problem& pr, int64_t B, int nt, DsbProblemArgs* pa, int* probes) {
+int fill_problem_args(const dsb_problem& pr, int64_t B, int nt, DsbProblemArgs* pa, int* probes,
+                      std::vector<int32_t>* color_full, std::vector<uint8_t>* nz_full) {
     std::memset(pa, 0, sizeof(*pa));
     pa->nbatch = B; pa->nt = nt;
     pa->rtol = pr.rtol; pa->t0 = pr.t0; pa->h0 = pr.h0;
@@ -190,7 +199,7 @@ int fill_problem_args(const dsb_problem& pr, int64_t B, int nt, DsbProblemArgs* 
     pa->use_coloring = pr.use_coloring;
     *probes = 0;
     if (pr.use_coloring) {
-        ColoringOf f{&pr, pa, probes};
+        ColoringOf f{&pr, pa, probes, color_full, nz_full};
         if (!dsb_dispatch_model(pr.model, f)) return DSB_BAD_ARG;
     }
     return DSB_OK;
@@ -387,7 +396,7 @@ int dsb_batch_free(dsb_batch* b) {
     cudaSetDevice(b->device);
     cudaFree(b->params); cudaFree(b->y0); cudaFree(b->dy0); cudaFree(b->h0);
     cudaFree(b->fin_t); cudaFree(b->fin_h); cudaFree(b->fin_order);
-    cudaFree(b->stats); cudaFree(b->status); cudaFree(b->work_counter); cudaFree(b->coop.ws_mem); cudaFree(b->coop.atol_dev); cudaFree(b->t_eval); cudaFree(b->ys_own); cudaFree(b->stage);
+    cudaFree(b->stats); cudaFree(b->status); cudaFree(b->work_counter); cudaFree(b->coop.ws_mem); cudaFree(b->coop.atol_dev); cudaFree(b->coop.color_dev); cudaFree(b->t_eval); cudaFree(b->ys_own); cudaFree(b->stage);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->ev_mid) cudaEventDestroy(b->ev_mid);
@@ -438,7 +447,8 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     DSB_CUDA(cudaMemcpyAsync(b->t_eval, t_eval, (size_t)nt * 8, cudaMemcpyHostToDevice, stream));
     DsbProblemArgs pa;
     int probes = 0;
-    if (fill_problem_args(b->prob, b->B, nt, &pa, &probes) != DSB_OK) return fail(DSB_BAD_ARG, "unknown model id");
+    std::vector<int32_t> color_full; std::vector<uint8_t> nz_full;
+    if (fill_problem_args(b->prob, b->B, nt, &pa, &probes, &color_full, &nz_full) != DSB_OK) return fail(DSB_BAD_ARG, "unknown model id");
     b->sparsity_probe_jac_muls = probes;
     pa.free_running = free_running;
     build_tableau(method, &pa.rk);
@@ -461,7 +471,9 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     if (b->prob.model < 0 || b->prob.model >= DSB_MODEL_COUNT) return fail(DSB_BAD_ARG, "unknown model id");
     std::vector<double> atol_full((size_t)b->prob.n);
     for (int i = 0; i < b->prob.n; ++i) atol_full[i] = b->prob.atol.size() == 1 ? b->prob.atol[0] : b->prob.atol[i];
-    if (const char* q = getenv("DSB_EXEC_MODE")) b->coop.exec_mode = atoi(q);      // test hook: 1 = lane kernels, 2 = cooperative
+    if (const char* q = getenv("DSB_EXEC_MODE")) b->coop.exec_mode = atoi(q);
+    b->coop.color_host = color_full.empty() ? nullptr : color_full.data();
+    b->coop.nz_host = nz_full.empty() ? nullptr : nz_full.data();      // test hook: 1 = lane kernels, 2 = cooperative
     cudaError_t lerr = g_launch_table[b->prob.model](&pa, &bb, method, stream, b->ev_mid, b->work_counter, &b->coop,
                                                      atol_full.data(), &b->last_launches);
     if (lerr == cudaErrorNotSupported) return fail(DSB_ERR, "this method / option is not available for this system size (cooperative path: BDF with dense Jacobian only)");

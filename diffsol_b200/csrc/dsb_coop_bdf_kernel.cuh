@@ -75,6 +75,8 @@ struct DsbCoopWorkspace {
     double* lu;       // [nblocks][n*n]  factors of M - cJ
     int32_t* piv;     // [nblocks][n]
     const double* atol;   // [n]
+    const int32_t* color; // [n] colour of every column (-1: empty column), or nullptr: dense assembly
+    const uint8_t* nz;    // [n*n] column-major sparsity pattern of df/dy
 };
 
 template <class M>
@@ -122,6 +124,9 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
     int32_t* const pivg = ws.piv + (size_t)blockIdx.x * N;
 
     for (int i = tid; i < N; i += T) atolv[i] = ws.atol[i];
+    if (ws.color != nullptr) {                             // coloured assembly only ever writes pattern entries
+        for (int e = tid; e < N * N; e += T) Jg[e] = 0.0;
+    }
 
     // sum_i term_i / n with term_i = (x_i / (|y_i| rtol + atol_i))^2, terms in parallel, the sum sequential
     auto squared_norm = [&](const double* x, const double* yref) -> double {
@@ -178,14 +183,29 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
         st.v[DSB_STAT_RHS_CALLS] += 1;
         __syncthreads();
 
-        // df/dy at (x, tt) into Jg, column by column (op/nonlinear_op.rs:211-220); colouring is not
-        // supported on this path
+        // df/dy at (x, tt) into Jg: one jac_mul per column (op/nonlinear_op.rs:211-220) or, with colouring, one per
+        // colour (jacobian/mod.rs:236-256: seed every column of the colour, scatter the product through the pattern)
         auto eval_jacobian = [&](const double* x, double tt) {
             st.v[DSB_STAT_RHS_MATRIX_EVALS] += 1;
-            st.v[DSB_STAT_RHS_JAC_MULS] += N;
-            for (int j = 0; j < N; ++j) {
-                const CoopUnitVec v{j};
-                for (int i = tid; i < N; i += T) Jg[(size_t)j * N + i] = E::jac_mul_i(i, x, p, tt, v);
+            if (ws.color != nullptr) {
+                st.v[DSB_STAT_RHS_JAC_MULS] += pa.ncolors;
+                for (int c = 0; c < pa.ncolors; ++c) {
+                    __syncthreads();
+                    for (int k = tid; k < N; k += T) tmpv[k] = (ws.color[k] == c) ? 1.0 : 0.0;
+                    __syncthreads();
+                    for (int i = tid; i < N; i += T) {
+                        const double ci = E::jac_mul_i(i, x, p, tt, tmpv);
+                        for (int j = 0; j < N; ++j)
+                            if (ws.color[j] == c && ws.nz[(size_t)j * N + i]) Jg[(size_t)j * N + i] = ci;
+                    }
+                }
+                __syncthreads();
+            } else {
+                st.v[DSB_STAT_RHS_JAC_MULS] += N;
+                for (int j = 0; j < N; ++j) {
+                    const CoopUnitVec v{j};
+                    for (int i = tid; i < N; i += T) Jg[(size_t)j * N + i] = E::jac_mul_i(i, x, p, tt, v);
+                }
             }
         };
         // ---- set_consistent (state.rs:84-162, op/init.rs:14-131) ----
@@ -513,6 +533,11 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
 
         int col = 0;
         if (status == DSB_STATUS_OK) {
+            if (ws.color != nullptr) {                     // consistent initialisation used Jg as scratch
+                __syncthreads();
+                for (int e = tid; e < N * N; e += T) Jg[e] = 0.0;
+                __syncthreads();
+            }
             reset_jacobian();
             st.v[DSB_STAT_LINEAR_SOLVER_SETUPS] += 1;
             st.v[DSB_STAT_SETUPS_FROM_CHECKPOINT] += 1;

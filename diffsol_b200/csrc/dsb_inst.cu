@@ -63,6 +63,26 @@ static cudaError_t launch_coop_bdf(const DsbProblemArgs* pa, const DsbBatchBuffe
     ws.lu = (double*)base; base += nn * sizeof(double) * grid;
     ws.piv = (int32_t*)base;
     ws.atol = coop->atol_dev;
+    ws.color = nullptr; ws.nz = nullptr;
+    if (pa->use_coloring) {
+        if (!coop->color_host || !coop->nz_host) return cudaErrorInvalidValue;
+        const size_t cbytes = (size_t)N * sizeof(int32_t) + nn;
+        if (coop->color_bytes < cbytes) {
+            if (coop->color_dev) cudaFree(coop->color_dev);
+            coop->color_dev = nullptr; coop->color_bytes = 0;
+            e = cudaMalloc(&coop->color_dev, cbytes);
+            if (e != cudaSuccess) return e;
+            coop->color_bytes = cbytes;
+        }
+        e = cudaMemcpyAsync(coop->color_dev, coop->color_host, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync((char*)coop->color_dev + (size_t)N * sizeof(int32_t), coop->nz_host, nn, cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(stream);          // the host vectors die with the caller's frame
+        if (e != cudaSuccess) return e;
+        ws.color = (const int32_t*)coop->color_dev;
+        ws.nz = (const uint8_t*)((char*)coop->color_dev + (size_t)N * sizeof(int32_t));
+    }
     e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     if (mid) cudaEventRecord(mid, stream);
@@ -141,7 +161,7 @@ cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const
                                                  DsbCoopState* coop, const double* atol_host, int* launches) {
     const bool use_coop = coop->exec_mode == 2 || (coop->exec_mode == 0 && !kLaneCapable);
     if (use_coop) {
-        if (method != DSB_METHOD_BDF || pa->use_coloring) return cudaErrorNotSupported;   // cooperative path: BDF, dense Jacobian
+        if (method != DSB_METHOD_BDF) return cudaErrorNotSupported;   // cooperative path: BDF only
         return launch_coop_bdf<InstModel>(pa, bb, stream, mid, work_counter, coop, atol_host, launches);
     }
     return LaneLauncher<InstModel, kLaneCapable>::run(pa, bb, method, stream, mid, work_counter, launches);

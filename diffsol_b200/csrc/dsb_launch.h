@@ -14,6 +14,8 @@ struct DsbCoopState {
     int exec_mode;
     void* ws_mem; size_t ws_bytes;
     double* atol_dev; int atol_n;
+    const int32_t* color_host; const uint8_t* nz_host;   // colouring of the current solve (host, valid during the launch call)
+    void* color_dev; size_t color_bytes;                 // device copy: [n] int32 colours then [n*n] pattern bytes
 };
 typedef cudaError_t (*dsb_launch_fn)(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method,
                                      cudaStream_t stream, cudaEvent_t mid, unsigned long long* work_counter,

@@ -111,3 +111,26 @@ def test_spm_battery_sweep_bit_exact(dsb, oracle):
     assert np.array_equal(ys, ys_o)
     # discharge capacity is I t / 3600 exactly up to the integration tolerance
     assert np.allclose(ys[:, -1, 0], current[:, 0] * 3600.0 / 3600.0, rtol=1e-5)
+
+
+@pytest.mark.parametrize("model,B", [("heat1d_dae_32", 40), ("heat1d_dae_256", 6), ("spm", 40)])
+def test_coloured_jacobian_block_per_instance(dsb, oracle, model, B):
+    """use_coloring(true) on the block-per-instance path: 3 jac_mul calls per Jacobian instead of n (plus the n
+    sparsity probes the reference counts once), same trajectory."""
+    from diffsol_b200 import sweeps
+    if model == "spm":
+        p = (0.6 + 0.8 * sweeps.uniform(np.arange(B), 0)).reshape(-1, 1)
+        t_eval = np.arange(1, 5) * 300.0
+    else:
+        p = heat_params(np.arange(B))
+        t_eval = HEAT_T_EVAL[:20]
+    solver = dsb.OdeBuilder().rhs_implicit(model).p(p).rtol(1e-6).atol(1e-6).use_coloring(True).build().bdf()
+    ys = solver.solve_dense(t_eval)
+    desc = oracle.make_desc(model, powmode=1, rtol=1e-6, atol=1e-6, use_coloring=True)
+    ys_o, stats_o, status_o = oracle.batch_solve_dense(desc, p, t_eval)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o)
+    n = ys.shape[2]
+    me = solver.statistics_array()[:, 12]
+    assert (solver.statistics_array()[:, 11] == 3 * me + n).all()      # 3 colours + n probes
