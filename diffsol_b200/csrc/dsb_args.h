@@ -12,7 +12,7 @@
 #define DSB_MAX_STATES 64      // register/local-memory lane kernels; larger n uses the block-cooperative path
 #define DSB_MAX_ORDER 5        // bdf_state.rs:44
 #define DSB_NDIFF (DSB_MAX_ORDER + 3)
-#define DSB_DEFAULT_QUORUM 12     // lanes of a warp that make a heavy block worth running (see dsb_bdf_kernel.cuh)
+#define DSB_DEFAULT_QUORUM 16     // lanes of a warp that make a heavy block worth running (see dsb_bdf_kernel.cuh)
 #define DSB_LANE_THREADS 128   // block size of the one-thread-per-instance kernels
 
 // Lane-kernel statistics are int32 in device memory, one array per counter (batch-major).
@@ -47,7 +47,6 @@ struct DsbProblemArgs {
     int32_t free_running;      // 1: no stop time; step until t passes each point, then interpolate (the
                                // `while t < t_k { step() }; interpolate(t_k)` loop of ode_solver/mod.rs:132-141)
     int32_t quorum;            // warp scheduler: lanes that make a heavy block worth running (dsb_bdf_kernel.cuh)
-    int32_t sched_mode, quorum_post, post_num, post_den;   // scheduler tuning knobs
     int32_t coop_dense_only, reserved1;   // 1: the block-per-instance path always uses the blocked dense LU (test hook)
     int32_t ncolors;
     int32_t color_of_col[DSB_MAX_STATES];      // colour index of every column

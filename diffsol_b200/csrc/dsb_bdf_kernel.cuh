@@ -62,7 +62,11 @@ struct BdfLayout {
     static constexpr int O_P = O_YP + N;                            // parameters
     static constexpr int WORDS = O_P + (NP > 0 ? NP : 1);
     // threads per block: the per-thread column must leave room for >= 2 blocks per SM (227 KB)
+#ifdef DSB_THREADS
+    static constexpr int THREADS = DSB_THREADS;                     // tuning experiments
+#else
     static constexpr int THREADS = (WORDS * 8 * 128 <= 75 * 1024) ? 128 : (WORDS * 8 * 64 <= 110 * 1024) ? 64 : 32;
+#endif
     // resident blocks per SM the register allocation is asked to allow (shared memory permitting)
 #ifndef DSB_MIN_BLOCKS
 #define DSB_MIN_BLOCKS 3
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCK
             return -DSB_STATUS_STOP_TIME_BEFORE_CURRENT;
         }
         if ((h > 0.0 && t + h > ts + troundoff) || (h < 0.0 && t + h < ts - troundoff)) {
-            rescale_factor = (ts - t) / h;
+            rescale_factor = DSB_DIV(ts - t, h);
             return 2;
         }
         return 0;
@@ -141,9 +145,9 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCK
     // runge_kutta.rs:1313-1335
     auto pi_controller_raw = [&](double err, int eff_order) -> double {
         const double order_f = (double)eff_order;
-        const double ki = pa.opt.pi_control_integral / order_f;
+        const double ki = DSB_DIV(pa.opt.pi_control_integral, order_f);
         const bool p_only = pa.opt.pi_control_proportional == 0.0 || !has_prev_error;
-        const double kp = p_only ? 0.0 : pa.opt.pi_control_proportional / order_f;
+        const double kp = p_only ? 0.0 : DSB_DIV(pa.opt.pi_control_proportional, order_f);
         double v = dsb_pow(err, p_only ? -ki : -(ki + kp));
         if (!p_only) v = v * dsb_pow(prev_error_norm, kp);
         return v;
@@ -153,10 +157,10 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCK
         double acc = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double term = SD(j, i) / (dsb_abs(SY(i)) * pa.rtol + pa.atol[i]);
+            const double term = DSB_DIV(SD(j, i), dsb_abs(SY(i)) * pa.rtol + pa.atol[i]);
             acc += term * term;
         }
-        return acc / (double)N;
+        return DSB_DIV(acc, (double)N);
     };
 
     while (true) {
@@ -168,25 +172,20 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCK
         // change and refactorisation) would run with a handful of active lanes on every trip, so a lane
         // that needs one WAITS until pa.quorum lanes (or half of the active ones) want the same group.
         // Waiting never changes a lane's arithmetic, only when it runs.
+#ifdef DSB_BLOCK_SYNC           // experiment: the warps of a block walk the loop body together (instruction-cache locality)
+        if (__syncthreads_and(state == L_IDLE)) break;
+        const unsigned m_idle = __ballot_sync(0xffffffffu, state == L_IDLE);
+        if (m_idle == 0xffffffffu) continue;
+#else
         const unsigned m_idle = __ballot_sync(0xffffffffu, state == L_IDLE);
         if (m_idle == 0xffffffffu) break;
+#endif
         const int n_active = 32 - __popc(m_idle);
-        const int n_select = __popc(__ballot_sync(0xffffffffu, state == L_SELECT));
-        const int n_setup = __popc(__ballot_sync(0xffffffffu, state == L_RESCALE || state == L_JAC));
-        const int n_post = __popc(__ballot_sync(0xffffffffu, state == L_POST));
-        const int n_slow = n_select + n_setup;
-        bool run_select, run_setup;
-        if (pa.sched_mode == 0) {        // separate pools
-            const bool none_running = n_slow == n_active;
-            run_select = n_select > 0 && (n_select >= quorum || 2 * n_select >= n_active || none_running);
-            run_setup = n_setup > 0 && (n_setup >= quorum || 2 * n_setup >= n_active || none_running);
-        } else {                         // one pool: SELECT -> RESCALE -> JAC flow through together
-            run_select = run_setup = n_slow > 0 && (n_slow >= quorum || 2 * n_slow >= n_active);
-        }
-        // POST (and the per-step chain behind it) may also wait for company: lanes whose Newton solve ended
-        // early idle a trip so that the chain runs once with more lanes
-        const int n_hot = n_active - n_slow;
-        const bool run_post = n_post > 0 && (n_post >= pa.quorum_post || n_post * pa.post_den >= n_hot * pa.post_num);
+        const int n_slow = __popc(__ballot_sync(0xffffffffu, state == L_SELECT || state == L_RESCALE || state == L_JAC));
+        // one pool: SELECT -> RESCALE -> JAC flow through together (separate pools and a quorum on POST were measured
+        // and rejected)
+        const bool run_select = n_slow > 0 && (n_slow >= quorum || 2 * n_slow >= n_active);
+        const bool run_setup = run_select;
 
         // ================= FINISH: write the instance's results, then fetch the next one =====================
         if (__any_sync(0xffffffffu, state == L_FINISH) && state == L_FINISH) {
@@ -234,22 +233,20 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCK
         if (run_select && state == L_SELECT) {
             const int ord = order;
             const double inf = dsb_from_bits(0x7ff0000000000000ULL);
-            double e0 = inf, e2 = inf;
-            if (accepted) {
-                if (ord > 1) {
-                    const double e = diff_col_norm(ord) * pa.tab.error_const2[ord - 1];
-                    e0 = (0.0 < e) ? e : 0.0;
-                }
-                if (ord < DSB_MAX_ORDER) {
-                    const double e = diff_col_norm(ord + 2) * pa.tab.error_const2[ord + 1];
-                    e2 = (0.0 < e) ? e : 0.0;
-                }
-            }
+            // the two neighbouring-order error estimates and the three controller factors come out of ONE rolled
+            // loop, so that the weighted norm and pow() each have a single call site (code size)
             double f0 = 0.0, f1 = 0.0, f2 = 0.0;
 #pragma unroll 1
             for (int q = 0; q < 3; ++q) {
                 if (accepted || q == 1) {
-                    const double err = (q == 0) ? e0 : (q == 1) ? error_norm : e2;
+                    double err = error_norm;
+                    if (q != 1) {
+                        err = inf;
+                        if ((q == 0) ? (ord > 1) : (ord < DSB_MAX_ORDER)) {
+                            const double e = diff_col_norm(ord + q) * pa.tab.error_const2[ord - 1 + q];
+                            err = (0.0 < e) ? e : 0.0;
+                        }
+                    }
                     const double v = pi_controller_raw(err, ord + q);
                     if (q == 0) f0 = v; else if (q == 1) f1 = v; else f2 = v;
                 }
@@ -293,31 +290,31 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCK
             const double* __restrict__ u = pa.tab.u[DSB_MAX_ORDER];         // leading dimension 6
             double rrow[DSB_MAX_ORDER + 1];
             double nd[DSB_MAX_ORDER + 1][N];
+            // The row loop is ROLLED (code size: the unrolled version was 720 SASS instructions, a fifth of the
+            // kernel, and the loop body of the kernel did not fit the 32 KB instruction cache).  Accumulators
+            // start at -0.0: (-0.0) + x == x bit for bit for every x, so the first term is "assigned" as in
+            // nalgebra's gemm with beta = 0.  x / 1, x / 2, x / 4 are exact, so `num / i` covers every row.
 #pragma unroll
-            for (int l = 1; l <= DSB_MAX_ORDER; ++l) rrow[l] = 1.0;
+            for (int l = 1; l <= DSB_MAX_ORDER; ++l) {
+                rrow[l] = 1.0;
 #pragma unroll
-            for (int i = 1; i <= DSB_MAX_ORDER; ++i) {
-                if (i <= k) {
-                    const double i_t = (double)i;
+                for (int s = 0; s < N; ++s) nd[l][s] = -0.0;
+            }
+#pragma unroll 1
+            for (int i = 1; i <= k; ++i) {
+                const double i_t = (double)i;
 #pragma unroll
-                    for (int l = 1; l <= DSB_MAX_ORDER; ++l) {
-                        const double num = rrow[l] * (i_t - 1.0 - factor * (double)l);
-                        // x / 1, x / 2, x / 4 are exact scalings
-                        rrow[l] = (i == 1) ? num : (i == 2) ? num * 0.5 : (i == 4) ? num * 0.25 : num / i_t;
-                    }
+                for (int l = 1; l <= DSB_MAX_ORDER; ++l) rrow[l] = DSB_DIV(rrow[l] * (i_t - 1.0 - factor * (double)l), i_t);
+                double di[N];
 #pragma unroll
-                    for (int j = 1; j <= DSB_MAX_ORDER; ++j) {
-                        if (j <= k) {
-                            double ru_ij = rrow[1] * u[j * 6 + 1];              // RU[i, j] = sum_{l <= j} R[i, l] U[l, j]
+                for (int s = 0; s < N; ++s) di[s] = SD(i, s);
 #pragma unroll
-                            for (int l = 2; l <= j; ++l) ru_ij = rrow[l] * u[j * 6 + l] + ru_ij;
+                for (int j = 1; j <= DSB_MAX_ORDER; ++j) {
+                    double ru_ij = rrow[1] * u[j * 6 + 1];              // RU[i, j] = sum_{l <= j} R[i, l] U[l, j]
 #pragma unroll
-                            for (int s = 0; s < N; ++s) {
-                                if (i == 1) nd[j][s] = SD(i, s) * ru_ij;
-                                else nd[j][s] = SD(i, s) * ru_ij + nd[j][s];
-                            }
-                        }
-                    }
+                    for (int l = 2; l <= j; ++l) ru_ij = rrow[l] * u[j * 6 + l] + ru_ij;
+#pragma unroll
+                    for (int s = 0; s < N; ++s) nd[j][s] = di[s] * ru_ij + nd[j][s];
                 }
             }
 #pragma unroll
@@ -361,15 +358,11 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCK
 #pragma unroll
                 for (int j = 0; j < NP; ++j) pl[j] = SP(j);
                 if (jacobian_is_stale) {
-                    // df/dy at (state.y, state.t) (quirk Q6); passes through lu.a on its way to shared memory
+                    // df/dy at (state.y, state.t) (quirk Q6), assembled straight into shared memory
                     double yl[N];
 #pragma unroll
                     for (int i = 0; i < N; ++i) yl[i] = SY(i);
-                    lane_jacobian<M>(pa, yl, pl, t, lu.a, st);
-#pragma unroll
-                    for (int j = 0; j < N; ++j)
-#pragma unroll
-                        for (int i = 0; i < N; ++i) SJ(j, i) = lu.a[j][i];
+                    lane_jacobian_to<M>(pa, yl, pl, t, st, [&](int j, int i, double val) { SJ(j, i) = val; });
                     if (M::HAS_MASS) {
                         lane_mass_matrix<M>(pl, t, lu.a);
 #pragma unroll
@@ -404,16 +397,18 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCK
         if (__any_sync(0xffffffffu, state == L_TSTOP) && state == L_TSTOP) {
             int next = first ? L_PREDICT : L_OUTPUT;
             int r = 0;
+            bool check = has_tstop;
             if (first) {
+                check = !free_running;
                 if (free_running) next = L_OUTPUT;
-                else {
-                    has_tstop = true; tstop = bb.t_eval[nt - 1];
-                    r = handle_tstop(tstop);
-                    if (r == 1) r = -DSB_STATUS_STOP_TIME_AT_CURRENT;
-                }
-            } else if (has_tstop) {
+                else { has_tstop = true; tstop = bb.t_eval[nt - 1]; }
+            }
+            if (check) {                                 // one call site for handle_tstop (code size)
                 r = handle_tstop(tstop);
-                if (r == 1) reached = true;
+                if (r == 1) {
+                    if (first) r = -DSB_STATUS_STOP_TIME_AT_CURRENT;
+                    else reached = true;
+                }
             }
             if (r < 0) {
                 finish(-r);
@@ -446,7 +441,7 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCK
 #pragma unroll 1
                 for (int j = 0; j < order; ++j) {
                     const double j_t = (double)j;
-                    time_factor *= (tq - (t - h * j_t)) / (h * (1.0 + j_t));
+                    time_factor *= DSB_DIV(tq - (t - h * j_t), h * (1.0 + j_t));
 #pragma unroll
                     for (int i = 0; i < N; ++i) yo[i] = time_factor * SD(j + 1, i) + yo[i];
                 }
@@ -538,23 +533,23 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCK
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     y_cur[i] -= delta[i];
-                    const double term = delta[i] / wt[i];
+                    const double term = DSB_DIV(delta[i], wt[i]);
                     acc += term * term;
                 }
-                const double norm = dsb_sqrt(acc / (double)N);
+                const double norm = dsb_sqrt(DSB_DIV(acc, (double)N));
                 // Convergence::check_new_iteration (convergence.rs:68-139) with its pow() hoisted to one call site
                 conv.niter += 1;
                 const bool have_rate = conv.has_old_norm;
                 double px, py;
-                if (have_rate) { px = norm / conv.old_norm; py = 1.0 / (double)(conv.niter - 1); }
+                if (have_rate) { px = DSB_DIV(norm, conv.old_norm); py = DSB_DIV(1.0, (double)(conv.niter - 1)); }
                 else { const double min_eta = 1e4 * eps; px = (conv.eta < min_eta) ? min_eta : conv.eta; py = 0.8; }
                 const double pw = dsb_pow(px, py);
                 int s = LANE_CONTINUE;
                 if (have_rate) {
                     const double rate = pw;
                     if (rate > 0.9) s = LANE_DIVERGED;
-                    else if (dsb_powi(rate, conv.max_iter - conv.niter) / (1.0 - rate) * norm > conv.tol) s = LANE_DIVERGED;
-                    else conv.eta = rate / (1.0 - rate);
+                    else if (DSB_DIV(dsb_powi(rate, conv.max_iter - conv.niter), 1.0 - rate) * norm > conv.tol) s = LANE_DIVERGED;
+                    else conv.eta = DSB_DIV(rate, 1.0 - rate);
                 } else {
                     conv.eta = pw;
                 }
@@ -565,7 +560,7 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCK
             }
         }
         // ================= POST: a Newton solve ended (bdf.rs:1338-1563) ==================================
-        if (run_post && state == L_POST) {
+        if (__any_sync(0xffffffffu, state == L_POST) && state == L_POST) {
             st.v[DSB_STAT_NONLINEAR_SOLVER_ITERATIONS] += conv.niter;
             if (newton_ok) {
                 const int ord = order;
@@ -576,15 +571,15 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCK
                     double acc = 0.0;
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
-                        const double term = d[i] / (dsb_abs(SY(i)) * pa.rtol + pa.atol[i]);
+                        const double term = DSB_DIV(d[i], dsb_abs(SY(i)) * pa.rtol + pa.atol[i]);
                         acc += term * term;
                     }
-                    const double err = acc / (double)N * pa.tab.error_const2[ord - 1];
+                    const double err = DSB_DIV(acc, (double)N) * pa.tab.error_const2[ord - 1];
                     error_norm = (0.0 < err) ? err : 0.0;
                 }
                 const double maxiter = (double)conv.max_iter;
                 const double niter = (double)conv.niter;
-                safety = 0.9 * (2.0 * maxiter + 1.0) / (2.0 * maxiter + niter);
+                safety = DSB_DIV(0.9 * (2.0 * maxiter + 1.0), 2.0 * maxiter + niter);
                 if (error_norm <= 1.0) {
                     // ---- accepted: _update_diff, state.y <- PREDICTOR (quirk Q1) ----
 #pragma unroll

@@ -201,6 +201,14 @@ int fill_problem_args(const dsb_problem& pr, int64_t B, int nt, DsbProblemArgs* 
     if (pr.use_coloring) {
         ColoringOf f{&pr, pa, probes, color_full, nz_full};
         if (!dsb_dispatch_model(pr.model, f)) return DSB_BAD_ARG;
+    } else if (pr.n <= DSB_MAX_STATES) {
+        // dense assembly (op/nonlinear_op.rs:211-220) expressed as one colour per column with a full pattern, so
+        // that the lane kernels carry a single assembly loop (dsb_lane.cuh:lane_jacobian_to)
+        pa->ncolors = pr.n;
+        for (int j = 0; j < pr.n; ++j) {
+            pa->color_of_col[j] = j;
+            pa->nz_rows_of_col[j] = pr.n >= 64 ? ~0ull : ((1ull << pr.n) - 1ull);
+        }
     }
     return DSB_OK;
 }
@@ -453,12 +461,7 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     pa.free_running = free_running;
     build_tableau(method, &pa.rk);
     pa.quorum = DSB_DEFAULT_QUORUM;
-    pa.sched_mode = 1; pa.quorum_post = 1; pa.post_num = 0; pa.post_den = 1;
     if (const char* q = getenv("DSB_COOP_DENSE_ONLY")) pa.coop_dense_only = atoi(q);
-    if (const char* q = getenv("DSB_SCHED_MODE")) pa.sched_mode = atoi(q);
-    if (const char* q = getenv("DSB_Q_POST")) pa.quorum_post = atoi(q);
-    if (const char* q = getenv("DSB_POST_NUM")) pa.post_num = atoi(q);
-    if (const char* q = getenv("DSB_POST_DEN")) pa.post_den = atoi(q);
     if (const char* q = getenv("DSB_QUORUM")) { int v = atoi(q); if (v >= 1 && v <= 33) pa.quorum = v; }   // tuning knob
     DsbBatchBuffers bb;
     bb.params = b->params; bb.t_eval = b->t_eval; bb.y0 = b->y0; bb.dy0 = b->dy0; bb.h0 = b->h0;

@@ -45,10 +45,10 @@ DSB_DEV double lane_squared_norm(const double (&x)[N], const double (&y)[N], con
     double acc = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        const double term = x[i] / (dsb_abs(y[i]) * rtol + atol[i]);
+        const double term = DSB_DIV(x[i], dsb_abs(y[i]) * rtol + atol[i]);
         acc += term * term;
     }
-    return acc / (double)N;
+    return DSB_DIV(acc, (double)N);
 }
 
 // ---- dense LU with partial pivoting, column-major a[col][row] -------------------------------------
@@ -123,7 +123,7 @@ struct LaneLU {
             const double diag = a[i][i];
             if (diag == 0.0) ok = false;
             if (ok) {
-                const double coeff = b[i] / diag;
+                const double coeff = DSB_DIV(b[i], diag);
                 b[i] = coeff;
                 const double mc = -coeff;
 #pragma unroll
@@ -183,13 +183,13 @@ struct LaneJacobianUpdate {
     DSB_DEV bool check_jacobian_update(const dsb_options& o, double h, int s) const {
         if (s == DSB_STEP_SUCCESS)
             return steps_since_jacobian_eval >= o.update_jacobian_after_steps
-                   || dsb_abs(h / h_at_last_jacobian_update - 1.0) > o.threshold_to_update_jacobian;
+                   || dsb_abs(DSB_DIV(h, h_at_last_jacobian_update) - 1.0) > o.threshold_to_update_jacobian;
         return true;
     }
     DSB_DEV bool check_rhs_jacobian_update(const dsb_options& o, double h, int s) const {
         if (s == DSB_STEP_SUCCESS) return steps_since_rhs_jacobian_eval >= o.update_rhs_jacobian_after_steps;
         if (s == DSB_FIRST_CONVERGENCE_FAIL)
-            return dsb_abs(h / h_at_last_jacobian_update - 1.0) < o.threshold_to_update_rhs_jacobian;
+            return dsb_abs(DSB_DIV(h, h_at_last_jacobian_update) - 1.0) < o.threshold_to_update_rhs_jacobian;
         if (s == DSB_SECOND_CONVERGENCE_FAIL) return steps_since_rhs_jacobian_eval > 0;
         if (s == DSB_ERROR_TEST_FAIL) return false;
         return true;   // Checkpoint
@@ -251,6 +251,40 @@ DSB_DEV void lane_jacobian(const DsbProblemArgs& pa, const double (&x)[M::N], co
 #pragma unroll
             for (int i = 0; i < N; ++i) J[j][i] = col[i];
             v[j] = 0.0;
+        }
+    }
+}
+
+// The same assembly for the integrator kernels, written for code size (their loop bodies are instruction-cache
+// bound): ONE seed/jac_mul/scatter sequence inside a rolled loop over the colours, results handed to
+// `store(col, row, value)` (shared memory, so the run-time column index costs nothing).  Without colouring the host
+// fills the colour tables with one colour per column and a full pattern (dsb_capi.cu:fill_problem_args), which makes
+// this loop the dense column-by-column assembly of op/nonlinear_op.rs:211-220, same values, same call counts.
+template <class M, class Store>
+DSB_DEV void lane_jacobian_to(const DsbProblemArgs& pa, const double (&x)[M::N], const double* p, double t,
+                              LaneStats& st, Store&& store) {
+    constexpr int N = M::N;
+    st.v[DSB_STAT_RHS_MATRIX_EVALS] += 1;
+    double v[N], col[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) col[i] = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) store(j, i, 0.0);
+#pragma unroll 1
+    for (int c = 0; c < pa.ncolors; ++c) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] = (pa.color_of_col[j] == c && pa.nz_rows_of_col[j] != 0) ? 1.0 : 0.0;
+        M::jac_mul(x, p, t, v, col);
+        st.v[DSB_STAT_RHS_JAC_MULS] += 1;
+#pragma unroll 1
+        for (int j = 0; j < N; ++j) {
+            if (pa.color_of_col[j] == c) {
+                const uint64_t nz = pa.nz_rows_of_col[j];
+#pragma unroll
+                for (int i = 0; i < N; ++i) if ((nz >> i) & 1ull) store(j, i, col[i]);
+            }
         }
     }
 }
