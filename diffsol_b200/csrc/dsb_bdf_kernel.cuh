@@ -60,22 +60,26 @@ struct BdfLayout {
     static constexpr int O_Y = O_LU + N * N;                        // state.y
     static constexpr int O_YP = O_Y + N;                            // y_predict
     static constexpr int O_P = O_YP + N;                            // parameters
-    static constexpr int WORDS = O_P + (NP > 0 ? NP : 1);
-    // threads per block: the per-thread column must leave room for >= 2 blocks per SM (227 KB)
+    static constexpr int O_ST = O_P + (NP > 0 ? NP : 1);            // statistics, two int32 per word
+    static constexpr int WORDS = O_ST + (DSB_NSTATS + 1) / 2;
+    // ONE persistent block per SM (the kernel never synchronises across warps, so the block size is free): as many
+    // lanes as shared memory (this column) and the register file allow.  Registers are split per scheduler
+    // (4 x 16384), so what counts is warps per scheduler: 4 at <= 128 registers, 3 at <= 168, 2 at <= 255.
+    // Resident warps are what hides the FP64 dependency latency: 12 -> 15 warps per SM on the Robertson sweep was
+    // worth 1.12x (profiles/r1_v10_*).
+    static constexpr int T_SMEM = (226 * 1024 / (WORDS * 8)) / 32 * 32;
+    static constexpr int T_REG = N <= 4 ? 512 : N <= 6 ? 384 : 256;
 #ifdef DSB_THREADS
     static constexpr int THREADS = DSB_THREADS;                     // tuning experiments
 #else
-    static constexpr int THREADS = (WORDS * 8 * 128 <= 75 * 1024) ? 128 : (WORDS * 8 * 64 <= 110 * 1024) ? 64 : 32;
+    static constexpr int THREADS = T_SMEM < 32 ? 32 : (T_SMEM < T_REG ? T_SMEM : T_REG);
 #endif
-    // resident blocks per SM the register allocation is asked to allow (shared memory permitting)
-#ifndef DSB_MIN_BLOCKS
-#define DSB_MIN_BLOCKS 3
-#endif
-    static constexpr int MIN_BLOCKS = (WORDS * 8 * THREADS * DSB_MIN_BLOCKS <= 226 * 1024) ? DSB_MIN_BLOCKS : 1;
+    static constexpr int WARPS_PER_SCHEDULER = (THREADS / 32 + 3) / 4;
+    static constexpr int MAXNREG = (512 / WARPS_PER_SCHEDULER) / 8 * 8 > 255 ? 255 : (512 / WARPS_PER_SCHEDULER) / 8 * 8;
 };
 
 template <class M>
-__global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCKS) dsb_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa,
+__global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa,
                                                                               const __grid_constant__ DsbBatchBuffers bb,
                                                                               unsigned long long* __restrict__ work_counter) {
     constexpr int N = M::N;
@@ -111,12 +115,13 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCK
     LaneConvergence conv;
     conv.tol = pa.opt.nonlinear_solver_tolerance; conv.max_iter = pa.opt.max_nonlinear_solver_iterations;
     conv.eta = pa.tab.eta_reset; conv.old_norm = 0.0; conv.reset();
-    LaneStats st; st.clear();
+    SmemLaneStats<2 * Lay::THREADS> st;
+    st.v.base = reinterpret_cast<int*>(&SM(Lay::O_ST));
     unsigned long long piv_packed = 0;         // 4 bits per row
     // Newton work vectors
-    double y_cur[N], psi_neg_y0[N], wt[N];
+    double y_cur[N], psi_neg_y0[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) { y_cur[i] = 0.0; psi_neg_y0[i] = 0.0; wt[i] = 1.0; }
+    for (int i = 0; i < N; ++i) { y_cur[i] = 0.0; psi_neg_y0[i] = 0.0; }
     // step()-local state
     bool convergence_fail = false, newton_ok = false, first = true, reached = false, accepted = false;
     bool repredict = true, pending_etf = false, rs_ignore_small = false;
@@ -483,7 +488,6 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCK
                     psi_neg_y0[i] *= a;
                     psi_neg_y0[i] -= yp[i];
                     SYP(i) = yp[i];
-                    wt[i] = dsb_abs(yp[i]) * pa.rtol + pa.atol[i];     // Newton norm weights use the predictor
                 }
                 t_predict = t + h;
             }
@@ -533,7 +537,8 @@ __global__ void __launch_bounds__(BdfLayout<M>::THREADS, BdfLayout<M>::MIN_BLOCK
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     y_cur[i] -= delta[i];
-                    const double term = DSB_DIV(delta[i], wt[i]);
+                    // Newton norm weights use the PREDICTOR (line_search.rs:67, convergence.rs:64-66)
+                    const double term = DSB_DIV(delta[i], dsb_abs(SYP(i)) * pa.rtol + pa.atol[i]);
                     acc += term * term;
                 }
                 const double norm = dsb_sqrt(DSB_DIV(acc, (double)N));

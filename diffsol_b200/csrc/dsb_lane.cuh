@@ -197,20 +197,34 @@ struct LaneJacobianUpdate {
 };
 
 // ---- per-instance statistics (ode_solver/mod.rs:27-69, op/mod.rs:108-145) -----------------------------
-struct LaneStats {
+template <class V>
+DSB_DEV void lane_record_linear_solver_setup(V& v, int s) {
+    v[DSB_STAT_LINEAR_SOLVER_SETUPS] += 1;
+    if (s == DSB_CHECKPOINT) v[DSB_STAT_SETUPS_FROM_CHECKPOINT] += 1;
+    else if (s == DSB_FIRST_CONVERGENCE_FAIL) v[DSB_STAT_SETUPS_FROM_FIRST_CONVERGENCE_FAIL] += 1;
+    else if (s == DSB_SECOND_CONVERGENCE_FAIL) v[DSB_STAT_SETUPS_FROM_SECOND_CONVERGENCE_FAIL] += 1;
+    else if (s == DSB_ERROR_TEST_FAIL) v[DSB_STAT_SETUPS_FROM_ERROR_TEST_FAIL] += 1;
+    else v[DSB_STAT_SETUPS_FROM_STEP_SUCCESS] += 1;
+}
+struct LaneStats {                 // counters in registers
     int v[DSB_NSTATS];
     DSB_DEV void clear() {
 #pragma unroll
         for (int i = 0; i < DSB_NSTATS; ++i) v[i] = 0;
     }
-    DSB_DEV void record_linear_solver_setup(int s) {
-        v[DSB_STAT_LINEAR_SOLVER_SETUPS] += 1;
-        if (s == DSB_CHECKPOINT) v[DSB_STAT_SETUPS_FROM_CHECKPOINT] += 1;
-        else if (s == DSB_FIRST_CONVERGENCE_FAIL) v[DSB_STAT_SETUPS_FROM_FIRST_CONVERGENCE_FAIL] += 1;
-        else if (s == DSB_SECOND_CONVERGENCE_FAIL) v[DSB_STAT_SETUPS_FROM_SECOND_CONVERGENCE_FAIL] += 1;
-        else if (s == DSB_ERROR_TEST_FAIL) v[DSB_STAT_SETUPS_FROM_ERROR_TEST_FAIL] += 1;
-        else v[DSB_STAT_SETUPS_FROM_STEP_SUCCESS] += 1;
-    }
+    DSB_DEV void record_linear_solver_setup(int s) { lane_record_linear_solver_setup(v, s); }
+};
+// The same counters in the lane's shared-memory column, two int32 per 64-bit word (word stride STRIDE2 / 2
+// doubles): frees 16 registers per lane, which is what limits the resident warps of the integrator kernels.
+template <int STRIDE2>
+struct SmemIntColumn {
+    int* base;
+    DSB_DEV int& operator[](int k) const { return base[(k >> 1) * STRIDE2 + (k & 1)]; }
+};
+template <int STRIDE2>
+struct SmemLaneStats {
+    SmemIntColumn<STRIDE2> v;
+    DSB_DEV void record_linear_solver_setup(int s) { lane_record_linear_solver_setup(v, s); }
 };
 
 // ---- df/dy assembly: J[col][row] ----------------------------------------------------------------------
@@ -260,9 +274,9 @@ DSB_DEV void lane_jacobian(const DsbProblemArgs& pa, const double (&x)[M::N], co
 // `store(col, row, value)` (shared memory, so the run-time column index costs nothing).  Without colouring the host
 // fills the colour tables with one colour per column and a full pattern (dsb_capi.cu:fill_problem_args), which makes
 // this loop the dense column-by-column assembly of op/nonlinear_op.rs:211-220, same values, same call counts.
-template <class M, class Store>
+template <class M, class Stats, class Store>
 DSB_DEV void lane_jacobian_to(const DsbProblemArgs& pa, const double (&x)[M::N], const double* p, double t,
-                              LaneStats& st, Store&& store) {
+                              Stats& st, Store&& store) {
     constexpr int N = M::N;
     st.v[DSB_STAT_RHS_MATRIX_EVALS] += 1;
     double v[N], col[N];
