@@ -62,20 +62,8 @@ struct BdfLayout {
     static constexpr int O_P = O_YP + N;                            // parameters
     static constexpr int O_ST = O_P + (NP > 0 ? NP : 1);            // statistics, two int32 per word
     static constexpr int WORDS = O_ST + (DSB_NSTATS + 1) / 2;
-    // ONE persistent block per SM (the kernel never synchronises across warps, so the block size is free): as many
-    // lanes as shared memory (this column) and the register file allow.  Registers are split per scheduler
-    // (4 x 16384), so what counts is warps per scheduler: 4 at <= 128 registers, 3 at <= 168, 2 at <= 255.
-    // Resident warps are what hides the FP64 dependency latency: 12 -> 15 warps per SM on the Robertson sweep was
-    // worth 1.12x (profiles/r1_v10_*).
-    static constexpr int T_SMEM = (226 * 1024 / (WORDS * 8)) / 32 * 32;
-    static constexpr int T_REG = N <= 4 ? 512 : N <= 6 ? 384 : 256;
-#ifdef DSB_THREADS
-    static constexpr int THREADS = DSB_THREADS;                     // tuning experiments
-#else
-    static constexpr int THREADS = T_SMEM < 32 ? 32 : (T_SMEM < T_REG ? T_SMEM : T_REG);
-#endif
-    static constexpr int WARPS_PER_SCHEDULER = (THREADS / 32 + 3) / 4;
-    static constexpr int MAXNREG = (512 / WARPS_PER_SCHEDULER) / 8 * 8 > 255 ? 255 : (512 / WARPS_PER_SCHEDULER) / 8 * 8;
+    static constexpr int THREADS = LaneBlockShape<WORDS, N>::THREADS;
+    static constexpr int MAXNREG = LaneBlockShape<WORDS, N>::MAXNREG;
 };
 
 template <class M>
@@ -89,6 +77,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
     extern __shared__ double dsb_lane_smem[];
     double* const sm = dsb_lane_smem + threadIdx.x;
 #define SM(w) sm[(w) * Lay::THREADS]
+#define DSB_DIV(a, b) DsbDivShared::div((a), (b))      // one shared division routine (code size, dsb_math.h)
 #define SD(j, i) SM(Lay::O_D + (j) * N + (i))
 #define SJ(j, i) SM(Lay::O_J + (j) * N + (i))
 #define SMM(j, i) SM(Lay::O_M + (j) * N + (i))
@@ -344,12 +333,12 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                 st.v[DSB_STAT_LINEAR_SOLVER_SETUPS] += 1;
                 st.v[DSB_STAT_SETUPS_FROM_CHECKPOINT] += 1;
                 after_jac = L_TSTOP;
-            } else if (ju.check_rhs_jacobian_update(pa.opt, c, jac_kind)) {
+            } else if (ju.check_rhs_jacobian_update<DsbDivShared>(pa.opt, c, jac_kind)) {
                 jacobian_is_stale = true;
                 ju.update_rhs_jacobian(c);
                 ju.update_jacobian(c);
                 do_factor = true;
-            } else if (ju.check_jacobian_update(pa.opt, c, jac_kind)) {
+            } else if (ju.check_jacobian_update<DsbDivShared>(pa.opt, c, jac_kind)) {
                 ju.update_jacobian(c);
                 do_factor = true;
             }
@@ -358,7 +347,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                     conv.eta = pa.tab.eta_reset;
                     st.record_linear_solver_setup(jac_kind);
                 }
-                LaneLU<N> lu;
+                LaneLU<N, DsbDivShared> lu;
                 double pl[NP > 0 ? NP : 1];
 #pragma unroll
                 for (int j = 0; j < NP; ++j) pl[j] = SP(j);
@@ -523,7 +512,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                     for (int i = 0; i < N; ++i) delta[i] = tmp[i] + mc * delta[i];
                 }
             }
-            LaneLU<N> lu;
+            LaneLU<N, DsbDivShared> lu;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 lu.piv[j] = (int)((piv_packed >> (4 * j)) & 15ull);
@@ -631,6 +620,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 
     }
 #undef SM
+#undef DSB_DIV
 #undef SD
 #undef SJ
 #undef SMM

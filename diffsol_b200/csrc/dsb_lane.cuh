@@ -40,8 +40,27 @@ DSB_DEV void dsb_static_for_down(F&& f) {
     }
 }
 
+// Block shape of the integrator kernels.  ONE persistent block per SM (they never synchronise across warps, so the
+// block size is free): as many lanes as shared memory (WORDS doubles per lane) and the register file allow.
+// Registers are split per scheduler (4 x 16384), so what counts is warps per scheduler: 4 at <= 128 registers,
+// 3 at <= 168, 2 at <= 255.  Resident warps are what hides the FP64 dependency latency: 12 -> 15 warps per SM on
+// the Robertson sweep was worth 1.12x (profiles/r1_v10_*).
+template <int WORDS, int N>
+struct LaneBlockShape {
+    static constexpr int T_SMEM = (226 * 1024 / (WORDS * 8)) / 32 * 32;
+    static constexpr int T_REG = N <= 4 ? 512 : N <= 6 ? 384 : 256;
+#ifdef DSB_THREADS
+    static constexpr int THREADS = DSB_THREADS;                     // tuning experiments
+#else
+    static constexpr int THREADS = T_SMEM < 32 ? 32 : (T_SMEM < T_REG ? T_SMEM : T_REG);
+#endif
+    static constexpr int WARPS_PER_SCHEDULER = (THREADS / 32 + 3) / 4;
+    static constexpr int MAXNREG = (512 / WARPS_PER_SCHEDULER) / 8 * 8 > 255 ? 255 : (512 / WARPS_PER_SCHEDULER) / 8 * 8;
+};
+
 template <int N>
 DSB_DEV double lane_squared_norm(const double (&x)[N], const double (&y)[N], const double* __restrict__ atol, double rtol) {
+#define DSB_DIV(a, b) ((a) / (b))
     double acc = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -49,10 +68,11 @@ DSB_DEV double lane_squared_norm(const double (&x)[N], const double (&y)[N], con
         acc += term * term;
     }
     return DSB_DIV(acc, (double)N);
+#undef DSB_DIV
 }
 
 // ---- dense LU with partial pivoting, column-major a[col][row] -------------------------------------
-template <int N>
+template <int N, class Div = DsbDivInline>
 struct LaneLU {
     double a[N][N];
     int piv[N];          // row i was swapped with row piv[i] (piv[i] == i: no swap)
@@ -123,7 +143,7 @@ struct LaneLU {
             const double diag = a[i][i];
             if (diag == 0.0) ok = false;
             if (ok) {
-                const double coeff = DSB_DIV(b[i], diag);
+                const double coeff = Div::div(b[i], diag);
                 b[i] = coeff;
                 const double mc = -coeff;
 #pragma unroll
@@ -180,16 +200,18 @@ struct LaneJacobianUpdate {
         steps_since_rhs_jacobian_eval = 0; steps_since_jacobian_eval = 0; h_at_last_jacobian_update = h;
     }
     DSB_DEV void step() { ++steps_since_jacobian_eval; ++steps_since_rhs_jacobian_eval; }
+    template <class Div = DsbDivInline>
     DSB_DEV bool check_jacobian_update(const dsb_options& o, double h, int s) const {
         if (s == DSB_STEP_SUCCESS)
             return steps_since_jacobian_eval >= o.update_jacobian_after_steps
-                   || dsb_abs(DSB_DIV(h, h_at_last_jacobian_update) - 1.0) > o.threshold_to_update_jacobian;
+                   || dsb_abs(Div::div(h, h_at_last_jacobian_update) - 1.0) > o.threshold_to_update_jacobian;
         return true;
     }
+    template <class Div = DsbDivInline>
     DSB_DEV bool check_rhs_jacobian_update(const dsb_options& o, double h, int s) const {
         if (s == DSB_STEP_SUCCESS) return steps_since_rhs_jacobian_eval >= o.update_rhs_jacobian_after_steps;
         if (s == DSB_FIRST_CONVERGENCE_FAIL)
-            return dsb_abs(DSB_DIV(h, h_at_last_jacobian_update) - 1.0) < o.threshold_to_update_rhs_jacobian;
+            return dsb_abs(Div::div(h, h_at_last_jacobian_update) - 1.0) < o.threshold_to_update_rhs_jacobian;
         if (s == DSB_SECOND_CONVERGENCE_FAIL) return steps_since_rhs_jacobian_eval > 0;
         if (s == DSB_ERROR_TEST_FAIL) return false;
         return true;   // Checkpoint

@@ -72,14 +72,14 @@ DSB_HD double dsb_sqrt(double a) {
     return __builtin_sqrt(a);
 #endif
 }
-// IEEE division.  On the device the inline expansion is ~21 SASS instructions per site; the lane kernels call one
-// shared copy instead (code size: their loop bodies are instruction-cache bound -- 30 sites, 1.14x faster on the
-// Robertson sweep).  -DDSB_INLINE_DIV restores the inline expansion.
-#if defined(__CUDA_ARCH__) && !defined(DSB_INLINE_DIV)
+// IEEE division policies for the lane kernels.  On the device the inline expansion of `a / b` is ~21 SASS
+// instructions per site.  The BDF lane kernel (30 sites; its loop body was instruction-cache bound) calls one shared
+// copy instead: 1.14x faster on the Robertson sweep.  The SDIRK kernel fits the cache and keeps the inline form
+// (the shared copy made it 1.18x slower: call overhead and lost instruction-level parallelism).
+#if defined(__CUDACC__)
 static __device__ __noinline__ double dsb_div_fn(double a, double b) { return a / b; }
-#define DSB_DIV(a, b) dsb_div_fn((a), (b))
-#else
-#define DSB_DIV(a, b) ((a) / (b))
+struct DsbDivShared { static __device__ __forceinline__ double div(double a, double b) { return dsb_div_fn(a, b); } };
+struct DsbDivInline { static __device__ __forceinline__ double div(double a, double b) { return a / b; } };
 #endif
 DSB_HD double dsb_abs(double a) { return dsb_from_bits(dsb_bits(a) & 0x7fffffffffffffffULL); }
 DSB_HD bool dsb_isnan(double a) { return a != a; }

@@ -41,13 +41,14 @@ struct SdirkLayout {
     static constexpr int O_OY = O_DY + N;                           // old_state.y (last stage value / previous step)
     static constexpr int O_PHI = O_OY + N;                          // SdirkCallable.phi
     static constexpr int O_P = O_PHI + N;                           // parameters
-    static constexpr int WORDS = O_P + (NP > 0 ? NP : 1);
-    static constexpr int THREADS = (WORDS * 8 * 128 <= 75 * 1024) ? 128 : (WORDS * 8 * 64 <= 110 * 1024) ? 64 : 32;
-    static constexpr int MIN_BLOCKS = (WORDS * 8 * THREADS * 3 <= 226 * 1024) ? 3 : 1;
+    static constexpr int O_ST = O_P + (NP > 0 ? NP : 1);            // statistics, two int32 per word
+    static constexpr int WORDS = O_ST + (DSB_NSTATS + 1) / 2;
+    static constexpr int THREADS = LaneBlockShape<WORDS, N>::THREADS;
+    static constexpr int MAXNREG = LaneBlockShape<WORDS, N>::MAXNREG;
 };
 
 template <class M>
-__global__ void __launch_bounds__(SdirkLayout<M>::THREADS, SdirkLayout<M>::MIN_BLOCKS)
+__global__ void __maxnreg__(SdirkLayout<M>::MAXNREG)
 dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __grid_constant__ DsbBatchBuffers bb,
                              unsigned long long* __restrict__ work_counter) {
     constexpr int N = M::N;
@@ -57,6 +58,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
     extern __shared__ double dsb_lane_smem[];
     double* const sm = dsb_lane_smem + threadIdx.x;
 #define SM(w) sm[(w) * Lay::THREADS]
+#define DSB_DIV(a, b) DsbDivInline::div((a), (b))      // this kernel fits the instruction cache (dsb_math.h)
 #define SDF(j, i) SM(Lay::O_DIFF + (j) * N + (i))
 #define SJ(j, i) SM(Lay::O_J + (j) * N + (i))
 #define SMM(j, i) SM(Lay::O_M + (j) * N + (i))
@@ -87,7 +89,8 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
     LaneConvergence conv;
     conv.tol = pa.opt.nonlinear_solver_tolerance; conv.max_iter = pa.opt.max_nonlinear_solver_iterations;
     conv.eta = pa.tab.eta_reset; conv.old_norm = 0.0; conv.reset();
-    LaneStats st; st.clear();
+    SmemLaneStats<2 * Lay::THREADS> st;
+    st.v.base = reinterpret_cast<int*>(&SM(Lay::O_ST));
     unsigned long long piv_packed = 0;
     double x_cur[N], wt[N];                                // Newton iterate (old_state.dy), norm weights from state.y
 #pragma unroll
@@ -106,7 +109,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
         if (dsb_abs(t - ts) <= troundoff) return 1;
         if ((h_state > 0.0 && ts < t - troundoff) || (h_state < 0.0 && ts > t + troundoff)) return -DSB_STATUS_STOP_TIME_BEFORE_CURRENT;
         if ((h_state > 0.0 && t + h_state > ts + troundoff) || (h_state < 0.0 && t + h_state < ts - troundoff)) {
-            const double f = (ts - t) / h_state;
+            const double f = DSB_DIV(ts - t, h_state);
             h_state *= f;
         }
         return 0;
@@ -197,19 +200,19 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                 double acc = 0.0;
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
-                    const double term = err[i] / wt[i];                 // weights from state.y
+                    const double term = DSB_DIV(err[i], wt[i]);                 // weights from state.y
                     acc += term * term;
                 }
-                const double e = acc / (double)N;
+                const double e = DSB_DIV(acc, (double)N);
                 error_norm = (0.0 < e) ? e : 0.0;
                 const double maxiter = (double)conv.max_iter;
                 const double niter = (double)conv.niter;
-                const double safety_factor = (2.0 * maxiter + 1.0) / (2.0 * maxiter + niter);
+                const double safety_factor = DSB_DIV(2.0 * maxiter + 1.0, 2.0 * maxiter + niter);
                 const double safety = 0.9 * safety_factor;
                 const double order_f = (double)(pa.rk.order + 1);
-                const double ki = pa.opt.pi_control_integral / order_f;
+                const double ki = DSB_DIV(pa.opt.pi_control_integral, order_f);
                 const bool p_only = pa.opt.pi_control_proportional == 0.0 || !has_prev_error;
-                const double kp = p_only ? 0.0 : pa.opt.pi_control_proportional / order_f;
+                const double kp = p_only ? 0.0 : DSB_DIV(pa.opt.pi_control_proportional, order_f);
                 double raw = dsb_pow(error_norm, p_only ? -ki : -(ki + kp));
                 if (!p_only) raw = raw * dsb_pow(prev_error_norm, kp);
                 double f = safety * raw;
@@ -263,11 +266,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                     double tmpv[N];                                      // set_tmp: phi + c * x with x = state.y
 #pragma unroll
                     for (int i = 0; i < N; ++i) tmpv[i] = cg * SY(i) + SPHI(i);
-                    lane_jacobian<M>(pa, tmpv, pl, t_jac, lu.a, st);
-#pragma unroll
-                    for (int j = 0; j < N; ++j)
-#pragma unroll
-                        for (int i = 0; i < N; ++i) SJ(j, i) = lu.a[j][i];
+                    lane_jacobian_to<M>(pa, tmpv, pl, t_jac, st, [&](int j, int i, double val) { SJ(j, i) = val; });
                     if (M::HAS_MASS) {
                         lane_mass_matrix<M>(pl, t_jac, lu.a);
 #pragma unroll
@@ -365,7 +364,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                     status = DSB_STATUS_INTERPOLATION_TIME_AFTER_CURRENT; break;
                 }
                 const double dt = t - old_t;
-                const double theta = (dt == 0.0) ? 1.0 : (tq - old_t) / dt;
+                const double theta = (dt == 0.0) ? 1.0 : DSB_DIV(tq - old_t, dt);
                 double yo[N];
                 if (pa.rk.has_beta) {
                     const double th2 = theta * theta;
@@ -443,7 +442,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
 #pragma unroll
                 for (int k = 0; k < N; ++k) x_cur[k] = SDF(0, k);
             } else {
-                const double cc = (pa.rk.c[i] - pa.rk.c[i - 2]) / (pa.rk.c[i - 1] - pa.rk.c[i - 2]);
+                const double cc = DSB_DIV(pa.rk.c[i] - pa.rk.c[i - 2], pa.rk.c[i - 1] - pa.rk.c[i - 2]);
                 const double al = -cc, be = 1.0 + cc;
 #pragma unroll
                 for (int k = 0; k < N; ++k) x_cur[k] = al * SDF(i - 2, k) + be * SDF(i - 1, k);
@@ -487,22 +486,22 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     x_cur[i] -= delta[i];
-                    const double term = delta[i] / wt[i];
+                    const double term = DSB_DIV(delta[i], wt[i]);
                     acc += term * term;
                 }
-                const double norm = dsb_sqrt(acc / (double)N);
+                const double norm = dsb_sqrt(DSB_DIV(acc, (double)N));
                 conv.niter += 1;
                 const bool have_rate = conv.has_old_norm;
                 double px, py;
-                if (have_rate) { px = norm / conv.old_norm; py = 1.0 / (double)(conv.niter - 1); }
+                if (have_rate) { px = DSB_DIV(norm, conv.old_norm); py = DSB_DIV(1.0, (double)(conv.niter - 1)); }
                 else { const double min_eta = 1e4 * eps; px = (conv.eta < min_eta) ? min_eta : conv.eta; py = 0.8; }
                 const double pw = dsb_pow(px, py);
                 int s = LANE_CONTINUE;
                 if (have_rate) {
                     const double rate = pw;
                     if (rate > 0.9) s = LANE_DIVERGED;
-                    else if (dsb_powi(rate, conv.max_iter - conv.niter) / (1.0 - rate) * norm > conv.tol) s = LANE_DIVERGED;
-                    else conv.eta = rate / (1.0 - rate);
+                    else if (DSB_DIV(dsb_powi(rate, conv.max_iter - conv.niter), 1.0 - rate) * norm > conv.tol) s = LANE_DIVERGED;
+                    else conv.eta = DSB_DIV(rate, 1.0 - rate);
                 } else {
                     conv.eta = pw;
                 }
@@ -541,6 +540,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
         }
     }
 #undef SM
+#undef DSB_DIV
 #undef SDF
 #undef SJ
 #undef SMM
