@@ -109,6 +109,7 @@ SIGNATURES = {
     "dsb_batch_last_kernel_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "dsb_batch_last_integrator_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "dsb_batch_last_launch_count": (ctypes.c_int, [_vp, _pi32]),
+    "dsb_batch_debug_words": (ctypes.c_int, [_vp, _vp]),
     "dsb_lu_factor_batched": (ctypes.c_int, [_vp, _i32, _i64, _vp, _vp, _vp]),
     "dsb_lu_solve_batched": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "dsb_lu_factor_instance_major": (ctypes.c_int, [_vp, _i32, _i64, _vp, _vp, _vp]),

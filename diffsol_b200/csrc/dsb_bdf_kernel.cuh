@@ -157,6 +157,14 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
         return DSB_DIV(acc, (double)N);
     };
 
+#ifdef DSB_LANE_PROFILE          // warp-scheduler occupancy counters (warp-uniform values, lane 0 publishes them)
+    unsigned long long prof[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) prof[k] = 0;
+#define DSB_PROF_BLOCK(k, cond) { const int n_ = __popc(__ballot_sync(0xffffffffu, (cond))); if (n_) { prof[k] += 1; prof[k + 1] += n_; } }
+#else
+#define DSB_PROF_BLOCK(k, cond)
+#endif
     while (true) {
         // ---- warp-level block scheduler ---------------------------------------------------------------
         // The lanes of a warp are in different states.  The blocks every lane passes through once per
@@ -180,6 +188,10 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
         // and rejected)
         const bool run_select = n_slow > 0 && (n_slow >= quorum || 2 * n_slow >= n_active);
         const bool run_setup = run_select;
+#ifdef DSB_LANE_PROFILE
+        prof[0] += 1; prof[1] += n_active; prof[2] += (run_select ? 0 : n_slow);
+        DSB_PROF_BLOCK(3, run_select && (state == L_SELECT || state == L_RESCALE || state == L_JAC))
+#endif
 
         // ================= FINISH: write the instance's results, then fetch the next one =====================
         if (__any_sync(0xffffffffu, state == L_FINISH) && state == L_FINISH) {
@@ -453,6 +465,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
         }
 
         // ================= PREDICT: _predict_forward + start of a Newton solve ============================
+        DSB_PROF_BLOCK(5, state == L_PREDICT)
         if (__any_sync(0xffffffffu, state == L_PREDICT) && state == L_PREDICT) {
             if (repredict) {
                 double yp[N];
@@ -493,6 +506,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
         }
 
         // ================= NEWTON: one iteration (newton.rs:13-36, line_search.rs:48-69) ==================
+        DSB_PROF_BLOCK(7, state == L_NEWTON)
         if (__any_sync(0xffffffffu, state == L_NEWTON) && state == L_NEWTON) {
             double pl[NP > 0 ? NP : 1];
 #pragma unroll
@@ -554,6 +568,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
             }
         }
         // ================= POST: a Newton solve ended (bdf.rs:1338-1563) ==================================
+        DSB_PROF_BLOCK(9, state == L_POST)
         if (__any_sync(0xffffffffu, state == L_POST) && state == L_POST) {
             st.v[DSB_STAT_NONLINEAR_SOLVER_ITERATIONS] += conv.niter;
             if (newton_ok) {
@@ -619,6 +634,13 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
         }
 
     }
+#ifdef DSB_LANE_PROFILE
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) atomicAdd(work_counter + 1 + k, prof[k]);
+    }
+#endif
+#undef DSB_PROF_BLOCK
 #undef SM
 #undef DSB_DIV
 #undef SD

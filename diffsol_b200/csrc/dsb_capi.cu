@@ -383,7 +383,7 @@ int dsb_batch_new(const dsb_problem* p, int64_t nbatch, int32_t device, dsb_batc
     alloc((void**)&b->fin_order, B * 4);
     alloc((void**)&b->stats, (size_t)DSB_NSTATS * B * 4);
     alloc((void**)&b->status, B * 4);
-    alloc((void**)&b->work_counter, 8);
+    alloc((void**)&b->work_counter, 256);     // word 0: the work counter; words 1..31: diagnostics (DSB_LANE_PROFILE builds)
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_mid);
@@ -574,6 +574,14 @@ int dsb_batch_last_integrator_ms(dsb_batch* b, float* ms) {
 int dsb_batch_last_launch_count(dsb_batch* b, int32_t* launches) {
     if (!b || !launches) return fail(DSB_BAD_ARG, "NULL argument");
     *launches = b->last_launches;
+    return DSB_OK;
+}
+
+int dsb_batch_debug_words(dsb_batch* b, uint64_t* words_host) {
+    if (!b || !words_host) return fail(DSB_BAD_ARG, "NULL argument");
+    DSB_CUDA(cudaSetDevice(b->device));
+    DSB_CUDA(cudaDeviceSynchronize());
+    DSB_CUDA(cudaMemcpy(words_host, b->work_counter + 1, 31 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return DSB_OK;
 }
 

@@ -83,7 +83,7 @@ static cudaError_t launch_coop_bdf(const DsbProblemArgs* pa, const DsbBatchBuffe
         ws.color = (const int32_t*)coop->color_dev;
         ws.nz = (const uint8_t*)((char*)coop->color_dev + (size_t)N * sizeof(int32_t));
     }
-    e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
+    e = cudaMemsetAsync(work_counter, 0, 32 * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     if (mid) cudaEventRecord(mid, stream);
     dsb_coop_bdf_solve_dense_kernel<M><<<grid, threads, smem, stream>>>(*pa, *bb, ws, work_counter);
@@ -119,7 +119,7 @@ template <class M> struct LaneLauncher<M, true> {
             if (per_sm < 1) return cudaErrorLaunchOutOfResources;
             resident_blocks = sms * per_sm;
         }
-        cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
+        cudaError_t e = cudaMemsetAsync(work_counter, 0, 32 * sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return e;
         dsb_init_kernel<M><<<init_blocks, init_threads, 0, stream>>>(*pa, *bb, 1);
         if (mid) cudaEventRecord(mid, stream);
@@ -144,7 +144,7 @@ template <class M> struct LaneLauncher<M, true> {
             if (per_sm < 1) return cudaErrorLaunchOutOfResources;
             resident_blocks = sms * per_sm;
         }
-        cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
+        cudaError_t e = cudaMemsetAsync(work_counter, 0, 32 * sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return e;
         dsb_init_kernel<M><<<init_blocks, init_threads, 0, stream>>>(*pa, *bb, pa->rk.order);
         if (mid) cudaEventRecord(mid, stream);

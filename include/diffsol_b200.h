@@ -181,6 +181,9 @@ int dsb_batch_last_kernel_ms(dsb_batch* b, float* ms);
 int dsb_batch_last_integrator_ms(dsb_batch* b, float* ms);
 /* Number of kernels this library launched for the last solve. */
 int dsb_batch_last_launch_count(dsb_batch* b, int32_t* launches);
+/* Diagnostics: the 31 device words behind the persistent kernels' work counter.  A library built with
+ * -DDSB_LANE_PROFILE accumulates warp-scheduler occupancy counters there (tools/lane_profile.py); otherwise zeros. */
+int dsb_batch_debug_words(dsb_batch* b, uint64_t* words_host /* [31] */);
 
 /* ---- the LinearSolver<M> pair a Rust `impl LinearSolver<BatchMat>` would call
  * (diffsol-la/src/linear_solver/mod.rs:19-42; replaces NalgebraLU nalgebra/lu.rs:31-51 and the
