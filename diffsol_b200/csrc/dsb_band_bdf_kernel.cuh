@@ -1,0 +1,717 @@
+// dsb_band_bdf_kernel.cuh -- `problem.bdf::<LS>()?.solve_dense(t_eval)` for BANDED systems of medium size
+// (16 < n <= 64, identity mass, df/dy inside a declared band kl, ku <= 2): method-of-lines models such as the
+// single-particle battery model of BASELINE config 5 (two radial diffusion grids, tridiagonal).
+//
+// Execution model: still ONE LANE PER INSTANCE with the per-lane state machine and warp-level block scheduler of
+// dsb_bdf_kernel.cuh, but the instance's vectors and matrices do not fit on chip any more (n = 42: 7 KB per
+// instance), so they live in GLOBAL memory, one column per resident lane, word w of lane g at ws[w * LS + g]
+// (LS = lanes of the whole grid).  Every vector operation is a loop over the components with the SAME trip count
+// in all lanes, so the 32 lanes of a warp touch 32 consecutive doubles in every load and store: 256-byte
+// coalesced accesses, the batch-major layout SURVEY.md section 8d asks for.  This kernel is bound by HBM
+// bandwidth, not by FP64 issue: what it moves per Newton iteration is the band factors (4n words), the Newton
+// work vectors (6n words) and nothing else.
+//
+// The iteration matrix I - c J is factored per lane, sequentially, in LAPACK band storage (dgbtf2 convention,
+// 2 kl + ku + 1 rows per column: room for the fill-in of partial pivoting); the substitutions keep the running
+// entries in a REGISTER WINDOW (kl + 1 resp. kl + ku + 1 values), so that the recurrence never waits for a
+// global-memory round trip.  Same arithmetic as nalgebra's dense LU / solve (first maximum as pivot,
+// reciprocal-pivot scaling, `a = (-u) * l + a` in ascending pivot order, column-axpy substitutions): every
+// operation that is skipped has an exactly zero multiplier or pivot-row entry, the interchanges are interleaved
+// with the forward substitution as in dsb_coop.cuh:warp_band_solve, and the solutions are bit-identical to the
+// dense path (tests/test_gpu_band_parity.py against the oracle's dense LU).
+//
+// Restated functions: the same list as dsb_bdf_kernel.cuh, plus new_without_initialise / set_step_size
+// (ode_solver/state.rs:1086-1124, 1209-1277), which the small-n path runs in dsb_init_kernel.cuh.
+#pragma once
+#include "dsb_bdf_kernel.cuh"
+
+template <class M>
+struct BandBdfLayout {
+    static constexpr int N = M::N, NP = M::NP;
+    static constexpr int KL = M::BAND_KL, KU = M::BAND_KU, KV = KL + KU;
+    static constexpr int LDJ = KL + KU + 1;                         // rows of the band storage of df/dy
+    static constexpr int LDAB = 2 * KL + KU + 1;                    // rows of the band storage of the factors
+    static constexpr int O_D = 0;                                   // D[DSB_NDIFF][N]
+    static constexpr int O_Y = O_D + DSB_NDIFF * N;                 // state.y
+    static constexpr int O_YP = O_Y + N;                            // y_predict
+    static constexpr int O_YC = O_YP + N;                           // Newton iterate
+    static constexpr int O_PSI = O_YC + N;                          // psi - y_predict
+    static constexpr int O_DL = O_PSI + N;                          // Newton residual / update
+    static constexpr int O_J = O_DL + N;                            // df/dy, band storage: (i, j) at j * LDJ + KU + i - j
+    static constexpr int O_LU = O_J + LDJ * N;                      // factors, band storage: (i, j) at j * LDAB + KV + i - j
+    static constexpr int O_PIV = O_LU + LDAB * N;                   // pivot offsets (row j interchanged with row j + piv[j])
+    static constexpr int WORDS = O_PIV + N;
+    static constexpr int THREADS = 512;
+    static constexpr int SMEM_WORDS = (DSB_NSTATS + 1) / 2 + 36;    // statistics + the 6 x 6 rescale matrix R U
+    static_assert(N <= 64, "sparsity pattern rows are 64-bit masks");
+    static_assert(KL >= 1 && KL <= 2 && KU >= 1 && KU <= 2, "register windows are sized for kl, ku <= 2");
+};
+
+// indexable view of one vector of the lane's global-memory column (what the component-wise equations read)
+struct BandVec {
+    const double* base; size_t ls;
+    __device__ __forceinline__ double operator[](int k) const { return base[(size_t)k * ls]; }
+};
+// seed of one colour: 1 in every column of the colour that has a non-zero
+struct BandColourSeed {
+    const DsbProblemArgs* pa; int c;
+    __device__ __forceinline__ double operator[](int k) const {
+        return (pa->color_of_col[k] == c && pa->nz_rows_of_col[k] != 0) ? 1.0 : 0.0;
+    }
+};
+
+template <class M>
+__global__ void __maxnreg__(128) dsb_band_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa,
+                                                                  const __grid_constant__ DsbBatchBuffers bb,
+                                                                  double* __restrict__ ws,
+                                                                  unsigned long long* __restrict__ work_counter) {
+    typedef BandBdfLayout<M> Lay;
+    constexpr int N = Lay::N, NP = Lay::NP, KL = Lay::KL, KU = Lay::KU, KV = Lay::KV, LDJ = Lay::LDJ, LDAB = Lay::LDAB;
+    extern __shared__ double dsb_lane_smem[];
+    double* const sm = dsb_lane_smem + threadIdx.x;
+#define SMW(w) sm[(w) * Lay::THREADS]
+#define SRU(i, j) SMW((DSB_NSTATS + 1) / 2 + (i) * 6 + (j))
+    const size_t LS = (size_t)gridDim.x * blockDim.x;
+    double* const g = ws + ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+#define G(w) g[(size_t)(w) * LS]
+#define GD(j, i) G(Lay::O_D + (j) * N + (i))
+#define GY(i) G(Lay::O_Y + (i))
+#define GYP(i) G(Lay::O_YP + (i))
+#define GYC(i) G(Lay::O_YC + (i))
+#define GPSI(i) G(Lay::O_PSI + (i))
+#define GDL(i) G(Lay::O_DL + (i))
+#define GJ(j, r) G(Lay::O_J + (j) * LDJ + (r))
+#define GAB(j, r) G(Lay::O_LU + (j) * LDAB + (r))
+#define GPIV(j) G(Lay::O_PIV + (j))
+#define DSB_DIV(a, b) DsbDivShared::div((a), (b))
+    const BandVec vY{g + (size_t)Lay::O_Y * LS, LS}, vYC{g + (size_t)Lay::O_YC * LS, LS};
+
+    const int64_t B = pa.nbatch;
+    const int nt = pa.nt;
+    const bool free_running = pa.free_running != 0;
+    const int quorum = pa.quorum;
+    const double eps = 2.220446049250313e-16;
+
+    // ---- per-lane registers (the controller of dsb_bdf_kernel.cuh) ----------------------------------------
+    int state = L_FETCH;
+    int64_t inst = 0;
+    int order = 1, n_equal_steps = 0;
+    double t = 0.0, h = 0.0, c = 0.0, t_predict = 0.0;
+    bool has_tstop = false, has_prev_error = false, jacobian_is_stale = true;
+    double tstop = 0.0, prev_error_norm = 0.0;
+    LaneJacobianUpdate ju; ju.init(1.0);
+    LaneConvergence conv;
+    conv.tol = pa.opt.nonlinear_solver_tolerance; conv.max_iter = pa.opt.max_nonlinear_solver_iterations;
+    conv.eta = pa.tab.eta_reset; conv.old_norm = 0.0; conv.reset();
+    SmemLaneStats<2 * Lay::THREADS> st;
+    st.v.base = reinterpret_cast<int*>(&SMW(0));
+    double pl[NP > 0 ? NP : 1];
+#pragma unroll
+    for (int j = 0; j < (NP > 0 ? NP : 1); ++j) pl[j] = 0.0;
+    bool convergence_fail = false, newton_ok = false, first = true, reached = false, accepted = false;
+    bool repredict = true, pending_etf = false, rs_ignore_small = false;
+    int old_num_error_test_failures = 0, col = 0;
+    double safety = 0.0, error_norm = 0.0;
+    int after_rescale = L_JAC, after_jac = L_TSTOP, jac_kind = DSB_CHECKPOINT;
+    double rescale_factor = 1.0;
+    int fin_status = DSB_STATUS_OK;
+    auto finish = [&](int status) { fin_status = status; state = L_FINISH; };
+    // bdf.rs:694-731
+    auto handle_tstop = [&](double ts) -> int {
+        const double troundoff = 100.0 * eps * (dsb_abs(t) + dsb_abs(h));
+        if (dsb_abs(t - ts) <= troundoff) { has_tstop = false; return 1; }
+        if ((h > 0.0 && ts < t - troundoff) || (h < 0.0 && ts > t + troundoff)) {
+            has_tstop = false;
+            return -DSB_STATUS_STOP_TIME_BEFORE_CURRENT;
+        }
+        if ((h > 0.0 && t + h > ts + troundoff) || (h < 0.0 && t + h < ts - troundoff)) {
+            rescale_factor = DSB_DIV(ts - t, h);
+            return 2;
+        }
+        return 0;
+    };
+    // runge_kutta.rs:1313-1335
+    auto pi_controller_raw = [&](double err, int eff_order) -> double {
+        const double order_f = (double)eff_order;
+        const double ki = DSB_DIV(pa.opt.pi_control_integral, order_f);
+        const bool p_only = pa.opt.pi_control_proportional == 0.0 || !has_prev_error;
+        const double kp = p_only ? 0.0 : DSB_DIV(pa.opt.pi_control_proportional, order_f);
+        double v = dsb_pow(err, p_only ? -ki : -(ki + kp));
+        if (!p_only) v = v * dsb_pow(prev_error_norm, kp);
+        return v;
+    };
+    // ||x||^2_w(ref) (vector/nalgebra_serial.rs:395-408): x and ref are word offsets of the lane's column; the
+    // terms are added in index order, the loads do not depend on the sum and run ahead of it
+    auto weighted_norm = [&](int ox, int oref) -> double {
+        double acc = 0.0;
+#pragma unroll 4
+        for (int i = 0; i < N; ++i) {
+            const double term = DSB_DIV(G(ox + i), dsb_abs(G(oref + i)) * pa.rtol + pa.atol[i]);
+            acc += term * term;
+        }
+        return DSB_DIV(acc, (double)N);
+    };
+
+    while (true) {
+        // ---- warp-level block scheduler (dsb_bdf_kernel.cuh) ---------------------------------------------------
+        const unsigned m_idle = __ballot_sync(0xffffffffu, state == L_IDLE);
+        if (m_idle == 0xffffffffu) break;
+        const int n_active = 32 - __popc(m_idle);
+        const int n_slow = __popc(__ballot_sync(0xffffffffu, state == L_SELECT || state == L_RESCALE || state == L_JAC));
+        const bool run_slow = n_slow > 0 && (n_slow >= quorum || 2 * n_slow >= n_active);
+
+        // ================= FINISH =================================================================================
+        if (__any_sync(0xffffffffu, state == L_FINISH) && state == L_FINISH) {
+            bb.status[inst] = fin_status;
+            bb.fin_t[inst] = t; bb.fin_h[inst] = h; bb.fin_order[inst] = order;
+#pragma unroll
+            for (int k = 0; k < DSB_NSTATS; ++k) bb.stats[(int64_t)k * B + inst] = st.v[k];
+            state = L_FETCH;
+        }
+        // ================= FETCH: next instance; new_without_initialise, set_step_size, Bdf::_new part 1 ==============
+        if (__any_sync(0xffffffffu, state == L_FETCH) && state == L_FETCH) {
+            inst = (int64_t)atomicAdd(work_counter, 1ull);
+            if (inst >= B) {
+                state = L_IDLE;
+            } else {
+#pragma unroll
+                for (int j = 0; j < NP; ++j) pl[j] = bb.params[(int64_t)j * B + inst];
+#pragma unroll
+                for (int k = 0; k < DSB_NSTATS; ++k) st.v[k] = 0;
+                t = pa.t0;
+                // y = init(p, t0); dy = f(y, t0)     (state.rs:1086-1124); dy is kept in D[1] until h is known
+#pragma unroll 2
+                for (int i = 0; i < N; ++i) GY(i) = M::init_i(i, pl, pa.t0);
+#pragma unroll 2
+                for (int i = 0; i < N; ++i) GD(1, i) = M::rhs_i(i, vY, pl, pa.t0);
+                st.v[DSB_STAT_RHS_CALLS] += 1;
+                // set_step_size (state.rs:1209-1277), solver order 1
+                {
+                    const bool is_neg_h = pa.h0 < 0.0;
+                    const double d0 = dsb_sqrt(weighted_norm(Lay::O_Y, Lay::O_Y));
+                    const double d1 = dsb_sqrt(weighted_norm(Lay::O_D + N, Lay::O_Y));
+                    const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * DSB_DIV(d0, d1);
+#pragma unroll 2
+                    for (int i = 0; i < N; ++i) GYC(i) = is_neg_h ? (GD(1, i) * (-h0) + GY(i)) : (GD(1, i) * h0 + GY(i));
+                    const double t1 = is_neg_h ? pa.t0 - h0 : pa.t0 + h0;
+#pragma unroll 2
+                    for (int i = 0; i < N; ++i) GDL(i) = M::rhs_i(i, vYC, pl, t1) - GD(1, i);
+                    st.v[DSB_STAT_RHS_CALLS] += 1;
+                    const double d2 = DSB_DIV(dsb_sqrt(weighted_norm(Lay::O_DL, Lay::O_Y)), dsb_abs(h0));
+                    double max_d = d2;
+                    if (max_d < d1) max_d = d1;
+                    double h1;
+                    if (max_d < 1e-15) { h1 = h0 * 1e-3; if (h1 < 1e-6) h1 = 1e-6; }
+                    else h1 = dsb_pow(DSB_DIV(0.01, max_d), DSB_DIV(1.0, 1.0 + 1.0));
+                    h = 100.0 * h0;
+                    if (h > h1) h = h1;
+                    if (is_neg_h) h = -h;
+                }
+                // state.set_problem (bdf_state.rs:72-78): D[:, 0] = y, D[:, 1] = h dy, the rest zero
+                for (int i = 0; i < N; ++i) {
+                    GD(0, i) = GY(i);
+                    GD(1, i) = GD(1, i) * h;
+#pragma unroll
+                    for (int j = 2; j < DSB_NDIFF; ++j) GD(j, i) = 0.0;
+                }
+                order = 1; n_equal_steps = 0;
+                conv.eta = pa.tab.eta_reset; conv.old_norm = 0.0; conv.reset();
+                c = h * pa.tab.alpha[1];
+                jacobian_is_stale = true;
+                ju.init(1.0);                                   // jacobian_update.rs:27 -- h_at_last starts at ONE
+                has_tstop = false; tstop = 0.0; has_prev_error = false; prev_error_norm = 0.0;
+                convergence_fail = false; first = true; reached = false; pending_etf = false; col = 0;
+                t_predict = t;
+                jac_kind = DSB_KIND_CONSTRUCT;
+                state = L_JAC;
+            }
+        }
+        // ================= SELECT (bdf.rs:1489-1563, 1431-1442) ===========================================================
+        if (run_slow && state == L_SELECT) {
+            const int ord = order;
+            const double inf = dsb_from_bits(0x7ff0000000000000ULL);
+            double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+#pragma unroll 1
+            for (int q = 0; q < 3; ++q) {
+                if (accepted || q == 1) {
+                    double err = error_norm;
+                    if (q != 1) {
+                        err = inf;
+                        if ((q == 0) ? (ord > 1) : (ord < DSB_MAX_ORDER)) {
+                            const double e = weighted_norm(Lay::O_D + (ord + q) * N, Lay::O_Y) * pa.tab.error_const2[ord - 1 + q];
+                            err = (0.0 < e) ? e : 0.0;
+                        }
+                    }
+                    const double v = pi_controller_raw(err, ord + q);
+                    if (q == 0) f0 = v; else if (q == 1) f1 = v; else f2 = v;
+                }
+            }
+            if (accepted) {
+                int max_index = 0;                      // Iterator::max_by keeps the LAST maximum
+                double fmax = f0;
+                if (!(fmax > f1)) { max_index = 1; fmax = f1; }
+                if (!(fmax > f2)) { max_index = 2; fmax = f2; }
+                order = ord + (max_index - 1);
+                double factor = safety * fmax;
+                if (factor > pa.opt.max_timestep_growth) factor = pa.opt.max_timestep_growth;
+                if (factor < pa.opt.min_timestep_shrink) factor = pa.opt.min_timestep_shrink;
+                state = L_TSTOP;
+                if (factor >= pa.opt.min_timestep_growth || factor <= pa.opt.max_timestep_shrink || max_index != 1) {
+                    rescale_factor = factor; rs_ignore_small = false;
+                    state = L_RESCALE; after_rescale = L_JAC;
+                    jac_kind = DSB_STEP_SUCCESS; after_jac = L_TSTOP;
+                }
+            } else {
+                double factor = safety * f1;
+                has_prev_error = false;
+                if (factor < pa.opt.min_timestep_shrink) factor = pa.opt.min_timestep_shrink;
+                rescale_factor = factor; rs_ignore_small = false;
+                state = L_RESCALE; after_rescale = L_JAC;
+                jac_kind = DSB_ERROR_TEST_FAIL; after_jac = L_PREDICT;
+                repredict = true; pending_etf = true;
+            }
+        }
+
+        // ================= RESCALE: _update_step_size(factor) (bdf.rs:508-577) ==============================================
+        // R U (rows / columns 1..k; row and column 0 are those of the identity) is built row by row as in
+        // dsb_bdf_kernel.cuh and parked in shared memory, then D[:, 1..k] <- D[:, 1..k] (R U) one component at a time.
+        if (run_slow && state == L_RESCALE) {
+            const double factor = rescale_factor;
+            const double new_h = factor * h;
+            n_equal_steps = 0;
+            const int k = order;
+            const double* __restrict__ u = pa.tab.u[DSB_MAX_ORDER];         // leading dimension 6
+            {
+                double rrow[DSB_MAX_ORDER + 1];
+#pragma unroll
+                for (int l = 1; l <= DSB_MAX_ORDER; ++l) rrow[l] = 1.0;
+#pragma unroll 1
+                for (int i = 1; i <= k; ++i) {
+                    const double i_t = (double)i;
+#pragma unroll
+                    for (int l = 1; l <= DSB_MAX_ORDER; ++l) rrow[l] = DSB_DIV(rrow[l] * (i_t - 1.0 - factor * (double)l), i_t);
+#pragma unroll
+                    for (int j = 1; j <= DSB_MAX_ORDER; ++j) {
+                        double ru_ij = rrow[1] * u[j * 6 + 1];
+#pragma unroll
+                        for (int l = 2; l <= j; ++l) ru_ij = rrow[l] * u[j * 6 + l] + ru_ij;
+                        SRU(i, j) = ru_ij;
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int s = 0; s < N; ++s) {
+                double nd[DSB_MAX_ORDER + 1];
+#pragma unroll
+                for (int j = 1; j <= DSB_MAX_ORDER; ++j) nd[j] = -0.0;      // (-0.0) + x == x: the first term is assigned
+#pragma unroll 1
+                for (int i = 1; i <= k; ++i) {
+                    const double di = GD(i, s);
+#pragma unroll
+                    for (int j = 1; j <= DSB_MAX_ORDER; ++j) nd[j] = di * SRU(i, j) + nd[j];
+                }
+#pragma unroll
+                for (int j = 1; j <= DSB_MAX_ORDER; ++j) if (j <= k) GD(j, s) = nd[j];
+            }
+            c = new_h * pa.tab.alpha[k];
+            h = new_h;
+            conv.eta = pa.tab.eta_reset_timestep;
+            if (!rs_ignore_small && dsb_abs(h) < pa.opt.min_timestep) finish(DSB_STATUS_STEP_SIZE_TOO_SMALL);
+            else state = after_rescale;
+        }
+
+        // ================= JAC: _jacobian_updates(c, kind) / Bdf::_new's reset_jacobian =====================================
+        if (run_slow && state == L_JAC) {
+            bool do_factor = false;
+            if (jac_kind == DSB_KIND_CONSTRUCT) {
+                do_factor = true;
+                st.v[DSB_STAT_LINEAR_SOLVER_SETUPS] += 1;
+                st.v[DSB_STAT_SETUPS_FROM_CHECKPOINT] += 1;
+                after_jac = L_TSTOP;
+            } else if (ju.check_rhs_jacobian_update<DsbDivShared>(pa.opt, c, jac_kind)) {
+                jacobian_is_stale = true;
+                ju.update_rhs_jacobian(c);
+                ju.update_jacobian(c);
+                do_factor = true;
+            } else if (ju.check_jacobian_update<DsbDivShared>(pa.opt, c, jac_kind)) {
+                ju.update_jacobian(c);
+                do_factor = true;
+            }
+            if (do_factor) {
+                if (jac_kind != DSB_KIND_CONSTRUCT) {
+                    conv.eta = pa.tab.eta_reset;
+                    st.record_linear_solver_setup(jac_kind);
+                }
+                if (jacobian_is_stale) {
+                    // df/dy at (state.y, state.t) (quirk Q6), one jac_mul per colour (jacobian/mod.rs:236-256; without
+                    // colouring the host supplies one colour per column: op/nonlinear_op.rs:211-220), scattered through
+                    // the sparsity pattern into band storage
+                    st.v[DSB_STAT_RHS_MATRIX_EVALS] += 1;
+                    for (int e = 0; e < LDJ * N; ++e) G(Lay::O_J + e) = 0.0;
+                    const bool one_colour_per_column = pa.ncolors == N;
+#pragma unroll 1
+                    for (int cc = 0; cc < pa.ncolors; ++cc) {
+                        const BandColourSeed seed{&pa, cc};
+                        st.v[DSB_STAT_RHS_JAC_MULS] += 1;
+                        // rows outside the band of the colour's only column hold exact zeros and are not evaluated
+                        const int i0 = one_colour_per_column ? (cc - KU < 0 ? 0 : cc - KU) : 0;
+                        const int i1 = one_colour_per_column ? (cc + KL > N - 1 ? N - 1 : cc + KL) : N - 1;
+#pragma unroll 1
+                        for (int i = i0; i <= i1; ++i) {
+                            const double val = M::jac_mul_i(i, vY, pl, t, seed);
+#pragma unroll
+                            for (int d = -KL; d <= KU; ++d) {               // column j = i + d
+                                const int j = i + d;
+                                if (j >= 0 && j < N && pa.color_of_col[j] == cc && ((pa.nz_rows_of_col[j] >> i) & 1ull))
+                                    GJ(j, KU - d) = val;
+                            }
+                        }
+                    }
+                    jacobian_is_stale = false;
+                }
+                // A = I - c J (op/bdf.rs:282-298: J * (-c) + M) in band storage with kl extra rows for the fill-in
+                const double mc = -c;
+#pragma unroll 1
+                for (int j = 0; j < N; ++j) {
+#pragma unroll
+                    for (int r = 0; r < LDAB; ++r) {
+                        const int i = j + r - KV;
+                        double v = 0.0;
+                        if (r >= KL && i >= 0 && i < N) v = GJ(j, r - KL) * mc + ((i == j) ? 1.0 : 0.0);
+                        GAB(j, r) = v;
+                    }
+                }
+                // band LU, dgbtf2 convention (dsb_coop.cuh:warp_band_factor, one lane instead of one warp)
+                int jlast = 0;                                   // last column touched by the fill-in so far
+#pragma unroll 1
+                for (int j = 0; j < N; ++j) {
+                    const int km = (KL < N - 1 - j) ? KL : (N - 1 - j);
+                    double colv[KL + 1];
+#pragma unroll
+                    for (int d = 0; d <= KL; ++d) colv[d] = (d <= km) ? GAB(j, KV + d) : 0.0;
+                    int jp = 0;
+                    double best = -1.0;
+#pragma unroll
+                    for (int d = 0; d <= KL; ++d) {
+                        const double av = dsb_abs(colv[d]);
+                        if (d <= km && av == av && av > best) { best = av; jp = d; }     // first maximum, NaNs never win
+                    }
+                    if (colv[0] != colv[0]) jp = 0;                  // a NaN diagonal keeps the diagonal
+                    double diag = colv[0];
+#pragma unroll
+                    for (int d = 1; d <= KL; ++d) if (jp == d) diag = colv[d];
+                    if (diag == 0.0) { GPIV(j) = 0.0; continue; }
+                    GPIV(j) = (double)jp;
+                    { const int cand = (j + KU + jp < N - 1) ? (j + KU + jp) : (N - 1); if (cand > jlast) jlast = cand; }
+                    if (jp != 0) {
+#pragma unroll
+                        for (int q = 0; q <= KV; ++q) {              // columns j .. jlast (at most kv + 1 of them)
+                            const int cq = j + q;
+                            if (cq <= jlast) {
+                                const double a = GAB(cq, KV - q), b = GAB(cq, KV - q + jp);
+                                GAB(cq, KV - q) = b; GAB(cq, KV - q + jp) = a;
+                            }
+                        }
+#pragma unroll
+                        for (int d = 0; d <= KL; ++d) {              // the register copy of column j follows the interchange
+                            const double a = colv[0];
+                            if (jp == d && d != 0) { colv[0] = colv[d]; colv[d] = a; }
+                        }
+                    }
+                    if (km > 0) {
+                        const double inv_diag = 1.0 / colv[0];
+#pragma unroll
+                        for (int d = 1; d <= KL; ++d) if (d <= km) { colv[d] *= inv_diag; GAB(j, KV + d) = colv[d]; }
+#pragma unroll
+                        for (int q = 1; q <= KV; ++q) {              // columns j + 1 .. jlast
+                            const int cq = j + q;
+                            if (cq <= jlast) {
+                                const double mpk = -GAB(cq, KV - q);
+#pragma unroll
+                                for (int d = 1; d <= KL; ++d)
+                                    if (d <= km) GAB(cq, KV - q + d) = mpk * colv[d] + GAB(cq, KV - q + d);
+                            }
+                        }
+                    }
+                }
+            }
+            state = after_jac;
+        }
+
+        // ================= TSTOP ==========================================================================================
+        if (__any_sync(0xffffffffu, state == L_TSTOP) && state == L_TSTOP) {
+            int next = first ? L_PREDICT : L_OUTPUT;
+            int r = 0;
+            bool check = has_tstop;
+            if (first) {
+                check = !free_running;
+                if (free_running) next = L_OUTPUT;
+                else { has_tstop = true; tstop = bb.t_eval[nt - 1]; }
+            }
+            if (check) {
+                r = handle_tstop(tstop);
+                if (r == 1) {
+                    if (first) r = -DSB_STATUS_STOP_TIME_AT_CURRENT;
+                    else reached = true;
+                }
+            }
+            if (r < 0) {
+                finish(-r);
+            } else if (r == 2) {
+                rs_ignore_small = true;            // "step size too small" is ignored here (bdf.rs:726-728)
+                state = L_RESCALE; after_rescale = next;
+            } else {
+                state = next;
+            }
+            if (first && state != L_FETCH) {       // start of the first step()
+                old_num_error_test_failures = st.v[DSB_STAT_ERROR_TEST_FAILURES];
+                convergence_fail = false; repredict = true;
+            }
+            first = false;
+        }
+
+        // ================= OUTPUT: dense output at every t_eval passed (method.rs:761-764, 822-848) =========================
+        if (__any_sync(0xffffffffu, state == L_OUTPUT) && state == L_OUTPUT) {
+            int status = DSB_STATUS_OK;
+            while (col < nt) {
+                const double tq = bb.t_eval[col];
+                if (free_running ? (dsb_abs(t) < dsb_abs(tq)) : !(tq <= t)) break;
+                const bool is_forward = h > 0.0;
+                if ((is_forward && tq > t) || (!is_forward && tq < t)) { status = DSB_STATUS_INTERPOLATION_TIME_AFTER_CURRENT; break; }
+                // interpolate (bdf.rs:767-782, 1080-1106): the time factors first, then one pass over the components
+                double tf[DSB_MAX_ORDER];
+                double time_factor = 1.0;
+#pragma unroll
+                for (int j = 0; j < DSB_MAX_ORDER; ++j) {
+                    if (j < order) {
+                        const double j_t = (double)j;
+                        time_factor *= DSB_DIV(tq - (t - h * j_t), h * (1.0 + j_t));
+                    }
+                    tf[j] = time_factor;
+                }
+#pragma unroll 2
+                for (int i = 0; i < N; ++i) {
+                    double yo = GD(0, i);
+#pragma unroll
+                    for (int j = 0; j < DSB_MAX_ORDER; ++j) if (j < order) yo = tf[j] * GD(j + 1, i) + yo;
+                    bb.ys[((int64_t)col * N + i) * B + inst] = yo;
+                }
+                ++col;
+            }
+            if (status != DSB_STATUS_OK) finish(status);
+            else if (free_running ? (col >= nt) : reached) finish(DSB_STATUS_OK);
+            else {                                  // start of the next step()
+                old_num_error_test_failures = st.v[DSB_STAT_ERROR_TEST_FAILURES];
+                convergence_fail = false; repredict = true;
+                state = L_PREDICT;
+            }
+        }
+
+        // ================= PREDICT: _predict_forward + start of a Newton solve ===============================================
+        if (__any_sync(0xffffffffu, state == L_PREDICT) && state == L_PREDICT) {
+            if (repredict) {
+                const int ord = order;
+                const double a = pa.tab.alpha[ord];
+#pragma unroll 2
+                for (int i = 0; i < N; ++i) {
+                    double yp = 0.0;
+                    double ps = 0.0;
+#pragma unroll
+                    for (int j = 0; j <= DSB_MAX_ORDER; ++j) {
+                        if (j <= ord) {
+                            const double d = GD(j, i);
+                            yp += d;
+                            if (j == 1) ps = pa.tab.gamma[1] * d;
+                            else if (j >= 2) ps = pa.tab.gamma[j] * d + ps;
+                        }
+                    }
+                    ps *= a;
+                    ps -= yp;
+                    GYP(i) = yp; GPSI(i) = ps; GYC(i) = yp;
+                }
+                t_predict = t + h;
+            } else {
+#pragma unroll 4
+                for (int i = 0; i < N; ++i) GYC(i) = GYP(i);
+            }
+            state = L_NEWTON;
+            if (pending_etf) {
+                pending_etf = false;
+                st.v[DSB_STAT_ERROR_TEST_FAILURES] += 1;
+                if (st.v[DSB_STAT_ERROR_TEST_FAILURES] - old_num_error_test_failures >= pa.opt.max_error_test_failures)
+                    finish(DSB_STATUS_TOO_MANY_ERROR_TEST_FAILURES);
+            }
+            conv.reset();
+        }
+
+        // ================= NEWTON: one iteration (newton.rs:13-36, line_search.rs:48-69) =====================================
+        if (__any_sync(0xffffffffu, state == L_NEWTON) && state == L_NEWTON) {
+            // delta = F(y) = (y + psi - y0) - c f(t, y)   (op/bdf.rs:240-256, identity mass)
+            const double mc = -c;
+#pragma unroll 2
+            for (int i = 0; i < N; ++i) {
+                const double f = M::rhs_i(i, vYC, pl, t_predict);
+                GDL(i) = (GYC(i) + GPSI(i)) + mc * f;
+            }
+            st.v[DSB_STAT_RHS_CALLS] += 1;
+            // forward substitution with the interchanges interleaved; b[j .. j + kl] travels in registers
+            {
+                double w[KL + 1];
+#pragma unroll
+                for (int d = 0; d <= KL; ++d) w[d] = GDL(d);
+#pragma unroll 2
+                for (int j = 0; j + 1 < N; ++j) {
+                    const int jp = (int)GPIV(j);
+                    if (jp != 0) {
+                        const double a = w[0];
+#pragma unroll
+                        for (int d = 1; d <= KL; ++d) if (jp == d) { w[0] = w[d]; w[d] = a; }
+                    }
+                    const double bj = w[0];
+                    GDL(j) = bj;
+                    const double nbj = -bj;
+                    const int lm = (KL < N - 1 - j) ? KL : (N - 1 - j);
+#pragma unroll
+                    for (int d = 1; d <= KL; ++d) if (d <= lm) w[d] = nbj * GAB(j, KV + d) + w[d];
+#pragma unroll
+                    for (int d = 0; d < KL; ++d) w[d] = w[d + 1];
+                    w[KL] = (j + 1 + KL < N) ? GDL(j + 1 + KL) : 0.0;
+                }
+                GDL(N - 1) = w[0];
+            }
+            // back substitution, column-axpy form; b[i - kv .. i] travels in registers
+            bool ok = true;
+            {
+                double w[KV + 1];
+#pragma unroll
+                for (int e = 0; e <= KV; ++e) w[e] = GDL(N - 1 - e);
+#pragma unroll 2
+                for (int i = N - 1; i >= 0; --i) {
+                    const double diag = GAB(i, KV);
+                    if (diag == 0.0) ok = false;
+                    if (ok) {
+                        const double coeff = DSB_DIV(w[0], diag);
+                        GDL(i) = coeff;
+                        const double ncoeff = -coeff;
+#pragma unroll
+                        for (int e = 1; e <= KV; ++e) if (i - e >= 0) w[e] = ncoeff * GAB(i, KV - e) + w[e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < KV; ++e) w[e] = w[e + 1];
+                    w[KV] = (i - 1 - KV >= 0) ? GDL(i - 1 - KV) : 0.0;
+                }
+            }
+            if (!ok) {
+                newton_ok = false; state = L_POST;              // LuSolveFailed
+            } else {
+                double acc = 0.0;
+#pragma unroll 4
+                for (int i = 0; i < N; ++i) {
+                    const double dl = GDL(i);
+                    GYC(i) = GYC(i) - dl;
+                    // Newton norm weights use the PREDICTOR (line_search.rs:67, convergence.rs:64-66)
+                    const double term = DSB_DIV(dl, dsb_abs(GYP(i)) * pa.rtol + pa.atol[i]);
+                    acc += term * term;
+                }
+                const double norm = dsb_sqrt(DSB_DIV(acc, (double)N));
+                // Convergence::check_new_iteration (convergence.rs:68-139)
+                conv.niter += 1;
+                const bool have_rate = conv.has_old_norm;
+                double px, py;
+                if (have_rate) { px = DSB_DIV(norm, conv.old_norm); py = DSB_DIV(1.0, (double)(conv.niter - 1)); }
+                else { const double min_eta = 1e4 * eps; px = (conv.eta < min_eta) ? min_eta : conv.eta; py = 0.8; }
+                const double pw = dsb_pow(px, py);
+                int s = LANE_CONTINUE;
+                if (have_rate) {
+                    const double rate = pw;
+                    if (rate > 0.9) s = LANE_DIVERGED;
+                    else if (DSB_DIV(dsb_powi(rate, conv.max_iter - conv.niter), 1.0 - rate) * norm > conv.tol) s = LANE_DIVERGED;
+                    else conv.eta = DSB_DIV(rate, 1.0 - rate);
+                } else {
+                    conv.eta = pw;
+                }
+                if (s != LANE_DIVERGED && conv.eta * norm < conv.tol) s = LANE_CONVERGED;
+                if (conv.niter == 1) { conv.has_old_norm = true; conv.old_norm = norm; }   // frozen at the FIRST norm (quirk Q3)
+                if (s == LANE_CONVERGED) { newton_ok = true; state = L_POST; }
+                else if (s == LANE_DIVERGED || conv.niter >= conv.max_iter) { newton_ok = false; state = L_POST; }
+            }
+        }
+        // ================= POST: a Newton solve ended (bdf.rs:1338-1563) =====================================================
+        if (__any_sync(0xffffffffu, state == L_POST) && state == L_POST) {
+            st.v[DSB_STAT_NONLINEAR_SOLVER_ITERATIONS] += conv.niter;
+            if (newton_ok) {
+                const int ord = order;
+                {   // error_control: ||d||^2_w(state.y) * error_const2[order - 1], d = y - y_predict
+                    double acc = 0.0;
+#pragma unroll 4
+                    for (int i = 0; i < N; ++i) {
+                        const double d = GYC(i) - GYP(i);
+                        const double term = DSB_DIV(d, dsb_abs(GY(i)) * pa.rtol + pa.atol[i]);
+                        acc += term * term;
+                    }
+                    const double err = DSB_DIV(acc, (double)N) * pa.tab.error_const2[ord - 1];
+                    error_norm = (0.0 < err) ? err : 0.0;
+                }
+                const double maxiter = (double)conv.max_iter;
+                const double niter = (double)conv.niter;
+                safety = DSB_DIV(0.9 * (2.0 * maxiter + 1.0), 2.0 * maxiter + niter);
+                if (error_norm <= 1.0) {
+                    // ---- accepted: _update_diff, state.y <- PREDICTOR (quirk Q1) ----
+#pragma unroll 2
+                    for (int i = 0; i < N; ++i) {
+                        const double yp = GYP(i);
+                        const double d = GYC(i) - yp;
+                        double above = d;                                   // the new D[:, ord + 1]
+                        GD(ord + 2, i) = d - GD(ord + 1, i);
+                        GD(ord + 1, i) = d;
+#pragma unroll 1
+                        for (int j = ord; j >= 0; --j) {
+                            above = GD(j, i) + 1.0 * above;
+                            GD(j, i) = above;
+                        }
+                        GY(i) = yp;
+                    }
+                    t = t_predict;
+                    st.v[DSB_STAT_STEPS] += 1;
+                    ju.step();
+                    has_prev_error = true; prev_error_norm = error_norm;
+                    n_equal_steps += 1;
+                    accepted = true;
+                    state = (n_equal_steps > ord) ? L_SELECT : L_TSTOP;
+                } else {
+                    accepted = false;
+                    state = L_SELECT;
+                }
+            } else {
+                // ---- Newton failed ----
+                st.v[DSB_STAT_NONLINEAR_SOLVER_FAILS] += 1;
+                has_prev_error = false;
+                if (st.v[DSB_STAT_NONLINEAR_SOLVER_FAILS] > pa.opt.max_nonlinear_solver_failures) {
+                    finish(DSB_STATUS_TOO_MANY_NONLINEAR_FAILURES);
+                } else if (convergence_fail) {
+                    rescale_factor = 0.3; rs_ignore_small = false;
+                    state = L_RESCALE; after_rescale = L_JAC;
+                    jac_kind = DSB_SECOND_CONVERGENCE_FAIL; after_jac = L_PREDICT;
+                    repredict = true;
+                } else {
+                    convergence_fail = true;
+                    state = L_JAC; jac_kind = DSB_FIRST_CONVERGENCE_FAIL; after_jac = L_PREDICT;
+                    repredict = false;                          // retry from the SAME predictor
+                }
+            }
+        }
+    }
+#undef SMW
+#undef SRU
+#undef G
+#undef GD
+#undef GY
+#undef GYP
+#undef GYC
+#undef GPSI
+#undef GDL
+#undef GJ
+#undef GAB
+#undef GPIV
+#undef DSB_DIV
+}

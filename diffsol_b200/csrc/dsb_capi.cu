@@ -495,7 +495,7 @@ int dsb_batch_step_and_interpolate(dsb_batch* b, int32_t method, const double* t
 }
 
 int dsb_batch_set_execution(dsb_batch* b, int32_t mode) {
-    if (!b || mode < 0 || mode > 2) return fail(DSB_BAD_ARG, "mode must be 0 (automatic), 1 (thread per instance) or 2 (block per instance)");
+    if (!b || mode < 0 || mode > 3) return fail(DSB_BAD_ARG, "mode must be 0 (automatic), 1 (thread per instance), 2 (block per instance) or 3 (thread per instance, banded, state in global memory)");
     b->coop.exec_mode = mode;
     return DSB_OK;
 }

@@ -87,8 +87,15 @@ struct CoopBdfLayout {
     static size_t smem_bytes() { return (size_t)NVEC * N * sizeof(double) + coop_lu_smem_bytes_host(N) + 64; }
 };
 
+// Resident blocks the register allocation is asked to allow: DSB_COOP_TARGET_THREADS lanes per SM (the kernel is
+// latency bound -- barriers, global-memory factors -- so resident warps matter more than registers per lane).
+// Measured on SPM (n = 42, 64-lane blocks): 4 -> 16 resident blocks per SM = 1.75x, spills included; at n = 256 shared
+// memory allows 2 blocks either way.
+#ifndef DSB_COOP_TARGET_THREADS
+#define DSB_COOP_TARGET_THREADS(threads) ((threads) <= 64 ? 1024 : 256)
+#endif
 template <class M>
-__global__ void __launch_bounds__(CoopBdfLayout<M>::THREADS, 2)
+__global__ void __launch_bounds__(CoopBdfLayout<M>::THREADS, DSB_COOP_TARGET_THREADS(CoopBdfLayout<M>::THREADS) / CoopBdfLayout<M>::THREADS)
 dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __grid_constant__ DsbBatchBuffers bb,
                                 const __grid_constant__ DsbCoopWorkspace ws, unsigned long long* __restrict__ work_counter) {
     constexpr int N = M::N;

@@ -1,4 +1,9 @@
 // dsb_inst.cu -- instantiates the lane kernels for ONE equation set: compile with -DDSB_INST=<model id>.
+#include <cmath>
+#include <limits>
+#include <vector>
+
+#include "dsb_band_bdf_kernel.cuh"
 #include "dsb_bdf_kernel.cuh"
 #include "dsb_coop_bdf_kernel.cuh"
 #include "dsb_init_kernel.cuh"
@@ -91,6 +96,69 @@ static cudaError_t launch_coop_bdf(const DsbProblemArgs* pa, const DsbBatchBuffe
     return cudaGetLastError();
 }
 
+// banded lane kernel (one thread per instance, state in global memory): component-wise models without a mass
+// matrix that declare a band, 16 < n <= 64
+template <class M, class = void> struct dsb_declares_band : std::false_type {};
+template <class M> struct dsb_declares_band<M, std::void_t<decltype(M::BAND_KL)>> : std::true_type {};
+constexpr bool kBandCapable = dsb_declares_band<InstModel>::value && dsb_is_componentwise<InstModel>::value &&
+                              !InstModel::HAS_MASS && InstModel::N > 16 && InstModel::N <= 64;
+
+template <class M, bool BAND> struct BandLauncher {
+    static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, cudaStream_t, cudaEvent_t, unsigned long long*, DsbCoopState*, int*) {
+        return cudaErrorNotSupported;
+    }
+};
+template <class M> struct BandLauncher<M, true> {
+    static cudaError_t run(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, cudaStream_t stream, cudaEvent_t mid,
+                           unsigned long long* work_counter, DsbCoopState* coop, int* launches) {
+        typedef BandBdfLayout<M> Lay;
+        constexpr int N = M::N;
+        // the declared band must cover the sparsity pattern (NaN probe, jacobian/mod.rs:16-48)
+        {
+            double p[M::NP > 0 ? M::NP : 1];
+            for (int j = 0; j < M::NP; ++j) p[j] = 1.0;
+            std::vector<double> y0(N), v(N, 0.0), col(N, 0.0);
+            M::init(p, pa->t0, y0.data());
+            for (int j = 0; j < N; ++j) {
+                v[j] = std::numeric_limits<double>::quiet_NaN();
+                M::jac_mul(y0.data(), p, pa->t0, v.data(), col.data());
+                for (int i = 0; i < N; ++i)
+                    if (std::isnan(col[i]) && (i - j > Lay::KL || j - i > Lay::KU)) return cudaErrorNotSupported;
+                for (int i = 0; i < N; ++i) col[i] = 0.0;
+                v[j] = 0.0;
+            }
+        }
+        const int threads = Lay::THREADS;
+        const size_t smem = (size_t)Lay::SMEM_WORDS * threads * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(dsb_band_bdf_solve_dense_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dsb_band_bdf_solve_dense_kernel<M>, threads, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        const int64_t want = (pa->nbatch + threads - 1) / threads;
+        const int64_t resident = (int64_t)sms * per_sm;
+        const unsigned grid = (unsigned)(want < resident ? want : resident);
+        // workspace: one column of WORDS doubles per resident lane
+        const size_t need = (size_t)Lay::WORDS * grid * threads * sizeof(double);
+        if (coop->ws_bytes < need) {
+            if (coop->ws_mem) cudaFree(coop->ws_mem);
+            coop->ws_mem = nullptr; coop->ws_bytes = 0;
+            e = cudaMalloc(&coop->ws_mem, need);
+            if (e != cudaSuccess) return e;
+            coop->ws_bytes = need;
+        }
+        e = cudaMemsetAsync(work_counter, 0, 32 * sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return e;
+        if (mid) cudaEventRecord(mid, stream);
+        dsb_band_bdf_solve_dense_kernel<M><<<grid, threads, smem, stream>>>(*pa, *bb, (double*)coop->ws_mem, work_counter);
+        *launches += 1;
+        return cudaGetLastError();
+    }
+};
+
 // lane kernels (one thread per instance): only instantiated for n <= 16
 template <class M, bool LANE> struct LaneLauncher {
     static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, int, cudaStream_t, cudaEvent_t, unsigned long long*, int*) {
@@ -159,6 +227,13 @@ template <class M> struct LaneLauncher<M, true> {
 cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method,
                                                  cudaStream_t stream, cudaEvent_t mid, unsigned long long* work_counter,
                                                  DsbCoopState* coop, const double* atol_host, int* launches) {
+    // exec_mode 3 / automatic: the banded lane kernel where the model qualifies (BDF, <= 64-bit pattern masks)
+    if (kBandCapable && method == DSB_METHOD_BDF && (coop->exec_mode == 3 || coop->exec_mode == 0)) {
+        const cudaError_t e = BandLauncher<InstModel, kBandCapable>::run(pa, bb, stream, mid, work_counter, coop, launches);
+        if (e != cudaErrorNotSupported || coop->exec_mode == 3) return e;
+    } else if (coop->exec_mode == 3) {
+        return cudaErrorNotSupported;
+    }
     const bool use_coop = coop->exec_mode == 2 || (coop->exec_mode == 0 && !kLaneCapable);
     if (use_coop) {
         if (method != DSB_METHOD_BDF) return cudaErrorNotSupported;   // cooperative path: BDF only

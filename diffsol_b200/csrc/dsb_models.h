@@ -271,6 +271,7 @@ struct ModelSpm {
     static constexpr int N = 42, NP = 1;
     static constexpr bool HAS_MASS = false;
     static constexpr bool COMPONENTWISE = true;
+    static constexpr int BAND_KL = 1, BAND_KU = 1;      // df/dy is tridiagonal (checked against the probed pattern at launch)
     DSB_HD static dsb_spm_row row(int i) {        // i in 2 .. 41
 #if defined(__CUDA_ARCH__)
         return i < 22 ? dsb_spm_neg_dev[i - 2] : dsb_spm_pos_dev[i - 22];

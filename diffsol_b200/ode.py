@@ -198,8 +198,9 @@ class BatchedSolver:
         self._stats = self._status = None
 
     def set_execution(self, mode):
-        """'auto' | 'lane' (one thread per instance, n <= 16) | 'block' (one thread block per instance)."""
-        capi.check(capi.lib().dsb_batch_set_execution(self._b, {"auto": 0, "lane": 1, "block": 2}[mode]))
+        """'auto' | 'lane' (one thread per instance, n <= 16) | 'block' (one thread block per instance) |
+        'band' (one thread per instance, banded models of 16 < n <= 64, state in global memory)."""
+        capi.check(capi.lib().dsb_batch_set_execution(self._b, {"auto": 0, "lane": 1, "block": 2, "band": 3}[mode]))
         return self
 
     def set_params(self):

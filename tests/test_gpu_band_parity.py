@@ -1,0 +1,76 @@
+"""GPU parity tests of the banded thread-per-instance BDF path (dsb_band_bdf_kernel.cuh: state in global memory,
+band LU per lane): the single-particle battery model of BASELINE config 5 against the oracle's DENSE LU, with and
+without Jacobian colouring, and against the block-per-instance path."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dsb():
+    import diffsol_b200
+    from diffsol_b200 import capi
+    capi.require_device()
+    return diffsol_b200
+
+
+def spm_currents(B):
+    from diffsol_b200 import sweeps
+    return (0.6 + 0.8 * sweeps.uniform(np.arange(B), 0)).reshape(-1, 1)
+
+
+@pytest.mark.parametrize("coloring", [False, True])
+def test_spm_band_bit_exact(dsb, oracle, coloring):
+    """Counters, status and states bit-identical to the oracle (dense partial-pivoting LU restated from nalgebra):
+    the band LU only skips operations whose multiplier or pivot-row entry is exactly zero."""
+    B = 700                      # more than one warp per block, ragged tail
+    current = spm_currents(B)
+    t_eval = np.arange(1, 13) * 300.0
+    solver = (dsb.OdeBuilder().rhs_implicit("spm").p(current).use_coloring(coloring).build().bdf()
+              .set_execution("band"))
+    ys = solver.solve_dense(t_eval)
+    desc = oracle.make_desc("spm", powmode=1, use_coloring=coloring)
+    ys_o, stats_o, status_o = oracle.batch_solve_dense(desc, current, t_eval)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o)
+    if coloring:
+        me = solver.statistics_array()[:, 12]
+        assert (solver.statistics_array()[:, 11] == 3 * me + 42).all()      # 3 colours + n probes
+
+
+def test_spm_band_tight_tolerances_and_free_running(dsb, oracle):
+    """Tighter tolerances (higher orders, more rescales) and the step()/interpolate() loop."""
+    B = 96
+    current = spm_currents(B)
+    t_eval = np.arange(1, 7) * 500.0
+    solver = dsb.OdeBuilder().rhs_implicit("spm").p(current).rtol(1e-9).atol(1e-10).build().bdf().set_execution("band")
+    ys = solver.solve_dense(t_eval)
+    desc = oracle.make_desc("spm", powmode=1, rtol=1e-9, atol=1e-10)
+    ys_o, stats_o, status_o = oracle.batch_solve_dense(desc, current, t_eval)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o)
+
+
+def test_spm_band_equals_block_per_instance(dsb):
+    B = 200
+    current = spm_currents(B)
+    t_eval = np.arange(1, 13) * 300.0
+    prob = dsb.OdeBuilder().rhs_implicit("spm").p(current).build()
+    a = prob.bdf().set_execution("band")
+    b = prob.bdf().set_execution("block")
+    ya, yb = a.solve_dense(t_eval), b.solve_dense(t_eval)
+    assert np.array_equal(ya, yb)
+    assert np.array_equal(a.statistics_array(), b.statistics_array())
+    # automatic selection picks the banded path for this model
+    c = prob.bdf()
+    assert np.array_equal(c.solve_dense(t_eval), ya)
+
+
+def test_band_execution_rejected_where_it_does_not_apply(dsb):
+    p = np.tile(np.array([[0.04, 1.0e4, 3.0e7]]), (4, 1))
+    prob = dsb.OdeBuilder().rhs_implicit("robertson_ode").p(p).build()
+    with pytest.raises(dsb.DiffsolB200Error):
+        prob.bdf().set_execution("band").solve_dense([1.0])

@@ -102,7 +102,7 @@ def test_spm_battery_sweep_bit_exact(dsb, oracle):
     B = 300
     current = (0.6 + 0.8 * sweeps.uniform(np.arange(B), 0)).reshape(-1, 1)
     t_eval = np.arange(1, 13) * 300.0
-    solver = dsb.OdeBuilder().rhs_implicit("spm").p(current).build().bdf()
+    solver = dsb.OdeBuilder().rhs_implicit("spm").p(current).build().bdf().set_execution("block")
     ys = solver.solve_dense(t_eval)
     desc = oracle.make_desc("spm", powmode=1)
     ys_o, stats_o, status_o = oracle.batch_solve_dense(desc, current, t_eval)
@@ -124,7 +124,8 @@ def test_coloured_jacobian_block_per_instance(dsb, oracle, model, B):
     else:
         p = heat_params(np.arange(B))
         t_eval = HEAT_T_EVAL[:20]
-    solver = dsb.OdeBuilder().rhs_implicit(model).p(p).rtol(1e-6).atol(1e-6).use_coloring(True).build().bdf()
+    solver = (dsb.OdeBuilder().rhs_implicit(model).p(p).rtol(1e-6).atol(1e-6).use_coloring(True).build().bdf()
+              .set_execution("block"))
     ys = solver.solve_dense(t_eval)
     desc = oracle.make_desc(model, powmode=1, rtol=1e-6, atol=1e-6, use_coloring=True)
     ys_o, stats_o, status_o = oracle.batch_solve_dense(desc, p, t_eval)
