@@ -40,9 +40,15 @@ struct BandBdfLayout {
     static constexpr int O_J = O_DL + N;                            // df/dy, band storage: (i, j) at j * LDJ + KU + i - j
     static constexpr int O_LU = O_J + LDJ * N;                      // factors, band storage: (i, j) at j * LDAB + KV + i - j
     static constexpr int O_PIV = O_LU + LDAB * N;                   // pivot offsets (row j interchanged with row j + piv[j])
-    static constexpr int WORDS = O_PIV + N;
-    static constexpr int THREADS = 512;
-    static constexpr int SMEM_WORDS = (DSB_NSTATS + 1) / 2 + 36;    // statistics + the 6 x 6 rescale matrix R U
+    static constexpr int O_RU = O_PIV + N;                          // rescale matrix R U when it does not fit shared memory
+    static constexpr int WORDS = O_RU + 25;
+#ifndef DSB_BAND_THREADS
+#define DSB_BAND_THREADS 768        // 24 warps at 80 registers: 1.16x over 16 warps at 128 (latency bound on global loads); 32 warps spill too much
+#endif
+    static constexpr int THREADS = DSB_BAND_THREADS;
+    static constexpr int MAXNREG = (65536 / THREADS) / 8 * 8;
+    static constexpr bool RU_IN_SMEM = THREADS <= 768;
+    static constexpr int SMEM_WORDS = (DSB_NSTATS + 1) / 2 + (RU_IN_SMEM ? 25 : 0);   // statistics (+ rows / columns 1..5 of R U)
     static_assert(N <= 64, "sparsity pattern rows are 64-bit masks");
     static_assert(KL >= 1 && KL <= 2 && KU >= 1 && KU <= 2, "register windows are sized for kl, ku <= 2");
 };
@@ -61,7 +67,7 @@ struct BandColourSeed {
 };
 
 template <class M>
-__global__ void __maxnreg__(128) dsb_band_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa,
+__global__ void __maxnreg__(BandBdfLayout<M>::MAXNREG) dsb_band_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa,
                                                                   const __grid_constant__ DsbBatchBuffers bb,
                                                                   double* __restrict__ ws,
                                                                   unsigned long long* __restrict__ work_counter) {
@@ -70,7 +76,7 @@ __global__ void __maxnreg__(128) dsb_band_bdf_solve_dense_kernel(const __grid_co
     extern __shared__ double dsb_lane_smem[];
     double* const sm = dsb_lane_smem + threadIdx.x;
 #define SMW(w) sm[(w) * Lay::THREADS]
-#define SRU(i, j) SMW((DSB_NSTATS + 1) / 2 + (i) * 6 + (j))
+#define SRU(i, j) (*(Lay::RU_IN_SMEM ? &SMW((DSB_NSTATS + 1) / 2 + ((i) - 1) * 5 + ((j) - 1)) : &g[(size_t)(Lay::O_RU + ((i) - 1) * 5 + ((j) - 1)) * LS]))
     const size_t LS = (size_t)gridDim.x * blockDim.x;
     double* const g = ws + ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
 #define G(w) g[(size_t)(w) * LS]
