@@ -1,5 +1,5 @@
 // dsb_band_bdf_kernel.cuh -- `problem.bdf::<LS>()?.solve_dense(t_eval)` for BANDED systems of medium size
-// (16 < n <= 64, identity mass, df/dy inside a declared band kl, ku <= 2): method-of-lines models such as the
+// (n > 16, identity mass, df/dy inside a declared band kl, ku <= 2): method-of-lines models such as the
 // single-particle battery model of BASELINE config 5 (two radial diffusion grids, tridiagonal).
 //
 // Execution model: still ONE LANE PER INSTANCE with the per-lane state machine and warp-level block scheduler of
@@ -49,7 +49,6 @@ struct BandBdfLayout {
     static constexpr int MAXNREG = (65536 / THREADS) / 8 * 8;
     static constexpr bool RU_IN_SMEM = THREADS <= 768;
     static constexpr int SMEM_WORDS = (DSB_NSTATS + 1) / 2 + (RU_IN_SMEM ? 25 : 0);   // statistics (+ rows / columns 1..5 of R U)
-    static_assert(N <= 64, "sparsity pattern rows are 64-bit masks");
     static_assert(KL >= 1 && KL <= 2 && KU >= 1 && KU <= 2, "register windows are sized for kl, ku <= 2");
 };
 
@@ -58,17 +57,25 @@ struct BandVec {
     const double* base; size_t ls;
     __device__ __forceinline__ double operator[](int k) const { return base[(size_t)k * ls]; }
 };
+// Per-column metadata of df/dy (device array, the same for every instance: jacobian/mod.rs:32): bits 0-15 the colour of
+// the column, bits 16.. the sparsity pattern of the column inside the band (bit 16 + KU + i - j <=> entry (i, j)).
+struct DsbBandMeta {
+    const double* atol;        // [n]
+    const int32_t* colmeta;    // [n]
+};
 // seed of one colour: 1 in every column of the colour that has a non-zero
 struct BandColourSeed {
-    const DsbProblemArgs* pa; int c;
+    const int32_t* colmeta; int c;
     __device__ __forceinline__ double operator[](int k) const {
-        return (pa->color_of_col[k] == c && pa->nz_rows_of_col[k] != 0) ? 1.0 : 0.0;
+        const int32_t m = colmeta[k];
+        return ((m & 0xffff) == c && (m >> 16) != 0) ? 1.0 : 0.0;
     }
 };
 
 template <class M>
 __global__ void __maxnreg__(BandBdfLayout<M>::MAXNREG) dsb_band_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa,
                                                                   const __grid_constant__ DsbBatchBuffers bb,
+                                                                  const __grid_constant__ DsbBandMeta meta,
                                                                   double* __restrict__ ws,
                                                                   unsigned long long* __restrict__ work_counter) {
     typedef BandBdfLayout<M> Lay;
@@ -152,7 +159,7 @@ __global__ void __maxnreg__(BandBdfLayout<M>::MAXNREG) dsb_band_bdf_solve_dense_
         double acc = 0.0;
 #pragma unroll 4
         for (int i = 0; i < N; ++i) {
-            const double term = DSB_DIV(G(ox + i), dsb_abs(G(oref + i)) * pa.rtol + pa.atol[i]);
+            const double term = DSB_DIV(G(ox + i), dsb_abs(G(oref + i)) * pa.rtol + meta.atol[i]);
             acc += term * term;
         }
         return DSB_DIV(acc, (double)N);
@@ -357,7 +364,7 @@ __global__ void __maxnreg__(BandBdfLayout<M>::MAXNREG) dsb_band_bdf_solve_dense_
                     const bool one_colour_per_column = pa.ncolors == N;
 #pragma unroll 1
                     for (int cc = 0; cc < pa.ncolors; ++cc) {
-                        const BandColourSeed seed{&pa, cc};
+                        const BandColourSeed seed{meta.colmeta, cc};
                         st.v[DSB_STAT_RHS_JAC_MULS] += 1;
                         // rows outside the band of the colour's only column hold exact zeros and are not evaluated
                         const int i0 = one_colour_per_column ? (cc - KU < 0 ? 0 : cc - KU) : 0;
@@ -368,8 +375,10 @@ __global__ void __maxnreg__(BandBdfLayout<M>::MAXNREG) dsb_band_bdf_solve_dense_
 #pragma unroll
                             for (int d = -KL; d <= KU; ++d) {               // column j = i + d
                                 const int j = i + d;
-                                if (j >= 0 && j < N && pa.color_of_col[j] == cc && ((pa.nz_rows_of_col[j] >> i) & 1ull))
-                                    GJ(j, KU - d) = val;
+                                if (j >= 0 && j < N) {
+                                    const int32_t m = meta.colmeta[j];
+                                    if ((m & 0xffff) == cc && ((m >> (16 + KU - d)) & 1)) GJ(j, KU - d) = val;
+                                }
                             }
                         }
                     }
@@ -616,7 +625,7 @@ __global__ void __maxnreg__(BandBdfLayout<M>::MAXNREG) dsb_band_bdf_solve_dense_
                     const double dl = GDL(i);
                     GYC(i) = GYC(i) - dl;
                     // Newton norm weights use the PREDICTOR (line_search.rs:67, convergence.rs:64-66)
-                    const double term = DSB_DIV(dl, dsb_abs(GYP(i)) * pa.rtol + pa.atol[i]);
+                    const double term = DSB_DIV(dl, dsb_abs(GYP(i)) * pa.rtol + meta.atol[i]);
                     acc += term * term;
                 }
                 const double norm = dsb_sqrt(DSB_DIV(acc, (double)N));
@@ -652,7 +661,7 @@ __global__ void __maxnreg__(BandBdfLayout<M>::MAXNREG) dsb_band_bdf_solve_dense_
 #pragma unroll 4
                     for (int i = 0; i < N; ++i) {
                         const double d = GYC(i) - GYP(i);
-                        const double term = DSB_DIV(d, dsb_abs(GY(i)) * pa.rtol + pa.atol[i]);
+                        const double term = DSB_DIV(d, dsb_abs(GY(i)) * pa.rtol + meta.atol[i]);
                         acc += term * term;
                     }
                     const double err = DSB_DIV(acc, (double)N) * pa.tab.error_const2[ord - 1];

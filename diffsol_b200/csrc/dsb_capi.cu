@@ -201,11 +201,12 @@ int fill_problem_args(const dsb_problem& pr, int64_t B, int nt, DsbProblemArgs* 
     if (pr.use_coloring) {
         ColoringOf f{&pr, pa, probes, color_full, nz_full};
         if (!dsb_dispatch_model(pr.model, f)) return DSB_BAD_ARG;
-    } else if (pr.n <= DSB_MAX_STATES) {
+    } else {
         // dense assembly (op/nonlinear_op.rs:211-220) expressed as one colour per column with a full pattern, so
-        // that the lane kernels carry a single assembly loop (dsb_lane.cuh:lane_jacobian_to)
+        // that the lane kernels carry a single assembly loop (dsb_lane.cuh:lane_jacobian_to; the banded kernel
+        // gets the same tables for any n as a device array, dsb_inst.cu:BandLauncher)
         pa->ncolors = pr.n;
-        for (int j = 0; j < pr.n; ++j) {
+        for (int j = 0; j < pr.n && j < DSB_MAX_STATES; ++j) {
             pa->color_of_col[j] = j;
             pa->nz_rows_of_col[j] = pr.n >= 64 ? ~0ull : ((1ull << pr.n) - 1ull);
         }
@@ -217,6 +218,7 @@ const dsb_launch_fn g_launch_table[DSB_MODEL_COUNT] = {
     dsb_launch_model_0, dsb_launch_model_1, dsb_launch_model_2, dsb_launch_model_3,
     dsb_launch_model_4, dsb_launch_model_5, dsb_launch_model_6, dsb_launch_model_7,
     dsb_launch_model_8, dsb_launch_model_9, dsb_launch_model_10, dsb_launch_model_11,
+    dsb_launch_model_12,
 };
 
 // instance-major <-> batch-major re-layout on the device (the host-facing layouts follow the

@@ -97,40 +97,77 @@ static cudaError_t launch_coop_bdf(const DsbProblemArgs* pa, const DsbBatchBuffe
 }
 
 // banded lane kernel (one thread per instance, state in global memory): component-wise models without a mass
-// matrix that declare a band, 16 < n <= 64
+// matrix that declare a band, n > 16
 template <class M, class = void> struct dsb_declares_band : std::false_type {};
 template <class M> struct dsb_declares_band<M, std::void_t<decltype(M::BAND_KL)>> : std::true_type {};
 constexpr bool kBandCapable = dsb_declares_band<InstModel>::value && dsb_is_componentwise<InstModel>::value &&
-                              !InstModel::HAS_MASS && InstModel::N > 16 && InstModel::N <= 64;
+                              !InstModel::HAS_MASS && InstModel::N > 16;
 
 template <class M, bool BAND> struct BandLauncher {
-    static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, cudaStream_t, cudaEvent_t, unsigned long long*, DsbCoopState*, int*) {
+    static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, cudaStream_t, cudaEvent_t, unsigned long long*, DsbCoopState*,
+                           const double*, int*) {
         return cudaErrorNotSupported;
     }
 };
 template <class M> struct BandLauncher<M, true> {
     static cudaError_t run(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, cudaStream_t stream, cudaEvent_t mid,
-                           unsigned long long* work_counter, DsbCoopState* coop, int* launches) {
+                           unsigned long long* work_counter, DsbCoopState* coop, const double* atol_host, int* launches) {
         typedef BandBdfLayout<M> Lay;
         constexpr int N = M::N;
-        // the declared band must cover the sparsity pattern (NaN probe, jacobian/mod.rs:16-48)
+        // sparsity pattern by NaN probe (jacobian/mod.rs:16-48): the declared band must cover it.  Per column: colour
+        // (greedy colouring computed by the caller, or one colour per column for the dense assembly, which stores
+        // every in-band entry) and the pattern inside the band.
+        std::vector<int32_t> colmeta(N, 0);
         {
             double p[M::NP > 0 ? M::NP : 1];
             for (int j = 0; j < M::NP; ++j) p[j] = 1.0;
             std::vector<double> y0(N), v(N, 0.0), col(N, 0.0);
             M::init(p, pa->t0, y0.data());
+            if (pa->use_coloring && !coop->color_host) return cudaErrorInvalidValue;
             for (int j = 0; j < N; ++j) {
                 v[j] = std::numeric_limits<double>::quiet_NaN();
                 M::jac_mul(y0.data(), p, pa->t0, v.data(), col.data());
-                for (int i = 0; i < N; ++i)
-                    if (std::isnan(col[i]) && (i - j > Lay::KL || j - i > Lay::KU)) return cudaErrorNotSupported;
+                int32_t mask = 0;
+                for (int i = 0; i < N; ++i) {
+                    if (!std::isnan(col[i])) continue;
+                    if (i - j > Lay::KL || j - i > Lay::KU) return cudaErrorNotSupported;
+                    mask |= 1 << (Lay::KU + i - j);
+                }
                 for (int i = 0; i < N; ++i) col[i] = 0.0;
                 v[j] = 0.0;
+                if (pa->use_coloring) {
+                    const int32_t colour = coop->color_host[j] < 0 ? 0xffff : coop->color_host[j];
+                    colmeta[j] = colour | (mask << 16);
+                } else {
+                    colmeta[j] = j | (((1 << Lay::LDJ) - 1) << 16);
+                }
             }
         }
+        cudaError_t e;
+        if (coop->atol_n < N) {
+            if (coop->atol_dev) cudaFree(coop->atol_dev);
+            coop->atol_dev = nullptr; coop->atol_n = 0;
+            e = cudaMalloc((void**)&coop->atol_dev, (size_t)N * sizeof(double));
+            if (e != cudaSuccess) return e;
+            coop->atol_n = N;
+        }
+        if (coop->color_bytes < (size_t)N * sizeof(int32_t)) {
+            if (coop->color_dev) cudaFree(coop->color_dev);
+            coop->color_dev = nullptr; coop->color_bytes = 0;
+            e = cudaMalloc(&coop->color_dev, (size_t)N * sizeof(int32_t));
+            if (e != cudaSuccess) return e;
+            coop->color_bytes = (size_t)N * sizeof(int32_t);
+        }
+        e = cudaMemcpyAsync(coop->atol_dev, atol_host, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(coop->color_dev, colmeta.data(), (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(stream);              // the host vectors die with this frame
+        if (e != cudaSuccess) return e;
+        const DsbBandMeta meta{coop->atol_dev, (const int32_t*)coop->color_dev};
         const int threads = Lay::THREADS;
         const size_t smem = (size_t)Lay::SMEM_WORDS * threads * sizeof(double);
-        cudaError_t e = cudaFuncSetAttribute(dsb_band_bdf_solve_dense_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(dsb_band_bdf_solve_dense_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
@@ -153,7 +190,7 @@ template <class M> struct BandLauncher<M, true> {
         e = cudaMemsetAsync(work_counter, 0, 32 * sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return e;
         if (mid) cudaEventRecord(mid, stream);
-        dsb_band_bdf_solve_dense_kernel<M><<<grid, threads, smem, stream>>>(*pa, *bb, (double*)coop->ws_mem, work_counter);
+        dsb_band_bdf_solve_dense_kernel<M><<<grid, threads, smem, stream>>>(*pa, *bb, meta, (double*)coop->ws_mem, work_counter);
         *launches += 1;
         return cudaGetLastError();
     }
@@ -229,7 +266,7 @@ cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const
                                                  DsbCoopState* coop, const double* atol_host, int* launches) {
     // exec_mode 3 / automatic: the banded lane kernel where the model qualifies (BDF, <= 64-bit pattern masks)
     if (kBandCapable && method == DSB_METHOD_BDF && (coop->exec_mode == 3 || coop->exec_mode == 0)) {
-        const cudaError_t e = BandLauncher<InstModel, kBandCapable>::run(pa, bb, stream, mid, work_counter, coop, launches);
+        const cudaError_t e = BandLauncher<InstModel, kBandCapable>::run(pa, bb, stream, mid, work_counter, coop, atol_host, launches);
         if (e != cudaErrorNotSupported || coop->exec_mode == 3) return e;
     } else if (coop->exec_mode == 3) {
         return cudaErrorNotSupported;

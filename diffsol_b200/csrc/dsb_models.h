@@ -25,6 +25,7 @@ enum dsb_model_id {
     DSB_MODEL_HEAT1D_DAE_256 = 9,       // n=256 np=3  1-D heat equation, boundary rows algebraic (BASELINE.json config 4)
     DSB_MODEL_HEAT1D_DAE_32 = 10,       // n=32  np=3  the same on a coarse grid (test size)
     DSB_MODEL_SPM = 11,                 // n=42  np=1  single-particle battery model, book/src/primer/src/spm.ds (BASELINE config 5)
+    DSB_MODEL_SPM99 = 12,               // n=200 np=1  the same model on 99 radial cells per particle (not in the reference)
     DSB_MODEL_COUNT
 };
 
@@ -263,29 +264,69 @@ struct ModelHeat1dDae {
 struct dsb_spm_row { double sub, diag, sup; };
 static const dsb_spm_row dsb_spm_neg_host[20] = { DSB_SPM_NEG_ROWS };
 static const dsb_spm_row dsb_spm_pos_host[20] = { DSB_SPM_POS_ROWS };
+static const dsb_spm_row dsb_spm99_neg_host[99] = { DSB_SPM99_NEG_ROWS };
+static const dsb_spm_row dsb_spm99_pos_host[99] = { DSB_SPM99_POS_ROWS };
 #if defined(__CUDACC__)
 static __device__ const dsb_spm_row dsb_spm_neg_dev[20] = { DSB_SPM_NEG_ROWS };
 static __device__ const dsb_spm_row dsb_spm_pos_dev[20] = { DSB_SPM_POS_ROWS };
+static __device__ const dsb_spm_row dsb_spm99_neg_dev[99] = { DSB_SPM99_NEG_ROWS };
+static __device__ const dsb_spm_row dsb_spm99_pos_dev[99] = { DSB_SPM99_POS_ROWS };
 #endif
-struct ModelSpm {
-    static constexpr int N = 42, NP = 1;
+// the discretisation tables: 20 cells per particle (the reference's model text) or 99 (finite-volume refinement
+// by the same formulas, tools/gen_spm_tables.py; not in the reference: BASELINE config 5 asks for n ~ 200)
+struct SpmTables20 {
+    static constexpr int NR = 20;
+    DSB_HD static double neg_flux() { return DSB_SPM_NEG_FLUX; }
+    DSB_HD static double pos_flux() { return DSB_SPM_POS_FLUX; }
+    DSB_HD static dsb_spm_row neg(int k) {
+#if defined(__CUDA_ARCH__)
+        return dsb_spm_neg_dev[k];
+#else
+        return dsb_spm_neg_host[k];
+#endif
+    }
+    DSB_HD static dsb_spm_row pos(int k) {
+#if defined(__CUDA_ARCH__)
+        return dsb_spm_pos_dev[k];
+#else
+        return dsb_spm_pos_host[k];
+#endif
+    }
+};
+struct SpmTables99 {
+    static constexpr int NR = 99;
+    DSB_HD static double neg_flux() { return DSB_SPM99_NEG_FLUX; }
+    DSB_HD static double pos_flux() { return DSB_SPM99_POS_FLUX; }
+    DSB_HD static dsb_spm_row neg(int k) {
+#if defined(__CUDA_ARCH__)
+        return dsb_spm99_neg_dev[k];
+#else
+        return dsb_spm99_neg_host[k];
+#endif
+    }
+    DSB_HD static dsb_spm_row pos(int k) {
+#if defined(__CUDA_ARCH__)
+        return dsb_spm99_pos_dev[k];
+#else
+        return dsb_spm99_pos_host[k];
+#endif
+    }
+};
+template <class Tab>
+struct ModelSpmT {
+    static constexpr int NR = Tab::NR;
+    static constexpr int N = 2 + 2 * NR, NP = 1;
     static constexpr bool HAS_MASS = false;
     static constexpr bool COMPONENTWISE = true;
     static constexpr int BAND_KL = 1, BAND_KU = 1;      // df/dy is tridiagonal (checked against the probed pattern at launch)
-    DSB_HD static dsb_spm_row row(int i) {        // i in 2 .. 41
-#if defined(__CUDA_ARCH__)
-        return i < 22 ? dsb_spm_neg_dev[i - 2] : dsb_spm_pos_dev[i - 22];
-#else
-        return i < 22 ? dsb_spm_neg_host[i - 2] : dsb_spm_pos_host[i - 22];
-#endif
-    }
     template <class X>
-    DSB_HD static double diffusion_i(int i, const X& x) {
-        const dsb_spm_row c = row(i);
-        const int k = (i < 22) ? i - 2 : i - 22;
+    DSB_HD static double diffusion_i(int i, const X& x) {        // i in 2 .. N - 1
+        const bool neg = i < 2 + NR;
+        const int k = neg ? i - 2 : i - 2 - NR;
+        const dsb_spm_row c = neg ? Tab::neg(k) : Tab::pos(k);
         double acc = 0.0;
-        if (k < 19) acc = c.sup * x[i + 1];
-        acc = (k < 19) ? (c.diag * x[i] + acc) : (c.diag * x[i]);
+        if (k < NR - 1) acc = c.sup * x[i + 1];
+        acc = (k < NR - 1) ? (c.diag * x[i] + acc) : (c.diag * x[i]);
         if (k > 0) acc = c.sub * x[i - 1] + acc;
         return acc;
     }
@@ -293,8 +334,8 @@ struct ModelSpm {
     DSB_HD static double rhs_i(int i, const X& x, const double* p, double) {
         if (i == 0) return 0.0002777777777777778 * p[0];
         if (i == 1) return 0.0002777777777777778 * dsb_abs(p[0]);
-        const double flux = (i == 21) ? DSB_SPM_NEG_FLUX * (-520607810.21082705 * p[0])
-                          : (i == 41) ? DSB_SPM_POS_FLUX * (243644455.17866704 * p[0]) : 0.0;
+        const double flux = (i == 1 + NR) ? Tab::neg_flux() * (-520607810.21082705 * p[0])
+                          : (i == 1 + 2 * NR) ? Tab::pos_flux() * (243644455.17866704 * p[0]) : 0.0;
         return diffusion_i(i, x) + flux;
     }
     template <class X, class V>
@@ -305,13 +346,15 @@ struct ModelSpm {
     template <class X>
     DSB_HD static double mass_i(int i, const X& x, const double*, double, double beta, double yi) { return x[i] + beta * yi; }
     DSB_HD static double init_i(int i, const double*, double) {
-        return i < 2 ? 0.0 : (i < 22 ? 0.8000000000000016 : 0.6000000000000001);
+        return i < 2 ? 0.0 : (i < 2 + NR ? 0.8000000000000016 : 0.6000000000000001);
     }
     DSB_HD static void rhs(const double* x, const double* p, double t, double* y) { for (int i = 0; i < N; ++i) y[i] = rhs_i(i, x, p, t); }
     DSB_HD static void jac_mul(const double* x, const double* p, double t, const double* v, double* y) { for (int i = 0; i < N; ++i) y[i] = jac_mul_i(i, x, p, t, v); }
     DSB_HD static void mass(const double* x, const double* p, double t, double beta, double* y) { for (int i = 0; i < N; ++i) y[i] = mass_i(i, x, p, t, beta, y[i]); }
     DSB_HD static void init(const double* p, double t, double* y) { for (int i = 0; i < N; ++i) y[i] = init_i(i, p, t); }
 };
+typedef ModelSpmT<SpmTables20> ModelSpm;
+typedef ModelSpmT<SpmTables99> ModelSpm99;
 
 // id -> functor type
 template <int ID> struct dsb_model_by_id;
@@ -327,6 +370,7 @@ template <> struct dsb_model_by_id<DSB_MODEL_VAN_DER_POL_SCALED> { typedef Model
 template <> struct dsb_model_by_id<DSB_MODEL_HEAT1D_DAE_256> { typedef ModelHeat1dDae<256> type; };
 template <> struct dsb_model_by_id<DSB_MODEL_HEAT1D_DAE_32> { typedef ModelHeat1dDae<32> type; };
 template <> struct dsb_model_by_id<DSB_MODEL_SPM> { typedef ModelSpm type; };
+template <> struct dsb_model_by_id<DSB_MODEL_SPM99> { typedef ModelSpm99 type; };
 
 // Compile-time dispatch over the registry: calls f.template operator()<Model>() for `id`.
 template <class F>
@@ -344,6 +388,7 @@ inline bool dsb_dispatch_model(int id, F&& f) {
         case DSB_MODEL_HEAT1D_DAE_256: f.template operator()<ModelHeat1dDae<256>>(); return true;
         case DSB_MODEL_HEAT1D_DAE_32: f.template operator()<ModelHeat1dDae<32>>(); return true;
         case DSB_MODEL_SPM: f.template operator()<ModelSpm>(); return true;
+        case DSB_MODEL_SPM99: f.template operator()<ModelSpm99>(); return true;
         default: return false;
     }
 }

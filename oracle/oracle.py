@@ -43,6 +43,7 @@ MODELS = {
     "heat1d_dae_256": 9,
     "heat1d_dae_32": 10,
     "spm": 11,
+    "spm99": 12,
 }
 
 

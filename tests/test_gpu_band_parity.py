@@ -69,6 +69,35 @@ def test_spm_band_equals_block_per_instance(dsb):
     assert np.array_equal(c.solve_dense(t_eval), ya)
 
 
+@pytest.mark.parametrize("coloring", [False, True])
+def test_spm99_band_bit_exact(dsb, oracle, coloring):
+    """The same model on 99 radial cells per particle (n = 200, BASELINE config 5's size): colours and pattern
+    travel in a device array, tolerances too."""
+    B = 100
+    current = spm_currents(B)
+    t_eval = np.arange(1, 7) * 600.0
+    solver = (dsb.OdeBuilder().rhs_implicit("spm99").p(current).use_coloring(coloring).build().bdf()
+              .set_execution("band"))
+    ys = solver.solve_dense(t_eval)
+    desc = oracle.make_desc("spm99", powmode=1, use_coloring=coloring)
+    ys_o, stats_o, status_o = oracle.batch_solve_dense(desc, current, t_eval)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o)
+    assert ys.shape == (B, 6, 200)
+
+
+def test_spm99_band_equals_block_per_instance(dsb):
+    B = 24
+    current = spm_currents(B)
+    t_eval = np.arange(1, 4) * 600.0
+    prob = dsb.OdeBuilder().rhs_implicit("spm99").p(current).build()
+    a = prob.bdf().set_execution("band")
+    b = prob.bdf().set_execution("block")
+    assert np.array_equal(a.solve_dense(t_eval), b.solve_dense(t_eval))
+    assert np.array_equal(a.statistics_array(), b.statistics_array())
+
+
 def test_band_execution_rejected_where_it_does_not_apply(dsb):
     p = np.tile(np.array([[0.04, 1.0e4, 3.0e7]]), (4, 1))
     prob = dsb.OdeBuilder().rhs_implicit("robertson_ode").p(p).build()

@@ -25,12 +25,12 @@ if which.startswith("heat"):
     t_eval = np.arange(1, 101) / 100.0 * 0.99
     prob = ds.OdeBuilder().rhs_implicit("heat1d_dae_%d" % n).p(p).rtol(1e-6).atol(1e-6).build()
     solver, npar, mass_words = prob.bdf(), 3, n * n
-elif which == "spm":
-    n, npar, mass_words = 42, 1, 0
+elif which in ("spm", "spm99"):
+    n, npar, mass_words = (42 if which == "spm" else 200), 1, 0
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 250000
     p = (0.6 + 0.8 * sweeps.uniform(np.arange(B), 0)).reshape(-1, 1)
     t_eval = np.arange(1, 13) * 300.0
-    prob = ds.OdeBuilder().rhs_implicit("spm").p(p).build()
+    prob = ds.OdeBuilder().rhs_implicit(which).p(p).use_coloring(True).build()
     solver = prob.bdf()
 elif which == "vdp":
     n, npar, mass_words = 2, 2, 0
