@@ -62,8 +62,17 @@ attempts = int(st[:, 6].sum() + st[:, 7].sum() + st[:, 9].sum())
 nt = len(t_eval)
 alg = (nli * (8 * (n * n + 4 * n + npar) + 4 * n) + setups * (8 * (2 * n * n + mass_words) + 4 * n)
        + me * 8 * (n * n + n + npar) + attempts * 8 * 19 * n + B * nt * 8 * n)
+# banded path (dsb_band_bdf_kernel.cuh): the same formula with the band storage it really reads (kl = ku = 1):
+# factors (2kl+ku+1) n + n pivots, Jacobian (kl+ku+1) n
+band = None
+if which in ("spm", "spm99"):
+    ldab, ldj = 4, 3
+    band = (nli * 8 * (ldab * n + n + 4 * n + npar) + setups * 8 * (ldj * n + ldab * n + n)
+            + me * 8 * (ldj * n + n + npar) + attempts * 8 * 19 * n + B * nt * 8 * n)
 print(json.dumps({"config": which, "n": n, "batch": B, "kernel_ms": kms, "e2e_ms": min(t for t, _ in times[1:]) * 1e3,
                   "instances_per_s": B / kms * 1e3, "newton_iters_per_s": nli / kms * 1e3,
                   "steps_mean": float(st[:, 6].mean()), "nli_mean": float(st[:, 8].mean()), "setups_mean": float(st[:, 0].mean()),
                   "failed": int((status != 0).sum()), "algorithmic_GB": alg / 1e9,
-                  "achieved_GBps": alg / kms / 1e6, "frac_hbm": alg / kms / 1e6 / peak}))
+                  "achieved_GBps": alg / kms / 1e6, "frac_hbm": alg / kms / 1e6 / peak,
+                  "band_algorithmic_GB": None if band is None else band / 1e9,
+                  "band_frac_hbm": None if band is None else band / kms / 1e6 / peak}))
