@@ -408,3 +408,112 @@ static __device__ __noinline__ bool warp_band_solve(const double* ab, int n, int
     }
     return true;
 }
+
+// ---- the same band routines for ONE thread, kl / ku known at compile time --------------------------------------------
+// With a narrow band (PDE stencils: kl = ku = 1) a warp has nothing to share out: 2 or 3 of 32 lanes work, and every
+// column costs two warp synchronisations.  One thread walking the band with its running entries in a REGISTER WINDOW
+// (kl + 1 values in the forward pass, kl + ku + 1 in the backward pass) and the pivots in SHARED memory is ~10x
+// faster per substitution at n = 256: the loads of band entries and pivots do not depend on the recurrence and run
+// ahead of it.  Same element-wise arithmetic and order as warp_band_factor / warp_band_solve above (and hence as
+// nalgebra's dense LU).  piv[j] = row interchanged with row j.
+template <int KL, int KU>
+static __device__ __noinline__ int thread_band_factor(double* ab, int n, int* piv) {
+    constexpr int KV = KL + KU;
+    int first_bad = 0;
+    int ju = 0;
+    for (int j = 0; j < n; ++j) {
+        const int km = (KL < n - 1 - j) ? KL : (n - 1 - j);
+        double colv[KL + 1];
+#pragma unroll
+        for (int d = 0; d <= KL; ++d) colv[d] = (d <= km) ? ab[j * 32 + KV + d] : 0.0;
+        int jp = 0;
+        double best = -1.0;
+#pragma unroll
+        for (int d = 0; d <= KL; ++d) {
+            const double av = dsb_abs(colv[d]);
+            if (d <= km && av == av && av > best) { best = av; jp = d; }
+        }
+        if (colv[0] != colv[0]) jp = 0;
+        double diag = colv[0];
+#pragma unroll
+        for (int d = 1; d <= KL; ++d) if (jp == d) diag = colv[d];
+        if (diag == 0.0) { piv[j] = j; if (first_bad == 0) first_bad = j + 1; continue; }
+        piv[j] = j + jp;
+        { const int cand = (j + KU + jp < n - 1) ? (j + KU + jp) : (n - 1); if (cand > ju) ju = cand; }
+        if (jp != 0) {
+#pragma unroll
+            for (int q = 0; q <= KV; ++q) {
+                const int c = j + q;
+                if (c <= ju) {
+                    const double a = ab[c * 32 + KV - q], b = ab[c * 32 + KV - q + jp];
+                    ab[c * 32 + KV - q] = b; ab[c * 32 + KV - q + jp] = a;
+                }
+            }
+#pragma unroll
+            for (int d = 1; d <= KL; ++d) if (jp == d) { const double a = colv[0]; colv[0] = colv[d]; colv[d] = a; }
+        }
+        if (km > 0) {
+            const double inv_diag = 1.0 / colv[0];
+#pragma unroll
+            for (int d = 1; d <= KL; ++d) if (d <= km) { colv[d] *= inv_diag; ab[j * 32 + KV + d] = colv[d]; }
+#pragma unroll
+            for (int q = 1; q <= KV; ++q) {
+                const int c = j + q;
+                if (c <= ju) {
+                    const double mpk = -ab[c * 32 + KV - q];
+#pragma unroll
+                    for (int d = 1; d <= KL; ++d)
+                        if (d <= km) ab[c * 32 + KV - q + d] = mpk * colv[d] + ab[c * 32 + KV - q + d];
+                }
+            }
+        }
+    }
+    return first_bad;
+}
+
+template <int KL, int KU>
+static __device__ __noinline__ bool thread_band_solve(const double* ab, int n, const int* piv, double* b) {
+    constexpr int KV = KL + KU;
+    {
+        double w[KL + 1];
+#pragma unroll
+        for (int d = 0; d <= KL; ++d) w[d] = (d < n) ? b[d] : 0.0;
+#pragma unroll 4
+        for (int j = 0; j + 1 < n; ++j) {
+            const int jp = piv[j] - j;
+            if (jp != 0) {
+                const double a = w[0];
+#pragma unroll
+                for (int d = 1; d <= KL; ++d) if (jp == d) { w[0] = w[d]; w[d] = a; }
+            }
+            const double bj = w[0];
+            b[j] = bj;
+            const double nbj = -bj;
+            const int lm = (KL < n - 1 - j) ? KL : (n - 1 - j);
+#pragma unroll
+            for (int d = 1; d <= KL; ++d) if (d <= lm) w[d] = nbj * ab[j * 32 + KV + d] + w[d];
+#pragma unroll
+            for (int d = 0; d < KL; ++d) w[d] = w[d + 1];
+            w[KL] = (j + 1 + KL < n) ? b[j + 1 + KL] : 0.0;
+        }
+        b[n - 1] = w[0];
+    }
+    double w[KV + 1];
+#pragma unroll
+    for (int e = 0; e <= KV; ++e) w[e] = (n - 1 - e >= 0) ? b[n - 1 - e] : 0.0;
+#pragma unroll 4
+    for (int i = n - 1; i >= 0; --i) {
+        const double diag = ab[i * 32 + KV];
+        if (diag == 0.0) return false;
+        const double coeff = w[0] / diag;
+        b[i] = coeff;
+        const double ncoeff = -coeff;
+#pragma unroll
+        for (int e = 1; e <= KV; ++e) if (i - e >= 0) w[e] = ncoeff * ab[i * 32 + KV - e] + w[e];
+#pragma unroll
+        for (int e = 0; e < KV; ++e) w[e] = w[e + 1];
+        w[KV] = (i - 1 - KV >= 0) ? b[i - 1 - KV] : 0.0;
+    }
+    return true;
+}
+

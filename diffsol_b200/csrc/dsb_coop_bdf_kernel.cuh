@@ -84,7 +84,7 @@ struct CoopBdfLayout {
     static constexpr int N = M::N;
     static constexpr int NVEC = DSB_NDIFF + 9;          // D[8], y, yp, ycur, psi, dlt, tmp, scr, atol, dy
     static constexpr int THREADS = (N + 31) / 32 * 32 > 128 ? 128 : (N + 31) / 32 * 32;
-    static size_t smem_bytes() { return (size_t)NVEC * N * sizeof(double) + coop_lu_smem_bytes_host(N) + 64; }
+    static size_t smem_bytes() { return (size_t)NVEC * N * sizeof(double) + coop_lu_smem_bytes_host(N) + 64 + (size_t)N * sizeof(int); }
 };
 
 // Resident blocks the register allocation is asked to allow: DSB_COOP_TARGET_THREADS lanes per SM (the kernel is
@@ -114,6 +114,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
     double* const atolv = scr + N;
     double* const dys = atolv + N;                       // state.dy (initialisation only)
     const CoopScratch sc = coop_carve(dys + N, N);
+    int* const piv_s = sc.bcast + 4;                     // pivots of the shared-memory band factors (tridiagonal fast path)
     __shared__ int s_band[2];                            // kl, ku of the current J / M
     __shared__ int s_banded;                             // 1: the current factors are the shared-memory band factors
     __shared__ double s_red;                             // broadcast of a sequential reduction
@@ -162,7 +163,8 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
     auto lu_solve = [&](double* b) -> bool {
         if (s_banded) {
             __syncthreads();
-            if (tid < 32) { const bool ok = warp_band_solve(sc.panel, N, s_band[0], s_band[1], pivg, b); if (tid == 0) sc.bcast[2] = ok ? 1 : 0; }
+            if (s_band[0] == 1 && s_band[1] == 1) { if (tid == 0) sc.bcast[2] = thread_band_solve<1, 1>(sc.panel, N, piv_s, b) ? 1 : 0; }
+            else if (tid < 32) { const bool ok = warp_band_solve(sc.panel, N, s_band[0], s_band[1], pivg, b); if (tid == 0) sc.bcast[2] = ok ? 1 : 0; }
             __syncthreads();
             return sc.bcast[2] != 0;
         }
@@ -418,7 +420,8 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                     ab[e] = v;
                 }
                 __syncthreads();
-                if (tid < 32) warp_band_factor(ab, N, kl, ku, pivg);
+                if (kl == 1 && ku == 1) { if (tid == 0) thread_band_factor<1, 1>(ab, N, piv_s); }
+                else if (tid < 32) warp_band_factor(ab, N, kl, ku, pivg);
                 if (tid == 0) s_banded = 1;
                 __syncthreads();
             } else {

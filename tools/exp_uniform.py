@@ -16,7 +16,20 @@ from diffsol_b200 import capi, sweeps  # noqa: E402
 capi.require_device()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 base = sweeps.robertson_sweep(np.arange(B))
-cases = {"sweep": base, "warp_uniform": base[(np.arange(B) // 32) * 32], "block_uniform": base[(np.arange(B) // 128) * 128],
+def morton_order(p, bits=7):
+    """instances ordered along a Z-curve through (log k1, log k2, log k3): neighbours in the batch are neighbours in
+    parameter space"""
+    q = np.log(p)
+    q = (q - q.min(axis=0)) / (q.max(axis=0) - q.min(axis=0) + 1e-300)
+    q = np.minimum((q * (1 << bits)).astype(np.uint64), (1 << bits) - 1)
+    code = np.zeros(len(p), dtype=np.uint64)
+    for b in range(bits):
+        for j in range(p.shape[1]):
+            code |= ((q[:, j] >> np.uint64(b)) & np.uint64(1)) << np.uint64(b * p.shape[1] + j)
+    return np.argsort(code, kind="stable")
+
+
+cases = {"sweep": base, "sorted_by_k1": base[np.argsort(base[:, 0])], "morton_sorted": base[morton_order(base)], "warp_uniform": base[(np.arange(B) // 32) * 32], "block_uniform": base[(np.arange(B) // 128) * 128],
          "all_identical": np.repeat(base[:1], B, axis=0)}
 for name, p in cases.items():
     prob = ds.OdeBuilder().rhs_implicit("robertson_ode").p(p).rtol(1e-4).atol([1e-8, 1e-14, 1e-6]).build()
