@@ -78,6 +78,9 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
     double* const sm = dsb_lane_smem + threadIdx.x;
 #define SM(w) sm[(w) * Lay::THREADS]
 #define DSB_DIV(a, b) DsbDivShared::div((a), (b))      // one shared division routine (code size, dsb_math.h)
+#ifndef DSB_NEWTON_DIV
+#define DSB_NEWTON_DIV DsbDivShared               // tuning experiment: inline expansion at the six hottest sites
+#endif
 #define SD(j, i) SM(Lay::O_D + (j) * N + (i))
 #define SJ(j, i) SM(Lay::O_J + (j) * N + (i))
 #define SMM(j, i) SM(Lay::O_M + (j) * N + (i))
@@ -526,7 +529,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                     for (int i = 0; i < N; ++i) delta[i] = tmp[i] + mc * delta[i];
                 }
             }
-            LaneLU<N, DsbDivShared> lu;
+            LaneLU<N, DSB_NEWTON_DIV> lu;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 lu.piv[j] = (int)((piv_packed >> (4 * j)) & 15ull);
@@ -541,7 +544,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                 for (int i = 0; i < N; ++i) {
                     y_cur[i] -= delta[i];
                     // Newton norm weights use the PREDICTOR (line_search.rs:67, convergence.rs:64-66)
-                    const double term = DSB_DIV(delta[i], dsb_abs(SYP(i)) * pa.rtol + pa.atol[i]);
+                    const double term = DSB_NEWTON_DIV::div(delta[i], dsb_abs(SYP(i)) * pa.rtol + pa.atol[i]);
                     acc += term * term;
                 }
                 const double norm = dsb_sqrt(DSB_DIV(acc, (double)N));
