@@ -15,7 +15,7 @@ METHODS = {"bdf": 0, "tr_bdf2": 1, "esdirk34": 2}
 MODELS = {
     "exp_decay": 0, "exp_decay_algebraic": 1, "robertson_dae": 2, "robertson_ode": 3,
     "robertson_ode_g3": 4, "dydt_y2": 5, "gaussian_decay": 6, "van_der_pol": 7, "van_der_pol_scaled": 8,
-    "heat1d_dae_256": 9, "heat1d_dae_32": 10, "spm": 11, "spm99": 12,
+    "heat1d_dae_256": 9, "heat1d_dae_32": 10, "spm": 11, "spm99": 12, "exp_decay_root": 13,
 }
 STAT_NAMES = [
     "number_of_linear_solver_setups",
@@ -110,6 +110,7 @@ SIGNATURES = {
     "dsb_batch_last_integrator_ms": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "dsb_batch_last_launch_count": (ctypes.c_int, [_vp, _pi32]),
     "dsb_batch_debug_words": (ctypes.c_int, [_vp, _vp]),
+    "dsb_batch_get_root_info": (ctypes.c_int, [_vp, _vp, _vp]),
     "dsb_lu_factor_batched": (ctypes.c_int, [_vp, _i32, _i64, _vp, _vp, _vp]),
     "dsb_lu_solve_batched": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "dsb_lu_factor_instance_major": (ctypes.c_int, [_vp, _i32, _i64, _vp, _vp, _vp]),

@@ -73,4 +73,6 @@ struct DsbBatchBuffers {
     double* fin_t;           // [B]
     double* fin_h;           // [B]
     int32_t* fin_order;      // [B]
+    int32_t* root_idx;       // [B]   index of the root function that stopped the instance, -1: none (OdeSolverStopReason::RootFound)
+    int32_t* ncols;          // [B]   solve_dense columns written (nt unless a root or an error stopped the instance)
 };

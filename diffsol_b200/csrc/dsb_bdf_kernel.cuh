@@ -125,6 +125,26 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 
     int fin_status = DSB_STATUS_OK;
     auto finish = [&](int status) { fin_status = status; state = L_FINISH; };
+    // root finding (nonlinear_solver/root.rs; bdf.rs:143, 301-306, 1566-1579): only compiled for equations with roots
+    constexpr int NR = dsb_model_nroots<M>::value;
+    double rf_g0[NR > 0 ? NR : 1];
+    double rf_t0 = 0.0;
+    int root_found = -1;
+#pragma unroll
+    for (int r = 0; r < (NR > 0 ? NR : 1); ++r) rf_g0[r] = 0.0;
+    // interpolate (bdf.rs:767-782, 1080-1106) at tq <= t from the difference array
+    auto interpolate = [&](double tq, double (&yo)[N]) {
+        double time_factor = 1.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) yo[i] = SD(0, i);
+#pragma unroll 1
+        for (int j = 0; j < order; ++j) {
+            const double j_t = (double)j;
+            time_factor *= DSB_DIV(tq - (t - h * j_t), h * (1.0 + j_t));
+#pragma unroll
+            for (int i = 0; i < N; ++i) yo[i] = time_factor * SD(j + 1, i) + yo[i];
+        }
+    };
     // bdf.rs:694-731.  0 = nothing, 1 = TstopReached, 2 = step size must be clipped (rescale_factor set), < 0 = -status
     auto handle_tstop = [&](double ts) -> int {
         const double troundoff = 100.0 * eps * (dsb_abs(t) + dsb_abs(h));
@@ -200,6 +220,8 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
         if (__any_sync(0xffffffffu, state == L_FINISH) && state == L_FINISH) {
             bb.status[inst] = fin_status;
             bb.fin_t[inst] = t; bb.fin_h[inst] = h; bb.fin_order[inst] = order;
+            bb.ncols[inst] = col;
+            if (NR > 0) bb.root_idx[inst] = root_found;
 #pragma unroll
             for (int k = 0; k < DSB_NSTATS; ++k) bb.stats[(int64_t)k * B + inst] = st.v[k];
             state = L_FETCH;
@@ -225,6 +247,15 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                 for (int i = 0; i < N; ++i) {
                     const double yi = bb.y0[(int64_t)i * B + inst];
                     SY(i) = yi; SD(0, i) = yi; SD(1, i) = bb.dy0[(int64_t)i * B + inst] * h;
+                }
+                if constexpr (NR > 0) {                         // Bdf::_new: root_finder.init(root_fn, state.y, state.t)
+                    double y0l[N], pl0[NP > 0 ? NP : 1];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) y0l[i] = SY(i);
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) pl0[j] = SP(j);
+                    M::root(y0l, pl0, t, rf_g0);
+                    rf_t0 = t; root_found = -1;
                 }
                 c = h * pa.tab.alpha[1];
                 jacobian_is_stale = true;
@@ -404,9 +435,120 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 
         // ================= TSTOP: set_stop_time (first) / handle_tstop after an accepted step =============
         if (__any_sync(0xffffffffu, state == L_TSTOP) && state == L_TSTOP) {
+            bool stopped_on_root = false;
+            if constexpr (NR > 0) {
+                // check for a root within the accepted step (bdf.rs:1566-1579), after the step-size update and before
+                // the stop time is handled; RootFinder::check_root (root.rs:60-160) with Vector::root_finding
+                // (diffsol-la/src/vector/nalgebra_serial.rs:484-504)
+                if (!first) {
+                    double pl[NP > 0 ? NP : 1], ys[N], g_end[NR], g1[NR], gmid[NR], ymid[N];
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) pl[j] = SP(j);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) ys[i] = SY(i);
+                    M::root(ys, pl, t, g_end);
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) g1[r] = g_end[r];
+                    auto root_finding = [&](const double (&ga)[NR], const double (&gb)[NR], bool& found, int& imax) {
+                        double max_frac = 0.0;
+                        imax = -1; found = false;
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) {
+                            if (gb[r] == 0.0) found = true;
+                            if (ga[r] * gb[r] < 0.0) {
+                                const double frac = dsb_abs(DSB_DIV(gb[r], gb[r] - ga[r]));
+                                if (frac > max_frac) { max_frac = frac; imax = r; }
+                            }
+                        }
+                    };
+                    auto pick = [&](const double (&g)[NR], int k) { double v = g[0];
+#pragma unroll
+                        for (int r = 1; r < NR; ++r) if (k == r) v = g[r];
+                        return v; };
+                    bool rootfnd; int imax;
+                    root_finding(rf_g0, g1, rootfnd, imax);
+                    double t_root = t;
+                    if (imax < 0) {
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) rf_g0[r] = g1[r];
+                        rf_t0 = t;
+                        if (rootfnd) {                              // find_zero_index: smallest |g|, first one on ties
+                            int min_idx = 0; double min_val = dsb_abs(rf_g0[0]);
+#pragma unroll
+                            for (int r = 1; r < NR; ++r) { const double v = dsb_abs(rf_g0[r]); if (v < min_val) { min_val = v; min_idx = r; } }
+                            stopped_on_root = true; root_found = min_idx;
+                        }
+                    } else {
+                        double alpha = 1.0;
+                        bool sc0 = false, sc1 = true;
+                        int it = 0;
+                        double t1 = t, tl = rf_t0;
+                        const double tol = 100.0 * eps * (dsb_abs(t1) + dsb_abs(t1 - tl));
+                        bool done = false;
+                        while (!done && dsb_abs(t1 - tl) > tol) {
+                            const double g1_val = pick(g1, imax), g0_val = pick(rf_g0, imax);
+                            double t_mid = t1 - DSB_DIV((t1 - tl) * g1_val, g1_val - alpha * g0_val);
+                            if (dsb_abs(t_mid - tl) < 0.5 * tol) {
+                                const double fracint = DSB_DIV(dsb_abs(t1 - tl), tol);
+                                const double fracsub = fracint > 5.0 ? 0.1 : DSB_DIV(0.5, fracint);
+                                t_mid = tl + fracsub * (t1 - tl);
+                            }
+                            if (dsb_abs(t1 - t_mid) < 0.5 * tol) {
+                                const double fracint = DSB_DIV(dsb_abs(t1 - tl), tol);
+                                const double fracsub = fracint > 5.0 ? 0.1 : DSB_DIV(0.5, fracint);
+                                t_mid = t1 - fracsub * (t1 - tl);
+                            }
+                            interpolate(t_mid, ymid);
+                            M::root(ymid, pl, t_mid, gmid);
+                            bool rf; int im;
+                            root_finding(rf_g0, gmid, rf, im);
+                            const bool lower = im >= 0;
+                            if (lower) {
+                                t1 = t_mid; imax = im;
+#pragma unroll
+                                for (int r = 0; r < NR; ++r) g1[r] = gmid[r];
+                            } else if (rf) {
+                                t_root = t_mid; done = true;
+                            } else {
+                                tl = t_mid;
+#pragma unroll
+                                for (int r = 0; r < NR; ++r) rf_g0[r] = gmid[r];
+                            }
+                            if (!done) {
+                                if ((it & 1) == 0) sc0 = lower; else sc1 = lower;
+                                if (it >= 2) alpha = (sc0 != sc1) ? 1.0 : (sc0 ? 0.5 * alpha : 2.0 * alpha);
+                                ++it;
+                            }
+                        }
+                        if (!done) t_root = t1;
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) rf_g0[r] = g_end[r];      // root_fn(y, t) again, into g0
+                        stopped_on_root = true; root_found = imax;
+                    }
+                    if (stopped_on_root) {
+                        // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root)
+                        // (bdf.rs:1228-1262), then the state at the root in the next column (method.rs:493-503)
+                        double yo[N];
+                        while (col < nt && bb.t_eval[col] <= t_root) {
+                            interpolate(bb.t_eval[col], yo);
+#pragma unroll
+                            for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
+                            ++col;
+                        }
+                        interpolate(t_root, yo);
+                        if (col < nt) {
+#pragma unroll
+                            for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
+                            ++col;
+                        }
+                        t = t_root;
+                        finish(DSB_STATUS_OK);
+                    }
+                }
+            }
             int next = first ? L_PREDICT : L_OUTPUT;
             int r = 0;
-            bool check = has_tstop;
+            bool check = has_tstop && !stopped_on_root;
             if (first) {
                 check = !free_running;
                 if (free_running) next = L_OUTPUT;
@@ -419,7 +561,9 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                     else reached = true;
                 }
             }
-            if (r < 0) {
+            if (stopped_on_root) {
+                // the lane is on its way to FINISH
+            } else if (r < 0) {
                 finish(-r);
             } else if (r == 2) {
                 rs_ignore_small = true;            // "step size too small" is ignored here (bdf.rs:726-728)
@@ -444,16 +588,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                 const bool is_forward = h > 0.0;
                 if ((is_forward && tq > t) || (!is_forward && tq < t)) { status = DSB_STATUS_INTERPOLATION_TIME_AFTER_CURRENT; break; }
                 double yo[N];
-                double time_factor = 1.0;
-#pragma unroll
-                for (int i = 0; i < N; ++i) yo[i] = SD(0, i);
-#pragma unroll 1
-                for (int j = 0; j < order; ++j) {
-                    const double j_t = (double)j;
-                    time_factor *= DSB_DIV(tq - (t - h * j_t), h * (1.0 + j_t));
-#pragma unroll
-                    for (int i = 0; i < N; ++i) yo[i] = time_factor * SD(j + 1, i) + yo[i];
-                }
+                interpolate(tq, yo);
 #pragma unroll
                 for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
                 ++col;

@@ -52,6 +52,8 @@ struct dsb_batch {
     double* fin_t = nullptr;
     double* fin_h = nullptr;
     int32_t* fin_order = nullptr;
+    int32_t* root_idx = nullptr;
+    int32_t* ncols = nullptr;
     int32_t* stats = nullptr;   // [DSB_NSTATS][B]
     int32_t* status = nullptr;
     unsigned long long* work_counter = nullptr;
@@ -218,7 +220,7 @@ const dsb_launch_fn g_launch_table[DSB_MODEL_COUNT] = {
     dsb_launch_model_0, dsb_launch_model_1, dsb_launch_model_2, dsb_launch_model_3,
     dsb_launch_model_4, dsb_launch_model_5, dsb_launch_model_6, dsb_launch_model_7,
     dsb_launch_model_8, dsb_launch_model_9, dsb_launch_model_10, dsb_launch_model_11,
-    dsb_launch_model_12,
+    dsb_launch_model_12, dsb_launch_model_13,
 };
 
 // instance-major <-> batch-major re-layout on the device (the host-facing layouts follow the
@@ -253,6 +255,10 @@ __global__ void dsb_stats_to_host_layout_kernel(const int32_t* __restrict__ src,
     int64_t v = src[(int64_t)s * B + b];
     if (s == DSB_STAT_RHS_JAC_MULS) v += probe_jac_muls;
     dst[idx] = v;
+}
+__global__ void dsb_fill_i32_kernel(int32_t* __restrict__ dst, int64_t B, int32_t v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) dst[i] = v;
 }
 __global__ void dsb_sum_stat_kernel(const int32_t* __restrict__ src, int64_t B, unsigned long long* out) {
     unsigned long long acc = 0;
@@ -383,6 +389,8 @@ int dsb_batch_new(const dsb_problem* p, int64_t nbatch, int32_t device, dsb_batc
     alloc((void**)&b->fin_t, B * 8);
     alloc((void**)&b->fin_h, B * 8);
     alloc((void**)&b->fin_order, B * 4);
+    alloc((void**)&b->root_idx, B * 4);
+    alloc((void**)&b->ncols, B * 4);
     alloc((void**)&b->stats, (size_t)DSB_NSTATS * B * 4);
     alloc((void**)&b->status, B * 4);
     alloc((void**)&b->work_counter, 256);     // word 0: the work counter; words 1..31: diagnostics (DSB_LANE_PROFILE builds)
@@ -405,7 +413,7 @@ int dsb_batch_free(dsb_batch* b) {
     if (!b) return DSB_OK;
     cudaSetDevice(b->device);
     cudaFree(b->params); cudaFree(b->y0); cudaFree(b->dy0); cudaFree(b->h0);
-    cudaFree(b->fin_t); cudaFree(b->fin_h); cudaFree(b->fin_order);
+    cudaFree(b->fin_t); cudaFree(b->fin_h); cudaFree(b->fin_order); cudaFree(b->root_idx); cudaFree(b->ncols);
     cudaFree(b->stats); cudaFree(b->status); cudaFree(b->work_counter); cudaFree(b->coop.ws_mem); cudaFree(b->coop.atol_dev); cudaFree(b->coop.color_dev); cudaFree(b->t_eval); cudaFree(b->ys_own); cudaFree(b->stage);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
@@ -469,6 +477,10 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     bb.params = b->params; bb.t_eval = b->t_eval; bb.y0 = b->y0; bb.dy0 = b->dy0; bb.h0 = b->h0;
     bb.ys = ys_dev; bb.stats = b->stats; bb.status = b->status;
     bb.fin_t = b->fin_t; bb.fin_h = b->fin_h; bb.fin_order = b->fin_order;
+    bb.root_idx = b->root_idx; bb.ncols = b->ncols;
+    // kernels without root finding leave these alone: no root, every column
+    DSB_CUDA(cudaMemsetAsync(b->root_idx, 0xFF, (size_t)b->B * 4, stream));
+    dsb_fill_i32_kernel<<<(unsigned)((b->B + 255) / 256), 256, 0, stream>>>(b->ncols, b->B, nt);
     // outputs never reached stay NaN (all-ones bit pattern)
     DSB_CUDA(cudaMemsetAsync(ys_dev, 0xFF, (size_t)nt * b->prob.n * b->B * 8, stream));
     b->last_launches = 0;
@@ -481,7 +493,7 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     b->coop.nz_host = nz_full.empty() ? nullptr : nz_full.data();      // test hook: 1 = lane kernels, 2 = cooperative
     cudaError_t lerr = g_launch_table[b->prob.model](&pa, &bb, method, stream, b->ev_mid, b->work_counter, &b->coop,
                                                      atol_full.data(), &b->last_launches);
-    if (lerr == cudaErrorNotSupported) return fail(DSB_ERR, "this method / option is not available for this system size (cooperative path: BDF with dense Jacobian only)");
+    if (lerr == cudaErrorNotSupported) return fail(DSB_ERR, "this method / execution mode is not available for this equation set (block-per-instance path: BDF only; banded path: BDF, banded ODE systems; root functions: BDF lane kernel only)");
     if (lerr != cudaSuccess) return fail(DSB_ERR, std::string("kernel launch: ") + cudaGetErrorString(lerr));
     DSB_CUDA(cudaEventRecord(b->ev1, stream));
     b->have_timing = true;
@@ -535,6 +547,14 @@ int dsb_batch_get_final_state(dsb_batch* b, double* t_host, double* h_host, int3
     if (t_host) DSB_CUDA(cudaMemcpy(t_host, b->fin_t, (size_t)b->B * 8, cudaMemcpyDeviceToHost));
     if (h_host) DSB_CUDA(cudaMemcpy(h_host, b->fin_h, (size_t)b->B * 8, cudaMemcpyDeviceToHost));
     if (order_host) DSB_CUDA(cudaMemcpy(order_host, b->fin_order, (size_t)b->B * 4, cudaMemcpyDeviceToHost));
+    return DSB_OK;
+}
+int dsb_batch_get_root_info(dsb_batch* b, int32_t* root_idx_host, int32_t* ncols_host) {
+    if (!b) return fail(DSB_BAD_ARG, "NULL argument");
+    DSB_CUDA(cudaSetDevice(b->device));
+    DSB_CUDA(cudaDeviceSynchronize());
+    if (root_idx_host) DSB_CUDA(cudaMemcpy(root_idx_host, b->root_idx, (size_t)b->B * 4, cudaMemcpyDeviceToHost));
+    if (ncols_host) DSB_CUDA(cudaMemcpy(ncols_host, b->ncols, (size_t)b->B * 4, cudaMemcpyDeviceToHost));
     return DSB_OK;
 }
 int dsb_batch_device_views(dsb_batch* b, const int32_t** stats_dev, const int32_t** status_dev) {

@@ -27,6 +27,11 @@
 
 #include "dsb_pow_tables.inc"
 
+// number of root (event) functions of an equation set (csrc/dsb_models.h): M::NROOTS when declared, else 0.  Lives
+// here because both the kernels and the oracle need it before the models are visible.
+template <class M, class = void> struct dsb_model_nroots { static constexpr int value = 0; };
+template <class M> struct dsb_model_nroots<M, decltype((void)M::NROOTS)> { static constexpr int value = M::NROOTS; };
+
 struct dsb_log_row { double invc, logc_hi, logc_lo; };
 struct dsb_exp_row { double hi, lo; };
 

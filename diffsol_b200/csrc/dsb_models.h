@@ -26,6 +26,7 @@ enum dsb_model_id {
     DSB_MODEL_HEAT1D_DAE_32 = 10,       // n=32  np=3  the same on a coarse grid (test size)
     DSB_MODEL_SPM = 11,                 // n=42  np=1  single-particle battery model, book/src/primer/src/spm.ds (BASELINE config 5)
     DSB_MODEL_SPM99 = 12,               // n=200 np=1  the same model on 99 radial cells per particle (not in the reference)
+    DSB_MODEL_EXP_DECAY_ROOT = 13,      // n=2  np=2   exp_decay with the root y[0] - 0.6 (test_models/exponential_decay.rs:370-390)
     DSB_MODEL_COUNT
 };
 
@@ -47,6 +48,13 @@ struct ModelExpDecay {
     DSB_HD static void init(const double* p, double, double* y) {
         for (int i = 0; i < N; ++i) y[i] = p[1];
     }
+};
+
+// The same equations with the root function of the reference's event tests
+// (test_models/exponential_decay.rs:102-104, 370-390): g = y[0] - 0.6; the integration stops at the first root.
+struct ModelExpDecayRoot : ModelExpDecay {
+    static constexpr int NROOTS = 1;
+    DSB_HD static void root(const double* x, const double*, double, double* g) { g[0] = x[0] - 0.6; }
 };
 
 // dy/dt = -a y ; 0 = z - y ; p = [a]; inconsistent IC [1,1,0]
@@ -371,6 +379,7 @@ template <> struct dsb_model_by_id<DSB_MODEL_HEAT1D_DAE_256> { typedef ModelHeat
 template <> struct dsb_model_by_id<DSB_MODEL_HEAT1D_DAE_32> { typedef ModelHeat1dDae<32> type; };
 template <> struct dsb_model_by_id<DSB_MODEL_SPM> { typedef ModelSpm type; };
 template <> struct dsb_model_by_id<DSB_MODEL_SPM99> { typedef ModelSpm99 type; };
+template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY_ROOT> { typedef ModelExpDecayRoot type; };
 
 // Compile-time dispatch over the registry: calls f.template operator()<Model>() for `id`.
 template <class F>
@@ -389,6 +398,7 @@ inline bool dsb_dispatch_model(int id, F&& f) {
         case DSB_MODEL_HEAT1D_DAE_32: f.template operator()<ModelHeat1dDae<32>>(); return true;
         case DSB_MODEL_SPM: f.template operator()<ModelSpm>(); return true;
         case DSB_MODEL_SPM99: f.template operator()<ModelSpm99>(); return true;
+        case DSB_MODEL_EXP_DECAY_ROOT: f.template operator()<ModelExpDecayRoot>(); return true;
         default: return false;
     }
 }

@@ -232,6 +232,14 @@ class BatchedSolver:
         capi.check(capi.lib().dsb_batch_get_final_state(self._b, _ptr(t), _ptr(h), _ptr(o)))
         return t, h, o
 
+    def root_info(self):
+        """(root_idx[B], ncols[B]): which root function stopped each instance (-1: none) and how many solve_dense
+        columns it wrote; the state at the root is column ncols - 1, its time is final_state()[0]."""
+        B = self.problem.nbatch
+        r, c = np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
+        capi.check(capi.lib().dsb_batch_get_root_info(self._b, _ptr(r), _ptr(c)))
+        return r, c
+
     def sum_statistic(self, name):
         tot = ctypes.c_int64()
         capi.check(capi.lib().dsb_batch_sum_stat(self._b, capi.STAT_NAMES.index(name), ctypes.byref(tot)))

@@ -52,7 +52,8 @@ enum dsb_method {
 enum dsb_model {
     DSB_EXP_DECAY = 0, DSB_EXP_DECAY_ALGEBRAIC = 1, DSB_ROBERTSON_DAE = 2, DSB_ROBERTSON_ODE = 3,
     DSB_ROBERTSON_ODE_G3 = 4, DSB_DYDT_Y2 = 5, DSB_GAUSSIAN_DECAY = 6, DSB_VAN_DER_POL = 7,
-    DSB_VAN_DER_POL_SCALED = 8, DSB_HEAT1D_DAE_256 = 9, DSB_HEAT1D_DAE_32 = 10, DSB_SPM = 11, DSB_SPM99 = 12
+    DSB_VAN_DER_POL_SCALED = 8, DSB_HEAT1D_DAE_256 = 9, DSB_HEAT1D_DAE_32 = 10, DSB_SPM = 11, DSB_SPM99 = 12,
+    DSB_EXP_DECAY_ROOT = 13
 };
 
 /* ---- statistics: one row of DSB_NSTATS int64 per instance.  Indices 0-9 are the fields of
@@ -171,6 +172,11 @@ int dsb_batch_get_status(dsb_batch* b, int32_t* status_host /* [nbatch] */);
 /* The same statistics written to a DEVICE buffer [nbatch][DSB_NSTATS] int64, asynchronously on `stream`. */
 int dsb_batch_get_stats_device(dsb_batch* b, int64_t* stats_dev, void* stream);
 int dsb_batch_get_final_state(dsb_batch* b, double* t_host, double* h_host, int32_t* order_host /* each [nbatch] or NULL */);
+/* Events (OdeSolverStopReason::RootFound, ode_solver/method.rs:774-805, 493-503): for equations with root functions
+ * an instance stops at its first root.  root_idx[b] = index of that root function, -1 when the instance ran to the
+ * last t_eval point; ncols[b] = solve_dense columns written: the points up to the root, then the state AT the root
+ * (its time is the final state's t); the columns behind stay NaN.  Each [nbatch] or NULL. */
+int dsb_batch_get_root_info(dsb_batch* b, int32_t* root_idx_host, int32_t* ncols_host);
 /* Device views (valid until the next solve / free): stats [DSB_NSTATS][nbatch] int32, status [nbatch] int32. */
 int dsb_batch_device_views(dsb_batch* b, const int32_t** stats_dev, const int32_t** status_dev);
 

@@ -71,12 +71,19 @@ struct Model {
     void (*jac_mul)(const double*, const double*, double, const double*, double*) = nullptr;
     void (*mass)(const double*, const double*, double, double, double*) = nullptr;
     void (*init)(const double*, double, double*) = nullptr;
+    int nroots = 0;                                                       // OdeEquations::root (ode_equations/mod.rs)
+    void (*root)(const double*, const double*, double, double*) = nullptr;
 };
+template <class M, int NR = dsb_model_nroots<M>::value> struct RootOf {
+    static void set(Model& m) { m.nroots = NR; m.root = &M::root; }
+};
+template <class M> struct RootOf<M, 0> { static void set(Model&) {} };
 template <class M>
 Model make_model() {
     Model m;
     m.n = M::N; m.np = M::NP; m.has_mass = M::HAS_MASS;
     m.rhs = &M::rhs; m.jac_mul = &M::jac_mul; m.mass = &M::mass; m.init = &M::init;
+    RootOf<M>::set(m);
     return m;
 }
 bool model_by_id(int id, Model* out);
@@ -195,7 +202,22 @@ struct InitialState {
 };
 int new_and_consistent(const Problem& pr, int solver_order, InitialState* st);
 
-enum StopReason { INTERNAL_TIMESTEP = 0, TSTOP_REACHED = 1, STEP_ERROR = 2 };
+enum StopReason { INTERNAL_TIMESTEP = 0, TSTOP_REACHED = 1, STEP_ERROR = 2, ROOT_FOUND = 3 };
+
+// ---- RootFinder (diffsol/src/nonlinear_solver/root.rs:12-160) + Vector::root_finding
+// (diffsol-la/src/vector/nalgebra_serial.rs:484-504) ------------------------------------------------
+struct RootFinder {
+    double t0 = 0.0;
+    Vec g0, g1, gmid, ymid;
+    void resize(int nroots, int nstates) { g0.assign(nroots, 0.0); g1 = g0; gmid = g0; ymid.assign(nstates, 0.0); }
+    // (found_root, max_frac, max_frac_index): g0 = lower end, g1 = upper end
+    static void root_finding(const Vec& g0, const Vec& g1, bool* found_root, int* imax);
+    // root.rs:34-37
+    void init(const Problem& pr, const double* y, double t);
+    // root.rs:60-160: true <=> a root was found in (t0, t]; *t_root, *idx
+    bool check_root(const Problem& pr, const std::function<int(double, double*)>& interpolate, const double* y,
+                    double t, double* t_root, int* idx);
+};
 
 // ---- the abstract surface both integrators share (OdeSolverMethod, ode_solver/method.rs:42-618) --
 struct Method {
@@ -208,12 +230,20 @@ struct Method {
     virtual int cur_order() const = 0;
     virtual const double* y() const = 0;
     virtual const Stats& stats() const = 0;
+    // RootFound(t, index) of the last step() that returned ROOT_FOUND
+    virtual double root_t() const { return 0.0; }
+    virtual int root_index() const { return -1; }
+    // OdeSolverMethod::state_mut_back (bdf.rs:1228-1262): move the state back to t inside the last step
+    virtual int state_mut_back(double) { return ST_BAD_ARG; }
 };
 
 Method* new_bdf(const Problem& pr, int* err);
 Method* new_sdirk(const Problem& pr, int tableau /*0 = tr_bdf2, 1 = esdirk34*/, int* err);
 
-// fn solve_dense (ode_solver/method.rs:721-818), without roots/checkpointing
-int solve_dense(Method& s, const double* t_eval, int nt, int n, double* out /* n*nt col-major */);
+// fn solve_dense (ode_solver/method.rs:721-818) + OdeSolverMethod::solve_dense (:467-505), without reset /
+// checkpointing.  When a root stops the integration, the columns up to the root are written, the state at the root
+// goes into the next column (when there is one) and *ncols / *root_t / *root_idx say so (ncols = nt otherwise).
+int solve_dense(Method& s, const double* t_eval, int nt, int n, double* out /* n*nt col-major */,
+                int* ncols = nullptr, double* root_t = nullptr, int* root_idx = nullptr);
 
 }  // namespace orc

@@ -38,6 +38,9 @@ struct Bdf : Method {
     Vec psi_neg_y0, tmp, rhs_jac, mass_jac, newton_tmp, A;
     double c = 0;
     bool jacobian_is_stale = true;
+    // root finding (bdf.rs:143, 301-306, 1566-1579)
+    RootFinder root_finder;
+    double root_t_ = 0.0; int root_idx_ = -1;
 
     explicit Bdf(const Problem& p) : pr(p), n(p.n()) {}
 
@@ -50,6 +53,10 @@ struct Bdf : Method {
         int err = new_and_consistent(pr, 1, &st);      // problem.rs:597-602: bdf_state -> solver_order = 1
         if (err) return err;
         y_ = st.y; dy_ = st.dy; t_ = st.t; h_ = st.h; order = 1;
+        if (pr.model.nroots > 0) {                         // bdf.rs:301-306
+            root_finder.resize(pr.model.nroots, n);
+            root_finder.init(pr, y_.data(), t_);
+        }
         const double kappa[6] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
         alpha[0] = 0.0; gamma[0] = 0.0; error_const2[0] = 1.0;
         for (int i = 1; i <= MAX_ORDER; ++i) {
@@ -332,6 +339,11 @@ struct Bdf : Method {
                 jacobian_updates(new_h * alpha[new_order], STEP_SUCCESS);
             }
         }
+        // check for a root within the accepted step (bdf.rs:1566-1579)
+        if (pr.model.nroots > 0) {
+            auto interp = [this](double tq, double* yq) { return interpolate(tq, yq); };
+            if (root_finder.check_root(pr, interp, y_.data(), t_, &root_t_, &root_idx_)) return ROOT_FOUND;
+        }
         if (has_tstop) {
             int r = handle_tstop(tstop);
             if (r == 1) return TSTOP_REACHED;
@@ -361,6 +373,20 @@ struct Bdf : Method {
             time_factor *= (t - (t_ - h_ * j_t)) / (h_ * (1.0 + j_t));
             for (int i = 0; i < n; ++i) y[i] = time_factor * D(j + 1)[i] + y[i];
         }
+        return ST_OK;
+    }
+
+    double root_t() const override { return root_t_; }
+    int root_index() const override { return root_idx_; }
+    // bdf.rs:1228-1262 (is_state_modified is false after a step; no integrate_out, no sensitivities)
+    int state_mut_back(double t) override {
+        const bool is_forward = h_ > 0.0;
+        if ((is_forward && t > t_) || (!is_forward && t < t_)) return ST_INTERPOLATION_TIME_AFTER_CURRENT;
+        Vec ynew(n);
+        int e = interpolate(t, ynew.data());
+        if (e) return e;
+        y_ = ynew;                          // dy is interpolated as well in the reference; nothing reads it afterwards here
+        t_ = t;
         return ST_OK;
     }
 

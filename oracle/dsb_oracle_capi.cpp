@@ -88,18 +88,25 @@ int orc_model_dims(int model_id, int* n, int* np, int* has_mass) {
     return ST_OK;
 }
 
-// `problem.bdf::<LS>()?.solve_dense(t_eval)`: out is n x nt column-major; fin = {t, h, order}
-int orc_solve_dense(const orc_problem_desc* d, const double* p, int np, const double* t_eval, int nt,
-                    double* out, int64_t* stats, double* fin) {
+// `problem.bdf::<LS>()?.solve_dense(t_eval)`: out is n x nt column-major; fin = {t, h, order}; root (may be NULL) =
+// {t_root, root index (-1: the integration did not stop on a root), number of columns written}
+static int solve_dense_one(const orc_problem_desc* d, const double* p, int np, const double* t_eval, int nt,
+                           double* out, int64_t* stats, double* fin, double* root) {
     Problem pr;
     int err = build_problem(d, p, np, &pr);
     if (err) return err;
     std::unique_ptr<Method> m(make_method(pr, d->method, &err));
     if (!m) { export_stats(pr, nullptr, stats); return err; }
-    err = solve_dense(*m, t_eval, nt, pr.n(), out);
+    int ncols = nt, ridx = -1; double rt = 0.0;
+    err = solve_dense(*m, t_eval, nt, pr.n(), out, &ncols, &rt, &ridx);
     export_stats(pr, m.get(), stats);
     if (fin) { fin[0] = m->t(); fin[1] = m->h(); fin[2] = (double)m->cur_order(); }
+    if (root) { root[0] = rt; root[1] = (double)ridx; root[2] = (double)ncols; }
     return err;
+}
+int orc_solve_dense(const orc_problem_desc* d, const double* p, int np, const double* t_eval, int nt,
+                    double* out, int64_t* stats, double* fin) {
+    return solve_dense_one(d, p, np, t_eval, nt, out, stats, fin, nullptr);
 }
 
 // The reference's test harness `test_ode_solver(.., use_tstop = false)` (ode_solver/mod.rs:104-194):
@@ -153,9 +160,17 @@ int orc_harness_tstop(const orc_problem_desc* d, const double* p, int np, const 
 // Batched driver: instance b uses params[b*np .. (b+1)*np) (instance-major, as the reference lays
 // out batched parameters, test_models/exponential_decay.rs:297-304).  out[b] is n x nt col-major,
 // stats[b] the 16 counters, status[b] the error code.  threads over instances = the CPU baseline.
+int orc_batch_solve_dense_roots(const orc_problem_desc* d, const double* params, int np, int64_t nbatch,
+                                const double* t_eval, int nt, int nthreads,
+                                double* out, int64_t* stats, int32_t* status, double* roots /* [nbatch][3] or NULL */);
 int orc_batch_solve_dense(const orc_problem_desc* d, const double* params, int np, int64_t nbatch,
                           const double* t_eval, int nt, int nthreads,
                           double* out, int64_t* stats, int32_t* status) {
+    return orc_batch_solve_dense_roots(d, params, np, nbatch, t_eval, nt, nthreads, out, stats, status, nullptr);
+}
+int orc_batch_solve_dense_roots(const orc_problem_desc* d, const double* params, int np, int64_t nbatch,
+                                const double* t_eval, int nt, int nthreads,
+                                double* out, int64_t* stats, int32_t* status, double* roots) {
     Model mm;
     if (!model_by_id(d->model_id, &mm)) return ST_BAD_ARG;
     const int n = mm.n;
@@ -171,9 +186,10 @@ int orc_batch_solve_dense(const orc_problem_desc* d, const double* params, int n
             if (b0 >= nbatch) break;
             int64_t b1 = b0 + chunk < nbatch ? b0 + chunk : nbatch;
             for (int64_t b = b0; b < b1; ++b) {
-                int err = orc_solve_dense(d, params + (size_t)b * np, np, t_eval, nt,
+                int err = solve_dense_one(d, params + (size_t)b * np, np, t_eval, nt,
                                           out ? out + (size_t)b * n * nt : nullptr,
-                                          stats ? stats + (size_t)b * S_COUNT : nullptr, nullptr);
+                                          stats ? stats + (size_t)b * S_COUNT : nullptr, nullptr,
+                                          roots ? roots + (size_t)b * 3 : nullptr);
                 if (status) status[b] = err;
             }
         }

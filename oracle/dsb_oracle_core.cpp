@@ -407,8 +407,92 @@ int new_and_consistent(const Problem& pr, int solver_order, InitialState* st) {
     return ST_OK;
 }
 
-// fn solve_dense (ode_solver/method.rs:721-818) + dense_write_out (:822-848), no out fn / roots
-int solve_dense(Method& s, const double* t_eval, int nt, int n, double* out) {
+// Vector::root_finding (diffsol-la/src/vector/nalgebra_serial.rs:484-504)
+void RootFinder::root_finding(const Vec& g0v, const Vec& g1v, bool* found_root, int* imax) {
+    double max_frac = 0.0;
+    int max_frac_index = -1;
+    bool found = false;
+    for (size_t i = 0; i < g0v.size(); ++i) {
+        const double g0 = g0v[i], g1 = g1v[i];
+        if (g1 == 0.0) found = true;
+        if (g0 * g1 < 0.0) {
+            const double frac = std::fabs(g1 / (g1 - g0));
+            if (frac > max_frac) { max_frac = frac; max_frac_index = (int)i; }
+        }
+    }
+    *found_root = found; *imax = max_frac_index;
+}
+
+void RootFinder::init(const Problem& pr, const double* y, double t) {
+    pr.model.root(y, pr.p.data(), t, g0.data());
+    t0 = t;
+}
+
+// root.rs:60-160 (the modified secant / Illinois iteration of SUNDIALS)
+bool RootFinder::check_root(const Problem& pr, const std::function<int(double, double*)>& interpolate, const double* y,
+                            double t, double* t_root, int* idx) {
+    const double* p = pr.p.data();
+    pr.model.root(y, p, t, g1.data());
+    bool rootfnd; int imax;
+    root_finding(g0, g1, &rootfnd, &imax);
+    if (imax < 0) {
+        std::swap(g0, g1);
+        t0 = t;
+        if (rootfnd) {
+            // find_zero_index (root.rs:44-58): the entry of smallest magnitude, first one on ties
+            int min_idx = 0; double min_val = std::fabs(g0[0]);
+            for (size_t i = 1; i < g0.size(); ++i) { const double v = std::fabs(g0[i]); if (v < min_val) { min_val = v; min_idx = (int)i; } }
+            *t_root = t; *idx = min_idx;
+            return true;
+        }
+        return false;
+    }
+    double alpha = 1.0;
+    bool sign_change[2] = {false, true};
+    int i = 0;
+    double t1 = t, tl = t0;
+    const double tol = 100.0 * 2.220446049250313e-16 * (std::fabs(t1) + std::fabs(t1 - tl));
+    while (std::fabs(t1 - tl) > tol) {
+        const double g1_val = g1[imax], g0_val = g0[imax];
+        double t_mid = t1 - (t1 - tl) * g1_val / (g1_val - alpha * g0_val);
+        if (std::fabs(t_mid - tl) < 0.5 * tol) {
+            const double fracint = std::fabs(t1 - tl) / tol;
+            const double fracsub = fracint > 5.0 ? 0.1 : 0.5 / fracint;
+            t_mid = tl + fracsub * (t1 - tl);
+        }
+        if (std::fabs(t1 - t_mid) < 0.5 * tol) {
+            const double fracint = std::fabs(t1 - tl) / tol;
+            const double fracsub = fracint > 5.0 ? 0.1 : 0.5 / fracint;
+            t_mid = t1 - fracsub * (t1 - tl);
+        }
+        interpolate(t_mid, ymid.data());                   // .unwrap() in the reference
+        pr.model.root(ymid.data(), p, t_mid, gmid.data());
+        bool rf; int im;
+        root_finding(g0, gmid, &rf, &im);
+        const bool lower = im >= 0;
+        if (lower) {
+            t1 = t_mid; imax = im; std::swap(g1, gmid);
+        } else if (rf) {
+            pr.model.root(y, p, t, g0.data());
+            *t_root = t_mid; *idx = imax;
+            return true;
+        } else {
+            tl = t_mid; std::swap(g0, gmid);
+        }
+        sign_change[i % 2] = lower;
+        if (i >= 2) alpha = (sign_change[0] != sign_change[1]) ? 1.0 : (sign_change[0] ? 0.5 * alpha : 2.0 * alpha);
+        ++i;
+    }
+    pr.model.root(y, p, t, g0.data());
+    *t_root = t1; *idx = imax;
+    return true;
+}
+
+// fn solve_dense (ode_solver/method.rs:721-818) + dense_write_out (:822-848) + the root column of
+// OdeSolverMethod::solve_dense (:493-503); no out fn, no reset, no checkpointing
+int solve_dense(Method& s, const double* t_eval, int nt, int n, double* out, int* ncols, double* root_t, int* root_idx) {
+    if (ncols) *ncols = nt;
+    if (root_idx) *root_idx = -1;
     if (nt <= 0) return ST_BAD_ARG;
     int err = s.set_stop_time(t_eval[nt - 1]);
     if (err) return err;
@@ -416,6 +500,24 @@ int solve_dense(Method& s, const double* t_eval, int nt, int n, double* out) {
     while (true) {
         StopReason r = s.step(&err);
         if (r == STEP_ERROR) return err;
+        if (r == ROOT_FOUND) {
+            const double tr = s.root_t();
+            while (col < nt && t_eval[col] <= tr) {
+                int e2 = s.interpolate(t_eval[col], out + (size_t)col * n);
+                if (e2) return e2;
+                ++col;
+            }
+            int e3 = s.state_mut_back(tr);
+            if (e3) return e3;
+            if (col < nt) {                                 // write_state_out at the root, then resize_cols(col + 1)
+                for (int i = 0; i < n; ++i) out[(size_t)col * n + i] = s.y()[i];
+                ++col;
+            }
+            if (ncols) *ncols = col;
+            if (root_t) *root_t = tr;
+            if (root_idx) *root_idx = s.root_index();
+            return ST_OK;
+        }
         while (col < nt && t_eval[col] <= s.t()) {
             int e2 = s.interpolate(t_eval[col], out + (size_t)col * n);
             if (e2) return e2;

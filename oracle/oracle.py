@@ -44,6 +44,7 @@ MODELS = {
     "heat1d_dae_32": 10,
     "spm": 11,
     "spm99": 12,
+    "exp_decay_root": 13,
 }
 
 
@@ -103,6 +104,8 @@ def lib():
         L.orc_batch_solve_dense.argtypes = [
             ctypes.POINTER(ProblemDesc), dp, ctypes.c_int, ctypes.c_int64, dp, ctypes.c_int, ctypes.c_int,
             dp, ip, ctypes.POINTER(ctypes.c_int32)]
+        L.orc_batch_solve_dense_roots.restype = ctypes.c_int
+        L.orc_batch_solve_dense_roots.argtypes = list(L.orc_batch_solve_dense.argtypes) + [dp]
         L.orc_model_dims.argtypes = [ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 3
         L.orc_pow.restype = ctypes.c_double
         L.orc_pow.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_int]
@@ -204,6 +207,25 @@ def batch_solve_dense(desc, params, t_eval, nthreads=0):
         status.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
     assert rc == 0
     return out, stats, status
+
+
+def batch_solve_dense_roots(desc, params, t_eval, nthreads=0):
+    """The same for models with root (event) functions -> (ys, stats, status, t_root[B], root_idx[B], ncols[B]):
+    an instance that stops on a root has its state at the root in column ncols - 1 and NaN behind it."""
+    n, np_, _ = _dims_by_id(desc.model_id)
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, max(np_, 1))
+    B = params.shape[0]
+    t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
+    out = np.full((B, len(t_eval), n), np.nan)
+    stats = np.zeros((B, S_COUNT), dtype=np.int64)
+    status = np.zeros(B, dtype=np.int32)
+    roots = np.zeros((B, 3))
+    rc = lib().orc_batch_solve_dense_roots(
+        ctypes.byref(desc), _dp(params), np_, B, _dp(t_eval), len(t_eval), int(nthreads), _dp(out),
+        stats.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+        status.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _dp(roots))
+    assert rc == 0
+    return out, stats, status, roots[:, 0].copy(), roots[:, 1].astype(np.int32), roots[:, 2].astype(np.int32)
 
 
 def num_threads():

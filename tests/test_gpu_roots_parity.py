@@ -1,0 +1,61 @@
+"""GPU parity tests of event handling: root finding inside the BDF lane kernel against
+the oracle, on the reference's exponential-decay-with-root problem swept over rate and initial value."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dsb():
+    import diffsol_b200
+    from diffsol_b200 import capi
+    capi.require_device()
+    return diffsol_b200
+
+
+def sweep(B):
+    from diffsol_b200 import sweeps
+    idx = np.arange(B)
+    k = 0.02 * 50.0 ** sweeps.uniform(idx, 0)             # 0.02 .. 1
+    y0 = 0.4 + 1.6 * sweeps.uniform(idx, 1)               # 0.4 .. 2: a quarter starts below the root level
+    return np.stack([k, y0], axis=1)
+
+
+@pytest.mark.parametrize("tol", [1e-6, 1e-9])
+def test_roots_bit_exact(dsb, oracle, tol):
+    B = 3000
+    p = sweep(B)
+    t_eval = np.arange(1.0, 21.0)
+    solver = dsb.OdeBuilder().rhs_implicit("exp_decay_root").p(p).rtol(tol).atol([tol]).build().bdf()
+    ys = solver.solve_dense(t_eval)
+    root_idx, ncols = solver.root_info()
+    t_fin = solver.final_state()[0]
+    desc = oracle.make_desc("exp_decay_root", powmode=1, rtol=tol, atol=[tol])
+    ys_o, stats_o, status_o, t_root_o, root_idx_o, ncols_o = oracle.batch_solve_dense_roots(desc, p, t_eval)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(root_idx, root_idx_o) and np.array_equal(ncols, ncols_o)
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o, equal_nan=True)
+    stopped = root_idx_o == 0
+    assert 0 < stopped.sum() < B                          # both kinds of instance are present
+    assert np.array_equal(t_fin[stopped], t_root_o[stopped])
+    # the state at the root sits in the last written column
+    assert np.abs(ys[stopped, ncols[stopped] - 1, 0] - 0.6).max() < 1e-5
+
+
+def test_roots_only_on_the_bdf_lane_kernel(dsb):
+    p = sweep(8)
+    prob = dsb.OdeBuilder().rhs_implicit("exp_decay_root").p(p).build()
+    with pytest.raises(dsb.DiffsolB200Error):
+        prob.tr_bdf2().solve_dense([1.0])
+    with pytest.raises(dsb.DiffsolB200Error):
+        prob.bdf().set_execution("block").solve_dense([1.0])
+
+
+def test_root_info_without_roots(dsb):
+    p = np.tile(np.array([[0.04, 1.0e4, 3.0e7]]), (40, 1))
+    solver = dsb.OdeBuilder().rhs_implicit("robertson_ode").p(p).rtol(1e-4).atol([1e-8, 1e-14, 1e-6]).build().bdf()
+    solver.solve_dense([0.4, 4.0])
+    root_idx, ncols = solver.root_info()
+    assert (root_idx == -1).all() and (ncols == 2).all()
