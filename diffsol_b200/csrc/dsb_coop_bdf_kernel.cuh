@@ -19,9 +19,8 @@
 
 #include "dsb_coop.cuh"
 #include "dsb_lane.cuh"
+#include "dsb_models.h"
 
-template <class M, class = void> struct dsb_is_componentwise : std::false_type {};
-template <class M> struct dsb_is_componentwise<M, std::void_t<decltype(M::COMPONENTWISE)>> : std::bool_constant<M::COMPONENTWISE> {};
 
 // Component-wise view of the equations.  Models written component-wise (dsb_models.h: `*_i`) are used
 // directly; for the small whole-vector models the component is picked out of a full evaluation (O(n) per

@@ -6,6 +6,7 @@
 #include "dsb_band_bdf_kernel.cuh"
 #include "dsb_bdf_kernel.cuh"
 #include "dsb_coop_bdf_kernel.cuh"
+#include "dsb_host_setup.h"
 #include "dsb_init_kernel.cuh"
 #include "dsb_launch.h"
 #include "dsb_models.h"
@@ -98,8 +99,6 @@ static cudaError_t launch_coop_bdf(const DsbProblemArgs* pa, const DsbBatchBuffe
 
 // banded lane kernel (one thread per instance, state in global memory): component-wise models without a mass
 // matrix that declare a band, n > 16
-template <class M, class = void> struct dsb_declares_band : std::false_type {};
-template <class M> struct dsb_declares_band<M, std::void_t<decltype(M::BAND_KL)>> : std::true_type {};
 constexpr bool kBandCapable = dsb_declares_band<InstModel>::value && dsb_is_componentwise<InstModel>::value &&
                               !InstModel::HAS_MASS && InstModel::N > 16;
 
@@ -117,32 +116,10 @@ template <class M> struct BandLauncher<M, true> {
         // sparsity pattern by NaN probe (jacobian/mod.rs:16-48): the declared band must cover it.  Per column: colour
         // (greedy colouring computed by the caller, or one colour per column for the dense assembly, which stores
         // every in-band entry) and the pattern inside the band.
-        std::vector<int32_t> colmeta(N, 0);
-        {
-            double p[M::NP > 0 ? M::NP : 1];
-            for (int j = 0; j < M::NP; ++j) p[j] = 1.0;
-            std::vector<double> y0(N), v(N, 0.0), col(N, 0.0);
-            M::init(p, pa->t0, y0.data());
-            if (pa->use_coloring && !coop->color_host) return cudaErrorInvalidValue;
-            for (int j = 0; j < N; ++j) {
-                v[j] = std::numeric_limits<double>::quiet_NaN();
-                M::jac_mul(y0.data(), p, pa->t0, v.data(), col.data());
-                int32_t mask = 0;
-                for (int i = 0; i < N; ++i) {
-                    if (!std::isnan(col[i])) continue;
-                    if (i - j > Lay::KL || j - i > Lay::KU) return cudaErrorNotSupported;
-                    mask |= 1 << (Lay::KU + i - j);
-                }
-                for (int i = 0; i < N; ++i) col[i] = 0.0;
-                v[j] = 0.0;
-                if (pa->use_coloring) {
-                    const int32_t colour = coop->color_host[j] < 0 ? 0xffff : coop->color_host[j];
-                    colmeta[j] = colour | (mask << 16);
-                } else {
-                    colmeta[j] = j | (((1 << Lay::LDJ) - 1) << 16);
-                }
-            }
-        }
+        std::vector<int32_t> colmeta;
+        if (pa->use_coloring && !coop->color_host) return cudaErrorInvalidValue;
+        if (!dsb_host::band_column_meta<M>(pa->t0, pa->use_coloring != 0, coop->color_host, Lay::KL, Lay::KU, &colmeta))
+            return cudaErrorNotSupported;
         cudaError_t e;
         if (coop->atol_n < N) {
             if (coop->atol_dev) cudaFree(coop->atol_dev);

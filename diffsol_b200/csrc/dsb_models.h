@@ -10,6 +10,8 @@
 // integrate *the same equations with the same floating-point expression trees*; the expression
 // order follows the reference closures literally (file:line cited on each model).
 #pragma once
+#include <type_traits>
+
 #include "dsb_math.h"
 
 enum dsb_model_id {
@@ -380,6 +382,12 @@ template <> struct dsb_model_by_id<DSB_MODEL_HEAT1D_DAE_32> { typedef ModelHeat1
 template <> struct dsb_model_by_id<DSB_MODEL_SPM> { typedef ModelSpm type; };
 template <> struct dsb_model_by_id<DSB_MODEL_SPM99> { typedef ModelSpm99 type; };
 template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY_ROOT> { typedef ModelExpDecayRoot type; };
+
+// traits of an equation set: written component-wise (`*_i` functions), declares a band for df/dy
+template <class M, class = void> struct dsb_is_componentwise : std::false_type {};
+template <class M> struct dsb_is_componentwise<M, std::void_t<decltype(M::COMPONENTWISE)>> : std::bool_constant<M::COMPONENTWISE> {};
+template <class M, class = void> struct dsb_declares_band : std::false_type {};
+template <class M> struct dsb_declares_band<M, std::void_t<decltype(M::BAND_KL)>> : std::true_type {};
 
 // Compile-time dispatch over the registry: calls f.template operator()<Model>() for `id`.
 template <class F>

@@ -1,0 +1,128 @@
+// dsb_emu.cpp -- TEST INFRASTRUCTURE: single-lane host build of the product's lane kernels (see cuda_shim.h).
+// `emu_solve` runs `problem.<method>().solve_dense(t_eval)` (or the free-running step/interpolate loop) for each
+// instance through the SAME kernel source the sm_100a library is built from, one instance per "launch", and hands
+// back what the C ABI's *_host entry points would.  Used by tests/test_host_emu_*.py to compare kernel logic with the
+// oracle without a GPU; never part of the product.
+#include "cuda_shim.h"
+
+#include <cstdlib>
+#include <vector>
+
+#include "../../diffsol_b200/csrc/dsb_host_setup.h"
+#include "../../diffsol_b200/csrc/dsb_band_bdf_kernel.cuh"
+#include "../../diffsol_b200/csrc/dsb_bdf_kernel.cuh"
+#include "../../diffsol_b200/csrc/dsb_init_kernel.cuh"
+#include "../../diffsol_b200/csrc/dsb_sdirk_kernel.cuh"
+
+double dsb_lane_smem[1 << 20];      // the "shared memory" of the emulated block (word w of lane 0 at w * THREADS)
+
+namespace {
+
+struct EmuDims { dsb_problem* p; template <class M> void operator()() { p->n = M::N; p->np = M::NP; p->has_mass = M::HAS_MASS; } };
+
+struct EmuCall {
+    const dsb_problem* pr; int method, kernel, free_running;
+    const double* params; int64_t B; const double* t_eval; int nt;
+    double* ys; int64_t* stats; int32_t* status; double* fin; int32_t* root_idx; int32_t* ncols;
+    int rc;
+
+    template <class M> void operator()() {
+        constexpr int N = M::N, NP = M::NP;
+        DsbProblemArgs pa;
+        int probes = 0;
+        std::vector<int32_t> color_full; std::vector<uint8_t> nz_full;
+        if (dsb_host::fill_problem_args(*pr, 1, nt, &pa, &probes, &color_full, &nz_full) != DSB_OK) { rc = DSB_BAD_ARG; return; }
+        pa.free_running = free_running;
+        dsb_host::build_tableau(method, &pa.rk);
+        pa.quorum = DSB_DEFAULT_QUORUM;
+        std::vector<double> atol_full(N);
+        for (int i = 0; i < N; ++i) atol_full[i] = pr->atol.size() == 1 ? pr->atol[0] : pr->atol[i];
+        std::vector<double> y0(N), dy0(N), h0(1), ysb((size_t)nt * N), fin_t(1), fin_h(1);
+        std::vector<int32_t> st(DSB_NSTATS), status1(1), fin_order(1), ridx(1), nc(1);
+        for (int64_t b = 0; b < B; ++b) {
+            DsbBatchBuffers bb;
+            bb.params = params + b * NP; bb.t_eval = t_eval; bb.y0 = y0.data(); bb.dy0 = dy0.data(); bb.h0 = h0.data();
+            bb.ys = ysb.data(); bb.stats = st.data(); bb.status = status1.data();
+            bb.fin_t = fin_t.data(); bb.fin_h = fin_h.data(); bb.fin_order = fin_order.data();
+            bb.root_idx = ridx.data(); bb.ncols = nc.data();
+            for (auto& v : ysb) v = dsb_from_bits(~0ull);
+            for (auto& v : st) v = 0;
+            status1[0] = -1; ridx[0] = -1; nc[0] = nt; fin_t[0] = fin_h[0] = 0.0; fin_order[0] = 0;
+            unsigned long long work_counter = 0;
+            bool ran = false;
+            if (kernel == 1) {
+                if constexpr (N <= 16) {
+                    if (method == DSB_METHOD_BDF) {
+                        blockDim.x = BdfLayout<M>::THREADS;
+                        dsb_init_kernel<M>(pa, bb, 1);
+                        dsb_bdf_solve_dense_kernel<M>(pa, bb, &work_counter);
+                    } else {
+                        blockDim.x = SdirkLayout<M>::THREADS;
+                        dsb_init_kernel<M>(pa, bb, pa.rk.order);
+                        dsb_sdirk_solve_dense_kernel<M>(pa, bb, &work_counter);
+                    }
+                    ran = true;
+                }
+            } else if (kernel == 3) {
+                if constexpr (dsb_declares_band<M>::value && dsb_is_componentwise<M>::value && !M::HAS_MASS && N > 16) {
+                    if (method == DSB_METHOD_BDF) {
+                        typedef BandBdfLayout<M> Lay;
+                        std::vector<int32_t> colmeta;
+                        if (!dsb_host::band_column_meta<M>(pa.t0, pa.use_coloring != 0, color_full.empty() ? nullptr : color_full.data(),
+                                                           Lay::KL, Lay::KU, &colmeta)) { rc = DSB_ERR; return; }
+                        const DsbBandMeta meta{atol_full.data(), colmeta.data()};
+                        blockDim.x = Lay::THREADS;
+                        std::vector<double> ws((size_t)Lay::WORDS * Lay::THREADS);
+                        dsb_band_bdf_solve_dense_kernel<M>(pa, bb, meta, ws.data(), &work_counter);
+                        ran = true;
+                    }
+                }
+            }
+            if (!ran) { rc = DSB_ERR; return; }
+            for (int k = 0; k < nt; ++k)
+                for (int i = 0; i < N; ++i) ys[(b * nt + k) * N + i] = ysb[(size_t)k * N + i];
+            for (int s = 0; s < DSB_NSTATS; ++s) stats[b * DSB_NSTATS + s] = st[s] + (s == DSB_STAT_RHS_JAC_MULS ? probes : 0);
+            status[b] = status1[0];
+            fin[b * 3 + 0] = fin_t[0]; fin[b * 3 + 1] = fin_h[0]; fin[b * 3 + 2] = (double)fin_order[0];
+            root_idx[b] = ridx[0]; ncols[b] = nc[0];
+        }
+        rc = DSB_OK;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+void dsb_options_default(dsb_options* o);   // defined below (the same defaults as dsb_capi.cu, problem.rs:132-152)
+
+// kernel: 1 = on-chip lane kernels (n <= 16), 3 = banded lane kernels
+int emu_solve(int model, int method, int kernel, double rtol, const double* atol, int natol, double t0, double h0,
+              int use_coloring, const dsb_options* opt, const double* params, int64_t B, const double* t_eval, int nt,
+              int free_running, double* ys, int64_t* stats, int32_t* status, double* fin, int32_t* root_idx, int32_t* ncols) {
+    dsb_problem pr;
+    pr.model = model; pr.n = 0; pr.np = 0; pr.has_mass = 0;
+    pr.rtol = rtol; pr.atol.assign(atol, atol + natol); pr.t0 = t0; pr.h0 = h0; pr.use_coloring = use_coloring;
+    if (opt) pr.opt = *opt; else dsb_options_default(&pr.opt);
+    EmuDims dims{&pr};
+    if (!dsb_dispatch_model(model, dims)) return DSB_BAD_ARG;
+    if (natol != 1 && natol != pr.n) return DSB_BAD_ARG;
+    EmuCall call{&pr, method, kernel, free_running, params, B, t_eval, nt, ys, stats, status, fin, root_idx, ncols, DSB_ERR};
+    dsb_dispatch_model(model, call);
+    return call.rc;
+}
+
+void dsb_options_default(dsb_options* o) {
+    std::memset(o, 0, sizeof(*o));
+    o->max_nonlinear_solver_iterations = 10; o->max_error_test_failures = 40; o->max_nonlinear_solver_failures = 50;
+    o->update_jacobian_after_steps = 20; o->update_rhs_jacobian_after_steps = 50;
+    o->ic_max_linesearch_iterations = 10; o->ic_max_newton_iterations = 10; o->ic_max_linear_solver_setups = 4;
+    o->ic_use_linesearch = 1;
+    o->nonlinear_solver_tolerance = 0.2; o->min_timestep = 1e-13;
+    o->max_timestep_growth = 2.0; o->min_timestep_growth = 2.0; o->max_timestep_shrink = 0.9; o->min_timestep_shrink = 0.5;
+    o->threshold_to_update_jacobian = 0.3; o->threshold_to_update_rhs_jacobian = 0.2;
+    o->pi_control_proportional = 0.0; o->pi_control_integral = 0.5;
+    o->ic_step_reduction_factor = 0.5; o->ic_armijo_constant = 1e-4;
+}
+
+}  // extern "C"

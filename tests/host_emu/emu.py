@@ -1,0 +1,112 @@
+"""ctypes wrapper around the single-lane HOST build of the product's lane kernels -- TEST INFRASTRUCTURE.
+
+tests/host_emu/dsb_emu.cpp compiles diffsol_b200/csrc/*.cuh with g++ through cuda_shim.h and runs one lane of the
+kernels per instance, so the kernels' control flow and arithmetic can be compared bit for bit with the oracle on a
+machine without a GPU.  The product package never imports this; it has no host integrator.
+"""
+import ctypes
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_CSRC = os.path.join(_ROOT, "diffsol_b200", "csrc")
+_OUT = os.path.join(_HERE, "_build")
+_LIB = os.path.join(_OUT, "libdsb_emu.so")
+NSTATS = 16
+METHODS = {"bdf": 0, "tr_bdf2": 1, "esdirk34": 2}
+KERNELS = {"lane": 1, "band": 3}
+
+
+class Options(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in (
+        "max_nonlinear_solver_iterations", "max_error_test_failures", "max_nonlinear_solver_failures",
+        "update_jacobian_after_steps", "update_rhs_jacobian_after_steps", "ic_max_linesearch_iterations",
+        "ic_max_newton_iterations", "ic_max_linear_solver_setups", "ic_use_linesearch", "reserved0")] + [
+        (k, ctypes.c_double) for k in (
+        "nonlinear_solver_tolerance", "min_timestep", "max_timestep_growth", "min_timestep_growth",
+        "max_timestep_shrink", "min_timestep_shrink", "threshold_to_update_jacobian",
+        "threshold_to_update_rhs_jacobian", "pi_control_proportional", "pi_control_integral",
+        "ic_step_reduction_factor", "ic_armijo_constant")]
+
+
+def _digest():
+    h = hashlib.sha256()
+    for d in (_CSRC, _HERE):
+        for name in sorted(os.listdir(d)):
+            path = os.path.join(d, name)
+            if os.path.isfile(path) and name.endswith((".h", ".cuh", ".inc", ".cpp")):
+                with open(path, "rb") as f:
+                    h.update(name.encode()); h.update(f.read())
+    return h.hexdigest()
+
+
+def build(force=False):
+    os.makedirs(_OUT, exist_ok=True)
+    stamp = os.path.join(_OUT, "build.sha256")
+    digest = _digest()
+    if not force and os.path.exists(_LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        return _LIB
+    cxx = os.environ.get("CXX", "g++")
+    subprocess.check_call([cxx, "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-mfma", "-shared",
+                           os.path.join(_HERE, "dsb_emu.cpp"), "-o", _LIB])
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = ctypes.CDLL(build())
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.emu_solve.restype = ctypes.c_int
+        L.emu_solve.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, dp, ctypes.c_int,
+                                ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.POINTER(Options), dp,
+                                ctypes.c_int64, dp, ctypes.c_int, ctypes.c_int, dp, ctypes.POINTER(ctypes.c_int64),
+                                ctypes.POINTER(ctypes.c_int32), dp, ctypes.POINTER(ctypes.c_int32),
+                                ctypes.POINTER(ctypes.c_int32)]
+        L.dsb_options_default.argtypes = [ctypes.POINTER(Options)]
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def solve(model_id, n, np_, params, t_eval, method="bdf", kernel="lane", rtol=1e-6, atol=1e-6, t0=0.0, h0=1.0,
+          use_coloring=False, options=None, free_running=False):
+    """-> dict(ys[B, nt, n], stats[B, 16], status[B], fin[B, 3], root_idx[B], ncols[B]); raises when the kernel does
+    not exist for the model."""
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, max(np_, 1))
+    B = params.shape[0]
+    t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
+    atol = np.ascontiguousarray(np.atleast_1d(np.asarray(atol, dtype=np.float64)))
+    nt = len(t_eval)
+    ys = np.full((B, nt, n), np.nan)
+    stats = np.zeros((B, NSTATS), dtype=np.int64)
+    status = np.zeros(B, dtype=np.int32)
+    fin = np.zeros((B, 3))
+    root_idx = np.zeros(B, dtype=np.int32)
+    ncols = np.zeros(B, dtype=np.int32)
+    opt = None
+    if options:
+        opt = Options()
+        lib().dsb_options_default(ctypes.byref(opt))
+        for k, v in options.items():
+            setattr(opt, k, v)
+    ip32 = ctypes.POINTER(ctypes.c_int32)
+    rc = lib().emu_solve(int(model_id), METHODS[method], KERNELS[kernel], float(rtol), _dp(atol), len(atol), float(t0),
+                         float(h0), int(use_coloring), ctypes.byref(opt) if opt is not None else None, _dp(params), B,
+                         _dp(t_eval), nt, int(free_running), _dp(ys), stats.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                         status.ctypes.data_as(ip32), _dp(fin), root_idx.ctypes.data_as(ip32), ncols.ctypes.data_as(ip32))
+    if rc != 0:
+        raise RuntimeError("emu_solve: rc = %d (kernel %r not available for this model / method?)" % (rc, kernel))
+    return dict(ys=ys, stats=stats, status=status, fin=fin, root_idx=root_idx, ncols=ncols)

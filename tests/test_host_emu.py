@@ -1,0 +1,60 @@
+"""The product's lane kernels, compiled for the HOST and run one lane at a time (tests/host_emu: the kernel source of
+diffsol_b200/csrc/*.cuh behind a CUDA shim), against the oracle: counters, status and states bit-identical.
+
+This checks the kernels' control flow and arithmetic on machines without a GPU; it does not replace the `-m gpu`
+parity tests (those run the real sm_100a build through the C ABI, many lanes per warp).  The product itself has no
+host integrator: nothing under diffsol_b200/ can reach this build."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from host_emu import emu  # noqa: E402
+
+from diffsol_b200 import sweeps  # noqa: E402
+
+
+def run_both(oracle, model, params, t_eval, method="bdf", kernel="lane", **kw):
+    n, np_, _ = oracle.model_dims(model)
+    desc = oracle.make_desc(model, method=method, powmode=1, **kw)
+    ys_o, stats_o, status_o = oracle.batch_solve_dense(desc, params, t_eval)
+    r = emu.solve(oracle.MODELS[model], n, np_, params, t_eval, method=method, kernel=kernel, **kw)
+    return r, ys_o, stats_o, status_o
+
+
+def assert_same(r, ys_o, stats_o, status_o):
+    assert np.array_equal(r["status"], status_o)
+    assert np.array_equal(r["stats"][:, :13], stats_o[:, :13])
+    assert np.array_equal(r["ys"], ys_o, equal_nan=True)
+
+
+def spm_currents(B):
+    return (0.6 + 0.8 * sweeps.uniform(np.arange(B), 0)).reshape(-1, 1)
+
+
+@pytest.mark.parametrize("model,tol,coloring", [
+    ("robertson_ode", sweeps.ROBERTSON_ODE_TOL, False),
+    ("robertson_ode", sweeps.ROBERTSON_ODE_TOL, True),
+    ("robertson_dae", sweeps.ROBERTSON_DAE_TOL, False),
+])
+def test_bdf_lane_kernel_on_host(oracle, model, tol, coloring):
+    p = sweeps.robertson_sweep(np.arange(48))
+    r, *o = run_both(oracle, model, p, sweeps.ROBERTSON_T_EVAL, use_coloring=coloring, **tol)
+    assert (o[2] == 0).all()
+    assert_same(r, *o)
+
+
+@pytest.mark.parametrize("method", ["tr_bdf2", "esdirk34"])
+def test_sdirk_lane_kernel_on_host(oracle, method):
+    p = sweeps.van_der_pol_scaled_sweep(np.arange(48))
+    r, *o = run_both(oracle, "van_der_pol_scaled", p, sweeps.VAN_DER_POL_T_EVAL, method=method, **sweeps.VAN_DER_POL_TOL)
+    assert_same(r, *o)
+
+
+@pytest.mark.parametrize("model,B,coloring", [("spm", 12, False), ("spm", 12, True), ("spm99", 3, True)])
+def test_band_bdf_lane_kernel_on_host(oracle, model, B, coloring):
+    r, *o = run_both(oracle, model, spm_currents(B), np.arange(1, 7) * 600.0, kernel="band", use_coloring=coloring)
+    assert (o[2] == 0).all()
+    assert_same(r, *o)
