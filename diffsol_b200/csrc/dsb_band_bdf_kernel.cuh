@@ -23,13 +23,19 @@
 // Restated functions: the same list as dsb_bdf_kernel.cuh, plus new_without_initialise / set_step_size
 // (ode_solver/state.rs:1086-1124, 1209-1277), which the small-n path runs in dsb_init_kernel.cuh.
 #pragma once
+#include "dsb_band_lu.cuh"
 #include "dsb_bdf_kernel.cuh"
 
-template <class M>
+#ifndef DSB_BAND_THREADS
+#define DSB_BAND_THREADS 768        // 24 warps at 80 registers: 1.16x over 16 warps at 128 (latency bound on global loads); 32 warps spill too much
+#endif
+#define DSB_BAND_THREADS_SMALL 128  // batches that do not fill one 768-lane block per SM are spread over the SMs in small blocks
+
+template <class M, int T = DSB_BAND_THREADS>
 struct BandBdfLayout {
     static constexpr int N = M::N, NP = M::NP;
     static constexpr int KL = M::BAND_KL, KU = M::BAND_KU, KV = KL + KU;
-    static constexpr int LDJ = KL + KU + 1;                         // rows of the band storage of df/dy
+    static constexpr int LDJ = KL + KU + 1;                         // rows of the band storage of df/dy (and of M)
     static constexpr int LDAB = 2 * KL + KU + 1;                    // rows of the band storage of the factors
     static constexpr int O_D = 0;                                   // D[DSB_NDIFF][N]
     static constexpr int O_Y = O_D + DSB_NDIFF * N;                 // state.y
@@ -41,12 +47,11 @@ struct BandBdfLayout {
     static constexpr int O_LU = O_J + LDJ * N;                      // factors, band storage: (i, j) at j * LDAB + KV + i - j
     static constexpr int O_PIV = O_LU + LDAB * N;                   // pivot offsets (row j interchanged with row j + piv[j])
     static constexpr int O_RU = O_PIV + N;                          // rescale matrix R U when it does not fit shared memory
-    static constexpr int WORDS = O_RU + 25;
-#ifndef DSB_BAND_THREADS
-#define DSB_BAND_THREADS 768        // 24 warps at 80 registers: 1.16x over 16 warps at 128 (latency bound on global loads); 32 warps spill too much
-#endif
-    static constexpr int THREADS = DSB_BAND_THREADS;
-    static constexpr int MAXNREG = (65536 / THREADS) / 8 * 8;
+    static constexpr int O_M = O_RU + 25;                           // mass matrix, band storage like df/dy (DAEs only)
+    static constexpr int O_TMP = O_M + (M::HAS_MASS ? LDJ * N : 0); // y + psi - y_predict, the argument of M (DAEs only)
+    static constexpr int WORDS = O_TMP + (M::HAS_MASS ? N : 0);
+    static constexpr int THREADS = T;
+    static constexpr int MAXNREG = (65536 / THREADS) / 8 * 8 > 255 ? 255 : (65536 / THREADS) / 8 * 8;
     static constexpr bool RU_IN_SMEM = THREADS <= 768;
     static constexpr int SMEM_WORDS = (DSB_NSTATS + 1) / 2 + (RU_IN_SMEM ? 25 : 0);   // statistics (+ rows / columns 1..5 of R U)
     static_assert(KL >= 1 && KL <= 2 && KU >= 1 && KU <= 2, "register windows are sized for kl, ku <= 2");
@@ -72,13 +77,20 @@ struct BandColourSeed {
     }
 };
 
-template <class M>
-__global__ void __maxnreg__(BandBdfLayout<M>::MAXNREG) dsb_band_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa,
+// e_j: the argument of `mass` when the mass matrix is assembled column by column (op/linear_op.rs:42-51)
+struct BandUnitVec {
+    int j;
+    __device__ __forceinline__ double operator[](int k) const { return k == j ? 1.0 : 0.0; }
+};
+
+template <class M, int T>
+__global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa,
                                                                   const __grid_constant__ DsbBatchBuffers bb,
                                                                   const __grid_constant__ DsbBandMeta meta,
                                                                   double* __restrict__ ws,
                                                                   unsigned long long* __restrict__ work_counter) {
-    typedef BandBdfLayout<M> Lay;
+    typedef BandBdfLayout<M, T> Lay;
+    typedef LaneBandLU<M::N, Lay::KL, Lay::KU, DsbDivShared> BLU;
     constexpr int N = Lay::N, NP = Lay::NP, KL = Lay::KL, KU = Lay::KU, KV = Lay::KV, LDJ = Lay::LDJ, LDAB = Lay::LDAB;
     extern __shared__ double dsb_lane_smem[];
     double* const sm = dsb_lane_smem + threadIdx.x;
@@ -96,8 +108,10 @@ __global__ void __maxnreg__(BandBdfLayout<M>::MAXNREG) dsb_band_bdf_solve_dense_
 #define GJ(j, r) G(Lay::O_J + (j) * LDJ + (r))
 #define GAB(j, r) G(Lay::O_LU + (j) * LDAB + (r))
 #define GPIV(j) G(Lay::O_PIV + (j))
+#define GM(j, r) G(Lay::O_M + (j) * LDJ + (r))
+#define GTMP(i) G(Lay::O_TMP + (i))
 #define DSB_DIV(a, b) DsbDivShared::div((a), (b))
-    const BandVec vY{g + (size_t)Lay::O_Y * LS, LS}, vYC{g + (size_t)Lay::O_YC * LS, LS};
+    const BandVec vY{g + (size_t)Lay::O_Y * LS, LS}, vYC{g + (size_t)Lay::O_YC * LS, LS}, vTMP{g + (size_t)Lay::O_TMP * LS, LS};
 
     const int64_t B = pa.nbatch;
     const int nt = pa.nt;
@@ -186,18 +200,27 @@ __global__ void __maxnreg__(BandBdfLayout<M>::MAXNREG) dsb_band_bdf_solve_dense_
             inst = (int64_t)atomicAdd(work_counter, 1ull);
             if (inst >= B) {
                 state = L_IDLE;
-            } else {
+            } else if (!M::HAS_MASS || bb.status[inst] == DSB_STATUS_OK) {     // else: consistent initialisation failed, keep its status
 #pragma unroll
                 for (int j = 0; j < NP; ++j) pl[j] = bb.params[(int64_t)j * B + inst];
 #pragma unroll
                 for (int k = 0; k < DSB_NSTATS; ++k) st.v[k] = 0;
                 t = pa.t0;
-                // y = init(p, t0); dy = f(y, t0)     (state.rs:1086-1124); dy is kept in D[1] until h is known
+                if constexpr (M::HAS_MASS) {
+                    // singular mass: y, dy after set_consistent and the counters so far come from dsb_band_init_kernel
+                    // (state.rs:84-162)
+#pragma unroll
+                    for (int k = 0; k < DSB_NSTATS; ++k) st.v[k] = bb.stats[(int64_t)k * B + inst];
 #pragma unroll 2
-                for (int i = 0; i < N; ++i) GY(i) = M::init_i(i, pl, pa.t0);
+                    for (int i = 0; i < N; ++i) { GY(i) = bb.y0[(int64_t)i * B + inst]; GD(1, i) = bb.dy0[(int64_t)i * B + inst]; }
+                } else {
+                    // y = init(p, t0); dy = f(y, t0)     (state.rs:1086-1124); dy is kept in D[1] until h is known
 #pragma unroll 2
-                for (int i = 0; i < N; ++i) GD(1, i) = M::rhs_i(i, vY, pl, pa.t0);
-                st.v[DSB_STAT_RHS_CALLS] += 1;
+                    for (int i = 0; i < N; ++i) GY(i) = M::init_i(i, pl, pa.t0);
+#pragma unroll 2
+                    for (int i = 0; i < N; ++i) GD(1, i) = M::rhs_i(i, vY, pl, pa.t0);
+                    st.v[DSB_STAT_RHS_CALLS] += 1;
+                }
                 // set_step_size (state.rs:1209-1277), solver order 1
                 {
                     const bool is_neg_h = pa.h0 < 0.0;
@@ -382,9 +405,21 @@ __global__ void __maxnreg__(BandBdfLayout<M>::MAXNREG) dsb_band_bdf_solve_dense_
                             }
                         }
                     }
+                    if constexpr (M::HAS_MASS) {
+                        // mass.matrix_inplace(t) with the Jacobian (op/bdf.rs:273-300): column j = M e_j, beta = 0
+#pragma unroll 1
+                        for (int j = 0; j < N; ++j) {
+                            const BandUnitVec ej{j};
+#pragma unroll
+                            for (int r = 0; r < LDJ; ++r) {
+                                const int i = j + r - KU;
+                                GM(j, r) = (i >= 0 && i < N) ? M::mass_i(i, ej, pl, t, 0.0, 0.0) : 0.0;
+                            }
+                        }
+                    }
                     jacobian_is_stale = false;
                 }
-                // A = I - c J (op/bdf.rs:282-298: J * (-c) + M) in band storage with kl extra rows for the fill-in
+                // A = M - c J (op/bdf.rs:282-298: J * (-c) + M) in band storage with kl extra rows for the fill-in
                 const double mc = -c;
 #pragma unroll 1
                 for (int j = 0; j < N; ++j) {
@@ -392,63 +427,15 @@ __global__ void __maxnreg__(BandBdfLayout<M>::MAXNREG) dsb_band_bdf_solve_dense_
                     for (int r = 0; r < LDAB; ++r) {
                         const int i = j + r - KV;
                         double v = 0.0;
-                        if (r >= KL && i >= 0 && i < N) v = GJ(j, r - KL) * mc + ((i == j) ? 1.0 : 0.0);
+                        if (r >= KL && i >= 0 && i < N) {
+                            if constexpr (M::HAS_MASS) v = GJ(j, r - KL) * mc + GM(j, r - KL);
+                            else v = GJ(j, r - KL) * mc + ((i == j) ? 1.0 : 0.0);
+                        }
                         GAB(j, r) = v;
                     }
                 }
-                // band LU, dgbtf2 convention (dsb_coop.cuh:warp_band_factor, one lane instead of one warp)
-                int jlast = 0;                                   // last column touched by the fill-in so far
-#pragma unroll 1
-                for (int j = 0; j < N; ++j) {
-                    const int km = (KL < N - 1 - j) ? KL : (N - 1 - j);
-                    double colv[KL + 1];
-#pragma unroll
-                    for (int d = 0; d <= KL; ++d) colv[d] = (d <= km) ? GAB(j, KV + d) : 0.0;
-                    int jp = 0;
-                    double best = -1.0;
-#pragma unroll
-                    for (int d = 0; d <= KL; ++d) {
-                        const double av = dsb_abs(colv[d]);
-                        if (d <= km && av == av && av > best) { best = av; jp = d; }     // first maximum, NaNs never win
-                    }
-                    if (colv[0] != colv[0]) jp = 0;                  // a NaN diagonal keeps the diagonal
-                    double diag = colv[0];
-#pragma unroll
-                    for (int d = 1; d <= KL; ++d) if (jp == d) diag = colv[d];
-                    if (diag == 0.0) { GPIV(j) = 0.0; continue; }
-                    GPIV(j) = (double)jp;
-                    { const int cand = (j + KU + jp < N - 1) ? (j + KU + jp) : (N - 1); if (cand > jlast) jlast = cand; }
-                    if (jp != 0) {
-#pragma unroll
-                        for (int q = 0; q <= KV; ++q) {              // columns j .. jlast (at most kv + 1 of them)
-                            const int cq = j + q;
-                            if (cq <= jlast) {
-                                const double a = GAB(cq, KV - q), b = GAB(cq, KV - q + jp);
-                                GAB(cq, KV - q) = b; GAB(cq, KV - q + jp) = a;
-                            }
-                        }
-#pragma unroll
-                        for (int d = 0; d <= KL; ++d) {              // the register copy of column j follows the interchange
-                            const double a = colv[0];
-                            if (jp == d && d != 0) { colv[0] = colv[d]; colv[d] = a; }
-                        }
-                    }
-                    if (km > 0) {
-                        const double inv_diag = 1.0 / colv[0];
-#pragma unroll
-                        for (int d = 1; d <= KL; ++d) if (d <= km) { colv[d] *= inv_diag; GAB(j, KV + d) = colv[d]; }
-#pragma unroll
-                        for (int q = 1; q <= KV; ++q) {              // columns j + 1 .. jlast
-                            const int cq = j + q;
-                            if (cq <= jlast) {
-                                const double mpk = -GAB(cq, KV - q);
-#pragma unroll
-                                for (int d = 1; d <= KL; ++d)
-                                    if (d <= km) GAB(cq, KV - q + d) = mpk * colv[d] + GAB(cq, KV - q + d);
-                            }
-                        }
-                    }
-                }
+                // band LU, dgbtf2 convention (dsb_band_lu.cuh)
+                BLU::factor(g, LS, Lay::O_LU, Lay::O_PIV);
             }
             state = after_jac;
         }
@@ -561,61 +548,25 @@ __global__ void __maxnreg__(BandBdfLayout<M>::MAXNREG) dsb_band_bdf_solve_dense_
 
         // ================= NEWTON: one iteration (newton.rs:13-36, line_search.rs:48-69) =====================================
         if (__any_sync(0xffffffffu, state == L_NEWTON) && state == L_NEWTON) {
-            // delta = F(y) = (y + psi - y0) - c f(t, y)   (op/bdf.rs:240-256, identity mass)
+            // delta = F(y) = M (y + psi - y0) - c f(t, y)   (op/bdf.rs:240-256)
             const double mc = -c;
+            if constexpr (M::HAS_MASS) {
+#pragma unroll 4
+                for (int i = 0; i < N; ++i) GTMP(i) = GYC(i) + GPSI(i);
 #pragma unroll 2
-            for (int i = 0; i < N; ++i) {
-                const double f = M::rhs_i(i, vYC, pl, t_predict);
-                GDL(i) = (GYC(i) + GPSI(i)) + mc * f;
+                for (int i = 0; i < N; ++i) {
+                    const double f = M::rhs_i(i, vYC, pl, t_predict);
+                    GDL(i) = M::mass_i(i, vTMP, pl, t_predict, mc, f);       // gemv_inplace(x, t, beta, y): y = M x + beta y
+                }
+            } else {
+#pragma unroll 2
+                for (int i = 0; i < N; ++i) {
+                    const double f = M::rhs_i(i, vYC, pl, t_predict);
+                    GDL(i) = (GYC(i) + GPSI(i)) + mc * f;
+                }
             }
             st.v[DSB_STAT_RHS_CALLS] += 1;
-            // forward substitution with the interchanges interleaved; b[j .. j + kl] travels in registers
-            {
-                double w[KL + 1];
-#pragma unroll
-                for (int d = 0; d <= KL; ++d) w[d] = GDL(d);
-#pragma unroll 2
-                for (int j = 0; j + 1 < N; ++j) {
-                    const int jp = (int)GPIV(j);
-                    if (jp != 0) {
-                        const double a = w[0];
-#pragma unroll
-                        for (int d = 1; d <= KL; ++d) if (jp == d) { w[0] = w[d]; w[d] = a; }
-                    }
-                    const double bj = w[0];
-                    GDL(j) = bj;
-                    const double nbj = -bj;
-                    const int lm = (KL < N - 1 - j) ? KL : (N - 1 - j);
-#pragma unroll
-                    for (int d = 1; d <= KL; ++d) if (d <= lm) w[d] = nbj * GAB(j, KV + d) + w[d];
-#pragma unroll
-                    for (int d = 0; d < KL; ++d) w[d] = w[d + 1];
-                    w[KL] = (j + 1 + KL < N) ? GDL(j + 1 + KL) : 0.0;
-                }
-                GDL(N - 1) = w[0];
-            }
-            // back substitution, column-axpy form; b[i - kv .. i] travels in registers
-            bool ok = true;
-            {
-                double w[KV + 1];
-#pragma unroll
-                for (int e = 0; e <= KV; ++e) w[e] = GDL(N - 1 - e);
-#pragma unroll 2
-                for (int i = N - 1; i >= 0; --i) {
-                    const double diag = GAB(i, KV);
-                    if (diag == 0.0) ok = false;
-                    if (ok) {
-                        const double coeff = DSB_DIV(w[0], diag);
-                        GDL(i) = coeff;
-                        const double ncoeff = -coeff;
-#pragma unroll
-                        for (int e = 1; e <= KV; ++e) if (i - e >= 0) w[e] = ncoeff * GAB(i, KV - e) + w[e];
-                    }
-#pragma unroll
-                    for (int e = 0; e < KV; ++e) w[e] = w[e + 1];
-                    w[KV] = (i - 1 - KV >= 0) ? GDL(i - 1 - KV) : 0.0;
-                }
-            }
+            const bool ok = BLU::solve(g, LS, Lay::O_LU, Lay::O_PIV, Lay::O_DL);
             if (!ok) {
                 newton_ok = false; state = L_POST;              // LuSolveFailed
             } else {
@@ -728,5 +679,7 @@ __global__ void __maxnreg__(BandBdfLayout<M>::MAXNREG) dsb_band_bdf_solve_dense_
 #undef GJ
 #undef GAB
 #undef GPIV
+#undef GM
+#undef GTMP
 #undef DSB_DIV
 }

@@ -1,9 +1,11 @@
 // dsb_inst.cu -- instantiates the lane kernels for ONE equation set: compile with -DDSB_INST=<model id>.
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 #include <vector>
 
 #include "dsb_band_bdf_kernel.cuh"
+#include "dsb_band_init_kernel.cuh"
 #include "dsb_bdf_kernel.cuh"
 #include "dsb_coop_bdf_kernel.cuh"
 #include "dsb_host_setup.h"
@@ -99,8 +101,7 @@ static cudaError_t launch_coop_bdf(const DsbProblemArgs* pa, const DsbBatchBuffe
 
 // banded lane kernel (one thread per instance, state in global memory): component-wise models without a mass
 // matrix that declare a band, n > 16
-constexpr bool kBandCapable = dsb_declares_band<InstModel>::value && dsb_is_componentwise<InstModel>::value &&
-                              !InstModel::HAS_MASS && InstModel::N > 16;
+constexpr bool kBandCapable = dsb_declares_band<InstModel>::value && dsb_is_componentwise<InstModel>::value && InstModel::N > 16;
 
 template <class M, bool BAND> struct BandLauncher {
     static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, cudaStream_t, cudaEvent_t, unsigned long long*, DsbCoopState*,
@@ -111,7 +112,7 @@ template <class M, bool BAND> struct BandLauncher {
 template <class M> struct BandLauncher<M, true> {
     static cudaError_t run(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, cudaStream_t stream, cudaEvent_t mid,
                            unsigned long long* work_counter, DsbCoopState* coop, const double* atol_host, int* launches) {
-        typedef BandBdfLayout<M> Lay;
+        typedef BandBdfLayout<M, DSB_BAND_THREADS> Lay;
         constexpr int N = M::N;
         // sparsity pattern by NaN probe (jacobian/mod.rs:16-48): the declared band must cover it.  Per column: colour
         // (greedy colouring computed by the caller, or one colour per column for the dense assembly, which stores
@@ -142,14 +143,29 @@ template <class M> struct BandLauncher<M, true> {
         e = cudaStreamSynchronize(stream);              // the host vectors die with this frame
         if (e != cudaSuccess) return e;
         const DsbBandMeta meta{coop->atol_dev, (const int32_t*)coop->color_dev};
-        const int threads = Lay::THREADS;
-        const size_t smem = (size_t)Lay::SMEM_WORDS * threads * sizeof(double);
-        e = cudaFuncSetAttribute(dsb_band_bdf_solve_dense_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int dev = 0, sms = 0, per_sm = 0;
+        int dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dsb_band_bdf_solve_dense_kernel<M>, threads, smem);
+        // a batch that does not fill one big block per SM is spread over the SMs in small blocks
+        bool small = (pa->nbatch + DSB_BAND_THREADS - 1) / DSB_BAND_THREADS < sms;
+        if (const char* q = getenv("DSB_BAND_BLOCK")) {           // test / tuning hook: force the block shape
+            const int v = atoi(q);
+            if (v == DSB_BAND_THREADS) small = false; else if (v == DSB_BAND_THREADS_SMALL) small = true;
+        }
+        if (small)
+            return launch<DSB_BAND_THREADS_SMALL>(pa, bb, stream, mid, work_counter, coop, meta, sms, launches);
+        return launch<DSB_BAND_THREADS>(pa, bb, stream, mid, work_counter, coop, meta, sms, launches);
+    }
+    template <int T>
+    static cudaError_t launch(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, cudaStream_t stream, cudaEvent_t mid,
+                              unsigned long long* work_counter, DsbCoopState* coop, const DsbBandMeta& meta, int sms, int* launches) {
+        typedef BandBdfLayout<M, T> Lay;
+        const int threads = Lay::THREADS;
+        const size_t smem = (size_t)Lay::SMEM_WORDS * threads * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(dsb_band_bdf_solve_dense_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dsb_band_bdf_solve_dense_kernel<M, T>, threads, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         const int64_t want = (pa->nbatch + threads - 1) / threads;
@@ -166,8 +182,12 @@ template <class M> struct BandLauncher<M, true> {
         }
         e = cudaMemsetAsync(work_counter, 0, 32 * sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return e;
+        if constexpr (M::HAS_MASS) {        // consistent initialisation of the DAE on the same lanes and workspace
+            dsb_band_init_kernel<M, T><<<grid, threads, 0, stream>>>(*pa, *bb, meta, (double*)coop->ws_mem);
+            *launches += 1;
+        }
         if (mid) cudaEventRecord(mid, stream);
-        dsb_band_bdf_solve_dense_kernel<M><<<grid, threads, smem, stream>>>(*pa, *bb, meta, (double*)coop->ws_mem, work_counter);
+        dsb_band_bdf_solve_dense_kernel<M, T><<<grid, threads, smem, stream>>>(*pa, *bb, meta, (double*)coop->ws_mem, work_counter);
         *launches += 1;
         return cudaGetLastError();
     }

@@ -229,6 +229,7 @@ struct ModelHeat1dDae {
     static constexpr int N = NS, NP = 3;
     static constexpr bool HAS_MASS = true;
     static constexpr bool COMPONENTWISE = true;
+    static constexpr int BAND_KL = 1, BAND_KU = 1;      // df/dy tridiagonal, M diagonal
     DSB_HD static double coef() { return 0.1 * (double)((NS - 1) * (NS - 1)); }
     template <class X>
     DSB_HD static double rhs_i(int i, const X& x, const double*, double) {

@@ -1,6 +1,7 @@
 """GPU parity tests of the banded thread-per-instance BDF path (dsb_band_bdf_kernel.cuh: state in global memory,
 band LU per lane): the single-particle battery model of BASELINE config 5 against the oracle's DENSE LU, with and
-without Jacobian colouring, and against the block-per-instance path."""
+without Jacobian colouring, and against the block-per-instance path; the heat-equation DAE of BASELINE config 4
+(singular mass: consistent initialisation by dsb_band_init_kernel.cuh, M - cJ in band storage)."""
 import numpy as np
 import pytest
 
@@ -20,8 +21,19 @@ def spm_currents(B):
     return (0.6 + 0.8 * sweeps.uniform(np.arange(B), 0)).reshape(-1, 1)
 
 
+def heat_params(B):
+    from diffsol_b200 import sweeps
+    i = np.arange(B)
+    return np.stack([1.0 + sweeps.uniform(i, 0), 0.1 + 0.3 * sweeps.uniform(i, 1), 0.6 + 0.3 * sweeps.uniform(i, 2)], axis=1)
+
+
+HEAT_T_EVAL = np.arange(1, 101) / 100.0 * 0.99
+
+
+@pytest.mark.parametrize("block", ["768", "128"])
 @pytest.mark.parametrize("coloring", [False, True])
-def test_spm_band_bit_exact(dsb, oracle, coloring):
+def test_spm_band_bit_exact(dsb, oracle, coloring, block, monkeypatch):
+    monkeypatch.setenv("DSB_BAND_BLOCK", block)           # both block shapes of the kernel (big batches / small batches)
     """Counters, status and states bit-identical to the oracle (dense partial-pivoting LU restated from nalgebra):
     the band LU only skips operations whose multiplier or pivot-row entry is exactly zero."""
     B = 700                      # more than one warp per block, ragged tail
@@ -103,3 +115,36 @@ def test_band_execution_rejected_where_it_does_not_apply(dsb):
     prob = dsb.OdeBuilder().rhs_implicit("robertson_ode").p(p).build()
     with pytest.raises(dsb.DiffsolB200Error):
         prob.bdf().set_execution("band").solve_dense([1.0])
+
+
+@pytest.mark.parametrize("block", ["768", "128"])
+@pytest.mark.parametrize("model,B,coloring", [("heat1d_dae_32", 200, False), ("heat1d_dae_32", 200, True),
+                                               ("heat1d_dae_256", 40, True)])
+def test_heat_dae_band_bit_exact(dsb, oracle, model, B, coloring, block, monkeypatch):
+    """BASELINE config 4 on the banded lane path: counters (including those of the consistent initialisation), status
+    and all 100 dense-output columns bit-identical to the oracle's dense LU."""
+    monkeypatch.setenv("DSB_BAND_BLOCK", block)
+    p = heat_params(B)
+    solver = (dsb.OdeBuilder().rhs_implicit(model).p(p).rtol(1e-6).atol(1e-6).use_coloring(coloring).build().bdf()
+              .set_execution("band"))
+    ys = solver.solve_dense(HEAT_T_EVAL)
+    desc = oracle.make_desc(model, powmode=1, rtol=1e-6, atol=1e-6, use_coloring=coloring)
+    ys_o, stats_o, status_o = oracle.batch_solve_dense(desc, p, HEAT_T_EVAL)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o)
+    assert (ys[:, -1].max(axis=1) < p[:, 0]).all()
+
+
+def test_heat_dae_band_equals_block_per_instance_and_is_default(dsb):
+    B = 64
+    p = heat_params(B)
+    prob = dsb.OdeBuilder().rhs_implicit("heat1d_dae_256").p(p).rtol(1e-6).atol(1e-6).build()
+    a = prob.bdf().set_execution("band")
+    b = prob.bdf().set_execution("block")
+    ya, yb = a.solve_dense(HEAT_T_EVAL), b.solve_dense(HEAT_T_EVAL)
+    assert np.array_equal(ya, yb)
+    assert np.array_equal(a.statistics_array(), b.statistics_array())
+    c = prob.bdf()
+    assert np.array_equal(c.solve_dense(HEAT_T_EVAL), ya)
+    assert c.last_launch_count() == a.last_launch_count()

@@ -74,7 +74,7 @@ def test_heat_dae_sweep_bit_exact(dsb, oracle, model, B):
     """BASELINE config 4 (1-D heat equation, boundary rows algebraic, initial-condition sweep) at sizes the
     oracle finishes in seconds: counters, status and all 100 dense-output columns bitwise."""
     p = heat_params(np.arange(B))
-    solver = dsb.OdeBuilder().rhs_implicit(model).p(p).rtol(1e-6).atol(1e-6).build().bdf()
+    solver = dsb.OdeBuilder().rhs_implicit(model).p(p).rtol(1e-6).atol(1e-6).build().bdf().set_execution("block")
     ys = solver.solve_dense(HEAT_T_EVAL)
     desc = oracle.make_desc(model, powmode=1, rtol=1e-6, atol=1e-6)
     ys_o, stats_o, status_o = oracle.batch_solve_dense(desc, p, HEAT_T_EVAL)

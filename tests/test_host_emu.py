@@ -58,3 +58,17 @@ def test_band_bdf_lane_kernel_on_host(oracle, model, B, coloring):
     r, *o = run_both(oracle, model, spm_currents(B), np.arange(1, 7) * 600.0, kernel="band", use_coloring=coloring)
     assert (o[2] == 0).all()
     assert_same(r, *o)
+
+
+def heat_params(B):
+    i = np.arange(B)
+    return np.stack([1.0 + sweeps.uniform(i, 0), 0.1 + 0.3 * sweeps.uniform(i, 1), 0.6 + 0.3 * sweeps.uniform(i, 2)], axis=1)
+
+
+@pytest.mark.parametrize("model,B,coloring", [("heat1d_dae_32", 10, False), ("heat1d_dae_32", 10, True), ("heat1d_dae_256", 2, True)])
+def test_band_dae_kernels_on_host(oracle, model, B, coloring):
+    """Singular mass on the banded lane path: dsb_band_init_kernel (consistent initialisation) + the BDF kernel."""
+    r, *o = run_both(oracle, model, heat_params(B), np.arange(1, 101) / 100.0 * 0.99, kernel="band", use_coloring=coloring,
+                     rtol=1e-6, atol=1e-6)
+    assert (o[2] == 0).all()
+    assert_same(r, *o)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Time one BASELINE.json configuration other than the headline one (which bench.py owns) on one GPU:
-   python tools/bench_config.py heat256 [batch]   |  vdp [batch]  |  robertson_dae [batch]
+   python tools/bench_config.py heat256 [batch] [auto|block|band]  |  spm | spm99 | vdp | robertson_dae [batch]
 Prints ms per pass, instances/s, Newton-it/s and the algorithmic-byte HBM roofline fraction."""
 import json
 import os
@@ -25,6 +25,8 @@ if which.startswith("heat"):
     t_eval = np.arange(1, 101) / 100.0 * 0.99
     prob = ds.OdeBuilder().rhs_implicit("heat1d_dae_%d" % n).p(p).rtol(1e-6).atol(1e-6).build()
     solver, npar, mass_words = prob.bdf(), 3, n * n
+    if len(sys.argv) > 3:
+        solver.set_execution(sys.argv[3])
 elif which in ("spm", "spm99"):
     n, npar, mass_words = (42 if which == "spm" else 200), 1, 0
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 250000
@@ -65,9 +67,10 @@ alg = (nli * (8 * (n * n + 4 * n + npar) + 4 * n) + setups * (8 * (2 * n * n + m
 # banded path (dsb_band_bdf_kernel.cuh): the same formula with the band storage it really reads (kl = ku = 1):
 # factors (2kl+ku+1) n + n pivots, Jacobian (kl+ku+1) n
 band = None
-if which in ("spm", "spm99"):
+if which in ("spm", "spm99") or which.startswith("heat"):
     ldab, ldj = 4, 3
-    band = (nli * 8 * (ldab * n + n + 4 * n + npar) + setups * 8 * (ldj * n + ldab * n + n)
+    band_mass = ldj * n if which.startswith("heat") else 0
+    band = (nli * 8 * (ldab * n + n + 4 * n + npar) + setups * 8 * (ldj * n + band_mass + ldab * n + n)
             + me * 8 * (ldj * n + n + npar) + attempts * 8 * 19 * n + B * nt * 8 * n)
 print(json.dumps({"config": which, "n": n, "batch": B, "kernel_ms": kms, "e2e_ms": min(t for t, _ in times[1:]) * 1e3,
                   "instances_per_s": B / kms * 1e3, "newton_iters_per_s": nli / kms * 1e3,
