@@ -30,6 +30,14 @@
 #define DSB_BAND_THREADS 768        // 24 warps at 80 registers: 1.16x over 16 warps at 128 (latency bound on global loads); 32 warps spill too much
 #endif
 #define DSB_BAND_THREADS_SMALL 128  // batches that do not fill one 768-lane block per SM are spread over the SMs in small blocks
+#ifndef DSB_BAND_UNROLL_SMALL
+#define DSB_BAND_UNROLL_SMALL 8     // vector loops of the small-block variant: few resident warps, so the memory-level
+#endif                              // parallelism has to come from independent loads of ONE lane (255 registers available)
+// unroll factors of the component loops (U2: loops that evaluate the equations, U4: plain vector loops)
+template <int T> struct BandUnroll {
+    static constexpr int U2 = T <= DSB_BAND_THREADS_SMALL ? DSB_BAND_UNROLL_SMALL : 2;
+    static constexpr int U4 = T <= DSB_BAND_THREADS_SMALL ? 2 * DSB_BAND_UNROLL_SMALL : 4;
+};
 
 template <class M, int T = DSB_BAND_THREADS>
 struct BandBdfLayout {
@@ -90,7 +98,8 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                                                                   double* __restrict__ ws,
                                                                   unsigned long long* __restrict__ work_counter) {
     typedef BandBdfLayout<M, T> Lay;
-    typedef LaneBandLU<M::N, Lay::KL, Lay::KU, DsbDivShared> BLU;
+    constexpr int U2 = BandUnroll<T>::U2, U4 = BandUnroll<T>::U4;
+    typedef LaneBandLU<M::N, Lay::KL, Lay::KU, DsbDivShared, U2> BLU;
     constexpr int N = Lay::N, NP = Lay::NP, KL = Lay::KL, KU = Lay::KU, KV = Lay::KV, LDJ = Lay::LDJ, LDAB = Lay::LDAB;
     extern __shared__ double dsb_lane_smem[];
     double* const sm = dsb_lane_smem + threadIdx.x;
@@ -171,7 +180,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
     // terms are added in index order, the loads do not depend on the sum and run ahead of it
     auto weighted_norm = [&](int ox, int oref) -> double {
         double acc = 0.0;
-#pragma unroll 4
+#pragma unroll U4
         for (int i = 0; i < N; ++i) {
             const double term = DSB_DIV(G(ox + i), dsb_abs(G(oref + i)) * pa.rtol + meta.atol[i]);
             acc += term * term;
@@ -211,13 +220,13 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                     // (state.rs:84-162)
 #pragma unroll
                     for (int k = 0; k < DSB_NSTATS; ++k) st.v[k] = bb.stats[(int64_t)k * B + inst];
-#pragma unroll 2
+#pragma unroll U2
                     for (int i = 0; i < N; ++i) { GY(i) = bb.y0[(int64_t)i * B + inst]; GD(1, i) = bb.dy0[(int64_t)i * B + inst]; }
                 } else {
                     // y = init(p, t0); dy = f(y, t0)     (state.rs:1086-1124); dy is kept in D[1] until h is known
-#pragma unroll 2
+#pragma unroll U2
                     for (int i = 0; i < N; ++i) GY(i) = M::init_i(i, pl, pa.t0);
-#pragma unroll 2
+#pragma unroll U2
                     for (int i = 0; i < N; ++i) GD(1, i) = M::rhs_i(i, vY, pl, pa.t0);
                     st.v[DSB_STAT_RHS_CALLS] += 1;
                 }
@@ -227,10 +236,10 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                     const double d0 = dsb_sqrt(weighted_norm(Lay::O_Y, Lay::O_Y));
                     const double d1 = dsb_sqrt(weighted_norm(Lay::O_D + N, Lay::O_Y));
                     const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * DSB_DIV(d0, d1);
-#pragma unroll 2
+#pragma unroll U2
                     for (int i = 0; i < N; ++i) GYC(i) = is_neg_h ? (GD(1, i) * (-h0) + GY(i)) : (GD(1, i) * h0 + GY(i));
                     const double t1 = is_neg_h ? pa.t0 - h0 : pa.t0 + h0;
-#pragma unroll 2
+#pragma unroll U2
                     for (int i = 0; i < N; ++i) GDL(i) = M::rhs_i(i, vYC, pl, t1) - GD(1, i);
                     st.v[DSB_STAT_RHS_CALLS] += 1;
                     const double d2 = DSB_DIV(dsb_sqrt(weighted_norm(Lay::O_DL, Lay::O_Y)), dsb_abs(h0));
@@ -491,7 +500,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                     }
                     tf[j] = time_factor;
                 }
-#pragma unroll 2
+#pragma unroll U2
                 for (int i = 0; i < N; ++i) {
                     double yo = GD(0, i);
 #pragma unroll
@@ -514,7 +523,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
             if (repredict) {
                 const int ord = order;
                 const double a = pa.tab.alpha[ord];
-#pragma unroll 2
+#pragma unroll U2
                 for (int i = 0; i < N; ++i) {
                     double yp = 0.0;
                     double ps = 0.0;
@@ -533,7 +542,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                 }
                 t_predict = t + h;
             } else {
-#pragma unroll 4
+#pragma unroll U4
                 for (int i = 0; i < N; ++i) GYC(i) = GYP(i);
             }
             state = L_NEWTON;
@@ -551,15 +560,15 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
             // delta = F(y) = M (y + psi - y0) - c f(t, y)   (op/bdf.rs:240-256)
             const double mc = -c;
             if constexpr (M::HAS_MASS) {
-#pragma unroll 4
+#pragma unroll U4
                 for (int i = 0; i < N; ++i) GTMP(i) = GYC(i) + GPSI(i);
-#pragma unroll 2
+#pragma unroll U2
                 for (int i = 0; i < N; ++i) {
                     const double f = M::rhs_i(i, vYC, pl, t_predict);
                     GDL(i) = M::mass_i(i, vTMP, pl, t_predict, mc, f);       // gemv_inplace(x, t, beta, y): y = M x + beta y
                 }
             } else {
-#pragma unroll 2
+#pragma unroll U2
                 for (int i = 0; i < N; ++i) {
                     const double f = M::rhs_i(i, vYC, pl, t_predict);
                     GDL(i) = (GYC(i) + GPSI(i)) + mc * f;
@@ -571,7 +580,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                 newton_ok = false; state = L_POST;              // LuSolveFailed
             } else {
                 double acc = 0.0;
-#pragma unroll 4
+#pragma unroll U4
                 for (int i = 0; i < N; ++i) {
                     const double dl = GDL(i);
                     GYC(i) = GYC(i) - dl;
@@ -609,7 +618,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                 const int ord = order;
                 {   // error_control: ||d||^2_w(state.y) * error_const2[order - 1], d = y - y_predict
                     double acc = 0.0;
-#pragma unroll 4
+#pragma unroll U4
                     for (int i = 0; i < N; ++i) {
                         const double d = GYC(i) - GYP(i);
                         const double term = DSB_DIV(d, dsb_abs(GY(i)) * pa.rtol + meta.atol[i]);
@@ -623,7 +632,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                 safety = DSB_DIV(0.9 * (2.0 * maxiter + 1.0), 2.0 * maxiter + niter);
                 if (error_norm <= 1.0) {
                     // ---- accepted: _update_diff, state.y <- PREDICTOR (quirk Q1) ----
-#pragma unroll 2
+#pragma unroll U2
                     for (int i = 0; i < N; ++i) {
                         const double yp = GYP(i);
                         const double d = GYC(i) - yp;

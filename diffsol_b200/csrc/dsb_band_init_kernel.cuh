@@ -21,7 +21,8 @@ __global__ void __launch_bounds__(T) dsb_band_init_kernel(const __grid_constant_
                                                           const __grid_constant__ DsbBandMeta meta,
                                                           double* __restrict__ ws) {
     typedef BandBdfLayout<M, T> Lay;
-    typedef LaneBandLU<M::N, Lay::KL, Lay::KU, DsbDivInline> BLU;
+    constexpr int U2 = BandUnroll<T>::U2, U4 = BandUnroll<T>::U4;
+    typedef LaneBandLU<M::N, Lay::KL, Lay::KU, DsbDivInline, U2> BLU;
     constexpr int N = Lay::N, NP = Lay::NP, KL = Lay::KL, KU = Lay::KU, KV = Lay::KV, LDJ = Lay::LDJ, LDAB = Lay::LDAB;
     // the integrator's words, reused: y, dy (D[1]), x = (du, v) iterate, yerr, delta, x0, delta0, InitOp.y0
     constexpr int O_YV = Lay::O_Y, O_DY = Lay::O_D + N, O_X = Lay::O_YC, O_YERR = Lay::O_YP, O_DELTA = Lay::O_DL,
@@ -45,16 +46,16 @@ __global__ void __launch_bounds__(T) dsb_band_init_kernel(const __grid_constant_
         // ||x||^2_w(ref) over words of the lane's column (vector/nalgebra_serial.rs:395-408)
         auto weighted_norm = [&](int ox, int oref) -> double {
             double acc = 0.0;
-#pragma unroll 4
+#pragma unroll U4
             for (int i = 0; i < N; ++i) {
                 const double term = G(ox + i) / (dsb_abs(G(oref + i)) * pa.rtol + meta.atol[i]);
                 acc += term * term;
             }
             return acc / (double)N;
         };
-#pragma unroll 2
+#pragma unroll U2
         for (int i = 0; i < N; ++i) G(O_YV + i) = M::init_i(i, pl, t0);
-#pragma unroll 2
+#pragma unroll U2
         for (int i = 0; i < N; ++i) G(O_DY + i) = M::rhs_i(i, vY, pl, t0);
         st.v[DSB_STAT_RHS_CALLS] += 1;
 
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(T) dsb_band_init_kernel(const __grid_constant_
             };
             // fun(x) -> delta: y0[alg] = x[alg]; out = f(y0, t0); out = neg_mass x + out (column sweep: ascending j)
             auto fun = [&]() {
-#pragma unroll 2
+#pragma unroll U2
                 for (int i = 0; i < N; ++i) if (is_alg(i)) G(O_Y0W + i) = G(O_X + i);
 #pragma unroll 1
                 for (int i = 0; i < N; ++i) {
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(T) dsb_band_init_kernel(const __grid_constant_
                 }
                 st.v[DSB_STAT_RHS_CALLS] += 1;
             };
-#pragma unroll 2
+#pragma unroll U2
             for (int i = 0; i < N; ++i) {
                 const double v = is_alg(i) ? G(O_YV + i) : G(O_DY + i);
                 G(O_X + i) = v; G(O_YERR + i) = v; G(O_Y0W + i) = G(O_YV + i);
@@ -159,13 +160,13 @@ __global__ void __launch_bounds__(T) dsb_band_init_kernel(const __grid_constant_
                             if (!BLU::solve(g, LS, Lay::O_LU, Lay::O_PIV, O_DELTA)) { result = 2; break; }
                             ls_norm = dsb_sqrt(weighted_norm(O_DELTA, O_YERR));
                             if (conv.check_norm(ls_norm) == LANE_CONVERGED) {
-#pragma unroll 4
+#pragma unroll U4
                                 for (int i = 0; i < N; ++i) G(O_X + i) -= G(O_DELTA + i);
                                 res = LANE_CONVERGED; have_res = true;
                             }
                         }
                         if (!have_res) {
-#pragma unroll 4
+#pragma unroll U4
                             for (int i = 0; i < N; ++i) { G(O_X0 + i) = G(O_X + i); G(O_DELTA0 + i) = G(O_DELTA + i); }
                             const double norm = ls_norm;
                             const double phi0 = norm * norm * 0.5, two_phi0 = norm * norm;
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(T) dsb_band_init_kernel(const __grid_constant_
                             double alpha = 1.0;
                             int ls_status = 1;
                             for (int li = 0; li < ls_max_iter; ++li) {
-#pragma unroll 4
+#pragma unroll U4
                                 for (int q = 0; q < N; ++q) G(O_X + q) = (-alpha) * G(O_DELTA0 + q) + G(O_X + q);
                                 fun();
                                 if (!BLU::solve(g, LS, Lay::O_LU, Lay::O_PIV, O_DELTA)) { ls_status = 2; break; }
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(T) dsb_band_init_kernel(const __grid_constant_
                                 }
                                 if (alpha < min_alpha) { ls_status = 2; break; }
                                 alpha *= tau;
-#pragma unroll 4
+#pragma unroll U4
                                 for (int q = 0; q < N; ++q) G(O_X + q) = G(O_X0 + q);
                             }
                             if (ls_status != 0) { result = 2; break; }
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(T) dsb_band_init_kernel(const __grid_constant_
                     } else {
                         fun();
                         if (!BLU::solve(g, LS, Lay::O_LU, Lay::O_PIV, O_DELTA)) { result = 2; break; }
-#pragma unroll 4
+#pragma unroll U4
                         for (int i = 0; i < N; ++i) G(O_X + i) -= G(O_DELTA + i);
                         res = conv.check_new_iteration(dsb_sqrt(weighted_norm(O_DELTA, O_YERR)));
                     }
@@ -205,20 +206,20 @@ __global__ void __launch_bounds__(T) dsb_band_init_kernel(const __grid_constant_
                 if (result == 0) ok = true;
                 else if (result == 2) status = DSB_STATUS_INITIAL_CONDITION_DID_NOT_CONVERGE;
                 else {
-#pragma unroll 4
+#pragma unroll U4
                     for (int i = 0; i < N; ++i) G(O_YERR + i) = G(O_X + i);
                 }
             }
             if (!ok) status = DSB_STATUS_INITIAL_CONDITION_DID_NOT_CONVERGE;
             if (status == DSB_STATUS_OK) {
-#pragma unroll 2
+#pragma unroll U2
                 for (int i = 0; i < N; ++i) {
                     if (is_alg(i)) { G(O_YV + i) = G(O_X + i); G(O_DY + i) = 0.0; }
                     else G(O_DY + i) = G(O_X + i);
                 }
             }
         }
-#pragma unroll 2
+#pragma unroll U2
         for (int i = 0; i < N; ++i) {
             bb.y0[(int64_t)i * B + inst] = G(O_YV + i);
             bb.dy0[(int64_t)i * B + inst] = G(O_DY + i);

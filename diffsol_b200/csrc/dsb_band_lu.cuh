@@ -15,7 +15,7 @@
 #pragma once
 #include "dsb_lane.cuh"
 
-template <int N, int KL, int KU, class DIV>
+template <int N, int KL, int KU, class DIV, int U = 2>      // U: unroll factor of the substitution loops
 struct LaneBandLU {
     static constexpr int KV = KL + KU, LDAB = 2 * KL + KU + 1;
     static_assert(KL >= 1 && KL <= 2 && KU >= 1 && KU <= 2, "register windows are sized for kl, ku <= 2");
@@ -86,7 +86,7 @@ struct LaneBandLU {
             double w[KL + 1];
 #pragma unroll
             for (int d = 0; d <= KL; ++d) w[d] = GB_(d);
-#pragma unroll 2
+#pragma unroll U
             for (int j = 0; j + 1 < N; ++j) {
                 const int jp = (int)GPIV_(j);
                 if (jp != 0) {
@@ -112,7 +112,7 @@ struct LaneBandLU {
             double w[KV + 1];
 #pragma unroll
             for (int e = 0; e <= KV; ++e) w[e] = GB_(N - 1 - e);
-#pragma unroll 2
+#pragma unroll U
             for (int i = N - 1; i >= 0; --i) {
                 const double diag = GAB_(i, KV);
                 if (diag == 0.0) ok = false;

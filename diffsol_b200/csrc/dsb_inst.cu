@@ -6,6 +6,7 @@
 
 #include "dsb_band_bdf_kernel.cuh"
 #include "dsb_band_init_kernel.cuh"
+#include "dsb_band_sdirk_kernel.cuh"
 #include "dsb_bdf_kernel.cuh"
 #include "dsb_coop_bdf_kernel.cuh"
 #include "dsb_host_setup.h"
@@ -104,13 +105,13 @@ static cudaError_t launch_coop_bdf(const DsbProblemArgs* pa, const DsbBatchBuffe
 constexpr bool kBandCapable = dsb_declares_band<InstModel>::value && dsb_is_componentwise<InstModel>::value && InstModel::N > 16;
 
 template <class M, bool BAND> struct BandLauncher {
-    static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, cudaStream_t, cudaEvent_t, unsigned long long*, DsbCoopState*,
+    static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, int, cudaStream_t, cudaEvent_t, unsigned long long*, DsbCoopState*,
                            const double*, int*) {
         return cudaErrorNotSupported;
     }
 };
 template <class M> struct BandLauncher<M, true> {
-    static cudaError_t run(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, cudaStream_t stream, cudaEvent_t mid,
+    static cudaError_t run(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method, cudaStream_t stream, cudaEvent_t mid,
                            unsigned long long* work_counter, DsbCoopState* coop, const double* atol_host, int* launches) {
         typedef BandBdfLayout<M, DSB_BAND_THREADS> Lay;
         constexpr int N = M::N;
@@ -153,26 +154,29 @@ template <class M> struct BandLauncher<M, true> {
             if (v == DSB_BAND_THREADS) small = false; else if (v == DSB_BAND_THREADS_SMALL) small = true;
         }
         if (small)
-            return launch<DSB_BAND_THREADS_SMALL>(pa, bb, stream, mid, work_counter, coop, meta, sms, launches);
-        return launch<DSB_BAND_THREADS>(pa, bb, stream, mid, work_counter, coop, meta, sms, launches);
+            return launch<DSB_BAND_THREADS_SMALL>(pa, bb, method, stream, mid, work_counter, coop, meta, sms, launches);
+        return launch<DSB_BAND_THREADS>(pa, bb, method, stream, mid, work_counter, coop, meta, sms, launches);
     }
     template <int T>
-    static cudaError_t launch(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, cudaStream_t stream, cudaEvent_t mid,
+    static cudaError_t launch(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method, cudaStream_t stream, cudaEvent_t mid,
                               unsigned long long* work_counter, DsbCoopState* coop, const DsbBandMeta& meta, int sms, int* launches) {
-        typedef BandBdfLayout<M, T> Lay;
-        const int threads = Lay::THREADS;
-        const size_t smem = (size_t)Lay::SMEM_WORDS * threads * sizeof(double);
-        cudaError_t e = cudaFuncSetAttribute(dsb_band_bdf_solve_dense_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        typedef BandBdfLayout<M, T> LayB;
+        typedef BandSdirkLayout<M, T> LayS;
+        const bool bdf = method == DSB_METHOD_BDF;
+        const int threads = T;
+        const size_t smem = (size_t)(bdf ? LayB::SMEM_WORDS : LayS::SMEM_WORDS) * threads * sizeof(double);
+        const void* kernel = bdf ? (const void*)dsb_band_bdf_solve_dense_kernel<M, T> : (const void*)dsb_band_sdirk_solve_dense_kernel<M, T>;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dsb_band_bdf_solve_dense_kernel<M, T>, threads, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         const int64_t want = (pa->nbatch + threads - 1) / threads;
         const int64_t resident = (int64_t)sms * per_sm;
         const unsigned grid = (unsigned)(want < resident ? want : resident);
-        // workspace: one column of WORDS doubles per resident lane
-        const size_t need = (size_t)Lay::WORDS * grid * threads * sizeof(double);
+        // workspace: one column of WORDS doubles per resident lane (LayS::WORDS covers both kernels and the initialisation)
+        const size_t need = (size_t)LayS::WORDS * grid * threads * sizeof(double);
         if (coop->ws_bytes < need) {
             if (coop->ws_mem) cudaFree(coop->ws_mem);
             coop->ws_mem = nullptr; coop->ws_bytes = 0;
@@ -187,7 +191,8 @@ template <class M> struct BandLauncher<M, true> {
             *launches += 1;
         }
         if (mid) cudaEventRecord(mid, stream);
-        dsb_band_bdf_solve_dense_kernel<M, T><<<grid, threads, smem, stream>>>(*pa, *bb, meta, (double*)coop->ws_mem, work_counter);
+        if (bdf) dsb_band_bdf_solve_dense_kernel<M, T><<<grid, threads, smem, stream>>>(*pa, *bb, meta, (double*)coop->ws_mem, work_counter);
+        else dsb_band_sdirk_solve_dense_kernel<M, T><<<grid, threads, smem, stream>>>(*pa, *bb, meta, (double*)coop->ws_mem, work_counter);
         *launches += 1;
         return cudaGetLastError();
     }
@@ -261,9 +266,9 @@ template <class M> struct LaneLauncher<M, true> {
 cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method,
                                                  cudaStream_t stream, cudaEvent_t mid, unsigned long long* work_counter,
                                                  DsbCoopState* coop, const double* atol_host, int* launches) {
-    // exec_mode 3 / automatic: the banded lane kernel where the model qualifies (BDF, <= 64-bit pattern masks)
-    if (kBandCapable && method == DSB_METHOD_BDF && (coop->exec_mode == 3 || coop->exec_mode == 0)) {
-        const cudaError_t e = BandLauncher<InstModel, kBandCapable>::run(pa, bb, stream, mid, work_counter, coop, atol_host, launches);
+    // exec_mode 3 / automatic: the banded lane kernels where the model qualifies (BDF and (E)SDIRK)
+    if (kBandCapable && (coop->exec_mode == 3 || coop->exec_mode == 0)) {
+        const cudaError_t e = BandLauncher<InstModel, kBandCapable>::run(pa, bb, method, stream, mid, work_counter, coop, atol_host, launches);
         if (e != cudaErrorNotSupported || coop->exec_mode == 3) return e;
     } else if (coop->exec_mode == 3) {
         return cudaErrorNotSupported;

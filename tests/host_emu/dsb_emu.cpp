@@ -11,6 +11,7 @@
 #include "../../diffsol_b200/csrc/dsb_host_setup.h"
 #include "../../diffsol_b200/csrc/dsb_band_bdf_kernel.cuh"
 #include "../../diffsol_b200/csrc/dsb_band_init_kernel.cuh"
+#include "../../diffsol_b200/csrc/dsb_band_sdirk_kernel.cuh"
 #include "../../diffsol_b200/csrc/dsb_bdf_kernel.cuh"
 #include "../../diffsol_b200/csrc/dsb_init_kernel.cuh"
 #include "../../diffsol_b200/csrc/dsb_sdirk_kernel.cuh"
@@ -66,19 +67,18 @@ struct EmuCall {
                 }
             } else if (kernel == 3) {
                 if constexpr (dsb_declares_band<M>::value && dsb_is_componentwise<M>::value && N > 16) {
-                    if (method == DSB_METHOD_BDF) {
-                        constexpr int T = DSB_BAND_THREADS_SMALL;
-                        typedef BandBdfLayout<M, T> Lay;
-                        std::vector<int32_t> colmeta;
-                        if (!dsb_host::band_column_meta<M>(pa.t0, pa.use_coloring != 0, color_full.empty() ? nullptr : color_full.data(),
-                                                           Lay::KL, Lay::KU, &colmeta)) { rc = DSB_ERR; return; }
-                        const DsbBandMeta meta{atol_full.data(), colmeta.data()};
-                        blockDim.x = Lay::THREADS;
-                        std::vector<double> ws((size_t)Lay::WORDS * Lay::THREADS);
-                        if constexpr (M::HAS_MASS) dsb_band_init_kernel<M, T>(pa, bb, meta, ws.data());
-                        dsb_band_bdf_solve_dense_kernel<M, T>(pa, bb, meta, ws.data(), &work_counter);
-                        ran = true;
-                    }
+                    constexpr int T = DSB_BAND_THREADS_SMALL;
+                    typedef BandSdirkLayout<M, T> Lay;           // WORDS covers both kernels and the initialisation
+                    std::vector<int32_t> colmeta;
+                    if (!dsb_host::band_column_meta<M>(pa.t0, pa.use_coloring != 0, color_full.empty() ? nullptr : color_full.data(),
+                                                       Lay::KL, Lay::KU, &colmeta)) { rc = DSB_ERR; return; }
+                    const DsbBandMeta meta{atol_full.data(), colmeta.data()};
+                    blockDim.x = Lay::THREADS;
+                    std::vector<double> ws((size_t)Lay::WORDS * Lay::THREADS);
+                    if constexpr (M::HAS_MASS) dsb_band_init_kernel<M, T>(pa, bb, meta, ws.data());
+                    if (method == DSB_METHOD_BDF) dsb_band_bdf_solve_dense_kernel<M, T>(pa, bb, meta, ws.data(), &work_counter);
+                    else dsb_band_sdirk_solve_dense_kernel<M, T>(pa, bb, meta, ws.data(), &work_counter);
+                    ran = true;
                 }
             }
             if (!ran) { rc = DSB_ERR; return; }

@@ -148,3 +148,42 @@ def test_heat_dae_band_equals_block_per_instance_and_is_default(dsb):
     c = prob.bdf()
     assert np.array_equal(c.solve_dense(HEAT_T_EVAL), ya)
     assert c.last_launch_count() == a.last_launch_count()
+
+
+@pytest.mark.parametrize("method", ["tr_bdf2", "esdirk34"])
+@pytest.mark.parametrize("model,B,coloring,block", [("spm", 300, False, "768"), ("spm", 300, True, "128"),
+                                                     ("spm99", 40, True, "768"), ("heat1d_dae_32", 200, False, "128"),
+                                                     ("heat1d_dae_256", 24, True, "768")])
+def test_band_sdirk_bit_exact(dsb, oracle, method, model, B, coloring, block, monkeypatch):
+    """(E)SDIRK on the banded lane path (dsb_band_sdirk_kernel.cuh), ODE and singular-mass DAE: counters, status and
+    states bit-identical to the oracle's dense LU."""
+    monkeypatch.setenv("DSB_BAND_BLOCK", block)
+    if model.startswith("spm"):
+        p, t_eval, tol = spm_currents(B), np.arange(1, 13) * 300.0, dict(rtol=1e-6, atol=1e-6)
+    else:
+        p, t_eval, tol = heat_params(B), HEAT_T_EVAL, dict(rtol=1e-6, atol=1e-6)
+    prob = dsb.OdeBuilder().rhs_implicit(model).p(p).rtol(tol["rtol"]).atol(tol["atol"]).use_coloring(coloring).build()
+    solver = getattr(prob, method)().set_execution("band")
+    ys = solver.solve_dense(t_eval)
+    desc = oracle.make_desc(model, method=method, powmode=1, use_coloring=coloring, **tol)
+    ys_o, stats_o, status_o = oracle.batch_solve_dense(desc, p, t_eval)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o)
+
+
+def test_band_sdirk_free_running_and_default_path(dsb, oracle):
+    """step()/interpolate() loop without a stop time; automatic selection picks the banded kernel for SDIRK too."""
+    B = 64
+    p = spm_currents(B)
+    t_pts = np.arange(1, 7) * 500.0
+    solver = dsb.OdeBuilder().rhs_implicit("spm").p(p).build().tr_bdf2()
+    ys = solver.step_and_interpolate(t_pts)
+    n, np_, _ = oracle.model_dims("spm")
+    desc = oracle.make_desc("spm", method="tr_bdf2", powmode=1)
+    for b in (0, 17, 63):
+        rc, ys_o, stats_o, _ = oracle.harness(desc, p[b], t_pts)
+        assert rc == 0
+        assert np.array_equal(ys[b], ys_o)
+        st = solver.get_statistics(b)
+        assert all(st[k] == v for k, v in stats_o.items())

@@ -89,7 +89,7 @@ def test_unsupported_combinations_fail_loudly(dsb):
     p = heat_params(np.arange(2))
     prob = dsb.OdeBuilder().rhs_implicit("heat1d_dae_32").p(p).build()
     with pytest.raises(dsb.DiffsolB200Error):
-        prob.tr_bdf2().solve_dense([0.5])           # SDIRK has no block-per-instance kernel yet
+        prob.tr_bdf2().set_execution("block").solve_dense([0.5])           # SDIRK has no block-per-instance kernel
     with pytest.raises(dsb.DiffsolB200Error):
         prob.bdf().set_execution("lane").solve_dense([0.5])
 

@@ -72,3 +72,16 @@ def test_band_dae_kernels_on_host(oracle, model, B, coloring):
                      rtol=1e-6, atol=1e-6)
     assert (o[2] == 0).all()
     assert_same(r, *o)
+
+
+@pytest.mark.parametrize("method", ["tr_bdf2", "esdirk34"])
+@pytest.mark.parametrize("model,B,coloring", [("spm", 8, False), ("spm", 8, True), ("spm99", 2, True),
+                                               ("heat1d_dae_32", 8, False), ("heat1d_dae_256", 2, True)])
+def test_band_sdirk_kernel_on_host(oracle, method, model, B, coloring):
+    if model.startswith("spm"):
+        p, t_eval = spm_currents(B), np.arange(1, 13) * 300.0
+    else:
+        p, t_eval = heat_params(B), np.arange(1, 101) / 100.0 * 0.99
+    r, *o = run_both(oracle, model, p, t_eval, method=method, kernel="band", use_coloring=coloring, rtol=1e-6, atol=1e-6)
+    assert (o[2] == 0).all()
+    assert_same(r, *o)

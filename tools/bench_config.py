@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Time one BASELINE.json configuration other than the headline one (which bench.py owns) on one GPU:
-   python tools/bench_config.py heat256 [batch] [auto|block|band]  |  spm | spm99 | vdp | robertson_dae [batch]
+   python tools/bench_config.py heat256 [batch] [auto|block|band] [bdf|tr_bdf2|esdirk34]  |  spm | spm99 | vdp | robertson_dae [batch]
 Prints ms per pass, instances/s, Newton-it/s and the algorithmic-byte HBM roofline fraction."""
 import json
 import os
@@ -24,7 +24,7 @@ if which.startswith("heat"):
     p = np.stack([1.0 + sweeps.uniform(idx, 0), 0.1 + 0.3 * sweeps.uniform(idx, 1), 0.6 + 0.3 * sweeps.uniform(idx, 2)], axis=1)
     t_eval = np.arange(1, 101) / 100.0 * 0.99
     prob = ds.OdeBuilder().rhs_implicit("heat1d_dae_%d" % n).p(p).rtol(1e-6).atol(1e-6).build()
-    solver, npar, mass_words = prob.bdf(), 3, n * n
+    solver, npar, mass_words = getattr(prob, sys.argv[4] if len(sys.argv) > 4 else "bdf")(), 3, n * n
     if len(sys.argv) > 3:
         solver.set_execution(sys.argv[3])
 elif which in ("spm", "spm99"):
