@@ -31,12 +31,17 @@
 #endif
 #define DSB_BAND_THREADS_SMALL 128  // batches that do not fill one 768-lane block per SM are spread over the SMs in small blocks
 #ifndef DSB_BAND_UNROLL_SMALL
-#define DSB_BAND_UNROLL_SMALL 8     // vector loops of the small-block variant: few resident warps, so the memory-level
+#define DSB_BAND_UNROLL_SMALL 4     // vector loops of the small-block variant: few resident warps, so the memory-level
 #endif                              // parallelism has to come from independent loads of ONE lane (255 registers available)
-// unroll factors of the component loops (U2: loops that evaluate the equations, U4: plain vector loops)
+// block sizes of the component loops (band_for; U2: loops that evaluate the equations or carry several results per
+// component, U4: plain vector loops)
+#ifndef DSB_BAND_UNROLL_BIG
+#define DSB_BAND_UNROLL_BIG 1     // 24 warps per SM at 80 registers: the warps provide the parallelism, bigger blocks spill
+#endif
 template <int T> struct BandUnroll {
-    static constexpr int U2 = T <= DSB_BAND_THREADS_SMALL ? DSB_BAND_UNROLL_SMALL : 2;
-    static constexpr int U4 = T <= DSB_BAND_THREADS_SMALL ? 2 * DSB_BAND_UNROLL_SMALL : 4;
+    static constexpr int U2 = T <= DSB_BAND_THREADS_SMALL ? DSB_BAND_UNROLL_SMALL : DSB_BAND_UNROLL_BIG;
+    static constexpr int U4 = 2 * U2;
+    static constexpr int UN = U4 > 4 ? U4 : 4;         // loops without stores (norms): plain unrolling is enough
 };
 
 template <class M, int T = DSB_BAND_THREADS>
@@ -85,6 +90,12 @@ struct BandColourSeed {
     }
 };
 
+// per-component results of the blocked loops (dsb_band_lu.cuh: band_for)
+struct BandR2 { double a, b; };
+struct BandRCols { double v[DSB_MAX_ORDER + 1]; };
+struct BandRDiff { double d2, d1, yp, col[DSB_MAX_ORDER + 1]; };
+template <int LD> struct BandRBand { double v[LD]; };
+
 // e_j: the argument of `mass` when the mass matrix is assembled column by column (op/linear_op.rs:42-51)
 struct BandUnitVec {
     int j;
@@ -98,7 +109,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                                                                   double* __restrict__ ws,
                                                                   unsigned long long* __restrict__ work_counter) {
     typedef BandBdfLayout<M, T> Lay;
-    constexpr int U2 = BandUnroll<T>::U2, U4 = BandUnroll<T>::U4;
+    constexpr int U2 = BandUnroll<T>::U2, U4 = BandUnroll<T>::U4, UN = BandUnroll<T>::UN;
     typedef LaneBandLU<M::N, Lay::KL, Lay::KU, DsbDivShared, U2> BLU;
     constexpr int N = Lay::N, NP = Lay::NP, KL = Lay::KL, KU = Lay::KU, KV = Lay::KV, LDJ = Lay::LDJ, LDAB = Lay::LDAB;
     extern __shared__ double dsb_lane_smem[];
@@ -180,7 +191,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
     // terms are added in index order, the loads do not depend on the sum and run ahead of it
     auto weighted_norm = [&](int ox, int oref) -> double {
         double acc = 0.0;
-#pragma unroll U4
+#pragma unroll UN
         for (int i = 0; i < N; ++i) {
             const double term = DSB_DIV(G(ox + i), dsb_abs(G(oref + i)) * pa.rtol + meta.atol[i]);
             acc += term * term;
@@ -220,14 +231,13 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                     // (state.rs:84-162)
 #pragma unroll
                     for (int k = 0; k < DSB_NSTATS; ++k) st.v[k] = bb.stats[(int64_t)k * B + inst];
-#pragma unroll U2
-                    for (int i = 0; i < N; ++i) { GY(i) = bb.y0[(int64_t)i * B + inst]; GD(1, i) = bb.dy0[(int64_t)i * B + inst]; }
+                    band_for<U4, BandR2>(N, [&](int i) { return BandR2{bb.y0[(int64_t)i * B + inst], bb.dy0[(int64_t)i * B + inst]}; },
+                                         [&](int i, const BandR2& r) { GY(i) = r.a; GD(1, i) = r.b; });
                 } else {
                     // y = init(p, t0); dy = f(y, t0)     (state.rs:1086-1124); dy is kept in D[1] until h is known
-#pragma unroll U2
+#pragma unroll UN
                     for (int i = 0; i < N; ++i) GY(i) = M::init_i(i, pl, pa.t0);
-#pragma unroll U2
-                    for (int i = 0; i < N; ++i) GD(1, i) = M::rhs_i(i, vY, pl, pa.t0);
+                    band_for<U2, double>(N, [&](int i) { return M::rhs_i(i, vY, pl, pa.t0); }, [&](int i, double r) { GD(1, i) = r; });
                     st.v[DSB_STAT_RHS_CALLS] += 1;
                 }
                 // set_step_size (state.rs:1209-1277), solver order 1
@@ -236,11 +246,10 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                     const double d0 = dsb_sqrt(weighted_norm(Lay::O_Y, Lay::O_Y));
                     const double d1 = dsb_sqrt(weighted_norm(Lay::O_D + N, Lay::O_Y));
                     const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * DSB_DIV(d0, d1);
-#pragma unroll U2
-                    for (int i = 0; i < N; ++i) GYC(i) = is_neg_h ? (GD(1, i) * (-h0) + GY(i)) : (GD(1, i) * h0 + GY(i));
+                    band_for<U4, double>(N, [&](int i) { return is_neg_h ? (GD(1, i) * (-h0) + GY(i)) : (GD(1, i) * h0 + GY(i)); },
+                                         [&](int i, double r) { GYC(i) = r; });
                     const double t1 = is_neg_h ? pa.t0 - h0 : pa.t0 + h0;
-#pragma unroll U2
-                    for (int i = 0; i < N; ++i) GDL(i) = M::rhs_i(i, vYC, pl, t1) - GD(1, i);
+                    band_for<U2, double>(N, [&](int i) { return M::rhs_i(i, vYC, pl, t1) - GD(1, i); }, [&](int i, double r) { GDL(i) = r; });
                     st.v[DSB_STAT_RHS_CALLS] += 1;
                     const double d2 = DSB_DIV(dsb_sqrt(weighted_norm(Lay::O_DL, Lay::O_Y)), dsb_abs(h0));
                     double max_d = d2;
@@ -253,12 +262,12 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                     if (is_neg_h) h = -h;
                 }
                 // state.set_problem (bdf_state.rs:72-78): D[:, 0] = y, D[:, 1] = h dy, the rest zero
-                for (int i = 0; i < N; ++i) {
-                    GD(0, i) = GY(i);
-                    GD(1, i) = GD(1, i) * h;
+                band_for<U4, BandR2>(N, [&](int i) { return BandR2{GY(i), GD(1, i) * h}; },
+                                     [&](int i, const BandR2& r) {
+                                         GD(0, i) = r.a; GD(1, i) = r.b;
 #pragma unroll
-                    for (int j = 2; j < DSB_NDIFF; ++j) GD(j, i) = 0.0;
-                }
+                                         for (int j = 2; j < DSB_NDIFF; ++j) GD(j, i) = 0.0;
+                                     });
                 order = 1; n_equal_steps = 0;
                 conv.eta = pa.tab.eta_reset; conv.old_norm = 0.0; conv.reset();
                 c = h * pa.tab.alpha[1];
@@ -344,20 +353,21 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                     }
                 }
             }
-#pragma unroll 1
-            for (int s = 0; s < N; ++s) {
-                double nd[DSB_MAX_ORDER + 1];
+            band_for<U2, BandRCols>(N, [&](int s) {
+                BandRCols nd;
 #pragma unroll
-                for (int j = 1; j <= DSB_MAX_ORDER; ++j) nd[j] = -0.0;      // (-0.0) + x == x: the first term is assigned
+                for (int j = 1; j <= DSB_MAX_ORDER; ++j) nd.v[j] = -0.0;    // (-0.0) + x == x: the first term is assigned
 #pragma unroll 1
                 for (int i = 1; i <= k; ++i) {
                     const double di = GD(i, s);
 #pragma unroll
-                    for (int j = 1; j <= DSB_MAX_ORDER; ++j) nd[j] = di * SRU(i, j) + nd[j];
+                    for (int j = 1; j <= DSB_MAX_ORDER; ++j) nd.v[j] = di * SRU(i, j) + nd.v[j];
                 }
+                return nd;
+            }, [&](int s, const BandRCols& nd) {
 #pragma unroll
-                for (int j = 1; j <= DSB_MAX_ORDER; ++j) if (j <= k) GD(j, s) = nd[j];
-            }
+                for (int j = 1; j <= DSB_MAX_ORDER; ++j) if (j <= k) GD(j, s) = nd.v[j];
+            });
             c = new_h * pa.tab.alpha[k];
             h = new_h;
             conv.eta = pa.tab.eta_reset_timestep;
@@ -401,9 +411,9 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                         // rows outside the band of the colour's only column hold exact zeros and are not evaluated
                         const int i0 = one_colour_per_column ? (cc - KU < 0 ? 0 : cc - KU) : 0;
                         const int i1 = one_colour_per_column ? (cc + KL > N - 1 ? N - 1 : cc + KL) : N - 1;
-#pragma unroll 1
-                        for (int i = i0; i <= i1; ++i) {
-                            const double val = M::jac_mul_i(i, vY, pl, t, seed);
+                        band_for<U2, double>(i1 - i0 + 1, [&](int q) { return M::jac_mul_i(i0 + q, vY, pl, t, seed); },
+                                             [&](int q, double val) {
+                            const int i = i0 + q;
 #pragma unroll
                             for (int d = -KL; d <= KU; ++d) {               // column j = i + d
                                 const int j = i + d;
@@ -412,7 +422,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                                     if ((m & 0xffff) == cc && ((m >> (16 + KU - d)) & 1)) GJ(j, KU - d) = val;
                                 }
                             }
-                        }
+                        });
                     }
                     if constexpr (M::HAS_MASS) {
                         // mass.matrix_inplace(t) with the Jacobian (op/bdf.rs:273-300): column j = M e_j, beta = 0
@@ -430,8 +440,8 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                 }
                 // A = M - c J (op/bdf.rs:282-298: J * (-c) + M) in band storage with kl extra rows for the fill-in
                 const double mc = -c;
-#pragma unroll 1
-                for (int j = 0; j < N; ++j) {
+                band_for<U2, BandRBand<LDAB>>(N, [&](int j) {
+                    BandRBand<LDAB> a;
 #pragma unroll
                     for (int r = 0; r < LDAB; ++r) {
                         const int i = j + r - KV;
@@ -440,9 +450,13 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                             if constexpr (M::HAS_MASS) v = GJ(j, r - KL) * mc + GM(j, r - KL);
                             else v = GJ(j, r - KL) * mc + ((i == j) ? 1.0 : 0.0);
                         }
-                        GAB(j, r) = v;
+                        a.v[r] = v;
                     }
-                }
+                    return a;
+                }, [&](int j, const BandRBand<LDAB>& a) {
+#pragma unroll
+                    for (int r = 0; r < LDAB; ++r) GAB(j, r) = a.v[r];
+                });
                 // band LU, dgbtf2 convention (dsb_band_lu.cuh)
                 BLU::factor(g, LS, Lay::O_LU, Lay::O_PIV);
             }
@@ -500,13 +514,12 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                     }
                     tf[j] = time_factor;
                 }
-#pragma unroll U2
-                for (int i = 0; i < N; ++i) {
+                band_for<U2, double>(N, [&](int i) {
                     double yo = GD(0, i);
 #pragma unroll
                     for (int j = 0; j < DSB_MAX_ORDER; ++j) if (j < order) yo = tf[j] * GD(j + 1, i) + yo;
-                    bb.ys[((int64_t)col * N + i) * B + inst] = yo;
-                }
+                    return yo;
+                }, [&](int i, double yo) { bb.ys[((int64_t)col * N + i) * B + inst] = yo; });
                 ++col;
             }
             if (status != DSB_STATUS_OK) finish(status);
@@ -523,8 +536,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
             if (repredict) {
                 const int ord = order;
                 const double a = pa.tab.alpha[ord];
-#pragma unroll U2
-                for (int i = 0; i < N; ++i) {
+                band_for<U2, BandR2>(N, [&](int i) {
                     double yp = 0.0;
                     double ps = 0.0;
 #pragma unroll
@@ -538,12 +550,11 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                     }
                     ps *= a;
                     ps -= yp;
-                    GYP(i) = yp; GPSI(i) = ps; GYC(i) = yp;
-                }
+                    return BandR2{yp, ps};
+                }, [&](int i, const BandR2& r) { GYP(i) = r.a; GPSI(i) = r.b; GYC(i) = r.a; });
                 t_predict = t + h;
             } else {
-#pragma unroll U4
-                for (int i = 0; i < N; ++i) GYC(i) = GYP(i);
+                band_for<U4, double>(N, [&](int i) { return GYP(i); }, [&](int i, double r) { GYC(i) = r; });
             }
             state = L_NEWTON;
             if (pending_etf) {
@@ -560,19 +571,16 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
             // delta = F(y) = M (y + psi - y0) - c f(t, y)   (op/bdf.rs:240-256)
             const double mc = -c;
             if constexpr (M::HAS_MASS) {
-#pragma unroll U4
-                for (int i = 0; i < N; ++i) GTMP(i) = GYC(i) + GPSI(i);
-#pragma unroll U2
-                for (int i = 0; i < N; ++i) {
+                band_for<U4, double>(N, [&](int i) { return GYC(i) + GPSI(i); }, [&](int i, double r) { GTMP(i) = r; });
+                band_for<U2, double>(N, [&](int i) {
                     const double f = M::rhs_i(i, vYC, pl, t_predict);
-                    GDL(i) = M::mass_i(i, vTMP, pl, t_predict, mc, f);       // gemv_inplace(x, t, beta, y): y = M x + beta y
-                }
+                    return M::mass_i(i, vTMP, pl, t_predict, mc, f);         // gemv_inplace(x, t, beta, y): y = M x + beta y
+                }, [&](int i, double r) { GDL(i) = r; });
             } else {
-#pragma unroll U2
-                for (int i = 0; i < N; ++i) {
+                band_for<U2, double>(N, [&](int i) {
                     const double f = M::rhs_i(i, vYC, pl, t_predict);
-                    GDL(i) = (GYC(i) + GPSI(i)) + mc * f;
-                }
+                    return (GYC(i) + GPSI(i)) + mc * f;
+                }, [&](int i, double r) { GDL(i) = r; });
             }
             st.v[DSB_STAT_RHS_CALLS] += 1;
             const bool ok = BLU::solve(g, LS, Lay::O_LU, Lay::O_PIV, Lay::O_DL);
@@ -580,14 +588,11 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                 newton_ok = false; state = L_POST;              // LuSolveFailed
             } else {
                 double acc = 0.0;
-#pragma unroll U4
-                for (int i = 0; i < N; ++i) {
+                band_for<U4, BandR2>(N, [&](int i) {
                     const double dl = GDL(i);
-                    GYC(i) = GYC(i) - dl;
                     // Newton norm weights use the PREDICTOR (line_search.rs:67, convergence.rs:64-66)
-                    const double term = DSB_DIV(dl, dsb_abs(GYP(i)) * pa.rtol + meta.atol[i]);
-                    acc += term * term;
-                }
+                    return BandR2{GYC(i) - dl, DSB_DIV(dl, dsb_abs(GYP(i)) * pa.rtol + meta.atol[i])};
+                }, [&](int i, const BandR2& r) { GYC(i) = r.a; acc += r.b * r.b; });
                 const double norm = dsb_sqrt(DSB_DIV(acc, (double)N));
                 // Convergence::check_new_iteration (convergence.rs:68-139)
                 conv.niter += 1;
@@ -618,7 +623,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                 const int ord = order;
                 {   // error_control: ||d||^2_w(state.y) * error_const2[order - 1], d = y - y_predict
                     double acc = 0.0;
-#pragma unroll U4
+#pragma unroll UN
                     for (int i = 0; i < N; ++i) {
                         const double d = GYC(i) - GYP(i);
                         const double term = DSB_DIV(d, dsb_abs(GY(i)) * pa.rtol + meta.atol[i]);
@@ -632,20 +637,28 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                 safety = DSB_DIV(0.9 * (2.0 * maxiter + 1.0), 2.0 * maxiter + niter);
                 if (error_norm <= 1.0) {
                     // ---- accepted: _update_diff, state.y <- PREDICTOR (quirk Q1) ----
-#pragma unroll U2
-                    for (int i = 0; i < N; ++i) {
-                        const double yp = GYP(i);
-                        const double d = GYC(i) - yp;
+                    band_for<(U2 > 4 ? 4 : U2), BandRDiff>(N, [&](int i) {
+                        BandRDiff r;
+                        r.yp = GYP(i);
+                        const double d = GYC(i) - r.yp;
                         double above = d;                                   // the new D[:, ord + 1]
-                        GD(ord + 2, i) = d - GD(ord + 1, i);
-                        GD(ord + 1, i) = d;
-#pragma unroll 1
-                        for (int j = ord; j >= 0; --j) {
-                            above = GD(j, i) + 1.0 * above;
-                            GD(j, i) = above;
+                        r.d2 = d - GD(ord + 1, i);
+                        r.d1 = d;
+#pragma unroll
+                        for (int j = DSB_MAX_ORDER; j >= 0; --j) {
+                            if (j <= ord) {
+                                above = GD(j, i) + 1.0 * above;
+                                r.col[j] = above;
+                            }
                         }
-                        GY(i) = yp;
-                    }
+                        return r;
+                    }, [&](int i, const BandRDiff& r) {
+                        GD(ord + 2, i) = r.d2;
+                        GD(ord + 1, i) = r.d1;
+#pragma unroll
+                        for (int j = DSB_MAX_ORDER; j >= 0; --j) if (j <= ord) GD(j, i) = r.col[j];
+                        GY(i) = r.yp;
+                    });
                     t = t_predict;
                     st.v[DSB_STAT_STEPS] += 1;
                     ju.step();

@@ -15,6 +15,24 @@
 #pragma once
 #include "dsb_lane.cuh"
 
+// Blocked component loop: store(i, compute(i)) for i in [0, n), with the loads and arithmetic of U consecutive
+// components issued BEFORE any of their stores.  Every vector of a lane lives behind the same base pointer with a
+// run-time stride, so the compiler cannot prove that the store of component i does not alias the loads of component
+// i + 1 and would otherwise serialise the loop at one global-memory round trip per component (a warp issues in
+// order: it stalls at the store until the loads that feed it return).  compute() must not read what store() writes
+// for another component.
+template <int U, class R, class C, class S>
+DSB_DEV void band_for(const int n, C&& compute, S&& store) {
+#pragma unroll 1
+    for (int i0 = 0; i0 < n; i0 += U) {
+        R r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) if (i0 + u < n) r[u] = compute(i0 + u);
+#pragma unroll
+        for (int u = 0; u < U; ++u) if (i0 + u < n) store(i0 + u, r[u]);
+    }
+}
+
 template <int N, int KL, int KU, class DIV, int U = 2>      // U: unroll factor of the substitution loops
 struct LaneBandLU {
     static constexpr int KV = KL + KU, LDAB = 2 * KL + KU + 1;
@@ -78,7 +96,9 @@ struct LaneBandLU {
         }
     }
 
-    // b <- A^-1 b for the vector at o_b; false when a zero pivot is met (LaError::LuSolveFailed): b is then partly solved
+    // b <- A^-1 b for the vector at o_b; false when a zero pivot is met (LaError::LuSolveFailed): b is then partly solved.
+    // Both sweeps run in blocks of U rows: the block's pivots, multipliers and incoming right-hand-side entries are
+    // loaded first, the recurrence runs in registers, the block's results are stored last (see band_for).
     static DSB_DEV bool solve(double* __restrict__ g, const size_t LS, const int o_ab, const int o_piv, const int o_b) {
 #define GB_(i) g[(size_t)(o_b + (i)) * LS]
         // forward substitution with the interchanges interleaved; b[j .. j + kl] travels in registers
@@ -86,23 +106,41 @@ struct LaneBandLU {
             double w[KL + 1];
 #pragma unroll
             for (int d = 0; d <= KL; ++d) w[d] = GB_(d);
-#pragma unroll U
-            for (int j = 0; j + 1 < N; ++j) {
-                const int jp = (int)GPIV_(j);
-                if (jp != 0) {
-                    const double a = w[0];
+#pragma unroll 1
+            for (int j0 = 0; j0 + 1 < N; j0 += U) {
+                int jp[U];
+                double lm_[U][KL], bin[U], out[U];
 #pragma unroll
-                    for (int d = 1; d <= KL; ++d) if (jp == d) { w[0] = w[d]; w[d] = a; }
+                for (int u = 0; u < U; ++u) {
+                    const int j = j0 + u;
+                    if (j + 1 < N) {
+                        jp[u] = (int)GPIV_(j);
+#pragma unroll
+                        for (int d = 1; d <= KL; ++d) lm_[u][d - 1] = (j + d < N) ? GAB_(j, KV + d) : 0.0;
+                        bin[u] = (j + 1 + KL < N) ? GB_(j + 1 + KL) : 0.0;
+                    }
                 }
-                const double bj = w[0];
-                GB_(j) = bj;
-                const double nbj = -bj;
-                const int lm = (KL < N - 1 - j) ? KL : (N - 1 - j);
 #pragma unroll
-                for (int d = 1; d <= KL; ++d) if (d <= lm) w[d] = nbj * GAB_(j, KV + d) + w[d];
+                for (int u = 0; u < U; ++u) {
+                    const int j = j0 + u;
+                    if (j + 1 < N) {
+                        if (jp[u] != 0) {
+                            const double a = w[0];
 #pragma unroll
-                for (int d = 0; d < KL; ++d) w[d] = w[d + 1];
-                w[KL] = (j + 1 + KL < N) ? GB_(j + 1 + KL) : 0.0;
+                            for (int d = 1; d <= KL; ++d) if (jp[u] == d) { w[0] = w[d]; w[d] = a; }
+                        }
+                        const double bj = w[0];
+                        out[u] = bj;
+                        const double nbj = -bj;
+#pragma unroll
+                        for (int d = 1; d <= KL; ++d) if (j + d < N) w[d] = nbj * lm_[u][d - 1] + w[d];
+#pragma unroll
+                        for (int d = 0; d < KL; ++d) w[d] = w[d + 1];
+                        w[KL] = bin[u];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (j0 + u + 1 < N) GB_(j0 + u) = out[u];
             }
             GB_(N - 1) = w[0];
         }
@@ -112,20 +150,40 @@ struct LaneBandLU {
             double w[KV + 1];
 #pragma unroll
             for (int e = 0; e <= KV; ++e) w[e] = GB_(N - 1 - e);
-#pragma unroll U
-            for (int i = N - 1; i >= 0; --i) {
-                const double diag = GAB_(i, KV);
-                if (diag == 0.0) ok = false;
-                if (ok) {
-                    const double coeff = DIV::div(w[0], diag);
-                    GB_(i) = coeff;
-                    const double ncoeff = -coeff;
+#pragma unroll 1
+            for (int i0 = N - 1; i0 >= 0; i0 -= U) {
+                double up[U][KV + 1], bin[U], out[U];
+                bool have[U];
 #pragma unroll
-                    for (int e = 1; e <= KV; ++e) if (i - e >= 0) w[e] = ncoeff * GAB_(i, KV - e) + w[e];
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 - u;
+                    if (i >= 0) {
+#pragma unroll
+                        for (int e = 0; e <= KV; ++e) up[u][e] = (i - e >= 0) ? GAB_(i, KV - e) : 0.0;
+                        bin[u] = (i - 1 - KV >= 0) ? GB_(i - 1 - KV) : 0.0;
+                    }
                 }
 #pragma unroll
-                for (int e = 0; e < KV; ++e) w[e] = w[e + 1];
-                w[KV] = (i - 1 - KV >= 0) ? GB_(i - 1 - KV) : 0.0;
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 - u;
+                    have[u] = false;
+                    if (i >= 0) {
+                        const double diag = up[u][0];
+                        if (diag == 0.0) ok = false;
+                        if (ok) {
+                            const double coeff = DIV::div(w[0], diag);
+                            out[u] = coeff; have[u] = true;
+                            const double ncoeff = -coeff;
+#pragma unroll
+                            for (int e = 1; e <= KV; ++e) if (i - e >= 0) w[e] = ncoeff * up[u][e] + w[e];
+                        }
+#pragma unroll
+                        for (int e = 0; e < KV; ++e) w[e] = w[e + 1];
+                        w[KV] = bin[u];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (have[u]) GB_(i0 - u) = out[u];
             }
         }
         return ok;

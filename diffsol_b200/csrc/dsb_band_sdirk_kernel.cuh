@@ -46,7 +46,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                                                                     double* __restrict__ ws,
                                                                     unsigned long long* __restrict__ work_counter) {
     typedef BandSdirkLayout<M, T> Lay;
-    constexpr int U2 = BandUnroll<T>::U2, U4 = BandUnroll<T>::U4;
+    constexpr int U2 = BandUnroll<T>::U2, U4 = BandUnroll<T>::U4, UN = BandUnroll<T>::UN;
     typedef LaneBandLU<M::N, Lay::KL, Lay::KU, DsbDivShared, U2> BLU;
     constexpr int N = Lay::N, NP = Lay::NP, KL = Lay::KL, KU = Lay::KU, KV = Lay::KV, LDJ = Lay::LDJ, LDAB = Lay::LDAB;
     extern __shared__ double dsb_lane_smem[];
@@ -116,7 +116,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
     // ||x||^2_w(ref) (vector/nalgebra_serial.rs:395-408) over words of the lane's column
     auto weighted_norm = [&](int ox, int oref) -> double {
         double acc = 0.0;
-#pragma unroll U4
+#pragma unroll UN
         for (int i = 0; i < N; ++i) {
             const double term = DSB_DIV(G(ox + i), dsb_abs(G(oref + i)) * pa.rtol + meta.atol[i]);
             acc += term * term;
@@ -155,14 +155,13 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                     // singular mass: y, dy after set_consistent and the counters so far come from dsb_band_init_kernel
 #pragma unroll
                     for (int k = 0; k < DSB_NSTATS; ++k) st.v[k] = bb.stats[(int64_t)k * B + inst];
-#pragma unroll U2
-                    for (int i = 0; i < N; ++i) { GY(i) = bb.y0[(int64_t)i * B + inst]; GDY(i) = bb.dy0[(int64_t)i * B + inst]; }
+                    band_for<U4, BandR2>(N, [&](int i) { return BandR2{bb.y0[(int64_t)i * B + inst], bb.dy0[(int64_t)i * B + inst]}; },
+                                         [&](int i, const BandR2& r) { GY(i) = r.a; GDY(i) = r.b; });
                 } else {
                     // y = init(p, t0); dy = f(y, t0)     (state.rs:1086-1124)
-#pragma unroll U2
+#pragma unroll UN
                     for (int i = 0; i < N; ++i) GY(i) = M::init_i(i, pl, pa.t0);
-#pragma unroll U2
-                    for (int i = 0; i < N; ++i) GDY(i) = M::rhs_i(i, vY, pl, pa.t0);
+                    band_for<U2, double>(N, [&](int i) { return M::rhs_i(i, vY, pl, pa.t0); }, [&](int i, double r) { GDY(i) = r; });
                     st.v[DSB_STAT_RHS_CALLS] += 1;
                 }
                 // set_step_size (state.rs:1209-1277), solver order = the tableau's
@@ -171,11 +170,10 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                     const double d0 = dsb_sqrt(weighted_norm(Lay::O_Y, Lay::O_Y));
                     const double d1 = dsb_sqrt(weighted_norm(Lay::O_DY, Lay::O_Y));
                     const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * DSB_DIV(d0, d1);
-#pragma unroll U2
-                    for (int i = 0; i < N; ++i) GTMP(i) = is_neg_h ? (GDY(i) * (-h0) + GY(i)) : (GDY(i) * h0 + GY(i));
+                    band_for<U4, double>(N, [&](int i) { return is_neg_h ? (GDY(i) * (-h0) + GY(i)) : (GDY(i) * h0 + GY(i)); },
+                                         [&](int i, double r) { GTMP(i) = r; });
                     const double t1 = is_neg_h ? pa.t0 - h0 : pa.t0 + h0;
-#pragma unroll U2
-                    for (int i = 0; i < N; ++i) GDL(i) = M::rhs_i(i, vTMP, pl, t1) - GDY(i);
+                    band_for<U2, double>(N, [&](int i) { return M::rhs_i(i, vTMP, pl, t1) - GDY(i); }, [&](int i, double r) { GDL(i) = r; });
                     st.v[DSB_STAT_RHS_CALLS] += 1;
                     const double d2 = DSB_DIV(dsb_sqrt(weighted_norm(Lay::O_DL, Lay::O_Y)), dsb_abs(h0));
                     double max_d = d2;
@@ -187,11 +185,11 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                     if (h_state > h1) h_state = h1;
                     if (is_neg_h) h_state = -h_state;
                 }
-                for (int i = 0; i < N; ++i) {
-                    GOY(i) = GY(i); GPHI(i) = 0.0;
+                band_for<U4, double>(N, [&](int i) { return GY(i); }, [&](int i, double r) {
+                    GOY(i) = r; GPHI(i) = 0.0;
 #pragma unroll
                     for (int j = 0; j < DSB_RK_MAX_STAGES; ++j) GDF(j, i) = 0.0;
-                }
+                });
                 ju.init(1.0);
                 ju.update_jacobian(h_state);
                 ju.update_rhs_jacobian(h_state);
@@ -211,26 +209,24 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                 double dco[DSB_RK_MAX_STAGES];
 #pragma unroll
                 for (int j = 0; j < DSB_RK_MAX_STAGES; ++j) dco[j] = (j < ns) ? pa.rk.d[j] : 0.0;
-#pragma unroll U2
-                for (int k = 0; k < N; ++k) {
+                band_for<U2, double>(N, [&](int k) {
                     double e = GDF(0, k) * dco[0];
 #pragma unroll
                     for (int j = 1; j < DSB_RK_MAX_STAGES; ++j) if (j < ns) e = GDF(j, k) * dco[j] + e;
-                    if constexpr (M::HAS_MASS) GTMP(k) = e; else GDL(k) = e;
-                }
+                    return e;
+                }, [&](int k, double e) { if constexpr (M::HAS_MASS) GTMP(k) = e; else GDL(k) = e; });
             }
             if constexpr (M::HAS_MASS) {
                 // error <- M error: column sweep, the first product is assigned (matrix gemv with beta = 0)
-#pragma unroll U2
-                for (int k = 0; k < N; ++k) {
+                band_for<U2, double>(N, [&](int k) {
                     double e = -0.0;                                  // (-0.0) + x == x
 #pragma unroll
                     for (int d = -KL; d <= KU; ++d) {
                         const int j = k + d;
                         if (j >= 0 && j < N) e = GM(j, KU - d) * GTMP(j) + e;
                     }
-                    GDL(k) = e;
-                }
+                    return e;
+                }, [&](int k, double e) { GDL(k) = e; });
             }
             if (!BLU::solve(g, LS, Lay::O_LU, Lay::O_PIV, Lay::O_DL)) {
                 finish(DSB_STATUS_LU_SOLVE_FAILED);
@@ -293,8 +289,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                 if (jacobian_is_stale) {
                     // df/dy at phi + c * state.y with the phi left over from the last stage (op/sdirk.rs:265-276), one
                     // jac_mul per colour, scattered through the sparsity pattern into band storage
-#pragma unroll U4
-                    for (int i = 0; i < N; ++i) GTMP(i) = cg * GY(i) + GPHI(i);
+                    band_for<U4, double>(N, [&](int i) { return cg * GY(i) + GPHI(i); }, [&](int i, double r) { GTMP(i) = r; });
                     st.v[DSB_STAT_RHS_MATRIX_EVALS] += 1;
                     for (int e = 0; e < LDJ * N; ++e) G(Lay::O_J + e) = 0.0;
                     const bool one_colour_per_column = pa.ncolors == N;
@@ -304,9 +299,9 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                         st.v[DSB_STAT_RHS_JAC_MULS] += 1;
                         const int i0 = one_colour_per_column ? (cc - KU < 0 ? 0 : cc - KU) : 0;
                         const int i1 = one_colour_per_column ? (cc + KL > N - 1 ? N - 1 : cc + KL) : N - 1;
-#pragma unroll 1
-                        for (int i = i0; i <= i1; ++i) {
-                            const double val = M::jac_mul_i(i, vTMP, pl, t_jac, seed);
+                        band_for<U2, double>(i1 - i0 + 1, [&](int q) { return M::jac_mul_i(i0 + q, vTMP, pl, t_jac, seed); },
+                                             [&](int q, double val) {
+                            const int i = i0 + q;
 #pragma unroll
                             for (int d = -KL; d <= KU; ++d) {               // column j = i + d
                                 const int j = i + d;
@@ -315,7 +310,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                                     if ((m & 0xffff) == cc && ((m >> (16 + KU - d)) & 1)) GJ(j, KU - d) = val;
                                 }
                             }
-                        }
+                        });
                     }
                     if constexpr (M::HAS_MASS) {
 #pragma unroll 1
@@ -332,8 +327,8 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                 }
                 // A = M - (c h) J (op/sdirk.rs:277-292) in band storage with kl extra rows for the fill-in
                 const double beta = -(cg * op_h);
-#pragma unroll 1
-                for (int j = 0; j < N; ++j) {
+                band_for<U2, BandRBand<LDAB>>(N, [&](int j) {
+                    BandRBand<LDAB> a;
 #pragma unroll
                     for (int r = 0; r < LDAB; ++r) {
                         const int i = j + r - KV;
@@ -342,9 +337,13 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                             if constexpr (M::HAS_MASS) v = GJ(j, r - KL) * beta + GM(j, r - KL);
                             else v = GJ(j, r - KL) * beta + ((i == j) ? 1.0 : 0.0);
                         }
-                        GAB(j, r) = v;
+                        a.v[r] = v;
                     }
-                }
+                    return a;
+                }, [&](int j, const BandRBand<LDAB>& a) {
+#pragma unroll
+                    for (int r = 0; r < LDAB; ++r) GAB(j, r) = a.v[r];
+                });
                 BLU::factor(g, LS, Lay::O_LU, Lay::O_PIV);
                 is_jacobian_set = true;
             }
@@ -375,13 +374,13 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
             old_t = t;
             t = t + h;
             h_state = new_h;
-#pragma unroll U2
-            for (int i = 0; i < N; ++i) {
-                const double y_new = GOY(i);                 // old_state.y held the last stage value
-                GOY(i) = GY(i);                              // swap: old_state <- previous state
-                GY(i) = y_new;
-                GDY(i) = GX(i) * inv_h;                      // old_state.dy *= 1/h, then swapped in
-            }
+            band_for<U2, BandRCols>(N, [&](int i) {
+                BandRCols r;
+                r.v[0] = GOY(i);                             // old_state.y held the last stage value
+                r.v[1] = GY(i);                              // swap: old_state <- previous state
+                r.v[2] = GX(i) * inv_h;                      // old_state.dy *= 1/h, then swapped in
+                return r;
+            }, [&](int i, const BandRCols& r) { GY(i) = r.v[0]; GOY(i) = r.v[1]; GDY(i) = r.v[2]; });
             st.v[DSB_STAT_STEPS] += 1;
             state = R_TSTOP;
         }
@@ -426,18 +425,16 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                         bf[j] = 0.0;
                         if (j < ns) { bf[j] = pa.rk.beta[j] * theta; bf[j] = pa.rk.beta[ns + j] * th2 + bf[j]; }
                     }
-#pragma unroll U2
-                    for (int i = 0; i < N; ++i) {
+                    band_for<U2, double>(N, [&](int i) {
                         double yo = GOY(i);
 #pragma unroll
                         for (int j = 0; j < DSB_RK_MAX_STAGES; ++j) if (j < ns) yo = GDF(j, i) * bf[j] + yo;
-                        bb.ys[((int64_t)col * N + i) * B + inst] = yo;
-                    }
+                        return yo;
+                    }, [&](int i, double yo) { bb.ys[((int64_t)col * N + i) * B + inst] = yo; });
                 } else {
                     const double al1 = theta - 1.0, be1 = 1.0 - 2.0 * theta;
                     const double al2 = 1.0 - theta, be2 = theta * (theta - 1.0);
-#pragma unroll U2
-                    for (int i = 0; i < N; ++i) {
+                    band_for<U2, double>(N, [&](int i) {
                         const double u0 = GOY(i), u1 = GY(i);
                         double v = u1;
                         v -= u0;
@@ -445,8 +442,8 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                         v = theta * GDF(ns - 1, i) + v;
                         v = al2 * u0 + be2 * v;
                         v = theta * u1 + v;
-                        bb.ys[((int64_t)col * N + i) * B + inst] = v;
-                    }
+                        return v;
+                    }, [&](int i, double v) { bb.ys[((int64_t)col * N + i) * B + inst] = v; });
                 }
                 ++col;
             }
@@ -468,8 +465,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
         // ================= ATTEMPT: start_step_attempt (runge_kutta.rs:505-535) =================================
         if (__any_sync(0xffffffffu, state == R_ATTEMPT) && state == R_ATTEMPT) {
             if (start == 1) {
-#pragma unroll U4
-                for (int k = 0; k < N; ++k) GDF(0, k) = h * GDY(k);
+                band_for<U4, double>(N, [&](int k) { return h * GDY(k); }, [&](int k, double r) { GDF(0, k) = r; });
             }
             stage = start;
             state = R_STAGE;
@@ -486,18 +482,16 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                 const double cc = DSB_DIV(pa.rk.c[i] - pa.rk.c[i - 2], pa.rk.c[i - 1] - pa.rk.c[i - 2]);
                 al = -cc; be = 1.0 + cc;
             }
-#pragma unroll U2
-            for (int k = 0; k < N; ++k) {
+            band_for<U2, BandR2>(N, [&](int k) {
                 double ph = GY(k);
 #pragma unroll
                 for (int j = 0; j < DSB_RK_MAX_STAGES - 1; ++j) if (j < i) ph = GDF(j, k) * aco[j] + ph;
-                GPHI(k) = ph;
                 double x;
                 if (i == 0) x = h * GDY(k);
                 else if (i == 1) x = GDF(0, k);
                 else x = al * GDF(i - 2, k) + be * GDF(i - 1, k);
-                GX(k) = x;
-            }
+                return BandR2{ph, x};
+            }, [&](int k, const BandR2& r) { GPHI(k) = r.a; GX(k) = r.b; });
             conv.reset();
             if (!is_jacobian_set) { jac_kind = DSB_KIND_LAZY; after_jac = R_NEWTON; state = R_JAC; }
             else state = R_NEWTON;
@@ -505,27 +499,22 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
 
         // ================= NEWTON: one iteration on F(x) = M x - h f(phi + c x) =================================
         if (__any_sync(0xffffffffu, state == R_NEWTON) && state == R_NEWTON) {
-#pragma unroll U4
-            for (int i = 0; i < N; ++i) GTMP(i) = cg * GX(i) + GPHI(i);
+            band_for<U4, double>(N, [&](int i) { return cg * GX(i) + GPHI(i); }, [&](int i, double r) { GTMP(i) = r; });
             const double beta = -op_h;
-#pragma unroll U2
-            for (int i = 0; i < N; ++i) {
+            band_for<U2, double>(N, [&](int i) {
                 const double f = M::rhs_i(i, vTMP, pl, t_stage);
-                if constexpr (M::HAS_MASS) GDL(i) = M::mass_i(i, vX, pl, t_stage, beta, f);   // gemv_inplace: y = M x + beta y
-                else GDL(i) = GX(i) + beta * f;
-            }
+                if constexpr (M::HAS_MASS) return M::mass_i(i, vX, pl, t_stage, beta, f);     // gemv_inplace: y = M x + beta y
+                else return GX(i) + beta * f;
+            }, [&](int i, double r) { GDL(i) = r; });
             st.v[DSB_STAT_RHS_CALLS] += 1;
             if (!BLU::solve(g, LS, Lay::O_LU, Lay::O_PIV, Lay::O_DL)) {
                 newton_ok = false; state = R_POST;
             } else {
                 double acc = 0.0;
-#pragma unroll U4
-                for (int i = 0; i < N; ++i) {
+                band_for<U4, BandR2>(N, [&](int i) {
                     const double dl = GDL(i);
-                    GX(i) = GX(i) - dl;
-                    const double term = DSB_DIV(dl, dsb_abs(GY(i)) * pa.rtol + meta.atol[i]);    // weights from state.y
-                    acc += term * term;
-                }
+                    return BandR2{GX(i) - dl, DSB_DIV(dl, dsb_abs(GY(i)) * pa.rtol + meta.atol[i])};    // weights from state.y
+                }, [&](int i, const BandR2& r) { GX(i) = r.a; acc += r.b * r.b; });
                 const double norm = dsb_sqrt(DSB_DIV(acc, (double)N));
                 conv.niter += 1;
                 const bool have_rate = conv.has_old_norm;
@@ -554,12 +543,10 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
             st.v[DSB_STAT_NONLINEAR_SOLVER_ITERATIONS] += conv.niter;
             if (newton_ok) {
                 const int i = stage;
-#pragma unroll U2
-                for (int k = 0; k < N; ++k) {
+                band_for<U4, BandR2>(N, [&](int k) {
                     const double x = GX(k);
-                    GOY(k) = cg * x + GPHI(k);               // get_f_eval: stage value
-                    GDF(i, k) = x;
-                }
+                    return BandR2{cg * x + GPHI(k), x};      // get_f_eval: stage value
+                }, [&](int k, const BandR2& r) { GOY(k) = r.a; GDF(i, k) = r.b; });
                 stage = i + 1;
                 state = (stage < ns) ? R_STAGE : R_ERRTEST;
             } else {
