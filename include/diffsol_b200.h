@@ -131,7 +131,7 @@ int dsb_batch_free(dsb_batch* b);
 int64_t dsb_batch_size(const dsb_batch* b);
 
 /* Execution model of the integrator kernels: 0 = automatic (one thread per instance for n <= 16; above, one thread
- * per instance with the state in global memory for banded models of n <= 64 without a mass matrix, else one thread
+ * per instance with the state in global memory for banded models (ODE or singular-mass DAE, BDF or SDIRK), else one thread
  * block per instance), 1 = thread per instance, 2 = block per instance, 3 = banded thread per instance.  Results
  * are identical. */
 int dsb_batch_set_execution(dsb_batch* b, int32_t mode);
