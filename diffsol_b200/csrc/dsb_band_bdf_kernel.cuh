@@ -24,6 +24,7 @@
 // (ode_solver/state.rs:1086-1124, 1209-1277), which the small-n path runs in dsb_init_kernel.cuh.
 #pragma once
 #include "dsb_band_lu.cuh"
+#include "dsb_roots.cuh"
 #include "dsb_bdf_kernel.cuh"
 
 #ifndef DSB_BAND_THREADS
@@ -131,7 +132,8 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
 #define GM(j, r) G(Lay::O_M + (j) * LDJ + (r))
 #define GTMP(i) G(Lay::O_TMP + (i))
 #define DSB_DIV(a, b) DsbDivShared::div((a), (b))
-    const BandVec vY{g + (size_t)Lay::O_Y * LS, LS}, vYC{g + (size_t)Lay::O_YC * LS, LS}, vTMP{g + (size_t)Lay::O_TMP * LS, LS};
+    const BandVec vY{g + (size_t)Lay::O_Y * LS, LS}, vYC{g + (size_t)Lay::O_YC * LS, LS}, vTMP{g + (size_t)Lay::O_TMP * LS, LS},
+                  vDL{g + (size_t)Lay::O_DL * LS, LS};
 
     const int64_t B = pa.nbatch;
     const int nt = pa.nt;
@@ -199,6 +201,33 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
         return DSB_DIV(acc, (double)N);
     };
 
+    // root finding (dsb_roots.cuh; bdf.rs:143, 301-306, 1566-1579): only compiled for equations with roots
+    constexpr int NR = dsb_model_nroots<M>::value;
+    LaneRootFinder<(NR > 0 ? NR : 1), DsbDivShared> rf;
+    rf.t0 = 0.0;
+    int root_found = -1;
+#pragma unroll
+    for (int r = 0; r < (NR > 0 ? NR : 1); ++r) rf.g0[r] = 0.0;
+    // interpolate (bdf.rs:767-782, 1080-1106): the time factors first, then one pass over the components
+    auto interpolate_to = [&](double tq, auto&& store) {
+        double tf[DSB_MAX_ORDER];
+        double time_factor = 1.0;
+#pragma unroll
+        for (int j = 0; j < DSB_MAX_ORDER; ++j) {
+            if (j < order) {
+                const double j_t = (double)j;
+                time_factor *= DSB_DIV(tq - (t - h * j_t), h * (1.0 + j_t));
+            }
+            tf[j] = time_factor;
+        }
+        band_for<U2, double>(N, [&](int i) {
+            double yo = GD(0, i);
+#pragma unroll
+            for (int j = 0; j < DSB_MAX_ORDER; ++j) if (j < order) yo = tf[j] * GD(j + 1, i) + yo;
+            return yo;
+        }, store);
+    };
+
     while (true) {
         // ---- warp-level block scheduler (dsb_bdf_kernel.cuh) ---------------------------------------------------
         const unsigned m_idle = __ballot_sync(0xffffffffu, state == L_IDLE);
@@ -213,6 +242,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
             bb.fin_t[inst] = t; bb.fin_h[inst] = h; bb.fin_order[inst] = order;
 #pragma unroll
             for (int k = 0; k < DSB_NSTATS; ++k) bb.stats[(int64_t)k * B + inst] = st.v[k];
+            if (NR > 0) { bb.ncols[inst] = col; bb.root_idx[inst] = root_found; }
             state = L_FETCH;
         }
         // ================= FETCH: next instance; new_without_initialise, set_step_size, Bdf::_new part 1 ==============
@@ -276,6 +306,10 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                 has_tstop = false; tstop = 0.0; has_prev_error = false; prev_error_norm = 0.0;
                 convergence_fail = false; first = true; reached = false; pending_etf = false; col = 0;
                 t_predict = t;
+                if constexpr (NR > 0) {                         // Bdf::_new: root_finder.init(root_fn, state.y, state.t)
+                    M::root(vY, pl, t, rf.g0);
+                    rf.t0 = t; root_found = -1;
+                }
                 jac_kind = DSB_KIND_CONSTRUCT;
                 state = L_JAC;
             }
@@ -465,9 +499,36 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
 
         // ================= TSTOP ==========================================================================================
         if (__any_sync(0xffffffffu, state == L_TSTOP) && state == L_TSTOP) {
+            bool stopped_on_root = false;
+            if constexpr (NR > 0) {
+                // check for a root within the accepted step (bdf.rs:1566-1579), after the step-size update and before the
+                // stop time is handled; the interpolated state of the secant iteration goes to the (free) Newton residual
+                if (!first) {
+                    double t_root = t;
+                    stopped_on_root = rf.check_root(t, [&](double (&gv)[NR]) { M::root(vY, pl, t, gv); },
+                                                    [&](double t_mid, double (&gv)[NR]) {
+                                                        interpolate_to(t_mid, [&](int i, double yo) { GDL(i) = yo; });
+                                                        M::root(vDL, pl, t_mid, gv);
+                                                    }, t_root, root_found);
+                    if (stopped_on_root) {
+                        // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root)
+                        // (bdf.rs:1228-1262), then the state at the root in the next column (method.rs:493-503)
+                        while (col < nt && bb.t_eval[col] <= t_root) {
+                            interpolate_to(bb.t_eval[col], [&](int i, double yo) { bb.ys[((int64_t)col * N + i) * B + inst] = yo; });
+                            ++col;
+                        }
+                        if (col < nt) {
+                            interpolate_to(t_root, [&](int i, double yo) { bb.ys[((int64_t)col * N + i) * B + inst] = yo; });
+                            ++col;
+                        }
+                        t = t_root;
+                        finish(DSB_STATUS_OK);
+                    }
+                }
+            }
             int next = first ? L_PREDICT : L_OUTPUT;
             int r = 0;
-            bool check = has_tstop;
+            bool check = has_tstop && !stopped_on_root;
             if (first) {
                 check = !free_running;
                 if (free_running) next = L_OUTPUT;
@@ -480,7 +541,9 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                     else reached = true;
                 }
             }
-            if (r < 0) {
+            if (stopped_on_root) {
+                // the lane is on its way to FINISH
+            } else if (r < 0) {
                 finish(-r);
             } else if (r == 2) {
                 rs_ignore_small = true;            // "step size too small" is ignored here (bdf.rs:726-728)
@@ -503,23 +566,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                 if (free_running ? (dsb_abs(t) < dsb_abs(tq)) : !(tq <= t)) break;
                 const bool is_forward = h > 0.0;
                 if ((is_forward && tq > t) || (!is_forward && tq < t)) { status = DSB_STATUS_INTERPOLATION_TIME_AFTER_CURRENT; break; }
-                // interpolate (bdf.rs:767-782, 1080-1106): the time factors first, then one pass over the components
-                double tf[DSB_MAX_ORDER];
-                double time_factor = 1.0;
-#pragma unroll
-                for (int j = 0; j < DSB_MAX_ORDER; ++j) {
-                    if (j < order) {
-                        const double j_t = (double)j;
-                        time_factor *= DSB_DIV(tq - (t - h * j_t), h * (1.0 + j_t));
-                    }
-                    tf[j] = time_factor;
-                }
-                band_for<U2, double>(N, [&](int i) {
-                    double yo = GD(0, i);
-#pragma unroll
-                    for (int j = 0; j < DSB_MAX_ORDER; ++j) if (j < order) yo = tf[j] * GD(j + 1, i) + yo;
-                    return yo;
-                }, [&](int i, double yo) { bb.ys[((int64_t)col * N + i) * B + inst] = yo; });
+                interpolate_to(tq, [&](int i, double yo) { bb.ys[((int64_t)col * N + i) * B + inst] = yo; });
                 ++col;
             }
             if (status != DSB_STATUS_OK) finish(status);

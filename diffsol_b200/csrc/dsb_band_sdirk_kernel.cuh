@@ -67,7 +67,8 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
 #define GAB(j, r) G(Lay::O_LU + (j) * LDAB + (r))
 #define GM(j, r) G(Lay::O_M + (j) * LDJ + (r))
 #define DSB_DIV(a, b) DsbDivShared::div((a), (b))
-    const BandVec vY{g + (size_t)Lay::O_Y * LS, LS}, vTMP{g + (size_t)Lay::O_TMP * LS, LS}, vX{g + (size_t)Lay::O_X * LS, LS};
+    const BandVec vY{g + (size_t)Lay::O_Y * LS, LS}, vTMP{g + (size_t)Lay::O_TMP * LS, LS}, vX{g + (size_t)Lay::O_X * LS, LS},
+                  vDL{g + (size_t)Lay::O_DL * LS, LS};
 
     const int64_t B = pa.nbatch;
     const int nt = pa.nt;
@@ -124,6 +125,47 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
         return DSB_DIV(acc, (double)N);
     };
 
+    // root finding (dsb_roots.cuh; runge_kutta.rs:43, 142-147, 935-948): only compiled for equations with roots
+    constexpr int NR = dsb_model_nroots<M>::value;
+    LaneRootFinder<(NR > 0 ? NR : 1), DsbDivShared> rf;
+    rf.t0 = 0.0;
+    int root_found = -1;
+#pragma unroll
+    for (int r = 0; r < (NR > 0 ? NR : 1); ++r) rf.g0[r] = 0.0;
+    // interpolate_inplace (runge_kutta.rs:1080-1127; :962-981 beta dense output, :1004-1024 Hermite) on [old_t, t]
+    auto interpolate_to = [&](double tq, auto&& store) {
+        const double dt = t - old_t;
+        const double theta = (dt == 0.0) ? 1.0 : DSB_DIV(tq - old_t, dt);
+        if (pa.rk.has_beta) {
+            const double th2 = theta * theta;
+            double bf[DSB_RK_MAX_STAGES];
+#pragma unroll
+            for (int j = 0; j < DSB_RK_MAX_STAGES; ++j) {
+                bf[j] = 0.0;
+                if (j < ns) { bf[j] = pa.rk.beta[j] * theta; bf[j] = pa.rk.beta[ns + j] * th2 + bf[j]; }
+            }
+            band_for<U2, double>(N, [&](int i) {
+                double yo = GOY(i);
+#pragma unroll
+                for (int j = 0; j < DSB_RK_MAX_STAGES; ++j) if (j < ns) yo = GDF(j, i) * bf[j] + yo;
+                return yo;
+            }, store);
+        } else {
+            const double al1 = theta - 1.0, be1 = 1.0 - 2.0 * theta;
+            const double al2 = 1.0 - theta, be2 = theta * (theta - 1.0);
+            band_for<U2, double>(N, [&](int i) {
+                const double u0 = GOY(i), u1 = GY(i);
+                double v = u1;
+                v -= u0;
+                v = al1 * GDF(0, i) + be1 * v;
+                v = theta * GDF(ns - 1, i) + v;
+                v = al2 * u0 + be2 * v;
+                v = theta * u1 + v;
+                return v;
+            }, store);
+        }
+    };
+
     while (true) {
         // ---- warp-level block scheduler (dsb_bdf_kernel.cuh) ---------------------------------------------------
         const unsigned m_idle = __ballot_sync(0xffffffffu, state == R_IDLE);
@@ -138,6 +180,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
             bb.fin_t[inst] = t; bb.fin_h[inst] = h_state; bb.fin_order[inst] = pa.rk.order;
 #pragma unroll
             for (int k = 0; k < DSB_NSTATS; ++k) bb.stats[(int64_t)k * B + inst] = st.v[k];
+            if (NR > 0) { bb.ncols[inst] = col; bb.root_idx[inst] = root_found; }
             state = R_FETCH;
         }
         // ================= FETCH: next instance; new_without_initialise, set_step_size, Rk::_new + Sdirk::_new ==
@@ -198,6 +241,10 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                 jacobian_is_stale = true; is_jacobian_set = false;
                 has_tstop = false; tstop = 0.0; has_prev_error = false; prev_error_norm = 0.0;
                 first = true; reached = false; col = 0;
+                if constexpr (NR > 0) {                         // Rk::_new: root_finder.init(root_fn, state.y, state.t)
+                    M::root(vY, pl, t, rf.g0);
+                    rf.t0 = t; root_found = -1;
+                }
                 state = R_TSTOP;
             }
         }
@@ -389,6 +436,33 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
         if (__any_sync(0xffffffffu, state == R_TSTOP) && state == R_TSTOP) {
             int r = 0;
             int next = first ? R_STEP : R_OUTPUT;
+            bool stopped_on_root = false;
+            if constexpr (NR > 0) {
+                // check for a root within the accepted step (runge_kutta.rs:935-948), before the stop time is handled;
+                // the interpolated state of the secant iteration goes to the (free) Newton residual
+                if (!first) {
+                    double t_root = t;
+                    stopped_on_root = rf.check_root(t, [&](double (&gv)[NR]) { M::root(vY, pl, t, gv); },
+                                                    [&](double t_mid, double (&gv)[NR]) {
+                                                        interpolate_to(t_mid, [&](int i, double yo) { GDL(i) = yo; });
+                                                        M::root(vDL, pl, t_mid, gv);
+                                                    }, t_root, root_found);
+                    if (stopped_on_root) {
+                        // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root)
+                        // (runge_kutta.rs:396-434), then the state at the root in the next column (method.rs:493-503)
+                        while (col < nt && bb.t_eval[col] <= t_root) {
+                            interpolate_to(bb.t_eval[col], [&](int i, double yo) { bb.ys[((int64_t)col * N + i) * B + inst] = yo; });
+                            ++col;
+                        }
+                        if (col < nt) {
+                            interpolate_to(t_root, [&](int i, double yo) { bb.ys[((int64_t)col * N + i) * B + inst] = yo; });
+                            ++col;
+                        }
+                        t = t_root;
+                        finish(DSB_STATUS_OK);
+                    }
+                }
+            }
             if (first) {
                 if (free_running) next = R_OUTPUT;
                 else {
@@ -396,11 +470,13 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                     r = handle_tstop(tstop);
                     if (r == 1) r = -DSB_STATUS_STOP_TIME_AT_CURRENT;
                 }
-            } else if (has_tstop) {
+            } else if (has_tstop && !stopped_on_root) {
                 r = handle_tstop(tstop);
                 if (r == 1) { reached = true; has_tstop = false; }
             }
-            if (r < 0) finish(-r);
+            if (stopped_on_root) {
+                // the lane is on its way to FINISH
+            } else if (r < 0) finish(-r);
             else state = next;
             first = false;
         }
@@ -415,36 +491,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                 if ((is_forward && (tq > t || tq < old_t)) || (!is_forward && (tq < t || tq > old_t))) {
                     status = DSB_STATUS_INTERPOLATION_TIME_AFTER_CURRENT; break;
                 }
-                const double dt = t - old_t;
-                const double theta = (dt == 0.0) ? 1.0 : DSB_DIV(tq - old_t, dt);
-                if (pa.rk.has_beta) {
-                    const double th2 = theta * theta;
-                    double bf[DSB_RK_MAX_STAGES];
-#pragma unroll
-                    for (int j = 0; j < DSB_RK_MAX_STAGES; ++j) {
-                        bf[j] = 0.0;
-                        if (j < ns) { bf[j] = pa.rk.beta[j] * theta; bf[j] = pa.rk.beta[ns + j] * th2 + bf[j]; }
-                    }
-                    band_for<U2, double>(N, [&](int i) {
-                        double yo = GOY(i);
-#pragma unroll
-                        for (int j = 0; j < DSB_RK_MAX_STAGES; ++j) if (j < ns) yo = GDF(j, i) * bf[j] + yo;
-                        return yo;
-                    }, [&](int i, double yo) { bb.ys[((int64_t)col * N + i) * B + inst] = yo; });
-                } else {
-                    const double al1 = theta - 1.0, be1 = 1.0 - 2.0 * theta;
-                    const double al2 = 1.0 - theta, be2 = theta * (theta - 1.0);
-                    band_for<U2, double>(N, [&](int i) {
-                        const double u0 = GOY(i), u1 = GY(i);
-                        double v = u1;
-                        v -= u0;
-                        v = al1 * GDF(0, i) + be1 * v;
-                        v = theta * GDF(ns - 1, i) + v;
-                        v = al2 * u0 + be2 * v;
-                        v = theta * u1 + v;
-                        return v;
-                    }, [&](int i, double v) { bb.ys[((int64_t)col * N + i) * B + inst] = v; });
-                }
+                interpolate_to(tq, [&](int i, double yo) { bb.ys[((int64_t)col * N + i) * B + inst] = yo; });
                 ++col;
             }
             if (status != DSB_STATUS_OK) finish(status);

@@ -44,6 +44,7 @@
 //   fn solve_dense               ode_solver/method.rs:721-848
 #pragma once
 #include "dsb_lane.cuh"
+#include "dsb_roots.cuh"
 
 enum dsb_lane_state {
     L_FETCH = 0, L_POST, L_SELECT, L_RESCALE, L_JAC, L_TSTOP, L_OUTPUT, L_PREDICT, L_NEWTON, L_FINISH, L_IDLE
@@ -127,11 +128,11 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
     auto finish = [&](int status) { fin_status = status; state = L_FINISH; };
     // root finding (nonlinear_solver/root.rs; bdf.rs:143, 301-306, 1566-1579): only compiled for equations with roots
     constexpr int NR = dsb_model_nroots<M>::value;
-    double rf_g0[NR > 0 ? NR : 1];
-    double rf_t0 = 0.0;
+    LaneRootFinder<(NR > 0 ? NR : 1), DsbDivShared> rf;
+    rf.t0 = 0.0;
     int root_found = -1;
 #pragma unroll
-    for (int r = 0; r < (NR > 0 ? NR : 1); ++r) rf_g0[r] = 0.0;
+    for (int r = 0; r < (NR > 0 ? NR : 1); ++r) rf.g0[r] = 0.0;
     // interpolate (bdf.rs:767-782, 1080-1106) at tq <= t from the difference array
     auto interpolate = [&](double tq, double (&yo)[N]) {
         double time_factor = 1.0;
@@ -254,8 +255,8 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                     for (int i = 0; i < N; ++i) y0l[i] = SY(i);
 #pragma unroll
                     for (int j = 0; j < NP; ++j) pl0[j] = SP(j);
-                    M::root(y0l, pl0, t, rf_g0);
-                    rf_t0 = t; root_found = -1;
+                    M::root(y0l, pl0, t, rf.g0);
+                    rf.t0 = t; root_found = -1;
                 }
                 c = h * pa.tab.alpha[1];
                 jacobian_is_stale = true;
@@ -441,90 +442,18 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                 // the stop time is handled; RootFinder::check_root (root.rs:60-160) with Vector::root_finding
                 // (diffsol-la/src/vector/nalgebra_serial.rs:484-504)
                 if (!first) {
-                    double pl[NP > 0 ? NP : 1], ys[N], g_end[NR], g1[NR], gmid[NR], ymid[N];
+                    double pl[NP > 0 ? NP : 1], ys[N];
 #pragma unroll
                     for (int j = 0; j < NP; ++j) pl[j] = SP(j);
 #pragma unroll
                     for (int i = 0; i < N; ++i) ys[i] = SY(i);
-                    M::root(ys, pl, t, g_end);
-#pragma unroll
-                    for (int r = 0; r < NR; ++r) g1[r] = g_end[r];
-                    auto root_finding = [&](const double (&ga)[NR], const double (&gb)[NR], bool& found, int& imax) {
-                        double max_frac = 0.0;
-                        imax = -1; found = false;
-#pragma unroll
-                        for (int r = 0; r < NR; ++r) {
-                            if (gb[r] == 0.0) found = true;
-                            if (ga[r] * gb[r] < 0.0) {
-                                const double frac = dsb_abs(DSB_DIV(gb[r], gb[r] - ga[r]));
-                                if (frac > max_frac) { max_frac = frac; imax = r; }
-                            }
-                        }
-                    };
-                    auto pick = [&](const double (&g)[NR], int k) { double v = g[0];
-#pragma unroll
-                        for (int r = 1; r < NR; ++r) if (k == r) v = g[r];
-                        return v; };
-                    bool rootfnd; int imax;
-                    root_finding(rf_g0, g1, rootfnd, imax);
                     double t_root = t;
-                    if (imax < 0) {
-#pragma unroll
-                        for (int r = 0; r < NR; ++r) rf_g0[r] = g1[r];
-                        rf_t0 = t;
-                        if (rootfnd) {                              // find_zero_index: smallest |g|, first one on ties
-                            int min_idx = 0; double min_val = dsb_abs(rf_g0[0]);
-#pragma unroll
-                            for (int r = 1; r < NR; ++r) { const double v = dsb_abs(rf_g0[r]); if (v < min_val) { min_val = v; min_idx = r; } }
-                            stopped_on_root = true; root_found = min_idx;
-                        }
-                    } else {
-                        double alpha = 1.0;
-                        bool sc0 = false, sc1 = true;
-                        int it = 0;
-                        double t1 = t, tl = rf_t0;
-                        const double tol = 100.0 * eps * (dsb_abs(t1) + dsb_abs(t1 - tl));
-                        bool done = false;
-                        while (!done && dsb_abs(t1 - tl) > tol) {
-                            const double g1_val = pick(g1, imax), g0_val = pick(rf_g0, imax);
-                            double t_mid = t1 - DSB_DIV((t1 - tl) * g1_val, g1_val - alpha * g0_val);
-                            if (dsb_abs(t_mid - tl) < 0.5 * tol) {
-                                const double fracint = DSB_DIV(dsb_abs(t1 - tl), tol);
-                                const double fracsub = fracint > 5.0 ? 0.1 : DSB_DIV(0.5, fracint);
-                                t_mid = tl + fracsub * (t1 - tl);
-                            }
-                            if (dsb_abs(t1 - t_mid) < 0.5 * tol) {
-                                const double fracint = DSB_DIV(dsb_abs(t1 - tl), tol);
-                                const double fracsub = fracint > 5.0 ? 0.1 : DSB_DIV(0.5, fracint);
-                                t_mid = t1 - fracsub * (t1 - tl);
-                            }
-                            interpolate(t_mid, ymid);
-                            M::root(ymid, pl, t_mid, gmid);
-                            bool rf; int im;
-                            root_finding(rf_g0, gmid, rf, im);
-                            const bool lower = im >= 0;
-                            if (lower) {
-                                t1 = t_mid; imax = im;
-#pragma unroll
-                                for (int r = 0; r < NR; ++r) g1[r] = gmid[r];
-                            } else if (rf) {
-                                t_root = t_mid; done = true;
-                            } else {
-                                tl = t_mid;
-#pragma unroll
-                                for (int r = 0; r < NR; ++r) rf_g0[r] = gmid[r];
-                            }
-                            if (!done) {
-                                if ((it & 1) == 0) sc0 = lower; else sc1 = lower;
-                                if (it >= 2) alpha = (sc0 != sc1) ? 1.0 : (sc0 ? 0.5 * alpha : 2.0 * alpha);
-                                ++it;
-                            }
-                        }
-                        if (!done) t_root = t1;
-#pragma unroll
-                        for (int r = 0; r < NR; ++r) rf_g0[r] = g_end[r];      // root_fn(y, t) again, into g0
-                        stopped_on_root = true; root_found = imax;
-                    }
+                    stopped_on_root = rf.check_root(t, [&](double (&g)[NR]) { M::root(ys, pl, t, g); },
+                                                    [&](double t_mid, double (&g)[NR]) {
+                                                        double ymid[N];
+                                                        interpolate(t_mid, ymid);
+                                                        M::root(ymid, pl, t_mid, g);
+                                                    }, t_root, root_found);
                     if (stopped_on_root) {
                         // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root)
                         // (bdf.rs:1228-1262), then the state at the root in the next column (method.rs:493-503)

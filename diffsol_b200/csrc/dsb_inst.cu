@@ -273,8 +273,8 @@ cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const
     } else if (coop->exec_mode == 3) {
         return cudaErrorNotSupported;
     }
-    // root functions (events) are built into the BDF lane kernel only
-    if (dsb_model_nroots<InstModel>::value > 0 && (method != DSB_METHOD_BDF || coop->exec_mode >= 2)) return cudaErrorNotSupported;
+    // root functions (events) are built into the lane kernels (on-chip and banded), not into the block-per-instance path
+    if (dsb_model_nroots<InstModel>::value > 0 && coop->exec_mode == 2) return cudaErrorNotSupported;
     const bool use_coop = coop->exec_mode == 2 || (coop->exec_mode == 0 && !kLaneCapable);
     if (use_coop) {
         if (method != DSB_METHOD_BDF) return cudaErrorNotSupported;   // cooperative path: BDF only

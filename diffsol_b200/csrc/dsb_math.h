@@ -220,3 +220,103 @@ DSB_HD double dsb_powi(double a, int b) {
     }
     return recip ? 1.0 / r : r;
 }
+
+// ---- exp / log / tanh / asinh for model output and event functions (the battery model's terminal voltage) ----------
+// Same tables and the same IEEE-only operation sequences as dsb_pow_core, so host and device agree bit for bit.  They
+// are NOT correctly rounded (exp and log: below 1 ulp; tanh and asinh: absolute error of a few 1e-16, relative error
+// that grows for |x| << 1), which is all an event threshold on a voltage needs; parity with the reference's libm
+// values is a tolerance, parity between the oracle and the kernels is exact.
+DSB_HD double dsb_exp(double x) {
+    const double inf = dsb_from_bits(0x7ff0000000000000ULL);
+    if (x != x) return x;
+    if (x > 709.8) return inf;
+    if (x < -745.2) return 0.0;
+    double zz = x * DSB_EXP_INVLN2N;
+    double kk = dsb_rint(zz);
+    int64_t ki = (int64_t)kk;
+    double rr = x - kk * DSB_EXP_LN2N_HI;
+    rr = rr - kk * DSB_EXP_LN2N_LO;
+    int j = (int)(ki & 127);
+    int64_t kq = ki >> 7;
+#if defined(__CUDA_ARCH__)
+    const dsb_exp_row er = dsb_exp_table_dev[j];
+#else
+    const dsb_exp_row er = dsb_exp_table_host[j];
+#endif
+    double rr2 = rr * rr;
+    double pe = rr + rr2 * (0.5 + rr * (1.0 / 6.0)) + (rr2 * rr2) * (1.0 / 24.0 + rr * (1.0 / 120.0 + rr * (1.0 / 720.0)));
+    double val = er.hi + (er.lo + er.hi * pe);
+    int64_t k1 = kq / 2;
+    int64_t k2 = kq - k1;
+    double sc1 = dsb_from_bits((uint64_t)(k1 + 1023) << 52);
+    double sc2 = dsb_from_bits((uint64_t)(k2 + 1023) << 52);
+    return (val * sc1) * sc2;
+}
+// natural logarithm of a positive, finite, normal x (anything else: NaN for x < 0 or NaN, -inf for 0, x for +inf;
+// subnormals are scaled first)
+DSB_HD double dsb_log(double x) {
+    const double inf = dsb_from_bits(0x7ff0000000000000ULL);
+    if (x != x || x < 0.0) return dsb_from_bits(0x7ff8000000000000ULL);
+    if (x == 0.0) return -inf;
+    if (x == inf) return x;
+    uint64_t ix = dsb_bits(x);
+    int sub = 0;
+    if (ix < 0x0010000000000000ULL) { ix = dsb_bits(x * 4503599627370496.0); sub = 52; }
+    const uint64_t OFF = 0x3FE6955500000000ULL;
+    uint64_t tmp = ix - OFF;
+    int i = (int)((tmp >> 45) & 127);
+    int k = (int)((int64_t)tmp >> 52) - sub;
+    uint64_t iz = ix - (tmp & 0xfff0000000000000ULL);
+    double z = dsb_from_bits(iz);
+    double kd = (double)k;
+#if defined(__CUDA_ARCH__)
+    const dsb_log_row row = dsb_log_table_dev[i];
+#else
+    const dsb_log_row row = dsb_log_table_host[i];
+#endif
+    double p_hi = z * row.invc;
+    double p_lo = dsb_fma(z, row.invc, -p_hi);
+    double q = p_hi - 1.0;
+    double r_hi = q + p_lo;
+    double r_lo = (q - r_hi) + p_lo;
+    double ar = -0.5 * r_hi;
+    double s_hi = r_hi * ar;
+    double s_lo = dsb_fma(r_hi, ar, -s_hi);
+    double r2 = r_hi * r_hi;
+    double poly = 1.0 / 3.0 + r_hi * (-0.25 + r_hi * (0.2 + r_hi * (-1.0 / 6.0 + r_hi * (1.0 / 7.0
+                  + r_hi * (-0.125 + r_hi * (1.0 / 9.0))))));
+    double tail = (r2 * r_hi) * poly;
+    double a0 = kd * DSB_LN2_HI;
+    double t1 = a0 + row.logc_hi;
+    double e1 = (a0 - t1) + row.logc_hi;
+    double t2 = t1 + r_hi;
+    double bb = t2 - t1;
+    double e2 = (t1 - (t2 - bb)) + (r_hi - bb);
+    double t3 = t2 + s_hi;
+    bb = t3 - t2;
+    double e3 = (t2 - (t3 - bb)) + (s_hi - bb);
+    double lo = kd * DSB_LN2_LO + row.logc_lo;
+    lo = lo + e1;
+    lo = lo + e2;
+    lo = lo + e3;
+    lo = lo + r_lo;
+    lo = lo + s_lo;
+    lo = lo - r_hi * r_lo;
+    lo = lo + tail;
+    return t3 + lo;
+}
+DSB_HD double dsb_tanh(double x) {
+    if (x != x) return x;
+    const double a = dsb_abs(x);
+    if (a < 1e-8) return x;
+    double r = 1.0;
+    if (a < 20.0) r = 1.0 - 2.0 / (dsb_exp(2.0 * a) + 1.0);
+    return x < 0.0 ? -r : r;
+}
+DSB_HD double dsb_asinh(double x) {
+    if (x != x) return x;
+    const double a = dsb_abs(x);
+    if (a < 1e-8) return x;
+    const double r = (a > 1e100) ? dsb_log(a) + 0.6931471805599453 : dsb_log(a + dsb_sqrt(a * a + 1.0));
+    return x < 0.0 ? -r : r;
+}

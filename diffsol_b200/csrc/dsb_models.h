@@ -29,6 +29,8 @@ enum dsb_model_id {
     DSB_MODEL_SPM = 11,                 // n=42  np=1  single-particle battery model, book/src/primer/src/spm.ds (BASELINE config 5)
     DSB_MODEL_SPM99 = 12,               // n=200 np=1  the same model on 99 radial cells per particle (not in the reference)
     DSB_MODEL_EXP_DECAY_ROOT = 13,      // n=2  np=2   exp_decay with the root y[0] - 0.6 (test_models/exponential_decay.rs:370-390)
+    DSB_MODEL_SPM_STOP = 14,            // n=42 np=1   spm with the model text's stop function: terminal voltage leaves [3.105, 4.1] V
+    DSB_MODEL_SPM99_STOP = 15,          // n=200 np=1  the same on 99 radial cells per particle
     DSB_MODEL_COUNT
 };
 
@@ -367,6 +369,65 @@ struct ModelSpmT {
 typedef ModelSpmT<SpmTables20> ModelSpm;
 typedef ModelSpmT<SpmTables99> ModelSpm99;
 
+// The battery model WITH its stop function (spm.ds `stop_i`: the terminal voltage leaves the window [3.105 V, 4.1 V]),
+// i.e. with `OdeEquations::root`: the integration ends at the first voltage cut-off exactly as in the reference's
+// battery example (examples/physics-based-battery-simulation/src/main.rs: `RootFound(t, _) => finished`).
+// voltage(x, I) restates `out_i` term by term, in the model text's order.  The surface concentrations are the
+// two-point extrapolations of the model text (constant5 / 8 / 9 / 10: rows over the outermost two cells of a particle;
+// products summed in the order the text lists them).  exp / tanh / arcsinh are the shared deterministic dsb_math.h
+// versions, sqrt is correctly rounded: oracle and kernels agree bit for bit, the reference (libm) to ~1e-15.
+template <class Tab>
+struct ModelSpmStopT : ModelSpmT<Tab> {
+    typedef ModelSpmT<Tab> Base;
+    static constexpr int NR = Base::NR, N = Base::N;
+    static constexpr int NROOTS = 2;
+    template <class X>
+    DSB_HD static double voltage(const X& x, const double* p) {
+        const double cur = p[0];
+        const double cn18 = x[2 + NR - 2], cn19 = x[2 + NR - 1];               // negative particle, outermost cells
+        const double cp18 = x[2 + 2 * NR - 2], cp19 = x[2 + 2 * NR - 1];       // positive particle
+        const double v2 = -25608.96286546366 * cp18 + 76826.88859639116 * cp19;
+        const double v3 = -0.4999999999999983 * cp18 + 1.4999999999999982 * cp19;
+        const double v4 = -12491.630996921805 * cn18 + 37474.892990765504 * cn19;
+        const double v5 = -0.4999999999999983 * cn18 + 1.4999999999999984 * cn19;
+        auto clamp = [](double v, double hi, double lo) { const double m = v < hi ? v : hi; return m > lo ? m : lo; };   // max(min(v, hi), lo)
+        const double cps = clamp(v2, 51217.92521874824, 0.000512179257309275);
+        const double xp = clamp(v3, 0.9999999999, 1e-10);
+        const double cns = clamp(v4, 24983.261744011077, 0.000249832619938437);
+        const double xn = clamp(v5, 0.9999999999, 1e-10);
+        const double eta_p = 0.05138515824298745 * dsb_asinh((-2.3508116177110145 * cur)
+                             / (2.0 * ((1.8973665961010275e-05 * dsb_sqrt(cps)) * dsb_sqrt(51217.9257309275 - cps))));
+        double up = 2.16216 + 0.07645 * dsb_tanh(30.834 - 57.858397200000006 * xp);
+        up = up + 2.1581 * dsb_tanh(52.294 - 53.412228 * xp);
+        up = up - 0.14169 * dsb_tanh(11.0923 - 21.0852666 * xp);
+        up = up + 0.2051 * dsb_tanh(1.4684 - 5.829105600000001 * xp);
+        up = up + 0.2531 * dsb_tanh(4.291641337386018 - 8.069908814589667 * xp);
+        up = up - 0.02167 * dsb_tanh(-87.5 + 177.0 * xp);
+        up = up + 1e-06 * ((1.0 / xp) + (1.0 / (-1.0 + xp)));
+        const double eta_n = 0.05138515824298745 * dsb_asinh((1.9590096814258458 * cur)
+                             / (2.0 * ((0.0006324555320336759 * dsb_sqrt(cns)) * dsb_sqrt(24983.2619938437 - cns))));
+        double un = 0.194 + 1.5 * dsb_exp(-120.0 * xn);
+        un = un + 0.0351 * dsb_tanh(-3.44578313253012 + 12.048192771084336 * xn);
+        un = un - 0.0045 * dsb_tanh(-7.1344537815126055 + 8.403361344537815 * xn);
+        un = un - 0.035 * dsb_tanh(-18.466 + 20.0 * xn);
+        un = un - 0.0147 * dsb_tanh(-14.705882352941176 + 29.41176470588235 * xn);
+        un = un - 0.102 * dsb_tanh(-1.3661971830985917 + 7.042253521126761 * xn);
+        un = un - 0.022 * dsb_tanh(-54.8780487804878 + 60.975609756097555 * xn);
+        un = un - 0.011 * dsb_tanh(-5.486725663716814 + 44.24778761061947 * xn);
+        un = un + 0.0155 * dsb_tanh(-3.6206896551724133 + 34.48275862068965 * xn);
+        un = un + 1e-06 * ((1.0 / xn) + (1.0 / (-1.0 + xn)));
+        return (eta_p + up) - (eta_n + un);
+    }
+    template <class X>
+    DSB_HD static void root(const X& x, const double* p, double, double* g) {
+        const double v = voltage(x, p);
+        g[0] = -3.105 + v;
+        g[1] = 4.1 - v;
+    }
+};
+typedef ModelSpmStopT<SpmTables20> ModelSpmStop;
+typedef ModelSpmStopT<SpmTables99> ModelSpm99Stop;
+
 // id -> functor type
 template <int ID> struct dsb_model_by_id;
 template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY> { typedef ModelExpDecay type; };
@@ -383,6 +444,8 @@ template <> struct dsb_model_by_id<DSB_MODEL_HEAT1D_DAE_32> { typedef ModelHeat1
 template <> struct dsb_model_by_id<DSB_MODEL_SPM> { typedef ModelSpm type; };
 template <> struct dsb_model_by_id<DSB_MODEL_SPM99> { typedef ModelSpm99 type; };
 template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY_ROOT> { typedef ModelExpDecayRoot type; };
+template <> struct dsb_model_by_id<DSB_MODEL_SPM_STOP> { typedef ModelSpmStop type; };
+template <> struct dsb_model_by_id<DSB_MODEL_SPM99_STOP> { typedef ModelSpm99Stop type; };
 
 // traits of an equation set: written component-wise (`*_i` functions), declares a band for df/dy
 template <class M, class = void> struct dsb_is_componentwise : std::false_type {};
@@ -408,6 +471,8 @@ inline bool dsb_dispatch_model(int id, F&& f) {
         case DSB_MODEL_SPM: f.template operator()<ModelSpm>(); return true;
         case DSB_MODEL_SPM99: f.template operator()<ModelSpm99>(); return true;
         case DSB_MODEL_EXP_DECAY_ROOT: f.template operator()<ModelExpDecayRoot>(); return true;
+        case DSB_MODEL_SPM_STOP: f.template operator()<ModelSpmStop>(); return true;
+        case DSB_MODEL_SPM99_STOP: f.template operator()<ModelSpm99Stop>(); return true;
         default: return false;
     }
 }

@@ -22,6 +22,7 @@
 // Newton iteration count of the last stage only; the error estimate is filtered through the LU.
 #pragma once
 #include "dsb_lane.cuh"
+#include "dsb_roots.cuh"
 
 enum dsb_rk_lane_state {
     R_FETCH = 0, R_FINISH, R_ERRTEST, R_JAC, R_ACCEPT, R_TSTOP, R_OUTPUT, R_STEP, R_ATTEMPT, R_STAGE, R_NEWTON, R_POST, R_IDLE
@@ -102,6 +103,44 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
     double jac_h = 0.0;
     int fin_status = DSB_STATUS_OK;
     auto finish = [&](int status) { fin_status = status; state = R_FINISH; };
+    // root finding (nonlinear_solver/root.rs; runge_kutta.rs:43, 142-147, 935-948): only compiled for equations with roots
+    constexpr int NR = dsb_model_nroots<M>::value;
+    LaneRootFinder<(NR > 0 ? NR : 1), DsbDivInline> rf;
+    rf.t0 = 0.0;
+    int root_found = -1;
+#pragma unroll
+    for (int r = 0; r < (NR > 0 ? NR : 1); ++r) rf.g0[r] = 0.0;
+    // interpolate_inplace (runge_kutta.rs:1080-1127; :962-981 beta dense output, :1004-1024 Hermite) on [old_t, t]
+    auto interpolate = [&](double tq, double (&yo)[N]) {
+        const double dt = t - old_t;
+        const double theta = (dt == 0.0) ? 1.0 : DSB_DIV(tq - old_t, dt);
+        if (pa.rk.has_beta) {
+            const double th2 = theta * theta;
+#pragma unroll
+            for (int i = 0; i < N; ++i) yo[i] = SOY(i);
+#pragma unroll 1
+            for (int j = 0; j < ns; ++j) {
+                double bf = pa.rk.beta[j] * theta;
+                bf = pa.rk.beta[ns + j] * th2 + bf;
+#pragma unroll
+                for (int i = 0; i < N; ++i) yo[i] = SDF(j, i) * bf + yo[i];
+            }
+        } else {
+            const double al1 = theta - 1.0, be1 = 1.0 - 2.0 * theta;
+            const double al2 = 1.0 - theta, be2 = theta * (theta - 1.0);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double u0 = SOY(i), u1 = SY(i);
+                double v = u1;
+                v -= u0;
+                v = al1 * SDF(0, i) + be1 * v;
+                v = theta * SDF(ns - 1, i) + v;
+                v = al2 * u0 + be2 * v;
+                v = theta * u1 + v;
+                yo[i] = v;
+            }
+        }
+    };
 
     // runge_kutta.rs:752-781.  0 = nothing, 1 = TstopReached, < 0 = -status
     auto handle_tstop = [&](double ts) -> int {
@@ -129,6 +168,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
             bb.fin_t[inst] = t; bb.fin_h[inst] = h_state; bb.fin_order[inst] = pa.rk.order;
 #pragma unroll
             for (int k = 0; k < DSB_NSTATS; ++k) bb.stats[(int64_t)k * B + inst] = st.v[k];
+            if (NR > 0) { bb.ncols[inst] = col; bb.root_idx[inst] = root_found; }
             state = R_FETCH;
         }
         // ================= FETCH: next instance; Rk::_new + Sdirk::_new =========================================
@@ -160,6 +200,15 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                 jacobian_is_stale = true; is_jacobian_set = false;
                 has_tstop = false; tstop = 0.0; has_prev_error = false; prev_error_norm = 0.0;
                 first = true; reached = false; col = 0;
+                if constexpr (NR > 0) {                         // Rk::_new: root_finder.init(root_fn, state.y, state.t)
+                    double y0l[N], pl0[NP > 0 ? NP : 1];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) y0l[i] = SY(i);
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) pl0[j] = SP(j);
+                    M::root(y0l, pl0, t, rf.g0);
+                    rf.t0 = t; root_found = -1;
+                }
                 state = R_TSTOP;
             }
         }
@@ -337,6 +386,43 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
         if (__any_sync(0xffffffffu, state == R_TSTOP) && state == R_TSTOP) {
             int r = 0;
             int next = first ? R_STEP : R_OUTPUT;
+            bool stopped_on_root = false;
+            if constexpr (NR > 0) {
+                // check for a root within the accepted step (runge_kutta.rs:935-948), before the stop time is handled
+                if (!first) {
+                    double pl[NP > 0 ? NP : 1], ys[N];
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) pl[j] = SP(j);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) ys[i] = SY(i);
+                    double t_root = t;
+                    stopped_on_root = rf.check_root(t, [&](double (&g)[NR]) { M::root(ys, pl, t, g); },
+                                                    [&](double t_mid, double (&g)[NR]) {
+                                                        double ymid[N];
+                                                        interpolate(t_mid, ymid);
+                                                        M::root(ymid, pl, t_mid, g);
+                                                    }, t_root, root_found);
+                    if (stopped_on_root) {
+                        // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root)
+                        // (runge_kutta.rs:396-434), then the state at the root in the next column (method.rs:493-503)
+                        double yo[N];
+                        while (col < nt && bb.t_eval[col] <= t_root) {
+                            interpolate(bb.t_eval[col], yo);
+#pragma unroll
+                            for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
+                            ++col;
+                        }
+                        interpolate(t_root, yo);
+                        if (col < nt) {
+#pragma unroll
+                            for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
+                            ++col;
+                        }
+                        t = t_root;
+                        finish(DSB_STATUS_OK);
+                    }
+                }
+            }
             if (first) {
                 if (free_running) next = R_OUTPUT;
                 else {
@@ -344,11 +430,13 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                     r = handle_tstop(tstop);
                     if (r == 1) r = -DSB_STATUS_STOP_TIME_AT_CURRENT;
                 }
-            } else if (has_tstop) {
+            } else if (has_tstop && !stopped_on_root) {
                 r = handle_tstop(tstop);
                 if (r == 1) { reached = true; has_tstop = false; }
             }
-            if (r < 0) finish(-r);
+            if (stopped_on_root) {
+                // the lane is on its way to FINISH
+            } else if (r < 0) finish(-r);
             else state = next;
             first = false;
         }
@@ -363,35 +451,8 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                 if ((is_forward && (tq > t || tq < old_t)) || (!is_forward && (tq < t || tq > old_t))) {
                     status = DSB_STATUS_INTERPOLATION_TIME_AFTER_CURRENT; break;
                 }
-                const double dt = t - old_t;
-                const double theta = (dt == 0.0) ? 1.0 : DSB_DIV(tq - old_t, dt);
                 double yo[N];
-                if (pa.rk.has_beta) {
-                    const double th2 = theta * theta;
-#pragma unroll
-                    for (int i = 0; i < N; ++i) yo[i] = SOY(i);
-#pragma unroll 1
-                    for (int j = 0; j < ns; ++j) {
-                        double bf = pa.rk.beta[j] * theta;
-                        bf = pa.rk.beta[ns + j] * th2 + bf;
-#pragma unroll
-                        for (int i = 0; i < N; ++i) yo[i] = SDF(j, i) * bf + yo[i];
-                    }
-                } else {
-                    const double al1 = theta - 1.0, be1 = 1.0 - 2.0 * theta;
-                    const double al2 = 1.0 - theta, be2 = theta * (theta - 1.0);
-#pragma unroll
-                    for (int i = 0; i < N; ++i) {
-                        const double u0 = SOY(i), u1 = SY(i);
-                        double v = u1;
-                        v -= u0;
-                        v = al1 * SDF(0, i) + be1 * v;
-                        v = theta * SDF(ns - 1, i) + v;
-                        v = al2 * u0 + be2 * v;
-                        v = theta * u1 + v;
-                        yo[i] = v;
-                    }
-                }
+                interpolate(tq, yo);
 #pragma unroll
                 for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
                 ++col;

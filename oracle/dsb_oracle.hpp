@@ -75,7 +75,10 @@ struct Model {
     void (*root)(const double*, const double*, double, double*) = nullptr;
 };
 template <class M, int NR = dsb_model_nroots<M>::value> struct RootOf {
-    static void set(Model& m) { m.nroots = NR; m.root = &M::root; }
+    static void set(Model& m) {          // M::root may be a template over the state accessor (component-wise models)
+        m.nroots = NR;
+        m.root = [](const double* x, const double* p, double t, double* g) { M::root(x, p, t, g); };
+    }
 };
 template <class M> struct RootOf<M, 0> { static void set(Model&) {} };
 template <class M>

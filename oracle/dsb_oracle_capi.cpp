@@ -88,6 +88,23 @@ int orc_model_dims(int model_id, int* n, int* np, int* has_mass) {
     return ST_OK;
 }
 
+// root (event) functions of a model at (y, p, t): g[nroots]; returns the number of root functions
+int orc_model_root(int model_id, const double* y, const double* p, double t, double* g) {
+    Model m;
+    if (!model_by_id(model_id, &m)) return -1;
+    if (m.nroots > 0) m.root(y, p, t, g);
+    return m.nroots;
+}
+// the shared deterministic elementary functions of csrc/dsb_math.h: which = 0 exp, 1 log, 2 tanh, 3 asinh
+double orc_math(int which, double x) {
+    switch (which) {
+        case 0: return dsb_exp(x);
+        case 1: return dsb_log(x);
+        case 2: return dsb_tanh(x);
+        default: return dsb_asinh(x);
+    }
+}
+
 // `problem.bdf::<LS>()?.solve_dense(t_eval)`: out is n x nt column-major; fin = {t, h, order}; root (may be NULL) =
 // {t_root, root index (-1: the integration did not stop on a root), number of columns written}
 static int solve_dense_one(const orc_problem_desc* d, const double* p, int np, const double* t_eval, int nt,

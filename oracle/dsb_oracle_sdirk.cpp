@@ -2,7 +2,7 @@
 // Restatement of `Sdirk` (crates/diffsol/src/ode_solver/sdirk.rs:147-543), the shared Runge-Kutta
 // core `Rk` (ode_solver/runge_kutta.rs:100-175, 446-960, 1080-1127), `SdirkCallable`
 // (crates/diffsol/src/op/sdirk.rs) and the TR-BDF2 / ESDIRK34 tableaux (ode_solver/tableau.rs:41-159),
-// without sensitivities, output integration or root finding.  Vector / matrix products follow the
+// without sensitivities or output integration.  Vector / matrix products follow the
 // evaluation order of nalgebra's `gemv` / `axpy` (first term assigned when beta == 0, the others added
 // one column at a time; every term is `alpha * a_ij * x_j`).
 //
@@ -83,6 +83,9 @@ struct Sdirk : Method {
     double c = 0, op_h = 0;
     Vec phi, tmp, rhs_jac, mass_jac, newton_tmp, A;
     bool jacobian_is_stale = true;
+    // root finding (runge_kutta.rs:43, 142-147, 935-948)
+    RootFinder root_finder;
+    double root_t_ = 0.0; int root_idx_ = -1;
 
     Sdirk(const Problem& p, const Tableau& t) : pr(p), n(p.n()), tab(t) {}
 
@@ -96,6 +99,10 @@ struct Sdirk : Method {
         if (err) return err;
         y_ = st.y; dy_ = st.dy; t_ = st.t; h_ = st.h;
         oy_ = y_; ody_ = dy_; ot_ = t_; oh_ = h_;             // old_state = state.clone()
+        if (pr.model.nroots > 0) {                             // Rk::_new, runge_kutta.rs:142-147
+            root_finder.resize(pr.model.nroots, n);
+            root_finder.init(pr, y_.data(), t_);
+        }
         diff.assign((size_t)n * tab.s, 0.0);
         error.assign(n, 0.0);
         jacobian_update.init(pr.opt, 1.0);
@@ -313,6 +320,11 @@ struct Sdirk : Method {
         }
         std::swap(y_, oy_); std::swap(dy_, ody_); std::swap(t_, ot_); std::swap(h_, oh_);
         statistics.v[S_STEPS] += 1;
+        // check for a root within the accepted step (runge_kutta.rs:935-948)
+        if (pr.model.nroots > 0) {
+            auto interp = [this](double tq, double* yq) { return interpolate(tq, yq); };
+            if (root_finder.check_root(pr, interp, y_.data(), t_, &root_t_, &root_idx_)) return ROOT_FOUND;
+        }
         if (has_tstop) {
             int r = handle_tstop(tstop);
             if (r == 1) { has_tstop = false; return TSTOP_REACHED; }
@@ -362,6 +374,18 @@ struct Sdirk : Method {
             }
             for (int k = 0; k < n; ++k) y[k] = theta * y_[k] + y[k];
         }
+        return ST_OK;
+    }
+
+    double root_t() const override { return root_t_; }
+    int root_index() const override { return root_idx_; }
+    // runge_kutta.rs:396-434 (no integrate_out, no sensitivities): y, dy interpolated at t, state.t = t
+    int state_mut_back(double t) override {
+        Vec ynew(n);
+        int e = interpolate(t, ynew.data());
+        if (e) return e;
+        y_ = ynew;                          // dy is interpolated as well in the reference; nothing reads it afterwards here
+        t_ = t;
         return ST_OK;
     }
 

@@ -45,6 +45,8 @@ MODELS = {
     "spm": 11,
     "spm99": 12,
     "exp_decay_root": 13,
+    "spm_stop": 14,
+    "spm99_stop": 15,
 }
 
 
@@ -116,6 +118,10 @@ def lib():
         L.orc_lu_solve.argtypes = [dp, ctypes.c_int, dp]
         L.orc_lu_factor.argtypes = [dp, ctypes.c_int, dp, ctypes.POINTER(ctypes.c_int32)]
         L.orc_num_threads.restype = ctypes.c_int
+        L.orc_model_root.restype = ctypes.c_int
+        L.orc_model_root.argtypes = [ctypes.c_int, dp, dp, ctypes.c_double, dp]
+        L.orc_math.restype = ctypes.c_double
+        L.orc_math.argtypes = [ctypes.c_int, ctypes.c_double]
         _lib = L
     return _lib
 
@@ -230,3 +236,19 @@ def batch_solve_dense_roots(desc, params, t_eval, nthreads=0):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def model_root(model, y, p, t=0.0):
+    """Root (event) functions of a model at (y, p, t) -> g[nroots]."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    g = np.zeros(8)
+    nr = lib().orc_model_root(MODELS[model], _dp(y), _dp(p), float(t), _dp(g))
+    assert nr >= 0
+    return g[:nr].copy()
+
+
+def math_fn(name, x):
+    """dsb_exp / dsb_log / dsb_tanh / dsb_asinh of csrc/dsb_math.h (shared by the oracle and the kernels)."""
+    which = {"exp": 0, "log": 1, "tanh": 2, "asinh": 3}[name]
+    return np.array([lib().orc_math(which, float(v)) for v in np.atleast_1d(x)])

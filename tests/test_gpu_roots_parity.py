@@ -1,5 +1,6 @@
-"""GPU parity tests of event handling: root finding inside the BDF lane kernel against
-the oracle, on the reference's exponential-decay-with-root problem swept over rate and initial value."""
+"""GPU parity tests of event handling: root finding inside the lane kernels (BDF and (E)SDIRK,
+on-chip and banded) against the oracle: the reference's exponential-decay-with-root problem swept over rate and initial
+value, and the battery model with its voltage cut-offs (spm.ds `stop_i`) swept over the applied current."""
 import numpy as np
 import pytest
 
@@ -44,11 +45,57 @@ def test_roots_bit_exact(dsb, oracle, tol):
     assert np.abs(ys[stopped, ncols[stopped] - 1, 0] - 0.6).max() < 1e-5
 
 
-def test_roots_only_on_the_bdf_lane_kernel(dsb):
+@pytest.mark.parametrize("method", ["tr_bdf2", "esdirk34"])
+def test_roots_sdirk_bit_exact(dsb, oracle, method):
+    """Rk::step_accepted's root check (runge_kutta.rs:935-948) in the SDIRK lane kernel."""
+    B = 2000
+    p = sweep(B)
+    t_eval = np.arange(1.0, 21.0)
+    solver = getattr(dsb.OdeBuilder().rhs_implicit("exp_decay_root").p(p).build(), method)()
+    ys = solver.solve_dense(t_eval)
+    root_idx, ncols = solver.root_info()
+    t_fin = solver.final_state()[0]
+    desc = oracle.make_desc("exp_decay_root", method=method, powmode=1)
+    ys_o, stats_o, status_o, t_root_o, root_idx_o, ncols_o = oracle.batch_solve_dense_roots(desc, p, t_eval)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(root_idx, root_idx_o) and np.array_equal(ncols, ncols_o)
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o, equal_nan=True)
+    stopped = root_idx_o == 0
+    assert 0 < stopped.sum() < B
+    assert np.array_equal(t_fin[stopped], t_root_o[stopped])
+
+
+@pytest.mark.parametrize("model,method,B,block", [("spm_stop", "bdf", 600, "768"), ("spm_stop", "bdf", 600, "128"),
+                                                   ("spm_stop", "tr_bdf2", 300, "768"), ("spm_stop", "esdirk34", 300, "128"),
+                                                   ("spm99_stop", "bdf", 60, "768"), ("spm99_stop", "tr_bdf2", 40, "128")])
+def test_battery_voltage_cut_off_bit_exact(dsb, oracle, model, method, B, block, monkeypatch):
+    """BASELINE config 5 with the model text's stop function on the banded lane kernels: every instance ends where the
+    terminal voltage reaches 3.105 V (or at 3600 s), at bit-identical root times, states and counters."""
+    from diffsol_b200 import sweeps
+    monkeypatch.setenv("DSB_BAND_BLOCK", block)
+    cur = (0.6 + 0.8 * sweeps.uniform(np.arange(B), 0)).reshape(-1, 1)
+    t_eval = np.arange(1, 121) * 30.0
+    solver = getattr(dsb.OdeBuilder().rhs_implicit(model).p(cur).use_coloring(True).build(), method)()
+    ys = solver.solve_dense(t_eval)
+    root_idx, ncols = solver.root_info()
+    t_fin = solver.final_state()[0]
+    desc = oracle.make_desc(model, method=method, powmode=1, use_coloring=True)
+    ys_o, stats_o, status_o, t_root_o, root_idx_o, ncols_o = oracle.batch_solve_dense_roots(desc, cur, t_eval)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(root_idx, root_idx_o) and np.array_equal(ncols, ncols_o)
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o, equal_nan=True)
+    stopped = root_idx_o == 0
+    assert 0 < stopped.sum() < B                          # small currents run to 3600 s, the others hit the cut-off
+    assert np.array_equal(t_fin[stopped], t_root_o[stopped])
+    capacity = cur[stopped, 0] * t_fin[stopped] / 3600.0
+    assert np.all((capacity > 0.66) & (capacity < 0.69))
+
+
+def test_roots_not_on_the_block_per_instance_path(dsb):
     p = sweep(8)
     prob = dsb.OdeBuilder().rhs_implicit("exp_decay_root").p(p).build()
-    with pytest.raises(dsb.DiffsolB200Error):
-        prob.tr_bdf2().solve_dense([1.0])
     with pytest.raises(dsb.DiffsolB200Error):
         prob.bdf().set_execution("block").solve_dense([1.0])
 

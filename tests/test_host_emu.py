@@ -85,3 +85,38 @@ def test_band_sdirk_kernel_on_host(oracle, method, model, B, coloring):
     r, *o = run_both(oracle, model, p, t_eval, method=method, kernel="band", use_coloring=coloring, rtol=1e-6, atol=1e-6)
     assert (o[2] == 0).all()
     assert_same(r, *o)
+
+
+def run_both_roots(oracle, model, params, t_eval, method="bdf", kernel="lane", **kw):
+    n, np_, _ = oracle.model_dims(model)
+    desc = oracle.make_desc(model, method=method, powmode=1, **kw)
+    o = oracle.batch_solve_dense_roots(desc, params, t_eval)
+    r = emu.solve(oracle.MODELS[model], n, np_, params, t_eval, method=method, kernel=kernel, **kw)
+    return r, o
+
+
+def assert_same_roots(r, o):
+    ys_o, stats_o, status_o, t_root_o, root_idx_o, ncols_o = o
+    assert_same(r, ys_o, stats_o, status_o)
+    assert np.array_equal(r["root_idx"], root_idx_o) and np.array_equal(r["ncols"], ncols_o)
+    stopped = root_idx_o >= 0
+    assert np.array_equal(r["fin"][stopped, 0], t_root_o[stopped])
+    return stopped
+
+
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
+def test_roots_in_the_on_chip_lane_kernels_on_host(oracle, method):
+    idx = np.arange(120)
+    p = np.stack([0.02 * 50.0 ** sweeps.uniform(idx, 0), 0.4 + 1.6 * sweeps.uniform(idx, 1)], axis=1)
+    r, o = run_both_roots(oracle, "exp_decay_root", p, np.arange(1.0, 21.0), method=method)
+    stopped = assert_same_roots(r, o)
+    assert 0 < stopped.sum() < len(idx)
+
+
+@pytest.mark.parametrize("model,method,B", [("spm_stop", "bdf", 24), ("spm_stop", "tr_bdf2", 12), ("spm_stop", "esdirk34", 12),
+                                             ("spm99_stop", "bdf", 3), ("spm99_stop", "tr_bdf2", 2)])
+def test_battery_voltage_cut_off_in_the_band_kernels_on_host(oracle, model, method, B):
+    r, o = run_both_roots(oracle, model, spm_currents(B), np.arange(1, 121) * 30.0, method=method, kernel="band",
+                          use_coloring=True)
+    stopped = assert_same_roots(r, o)
+    assert stopped.sum() > 0

@@ -46,3 +46,93 @@ def test_no_root_runs_to_the_end(oracle):
     desc2 = oracle.make_desc("exp_decay", powmode=1)
     ys2, stats2, status2 = oracle.batch_solve_dense(desc2, [[0.1, 0.5], [0.01, 1.0]], t_eval)
     assert np.array_equal(ys, ys2) and np.array_equal(stats, stats2)      # the root function does not steer the steps
+
+
+def test_root_finder_sdirk(oracle):
+    """ode_solver/sdirk.rs:1027-1047 test_root_finder_tr_bdf2 (and the same for esdirk34): the solve stops at the root
+    of y[0] - 0.6 and the state there is y0 exp(-k t_root) within the reference's norm bound of 15."""
+    k, y0 = 0.1, 1.0
+    t_root = -np.log(0.6 / y0) / k
+    for method in ("tr_bdf2", "esdirk34"):
+        desc = oracle.make_desc("exp_decay_root", method=method)      # builder defaults, libm pow
+        t_eval = np.arange(0.0, 11.0)
+        ys, stats, status, t_found, root_idx, ncols = oracle.batch_solve_dense_roots(desc, [[k, y0]], t_eval)
+        assert status[0] == 0 and root_idx[0] == 0
+        assert abs(t_found[0] - t_root) < 1e-3
+        expected = np.full(2, y0 * np.exp(-k * t_root))
+        assert weighted_norm(ys[0, ncols[0] - 1], expected, 1e-6, 1e-6) < 15.0
+        assert np.isnan(ys[0, ncols[0]:]).all()
+
+
+def spm_voltage_numpy(cn18, cn19, cp18, cp19, cur):
+    """The model text's out_i (book/src/primer/src/spm.ds) with numpy's libm functions."""
+    v2 = -25608.96286546366 * cp18 + 76826.88859639116 * cp19
+    v3 = -0.4999999999999983 * cp18 + 1.4999999999999982 * cp19
+    v4 = -12491.630996921805 * cn18 + 37474.892990765504 * cn19
+    v5 = -0.4999999999999983 * cn18 + 1.4999999999999984 * cn19
+    cps = max(min(v2, 51217.92521874824), 0.000512179257309275)
+    xp = max(min(v3, 0.9999999999), 1e-10)
+    cns = max(min(v4, 24983.261744011077), 0.000249832619938437)
+    xn = max(min(v5, 0.9999999999), 1e-10)
+    th = np.tanh
+    eta_p = 0.05138515824298745 * np.arcsinh((-2.3508116177110145 * cur) / (2.0 * ((1.8973665961010275e-05 * cps ** 0.5) * (51217.9257309275 - cps) ** 0.5)))
+    up = (2.16216 + 0.07645 * th(30.834 - 57.858397200000006 * xp) + 2.1581 * th(52.294 - 53.412228 * xp)
+          - 0.14169 * th(11.0923 - 21.0852666 * xp) + 0.2051 * th(1.4684 - 5.829105600000001 * xp)
+          + 0.2531 * th(4.291641337386018 - 8.069908814589667 * xp) - 0.02167 * th(-87.5 + 177.0 * xp)
+          + 1e-06 * ((1.0 / xp) + (1.0 / (-1.0 + xp))))
+    eta_n = 0.05138515824298745 * np.arcsinh((1.9590096814258458 * cur) / (2.0 * ((0.0006324555320336759 * cns ** 0.5) * (24983.2619938437 - cns) ** 0.5)))
+    un = (0.194 + 1.5 * np.exp(-120.0 * xn) + 0.0351 * th(-3.44578313253012 + 12.048192771084336 * xn)
+          - 0.0045 * th(-7.1344537815126055 + 8.403361344537815 * xn) - 0.035 * th(-18.466 + 20.0 * xn)
+          - 0.0147 * th(-14.705882352941176 + 29.41176470588235 * xn) - 0.102 * th(-1.3661971830985917 + 7.042253521126761 * xn)
+          - 0.022 * th(-54.8780487804878 + 60.975609756097555 * xn) - 0.011 * th(-5.486725663716814 + 44.24778761061947 * xn)
+          + 0.0155 * th(-3.6206896551724133 + 34.48275862068965 * xn) + 1e-06 * ((1.0 / xn) + (1.0 / (-1.0 + xn))))
+    return (eta_p + up) - (eta_n + un)
+
+
+def test_shared_elementary_functions(oracle):
+    """dsb_exp / dsb_log / dsb_tanh / dsb_asinh (csrc/dsb_math.h) against libm over the ranges the battery model uses."""
+    x = np.concatenate([np.linspace(-120.0, 60.0, 2001), np.array([-700.0, 700.0, 1e-9, -1e-9, 0.0])])
+    assert np.allclose(oracle.math_fn("exp", x), np.exp(x), rtol=4e-16, atol=0.0)
+    xl = np.concatenate([np.logspace(-300, 300, 1201), np.linspace(0.5, 2.0, 997)])
+    assert np.allclose(oracle.math_fn("log", xl), np.log(xl), rtol=4e-16, atol=2e-16)
+    xt = np.linspace(-90.0, 90.0, 4001)
+    assert np.abs(oracle.math_fn("tanh", xt) - np.tanh(xt)).max() < 4e-16
+    xa = np.concatenate([np.linspace(-50.0, 50.0, 2001), np.logspace(-6, 8, 300)])
+    assert np.allclose(oracle.math_fn("asinh", xa), np.arcsinh(xa), rtol=1e-15, atol=4e-16)
+
+
+def test_spm_stop_function_matches_the_model_text(oracle):
+    """`stop_i` of spm.ds restated in csrc/dsb_models.h (ModelSpmStopT::root) against the same formula evaluated with
+    numpy: the two root functions are V - 3.105 and 4.1 - V."""
+    rng = np.random.default_rng(7)
+    for _ in range(200):
+        y = np.zeros(42)
+        y[2:22] = rng.uniform(0.05, 0.95)
+        y[22:42] = rng.uniform(0.05, 0.95)
+        y[20:22] += rng.uniform(-0.02, 0.02, 2)
+        y[40:42] += rng.uniform(-0.02, 0.02, 2)
+        cur = rng.uniform(0.6, 1.4)
+        g = oracle.model_root("spm_stop", y, [cur])
+        v = spm_voltage_numpy(y[20], y[21], y[40], y[41], cur)
+        assert abs(g[0] - (-3.105 + v)) < 1e-13 and abs(g[1] - (4.1 - v)) < 1e-13
+    # the fresh cell of the model text (stoichiometries 0.8 / 0.6) sits inside the voltage window
+    y0 = np.concatenate([[0.0, 0.0], np.full(20, 0.8000000000000016), np.full(20, 0.6000000000000001)])
+    g0 = oracle.model_root("spm_stop", y0, [1.0])
+    assert g0[0] > 0 and g0[1] > 0 and 3.5 < 3.105 + g0[0] < 4.1
+
+
+def test_spm_discharge_ends_at_the_lower_cut_off(oracle):
+    """The reference's battery example (examples/physics-based-battery-simulation/src/main.rs: currents 0.6 .. 1.4 A,
+    3600 s): all but the smallest current end on the 3.105 V cut-off, at a discharged capacity of about 0.68 A h."""
+    cur = np.array([[0.6], [0.8], [1.0], [1.2], [1.4]])
+    t_eval = np.arange(1, 1201) * 3.0
+    desc = oracle.make_desc("spm_stop")
+    ys, stats, status, t_root, root_idx, ncols = oracle.batch_solve_dense_roots(desc, cur, t_eval)
+    assert (status == 0).all()
+    assert root_idx.tolist() == [-1, 0, 0, 0, 0] and ncols[0] == len(t_eval)
+    capacity = cur[1:, 0] * t_root[1:] / 3600.0
+    assert np.all((capacity > 0.66) & (capacity < 0.69))
+    at_root = ys[np.arange(1, 5), ncols[1:] - 1]
+    for b in range(4):
+        g = oracle.model_root("spm_stop", at_root[b], cur[b + 1])
+        assert abs(g[0]) < 1e-6                                  # V = 3.105 at the root, on the interpolant

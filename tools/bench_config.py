@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Time one BASELINE.json configuration other than the headline one (which bench.py owns) on one GPU:
-   python tools/bench_config.py heat256 [batch] [auto|block|band] [bdf|tr_bdf2|esdirk34]  |  spm | spm99 | vdp | robertson_dae [batch]
+   python tools/bench_config.py heat256 [batch] [auto|block|band] [bdf|tr_bdf2|esdirk34]  |  spm | spm99 | spm_stop | spm99_stop [batch] [bdf|tr_bdf2|esdirk34]  |  vdp | robertson_dae [batch]
 Prints ms per pass, instances/s, Newton-it/s and the algorithmic-byte HBM roofline fraction."""
 import json
 import os
@@ -27,13 +27,13 @@ if which.startswith("heat"):
     solver, npar, mass_words = getattr(prob, sys.argv[4] if len(sys.argv) > 4 else "bdf")(), 3, n * n
     if len(sys.argv) > 3:
         solver.set_execution(sys.argv[3])
-elif which in ("spm", "spm99"):
-    n, npar, mass_words = (42 if which == "spm" else 200), 1, 0
+elif which in ("spm", "spm99", "spm_stop", "spm99_stop"):
+    n, npar, mass_words = (42 if which in ("spm", "spm_stop") else 200), 1, 0
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 250000
     p = (0.6 + 0.8 * sweeps.uniform(np.arange(B), 0)).reshape(-1, 1)
     t_eval = np.arange(1, 13) * 300.0
     prob = ds.OdeBuilder().rhs_implicit(which).p(p).use_coloring(True).build()
-    solver = prob.bdf()
+    solver = getattr(prob, sys.argv[3] if len(sys.argv) > 3 else "bdf")()
 elif which == "vdp":
     n, npar, mass_words = 2, 2, 0
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 4000000
@@ -67,7 +67,7 @@ alg = (nli * (8 * (n * n + 4 * n + npar) + 4 * n) + setups * (8 * (2 * n * n + m
 # banded path (dsb_band_bdf_kernel.cuh): the same formula with the band storage it really reads (kl = ku = 1):
 # factors (2kl+ku+1) n + n pivots, Jacobian (kl+ku+1) n
 band = None
-if which in ("spm", "spm99") or which.startswith("heat"):
+if which.startswith("spm") or which.startswith("heat"):
     ldab, ldj = 4, 3
     band_mass = ldj * n if which.startswith("heat") else 0
     band = (nli * 8 * (ldab * n + n + 4 * n + npar) + setups * 8 * (ldj * n + band_mass + ldab * n + n)
@@ -75,7 +75,7 @@ if which in ("spm", "spm99") or which.startswith("heat"):
 print(json.dumps({"config": which, "n": n, "batch": B, "kernel_ms": kms, "e2e_ms": min(t for t, _ in times[1:]) * 1e3,
                   "instances_per_s": B / kms * 1e3, "newton_iters_per_s": nli / kms * 1e3,
                   "steps_mean": float(st[:, 6].mean()), "nli_mean": float(st[:, 8].mean()), "setups_mean": float(st[:, 0].mean()),
-                  "failed": int((status != 0).sum()), "algorithmic_GB": alg / 1e9,
+                  "failed": int((status != 0).sum()), "stopped_on_root": int((solver.root_info()[0] >= 0).sum()), "algorithmic_GB": alg / 1e9,
                   "achieved_GBps": alg / kms / 1e6, "frac_hbm": alg / kms / 1e6 / peak,
                   "band_algorithmic_GB": None if band is None else band / 1e9,
                   "band_frac_hbm": None if band is None else band / kms / 1e6 / peak}))
