@@ -83,6 +83,7 @@ SIGNATURES = {
     "dsb_problem_new": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_vp)]),
     "dsb_problem_free": (ctypes.c_int, [_vp]),
     "dsb_problem_dims": (ctypes.c_int, [_vp, _pi32, _pi32, _pi32]),
+    "dsb_problem_nout": (ctypes.c_int, [_vp, _pi32]),
     "dsb_problem_set_rtol": (ctypes.c_int, [_vp, _dbl]),
     "dsb_problem_set_atol": (ctypes.c_int, [_vp, _vp, _i32]),
     "dsb_problem_set_t0": (ctypes.c_int, [_vp, _dbl]),

@@ -166,6 +166,22 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
         }
     };
 
+    // one column of the solve_dense result (dense_write_out, method.rs:822-848): the interpolated state, or -- for
+    // equations with an output function -- out(y(tq), tq), evaluated on the state interpolated into the (free) Newton
+    // residual vector
+    constexpr int NOUT = dsb_model_nout<M>::value;
+    auto write_column = [&](double tq, int column) {
+        if constexpr (dsb_model_nout<M>::has_out) {
+            interpolate_to(tq, [&](int i, double yo) { GDL(i) = yo; });
+            double o[NOUT];
+            M::out(vDL, pl, tq, o);
+#pragma unroll
+            for (int k = 0; k < NOUT; ++k) bb.ys[((int64_t)column * NOUT + k) * B + inst] = o[k];
+        } else {
+            interpolate_to(tq, [&](int i, double yo) { bb.ys[((int64_t)column * N + i) * B + inst] = yo; });
+        }
+    };
+
     while (true) {
         // ---- warp-level block scheduler (dsb_bdf_kernel.cuh) ---------------------------------------------------
         const unsigned m_idle = __ballot_sync(0xffffffffu, state == R_IDLE);
@@ -451,11 +467,11 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                         // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root)
                         // (runge_kutta.rs:396-434), then the state at the root in the next column (method.rs:493-503)
                         while (col < nt && bb.t_eval[col] <= t_root) {
-                            interpolate_to(bb.t_eval[col], [&](int i, double yo) { bb.ys[((int64_t)col * N + i) * B + inst] = yo; });
+                            write_column(bb.t_eval[col], col);
                             ++col;
                         }
                         if (col < nt) {
-                            interpolate_to(t_root, [&](int i, double yo) { bb.ys[((int64_t)col * N + i) * B + inst] = yo; });
+                            write_column(t_root, col);
                             ++col;
                         }
                         t = t_root;
@@ -491,7 +507,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                 if ((is_forward && (tq > t || tq < old_t)) || (!is_forward && (tq < t || tq > old_t))) {
                     status = DSB_STATUS_INTERPOLATION_TIME_AFTER_CURRENT; break;
                 }
-                interpolate_to(tq, [&](int i, double yo) { bb.ys[((int64_t)col * N + i) * B + inst] = yo; });
+                write_column(tq, col);
                 ++col;
             }
             if (status != DSB_STATUS_OK) finish(status);

@@ -61,8 +61,8 @@ struct dsb_batch {
 namespace {
 
 struct DimsOf {
-    int *n, *np, *hm;
-    template <class M> void operator()() { *n = M::N; *np = M::NP; *hm = M::HAS_MASS ? 1 : 0; }
+    int *n, *np, *hm, *nout;
+    template <class M> void operator()() { *n = M::N; *np = M::NP; *hm = M::HAS_MASS ? 1 : 0; *nout = dsb_model_nout<M>::value; }
 };
 
 using namespace dsb_host;
@@ -174,12 +174,12 @@ int dsb_device_count(int* count) {
 
 int dsb_problem_new(int model, dsb_problem** out) {
     if (!out) return fail(DSB_BAD_ARG, "out is NULL");
-    int n = 0, np = 0, hm = 0;
-    DimsOf f{&n, &np, &hm};
+    int n = 0, np = 0, hm = 0, nout = 0;
+    DimsOf f{&n, &np, &hm, &nout};
     if (!dsb_dispatch_model(model, f)) return fail(DSB_BAD_ARG, "unknown model id");
     dsb_problem* p = new (std::nothrow) dsb_problem();
     if (!p) return fail(DSB_ERR, "out of memory");
-    p->model = model; p->n = n; p->np = np; p->has_mass = hm;
+    p->model = model; p->n = n; p->np = np; p->has_mass = hm; p->nout = nout;
     p->rtol = 1e-6; p->atol.assign(1, 1e-6); p->t0 = 0.0; p->h0 = 1.0; p->use_coloring = 0;   // builder.rs:112-140
     dsb_options_default(&p->opt);
     *out = p;
@@ -191,6 +191,11 @@ int dsb_problem_dims(const dsb_problem* p, int32_t* nstates, int32_t* nparams, i
     if (nstates) *nstates = p->n;
     if (nparams) *nparams = p->np;
     if (has_mass) *has_mass = p->has_mass;
+    return DSB_OK;
+}
+int dsb_problem_nout(const dsb_problem* p, int32_t* nout) {
+    if (!p || !nout) return fail(DSB_BAD_ARG, "NULL argument");
+    *nout = p->nout;
     return DSB_OK;
 }
 int dsb_problem_set_rtol(dsb_problem* p, double rtol) {
@@ -333,7 +338,7 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     DSB_CUDA(cudaMemsetAsync(b->root_idx, 0xFF, (size_t)b->B * 4, stream));
     dsb_fill_i32_kernel<<<(unsigned)((b->B + 255) / 256), 256, 0, stream>>>(b->ncols, b->B, nt);
     // outputs never reached stay NaN (all-ones bit pattern)
-    DSB_CUDA(cudaMemsetAsync(ys_dev, 0xFF, (size_t)nt * b->prob.n * b->B * 8, stream));
+    DSB_CUDA(cudaMemsetAsync(ys_dev, 0xFF, (size_t)nt * b->prob.nout * b->B * 8, stream));
     b->last_launches = 0;
     DSB_CUDA(cudaEventRecord(b->ev0, stream));
     if (b->prob.model < 0 || b->prob.model >= DSB_MODEL_COUNT) return fail(DSB_BAD_ARG, "unknown model id");
@@ -463,7 +468,7 @@ static int solve_host_impl(dsb_batch* b, int32_t method, const double* params_ho
                            int32_t* status_host, int free_running) {
     if (!b || !ys_host) return fail(DSB_BAD_ARG, "NULL argument");
     DSB_CUDA(cudaSetDevice(b->device));
-    const int n = b->prob.n;
+    const int n = b->prob.nout;                       // rows of a result column
     const size_t ys_bytes = (size_t)nt * n * b->B * 8;
     size_t stage_need = ys_bytes;
     if ((size_t)b->B * DSB_NSTATS * 8 > stage_need) stage_need = (size_t)b->B * DSB_NSTATS * 8;

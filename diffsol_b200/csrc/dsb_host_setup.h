@@ -18,6 +18,7 @@
 struct dsb_problem {
     int model;
     int n, np, has_mass;
+    int nout;                   // rows of a solve_dense column: outputs of the out function, else n
     double rtol;
     std::vector<double> atol;
     double t0, h0;

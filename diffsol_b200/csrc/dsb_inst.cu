@@ -273,8 +273,10 @@ cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const
     } else if (coop->exec_mode == 3) {
         return cudaErrorNotSupported;
     }
-    // root functions (events) are built into the lane kernels (on-chip and banded), not into the block-per-instance path
+    // root functions (events) are built into the lane kernels (on-chip and banded), not into the block-per-instance path;
+    // output functions into the banded lane kernels only
     if (dsb_model_nroots<InstModel>::value > 0 && coop->exec_mode == 2) return cudaErrorNotSupported;
+    if (dsb_model_nout<InstModel>::has_out) return cudaErrorNotSupported;
     const bool use_coop = coop->exec_mode == 2 || (coop->exec_mode == 0 && !kLaneCapable);
     if (use_coop) {
         if (method != DSB_METHOD_BDF) return cudaErrorNotSupported;   // cooperative path: BDF only

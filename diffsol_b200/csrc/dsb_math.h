@@ -32,6 +32,10 @@
 template <class M, class = void> struct dsb_model_nroots { static constexpr int value = 0; };
 template <class M> struct dsb_model_nroots<M, decltype((void)M::NROOTS)> { static constexpr int value = M::NROOTS; };
 
+// output function of an equation set (OdeEquations::out): M::NOUT outputs when declared, else solve_dense returns the states
+template <class M, class = void> struct dsb_model_nout { static constexpr int value = M::N; static constexpr bool has_out = false; };
+template <class M> struct dsb_model_nout<M, decltype((void)M::NOUT)> { static constexpr int value = M::NOUT; static constexpr bool has_out = true; };
+
 struct dsb_log_row { double invc, logc_hi, logc_lo; };
 struct dsb_exp_row { double hi, lo; };
 

@@ -29,7 +29,7 @@ enum dsb_model_id {
     DSB_MODEL_SPM = 11,                 // n=42  np=1  single-particle battery model, book/src/primer/src/spm.ds (BASELINE config 5)
     DSB_MODEL_SPM99 = 12,               // n=200 np=1  the same model on 99 radial cells per particle (not in the reference)
     DSB_MODEL_EXP_DECAY_ROOT = 13,      // n=2  np=2   exp_decay with the root y[0] - 0.6 (test_models/exponential_decay.rs:370-390)
-    DSB_MODEL_SPM_STOP = 14,            // n=42 np=1   spm with the model text's stop function: terminal voltage leaves [3.105, 4.1] V
+    DSB_MODEL_SPM_STOP = 14,            // n=42 np=1   spm with the model text's out (terminal voltage) and stop (voltage leaves [3.105, 4.1] V) functions
     DSB_MODEL_SPM99_STOP = 15,          // n=200 np=1  the same on 99 radial cells per particle
     DSB_MODEL_COUNT
 };
@@ -369,8 +369,8 @@ struct ModelSpmT {
 typedef ModelSpmT<SpmTables20> ModelSpm;
 typedef ModelSpmT<SpmTables99> ModelSpm99;
 
-// The battery model WITH its stop function (spm.ds `stop_i`: the terminal voltage leaves the window [3.105 V, 4.1 V]),
-// i.e. with `OdeEquations::root`: the integration ends at the first voltage cut-off exactly as in the reference's
+// The battery model WITH its output function (spm.ds `out_i`: the terminal voltage) and its stop function (`stop_i`:
+// the voltage leaves the window [3.105 V, 4.1 V]), i.e. with `OdeEquations::out` and `OdeEquations::root`: the integration ends at the first voltage cut-off exactly as in the reference's
 // battery example (examples/physics-based-battery-simulation/src/main.rs: `RootFound(t, _) => finished`).
 // voltage(x, I) restates `out_i` term by term, in the model text's order.  The surface concentrations are the
 // two-point extrapolations of the model text (constant5 / 8 / 9 / 10: rows over the outermost two cells of a particle;
@@ -424,6 +424,11 @@ struct ModelSpmStopT : ModelSpmT<Tab> {
         g[0] = -3.105 + v;
         g[1] = 4.1 - v;
     }
+    // `out_i` of the model text: solve_dense returns the terminal voltage, one value per column (dense_write_out,
+    // ode_solver/method.rs:822-848)
+    static constexpr int NOUT = 1;
+    template <class X>
+    DSB_HD static void out(const X& x, const double* p, double, double* o) { o[0] = voltage(x, p); }
 };
 typedef ModelSpmStopT<SpmTables20> ModelSpmStop;
 typedef ModelSpmStopT<SpmTables99> ModelSpm99Stop;

@@ -27,10 +27,11 @@ def _ptr(a):
 
 
 class OdeSolverProblem:
-    def __init__(self, handle, model, n, nparams, has_mass, nbatch, params, device):
+    def __init__(self, handle, model, n, nparams, has_mass, nbatch, params, device, nout=None):
         self._h = handle
         self.model = model
         self.nstates, self.nparams, self.has_mass = n, nparams, has_mass
+        self.nout = n if nout is None else nout      # rows of a solve_dense column (the `out` function's outputs, else the states)
         self.nbatch = nbatch
         self.p = params
         self.device = device
@@ -108,6 +109,8 @@ class OdeBuilder:
         capi.check(L.dsb_problem_new(capi.MODELS[self._model], ctypes.byref(h)))
         n, npar, hm = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         capi.check(L.dsb_problem_dims(h, ctypes.byref(n), ctypes.byref(npar), ctypes.byref(hm)))
+        nout = ctypes.c_int32()
+        capi.check(L.dsb_problem_nout(h, ctypes.byref(nout)))
         try:
             capi.check(L.dsb_problem_set_rtol(h, self._rtol))
             atol = np.asarray(self._atol, dtype=np.float64)
@@ -141,7 +144,7 @@ class OdeBuilder:
             L.dsb_problem_free(h)
             raise
         return OdeSolverProblem(h, self._model, n.value, npar.value, bool(hm.value), p.shape[0],
-                                np.ascontiguousarray(p), self._device)
+                                np.ascontiguousarray(p), self._device, nout=nout.value)
 
 
 class BatchedSolver:
@@ -169,14 +172,15 @@ class BatchedSolver:
         return self._solve_host(t_points, "dsb_batch_step_and_interpolate_host")
 
     def solve_dense(self, t_eval):
-        """-> ys[nbatch, nt, nstates] (host).  Per-instance statistics/status via get_statistics()/status()."""
+        """-> ys[nbatch, nt, nout] (host): the states, or the outputs of the equations' `out` function when they have one
+        (problem.nout).  Per-instance statistics/status via get_statistics()/status()."""
         return self._solve_host(t_eval, "dsb_batch_solve_dense_host")
 
     def _solve_host(self, t_eval, entry):
         pr = self.problem
         t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
         nt = len(t_eval)
-        ys = np.empty((pr.nbatch, nt, pr.nstates))
+        ys = np.empty((pr.nbatch, nt, pr.nout))
         stats = np.empty((pr.nbatch, capi.DSB_NSTATS), dtype=np.int64)
         status = np.empty(pr.nbatch, dtype=np.int32)
         capi.check(getattr(capi.lib(), entry)(
@@ -186,7 +190,7 @@ class BatchedSolver:
         return ys
 
     def solve_dense_device(self, t_eval, ys_dev_ptr, stream=None, params_dev_ptr=None):
-        """Device-resident variant: ys_dev_ptr -> [nt][nstates][nbatch] doubles (batch-major), asynchronous."""
+        """Device-resident variant: ys_dev_ptr -> [nt][nout][nbatch] doubles (batch-major), asynchronous."""
         pr = self.problem
         L = capi.lib()
         if params_dev_ptr is not None:

@@ -114,6 +114,10 @@ typedef struct dsb_problem dsb_problem;
 int dsb_problem_new(int model, dsb_problem** out);
 int dsb_problem_free(dsb_problem* p);
 int dsb_problem_dims(const dsb_problem* p, int32_t* nstates, int32_t* nparams, int32_t* has_mass);
+/* Rows of every solve_dense column: the outputs of the equations' `out` function (OdeEquations::out; dense_write_out,
+ * ode_solver/method.rs:822-848) when they have one, else nstates.  Wherever the result layouts below say nstates,
+ * read nout. */
+int dsb_problem_nout(const dsb_problem* p, int32_t* nout);
 int dsb_problem_set_rtol(dsb_problem* p, double rtol);                      /* OdeBuilder::rtol */
 int dsb_problem_set_atol(dsb_problem* p, const double* atol, int32_t n);    /* OdeBuilder::atol; n == 1 broadcasts */
 int dsb_problem_set_t0(dsb_problem* p, double t0);                          /* OdeBuilder::t0 */

@@ -73,6 +73,9 @@ struct Model {
     void (*init)(const double*, double, double*) = nullptr;
     int nroots = 0;                                                       // OdeEquations::root (ode_equations/mod.rs)
     void (*root)(const double*, const double*, double, double*) = nullptr;
+    int nout = 0;                                                         // OdeEquations::out: 0 = none (solve_dense returns the states)
+    void (*out)(const double*, const double*, double, double*) = nullptr;
+    int ncols_out() const { return nout > 0 ? nout : n; }                 // rows of the solve_dense result
 };
 template <class M, int NR = dsb_model_nroots<M>::value> struct RootOf {
     static void set(Model& m) {          // M::root may be a template over the state accessor (component-wise models)
@@ -81,12 +84,20 @@ template <class M, int NR = dsb_model_nroots<M>::value> struct RootOf {
     }
 };
 template <class M> struct RootOf<M, 0> { static void set(Model&) {} };
+template <class M, bool HAS = dsb_model_nout<M>::has_out> struct OutOf {
+    static void set(Model& m) {
+        m.nout = dsb_model_nout<M>::value;
+        m.out = [](const double* x, const double* p, double t, double* o) { M::out(x, p, t, o); };
+    }
+};
+template <class M> struct OutOf<M, false> { static void set(Model&) {} };
 template <class M>
 Model make_model() {
     Model m;
     m.n = M::N; m.np = M::NP; m.has_mass = M::HAS_MASS;
     m.rhs = &M::rhs; m.jac_mul = &M::jac_mul; m.mass = &M::mass; m.init = &M::init;
     RootOf<M>::set(m);
+    OutOf<M>::set(m);
     return m;
 }
 bool model_by_id(int id, Model* out);
@@ -246,7 +257,9 @@ Method* new_sdirk(const Problem& pr, int tableau /*0 = tr_bdf2, 1 = esdirk34*/, 
 // fn solve_dense (ode_solver/method.rs:721-818) + OdeSolverMethod::solve_dense (:467-505), without reset /
 // checkpointing.  When a root stops the integration, the columns up to the root are written, the state at the root
 // goes into the next column (when there is one) and *ncols / *root_t / *root_idx say so (ncols = nt otherwise).
-int solve_dense(Method& s, const double* t_eval, int nt, int n, double* out /* n*nt col-major */,
-                int* ncols = nullptr, double* root_t = nullptr, int* root_idx = nullptr);
+// With an output function (OdeEquations::out, dense_write_out method.rs:822-848) every column holds out(y(t), t)
+// (nout values) instead of the n states; `pr` supplies it (may be NULL: states).
+int solve_dense(Method& s, const double* t_eval, int nt, int n, double* out /* n*nt (or nout*nt) col-major */,
+                int* ncols = nullptr, double* root_t = nullptr, int* root_idx = nullptr, const Problem* pr = nullptr);
 
 }  // namespace orc

@@ -88,6 +88,12 @@ int orc_model_dims(int model_id, int* n, int* np, int* has_mass) {
     return ST_OK;
 }
 
+// rows of the solve_dense result: the number of outputs of the model's out function, else the number of states
+int orc_model_nout(int model_id) {
+    Model m;
+    if (!model_by_id(model_id, &m)) return -1;
+    return m.ncols_out();
+}
 // root (event) functions of a model at (y, p, t): g[nroots]; returns the number of root functions
 int orc_model_root(int model_id, const double* y, const double* p, double t, double* g) {
     Model m;
@@ -115,7 +121,7 @@ static int solve_dense_one(const orc_problem_desc* d, const double* p, int np, c
     std::unique_ptr<Method> m(make_method(pr, d->method, &err));
     if (!m) { export_stats(pr, nullptr, stats); return err; }
     int ncols = nt, ridx = -1; double rt = 0.0;
-    err = solve_dense(*m, t_eval, nt, pr.n(), out, &ncols, &rt, &ridx);
+    err = solve_dense(*m, t_eval, nt, pr.n(), out, &ncols, &rt, &ridx, &pr);
     export_stats(pr, m.get(), stats);
     if (fin) { fin[0] = m->t(); fin[1] = m->h(); fin[2] = (double)m->cur_order(); }
     if (root) { root[0] = rt; root[1] = (double)ridx; root[2] = (double)ncols; }
@@ -190,7 +196,7 @@ int orc_batch_solve_dense_roots(const orc_problem_desc* d, const double* params,
                                 double* out, int64_t* stats, int32_t* status, double* roots) {
     Model mm;
     if (!model_by_id(d->model_id, &mm)) return ST_BAD_ARG;
-    const int n = mm.n;
+    const int n = mm.ncols_out();                           // rows of every instance's result block
     // std::thread pool with a shared work counter (dynamic schedule, 16 instances per grab);
     // libgomp is not usable in this image.
     int nt_use = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();

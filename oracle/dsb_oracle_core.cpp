@@ -489,11 +489,23 @@ bool RootFinder::check_root(const Problem& pr, const std::function<int(double, d
 }
 
 // fn solve_dense (ode_solver/method.rs:721-818) + dense_write_out (:822-848) + the root column of
-// OdeSolverMethod::solve_dense (:493-503); no out fn, no reset, no checkpointing
-int solve_dense(Method& s, const double* t_eval, int nt, int n, double* out, int* ncols, double* root_t, int* root_idx) {
+// OdeSolverMethod::solve_dense (:493-503); no reset, no checkpointing
+int solve_dense(Method& s, const double* t_eval, int nt, int n, double* out, int* ncols, double* root_t, int* root_idx,
+                const Problem* pr) {
     if (ncols) *ncols = nt;
     if (root_idx) *root_idx = -1;
     if (nt <= 0) return ST_BAD_ARG;
+    const bool has_out = pr && pr->model.nout > 0;
+    const int nrow = has_out ? pr->model.nout : n;
+    Vec tmp_nstates(n);
+    // dense_write_out (method.rs:822-848): interpolate, then the output function when the equations have one
+    auto write_column = [&](double tq, int col) -> int {
+        if (!has_out) return s.interpolate(tq, out + (size_t)col * nrow);
+        int e = s.interpolate(tq, tmp_nstates.data());
+        if (e) return e;
+        pr->model.out(tmp_nstates.data(), pr->p.data(), tq, out + (size_t)col * nrow);
+        return ST_OK;
+    };
     int err = s.set_stop_time(t_eval[nt - 1]);
     if (err) return err;
     int col = 0;
@@ -503,14 +515,15 @@ int solve_dense(Method& s, const double* t_eval, int nt, int n, double* out, int
         if (r == ROOT_FOUND) {
             const double tr = s.root_t();
             while (col < nt && t_eval[col] <= tr) {
-                int e2 = s.interpolate(t_eval[col], out + (size_t)col * n);
+                int e2 = write_column(t_eval[col], col);
                 if (e2) return e2;
                 ++col;
             }
             int e3 = s.state_mut_back(tr);
             if (e3) return e3;
             if (col < nt) {                                 // write_state_out at the root, then resize_cols(col + 1)
-                for (int i = 0; i < n; ++i) out[(size_t)col * n + i] = s.y()[i];
+                if (has_out) pr->model.out(s.y(), pr->p.data(), s.t(), out + (size_t)col * nrow);
+                else for (int i = 0; i < n; ++i) out[(size_t)col * n + i] = s.y()[i];
                 ++col;
             }
             if (ncols) *ncols = col;
@@ -519,7 +532,7 @@ int solve_dense(Method& s, const double* t_eval, int nt, int n, double* out, int
             return ST_OK;
         }
         while (col < nt && t_eval[col] <= s.t()) {
-            int e2 = s.interpolate(t_eval[col], out + (size_t)col * n);
+            int e2 = write_column(t_eval[col], col);
             if (e2) return e2;
             ++col;
         }

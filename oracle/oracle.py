@@ -118,6 +118,8 @@ def lib():
         L.orc_lu_solve.argtypes = [dp, ctypes.c_int, dp]
         L.orc_lu_factor.argtypes = [dp, ctypes.c_int, dp, ctypes.POINTER(ctypes.c_int32)]
         L.orc_num_threads.restype = ctypes.c_int
+        L.orc_model_nout.restype = ctypes.c_int
+        L.orc_model_nout.argtypes = [ctypes.c_int]
         L.orc_model_root.restype = ctypes.c_int
         L.orc_model_root.argtypes = [ctypes.c_int, dp, dp, ctypes.c_double, dp]
         L.orc_math.restype = ctypes.c_double
@@ -168,8 +170,9 @@ def _stats_dict(stats):
     return {name: int(stats[i]) for i, name in enumerate(S_NAMES)}
 
 
-def _run(fn, desc, p, ts):
-    n, np_, _ = model_dims(desc.model_id) if False else _dims_by_id(desc.model_id)
+def _run(fn, desc, p, ts, rows=None):
+    n, np_, _ = _dims_by_id(desc.model_id)
+    n = rows or n
     p = np.ascontiguousarray(p, dtype=np.float64)
     assert p.size == np_, (p.size, np_)
     ts = np.ascontiguousarray(ts, dtype=np.float64)
@@ -190,7 +193,7 @@ def _dims_by_id(model_id):
 
 def solve_dense(desc, p, t_eval):
     """problem.<method>().solve_dense(t_eval) -> (rc, ys[nt, n], stats, final)"""
-    return _run(lib().orc_solve_dense, desc, p, t_eval)
+    return _run(lib().orc_solve_dense, desc, p, t_eval, rows=model_nout(desc.model_id))
 
 
 def harness(desc, p, t_points, use_tstop=False):
@@ -204,7 +207,7 @@ def batch_solve_dense(desc, params, t_eval, nthreads=0):
     params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, max(np_, 1))
     B = params.shape[0]
     t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
-    out = np.full((B, len(t_eval), n), np.nan)
+    out = np.full((B, len(t_eval), model_nout(desc.model_id)), np.nan)
     stats = np.zeros((B, S_COUNT), dtype=np.int64)
     status = np.zeros(B, dtype=np.int32)
     rc = lib().orc_batch_solve_dense(
@@ -222,7 +225,7 @@ def batch_solve_dense_roots(desc, params, t_eval, nthreads=0):
     params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, max(np_, 1))
     B = params.shape[0]
     t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
-    out = np.full((B, len(t_eval), n), np.nan)
+    out = np.full((B, len(t_eval), model_nout(desc.model_id)), np.nan)
     stats = np.zeros((B, S_COUNT), dtype=np.int64)
     status = np.zeros(B, dtype=np.int32)
     roots = np.zeros((B, 3))
@@ -236,6 +239,11 @@ def batch_solve_dense_roots(desc, params, t_eval, nthreads=0):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def model_nout(model):
+    """Rows of a solve_dense column: the outputs of the model's out function, else its states."""
+    return lib().orc_model_nout(MODELS[model] if isinstance(model, str) else int(model))
 
 
 def model_root(model, y, p, t=0.0):

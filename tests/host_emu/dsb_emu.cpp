@@ -39,7 +39,8 @@ struct EmuCall {
         pa.quorum = DSB_DEFAULT_QUORUM;
         std::vector<double> atol_full(N);
         for (int i = 0; i < N; ++i) atol_full[i] = pr->atol.size() == 1 ? pr->atol[0] : pr->atol[i];
-        std::vector<double> y0(N), dy0(N), h0(1), ysb((size_t)nt * N), fin_t(1), fin_h(1);
+        constexpr int NOUT = dsb_model_nout<M>::value;
+        std::vector<double> y0(N), dy0(N), h0(1), ysb((size_t)nt * NOUT), fin_t(1), fin_h(1);
         std::vector<int32_t> st(DSB_NSTATS), status1(1), fin_order(1), ridx(1), nc(1);
         for (int64_t b = 0; b < B; ++b) {
             DsbBatchBuffers bb;
@@ -53,7 +54,7 @@ struct EmuCall {
             unsigned long long work_counter = 0;
             bool ran = false;
             if (kernel == 1) {
-                if constexpr (N <= 16) {
+                if constexpr (N <= 16 && !dsb_model_nout<M>::has_out) {
                     if (method == DSB_METHOD_BDF) {
                         blockDim.x = BdfLayout<M>::THREADS;
                         dsb_init_kernel<M>(pa, bb, 1);
@@ -83,7 +84,7 @@ struct EmuCall {
             }
             if (!ran) { rc = DSB_ERR; return; }
             for (int k = 0; k < nt; ++k)
-                for (int i = 0; i < N; ++i) ys[(b * nt + k) * N + i] = ysb[(size_t)k * N + i];
+                for (int i = 0; i < NOUT; ++i) ys[(b * nt + k) * NOUT + i] = ysb[(size_t)k * NOUT + i];
             for (int s = 0; s < DSB_NSTATS; ++s) stats[b * DSB_NSTATS + s] = st[s] + (s == DSB_STAT_RHS_JAC_MULS ? probes : 0);
             status[b] = status1[0];
             fin[b * 3 + 0] = fin_t[0]; fin[b * 3 + 1] = fin_h[0]; fin[b * 3 + 2] = (double)fin_order[0];

@@ -82,7 +82,7 @@ def _dp(a):
 
 
 def solve(model_id, n, np_, params, t_eval, method="bdf", kernel="lane", rtol=1e-6, atol=1e-6, t0=0.0, h0=1.0,
-          use_coloring=False, options=None, free_running=False):
+          use_coloring=False, options=None, free_running=False, nout=None):
     """-> dict(ys[B, nt, n], stats[B, 16], status[B], fin[B, 3], root_idx[B], ncols[B]); raises when the kernel does
     not exist for the model."""
     params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, max(np_, 1))
@@ -90,7 +90,7 @@ def solve(model_id, n, np_, params, t_eval, method="bdf", kernel="lane", rtol=1e
     t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
     atol = np.ascontiguousarray(np.atleast_1d(np.asarray(atol, dtype=np.float64)))
     nt = len(t_eval)
-    ys = np.full((B, nt, n), np.nan)
+    ys = np.full((B, nt, nout or n), np.nan)      # nout: rows of a column for models with an output function
     stats = np.zeros((B, NSTATS), dtype=np.int64)
     status = np.zeros(B, dtype=np.int32)
     fin = np.zeros((B, 3))

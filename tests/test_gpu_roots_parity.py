@@ -91,6 +91,9 @@ def test_battery_voltage_cut_off_bit_exact(dsb, oracle, model, method, B, block,
     assert np.array_equal(t_fin[stopped], t_root_o[stopped])
     capacity = cur[stopped, 0] * t_fin[stopped] / 3600.0
     assert np.all((capacity > 0.66) & (capacity < 0.69))
+    # the result is the model's output function (terminal voltage): one row per column, 3.105 V at the root
+    assert ys.shape == (B, len(t_eval), 1)
+    assert np.abs(ys[stopped, ncols[stopped] - 1, 0] - 3.105).max() < 1e-6
 
 
 def test_roots_not_on_the_block_per_instance_path(dsb):

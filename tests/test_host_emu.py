@@ -91,7 +91,8 @@ def run_both_roots(oracle, model, params, t_eval, method="bdf", kernel="lane", *
     n, np_, _ = oracle.model_dims(model)
     desc = oracle.make_desc(model, method=method, powmode=1, **kw)
     o = oracle.batch_solve_dense_roots(desc, params, t_eval)
-    r = emu.solve(oracle.MODELS[model], n, np_, params, t_eval, method=method, kernel=kernel, **kw)
+    r = emu.solve(oracle.MODELS[model], n, np_, params, t_eval, method=method, kernel=kernel,
+                  nout=oracle.model_nout(model), **kw)
     return r, o
 
 

@@ -31,7 +31,9 @@ elif which in ("spm", "spm99", "spm_stop", "spm99_stop"):
     n, npar, mass_words = (42 if which in ("spm", "spm_stop") else 200), 1, 0
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 250000
     p = (0.6 + 0.8 * sweeps.uniform(np.arange(B), 0)).reshape(-1, 1)
-    t_eval = np.arange(1, 13) * 300.0
+    # states-only models: 12 output points; the full model (output = terminal voltage, stop = voltage cut-offs): the
+    # reference example's output every 3 s over 3600 s (examples/physics-based-battery-simulation/src/main.rs:20-21)
+    t_eval = np.arange(1, 1201) * 3.0 if which.endswith("_stop") else np.arange(1, 13) * 300.0
     prob = ds.OdeBuilder().rhs_implicit(which).p(p).use_coloring(True).build()
     solver = getattr(prob, sys.argv[3] if len(sys.argv) > 3 else "bdf")()
 elif which == "vdp":
@@ -63,7 +65,7 @@ nli, setups, me = int(st[:, 8].sum()), int(st[:, 0].sum()), int(st[:, 12].sum())
 attempts = int(st[:, 6].sum() + st[:, 7].sum() + st[:, 9].sum())
 nt = len(t_eval)
 alg = (nli * (8 * (n * n + 4 * n + npar) + 4 * n) + setups * (8 * (2 * n * n + mass_words) + 4 * n)
-       + me * 8 * (n * n + n + npar) + attempts * 8 * 19 * n + B * nt * 8 * n)
+       + me * 8 * (n * n + n + npar) + attempts * 8 * 19 * n + B * nt * 8 * prob.nout)
 # banded path (dsb_band_bdf_kernel.cuh): the same formula with the band storage it really reads (kl = ku = 1):
 # factors (2kl+ku+1) n + n pivots, Jacobian (kl+ku+1) n
 band = None
@@ -71,7 +73,7 @@ if which.startswith("spm") or which.startswith("heat"):
     ldab, ldj = 4, 3
     band_mass = ldj * n if which.startswith("heat") else 0
     band = (nli * 8 * (ldab * n + n + 4 * n + npar) + setups * 8 * (ldj * n + band_mass + ldab * n + n)
-            + me * 8 * (ldj * n + n + npar) + attempts * 8 * 19 * n + B * nt * 8 * n)
+            + me * 8 * (ldj * n + n + npar) + attempts * 8 * 19 * n + B * nt * 8 * prob.nout)
 print(json.dumps({"config": which, "n": n, "batch": B, "kernel_ms": kms, "e2e_ms": min(t for t, _ in times[1:]) * 1e3,
                   "instances_per_s": B / kms * 1e3, "newton_iters_per_s": nli / kms * 1e3,
                   "steps_mean": float(st[:, 6].mean()), "nli_mean": float(st[:, 8].mean()), "setups_mean": float(st[:, 0].mean()),
