@@ -227,6 +227,32 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
             return yo;
         }, store);
     };
+    // the same into the (free) Newton residual vector, for the output and root functions: only the components they
+    // read when the equations declare them (dsb_math.h: dsb_model_ndep)
+    constexpr int NDEP = dsb_model_ndep<M>::value;
+    auto interpolate_for_functions = [&](double tq) {
+        if constexpr (NDEP > 0) {
+            double tf[DSB_MAX_ORDER];
+            double time_factor = 1.0;
+#pragma unroll
+            for (int j = 0; j < DSB_MAX_ORDER; ++j) {
+                if (j < order) {
+                    const double j_t = (double)j;
+                    time_factor *= DSB_DIV(tq - (t - h * j_t), h * (1.0 + j_t));
+                }
+                tf[j] = time_factor;
+            }
+            band_for<NDEP, double>(NDEP, [&](int q) {
+                const int i = M::dep(q);
+                double yo = GD(0, i);
+#pragma unroll
+                for (int j = 0; j < DSB_MAX_ORDER; ++j) if (j < order) yo = tf[j] * GD(j + 1, i) + yo;
+                return yo;
+            }, [&](int q, double yo) { GDL(M::dep(q)) = yo; });
+        } else {
+            interpolate_to(tq, [&](int i, double yo) { GDL(i) = yo; });
+        }
+    };
 
     // one column of the solve_dense result (dense_write_out, method.rs:822-848): the interpolated state, or -- for
     // equations with an output function -- out(y(tq), tq), evaluated on the state interpolated into the (free) Newton
@@ -234,7 +260,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
     constexpr int NOUT = dsb_model_nout<M>::value;
     auto write_column = [&](double tq, int column) {
         if constexpr (dsb_model_nout<M>::has_out) {
-            interpolate_to(tq, [&](int i, double yo) { GDL(i) = yo; });
+            interpolate_for_functions(tq);
             double o[NOUT];
             M::out(vDL, pl, tq, o);
 #pragma unroll
@@ -523,7 +549,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                     double t_root = t;
                     stopped_on_root = rf.check_root(t, [&](double (&gv)[NR]) { M::root(vY, pl, t, gv); },
                                                     [&](double t_mid, double (&gv)[NR]) {
-                                                        interpolate_to(t_mid, [&](int i, double yo) { GDL(i) = yo; });
+                                                        interpolate_for_functions(t_mid);
                                                         M::root(vDL, pl, t_mid, gv);
                                                     }, t_root, root_found);
                     if (stopped_on_root) {

@@ -133,7 +133,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
 #pragma unroll
     for (int r = 0; r < (NR > 0 ? NR : 1); ++r) rf.g0[r] = 0.0;
     // interpolate_inplace (runge_kutta.rs:1080-1127; :962-981 beta dense output, :1004-1024 Hermite) on [old_t, t]
-    auto interpolate_to = [&](double tq, auto&& store) {
+    auto interpolate_range = [&](double tq, auto&& index, const int count, auto&& store) {
         const double dt = t - old_t;
         const double theta = (dt == 0.0) ? 1.0 : DSB_DIV(tq - old_t, dt);
         if (pa.rk.has_beta) {
@@ -144,7 +144,8 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                 bf[j] = 0.0;
                 if (j < ns) { bf[j] = pa.rk.beta[j] * theta; bf[j] = pa.rk.beta[ns + j] * th2 + bf[j]; }
             }
-            band_for<U2, double>(N, [&](int i) {
+            band_for<U2, double>(count, [&](int q) {
+                const int i = index(q);
                 double yo = GOY(i);
 #pragma unroll
                 for (int j = 0; j < DSB_RK_MAX_STAGES; ++j) if (j < ns) yo = GDF(j, i) * bf[j] + yo;
@@ -153,7 +154,8 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
         } else {
             const double al1 = theta - 1.0, be1 = 1.0 - 2.0 * theta;
             const double al2 = 1.0 - theta, be2 = theta * (theta - 1.0);
-            band_for<U2, double>(N, [&](int i) {
+            band_for<U2, double>(count, [&](int q) {
+                const int i = index(q);
                 const double u0 = GOY(i), u1 = GY(i);
                 double v = u1;
                 v -= u0;
@@ -165,6 +167,14 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
             }, store);
         }
     };
+    auto interpolate_to = [&](double tq, auto&& store) { interpolate_range(tq, [](int q) { return q; }, N, store); };
+    // into the (free) Newton residual vector, for the output and root functions: only the components they read when
+    // the equations declare them (dsb_math.h: dsb_model_ndep)
+    constexpr int NDEP = dsb_model_ndep<M>::value;
+    auto interpolate_for_functions = [&](double tq) {
+        if constexpr (NDEP > 0) interpolate_range(tq, [](int q) { return M::dep(q); }, NDEP, [&](int q, double yo) { GDL(M::dep(q)) = yo; });
+        else interpolate_to(tq, [&](int i, double yo) { GDL(i) = yo; });
+    };
 
     // one column of the solve_dense result (dense_write_out, method.rs:822-848): the interpolated state, or -- for
     // equations with an output function -- out(y(tq), tq), evaluated on the state interpolated into the (free) Newton
@@ -172,7 +182,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
     constexpr int NOUT = dsb_model_nout<M>::value;
     auto write_column = [&](double tq, int column) {
         if constexpr (dsb_model_nout<M>::has_out) {
-            interpolate_to(tq, [&](int i, double yo) { GDL(i) = yo; });
+            interpolate_for_functions(tq);
             double o[NOUT];
             M::out(vDL, pl, tq, o);
 #pragma unroll
@@ -460,7 +470,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                     double t_root = t;
                     stopped_on_root = rf.check_root(t, [&](double (&gv)[NR]) { M::root(vY, pl, t, gv); },
                                                     [&](double t_mid, double (&gv)[NR]) {
-                                                        interpolate_to(t_mid, [&](int i, double yo) { GDL(i) = yo; });
+                                                        interpolate_for_functions(t_mid);
                                                         M::root(vDL, pl, t_mid, gv);
                                                     }, t_root, root_found);
                     if (stopped_on_root) {

@@ -36,6 +36,11 @@ template <class M> struct dsb_model_nroots<M, decltype((void)M::NROOTS)> { stati
 template <class M, class = void> struct dsb_model_nout { static constexpr int value = M::N; static constexpr bool has_out = false; };
 template <class M> struct dsb_model_nout<M, decltype((void)M::NOUT)> { static constexpr int value = M::NOUT; static constexpr bool has_out = true; };
 
+// state components the out / root functions of an equation set read: M::NDEP of them, listed by M::dep(k), when the
+// equations declare that (the lane kernels then interpolate only those for an output point or a root iteration); 0 = all
+template <class M, class = void> struct dsb_model_ndep { static constexpr int value = 0; };
+template <class M> struct dsb_model_ndep<M, decltype((void)M::NDEP)> { static constexpr int value = M::NDEP; };
+
 struct dsb_log_row { double invc, logc_hi, logc_lo; };
 struct dsb_exp_row { double hi, lo; };
 

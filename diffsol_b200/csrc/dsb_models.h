@@ -429,6 +429,9 @@ struct ModelSpmStopT : ModelSpmT<Tab> {
     static constexpr int NOUT = 1;
     template <class X>
     DSB_HD static void out(const X& x, const double* p, double, double* o) { o[0] = voltage(x, p); }
+    // out and root read the outermost two cells of each particle only
+    static constexpr int NDEP = 4;
+    DSB_HD static int dep(int k) { return k == 0 ? 2 + NR - 2 : k == 1 ? 2 + NR - 1 : k == 2 ? 2 + 2 * NR - 2 : 2 + 2 * NR - 1; }
 };
 typedef ModelSpmStopT<SpmTables20> ModelSpmStop;
 typedef ModelSpmStopT<SpmTables99> ModelSpm99Stop;
