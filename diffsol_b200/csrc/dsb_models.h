@@ -31,6 +31,7 @@ enum dsb_model_id {
     DSB_MODEL_EXP_DECAY_ROOT = 13,      // n=2  np=2   exp_decay with the root y[0] - 0.6 (test_models/exponential_decay.rs:370-390)
     DSB_MODEL_SPM_STOP = 14,            // n=42 np=1   spm with the model text's out (terminal voltage) and stop (voltage leaves [3.105, 4.1] V) functions
     DSB_MODEL_SPM99_STOP = 15,          // n=200 np=1  the same on 99 radial cells per particle
+    DSB_MODEL_HEAT1D_DAE_32_BC = 16,    // n=32 np=3   heat1d_dae_32 with warm boundaries 0 = u - height/4: INCONSISTENT initial values
     DSB_MODEL_COUNT
 };
 
@@ -266,6 +267,23 @@ struct ModelHeat1dDae {
     }
 };
 
+// The same equations with the boundary rows 0 = u - height / 4 while the initial profile is 0 at the boundary: the
+// algebraic components START INCONSISTENT, so `new_and_consistent` has to move them (InitOp Newton with the backtracking
+// line search, state.rs:84-162) before the first step -- the test problem of the initialisation kernels.
+template <int NS>
+struct ModelHeat1dDaeBc : ModelHeat1dDae<NS> {
+    typedef ModelHeat1dDae<NS> Base;
+    static constexpr int N = NS;
+    template <class X>
+    DSB_HD static double rhs_i(int i, const X& x, const double* p, double t) {
+        if (i == 0 || i == NS - 1) return x[i] - 0.25 * p[0];
+        return Base::rhs_i(i, x, p, t);
+    }
+    DSB_HD static void rhs(const double* x, const double* p, double t, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = rhs_i(i, x, p, t);
+    }
+};
+
 // Single-particle battery model (SPM) of the reference's battery example
 // (examples/physics-based-battery-simulation/src/main.rs, model text book/src/primer/src/spm.ds), states only:
 // u = [discharge capacity, throughput capacity, 20 negative-particle concentrations, 20 positive-particle
@@ -454,6 +472,7 @@ template <> struct dsb_model_by_id<DSB_MODEL_SPM99> { typedef ModelSpm99 type; }
 template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY_ROOT> { typedef ModelExpDecayRoot type; };
 template <> struct dsb_model_by_id<DSB_MODEL_SPM_STOP> { typedef ModelSpmStop type; };
 template <> struct dsb_model_by_id<DSB_MODEL_SPM99_STOP> { typedef ModelSpm99Stop type; };
+template <> struct dsb_model_by_id<DSB_MODEL_HEAT1D_DAE_32_BC> { typedef ModelHeat1dDaeBc<32> type; };
 
 // traits of an equation set: written component-wise (`*_i` functions), declares a band for df/dy
 template <class M, class = void> struct dsb_is_componentwise : std::false_type {};
@@ -481,6 +500,7 @@ inline bool dsb_dispatch_model(int id, F&& f) {
         case DSB_MODEL_EXP_DECAY_ROOT: f.template operator()<ModelExpDecayRoot>(); return true;
         case DSB_MODEL_SPM_STOP: f.template operator()<ModelSpmStop>(); return true;
         case DSB_MODEL_SPM99_STOP: f.template operator()<ModelSpm99Stop>(); return true;
+        case DSB_MODEL_HEAT1D_DAE_32_BC: f.template operator()<ModelHeat1dDaeBc<32>>(); return true;
         default: return false;
     }
 }

@@ -47,6 +47,7 @@ MODELS = {
     "exp_decay_root": 13,
     "spm_stop": 14,
     "spm99_stop": 15,
+    "heat1d_dae_32_bc": 16,
 }
 
 

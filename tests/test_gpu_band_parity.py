@@ -187,3 +187,22 @@ def test_band_sdirk_free_running_and_default_path(dsb, oracle):
         assert np.array_equal(ys[b], ys_o)
         st = solver.get_statistics(b)
         assert all(st[k] == v for k, v in stats_o.items())
+
+
+@pytest.mark.parametrize("method,execution", [("bdf", "band"), ("tr_bdf2", "band"), ("bdf", "block")])
+def test_dae_inconsistent_initial_values_bit_exact(dsb, oracle, method, execution):
+    """Boundary rows 0 = u - height / 4 with u = 0 initially: `new_and_consistent` (state.rs:84-162) has to move the
+    algebraic components -- dsb_band_init_kernel.cuh on the banded path, the cooperative kernel's own initialisation on
+    the block-per-instance path -- before the first step; counters include the initialisation's rhs calls."""
+    B = 150
+    p = heat_params(B)
+    t_eval = np.arange(1, 11) / 10.0 * 0.99
+    prob = dsb.OdeBuilder().rhs_implicit("heat1d_dae_32_bc").p(p).rtol(1e-6).atol(1e-6).build()
+    solver = getattr(prob, method)().set_execution(execution)
+    ys = solver.solve_dense(t_eval)
+    desc = oracle.make_desc("heat1d_dae_32_bc", method=method, powmode=1, rtol=1e-6, atol=1e-6)
+    ys_o, stats_o, status_o = oracle.batch_solve_dense(desc, p, t_eval)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o)
+    assert np.abs(ys[:, :, 0] - 0.25 * p[:, :1]).max() < 1e-12

@@ -121,3 +121,16 @@ def test_battery_voltage_cut_off_in_the_band_kernels_on_host(oracle, model, meth
                           use_coloring=True)
     stopped = assert_same_roots(r, o)
     assert stopped.sum() > 0
+
+
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2"])
+@pytest.mark.parametrize("coloring", [False, True])
+def test_band_dae_inconsistent_initial_values_on_host(oracle, method, coloring):
+    """Boundary rows 0 = u - height / 4 with u = 0 initially: dsb_band_init_kernel has to move the algebraic components
+    (InitOp Newton + backtracking line search on the band LU) before the integrator starts."""
+    p = heat_params(8)
+    t_eval = np.arange(1, 11) / 10.0 * 0.99
+    r, *o = run_both(oracle, "heat1d_dae_32_bc", p, t_eval, method=method, kernel="band", use_coloring=coloring, rtol=1e-6, atol=1e-6)
+    assert (o[2] == 0).all()
+    assert_same(r, *o)
+    assert np.abs(r["ys"][:, :, 0] - 0.25 * p[:, :1]).max() < 1e-12 and np.abs(r["ys"][:, :, -1] - 0.25 * p[:, :1]).max() < 1e-12
