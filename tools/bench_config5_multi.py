@@ -88,7 +88,8 @@ def main():
     root_idx, ncols = solver.root_info()
     status = solver.status()
     # the gathered block is in GLOBAL instance order: column b of this rank's shard is global instance rank + world * b
-    ok = bool(torch.equal(gathered[:, rank::world][:, :B], ys_dev)) if world > 1 else True
+    # (bitwise: columns behind a root are NaN)
+    ok = bool(torch.equal(gathered[:, rank::world][:, :B].contiguous().view(torch.int64), ys_dev.view(torch.int64))) if world > 1 else True
     t = torch.tensor([float(np.mean(ms)), float(np.mean(integ))], dtype=torch.float64, device=dev)
     c = torch.tensor([nli, int((status != 0).sum()), int((root_idx >= 0).sum()), int(ok)], dtype=torch.int64, device=dev)
     if world > 1:
