@@ -47,7 +47,8 @@
 #include "dsb_roots.cuh"
 
 enum dsb_lane_state {
-    L_FETCH = 0, L_POST, L_SELECT, L_RESCALE, L_JAC, L_TSTOP, L_OUTPUT, L_PREDICT, L_NEWTON, L_FINISH, L_IDLE
+    L_FETCH = 0, L_POST, L_SELECT, L_RESCALE, L_JAC, L_TSTOP, L_OUTPUT, L_PREDICT, L_NEWTON, L_FINISH, L_IDLE,
+    L_REINIT            // equations with a reset function: the is_state_modified branch of Bdf::step after a reset
 };
 #define DSB_KIND_CONSTRUCT 5      // Bdf::_new's reset_jacobian (counted as a checkpoint setup, bdf.rs:351-359)
 
@@ -268,6 +269,29 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                 state = L_JAC;
             }
         }
+        // ================= REINIT: Bdf::step finds the state modified by a reset (bdf.rs:1291-1318) ==========
+        // root finder re-initialised, difference array back to first order (D[:, 0] = y, D[:, 1] = h dy: the dy of
+        // apply_reset is parked in the predictor's words; the higher columns keep what they held), _jacobian_updates(c,
+        // StepSuccess), then set_stop_time again: the TSTOP block's first-step path.  Only compiled for such equations.
+        if constexpr (dsb_model_has_reset<M>::value) {
+            if (__any_sync(0xffffffffu, state == L_REINIT) && state == L_REINIT) {
+                double yl[N], pl[NP > 0 ? NP : 1];
+#pragma unroll
+                for (int i = 0; i < N; ++i) yl[i] = SY(i);
+#pragma unroll
+                for (int j = 0; j < NP; ++j) pl[j] = SP(j);
+                M::root(yl, pl, t, rf.g0);
+                rf.t0 = t;
+                order = 1; n_equal_steps = 0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) { SD(0, i) = yl[i]; SD(1, i) = SYP(i) * h; }
+                c = h * pa.tab.alpha[1];
+                has_prev_error = false;
+                jac_kind = DSB_STEP_SUCCESS; after_jac = L_TSTOP;
+                first = true;
+                state = L_JAC;
+            }
+        }
         // ================= SELECT: order / step-size selection after an accepted step (bdf.rs:1489-1563), ==
         // or the shrink factor after a failed error test (bdf.rs:1431-1442).  Every pow() of the controller
         // is issued from ONE call site inside a rolled loop so that the lanes of the warp share it.
@@ -437,6 +461,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
         // ================= TSTOP: set_stop_time (first) / handle_tstop after an accepted step =============
         if (__any_sync(0xffffffffu, state == L_TSTOP) && state == L_TSTOP) {
             bool stopped_on_root = false;
+            bool reset_now = false;             // a reset was applied at a root: set_stop_time again, then L_REINIT
             if constexpr (NR > 0) {
                 // check for a root within the accepted step (bdf.rs:1566-1579), after the step-size update and before
                 // the stop time is handled; RootFinder::check_root (root.rs:60-160) with Vector::root_finding
@@ -456,7 +481,8 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                                                     }, t_root, root_found);
                     if (stopped_on_root) {
                         // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root)
-                        // (bdf.rs:1228-1262), then the state at the root in the next column (method.rs:493-503)
+                        // (bdf.rs:1228-1262), then -- without a reset function -- the state at the root in the next column
+                        // (method.rs:493-503) and the end of the solve
                         double yo[N];
                         while (col < nt && bb.t_eval[col] <= t_root) {
                             interpolate(bb.t_eval[col], yo);
@@ -465,19 +491,39 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                             ++col;
                         }
                         interpolate(t_root, yo);
-                        if (col < nt) {
-#pragma unroll
-                            for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
-                            ++col;
-                        }
                         t = t_root;
-                        finish(DSB_STATUS_OK);
+                        bool ended = true;
+                        if constexpr (dsb_model_has_reset<M>::value) {
+                            if (!free_running) {
+                                // has_reset (method.rs:783-797): apply_reset (state.rs:246-270: y <- reset(y, t),
+                                // dy <- f(y, t)), then a new stop time and on with the integration -- or TstopReached
+                                double yr[N], dyr[N];
+                                M::reset(yo, pl, t, yr);
+                                M::rhs(yr, pl, t, dyr);
+                                st.v[DSB_STAT_RHS_CALLS] += 1;
+#pragma unroll
+                                for (int i = 0; i < N; ++i) { SY(i) = yr[i]; SYP(i) = dyr[i]; }
+                                root_found = -1;
+                                if (t < bb.t_eval[nt - 1]) { reset_now = true; stopped_on_root = false; }
+                                else finish(DSB_STATUS_OK);                        // TstopReached
+                                ended = false;
+                            }
+                        }
+                        if (ended) {
+                            if (col < nt) {
+#pragma unroll
+                                for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
+                                ++col;
+                            }
+                            finish(DSB_STATUS_OK);
+                        }
                     }
                 }
             }
             int next = first ? L_PREDICT : L_OUTPUT;
             int r = 0;
             bool check = has_tstop && !stopped_on_root;
+            if (reset_now) { next = L_REINIT; check = true; has_tstop = true; tstop = bb.t_eval[nt - 1]; }
             if (first) {
                 check = !free_running;
                 if (free_running) next = L_OUTPUT;
@@ -486,7 +532,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
             if (check) {                                 // one call site for handle_tstop (code size)
                 r = handle_tstop(tstop);
                 if (r == 1) {
-                    if (first) r = -DSB_STATUS_STOP_TIME_AT_CURRENT;
+                    if (first || reset_now) r = -DSB_STATUS_STOP_TIME_AT_CURRENT;
                     else reached = true;
                 }
             }

@@ -41,6 +41,10 @@ template <class M> struct dsb_model_nout<M, decltype((void)M::NOUT)> { static co
 template <class M, class = void> struct dsb_model_ndep { static constexpr int value = 0; };
 template <class M> struct dsb_model_ndep<M, decltype((void)M::NDEP)> { static constexpr int value = M::NDEP; };
 
+// reset function of an equation set (OdeEquations::reset: the state map applied at a root): declared by M::HAS_RESET
+template <class M, class = void> struct dsb_model_has_reset { static constexpr bool value = false; };
+template <class M> struct dsb_model_has_reset<M, decltype((void)M::HAS_RESET)> { static constexpr bool value = M::HAS_RESET; };
+
 struct dsb_log_row { double invc, logc_hi, logc_lo; };
 struct dsb_exp_row { double hi, lo; };
 

@@ -32,6 +32,7 @@ enum dsb_model_id {
     DSB_MODEL_SPM_STOP = 14,            // n=42 np=1   spm with the model text's out (terminal voltage) and stop (voltage leaves [3.105, 4.1] V) functions
     DSB_MODEL_SPM99_STOP = 15,          // n=200 np=1  the same on 99 radial cells per particle
     DSB_MODEL_HEAT1D_DAE_32_BC = 16,    // n=32 np=3   heat1d_dae_32 with warm boundaries 0 = u - height/4: INCONSISTENT initial values
+    DSB_MODEL_EXP_DECAY_RESET = 17,     // n=2  np=2   exp_decay with the roots y[0] - 0.6, y[0] - 0.3 and the reset y -> 0.4 (exponential_decay.rs:818-880)
     DSB_MODEL_COUNT
 };
 
@@ -63,6 +64,16 @@ struct ModelExpDecayRoot : ModelExpDecay {
 };
 
 // dy/dt = -a y ; 0 = z - y ; p = [a]; inconsistent IC [1,1,0]
+// The reference's reset test problem (test_models/exponential_decay.rs:818-880, exponential_decay_with_reset_problem):
+// roots g0 = y[0] - 0.6 and g1 = y[0] - 0.3, reset y -> [0.4, 0.4]: with a reset function a root does not end
+// solve_dense -- the state is reset and the integration goes on to the last t_eval (method.rs:783-797).
+struct ModelExpDecayReset : ModelExpDecay {
+    static constexpr int NROOTS = 2;
+    static constexpr bool HAS_RESET = true;
+    DSB_HD static void root(const double* x, const double*, double, double* g) { g[0] = x[0] - 0.6; g[1] = x[0] - 0.3; }
+    DSB_HD static void reset(const double*, const double*, double, double* y) { for (int i = 0; i < N; ++i) y[i] = 0.4; }
+};
+
 struct ModelExpDecayAlgebraic {
     static constexpr int N = 3, NP = 1;
     static constexpr bool HAS_MASS = true;
@@ -473,6 +484,7 @@ template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY_ROOT> { typedef ModelExpD
 template <> struct dsb_model_by_id<DSB_MODEL_SPM_STOP> { typedef ModelSpmStop type; };
 template <> struct dsb_model_by_id<DSB_MODEL_SPM99_STOP> { typedef ModelSpm99Stop type; };
 template <> struct dsb_model_by_id<DSB_MODEL_HEAT1D_DAE_32_BC> { typedef ModelHeat1dDaeBc<32> type; };
+template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY_RESET> { typedef ModelExpDecayReset type; };
 
 // traits of an equation set: written component-wise (`*_i` functions), declares a band for df/dy
 template <class M, class = void> struct dsb_is_componentwise : std::false_type {};
@@ -501,6 +513,7 @@ inline bool dsb_dispatch_model(int id, F&& f) {
         case DSB_MODEL_SPM_STOP: f.template operator()<ModelSpmStop>(); return true;
         case DSB_MODEL_SPM99_STOP: f.template operator()<ModelSpm99Stop>(); return true;
         case DSB_MODEL_HEAT1D_DAE_32_BC: f.template operator()<ModelHeat1dDaeBc<32>>(); return true;
+        case DSB_MODEL_EXP_DECAY_RESET: f.template operator()<ModelExpDecayReset>(); return true;
         default: return false;
     }
 }

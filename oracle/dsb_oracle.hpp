@@ -76,6 +76,7 @@ struct Model {
     int nout = 0;                                                         // OdeEquations::out: 0 = none (solve_dense returns the states)
     void (*out)(const double*, const double*, double, double*) = nullptr;
     int ncols_out() const { return nout > 0 ? nout : n; }                 // rows of the solve_dense result
+    void (*reset)(const double*, const double*, double, double*) = nullptr;   // OdeEquations::reset: y <- reset(y, t) at a root
 };
 template <class M, int NR = dsb_model_nroots<M>::value> struct RootOf {
     static void set(Model& m) {          // M::root may be a template over the state accessor (component-wise models)
@@ -91,6 +92,10 @@ template <class M, bool HAS = dsb_model_nout<M>::has_out> struct OutOf {
     }
 };
 template <class M> struct OutOf<M, false> { static void set(Model&) {} };
+template <class M, bool HAS = dsb_model_has_reset<M>::value> struct ResetOf {
+    static void set(Model& m) { m.reset = [](const double* x, const double* p, double t, double* y) { M::reset(x, p, t, y); }; }
+};
+template <class M> struct ResetOf<M, false> { static void set(Model&) {} };
 template <class M>
 Model make_model() {
     Model m;
@@ -98,6 +103,7 @@ Model make_model() {
     m.rhs = &M::rhs; m.jac_mul = &M::jac_mul; m.mass = &M::mass; m.init = &M::init;
     RootOf<M>::set(m);
     OutOf<M>::set(m);
+    ResetOf<M>::set(m);
     return m;
 }
 bool model_by_id(int id, Model* out);
@@ -249,13 +255,16 @@ struct Method {
     virtual int root_index() const { return -1; }
     // OdeSolverMethod::state_mut_back (bdf.rs:1228-1262): move the state back to t inside the last step
     virtual int state_mut_back(double) { return ST_BAD_ARG; }
+    // OdeSolverMethod::apply_reset (method.rs:175-181 -> state.rs:246-270): y <- reset(y, t), dy <- f(y, t)
+    virtual int apply_reset() { return ST_BAD_ARG; }
 };
 
 Method* new_bdf(const Problem& pr, int* err);
 Method* new_sdirk(const Problem& pr, int tableau /*0 = tr_bdf2, 1 = esdirk34*/, int* err);
 
-// fn solve_dense (ode_solver/method.rs:721-818) + OdeSolverMethod::solve_dense (:467-505), without reset /
-// checkpointing.  When a root stops the integration, the columns up to the root are written, the state at the root
+// fn solve_dense (ode_solver/method.rs:721-818) + OdeSolverMethod::solve_dense (:467-505), without checkpointing.
+// With a reset function (OdeEquations::reset) a root does not end the solve: the state is moved back to the root, reset,
+// the stop time is set again and the integration continues (method.rs:774-805).  When a root stops the integration, the columns up to the root are written, the state at the root
 // goes into the next column (when there is one) and *ncols / *root_t / *root_idx say so (ncols = nt otherwise).
 // With an output function (OdeEquations::out, dense_write_out method.rs:822-848) every column holds out(y(t), t)
 // (nout values) instead of the n states; `pr` supplies it (may be NULL: states).

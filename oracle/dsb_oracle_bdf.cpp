@@ -41,6 +41,7 @@ struct Bdf : Method {
     // root finding (bdf.rs:143, 301-306, 1566-1579)
     RootFinder root_finder;
     double root_t_ = 0.0; int root_idx_ = -1;
+    bool is_state_modified = false;                        // bdf.rs:1223-1226: set by state_mut() / state_mut_back()
 
     explicit Bdf(const Problem& p) : pr(p), n(p.n()) {}
 
@@ -257,6 +258,24 @@ struct Bdf : Method {
         const int64_t old_num_error_test_failures = statistics.v[S_ERROR_TEST_FAILS];
         bool convergence_fail = false;
         double new_h = 0.0;
+        if (is_state_modified) {                           // bdf.rs:1291-1318
+            if (pr.model.nroots > 0) root_finder.init(pr, y_.data(), t_);
+            // initialise_to_first_order (bdf.rs:733-763, bdf_state.rs:72-78): order 1, D[:, 0] = y, D[:, 1] = h dy (the
+            // higher columns keep what they held)
+            n_equal_steps = 0;
+            order = 1;
+            for (int i = 0; i < n; ++i) { D(0)[i] = y_[i]; D(1)[i] = dy_[i] * h_; }
+            u = compute_r(1, 1.0);
+            is_state_modified = false;
+            const double c_new = h_ * alpha[order];
+            set_c(h_, alpha[order]);
+            jacobian_updates(c_new, STEP_SUCCESS);
+            has_prev_error = false;
+            if (has_tstop) {
+                int e = set_stop_time(tstop);
+                if (e) { *err = e; return STEP_ERROR; }
+            }
+        }
         predict_forward();
         while (true) {
             const int ord = order;
@@ -380,13 +399,25 @@ struct Bdf : Method {
     int root_index() const override { return root_idx_; }
     // bdf.rs:1228-1262 (is_state_modified is false after a step; no integrate_out, no sensitivities)
     int state_mut_back(double t) override {
+        if (is_state_modified) return t == t_ ? ST_OK : ST_INTERPOLATION_TIME_AFTER_CURRENT;
         const bool is_forward = h_ > 0.0;
         if ((is_forward && t > t_) || (!is_forward && t < t_)) return ST_INTERPOLATION_TIME_AFTER_CURRENT;
         Vec ynew(n);
         int e = interpolate(t, ynew.data());
         if (e) return e;
-        y_ = ynew;                          // dy is interpolated as well in the reference; nothing reads it afterwards here
+        y_ = ynew;                          // dy is interpolated as well in the reference; apply_reset overwrites it
         t_ = t;
+        is_state_modified = true;
+        return ST_OK;
+    }
+    // method.rs:175-181 -> state.rs:246-270 through state_mut() (no mass matrix: dy = f(y, t))
+    int apply_reset() override {
+        if (!pr.model.reset || pr.model.has_mass) return ST_BAD_ARG;
+        is_state_modified = true;
+        Vec ynew(n);
+        pr.model.reset(y_.data(), pr.p.data(), t_, ynew.data());
+        y_ = ynew;
+        pr.rhs(y_.data(), t_, dy_.data());
         return ST_OK;
     }
 

@@ -521,6 +521,16 @@ int solve_dense(Method& s, const double* t_eval, int nt, int n, double* out, int
             }
             int e3 = s.state_mut_back(tr);
             if (e3) return e3;
+            if (pr && pr->model.reset) {                    // has_reset (method.rs:783-797): reset, new stop time, go on
+                int e4 = s.apply_reset();
+                if (e4) return e4;
+                if (s.t() < t_eval[nt - 1]) {
+                    int e5 = s.set_stop_time(t_eval[nt - 1]);
+                    if (e5) return e5;
+                    continue;
+                }
+                break;                                      // TstopReached
+            }
             if (col < nt) {                                 // write_state_out at the root, then resize_cols(col + 1)
                 if (has_out) pr->model.out(s.y(), pr->p.data(), s.t(), out + (size_t)col * nrow);
                 else for (int i = 0; i < n; ++i) out[(size_t)col * n + i] = s.y()[i];
@@ -538,6 +548,9 @@ int solve_dense(Method& s, const double* t_eval, int nt, int n, double* out, int
         }
         if (r == TSTOP_REACHED) break;
     }
+    // columns actually written: nt, unless the stop time was declared reached within its round-off tolerance just
+    // below the last t_eval (the reference asserts col == t_eval.len() there, method.rs:771)
+    if (ncols) *ncols = col;
     return ST_OK;
 }
 

@@ -48,6 +48,7 @@ MODELS = {
     "spm_stop": 14,
     "spm99_stop": 15,
     "heat1d_dae_32_bc": 16,
+    "exp_decay_reset": 17,
 }
 
 

@@ -139,3 +139,25 @@ def test_spm_discharge_ends_at_the_lower_cut_off(oracle):
     at_root = v[np.arange(1, 5), ncols[1:] - 1]
     assert np.abs(at_root - 3.105).max() < 1e-6                  # V = 3.105 at the root, on the interpolant
     assert np.isnan(v[1, ncols[1]:]).all()
+
+
+def test_solve_dense_with_reset(oracle):
+    """ode_solver/mod.rs:1302-1372 test_solve_dense_with_reset on exponential_decay_with_reset_problem
+    (test_models/exponential_decay.rs:818-880: roots y[0] - 0.6 and y[0] - 0.3, reset y -> 0.4): solve_dense applies the
+    resets and runs on to the last evaluation time; the state just before the second event is 0.3, just after 0.4."""
+    k = 0.1
+    t_root0 = -np.log(0.6) / k
+    t_stop = t_root0 + np.log(4.0 / 3.0) / k              # second event: 0.4 decays to 0.3
+    final_time = 2.0 * t_stop
+    dt = 1e-3                                             # the reference probes the exact event time with solve(); here: just around it
+    t_eval = np.array([1e-12, t_stop - dt, t_stop + dt, final_time])
+    desc = oracle.make_desc("exp_decay_reset")            # builder defaults, libm pow
+    ys, stats, status, t_root, root_idx, ncols = oracle.batch_solve_dense_roots(desc, [[k, 1.0]], t_eval)
+    assert status[0] == 0 and root_idx[0] == -1 and ncols[0] == len(t_eval)       # TstopReached, every column filled
+    pre = np.full(2, 0.4 * np.exp(-k * (t_eval[1] - t_root0)))
+    post = np.full(2, 0.4 * np.exp(-k * (t_eval[2] - t_stop)))
+    assert weighted_norm(ys[0, 1], pre, 1e-6, 1e-6) < 20.0
+    assert weighted_norm(ys[0, 2], post, 1e-6, 1e-6) < 20.0
+    assert abs(ys[0, 1, 0] - 0.3) < 1e-4 and abs(ys[0, 2, 0] - 0.4) < 1e-4
+    # the state keeps cycling between 0.4 and 0.3 until the final time
+    assert 0.3 <= ys[0, 3, 0] <= 0.4
