@@ -309,8 +309,12 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     if (!b || !t_eval || nt < 1 || !ys_dev) return fail(DSB_BAD_ARG, "bad argument to dsb_batch_solve_dense");
     if (method != DSB_METHOD_BDF && method != DSB_METHOD_TR_BDF2 && method != DSB_METHOD_ESDIRK34)
         return fail(DSB_BAD_ARG, "unknown method");
-    for (int k = 1; k < nt; ++k)
-        if (!(t_eval[k] >= t_eval[k - 1])) return fail(DSB_BAD_ARG, "t_eval must be increasing");
+    // solve_dense walks forward through t_eval (method.rs:761-764); the free-running loop steps while |t| < |t_k|
+    // (ode_solver/mod.rs:132-141), which also serves backward integration (h0 < 0: negative_exponential_decay_problem)
+    for (int k = 1; k < nt; ++k) {
+        if (!free_running && !(t_eval[k] >= t_eval[k - 1])) return fail(DSB_BAD_ARG, "t_eval must be increasing");
+        if (free_running && !(std::fabs(t_eval[k]) >= std::fabs(t_eval[k - 1]))) return fail(DSB_BAD_ARG, "|t_points| must be increasing");
+    }
     cudaStream_t stream = (cudaStream_t)stream_;
     DSB_CUDA(cudaSetDevice(b->device));
     if (b->t_eval_cap < nt) {

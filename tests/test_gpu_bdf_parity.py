@@ -245,3 +245,24 @@ def test_cooperative_lu_matches_nalgebra_restatement(dsb, oracle, n):
         assert (rc != 0) == (info2[b] != 0), b
         if rc == 0:
             assert np.array_equal(x_g[b], x_o), b
+
+
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
+def test_backward_integration(dsb, oracle, method):
+    """negative_exponential_decay_problem (h0 = -1, points 0, -1, .., -9) through step()/interpolate(), as the
+    reference's bdf.rs:1729-1733 / sdirk.rs:669-673 do; solve_dense itself is forward-only in the reference."""
+    k, y0 = 0.1, np.exp(-1.0)
+    pts = -np.arange(0.0, 10.0)
+    p = np.tile([[k, y0]], (40, 1))
+    prob = dsb.OdeBuilder().rhs_implicit("exp_decay").p(p).h0(-1.0).build()
+    solver = getattr(prob, method)()
+    ys = solver.step_and_interpolate(pts)
+    desc = oracle.make_desc("exp_decay", method=method, powmode=1, h0=-1.0)
+    rc, ys_o, stats_o, fin = oracle.harness(desc, [k, y0], pts)
+    assert rc == 0 and (solver.status() == 0).all()
+    for b in (0, 17, 39):
+        assert np.array_equal(ys[b], ys_o) and solver.get_statistics(b) == stats_o
+    tf, hf, _ = solver.final_state()
+    assert tf[0] == fin["t"] and hf[0] == fin["h"] and hf[0] < 0
+    with pytest.raises(dsb.DiffsolB200Error):
+        solver.solve_dense(pts[1:])                  # decreasing t_eval: rejected

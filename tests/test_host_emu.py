@@ -146,3 +146,21 @@ def test_reset_in_the_bdf_lane_kernel_on_host(oracle, tol):
     assert_same_roots(r, o)
     assert (o[2] == 0).all() and (o[4] == -1).all()
     assert r["ys"][:, -1, 0].max() <= 0.6 + 1e-6          # nobody stays above the first root level
+
+
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
+def test_backward_integration_on_host(oracle, method):
+    """negative_exponential_decay_problem (test_models/exponential_decay.rs:168-197: h0 = -1, points 0, -1, .., -9)
+    through the step()/interpolate() loop of the reference's harness, as bdf.rs:1729-1733 / sdirk.rs:669-673 run it."""
+    k, y0 = 0.1, np.exp(-1.0)
+    pts = -np.arange(0.0, 10.0)
+    desc = oracle.make_desc("exp_decay", method=method, powmode=1, h0=-1.0)
+    rc, ys_o, stats_o, fin = oracle.harness(desc, [k, y0], pts)
+    assert rc == 0
+    r = emu.solve(oracle.MODELS["exp_decay"], 2, 2, [[k, y0]], pts, method=method, h0=-1.0, free_running=True)
+    assert r["status"][0] == 0 and np.array_equal(r["ys"][0], ys_o)
+    assert {n: int(r["stats"][0, i]) for i, n in enumerate(oracle.S_NAMES)} == stats_o
+    assert r["fin"][0, 0] == fin["t"] and r["fin"][0, 1] == fin["h"] and fin["h"] < 0
+    exact = y0 * np.exp(-k * pts)
+    err = np.sqrt(np.mean(((ys_o - exact[:, None]) / (np.abs(exact[:, None]) * 1e-6 + 1e-6)) ** 2, axis=1))
+    assert err.max() < (30.0 if method == "esdirk34" else 20.0)      # the reference's acceptance thresholds
