@@ -33,6 +33,7 @@ enum dsb_model_id {
     DSB_MODEL_SPM99_STOP = 15,          // n=200 np=1  the same on 99 radial cells per particle
     DSB_MODEL_HEAT1D_DAE_32_BC = 16,    // n=32 np=3   heat1d_dae_32 with warm boundaries 0 = u - height/4: INCONSISTENT initial values
     DSB_MODEL_EXP_DECAY_RESET = 17,     // n=2  np=2   exp_decay with the roots y[0] - 0.6, y[0] - 0.3 and the reset y -> 0.4 (exponential_decay.rs:818-880)
+    DSB_MODEL_HEAT2D_10 = 18,           // n=100 np=0  2-D heat equation on a 10 x 10 grid, boundary rows algebraic (test_models/heat2d.rs), states only
     DSB_MODEL_COUNT
 };
 
@@ -295,6 +296,45 @@ struct ModelHeat1dDaeBc : ModelHeat1dDae<NS> {
     }
 };
 
+// 2-D heat equation u_t = u_xx + u_yy on the unit square, MG x MG grid, 5-point differences on the interior points, the
+// boundary rows algebraic (0 = u): the reference's heat2d test problem (test_models/heat2d.rs:101-196, the SUNDIALS
+// idaHeat2D_klu example), whose statistics snapshot bdf.rs:2424-2446 is the only golden of the reference with n > 16.
+// States only: the reference's output function (dx ||u||_2)^2 is evaluated by the tests from the states.
+template <int MG>
+struct ModelHeat2d {
+    static constexpr int N = MG * MG, NP = 0;
+    static constexpr bool HAS_MASS = true;
+    static constexpr bool COMPONENTWISE = true;
+    DSB_HD static bool boundary(int loc) { const int j = loc / MG, i = loc - j * MG; return j == 0 || j == MG - 1 || i == 0 || i == MG - 1; }
+    DSB_HD static double coeff() { const double dx = 1.0 / ((double)MG - 1.0); return 1.0 / (dx * dx); }
+    template <class X>
+    DSB_HD static double rhs_i(int loc, const X& x, const double*, double) {
+        if (boundary(loc)) return x[loc];
+        return coeff() * (x[loc - 1] + x[loc + 1] + x[loc - MG] + x[loc + MG] - 4.0 * x[loc]);
+    }
+    template <class X, class V>
+    DSB_HD static double jac_mul_i(int loc, const X&, const double*, double, const V& v) {
+        if (boundary(loc)) return v[loc];
+        return coeff() * (v[loc - 1] + v[loc + 1] + v[loc - MG] + v[loc + MG] - 4.0 * v[loc]);
+    }
+    template <class X>
+    DSB_HD static double mass_i(int loc, const X& x, const double*, double, double beta, double yi) {
+        if (boundary(loc)) return yi * beta;
+        return x[loc] + beta * yi;
+    }
+    DSB_HD static double init_i(int loc, const double*, double) {
+        if (boundary(loc)) return 0.0;
+        const double dx = 1.0 / ((double)MG - 1.0);
+        const int j = loc / MG, i = loc - j * MG;
+        const double yfact = dx * (double)j, xfact = dx * (double)i;
+        return 16.0 * xfact * (1.0 - xfact) * yfact * (1.0 - yfact);
+    }
+    DSB_HD static void rhs(const double* x, const double* p, double t, double* y) { for (int i = 0; i < N; ++i) y[i] = rhs_i(i, x, p, t); }
+    DSB_HD static void jac_mul(const double* x, const double* p, double t, const double* v, double* y) { for (int i = 0; i < N; ++i) y[i] = jac_mul_i(i, x, p, t, v); }
+    DSB_HD static void mass(const double* x, const double* p, double t, double beta, double* y) { for (int i = 0; i < N; ++i) y[i] = mass_i(i, x, p, t, beta, y[i]); }
+    DSB_HD static void init(const double* p, double t, double* y) { for (int i = 0; i < N; ++i) y[i] = init_i(i, p, t); }
+};
+
 // Single-particle battery model (SPM) of the reference's battery example
 // (examples/physics-based-battery-simulation/src/main.rs, model text book/src/primer/src/spm.ds), states only:
 // u = [discharge capacity, throughput capacity, 20 negative-particle concentrations, 20 positive-particle
@@ -485,6 +525,7 @@ template <> struct dsb_model_by_id<DSB_MODEL_SPM_STOP> { typedef ModelSpmStop ty
 template <> struct dsb_model_by_id<DSB_MODEL_SPM99_STOP> { typedef ModelSpm99Stop type; };
 template <> struct dsb_model_by_id<DSB_MODEL_HEAT1D_DAE_32_BC> { typedef ModelHeat1dDaeBc<32> type; };
 template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY_RESET> { typedef ModelExpDecayReset type; };
+template <> struct dsb_model_by_id<DSB_MODEL_HEAT2D_10> { typedef ModelHeat2d<10> type; };
 
 // traits of an equation set: written component-wise (`*_i` functions), declares a band for df/dy
 template <class M, class = void> struct dsb_is_componentwise : std::false_type {};
@@ -514,6 +555,7 @@ inline bool dsb_dispatch_model(int id, F&& f) {
         case DSB_MODEL_SPM99_STOP: f.template operator()<ModelSpm99Stop>(); return true;
         case DSB_MODEL_HEAT1D_DAE_32_BC: f.template operator()<ModelHeat1dDaeBc<32>>(); return true;
         case DSB_MODEL_EXP_DECAY_RESET: f.template operator()<ModelExpDecayReset>(); return true;
+        case DSB_MODEL_HEAT2D_10: f.template operator()<ModelHeat2d<10>>(); return true;
         default: return false;
     }
 }

@@ -49,6 +49,7 @@ MODELS = {
     "spm99_stop": 15,
     "heat1d_dae_32_bc": 16,
     "exp_decay_reset": 17,
+    "heat2d_10": 18,
 }
 
 

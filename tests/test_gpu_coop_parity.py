@@ -135,3 +135,30 @@ def test_coloured_jacobian_block_per_instance(dsb, oracle, model, B):
     n = ys.shape[2]
     me = solver.statistics_array()[:, 12]
     assert (solver.statistics_array()[:, 11] == 3 * me + n).all()      # 3 colours + n probes
+
+
+def test_reference_snapshot_heat2d_on_gpu(dsb, oracle):
+    """The reference's only statistics snapshot with n > 16 (bdf.rs:2424-2446: 2-D heat equation DAE, 10 x 10 grid,
+    n = 100, coloured Jacobian) on the block-per-instance path (band LU in shared memory: kl = ku = 10), through the
+    stepping loop of the reference's harness: all 13 integers, for every instance of a batch, and the states
+    bit-identical to the oracle."""
+    import json
+    import os
+    from test_oracle_golden import expected_stats
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_snapshots.json")) as f:
+        case = json.load(f)["heat2d_10"]
+    nb = 9
+    solver = (dsb.OdeBuilder().rhs_implicit("heat2d_10").nbatch(nb).rtol(case["rtol"]).atol(case["atol"])
+              .use_coloring(True).build().bdf())
+    ys = solver.step_and_interpolate(case["t"])
+    assert (solver.status() == 0).all()
+    for b in range(nb):
+        assert solver.get_statistics(b) == expected_stats(case), case["cite"]
+    desc = oracle.make_desc("heat2d_10", rtol=case["rtol"], atol=case["atol"], use_coloring=True, powmode=1)
+    rc, ys_o, stats_o, fin = oracle.harness(desc, [], case["t"])
+    assert rc == 0
+    for b in range(nb):
+        assert np.array_equal(ys[b], ys_o)
+    out = (np.sqrt((ys[0] ** 2).sum(axis=1)) / 9.0) ** 2
+    expected = np.array(case["out"])
+    assert (np.abs(out - expected) / (np.abs(expected) * 1e-5 + 1e-5)).max() < 20.0

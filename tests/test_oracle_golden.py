@@ -139,3 +139,20 @@ def test_dsb_pow_accuracy(oracle):
     assert nbad / len(xs) < 0.03
     assert oracle.lib().orc_powi(0.5, 9) == 0.5 ** 9
     assert oracle.lib().orc_powi(3.0, 0) == 1.0
+
+
+@pytest.mark.parametrize("powmode", [0, 1], ids=["libm_pow", "dsb_pow"])
+def test_reference_snapshot_heat2d(oracle, powmode):
+    """bdf.rs:2424-2446: the 2-D heat equation DAE on a 10 x 10 grid (n = 100, boundary rows algebraic, Jacobian
+    colouring) -- the reference's only statistics snapshot with n > 16.  It was taken with faer's sparse LU; the dense
+    partial-pivoting restatement reproduces all 13 integers, and the output function (dx ||u||_2)^2 passes the
+    reference's acceptance test against the SUNDIALS idaHeat2D table."""
+    case = GOLD["heat2d_10"]
+    desc = oracle.make_desc(case["model"], rtol=case["rtol"], atol=case["atol"], use_coloring=case["coloring"], powmode=powmode)
+    rc, ys, stats, fin = oracle.harness(desc, case["p"], case["t"])
+    assert rc == 0
+    assert stats == expected_stats(case), case["cite"]
+    out = (np.sqrt((ys ** 2).sum(axis=1)) / 9.0) ** 2           # heat2d_out (test_models/heat2d.rs:206-211)
+    expected = np.array(case["out"])
+    err = np.abs(out - expected) / (np.abs(expected) * case["out_rtol"] + case["out_atol"])
+    assert err.max() < 20.0
