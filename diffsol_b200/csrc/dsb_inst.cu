@@ -277,8 +277,8 @@ cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const
     // output functions into the banded lane kernels only
     if (dsb_model_nroots<InstModel>::value > 0 && coop->exec_mode == 2) return cudaErrorNotSupported;
     if (dsb_model_nout<InstModel>::has_out) return cudaErrorNotSupported;
-    // reset functions (re-initialisation after an event) are built into the on-chip BDF lane kernel only
-    if (dsb_model_has_reset<InstModel>::value && (method != DSB_METHOD_BDF || coop->exec_mode >= 2)) return cudaErrorNotSupported;
+    // reset functions (re-initialisation after an event) are built into the on-chip lane kernels (BDF and SDIRK) only
+    if (dsb_model_has_reset<InstModel>::value && coop->exec_mode >= 2) return cudaErrorNotSupported;
     const bool use_coop = coop->exec_mode == 2 || (coop->exec_mode == 0 && !kLaneCapable);
     if (use_coop) {
         if (method != DSB_METHOD_BDF) return cudaErrorNotSupported;   // cooperative path: BDF only

@@ -387,6 +387,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
             int r = 0;
             int next = first ? R_STEP : R_OUTPUT;
             bool stopped_on_root = false;
+            bool reset_now = false;            // a reset was applied at a root: the stop time is set again, then R_STEP
             if constexpr (NR > 0) {
                 // check for a root within the accepted step (runge_kutta.rs:935-948), before the stop time is handled
                 if (!first) {
@@ -413,13 +414,48 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                             ++col;
                         }
                         interpolate(t_root, yo);
-                        if (col < nt) {
-#pragma unroll
-                            for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
-                            ++col;
-                        }
                         t = t_root;
-                        finish(DSB_STATUS_OK);
+                        bool ended = true;
+                        if constexpr (dsb_model_has_reset<M>::value) {
+                            if (!free_running) {
+                                // has_reset (method.rs:783-797): apply_reset (sdirk.rs:368-374 -> state.rs:279-306:
+                                // y <- reset(y, t), dy <- f(y, t)), then set_stop_time(final_time) and on with the
+                                // integration -- or TstopReached.  The step size, the Jacobian and the LU stay as they
+                                // are; Rk::start_step (runge_kutta.rs:446-464) finds the state mutated, re-initialises
+                                // the root finder and sets the stop time once more.
+                                double yr[N], dyr[N];
+                                M::reset(yo, pl, t, yr);
+                                M::rhs(yr, pl, t, dyr);
+                                st.v[DSB_STAT_RHS_CALLS] += 1;
+#pragma unroll
+                                for (int i = 0; i < N; ++i) {
+                                    SY(i) = yr[i]; SDY(i) = dyr[i];
+                                    wt[i] = dsb_abs(yr[i]) * pa.rtol + pa.atol[i];
+                                }
+                                root_found = -1;
+                                ended = false;
+                                if (t < bb.t_eval[nt - 1]) {
+                                    has_tstop = true; tstop = bb.t_eval[nt - 1];
+                                    r = handle_tstop(tstop);                       // method.rs:792
+                                    if (r == 0) {
+                                        M::root(yr, pl, t, rf.g0);                 // start_step: root_finder.init
+                                        rf.t0 = t;
+                                        r = handle_tstop(tstop);                   // start_step: set_stop_time(tstop)
+                                    }
+                                    if (r == 1) r = -DSB_STATUS_STOP_TIME_AT_CURRENT;
+                                    stopped_on_root = false; reset_now = true;
+                                    next = R_STEP;
+                                } else finish(DSB_STATUS_OK);                      // TstopReached
+                            }
+                        }
+                        if (ended) {
+                            if (col < nt) {
+#pragma unroll
+                                for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
+                                ++col;
+                            }
+                            finish(DSB_STATUS_OK);
+                        }
                     }
                 }
             }
@@ -430,11 +466,11 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                     r = handle_tstop(tstop);
                     if (r == 1) r = -DSB_STATUS_STOP_TIME_AT_CURRENT;
                 }
-            } else if (has_tstop && !stopped_on_root) {
+            } else if (has_tstop && !stopped_on_root && !reset_now) {
                 r = handle_tstop(tstop);
                 if (r == 1) { reached = true; has_tstop = false; }
             }
-            if (stopped_on_root) {
+            if (stopped_on_root || state == R_FINISH) {
                 // the lane is on its way to FINISH
             } else if (r < 0) finish(-r);
             else state = next;

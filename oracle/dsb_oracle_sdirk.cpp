@@ -86,6 +86,7 @@ struct Sdirk : Method {
     // root finding (runge_kutta.rs:43, 142-147, 935-948)
     RootFinder root_finder;
     double root_t_ = 0.0; int root_idx_ = -1;
+    bool is_state_mutated = false;                         // runge_kutta.rs:50: set by state_mut() (:391-394)
 
     Sdirk(const Problem& p, const Tableau& t) : pr(p), n(p.n()), tab(t) {}
 
@@ -241,7 +242,15 @@ struct Sdirk : Method {
 
     // sdirk.rs:409-543
     StopReason step(int* err) override {
-        double h = h_;                                       // rk.start_step()
+        if (is_state_mutated) {                              // rk.start_step() (runge_kutta.rs:446-464)
+            if (pr.model.nroots > 0) root_finder.init(pr, y_.data(), t_);
+            if (has_tstop) {
+                int e = set_stop_time(tstop);
+                if (e) { *err = e; return STEP_ERROR; }
+            }
+            is_state_mutated = false;
+        }
+        double h = h_;
         if (std::fabs(h) < pr.opt.min_timestep) { *err = ST_STEP_SIZE_TOO_SMALL; return STEP_ERROR; }
         op_h = h;
         int nattempts = 0;
@@ -344,6 +353,11 @@ struct Sdirk : Method {
 
     // runge_kutta.rs:1080-1127 (+ :962-981 beta dense output, :1004-1024 Hermite)
     int interpolate(double t, double* y) const override {
+        if (is_state_mutated) {                              // runge_kutta.rs:1089-1096
+            if (t != t_) return ST_INTERPOLATION_TIME_AFTER_CURRENT;
+            for (int k = 0; k < n; ++k) y[k] = y_[k];
+            return ST_OK;
+        }
         const bool is_forward = h_ > 0.0;
         if ((is_forward && (t > t_ || t < ot_)) || (!is_forward && (t < t_ || t > ot_)))
             return ST_INTERPOLATION_TIME_AFTER_CURRENT;
@@ -384,8 +398,21 @@ struct Sdirk : Method {
         Vec ynew(n);
         int e = interpolate(t, ynew.data());
         if (e) return e;
-        y_ = ynew;                          // dy is interpolated as well in the reference; nothing reads it afterwards here
+        y_ = ynew;                          // dy is interpolated as well in the reference; apply_reset overwrites it
         t_ = t;
+        is_state_mutated = true;            // through state_mut()
+        return ST_OK;
+    }
+    // sdirk.rs:368-374 -> state.rs:279-306 through Rk::state_mut() (no mass matrix: y <- reset(y, t), dy <- f(y, t));
+    // the step size, the Jacobian and its LU stay as they are: the next Sdirk::step only re-initialises the root finder
+    // and the stop time (Rk::start_step)
+    int apply_reset() override {
+        if (!pr.model.reset || pr.model.has_mass) return ST_BAD_ARG;
+        is_state_mutated = true;
+        Vec ynew(n);
+        pr.model.reset(y_.data(), pr.p.data(), t_, ynew.data());
+        y_ = ynew;
+        pr.rhs(y_.data(), t_, dy_.data());
         return ST_OK;
     }
 

@@ -96,27 +96,28 @@ def test_battery_voltage_cut_off_bit_exact(dsb, oracle, model, method, B, block,
     assert np.abs(ys[stopped, ncols[stopped] - 1, 0] - 3.105).max() < 1e-6
 
 
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
 @pytest.mark.parametrize("tol", [1e-6, 1e-9])
-def test_reset_bit_exact(dsb, oracle, tol):
+def test_reset_bit_exact(dsb, oracle, tol, method):
     """Reset functions (OdeEquations::reset): the reference's exponential_decay_with_reset_problem swept over rate and
     initial value -- every root applies y -> 0.4 and the solve runs on to the last t_eval (method.rs:783-797,
-    state.rs:246-270, bdf.rs:1291-1318)."""
+    state.rs:246-270, bdf.rs:1291-1318; Rk::start_step runge_kutta.rs:446-464 for the SDIRK methods)."""
     B = 2000
     idx = np.arange(B)
     from diffsol_b200 import sweeps
     p = np.stack([0.02 * 50.0 ** sweeps.uniform(idx, 0), 0.35 + 1.65 * sweeps.uniform(idx, 1)], axis=1)
     t_eval = np.arange(1.0, 41.0)
-    solver = dsb.OdeBuilder().rhs_implicit("exp_decay_reset").p(p).rtol(tol).atol([tol]).build().bdf()
+    solver = getattr(dsb.OdeBuilder().rhs_implicit("exp_decay_reset").p(p).rtol(tol).atol([tol]).build(), method)()
     ys = solver.solve_dense(t_eval)
     root_idx, ncols = solver.root_info()
-    desc = oracle.make_desc("exp_decay_reset", powmode=1, rtol=tol, atol=[tol])
+    desc = oracle.make_desc("exp_decay_reset", method=method, powmode=1, rtol=tol, atol=[tol])
     ys_o, stats_o, status_o, t_root_o, root_idx_o, ncols_o = oracle.batch_solve_dense_roots(desc, p, t_eval)
     assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
     assert np.array_equal(root_idx, root_idx_o) and (root_idx == -1).all() and np.array_equal(ncols, ncols_o)
     assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
     assert np.array_equal(ys, ys_o, equal_nan=True)
-    with pytest.raises(dsb.DiffsolB200Error):               # only the on-chip BDF lane kernel applies resets
-        dsb.OdeBuilder().rhs_implicit("exp_decay_reset").p(p[:4]).build().tr_bdf2().solve_dense([1.0])
+    with pytest.raises(dsb.DiffsolB200Error):               # only the on-chip lane kernels apply resets
+        dsb.OdeBuilder().rhs_implicit("exp_decay_reset").p(p[:4]).build().bdf().set_execution("block").solve_dense([1.0])
 
 
 def test_roots_not_on_the_block_per_instance_path(dsb):

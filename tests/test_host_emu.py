@@ -136,13 +136,16 @@ def test_band_dae_inconsistent_initial_values_on_host(oracle, method, coloring):
     assert np.abs(r["ys"][:, :, 0] - 0.25 * p[:, :1]).max() < 1e-12 and np.abs(r["ys"][:, :, -1] - 0.25 * p[:, :1]).max() < 1e-12
 
 
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
 @pytest.mark.parametrize("tol", [1e-6, 1e-9])
-def test_reset_in_the_bdf_lane_kernel_on_host(oracle, tol):
-    """Equations with a reset function: a root does not end solve_dense (method.rs:783-797); the BDF lane kernel applies
-    the reset, re-initialises to first order (bdf.rs:1291-1318) and integrates on, many resets per instance."""
+def test_reset_in_the_on_chip_lane_kernels_on_host(oracle, tol, method):
+    """Equations with a reset function: a root does not end solve_dense (method.rs:783-797).  The BDF lane kernel applies
+    the reset and re-initialises to first order (bdf.rs:1291-1318); the SDIRK lane kernel applies it and re-initialises
+    the root finder and the stop time (Rk::start_step, runge_kutta.rs:446-464); both integrate on, many resets per
+    instance."""
     idx = np.arange(100)
     p = np.stack([0.02 * 50.0 ** sweeps.uniform(idx, 0), 0.35 + 1.65 * sweeps.uniform(idx, 1)], axis=1)
-    r, o = run_both_roots(oracle, "exp_decay_reset", p, np.arange(1.0, 41.0), rtol=tol, atol=[tol])
+    r, o = run_both_roots(oracle, "exp_decay_reset", p, np.arange(1.0, 41.0), method=method, rtol=tol, atol=[tol])
     assert_same_roots(r, o)
     assert (o[2] == 0).all() and (o[4] == -1).all()
     assert r["ys"][:, -1, 0].max() <= 0.6 + 1e-6          # nobody stays above the first root level

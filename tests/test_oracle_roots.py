@@ -2,6 +2,7 @@
 bdf.rs:1566-1579; fn solve_dense RootFound branch, method.rs:774-805, 493-503) against the reference's own tests of
 the same problem: exponential_decay_problem_with_root (test_models/exponential_decay.rs:370-390, root y[0] - 0.6)."""
 import numpy as np
+import pytest
 
 
 def weighted_norm(y, ystar, atol, rtol):
@@ -141,8 +142,10 @@ def test_spm_discharge_ends_at_the_lower_cut_off(oracle):
     assert np.isnan(v[1, ncols[1]:]).all()
 
 
-def test_solve_dense_with_reset(oracle):
-    """ode_solver/mod.rs:1302-1372 test_solve_dense_with_reset on exponential_decay_with_reset_problem
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
+def test_solve_dense_with_reset(oracle, method):
+    """ode_solver/mod.rs:1302-1372 test_solve_dense_with_reset (bdf.rs test_solve_dense_with_reset_bdf,
+    sdirk.rs:1114-1122 test_solve_dense_with_reset_tr_bdf2) on exponential_decay_with_reset_problem
     (test_models/exponential_decay.rs:818-880: roots y[0] - 0.6 and y[0] - 0.3, reset y -> 0.4): solve_dense applies the
     resets and runs on to the last evaluation time; the state just before the second event is 0.3, just after 0.4."""
     k = 0.1
@@ -151,7 +154,7 @@ def test_solve_dense_with_reset(oracle):
     final_time = 2.0 * t_stop
     dt = 1e-3                                             # the reference probes the exact event time with solve(); here: just around it
     t_eval = np.array([1e-12, t_stop - dt, t_stop + dt, final_time])
-    desc = oracle.make_desc("exp_decay_reset")            # builder defaults, libm pow
+    desc = oracle.make_desc("exp_decay_reset", method=method)            # builder defaults, libm pow
     ys, stats, status, t_root, root_idx, ncols = oracle.batch_solve_dense_roots(desc, [[k, 1.0]], t_eval)
     assert status[0] == 0 and root_idx[0] == -1 and ncols[0] == len(t_eval)       # TstopReached, every column filled
     pre = np.full(2, 0.4 * np.exp(-k * (t_eval[1] - t_root0)))
