@@ -34,6 +34,8 @@ enum dsb_model_id {
     DSB_MODEL_HEAT1D_DAE_32_BC = 16,    // n=32 np=3   heat1d_dae_32 with warm boundaries 0 = u - height/4: INCONSISTENT initial values
     DSB_MODEL_EXP_DECAY_RESET = 17,     // n=2  np=2   exp_decay with the roots y[0] - 0.6, y[0] - 0.3 and the reset y -> 0.4 (exponential_decay.rs:818-880)
     DSB_MODEL_HEAT2D_10 = 18,           // n=100 np=0  2-D heat equation on a 10 x 10 grid, boundary rows algebraic (test_models/heat2d.rs), states only
+    DSB_MODEL_BALL_BOUNCE = 19,         // n=2  np=3   bouncing ball x' = v, v' = -g with the root x and the reset v -> -e v (ode_solver/mod.rs:1001-1080)
+    DSB_MODEL_EXP_DECAY_TWO_ROOTS = 20, // n=2  np=2   exp_decay with the roots y[0] - 0.6, y[0] - 0.3 and no reset (exponential_decay.rs:827-832, 890-912)
     DSB_MODEL_COUNT
 };
 
@@ -73,6 +75,35 @@ struct ModelExpDecayReset : ModelExpDecay {
     static constexpr bool HAS_RESET = true;
     DSB_HD static void root(const double* x, const double*, double, double* g) { g[0] = x[0] - 0.6; g[1] = x[0] - 0.3; }
     DSB_HD static void reset(const double*, const double*, double, double* y) { for (int i = 0; i < N; ++i) y[i] = 0.4; }
+};
+
+// The reference's root-index test problem (test_models/exponential_decay.rs:890-912, exponential_decay_with_two_roots_problem):
+// the same two root functions without a reset; the solve ends at the first root and reports which one fired.
+struct ModelExpDecayTwoRoots : ModelExpDecay {
+    static constexpr int NROOTS = 2;
+    DSB_HD static void root(const double* x, const double*, double, double* g) { g[0] = x[0] - 0.6; g[1] = x[0] - 0.3; }
+};
+
+// The reference's bouncing-ball test (ode_solver/mod.rs:1001-1080: DiffSL text `g { 9.81 } h { 10.0 } u_i { x = h, v = 0 }
+// F_i { v, -g } stop { x }`, restitution e = 0.8 applied by the test at the root: v <- -e v, x <- max(x, eps)), with
+// g, h and e as the instance's parameters p = [g, h, e] and the test's state update as the reset function.
+struct ModelBallBounce {
+    static constexpr int N = 2, NP = 3;
+    static constexpr bool HAS_MASS = false;
+    static constexpr int NROOTS = 1;
+    static constexpr bool HAS_RESET = true;
+    DSB_HD static void rhs(const double* x, const double* p, double, double* y) { y[0] = x[1]; y[1] = -p[0]; }
+    DSB_HD static void jac_mul(const double*, const double*, double, const double* v, double* y) { y[0] = v[1]; y[1] = 0.0; }
+    DSB_HD static void mass(const double* x, const double*, double, double beta, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = x[i] + beta * y[i];
+    }
+    DSB_HD static void init(const double* p, double, double* y) { y[0] = p[1]; y[1] = 0.0; }
+    DSB_HD static void root(const double* x, const double*, double, double* g) { g[0] = x[0]; }
+    DSB_HD static void reset(const double* x, const double* p, double, double* y) {
+        const double eps = 2.220446049250313e-16;
+        y[0] = x[0] > eps ? x[0] : eps;
+        y[1] = x[1] * -p[2];
+    }
 };
 
 struct ModelExpDecayAlgebraic {
@@ -526,6 +557,8 @@ template <> struct dsb_model_by_id<DSB_MODEL_SPM99_STOP> { typedef ModelSpm99Sto
 template <> struct dsb_model_by_id<DSB_MODEL_HEAT1D_DAE_32_BC> { typedef ModelHeat1dDaeBc<32> type; };
 template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY_RESET> { typedef ModelExpDecayReset type; };
 template <> struct dsb_model_by_id<DSB_MODEL_HEAT2D_10> { typedef ModelHeat2d<10> type; };
+template <> struct dsb_model_by_id<DSB_MODEL_BALL_BOUNCE> { typedef ModelBallBounce type; };
+template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY_TWO_ROOTS> { typedef ModelExpDecayTwoRoots type; };
 
 // traits of an equation set: written component-wise (`*_i` functions), declares a band for df/dy
 template <class M, class = void> struct dsb_is_componentwise : std::false_type {};
@@ -556,6 +589,8 @@ inline bool dsb_dispatch_model(int id, F&& f) {
         case DSB_MODEL_HEAT1D_DAE_32_BC: f.template operator()<ModelHeat1dDaeBc<32>>(); return true;
         case DSB_MODEL_EXP_DECAY_RESET: f.template operator()<ModelExpDecayReset>(); return true;
         case DSB_MODEL_HEAT2D_10: f.template operator()<ModelHeat2d<10>>(); return true;
+        case DSB_MODEL_BALL_BOUNCE: f.template operator()<ModelBallBounce>(); return true;
+        case DSB_MODEL_EXP_DECAY_TWO_ROOTS: f.template operator()<ModelExpDecayTwoRoots>(); return true;
         default: return false;
     }
 }

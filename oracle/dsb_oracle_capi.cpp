@@ -180,6 +180,44 @@ int orc_harness_tstop(const orc_problem_desc* d, const double* p, int np, const 
     return err;
 }
 
+// The driver loop of the reference's test_ball_bounce (ode_solver/mod.rs:1024-1080): set_stop_time(tstop), step until the
+// first root, put the solver's state at the root and apply the model's reset function (the test's hand-written update
+// v <- -e v, x <- max(x, eps), dy[0] <- v), then take up to nsteps further steps and record (t, y) after each; a step
+// that reaches the stop time is the last one.  rows is nsteps x (1 + n); *ntaken = rows written.
+int orc_steps_after_first_root(const orc_problem_desc* d, const double* p, int np, double tstop, int nsteps,
+                               double* rows, int* ntaken) {
+    *ntaken = 0;
+    Problem pr;
+    int err = build_problem(d, p, np, &pr);
+    if (err) return err;
+    std::unique_ptr<Method> m(make_method(pr, d->method, &err));
+    if (!m) return err;
+    const int n = pr.n();
+    err = m->set_stop_time(tstop);
+    if (err) return err;
+    while (true) {
+        StopReason r = m->step(&err);
+        if (r == STEP_ERROR) return err;
+        if (r == TSTOP_REACHED) break;
+        if (r == ROOT_FOUND) {
+            err = m->state_mut_back(m->root_t());
+            if (!err) err = m->apply_reset();
+            if (err) return err;
+            break;
+        }
+    }
+    for (int k = 0; k < nsteps; ++k) {
+        StopReason r = m->step(&err);
+        if (r == STEP_ERROR) return err;
+        if (r == ROOT_FOUND) return ST_BAD_ARG;            // "should be an internal timestep but found a root"
+        rows[(size_t)k * (1 + n)] = m->t();
+        for (int i = 0; i < n; ++i) rows[(size_t)k * (1 + n) + 1 + i] = m->y()[i];
+        *ntaken = k + 1;
+        if (r == TSTOP_REACHED) break;
+    }
+    return ST_OK;
+}
+
 // Batched driver: instance b uses params[b*np .. (b+1)*np) (instance-major, as the reference lays
 // out batched parameters, test_models/exponential_decay.rs:297-304).  out[b] is n x nt col-major,
 // stats[b] the 16 counters, status[b] the error code.  threads over instances = the CPU baseline.

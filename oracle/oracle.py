@@ -50,6 +50,8 @@ MODELS = {
     "heat1d_dae_32_bc": 16,
     "exp_decay_reset": 17,
     "heat2d_10": 18,
+    "ball_bounce": 19,
+    "exp_decay_two_roots": 20,
 }
 
 
@@ -127,6 +129,9 @@ def lib():
         L.orc_model_root.argtypes = [ctypes.c_int, dp, dp, ctypes.c_double, dp]
         L.orc_math.restype = ctypes.c_double
         L.orc_math.argtypes = [ctypes.c_int, ctypes.c_double]
+        L.orc_steps_after_first_root.restype = ctypes.c_int
+        L.orc_steps_after_first_root.argtypes = [ctypes.POINTER(ProblemDesc), dp, ctypes.c_int, ctypes.c_double,
+                                                 ctypes.c_int, dp, ctypes.POINTER(ctypes.c_int)]
         _lib = L
     return _lib
 
@@ -202,6 +207,18 @@ def solve_dense(desc, p, t_eval):
 def harness(desc, p, t_points, use_tstop=False):
     """The reference's test_ode_solver() loop -> (rc, ys[npts, n], stats, final)"""
     return _run(lib().orc_harness_tstop if use_tstop else lib().orc_harness, desc, p, t_points)
+
+
+def steps_after_first_root(desc, p, tstop, nsteps):
+    """The reference's test_ball_bounce loop (ode_solver/mod.rs:1024-1080) -> (rc, t[k], y[k, n]) for the k <= nsteps
+    internal steps taken after the first root + reset."""
+    n, np_, _ = _dims_by_id(desc.model_id)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    rows = np.full((nsteps, 1 + n), np.nan)
+    taken = ctypes.c_int()
+    rc = lib().orc_steps_after_first_root(ctypes.byref(desc), _dp(p), int(p.size), ctypes.c_double(tstop), int(nsteps),
+                                          _dp(rows), ctypes.byref(taken))
+    return rc, rows[:taken.value, 0].copy(), rows[:taken.value, 1:].copy()
 
 
 def batch_solve_dense(desc, params, t_eval, nthreads=0):

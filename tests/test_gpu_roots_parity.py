@@ -120,6 +120,48 @@ def test_reset_bit_exact(dsb, oracle, tol, method):
         dsb.OdeBuilder().rhs_implicit("exp_decay_reset").p(p[:4]).build().bdf().set_execution("block").solve_dense([1.0])
 
 
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
+def test_ball_bounce_bit_exact(dsb, oracle, method):
+    """The reference's bouncing ball (ode_solver/mod.rs:1001-1080; known answers bdf.rs:2691-2697 pinned on the oracle in
+    tests/test_oracle_roots.py) swept over gravity, drop height and restitution: several root + reset events per
+    instance inside the lane kernel."""
+    B = 3000
+    idx = np.arange(B)
+    from diffsol_b200 import sweeps
+    p = np.stack([5.0 + 10.0 * sweeps.uniform(idx, 0), 2.0 + 18.0 * sweeps.uniform(idx, 1), 0.8 + 0.15 * sweeps.uniform(idx, 2)], axis=1)
+    t_eval = np.linspace(0.05, 4.0, 80)      # ends before the earliest accumulation point of bounces (Zeno time) in the sweep
+    solver = getattr(dsb.OdeBuilder().rhs_implicit("ball_bounce").p(p).build(), method)()
+    ys = solver.solve_dense(t_eval)
+    root_idx, ncols = solver.root_info()
+    desc = oracle.make_desc("ball_bounce", method=method, powmode=1)
+    ys_o, stats_o, status_o, t_root_o, root_idx_o, ncols_o = oracle.batch_solve_dense_roots(desc, p, t_eval)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(root_idx, root_idx_o) and np.array_equal(ncols, ncols_o)
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o, equal_nan=True)
+
+
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
+def test_root_index_bit_exact(dsb, oracle, method):
+    """exponential_decay_with_two_roots_problem (test_models/exponential_decay.rs:890-912; test_root_found_index,
+    ode_solver/mod.rs:1187-1220): which of the two root functions fired, per instance."""
+    B = 3000
+    idx = np.arange(B)
+    from diffsol_b200 import sweeps
+    p = np.stack([0.02 * 50.0 ** sweeps.uniform(idx, 0), 0.1 + 1.4 * sweeps.uniform(idx, 1)], axis=1)
+    t_eval = np.arange(1.0, 21.0)
+    solver = getattr(dsb.OdeBuilder().rhs_implicit("exp_decay_two_roots").p(p).build(), method)()
+    ys = solver.solve_dense(t_eval)
+    root_idx, ncols = solver.root_info()
+    desc = oracle.make_desc("exp_decay_two_roots", method=method, powmode=1)
+    ys_o, stats_o, status_o, t_root_o, root_idx_o, ncols_o = oracle.batch_solve_dense_roots(desc, p, t_eval)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(root_idx, root_idx_o) and np.array_equal(ncols, ncols_o)
+    assert set(root_idx.tolist()) == {-1, 0, 1}
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o, equal_nan=True)
+
+
 def test_roots_not_on_the_block_per_instance_path(dsb):
     p = sweep(8)
     prob = dsb.OdeBuilder().rhs_implicit("exp_decay_root").p(p).build()

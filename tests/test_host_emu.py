@@ -152,6 +152,20 @@ def test_reset_in_the_on_chip_lane_kernels_on_host(oracle, tol, method):
 
 
 @pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
+def test_ball_bounce_in_the_on_chip_lane_kernels_on_host(oracle, method):
+    """The reference's bouncing ball (ode_solver/mod.rs:1001-1080) swept over gravity, drop height and restitution:
+    several bounces per instance, each one a root + reset inside the lane kernel; the window ends before the earliest
+    accumulation point of bounces in the sweep (t_b (1 + e) / (1 - e) >= 4.6)."""
+    idx = np.arange(60)
+    p = np.stack([5.0 + 10.0 * sweeps.uniform(idx, 0), 2.0 + 18.0 * sweeps.uniform(idx, 1), 0.8 + 0.15 * sweeps.uniform(idx, 2)], axis=1)
+    r, o = run_both_roots(oracle, "ball_bounce", p, np.linspace(0.05, 4.0, 80), method=method)
+    assert_same_roots(r, o)
+    assert (o[2] == 0).all() and (o[4] == -1).all()
+    assert (o[5] >= 79).all()
+    assert np.nanmin(r["ys"][:, :, 0]) > -1e-3             # the ball stays above the ground
+
+
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
 def test_backward_integration_on_host(oracle, method):
     """negative_exponential_decay_problem (test_models/exponential_decay.rs:168-197: h0 = -1, points 0, -1, .., -9)
     through the step()/interpolate() loop of the reference's harness, as bdf.rs:1729-1733 / sdirk.rs:669-673 run it."""
@@ -167,3 +181,16 @@ def test_backward_integration_on_host(oracle, method):
     exact = y0 * np.exp(-k * pts)
     err = np.sqrt(np.mean(((ys_o - exact[:, None]) / (np.abs(exact[:, None]) * 1e-6 + 1e-6)) ** 2, axis=1))
     assert err.max() < (30.0 if method == "esdirk34" else 20.0)      # the reference's acceptance thresholds
+
+
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
+def test_root_index_in_the_on_chip_lane_kernels_on_host(oracle, method):
+    """exponential_decay_with_two_roots_problem (test_models/exponential_decay.rs:890-912) swept over rate and initial
+    value: instances started above 0.6 stop on root 0, those between 0.3 and 0.6 on root 1, the rest run to the end."""
+    idx = np.arange(120)
+    p = np.stack([0.02 * 50.0 ** sweeps.uniform(idx, 0), 0.1 + 1.4 * sweeps.uniform(idx, 1)], axis=1)
+    r, o = run_both_roots(oracle, "exp_decay_two_roots", p, np.arange(1.0, 21.0), method=method)
+    assert_same_roots(r, o)
+    fired = o[4]
+    assert set(fired.tolist()) == {-1, 0, 1}
+    assert (fired[p[:, 1] > 0.6] != 1).all() and (fired[p[:, 1] < 0.6] != 0).all() and (fired[p[:, 1] < 0.3] == -1).all()

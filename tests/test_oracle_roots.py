@@ -164,3 +164,79 @@ def test_solve_dense_with_reset(oracle, method):
     assert abs(ys[0, 1, 0] - 0.3) < 1e-4 and abs(ys[0, 2, 0] - 0.4) < 1e-4
     # the state keeps cycling between 0.4 and 0.3 until the final time
     assert 0.3 <= ys[0, 3, 0] <= 0.4
+
+
+BALL_BOUNCE_BDF = {            # bdf.rs:2691-2697: the three steps after the first bounce
+    "x": [0.003978879413779122, 0.007955671343150521, 0.015904102550507716],
+    "v": [11.202229406994425, 11.198746111635534, 11.191779520917754],
+    "t": [1.4281779078441663, 1.4285126937676944, 1.4292157442071036],
+}
+BALL_BOUNCE_TR_BDF2 = {"x": [6.375884661615263], "v": [0.6878538646461059], "t": [2.5]}     # sdirk.rs:1084-1086
+
+
+@pytest.mark.parametrize("method,expected", [("bdf", BALL_BOUNCE_BDF), ("tr_bdf2", BALL_BOUNCE_TR_BDF2)])
+def test_ball_bounce_known_answers(oracle, method, expected):
+    """test_ball_bounce (ode_solver/mod.rs:1024-1080) with the known answers of bdf.rs:2683-2712 and sdirk.rs:1076-1092:
+    g = 9.81, drop height 10, restitution 0.8, stop time 2.5.  The test's state update at the root (v <- -e v,
+    x <- max(x, eps), dy[0] <- v) is the model's reset function here; the reference then takes up to three internal
+    steps and compares (x, v, t) after each with 1e-4.  BDF restarts at first order with small steps; TR-BDF2 keeps its
+    step size and reaches the stop time with the first step after the bounce."""
+    desc = oracle.make_desc("ball_bounce", method=method)           # builder defaults: rtol = atol = 1e-6, h0 = 1
+    rc, t, y = oracle.steps_after_first_root(desc, [9.81, 10.0, 0.8], 2.5, 3)
+    assert rc == 0 and len(t) == len(expected["t"])
+    assert np.abs(t - expected["t"]).max() < 1e-4                   # the reference's tolerance
+    # x and v after each step reproduce the reference's recorded values to the last digit
+    assert np.abs(y[:, 0] - expected["x"]).max() < 1e-14
+    assert np.abs(y[:, 1] - expected["v"]).max() < 1e-14
+
+
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
+def test_ball_bounce_solve_dense(oracle, method):
+    """The same problem through solve_dense with the reset function: the ball keeps bouncing (energy loss 1 - e^2 per
+    bounce) and the trajectory follows the closed-form piecewise parabola."""
+    g, h0, e = 9.81, 10.0, 0.8
+    t_eval = np.linspace(0.05, 6.0, 120)
+    desc = oracle.make_desc("ball_bounce", method=method)
+    ys, stats, status, t_root, root_idx, ncols = oracle.batch_solve_dense_roots(desc, [[g, h0, e]], t_eval)
+    assert status[0] == 0 and root_idx[0] == -1 and ncols[0] == len(t_eval)
+    tb, v0, exact = np.sqrt(2 * h0 / g), 0.0, []
+    t_start, x_start = 0.0, h0
+    for t in t_eval:
+        while True:
+            t_land = t_start + (v0 + np.sqrt(v0 * v0 + 2 * g * x_start)) / g
+            if t <= t_land:
+                break
+            v0 = e * (g * (t_land - t_start) - v0)
+            t_start, x_start = t_land, 0.0
+        exact.append(x_start + v0 * (t - t_start) - 0.5 * g * (t - t_start) ** 2)
+    assert np.abs(ys[0, :, 0] - np.array(exact)).max() < 2e-3
+    assert t_eval[-1] > tb + 2 * e * np.sqrt(2 * h0 / g)          # more than one bounce inside the window
+
+
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2"])
+def test_root_found_index(oracle, method):
+    """test_root_found_index (ode_solver/mod.rs:1187-1220; bdf.rs:2725-2731, sdirk.rs:1096-1103) on
+    exponential_decay_with_two_roots_problem: root 0 (y[0] = 0.6) fires at t = -ln(0.6) / 0.1 within 1e-4, and the solve
+    reports index 0.  Started below 0.6 the second root function (y[0] = 0.3) fires instead, with index 1."""
+    desc = oracle.make_desc("exp_decay_two_roots", method=method)
+    t_eval = np.array([50.0, 100.0])                      # set_stop_time(100)
+    ys, stats, status, t_root, root_idx, ncols = oracle.batch_solve_dense_roots(desc, [[0.1, 1.0], [0.1, 0.5]], t_eval)
+    assert (status == 0).all() and root_idx.tolist() == [0, 1] and ncols.tolist() == [1, 1]
+    assert abs(t_root[0] - (-np.log(0.6) / 0.1)) < 1e-4
+    assert abs(t_root[1] - (-np.log(0.3 / 0.5) / 0.1)) < 1e-4
+    assert abs(ys[0, 0, 0] - 0.6) < 1e-5 and abs(ys[1, 0, 0] - 0.3) < 1e-5
+
+
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2"])
+def test_tstop(oracle, method):
+    """test_tstop_bdf (bdf.rs:2490-2494) / test_tstop_tr_bdf2: test_ode_solver(.., use_tstop = true) on the exponential
+    decay problem -- set_stop_time(point), step until TstopReached, state().y against the analytic solution with the
+    harness's criterion (ode_solver/mod.rs:164-173: weighted error norm < 15)."""
+    k, y0 = 0.1, 1.0
+    pts = np.arange(0.0, 10.0)[1:]                        # a stop time at the current time is an error (t = 0)
+    desc = oracle.make_desc("exp_decay", method=method)
+    rc, ys, stats, fin = oracle.harness(desc, [k, y0], pts, use_tstop=True)
+    assert rc == 0 and abs(fin["t"] - pts[-1]) < 1e-12
+    for t, y in zip(pts, ys):
+        exact = np.full(2, y0 * np.exp(-k * t))
+        assert weighted_norm(y, exact, 1e-6, 1e-6) < 15.0
