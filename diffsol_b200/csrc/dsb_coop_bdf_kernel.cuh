@@ -18,6 +18,7 @@
 #include <type_traits>
 
 #include "dsb_coop.cuh"
+#include "dsb_roots.cuh"
 #include "dsb_lane.cuh"
 #include "dsb_models.h"
 
@@ -99,6 +100,9 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                                 const __grid_constant__ DsbCoopWorkspace ws, unsigned long long* __restrict__ work_counter) {
     constexpr int N = M::N;
     constexpr int NP = M::NP;
+    constexpr int NR = dsb_model_nroots<M>::value;
+    constexpr int NOUT = dsb_model_nout<M>::value;
+    constexpr bool HAS_OUT = dsb_model_nout<M>::has_out;
     typedef CoopEval<M> E;
     extern __shared__ unsigned char dsb_coop_bdf_smem[];
     double* const vec = (double*)dsb_coop_bdf_smem;
@@ -523,9 +527,35 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
             const double kp = pa.opt.pi_control_proportional / order_f;
             return dsb_pow(err, -(ki + kp)) * dsb_pow(prev_error_norm, kp);
         };
+        // interpolate_from_diff (bdf.rs:767-782) into a (free) shared vector, for the output / root functions
+        auto interpolate_to_shared = [&](double tq, double* dst) {
+            __syncthreads();
+            for (int i = tid; i < N; i += T) {
+                double time_factor = 1.0;
+                double yo = Dm[i];
+                for (int j = 0; j < order; ++j) {
+                    const double j_t = (double)j;
+                    time_factor *= (tq - (t - h * j_t)) / (h * (1.0 + j_t));
+                    yo = time_factor * Dm[(j + 1) * N + i] + yo;
+                }
+                dst[i] = yo;
+            }
+            __syncthreads();
+        };
+        // one column of the solve_dense result (dense_write_out, method.rs:822-848): the interpolated state, or -- for
+        // equations with an output function -- out(y(tq), tq)
         auto interpolate_and_write = [&](double tq, int col) -> int {
             const bool is_forward = h > 0.0;
             if ((is_forward && tq > t) || (!is_forward && tq < t)) return DSB_STATUS_INTERPOLATION_TIME_AFTER_CURRENT;
+            if constexpr (HAS_OUT) {
+                interpolate_to_shared(tq, tmpv);
+                if (tid == 0) {
+                    double o[NOUT];
+                    M::out(tmpv, p, tq, o);
+                    for (int k = 0; k < NOUT; ++k) bb.ys[((int64_t)col * NOUT + k) * B + inst] = o[k];
+                }
+                return DSB_STATUS_OK;
+            }
             __syncthreads();
             for (int i = tid; i < N; i += T) {
                 double time_factor = 1.0;
@@ -539,6 +569,13 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
             }
             return DSB_STATUS_OK;
         };
+        // root finding (nonlinear_solver/root.rs; bdf.rs:361-366, 1566-1579): every thread of the block runs the same
+        // scalar iteration on the same values (the state it reads is in shared memory), so the block's control flow
+        // stays uniform; only compiled for equations with roots
+        LaneRootFinder<(NR > 0 ? NR : 1), DsbDivInline> rf;
+        rf.t0 = t;
+        for (int r = 0; r < (NR > 0 ? NR : 1); ++r) rf.g0[r] = 0.0;
+        int root_found = -1;
 
         int col = 0;
         if (status == DSB_STATUS_OK) {
@@ -555,6 +592,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                 Dm[i] = ys[i]; Dm[N + i] = dys[i] * h;
             }
             __syncthreads();
+            if constexpr (NR > 0) { M::root(ys, p, t, rf.g0); rf.t0 = t; }      // Bdf::_new: root_finder.init(root_fn, y, t)
             if (!free_running) {
                 has_tstop = true; tstop = bb.t_eval[nt - 1];
                 const int r = handle_tstop(tstop);
@@ -686,12 +724,39 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                         jacobian_updates(new_h * pa.tab.alpha[order], DSB_STEP_SUCCESS);
                     }
                 }
-                if (has_tstop) {
+                if constexpr (NR > 0) {
+                    // check for a root within the accepted step (bdf.rs:1566-1579), after the step-size update and before
+                    // the stop time is handled; the interpolated state of the secant iteration goes to the (free) vector yc
+                    double t_root = t;
+                    __syncthreads();
+                    const bool stopped_on_root = rf.check_root(t, [&](double (&gv)[NR]) { M::root(ys, p, t, gv); },
+                                                               [&](double t_mid, double (&gv)[NR]) {
+                                                                   interpolate_to_shared(t_mid, yc);
+                                                                   M::root(yc, p, t_mid, gv);
+                                                               }, t_root, root_found);
+                    if (stopped_on_root) {
+                        // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root)
+                        // (bdf.rs:1228-1262), then the state at the root in the next column (method.rs:493-503)
+                        while (col < nt && bb.t_eval[col] <= t_root) {
+                            (void)interpolate_and_write(bb.t_eval[col], col);
+                            ++col;
+                        }
+                        if (col < nt) {
+                            (void)interpolate_and_write(t_root, col);
+                            ++col;
+                        }
+                        __syncthreads();
+                        t = t_root;
+                        step_result = 2;
+                    }
+                }
+                if (has_tstop && step_result != 2) {
                     const int r = handle_tstop(tstop);
                     if (r == 1) step_result = 1;
                     else if (r < 0) { status = -r; break; }
                 }
             }
+            if (step_result == 2) break;                           // RootFound ends the solve
             if (!free_running) {
                 while (col < nt && bb.t_eval[col] <= t) {
                     const int e = interpolate_and_write(bb.t_eval[col], col);
@@ -706,6 +771,8 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
             bb.status[inst] = status;
             bb.fin_t[inst] = t; bb.fin_h[inst] = h; bb.fin_order[inst] = order;
             for (int k = 0; k < DSB_NSTATS; ++k) bb.stats[(int64_t)k * B + inst] = st.v[k];
+            if (status == DSB_STATUS_OK) bb.ncols[inst] = col;
+            if (NR > 0) bb.root_idx[inst] = root_found;
         }
     }
 }

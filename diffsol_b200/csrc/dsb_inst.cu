@@ -273,10 +273,8 @@ cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const
     } else if (coop->exec_mode == 3) {
         return cudaErrorNotSupported;
     }
-    // root functions (events) are built into the lane kernels (on-chip and banded), not into the block-per-instance path;
-    // output functions into the banded lane kernels only
-    if (dsb_model_nroots<InstModel>::value > 0 && coop->exec_mode == 2) return cudaErrorNotSupported;
-    if (dsb_model_nout<InstModel>::has_out) return cudaErrorNotSupported;
+    // root functions (events) are built into every kernel family; output functions into the banded lane kernels and the
+    // block-per-instance kernel (the on-chip lane kernels hold n <= 16 states and return them all)
     // reset functions (re-initialisation after an event) are built into the on-chip lane kernels (BDF and SDIRK) only
     if (dsb_model_has_reset<InstModel>::value && coop->exec_mode >= 2) return cudaErrorNotSupported;
     const bool use_coop = coop->exec_mode == 2 || (coop->exec_mode == 0 && !kLaneCapable);
@@ -284,5 +282,6 @@ cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const
         if (method != DSB_METHOD_BDF) return cudaErrorNotSupported;   // cooperative path: BDF only
         return launch_coop_bdf<InstModel>(pa, bb, stream, mid, work_counter, coop, atol_host, launches);
     }
+    if (dsb_model_nout<InstModel>::has_out) return cudaErrorNotSupported;
     return LaneLauncher<InstModel, kLaneCapable>::run(pa, bb, method, stream, mid, work_counter, launches);
 }

@@ -162,9 +162,43 @@ def test_root_index_bit_exact(dsb, oracle, method):
     assert np.array_equal(ys, ys_o, equal_nan=True)
 
 
-def test_roots_not_on_the_block_per_instance_path(dsb):
+@pytest.mark.parametrize("model,B,coloring", [("exp_decay_root", 600, False), ("exp_decay_two_roots", 600, False),
+                                              ("spm_stop", 120, True), ("spm_stop", 60, False), ("spm99_stop", 12, True)])
+def test_roots_and_outputs_on_the_block_per_instance_path(dsb, oracle, model, B, coloring):
+    """The root check of Bdf::step (bdf.rs:1566-1579), the RootFound branch of solve_dense (method.rs:774-805) and
+    dense_write_out with an output function (method.rs:822-848) in the block-per-instance kernel: every thread of the
+    block runs the same scalar root iteration on the shared state.  Bit-identical to the oracle and to the lane kernels."""
+    from diffsol_b200 import sweeps
+    if model.startswith("spm"):
+        p = (0.6 + 0.8 * sweeps.uniform(np.arange(B), 0)).reshape(-1, 1)
+        t_eval = np.arange(1, 121) * 30.0
+    else:
+        idx = np.arange(B)
+        p = np.stack([0.02 * 50.0 ** sweeps.uniform(idx, 0), 0.1 + 1.9 * sweeps.uniform(idx, 1)], axis=1)
+        t_eval = np.arange(1.0, 21.0)
+    prob = dsb.OdeBuilder().rhs_implicit(model).p(p).use_coloring(coloring).build()
+    solver = prob.bdf().set_execution("block")
+    ys = solver.solve_dense(t_eval)
+    root_idx, ncols = solver.root_info()
+    t_fin = solver.final_state()[0]
+    desc = oracle.make_desc(model, powmode=1, use_coloring=coloring)
+    ys_o, stats_o, status_o, t_root_o, root_idx_o, ncols_o = oracle.batch_solve_dense_roots(desc, p, t_eval)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(root_idx, root_idx_o) and np.array_equal(ncols, ncols_o)
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o, equal_nan=True)
+    stopped = root_idx_o >= 0
+    assert stopped.sum() > 0
+    assert np.array_equal(t_fin[stopped], t_root_o[stopped])
+    # and the default kernel family of the model gives the same bits
+    lane = prob.bdf()
+    assert np.array_equal(lane.solve_dense(t_eval), ys, equal_nan=True)
+    assert np.array_equal(lane.statistics_array(), solver.statistics_array())
+
+
+def test_resets_not_on_the_block_per_instance_path(dsb):
     p = sweep(8)
-    prob = dsb.OdeBuilder().rhs_implicit("exp_decay_root").p(p).build()
+    prob = dsb.OdeBuilder().rhs_implicit("exp_decay_reset").p(p).build()
     with pytest.raises(dsb.DiffsolB200Error):
         prob.bdf().set_execution("block").solve_dense([1.0])
 
