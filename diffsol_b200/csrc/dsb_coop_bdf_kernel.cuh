@@ -736,21 +736,68 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                                                                }, t_root, root_found);
                     if (stopped_on_root) {
                         // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root)
-                        // (bdf.rs:1228-1262), then the state at the root in the next column (method.rs:493-503)
+                        // (bdf.rs:1228-1262), then -- without a reset function -- the state at the root in the next column
+                        // (method.rs:493-503) and the end of the solve
                         while (col < nt && bb.t_eval[col] <= t_root) {
                             (void)interpolate_and_write(bb.t_eval[col], col);
                             ++col;
                         }
-                        if (col < nt) {
-                            (void)interpolate_and_write(t_root, col);
-                            ++col;
+                        bool ended = true;
+                        if constexpr (dsb_model_has_reset<M>::value) {
+                            if (!free_running) {
+                                // has_reset (method.rs:783-797): apply_reset (state.rs:246-270: y <- reset(y, t),
+                                // dy <- f(y, t)), a new stop time, then Bdf::step finds the state modified
+                                // (bdf.rs:1291-1318): root finder re-initialised, difference array back to first order,
+                                // _jacobian_updates(c, StepSuccess), set_stop_time again.  Every thread evaluates the
+                                // (small) whole-vector reset and rhs functions on the shared state at the root.
+                                ended = false;
+                                interpolate_to_shared(t_root, yc);
+                                t = t_root;
+                                double yl[N], yr[N], dyr[N];
+                                for (int i = 0; i < N; ++i) yl[i] = yc[i];
+                                M::reset(yl, p, t, yr);
+                                M::rhs(yr, p, t, dyr);
+                                st.v[DSB_STAT_RHS_CALLS] += 1;
+                                __syncthreads();
+                                for (int i = tid; i < N; i += T) { ys[i] = yr[i]; dys[i] = dyr[i]; }
+                                __syncthreads();
+                                root_found = -1;
+                                if (t < bb.t_eval[nt - 1]) {
+                                    step_result = 3;
+                                    has_tstop = true; tstop = bb.t_eval[nt - 1];
+                                    int r = handle_tstop(tstop);                              // method.rs:792
+                                    if (r == 0) {
+                                        M::root(ys, p, t, rf.g0); rf.t0 = t;
+                                        order = 1; n_equal_steps = 0;
+                                        __syncthreads();
+                                        for (int i = tid; i < N; i += T) { Dm[i] = ys[i]; Dm[N + i] = dys[i] * h; }
+                                        __syncthreads();
+                                        c = h * pa.tab.alpha[1];
+                                        jacobian_updates(c, DSB_STEP_SUCCESS);
+                                        has_prev_error = false;
+                                        has_tstop = true;
+                                        r = handle_tstop(tstop);                              // bdf.rs:1314-1316
+                                    }
+                                    if (r == 1) { has_tstop = false; status = DSB_STATUS_STOP_TIME_AT_CURRENT; break; }
+                                    else if (r < 0) { status = -r; break; }
+                                } else {
+                                    step_result = 1;                                          // TstopReached
+                                }
+                            }
                         }
-                        __syncthreads();
-                        t = t_root;
-                        step_result = 2;
+                        if (ended) {
+                            if (col < nt) {
+                                (void)interpolate_and_write(t_root, col);
+                                ++col;
+                            }
+                            __syncthreads();
+                            t = t_root;
+                            step_result = 2;
+                        }
                     }
                 }
-                if (has_tstop && step_result != 2) {
+                if (step_result == 3) step_result = 0;             // a reset was applied: the stop time is set already
+                else if (has_tstop && step_result == 0) {
                     const int r = handle_tstop(tstop);
                     if (r == 1) step_result = 1;
                     else if (r < 0) { status = -r; break; }

@@ -267,6 +267,7 @@ cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const
                                                  cudaStream_t stream, cudaEvent_t mid, unsigned long long* work_counter,
                                                  DsbCoopState* coop, const double* atol_host, int* launches) {
     // exec_mode 3 / automatic: the banded lane kernels where the model qualifies (BDF and (E)SDIRK)
+    static_assert(!(kBandCapable && dsb_model_has_reset<InstModel>::value), "the banded lane kernels do not apply resets");
     if (kBandCapable && (coop->exec_mode == 3 || coop->exec_mode == 0)) {
         const cudaError_t e = BandLauncher<InstModel, kBandCapable>::run(pa, bb, method, stream, mid, work_counter, coop, atol_host, launches);
         if (e != cudaErrorNotSupported || coop->exec_mode == 3) return e;
@@ -275,8 +276,8 @@ cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const
     }
     // root functions (events) are built into every kernel family; output functions into the banded lane kernels and the
     // block-per-instance kernel (the on-chip lane kernels hold n <= 16 states and return them all)
-    // reset functions (re-initialisation after an event) are built into the on-chip lane kernels (BDF and SDIRK) only
-    if (dsb_model_has_reset<InstModel>::value && coop->exec_mode >= 2) return cudaErrorNotSupported;
+    // reset functions (re-initialisation after an event) are built into the on-chip lane kernels (BDF and SDIRK) and the
+    // block-per-instance kernel, not into the banded lane kernels
     const bool use_coop = coop->exec_mode == 2 || (coop->exec_mode == 0 && !kLaneCapable);
     if (use_coop) {
         if (method != DSB_METHOD_BDF) return cudaErrorNotSupported;   // cooperative path: BDF only

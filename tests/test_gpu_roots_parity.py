@@ -116,8 +116,6 @@ def test_reset_bit_exact(dsb, oracle, tol, method):
     assert np.array_equal(root_idx, root_idx_o) and (root_idx == -1).all() and np.array_equal(ncols, ncols_o)
     assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
     assert np.array_equal(ys, ys_o, equal_nan=True)
-    with pytest.raises(dsb.DiffsolB200Error):               # only the on-chip lane kernels apply resets
-        dsb.OdeBuilder().rhs_implicit("exp_decay_reset").p(p[:4]).build().bdf().set_execution("block").solve_dense([1.0])
 
 
 @pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
@@ -196,11 +194,30 @@ def test_roots_and_outputs_on_the_block_per_instance_path(dsb, oracle, model, B,
     assert np.array_equal(lane.statistics_array(), solver.statistics_array())
 
 
-def test_resets_not_on_the_block_per_instance_path(dsb):
-    p = sweep(8)
-    prob = dsb.OdeBuilder().rhs_implicit("exp_decay_reset").p(p).build()
-    with pytest.raises(dsb.DiffsolB200Error):
-        prob.bdf().set_execution("block").solve_dense([1.0])
+@pytest.mark.parametrize("model", ["exp_decay_reset", "ball_bounce"])
+def test_resets_on_the_block_per_instance_path(dsb, oracle, model):
+    """apply_reset + the modified-state branch of Bdf::step (bdf.rs:1291-1318) in the block-per-instance kernel."""
+    from diffsol_b200 import sweeps
+    B = 400
+    idx = np.arange(B)
+    if model == "ball_bounce":
+        p = np.stack([5.0 + 10.0 * sweeps.uniform(idx, 0), 2.0 + 18.0 * sweeps.uniform(idx, 1), 0.8 + 0.15 * sweeps.uniform(idx, 2)], axis=1)
+        t_eval = np.linspace(0.05, 4.0, 80)
+    else:
+        p = np.stack([0.02 * 50.0 ** sweeps.uniform(idx, 0), 0.35 + 1.65 * sweeps.uniform(idx, 1)], axis=1)
+        t_eval = np.arange(1.0, 41.0)
+    prob = dsb.OdeBuilder().rhs_implicit(model).p(p).build()
+    solver = prob.bdf().set_execution("block")
+    ys = solver.solve_dense(t_eval)
+    root_idx, ncols = solver.root_info()
+    desc = oracle.make_desc(model, powmode=1)
+    ys_o, stats_o, status_o, t_root_o, root_idx_o, ncols_o = oracle.batch_solve_dense_roots(desc, p, t_eval)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(root_idx, root_idx_o) and (root_idx == -1).all() and np.array_equal(ncols, ncols_o)
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o, equal_nan=True)
+    with pytest.raises(dsb.DiffsolB200Error):               # SDIRK has no block-per-instance kernel
+        prob.tr_bdf2().set_execution("block").solve_dense([1.0])
 
 
 def test_root_info_without_roots(dsb):
