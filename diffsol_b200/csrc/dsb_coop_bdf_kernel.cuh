@@ -94,7 +94,8 @@ struct CoopBdfLayout {
 #ifndef DSB_COOP_TARGET_THREADS
 #define DSB_COOP_TARGET_THREADS(threads) ((threads) <= 64 ? 1024 : 256)
 #endif
-template <class M>
+// RK = false: Bdf; RK = true: Sdirk (TR-BDF2 / ESDIRK34, the tableau in pa.rk) on the same cooperative pieces
+template <class M, bool RK = false>
 __global__ void __launch_bounds__(CoopBdfLayout<M>::THREADS, DSB_COOP_TARGET_THREADS(CoopBdfLayout<M>::THREADS) / CoopBdfLayout<M>::THREADS)
 dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __grid_constant__ DsbBatchBuffers bb,
                                 const __grid_constant__ DsbCoopWorkspace ws, unsigned long long* __restrict__ work_counter) {
@@ -372,43 +373,28 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
             if (max_d < d1) max_d = d1;
             double h1;
             if (max_d < 1e-15) { h1 = h0 * 1e-3; if (h1 < 1e-6) h1 = 1e-6; }
-            else h1 = dsb_pow(0.01 / max_d, 1.0 / (1.0 + 1.0));        // solver_order = 1 for Bdf
+            else h1 = dsb_pow(0.01 / max_d, 1.0 / (1.0 + (RK ? (double)pa.rk.order : 1.0)));   // solver_order: 1 for Bdf (problem.rs:597-602), the tableau's for Sdirk
             h = 100.0 * h0;
             if (h > h1) h = h1;
             if (is_neg_h) h = -h;
         }
 
-        // ================= Bdf::_new (bdf.rs:230-368) =================
-        int order = 1, n_equal_steps = 0;
-        double c = h * pa.tab.alpha[1], t_predict = t;
-        bool has_tstop = false, has_prev_error = false, jacobian_is_stale = true;
-        double tstop = 0.0, prev_error_norm = 0.0;
-        LaneJacobianUpdate ju; ju.init(1.0);
-        LaneConvergence conv;
-        conv.tol = pa.opt.nonlinear_solver_tolerance; conv.max_iter = pa.opt.max_nonlinear_solver_iterations;
-        conv.eta = pa.tab.eta_reset; conv.old_norm = 0.0; conv.reset();
-
-        // BdfCallable::jacobian_inplace + NalgebraLU::set_linearisation: (re)evaluate J, M when stale; A = M - cJ; LU
-        auto reset_jacobian = [&]() {
+        // results of the instance (thread 0 writes)
+        auto write_results = [&](int status_, double t_, double h_, int order_, int col_, int root_found_) {
             __syncthreads();
-            if (jacobian_is_stale) {
-                eval_jacobian(ys, t);
-                if (M::HAS_MASS) {
-                    for (int j = 0; j < N; ++j) {
-                        __syncthreads();
-                        for (int i = tid; i < N; i += T) tmpv[i] = (i == j) ? 1.0 : 0.0;
-                        __syncthreads();
-                        for (int i = tid; i < N; i += T) Mg[(size_t)j * N + i] = E::mass_i(i, tmpv, p, t, 0.0, 0.0);
-                    }
-                }
-                jacobian_is_stale = false;
-                __syncthreads();
-                coop_band_scan(Jg, M::HAS_MASS ? Mg : nullptr, N, s_band);       // structure only changes when J / M do
+            if (tid == 0) {
+                bb.status[inst] = status_;
+                bb.fin_t[inst] = t_; bb.fin_h[inst] = h_; bb.fin_order[inst] = order_;
+                for (int k = 0; k < DSB_NSTATS; ++k) bb.stats[(int64_t)k * B + inst] = st.v[k];
+                if (status_ == DSB_STATUS_OK) bb.ncols[inst] = col_;
+                if (NR > 0) bb.root_idx[inst] = root_found_;
             }
-            const double mc = -c;
+        };
+        // A = J * mc + M (M - cJ for Bdf, M - c h J for Sdirk) and its LU: in LAPACK band storage in shared memory when the
+        // band of J / M is narrow, else dense in global memory
+        auto assemble_and_factor = [&](double mc) {
             const int kl = s_band[0], ku = s_band[1];
             if (pa.coop_dense_only == 0 && N > 32 && 2 * kl + ku + 1 <= 32) {
-                // banded: build A = M - cJ directly in LAPACK band storage in shared memory, factor there
                 const int kv = kl + ku;
                 double* ab = sc.panel;
                 __syncthreads();
@@ -436,6 +422,384 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                 __syncthreads();
                 lu_factor();
             }
+        };
+        // M at time tt into Mg: column j = M e_j (beta = 0)
+        auto eval_mass = [&](double tt) {
+            for (int j = 0; j < N; ++j) {
+                __syncthreads();
+                for (int i = tid; i < N; i += T) tmpv[i] = (i == j) ? 1.0 : 0.0;
+                __syncthreads();
+                for (int i = tid; i < N; i += T) Mg[(size_t)j * N + i] = E::mass_i(i, tmpv, p, tt, 0.0, 0.0);
+            }
+        };
+
+        if constexpr (RK) {
+        // ================= Rk::_new + Sdirk::_new (runge_kutta.rs:100-190, sdirk.rs:80-160) =================
+        const int ns = pa.rk.s;
+        const double cg = pa.rk.a[1 * ns + 1];                       // the SDIRK diagonal
+        const int start = (pa.rk.a[0] == 0.0) ? 1 : 0;               // explicit first stage (ESDIRK, TR-BDF2)
+        double* const diff = Dm;                                     // diff[j][i] = h k_j at diff[j * N + i], j < 4
+        double* const oy = Dm + 4 * N;                               // old_state.y (last stage value / previous step)
+        double* const phi = Dm + 5 * N;                              // SdirkCallable.phi
+        double* const errv = Dm + 6 * N;                             // embedded error estimate
+        double* const xc = yc;                                       // stage iterate (old_state.dy)
+        double old_t = t, op_h = h;
+        bool has_tstop = false, has_prev_error = false, jacobian_is_stale = true, is_jacobian_set = false;
+        double tstop = 0.0, prev_error_norm = 0.0;
+        LaneJacobianUpdate ju; ju.init(1.0); ju.update_jacobian(h); ju.update_rhs_jacobian(h);
+        LaneConvergence conv;
+        conv.tol = pa.opt.nonlinear_solver_tolerance; conv.max_iter = pa.opt.max_nonlinear_solver_iterations;
+        conv.eta = pa.tab.eta_reset; conv.old_norm = 0.0; conv.reset();
+        LaneRootFinder<(NR > 0 ? NR : 1), DsbDivInline> rf;
+        rf.t0 = t;
+        for (int r = 0; r < (NR > 0 ? NR : 1); ++r) rf.g0[r] = 0.0;
+        int root_found = -1;
+        int col = 0;
+
+        // SdirkCallable::jacobian_inplace (op/sdirk.rs:257-292) + set_linearisation: J at phi + c x with x = state.y (phi is
+        // whatever the last stage left there), M, both when stale; A = M - (c h) J; LU
+        auto reset_jacobian = [&](double tt) {
+            __syncthreads();
+            if (jacobian_is_stale) {
+                for (int i = tid; i < N; i += T) psi[i] = cg * ys[i] + phi[i];
+                __syncthreads();
+                eval_jacobian(psi, tt);
+                if (M::HAS_MASS) eval_mass(tt);
+                jacobian_is_stale = false;
+                __syncthreads();
+                coop_band_scan(Jg, M::HAS_MASS ? Mg : nullptr, N, s_band);
+            }
+            assemble_and_factor(-(cg * op_h));
+            is_jacobian_set = true;
+        };
+        // Sdirk::jacobian_updates (sdirk.rs:256-304)
+        auto jacobian_updates = [&](double hh, int kind) {
+            bool did_update = false;
+            if (ju.check_rhs_jacobian_update(pa.opt, hh, kind)) {
+                jacobian_is_stale = true;
+                reset_jacobian(t);
+                ju.update_rhs_jacobian(hh);
+                ju.update_jacobian(hh);
+                conv.eta = pa.tab.eta_reset;
+                did_update = true;
+            } else if (ju.check_jacobian_update(pa.opt, hh, kind)) {
+                reset_jacobian(t);
+                ju.update_jacobian(hh);
+                conv.eta = pa.tab.eta_reset;
+                did_update = true;
+            }
+            if (did_update) st.record_linear_solver_setup(kind);
+        };
+        // runge_kutta.rs:752-781.  0 = nothing, 1 = TstopReached, < 0 = -status
+        auto handle_tstop = [&](double ts) -> int {
+            const double troundoff = 100.0 * eps * (dsb_abs(t) + dsb_abs(h));
+            if (dsb_abs(t - ts) <= troundoff) return 1;
+            if ((h > 0.0 && ts < t - troundoff) || (h < 0.0 && ts > t + troundoff)) return -DSB_STATUS_STOP_TIME_BEFORE_CURRENT;
+            if ((h > 0.0 && t + h > ts + troundoff) || (h < 0.0 && t + h < ts - troundoff)) {
+                const double f = (ts - t) / h;
+                h *= f;
+            }
+            return 0;
+        };
+        // interpolate_inplace (runge_kutta.rs:1080-1127; :962-981 beta dense output, :1004-1024 Hermite) on [old_t, t]
+        auto interpolate_i = [&](double theta, int i) -> double {
+            if (pa.rk.has_beta) {
+                const double th2 = theta * theta;
+                double yo = oy[i];
+                for (int j = 0; j < ns; ++j) {
+                    double bf = pa.rk.beta[j] * theta;
+                    bf = pa.rk.beta[ns + j] * th2 + bf;
+                    yo = diff[j * N + i] * bf + yo;
+                }
+                return yo;
+            }
+            const double al1 = theta - 1.0, be1 = 1.0 - 2.0 * theta;
+            const double al2 = 1.0 - theta, be2 = theta * (theta - 1.0);
+            const double u0 = oy[i], u1 = ys[i];
+            double v = u1;
+            v -= u0;
+            v = al1 * diff[i] + be1 * v;
+            v = theta * diff[(ns - 1) * N + i] + v;
+            v = al2 * u0 + be2 * v;
+            v = theta * u1 + v;
+            return v;
+        };
+        auto interpolate_to_shared = [&](double tq, double* dst) {
+            const double dt = t - old_t;
+            const double theta = (dt == 0.0) ? 1.0 : (tq - old_t) / dt;
+            __syncthreads();
+            for (int i = tid; i < N; i += T) dst[i] = interpolate_i(theta, i);
+            __syncthreads();
+        };
+        auto interpolate_and_write = [&](double tq, int column) -> int {
+            const bool is_forward = h > 0.0;
+            if ((is_forward && (tq > t || tq < old_t)) || (!is_forward && (tq < t || tq > old_t)))
+                return DSB_STATUS_INTERPOLATION_TIME_AFTER_CURRENT;
+            if constexpr (HAS_OUT) {
+                interpolate_to_shared(tq, tmpv);
+                if (tid == 0) {
+                    double o[NOUT];
+                    M::out(tmpv, p, tq, o);
+                    for (int k = 0; k < NOUT; ++k) bb.ys[((int64_t)column * NOUT + k) * B + inst] = o[k];
+                }
+                return DSB_STATUS_OK;
+            }
+            const double dt = t - old_t;
+            const double theta = (dt == 0.0) ? 1.0 : (tq - old_t) / dt;
+            __syncthreads();
+            for (int i = tid; i < N; i += T) bb.ys[((int64_t)column * N + i) * B + inst] = interpolate_i(theta, i);
+            return DSB_STATUS_OK;
+        };
+
+        if (status == DSB_STATUS_OK) {
+            if (ws.color != nullptr) {                     // consistent initialisation used Jg as scratch
+                __syncthreads();
+                for (int e = tid; e < N * N; e += T) Jg[e] = 0.0;
+                __syncthreads();
+            }
+            for (int i = tid; i < N; i += T) {
+                for (int j = 0; j < DSB_NDIFF; ++j) Dm[j * N + i] = 0.0;
+                oy[i] = ys[i];
+            }
+            __syncthreads();
+            if constexpr (NR > 0) { M::root(ys, p, t, rf.g0); rf.t0 = t; }      // Rk::_new: root_finder.init(root_fn, y, t)
+            if (!free_running) {
+                has_tstop = true; tstop = bb.t_eval[nt - 1];
+                const int r = handle_tstop(tstop);
+                if (r == 1) { has_tstop = false; status = DSB_STATUS_STOP_TIME_AT_CURRENT; }
+                else if (r < 0) status = -r;
+            }
+        }
+
+        // ================= solve_dense loop (method.rs:721-818) around Sdirk::step (sdirk.rs:409-543) =================
+        while (status == DSB_STATUS_OK && col < nt) {
+            if (free_running) {
+                while (col < nt && !(dsb_abs(t) < dsb_abs(bb.t_eval[col]))) {
+                    const int e = interpolate_and_write(bb.t_eval[col], col);
+                    if (e) { status = e; break; }
+                    ++col;
+                }
+                if (col >= nt || status != DSB_STATUS_OK) break;
+            }
+            int step_result = 0;                                    // 0 internal, 1 tstop reached, 2 root found
+            {
+                double hs = h;                                      // rk.start_step()
+                if (dsb_abs(hs) < pa.opt.min_timestep) { status = DSB_STATUS_STEP_SIZE_TOO_SMALL; break; }
+                op_h = hs;
+                int nattempts = 0;
+                bool updated_jacobian = false;
+                double factor = 1.0, error_norm = 0.0;
+                while (true) {
+                    if (start == 1) {                               // start_step_attempt (runge_kutta.rs:505-535)
+                        __syncthreads();
+                        for (int k = tid; k < N; k += T) diff[k] = hs * dys[k];
+                        __syncthreads();
+                    }
+                    bool failed = false;
+                    for (int i = start; i < ns; ++i) {
+                        // Rk::do_stage_sdirk (runge_kutta.rs:631-750): set_phi, predict_stage_sdirk, Newton on
+                        // F(x) = M x - h f(phi + c x)
+                        const double t_stage = t + pa.rk.c[i] * hs;
+                        double al = 0.0, be = 0.0;
+                        if (i >= 2) {
+                            const double cc = (pa.rk.c[i] - pa.rk.c[i - 2]) / (pa.rk.c[i - 1] - pa.rk.c[i - 2]);
+                            al = -cc; be = 1.0 + cc;
+                        }
+                        __syncthreads();
+                        for (int k = tid; k < N; k += T) {
+                            double ph = ys[k];
+                            for (int j = 0; j < i; ++j) ph = diff[j * N + k] * pa.rk.a[j * ns + i] + ph;
+                            phi[k] = ph;
+                            if (i == 0) xc[k] = hs * dys[k];
+                            else if (i == 1) xc[k] = diff[k];
+                            else xc[k] = al * diff[(i - 2) * N + k] + be * diff[(i - 1) * N + k];
+                        }
+                        __syncthreads();
+                        if (!is_jacobian_set) {                     // the lazy first reset_jacobian (runge_kutta.rs:661-665)
+                            reset_jacobian(t_stage);
+                            st.record_linear_solver_setup(DSB_CHECKPOINT);
+                        }
+                        bool ok = false;
+                        conv.reset();
+                        for (int it = 0; it < conv.max_iter; ++it) {
+                            __syncthreads();
+                            for (int k = tid; k < N; k += T) tmpv[k] = cg * xc[k] + phi[k];
+                            __syncthreads();
+                            for (int k = tid; k < N; k += T) dlt[k] = E::rhs_i(k, tmpv, p, t_stage);
+                            st.v[DSB_STAT_RHS_CALLS] += 1;
+                            __syncthreads();
+                            const double beta = -op_h;
+                            for (int k = tid; k < N; k += T)
+                                dlt[k] = M::HAS_MASS ? E::mass_i(k, xc, p, t_stage, beta, dlt[k]) : (xc[k] + beta * dlt[k]);
+                            __syncthreads();
+                            if (!lu_solve(dlt)) break;
+                            for (int k = tid; k < N; k += T) xc[k] -= dlt[k];
+                            const double norm = dsb_sqrt(squared_norm(dlt, ys));
+                            const int sres = conv.check_new_iteration(norm);
+                            if (sres == LANE_CONVERGED) { ok = true; break; }
+                            if (sres == LANE_DIVERGED) break;
+                        }
+                        st.v[DSB_STAT_NONLINEAR_SOLVER_ITERATIONS] += conv.niter;
+                        if (!ok) { failed = true; break; }
+                        __syncthreads();
+                        for (int k = tid; k < N; k += T) {
+                            oy[k] = cg * xc[k] + phi[k];            // get_f_eval: the stage value
+                            diff[i * N + k] = xc[k];
+                        }
+                        __syncthreads();
+                    }
+                    if (failed) {                                   // sdirk.rs:436-472
+                        if (!updated_jacobian) {
+                            updated_jacobian = true;
+                            jacobian_updates(hs, DSB_FIRST_CONVERGENCE_FAIL);
+                        } else {
+                            hs *= 0.3;
+                            conv.eta = pa.tab.eta_reset_timestep;
+                            op_h = hs;
+                            jacobian_updates(hs, DSB_SECOND_CONVERGENCE_FAIL);
+                        }
+                        has_prev_error = false;
+                        st.v[DSB_STAT_NONLINEAR_SOLVER_FAILS] += 1;
+                        if (st.v[DSB_STAT_NONLINEAR_SOLVER_FAILS] > pa.opt.max_nonlinear_solver_failures) { status = DSB_STATUS_TOO_MANY_NONLINEAR_FAILURES; break; }
+                        if (dsb_abs(hs) < pa.opt.min_timestep) { status = DSB_STATUS_STEP_SIZE_TOO_SMALL; break; }
+                        continue;
+                    }
+                    // rk.error_norm (runge_kutta.rs:783-800): error = diff . d ; [error = M error] ; error = LU^-1 error
+                    __syncthreads();
+                    for (int k = tid; k < N; k += T) {
+                        double e = diff[k] * pa.rk.d[0];
+                        for (int j = 1; j < ns; ++j) e = diff[j * N + k] * pa.rk.d[j] + e;
+                        errv[k] = e;
+                    }
+                    __syncthreads();
+                    double* ev = errv;
+                    if (M::HAS_MASS) {
+                        for (int k = tid; k < N; k += T) {
+                            double e = Mg[k] * errv[0];
+                            for (int j = 1; j < N; ++j) e = Mg[(size_t)j * N + k] * errv[j] + e;
+                            dlt[k] = e;
+                        }
+                        __syncthreads();
+                        ev = dlt;
+                    }
+                    if (!lu_solve(ev)) { status = DSB_STATUS_LU_SOLVE_FAILED; break; }
+                    {
+                        const double e = squared_norm(ev, ys);
+                        error_norm = (0.0 < e) ? e : 0.0;
+                    }
+                    {   // Rk::factor (runge_kutta.rs:466-495) + pi_controller_raw (:1313-1335)
+                        const double maxiter = (double)conv.max_iter;
+                        const double niter = (double)conv.niter;
+                        const double safety = 0.9 * ((2.0 * maxiter + 1.0) / (2.0 * maxiter + niter));
+                        const double order_f = (double)(pa.rk.order + 1);
+                        const double ki = pa.opt.pi_control_integral / order_f;
+                        double raw;
+                        if (pa.opt.pi_control_proportional == 0.0 || !has_prev_error) raw = dsb_pow(error_norm, -ki);
+                        else {
+                            const double kp = pa.opt.pi_control_proportional / order_f;
+                            raw = dsb_pow(error_norm, -(ki + kp)) * dsb_pow(prev_error_norm, kp);
+                        }
+                        double f = safety * raw;
+                        if (f > pa.opt.max_timestep_shrink && f < pa.opt.min_timestep_growth) f = 1.0;
+                        if (f < pa.opt.min_timestep_shrink) f = pa.opt.min_timestep_shrink;
+                        if (f > pa.opt.max_timestep_growth) f = pa.opt.max_timestep_growth;
+                        factor = f;
+                    }
+                    if (error_norm < 1.0) break;
+                    hs *= factor;
+                    conv.eta = pa.tab.eta_reset_timestep;
+                    op_h = hs;
+                    jacobian_updates(hs, DSB_ERROR_TEST_FAIL);
+                    nattempts += 1;
+                    has_prev_error = false;
+                    st.v[DSB_STAT_ERROR_TEST_FAILURES] += 1;
+                    if (nattempts >= pa.opt.max_error_test_failures) { status = DSB_STATUS_TOO_MANY_ERROR_TEST_FAILURES; break; }
+                    if (dsb_abs(hs) < pa.opt.min_timestep) { status = DSB_STATUS_STEP_SIZE_TOO_SMALL; break; }
+                }
+                if (status != DSB_STATUS_OK) break;
+                // accepted (sdirk.rs:531-542) + Rk::step_accepted (runge_kutta.rs:894-960)
+                const double new_h = hs * factor;
+                if (factor != 1.0) conv.eta = pa.tab.eta_reset_timestep;
+                op_h = new_h;
+                jacobian_updates(new_h, DSB_STEP_SUCCESS);
+                ju.step();
+                has_prev_error = true; prev_error_norm = error_norm;
+                const double inv_h = 1.0 / hs;
+                __syncthreads();
+                for (int k = tid; k < N; k += T) {
+                    const double y_new = oy[k];                     // old_state.y held the last stage value
+                    oy[k] = ys[k];                                  // swap: old_state <- previous state
+                    ys[k] = y_new;
+                    dys[k] = xc[k] * inv_h;                         // old_state.dy *= 1/h, then swapped in
+                }
+                __syncthreads();
+                old_t = t;
+                t = t + hs;
+                h = new_h;
+                st.v[DSB_STAT_STEPS] += 1;
+                if constexpr (NR > 0) {
+                    // check for a root within the accepted step (runge_kutta.rs:935-948), before the stop time is handled
+                    double t_root = t;
+                    const bool stopped_on_root = rf.check_root(t, [&](double (&gv)[NR]) { M::root(ys, p, t, gv); },
+                                                               [&](double t_mid, double (&gv)[NR]) {
+                                                                   interpolate_to_shared(t_mid, yp);
+                                                                   M::root(yp, p, t_mid, gv);
+                                                               }, t_root, root_found);
+                    if (stopped_on_root) {
+                        // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root),
+                        // then the state at the root in the next column (method.rs:493-503)
+                        while (col < nt && bb.t_eval[col] <= t_root) {
+                            (void)interpolate_and_write(bb.t_eval[col], col);
+                            ++col;
+                        }
+                        if (col < nt) {
+                            (void)interpolate_and_write(t_root, col);
+                            ++col;
+                        }
+                        __syncthreads();
+                        t = t_root;
+                        step_result = 2;
+                    }
+                }
+                if (has_tstop && step_result == 0) {
+                    const int r = handle_tstop(tstop);
+                    if (r == 1) { step_result = 1; has_tstop = false; }
+                    else if (r < 0) { status = -r; break; }
+                }
+            }
+            if (step_result == 2) break;                           // RootFound ends the solve
+            if (!free_running) {
+                while (col < nt && bb.t_eval[col] <= t) {
+                    const int e = interpolate_and_write(bb.t_eval[col], col);
+                    if (e) { status = e; break; }
+                    ++col;
+                }
+                if (step_result == 1) break;
+            }
+        }
+        write_results(status, t, h, pa.rk.order, col, root_found);
+        } else {
+        // ================= Bdf::_new (bdf.rs:230-368) =================
+        int order = 1, n_equal_steps = 0;
+        double c = h * pa.tab.alpha[1], t_predict = t;
+        bool has_tstop = false, has_prev_error = false, jacobian_is_stale = true;
+        double tstop = 0.0, prev_error_norm = 0.0;
+        LaneJacobianUpdate ju; ju.init(1.0);
+        LaneConvergence conv;
+        conv.tol = pa.opt.nonlinear_solver_tolerance; conv.max_iter = pa.opt.max_nonlinear_solver_iterations;
+        conv.eta = pa.tab.eta_reset; conv.old_norm = 0.0; conv.reset();
+
+        // BdfCallable::jacobian_inplace + NalgebraLU::set_linearisation: (re)evaluate J, M when stale; A = M - cJ; LU
+        auto reset_jacobian = [&]() {
+            __syncthreads();
+            if (jacobian_is_stale) {
+                eval_jacobian(ys, t);
+                if (M::HAS_MASS) eval_mass(t);
+                jacobian_is_stale = false;
+                __syncthreads();
+                coop_band_scan(Jg, M::HAS_MASS ? Mg : nullptr, N, s_band);       // structure only changes when J / M do
+            }
+            assemble_and_factor(-c);
         };
         auto jacobian_updates = [&](double cc, int kind) {
             bool did_update = false;
@@ -813,13 +1177,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                 if (step_result == 1) break;
             }
         }
-        __syncthreads();
-        if (tid == 0) {
-            bb.status[inst] = status;
-            bb.fin_t[inst] = t; bb.fin_h[inst] = h; bb.fin_order[inst] = order;
-            for (int k = 0; k < DSB_NSTATS; ++k) bb.stats[(int64_t)k * B + inst] = st.v[k];
-            if (status == DSB_STATUS_OK) bb.ncols[inst] = col;
-            if (NR > 0) bb.root_idx[inst] = root_found;
+        write_results(status, t, h, order, col, root_found);
         }
     }
 }

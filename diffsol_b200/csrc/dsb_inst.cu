@@ -28,18 +28,21 @@ constexpr bool kLaneCapable = InstModel::N <= 16;
 template <class M>
 static cudaError_t launch_coop_bdf(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, cudaStream_t stream,
                                    cudaEvent_t mid, unsigned long long* work_counter, DsbCoopState* coop,
-                                   const double* atol_host, int* launches) {
+                                   const double* atol_host, int* launches, bool rk) {
     constexpr int N = M::N;
+    // one kernel, two instantiations: Bdf, or Sdirk with the tableau of pa->rk (TR-BDF2 / ESDIRK34)
+    void (*const kern)(const DsbProblemArgs, const DsbBatchBuffers, const DsbCoopWorkspace, unsigned long long*) =
+        rk ? dsb_coop_bdf_solve_dense_kernel<M, true> : dsb_coop_bdf_solve_dense_kernel<M, false>;
     const int threads = CoopBdfLayout<M>::THREADS;
     const size_t smem = CoopBdfLayout<M>::smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(dsb_coop_bdf_solve_dense_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(dsb_coop_bdf_solve_dense_kernel<M>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dsb_coop_bdf_solve_dense_kernel<M>, threads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     const int64_t resident = (int64_t)sms * per_sm;
@@ -95,7 +98,7 @@ static cudaError_t launch_coop_bdf(const DsbProblemArgs* pa, const DsbBatchBuffe
     e = cudaMemsetAsync(work_counter, 0, 32 * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     if (mid) cudaEventRecord(mid, stream);
-    dsb_coop_bdf_solve_dense_kernel<M><<<grid, threads, smem, stream>>>(*pa, *bb, ws, work_counter);
+    kern<<<grid, threads, smem, stream>>>(*pa, *bb, ws, work_counter);
     *launches += 1;
     return cudaGetLastError();
 }
@@ -280,8 +283,9 @@ cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const
     // block-per-instance kernel, not into the banded lane kernels
     const bool use_coop = coop->exec_mode == 2 || (coop->exec_mode == 0 && !kLaneCapable);
     if (use_coop) {
-        if (method != DSB_METHOD_BDF) return cudaErrorNotSupported;   // cooperative path: BDF only
-        return launch_coop_bdf<InstModel>(pa, bb, stream, mid, work_counter, coop, atol_host, launches);
+        // block-per-instance kernel: Bdf, or Sdirk (TR-BDF2 / ESDIRK34); resets in its Bdf form only
+        if (method != DSB_METHOD_BDF && dsb_model_has_reset<InstModel>::value) return cudaErrorNotSupported;
+        return launch_coop_bdf<InstModel>(pa, bb, stream, mid, work_counter, coop, atol_host, launches, method != DSB_METHOD_BDF);
     }
     if (dsb_model_nout<InstModel>::has_out) return cudaErrorNotSupported;
     return LaneLauncher<InstModel, kLaneCapable>::run(pa, bb, method, stream, mid, work_counter, launches);

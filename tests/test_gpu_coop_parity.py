@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 with open(os.path.join(HERE, "golden", "reference_snapshots.json")) as f:
     GOLD = json.load(f)
 BDF_CASES = [c for c in GOLD["cases"] if c["method"] == "bdf" and not c["coloring"]]
+SDIRK_CASES = [c for c in GOLD["cases"] if c["method"] != "bdf"]
 
 
 @pytest.fixture(scope="module")
@@ -48,6 +49,70 @@ def test_reference_snapshots_block_per_instance(dsb, oracle, case):
     assert rc == 0
     for k in range(nb):
         assert np.array_equal(ys[k], ys_o), case["name"]
+
+
+@pytest.mark.parametrize("case", SDIRK_CASES, ids=[c["name"] for c in SDIRK_CASES])
+def test_reference_sdirk_snapshots_block_per_instance(dsb, oracle, case):
+    """The six sdirk.rs statistics snapshots (TR-BDF2 / ESDIRK34; exponential decay, its DAE form, Robertson DAE and ODE)
+    through the Sdirk form of the block-per-instance kernel: all 13 integers, and the states bitwise vs the oracle."""
+    from test_oracle_golden import expected_stats, solution_points
+    t, ystar = solution_points(case["points"])
+    nb = 3
+    b = dsb.OdeBuilder().rhs_implicit(case["model"]).rtol(case["rtol"]).atol(case["atol"]).nbatch(nb)
+    if len(case["p"]):
+        b = b.p(case["p"])
+    solver = getattr(b.build(), case["method"])().set_execution("block")
+    ys = solver.step_and_interpolate(t)
+    assert (solver.status() == 0).all()
+    for k in range(nb):
+        assert solver.get_statistics(k) == expected_stats(case), case["cite"]
+    desc = oracle.make_desc(case["model"], method=case["method"], rtol=case["rtol"], atol=case["atol"], powmode=1)
+    rc, ys_o, stats_o, fin = oracle.harness(desc, case["p"], t)
+    assert rc == 0
+    for k in range(nb):
+        assert np.array_equal(ys[k], ys_o), case["name"]
+
+
+@pytest.mark.parametrize("method", ["tr_bdf2", "esdirk34"])
+@pytest.mark.parametrize("model,B,coloring", [("robertson_dae", 300, False), ("van_der_pol_scaled", 300, False),
+                                              ("heat1d_dae_32", 48, False), ("heat1d_dae_32", 48, True),
+                                              ("heat1d_dae_256", 6, True), ("spm", 60, True), ("spm_stop", 60, True),
+                                              ("exp_decay_two_roots", 300, False)])
+def test_sdirk_block_per_instance_bit_exact(dsb, oracle, method, model, B, coloring):
+    """Sdirk::step (sdirk.rs:409-543) on the block-per-instance kernel: dense and banded LU, ODEs and singular-mass DAEs,
+    coloured and dense Jacobians, output and root functions -- bitwise vs the oracle, and vs the kernel family the model
+    runs on by default (lane or banded lane kernels) where SDIRK exists there."""
+    from diffsol_b200 import sweeps
+    idx = np.arange(B)
+    kw = {}
+    if model == "robertson_dae":
+        p, t_eval, kw = sweeps.robertson_sweep(idx), sweeps.ROBERTSON_T_EVAL, dict(sweeps.ROBERTSON_DAE_TOL)
+    elif model == "van_der_pol_scaled":
+        p, t_eval, kw = sweeps.van_der_pol_scaled_sweep(idx), sweeps.VAN_DER_POL_T_EVAL, dict(sweeps.VAN_DER_POL_TOL)
+    elif model.startswith("heat1d"):
+        p, t_eval = heat_params(idx), HEAT_T_EVAL[9::10]
+    elif model.startswith("spm"):
+        p, t_eval = (0.6 + 0.8 * sweeps.uniform(idx, 0)).reshape(-1, 1), np.arange(1, 41) * 90.0
+    else:
+        p, t_eval = np.stack([0.02 * 50.0 ** sweeps.uniform(idx, 0), 0.1 + 1.9 * sweeps.uniform(idx, 1)], axis=1), np.arange(1.0, 21.0)
+    b = dsb.OdeBuilder().rhs_implicit(model).p(p).use_coloring(coloring)
+    if kw:
+        b = b.rtol(kw["rtol"]).atol(kw["atol"])
+    prob = b.build()
+    solver = getattr(prob, method)().set_execution("block")
+    ys = solver.solve_dense(t_eval)
+    desc = oracle.make_desc(model, method=method, powmode=1, use_coloring=coloring, **kw)
+    ys_o, stats_o, status_o, t_root_o, root_idx_o, ncols_o = oracle.batch_solve_dense_roots(desc, p, t_eval)
+    assert np.array_equal(solver.status(), status_o)
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    ok = status_o == 0
+    assert ok.sum() > 0
+    assert np.array_equal(ys[ok], ys_o[ok], equal_nan=True)
+    root_idx, ncols = solver.root_info()
+    assert np.array_equal(root_idx[ok], root_idx_o[ok]) and np.array_equal(ncols[ok], ncols_o[ok])
+    other = getattr(prob, method)()
+    assert np.array_equal(other.solve_dense(t_eval)[ok], ys[ok], equal_nan=True)
+    assert np.array_equal(other.statistics_array(), solver.statistics_array())
 
 
 @pytest.mark.parametrize("model,tol", [("robertson_ode", "ROBERTSON_ODE_TOL"), ("robertson_dae", "ROBERTSON_DAE_TOL")])
@@ -88,8 +153,6 @@ def test_heat_dae_sweep_bit_exact(dsb, oracle, model, B):
 def test_unsupported_combinations_fail_loudly(dsb):
     p = heat_params(np.arange(2))
     prob = dsb.OdeBuilder().rhs_implicit("heat1d_dae_32").p(p).build()
-    with pytest.raises(dsb.DiffsolB200Error):
-        prob.tr_bdf2().set_execution("block").solve_dense([0.5])           # SDIRK has no block-per-instance kernel
     with pytest.raises(dsb.DiffsolB200Error):
         prob.bdf().set_execution("lane").solve_dense([0.5])
 

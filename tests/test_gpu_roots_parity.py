@@ -216,7 +216,7 @@ def test_resets_on_the_block_per_instance_path(dsb, oracle, model):
     assert np.array_equal(root_idx, root_idx_o) and (root_idx == -1).all() and np.array_equal(ncols, ncols_o)
     assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
     assert np.array_equal(ys, ys_o, equal_nan=True)
-    with pytest.raises(dsb.DiffsolB200Error):               # SDIRK has no block-per-instance kernel
+    with pytest.raises(dsb.DiffsolB200Error):               # resets on the block-per-instance kernel: its Bdf form only
         prob.tr_bdf2().set_execution("block").solve_dense([1.0])
 
 
