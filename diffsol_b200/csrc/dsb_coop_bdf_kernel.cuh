@@ -752,16 +752,52 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                             (void)interpolate_and_write(bb.t_eval[col], col);
                             ++col;
                         }
-                        if (col < nt) {
-                            (void)interpolate_and_write(t_root, col);
-                            ++col;
+                        bool ended = true;
+                        if constexpr (dsb_model_has_reset<M>::value) {
+                            if (!free_running) {
+                                // has_reset (method.rs:783-797): apply_reset (sdirk.rs:368-374 -> state.rs:279-306), a new
+                                // stop time, then Rk::start_step (runge_kutta.rs:446-464) finds the state mutated:
+                                // root finder re-initialised, stop time set again; step size, Jacobian and LU stay
+                                ended = false;
+                                interpolate_to_shared(t_root, yp);
+                                t = t_root;
+                                double yl[N], yr[N], dyr[N];
+                                for (int i = 0; i < N; ++i) yl[i] = yp[i];
+                                M::reset(yl, p, t, yr);
+                                M::rhs(yr, p, t, dyr);
+                                st.v[DSB_STAT_RHS_CALLS] += 1;
+                                __syncthreads();
+                                for (int i = tid; i < N; i += T) { ys[i] = yr[i]; dys[i] = dyr[i]; }
+                                __syncthreads();
+                                root_found = -1;
+                                if (t < bb.t_eval[nt - 1]) {
+                                    step_result = 3;
+                                    has_tstop = true; tstop = bb.t_eval[nt - 1];
+                                    int r = handle_tstop(tstop);                              // method.rs:792
+                                    if (r == 0) {
+                                        M::root(ys, p, t, rf.g0); rf.t0 = t;
+                                        r = handle_tstop(tstop);                              // start_step: set_stop_time(tstop)
+                                    }
+                                    if (r == 1) { has_tstop = false; status = DSB_STATUS_STOP_TIME_AT_CURRENT; break; }
+                                    else if (r < 0) { status = -r; break; }
+                                } else {
+                                    step_result = 1;                                          // TstopReached
+                                }
+                            }
                         }
-                        __syncthreads();
-                        t = t_root;
-                        step_result = 2;
+                        if (ended) {
+                            if (col < nt) {
+                                (void)interpolate_and_write(t_root, col);
+                                ++col;
+                            }
+                            __syncthreads();
+                            t = t_root;
+                            step_result = 2;
+                        }
                     }
                 }
-                if (has_tstop && step_result == 0) {
+                if (step_result == 3) step_result = 0;             // a reset was applied: the stop time is set already
+                else if (has_tstop && step_result == 0) {
                     const int r = handle_tstop(tstop);
                     if (r == 1) { step_result = 1; has_tstop = false; }
                     else if (r < 0) { status = -r; break; }

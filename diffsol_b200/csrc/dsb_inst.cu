@@ -283,8 +283,7 @@ cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const
     // block-per-instance kernel, not into the banded lane kernels
     const bool use_coop = coop->exec_mode == 2 || (coop->exec_mode == 0 && !kLaneCapable);
     if (use_coop) {
-        // block-per-instance kernel: Bdf, or Sdirk (TR-BDF2 / ESDIRK34); resets in its Bdf form only
-        if (method != DSB_METHOD_BDF && dsb_model_has_reset<InstModel>::value) return cudaErrorNotSupported;
+        // block-per-instance kernel: Bdf, or Sdirk (TR-BDF2 / ESDIRK34)
         return launch_coop_bdf<InstModel>(pa, bb, stream, mid, work_counter, coop, atol_host, launches, method != DSB_METHOD_BDF);
     }
     if (dsb_model_nout<InstModel>::has_out) return cudaErrorNotSupported;

@@ -194,9 +194,11 @@ def test_roots_and_outputs_on_the_block_per_instance_path(dsb, oracle, model, B,
     assert np.array_equal(lane.statistics_array(), solver.statistics_array())
 
 
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
 @pytest.mark.parametrize("model", ["exp_decay_reset", "ball_bounce"])
-def test_resets_on_the_block_per_instance_path(dsb, oracle, model):
-    """apply_reset + the modified-state branch of Bdf::step (bdf.rs:1291-1318) in the block-per-instance kernel."""
+def test_resets_on_the_block_per_instance_path(dsb, oracle, model, method):
+    """apply_reset + the modified-state branch of Bdf::step (bdf.rs:1291-1318) / Rk::start_step (runge_kutta.rs:446-464)
+    in the block-per-instance kernel."""
     from diffsol_b200 import sweeps
     B = 400
     idx = np.arange(B)
@@ -207,17 +209,15 @@ def test_resets_on_the_block_per_instance_path(dsb, oracle, model):
         p = np.stack([0.02 * 50.0 ** sweeps.uniform(idx, 0), 0.35 + 1.65 * sweeps.uniform(idx, 1)], axis=1)
         t_eval = np.arange(1.0, 41.0)
     prob = dsb.OdeBuilder().rhs_implicit(model).p(p).build()
-    solver = prob.bdf().set_execution("block")
+    solver = getattr(prob, method)().set_execution("block")
     ys = solver.solve_dense(t_eval)
     root_idx, ncols = solver.root_info()
-    desc = oracle.make_desc(model, powmode=1)
+    desc = oracle.make_desc(model, method=method, powmode=1)
     ys_o, stats_o, status_o, t_root_o, root_idx_o, ncols_o = oracle.batch_solve_dense_roots(desc, p, t_eval)
     assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
     assert np.array_equal(root_idx, root_idx_o) and (root_idx == -1).all() and np.array_equal(ncols, ncols_o)
     assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
     assert np.array_equal(ys, ys_o, equal_nan=True)
-    with pytest.raises(dsb.DiffsolB200Error):               # resets on the block-per-instance kernel: its Bdf form only
-        prob.tr_bdf2().set_execution("block").solve_dense([1.0])
 
 
 def test_root_info_without_roots(dsb):
