@@ -257,6 +257,12 @@ struct Method {
     virtual int state_mut_back(double) { return ST_BAD_ARG; }
     // OdeSolverMethod::apply_reset (method.rs:175-181 -> state.rs:246-270): y <- reset(y, t), dy <- f(y, t)
     virtual int apply_reset() { return ST_BAD_ARG; }
+    // Test hook for the reference's residual-operator tests (op/bdf.rs:317-360 test_bdf_callable, op/sdirk.rs:338-388
+    // test_sdirk_callable): set the callable's scalars (Bdf: c; Sdirk: c and h) and its vector (Bdf: psi - y0; Sdirk:
+    // phi) directly, then evaluate F(x) and the iteration matrix A (n x n col-major) with the SAME member functions
+    // step() uses
+    virtual int residual_known_answer(double /*c*/, double /*h*/, const double* /*vec*/, const double* /*x*/, double /*t*/,
+                                      double* /*F*/, double* /*A*/) { return ST_BAD_ARG; }
 };
 
 Method* new_bdf(const Problem& pr, int* err);

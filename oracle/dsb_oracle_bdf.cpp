@@ -421,6 +421,16 @@ struct Bdf : Method {
         return ST_OK;
     }
 
+    int residual_known_answer(double cc, double, const double* vec, const double* x, double t, double* F, double* Aout) override {
+        c = cc;                                                     // set_c_direct
+        for (int i = 0; i < n; ++i) psi_neg_y0[i] = vec[i];         // set_psi_neg_y0_direct
+        callable(x, t, F);
+        jacobian_is_stale = true;
+        reset_jacobian(x, t);
+        for (size_t q = 0; q < (size_t)n * n; ++q) Aout[q] = A[q];
+        return ST_OK;
+    }
+
     double t() const override { return t_; }
     double h() const override { return h_; }
     int cur_order() const override { return order; }

@@ -180,6 +180,18 @@ int orc_harness_tstop(const orc_problem_desc* d, const double* p, int np, const 
     return err;
 }
 
+// The reference's residual-operator unit tests (op/bdf.rs:317-360, op/sdirk.rs:338-388): F(x) and the iteration matrix of
+// the method's callable with its scalars and vector set directly.  F is n, A is n x n column-major.
+int orc_residual_known_answer(const orc_problem_desc* d, const double* p, int np, double c, double h, const double* vec,
+                              const double* x, double t, double* F, double* A) {
+    Problem pr;
+    int err = build_problem(d, p, np, &pr);
+    if (err) return err;
+    std::unique_ptr<Method> m(make_method(pr, d->method, &err));
+    if (!m) return err;
+    return m->residual_known_answer(c, h, vec, x, t, F, A);
+}
+
 // The driver loop of the reference's test_ball_bounce (ode_solver/mod.rs:1024-1080): set_stop_time(tstop), step until the
 // first root, put the solver's state at the root and apply the model's reset function (the test's hand-written update
 // v <- -e v, x <- max(x, eps), dy[0] <- v), then take up to nsteps further steps and record (t, y) after each; a step

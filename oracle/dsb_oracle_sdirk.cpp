@@ -416,6 +416,16 @@ struct Sdirk : Method {
         return ST_OK;
     }
 
+    int residual_known_answer(double cc, double hh, const double* vec, const double* x, double t, double* F, double* Aout) override {
+        c = cc; op_h = hh;                                          // SdirkCallable::new(eqn, c); set_h(h)
+        for (int i = 0; i < n; ++i) phi[i] = vec[i];                // set_phi_direct
+        callable(x, t, F);
+        jacobian_is_stale = true;
+        reset_jacobian(x, t);
+        for (size_t q = 0; q < (size_t)n * n; ++q) Aout[q] = A[q];
+        return ST_OK;
+    }
+
     double t() const override { return t_; }
     double h() const override { return h_; }
     int cur_order() const override { return tab.order; }

@@ -209,6 +209,23 @@ def harness(desc, p, t_points, use_tstop=False):
     return _run(lib().orc_harness_tstop if use_tstop else lib().orc_harness, desc, p, t_points)
 
 
+def residual_known_answer(desc, p, c, h, vec, x, t=0.0):
+    """BdfCallable / SdirkCallable with c, (h) and psi - y0 / phi set directly -> (rc, F(x)[n], A[n, n])."""
+    n, np_, _ = _dims_by_id(desc.model_id)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    vec = np.ascontiguousarray(vec, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    F = np.zeros(n)
+    A = np.zeros((n, n))
+    L = lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.orc_residual_known_answer.restype = ctypes.c_int
+    L.orc_residual_known_answer.argtypes = [ctypes.POINTER(ProblemDesc), dp, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                            dp, dp, ctypes.c_double, dp, dp]
+    rc = L.orc_residual_known_answer(ctypes.byref(desc), _dp(p), int(p.size), c, h, _dp(vec), _dp(x), t, _dp(F), _dp(A))
+    return rc, F, A.T.copy()          # A comes back column-major
+
+
 def steps_after_first_root(desc, p, tstop, nsteps):
     """The reference's test_ball_bounce loop (ode_solver/mod.rs:1024-1080) -> (rc, t[k], y[k, n]) for the k <= nsteps
     internal steps taken after the first root + reset."""

@@ -156,3 +156,18 @@ def test_reference_snapshot_heat2d(oracle, powmode):
     expected = np.array(case["out"])
     err = np.abs(out - expected) / (np.abs(expected) * case["out_rtol"] + case["out_atol"])
     assert err.max() < 20.0
+
+
+@pytest.mark.parametrize("method,c,h,vec,F_expected", [("bdf", 0.1, 0.0, [1.1, 1.2], [2.11, 2.21]),
+                                                        ("tr_bdf2", 0.1, 1.0, [1.1, 1.2], [1.12, 1.13])])
+def test_residual_operator_known_answers(oracle, method, c, h, vec, F_expected):
+    """test_bdf_callable (op/bdf.rs:317-360): F(y) = M (y - y0 + psi) - c f(y) = [2.11, 2.21], J = M - c f'(y) =
+    diag(1.01), J v = [1.01, 1.01]; test_sdirk_callable (op/sdirk.rs:338-388): F(y) = M y - h f(phi + c y) =
+    [1.12, 1.13], J = M - c h f'(phi + c y) = diag(1.01).  Both on the exponential decay problem (k = 0.1), evaluated
+    with the member functions the oracle's step() uses."""
+    desc = oracle.make_desc("exp_decay", method=method)
+    rc, F, A = oracle.residual_known_answer(desc, [0.1, 1.0], c, h, vec, [1.0, 1.0])
+    assert rc == 0
+    assert np.abs(F - F_expected).max() < 1e-10
+    assert A[0, 0] == 1.01 and A[1, 1] == 1.01 and A[0, 1] == 0.0 and A[1, 0] == 0.0      # assert_eq! in the reference
+    assert np.abs(A @ np.ones(2) - [1.01, 1.01]).max() < 1e-10
