@@ -356,6 +356,23 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                 state = L_JAC;
             }
         }
+        // ================= REINIT: Bdf::step finds the state modified by a reset (bdf.rs:1291-1318) =========================
+        // root finder re-initialised, difference array back to first order (D[:, 0] = y, D[:, 1] = h dy; the higher columns
+        // keep what they held), _jacobian_updates(c, StepSuccess), then set_stop_time again: the TSTOP block's first-step path
+        if constexpr (dsb_model_has_reset<M>::value) {
+            if (__any_sync(0xffffffffu, state == L_REINIT) && state == L_REINIT) {
+                M::root(vY, pl, t, rf.g0);
+                rf.t0 = t;
+                order = 1; n_equal_steps = 0;
+                band_for<U4, BandR2>(N, [&](int i) { return BandR2{GY(i), GYP(i) * h}; },
+                                     [&](int i, const BandR2& r) { GD(0, i) = r.a; GD(1, i) = r.b; });
+                c = h * pa.tab.alpha[1];
+                has_prev_error = false;
+                jac_kind = DSB_STEP_SUCCESS; after_jac = L_TSTOP;
+                first = true;
+                state = L_JAC;
+            }
+        }
         // ================= SELECT (bdf.rs:1489-1563, 1431-1442) ===========================================================
         if (run_slow && state == L_SELECT) {
             const int ord = order;
@@ -542,6 +559,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
         // ================= TSTOP ==========================================================================================
         if (__any_sync(0xffffffffu, state == L_TSTOP) && state == L_TSTOP) {
             bool stopped_on_root = false;
+            bool reset_now = false;             // a reset was applied at a root: set_stop_time again, then L_REINIT
             if constexpr (NR > 0) {
                 // check for a root within the accepted step (bdf.rs:1566-1579), after the step-size update and before the
                 // stop time is handled; the interpolated state of the secant iteration goes to the (free) Newton residual
@@ -554,23 +572,44 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                                                     }, t_root, root_found);
                     if (stopped_on_root) {
                         // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root)
-                        // (bdf.rs:1228-1262), then the state at the root in the next column (method.rs:493-503)
+                        // (bdf.rs:1228-1262), then -- without a reset function -- the state at the root in the next column
+                        // (method.rs:493-503) and the end of the solve
                         while (col < nt && bb.t_eval[col] <= t_root) {
                             write_column(bb.t_eval[col], col);
                             ++col;
                         }
-                        if (col < nt) {
-                            write_column(t_root, col);
-                            ++col;
+                        bool ended = true;
+                        if constexpr (dsb_model_has_reset<M>::value) {
+                            if (!free_running) {
+                                // has_reset (method.rs:783-797): apply_reset (state.rs:246-270: y <- reset(y, t),
+                                // dy <- f(y, t); dy is parked in the predictor's vector until the difference array is
+                                // re-initialised), then a new stop time and on with the integration -- or TstopReached
+                                interpolate_to(t_root, [&](int i, double yo) { GDL(i) = yo; });
+                                t = t_root;
+                                band_for<U2, double>(N, [&](int i) { return M::reset_i(i, vDL, pl, t); }, [&](int i, double r) { GY(i) = r; });
+                                band_for<U2, double>(N, [&](int i) { return M::rhs_i(i, vY, pl, t); }, [&](int i, double r) { GYP(i) = r; });
+                                st.v[DSB_STAT_RHS_CALLS] += 1;
+                                root_found = -1;
+                                ended = false;
+                                if (t < bb.t_eval[nt - 1]) { reset_now = true; stopped_on_root = false; }
+                                else finish(DSB_STATUS_OK);                        // TstopReached
+                            }
                         }
-                        t = t_root;
-                        finish(DSB_STATUS_OK);
+                        if (ended) {
+                            if (col < nt) {
+                                write_column(t_root, col);
+                                ++col;
+                            }
+                            t = t_root;
+                            finish(DSB_STATUS_OK);
+                        }
                     }
                 }
             }
             int next = first ? L_PREDICT : L_OUTPUT;
             int r = 0;
             bool check = has_tstop && !stopped_on_root;
+            if (reset_now) { next = L_REINIT; check = true; has_tstop = true; tstop = bb.t_eval[nt - 1]; }
             if (first) {
                 check = !free_running;
                 if (free_running) next = L_OUTPUT;
@@ -579,7 +618,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
             if (check) {
                 r = handle_tstop(tstop);
                 if (r == 1) {
-                    if (first) r = -DSB_STATUS_STOP_TIME_AT_CURRENT;
+                    if (first || reset_now) r = -DSB_STATUS_STOP_TIME_AT_CURRENT;
                     else reached = true;
                 }
             }

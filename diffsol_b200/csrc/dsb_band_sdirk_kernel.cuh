@@ -463,6 +463,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
             int r = 0;
             int next = first ? R_STEP : R_OUTPUT;
             bool stopped_on_root = false;
+            bool reset_now = false;            // a reset was applied at a root: the stop time is set again, then R_STEP
             if constexpr (NR > 0) {
                 // check for a root within the accepted step (runge_kutta.rs:935-948), before the stop time is handled;
                 // the interpolated state of the secant iteration goes to the (free) Newton residual
@@ -480,12 +481,42 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                             write_column(bb.t_eval[col], col);
                             ++col;
                         }
-                        if (col < nt) {
-                            write_column(t_root, col);
-                            ++col;
+                        bool ended = true;
+                        if constexpr (dsb_model_has_reset<M>::value) {
+                            if (!free_running) {
+                                // has_reset (method.rs:783-797): apply_reset (sdirk.rs:368-374 -> state.rs:279-306:
+                                // y <- reset(y, t), dy <- f(y, t)), set_stop_time(final_time) and on with the
+                                // integration -- or TstopReached.  Step size, Jacobian and LU stay; Rk::start_step
+                                // (runge_kutta.rs:446-464) re-initialises the root finder and sets the stop time again.
+                                interpolate_to(t_root, [&](int i, double yo) { GDL(i) = yo; });
+                                t = t_root;
+                                band_for<U2, double>(N, [&](int i) { return M::reset_i(i, vDL, pl, t); }, [&](int i, double v) { GY(i) = v; });
+                                band_for<U2, double>(N, [&](int i) { return M::rhs_i(i, vY, pl, t); }, [&](int i, double v) { GDY(i) = v; });
+                                st.v[DSB_STAT_RHS_CALLS] += 1;
+                                root_found = -1;
+                                ended = false;
+                                if (t < bb.t_eval[nt - 1]) {
+                                    has_tstop = true; tstop = bb.t_eval[nt - 1];
+                                    r = handle_tstop(tstop);                       // method.rs:792
+                                    if (r == 0) {
+                                        M::root(vY, pl, t, rf.g0);                 // start_step: root_finder.init
+                                        rf.t0 = t;
+                                        r = handle_tstop(tstop);                   // start_step: set_stop_time(tstop)
+                                    }
+                                    if (r == 1) r = -DSB_STATUS_STOP_TIME_AT_CURRENT;
+                                    stopped_on_root = false; reset_now = true;
+                                    next = R_STEP;
+                                } else finish(DSB_STATUS_OK);                      // TstopReached
+                            }
                         }
-                        t = t_root;
-                        finish(DSB_STATUS_OK);
+                        if (ended) {
+                            if (col < nt) {
+                                write_column(t_root, col);
+                                ++col;
+                            }
+                            t = t_root;
+                            finish(DSB_STATUS_OK);
+                        }
                     }
                 }
             }
@@ -496,11 +527,11 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                     r = handle_tstop(tstop);
                     if (r == 1) r = -DSB_STATUS_STOP_TIME_AT_CURRENT;
                 }
-            } else if (has_tstop && !stopped_on_root) {
+            } else if (has_tstop && !stopped_on_root && !reset_now) {
                 r = handle_tstop(tstop);
                 if (r == 1) { reached = true; has_tstop = false; }
             }
-            if (stopped_on_root) {
+            if (stopped_on_root || state == R_FINISH) {
                 // the lane is on its way to FINISH
             } else if (r < 0) finish(-r);
             else state = next;

@@ -433,6 +433,30 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
             }
         };
 
+        // apply_reset (state.rs:246-270, no mass matrix): y <- reset(x, t) with x the state at the root (a shared vector),
+        // dy <- f(y, t).  Component-wise equations are evaluated cooperatively; the small whole-vector ones by every
+        // thread on local copies.
+        auto apply_reset_at = [&](const double* x, double tt) {
+            if constexpr (dsb_model_has_reset<M>::value) {
+                if constexpr (dsb_is_componentwise<M>::value) {
+                    __syncthreads();
+                    for (int i = tid; i < N; i += T) ys[i] = M::reset_i(i, x, p, tt);
+                    __syncthreads();
+                    for (int i = tid; i < N; i += T) dys[i] = E::rhs_i(i, ys, p, tt);
+                    __syncthreads();
+                } else {
+                    double yl[N], yr[N], dyr[N];
+                    for (int i = 0; i < N; ++i) yl[i] = x[i];
+                    M::reset(yl, p, tt, yr);
+                    M::rhs(yr, p, tt, dyr);
+                    __syncthreads();
+                    for (int i = tid; i < N; i += T) { ys[i] = yr[i]; dys[i] = dyr[i]; }
+                    __syncthreads();
+                }
+                st.v[DSB_STAT_RHS_CALLS] += 1;
+            }
+        };
+
         if constexpr (RK) {
         // ================= Rk::_new + Sdirk::_new (runge_kutta.rs:100-190, sdirk.rs:80-160) =================
         const int ns = pa.rk.s;
@@ -761,14 +785,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                                 ended = false;
                                 interpolate_to_shared(t_root, yp);
                                 t = t_root;
-                                double yl[N], yr[N], dyr[N];
-                                for (int i = 0; i < N; ++i) yl[i] = yp[i];
-                                M::reset(yl, p, t, yr);
-                                M::rhs(yr, p, t, dyr);
-                                st.v[DSB_STAT_RHS_CALLS] += 1;
-                                __syncthreads();
-                                for (int i = tid; i < N; i += T) { ys[i] = yr[i]; dys[i] = dyr[i]; }
-                                __syncthreads();
+                                apply_reset_at(yp, t);
                                 root_found = -1;
                                 if (t < bb.t_eval[nt - 1]) {
                                     step_result = 3;
@@ -1153,14 +1170,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                                 ended = false;
                                 interpolate_to_shared(t_root, yc);
                                 t = t_root;
-                                double yl[N], yr[N], dyr[N];
-                                for (int i = 0; i < N; ++i) yl[i] = yc[i];
-                                M::reset(yl, p, t, yr);
-                                M::rhs(yr, p, t, dyr);
-                                st.v[DSB_STAT_RHS_CALLS] += 1;
-                                __syncthreads();
-                                for (int i = tid; i < N; i += T) { ys[i] = yr[i]; dys[i] = dyr[i]; }
-                                __syncthreads();
+                                apply_reset_at(yc, t);
                                 root_found = -1;
                                 if (t < bb.t_eval[nt - 1]) {
                                     step_result = 3;

@@ -270,7 +270,6 @@ cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const
                                                  cudaStream_t stream, cudaEvent_t mid, unsigned long long* work_counter,
                                                  DsbCoopState* coop, const double* atol_host, int* launches) {
     // exec_mode 3 / automatic: the banded lane kernels where the model qualifies (BDF and (E)SDIRK)
-    static_assert(!(kBandCapable && dsb_model_has_reset<InstModel>::value), "the banded lane kernels do not apply resets");
     if (kBandCapable && (coop->exec_mode == 3 || coop->exec_mode == 0)) {
         const cudaError_t e = BandLauncher<InstModel, kBandCapable>::run(pa, bb, method, stream, mid, work_counter, coop, atol_host, launches);
         if (e != cudaErrorNotSupported || coop->exec_mode == 3) return e;

@@ -36,6 +36,7 @@ enum dsb_model_id {
     DSB_MODEL_HEAT2D_10 = 18,           // n=100 np=0  2-D heat equation on a 10 x 10 grid, boundary rows algebraic (test_models/heat2d.rs), states only
     DSB_MODEL_BALL_BOUNCE = 19,         // n=2  np=3   bouncing ball x' = v, v' = -g with the root x and the reset v -> -e v (ode_solver/mod.rs:1001-1080)
     DSB_MODEL_EXP_DECAY_TWO_ROOTS = 20, // n=2  np=2   exp_decay with the roots y[0] - 0.6, y[0] - 0.3 and no reset (exponential_decay.rs:827-832, 890-912)
+    DSB_MODEL_SPM_CYCLE = 21,           // n=42 np=1   spm_stop with a reset: at a voltage cut-off the cell goes back to its initial (charged) state
     DSB_MODEL_COUNT
 };
 
@@ -536,6 +537,20 @@ struct ModelSpmStopT : ModelSpmT<Tab> {
 typedef ModelSpmStopT<SpmTables20> ModelSpmStop;
 typedef ModelSpmStopT<SpmTables99> ModelSpm99Stop;
 
+// The battery model cycled: the stop function's roots do not end the solve, the reset function (OdeEquations::reset,
+// applied by solve_dense at every root, ode_solver/method.rs:783-797) puts the cell back into its initial, charged
+// state and the discharge starts again.  Not a reference problem (the reference has no reset problem with n > 16): it
+// exists to run resets through the banded lane kernels; pinned GPU-vs-oracle only.
+template <class Tab>
+struct ModelSpmCycleT : ModelSpmStopT<Tab> {
+    typedef ModelSpmStopT<Tab> Base;
+    static constexpr bool HAS_RESET = true;
+    template <class X>
+    DSB_HD static double reset_i(int i, const X&, const double* p, double t) { return Base::init_i(i, p, t); }
+    DSB_HD static void reset(const double*, const double* p, double t, double* y) { for (int i = 0; i < Base::N; ++i) y[i] = Base::init_i(i, p, t); }
+};
+typedef ModelSpmCycleT<SpmTables20> ModelSpmCycle;
+
 // id -> functor type
 template <int ID> struct dsb_model_by_id;
 template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY> { typedef ModelExpDecay type; };
@@ -559,6 +574,7 @@ template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY_RESET> { typedef ModelExp
 template <> struct dsb_model_by_id<DSB_MODEL_HEAT2D_10> { typedef ModelHeat2d<10> type; };
 template <> struct dsb_model_by_id<DSB_MODEL_BALL_BOUNCE> { typedef ModelBallBounce type; };
 template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY_TWO_ROOTS> { typedef ModelExpDecayTwoRoots type; };
+template <> struct dsb_model_by_id<DSB_MODEL_SPM_CYCLE> { typedef ModelSpmCycle type; };
 
 // traits of an equation set: written component-wise (`*_i` functions), declares a band for df/dy
 template <class M, class = void> struct dsb_is_componentwise : std::false_type {};
@@ -591,6 +607,7 @@ inline bool dsb_dispatch_model(int id, F&& f) {
         case DSB_MODEL_HEAT2D_10: f.template operator()<ModelHeat2d<10>>(); return true;
         case DSB_MODEL_BALL_BOUNCE: f.template operator()<ModelBallBounce>(); return true;
         case DSB_MODEL_EXP_DECAY_TWO_ROOTS: f.template operator()<ModelExpDecayTwoRoots>(); return true;
+        case DSB_MODEL_SPM_CYCLE: f.template operator()<ModelSpmCycle>(); return true;
         default: return false;
     }
 }

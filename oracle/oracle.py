@@ -52,6 +52,7 @@ MODELS = {
     "heat2d_10": 18,
     "ball_bounce": 19,
     "exp_decay_two_roots": 20,
+    "spm_cycle": 21,
 }
 
 

@@ -220,6 +220,27 @@ def test_resets_on_the_block_per_instance_path(dsb, oracle, model, method):
     assert np.array_equal(ys, ys_o, equal_nan=True)
 
 
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
+@pytest.mark.parametrize("execution", ["band", "block"])
+def test_battery_cycling_with_resets_bit_exact(dsb, oracle, method, execution):
+    """Resets at n > 16: the battery model cycled (spm_cycle: at a voltage cut-off the cell goes back to its charged state
+    and the discharge starts again) on the banded lane kernels and on the block-per-instance kernel, all three methods."""
+    from diffsol_b200 import sweeps
+    B = 96 if execution == "band" else 32
+    cur = (0.6 + 0.8 * sweeps.uniform(np.arange(B), 0)).reshape(-1, 1)
+    t_eval = np.arange(1, 121) * 60.0
+    solver = getattr(dsb.OdeBuilder().rhs_implicit("spm_cycle").p(cur).use_coloring(True).build(), method)().set_execution(execution)
+    ys = solver.solve_dense(t_eval)
+    root_idx, ncols = solver.root_info()
+    desc = oracle.make_desc("spm_cycle", method=method, powmode=1, use_coloring=True)
+    ys_o, stats_o, status_o, t_root_o, root_idx_o, ncols_o = oracle.batch_solve_dense_roots(desc, cur, t_eval)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(root_idx, root_idx_o) and (root_idx == -1).all() and np.array_equal(ncols, ncols_o)
+    assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
+    assert np.array_equal(ys, ys_o, equal_nan=True)
+    assert (np.diff(ys[:, :, 0], axis=1) > 0.3).sum(axis=1).min() >= 1          # every cell was recharged at least once
+
+
 def test_root_info_without_roots(dsb):
     p = np.tile(np.array([[0.04, 1.0e4, 3.0e7]]), (40, 1))
     solver = dsb.OdeBuilder().rhs_implicit("robertson_ode").p(p).rtol(1e-4).atol([1e-8, 1e-14, 1e-6]).build().bdf()

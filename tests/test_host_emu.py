@@ -194,3 +194,17 @@ def test_root_index_in_the_on_chip_lane_kernels_on_host(oracle, method):
     fired = o[4]
     assert set(fired.tolist()) == {-1, 0, 1}
     assert (fired[p[:, 1] > 0.6] != 1).all() and (fired[p[:, 1] < 0.6] != 0).all() and (fired[p[:, 1] < 0.3] == -1).all()
+
+
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
+def test_reset_in_the_band_kernels_on_host(oracle, method):
+    """Resets on the banded lane kernels: the battery model cycled (spm_cycle: at a voltage cut-off the cell goes back
+    to its charged state and the discharge starts again), two to three discharges per instance."""
+    B = 10
+    r, o = run_both_roots(oracle, "spm_cycle", spm_currents(B), np.arange(1, 121) * 60.0, method=method, kernel="band",
+                          use_coloring=True)
+    assert_same_roots(r, o)
+    assert (o[2] == 0).all() and (o[4] == -1).all()
+    v = r["ys"][:, :, 0]
+    assert (np.diff(v, axis=1) > 0.3).sum(axis=1).min() >= 1          # every instance was recharged at least once
+    assert v.min() > 3.0 and v.max() < 4.2
