@@ -467,7 +467,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
             if constexpr (NR > 0) {
                 // check for a root within the accepted step (runge_kutta.rs:935-948), before the stop time is handled;
                 // the interpolated state of the secant iteration goes to the (free) Newton residual
-                if (!first) {
+                if (!first && !free_running) {   // the step()/interpolate() loop of the reference's harness (free_running) ignores RootFound: it steps on
                     double t_root = t;
                     stopped_on_root = rf.check_root(t, [&](double (&gv)[NR]) { M::root(vY, pl, t, gv); },
                                                     [&](double t_mid, double (&gv)[NR]) {

@@ -466,7 +466,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                 // check for a root within the accepted step (bdf.rs:1566-1579), after the step-size update and before
                 // the stop time is handled; RootFinder::check_root (root.rs:60-160) with Vector::root_finding
                 // (diffsol-la/src/vector/nalgebra_serial.rs:484-504)
-                if (!first) {
+                if (!first && !free_running) {   // the step()/interpolate() loop of the reference's harness (free_running) ignores RootFound: it steps on
                     double pl[NP > 0 ? NP : 1], ys[N];
 #pragma unroll
                     for (int j = 0; j < NP; ++j) pl[j] = SP(j);

@@ -761,7 +761,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                 t = t + hs;
                 h = new_h;
                 st.v[DSB_STAT_STEPS] += 1;
-                if constexpr (NR > 0) {
+                if constexpr (NR > 0) if (!free_running) {   // the step()/interpolate() loop of the reference's harness (free_running) ignores RootFound: it steps on
                     // check for a root within the accepted step (runge_kutta.rs:935-948), before the stop time is handled
                     double t_root = t;
                     const bool stopped_on_root = rf.check_root(t, [&](double (&gv)[NR]) { M::root(ys, p, t, gv); },
@@ -1141,7 +1141,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                         jacobian_updates(new_h * pa.tab.alpha[order], DSB_STEP_SUCCESS);
                     }
                 }
-                if constexpr (NR > 0) {
+                if constexpr (NR > 0) if (!free_running) {   // the step()/interpolate() loop of the reference's harness (free_running) ignores RootFound: it steps on
                     // check for a root within the accepted step (bdf.rs:1566-1579), after the step-size update and before
                     // the stop time is handled; the interpolated state of the secant iteration goes to the (free) vector yc
                     double t_root = t;

@@ -390,7 +390,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
             bool reset_now = false;            // a reset was applied at a root: the stop time is set again, then R_STEP
             if constexpr (NR > 0) {
                 // check for a root within the accepted step (runge_kutta.rs:935-948), before the stop time is handled
-                if (!first) {
+                if (!first && !free_running) {   // the step()/interpolate() loop of the reference's harness (free_running) ignores RootFound: it steps on
                     double pl[NP > 0 ? NP : 1], ys[N];
 #pragma unroll
                     for (int j = 0; j < NP; ++j) pl[j] = SP(j);

@@ -241,6 +241,22 @@ def test_battery_cycling_with_resets_bit_exact(dsb, oracle, method, execution):
     assert (np.diff(ys[:, :, 0], axis=1) > 0.3).sum(axis=1).min() >= 1          # every cell was recharged at least once
 
 
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
+@pytest.mark.parametrize("execution", ["lane", "block"])
+def test_harness_loop_ignores_roots(dsb, oracle, method, execution):
+    """The step()/interpolate() loop of the reference's harness (ode_solver/mod.rs:132-141) does not look at the stop
+    reason: with a root function the loop steps on past the root.  step_and_interpolate does the same."""
+    pts = np.arange(0.0, 10.0)
+    solver = getattr(dsb.OdeBuilder().rhs_implicit("exp_decay_root").p([[0.1, 1.0], [0.2, 1.5]]).build(), method)().set_execution(execution)
+    ys = solver.step_and_interpolate(pts)
+    desc = oracle.make_desc("exp_decay_root", method=method, powmode=1)
+    for b, p in enumerate([[0.1, 1.0], [0.2, 1.5]]):
+        rc, ys_o, stats_o, fin = oracle.harness(desc, p, pts)
+        assert rc == 0 and solver.status()[b] == 0
+        assert np.array_equal(ys[b], ys_o) and solver.get_statistics(b) == stats_o
+    assert (solver.root_info()[0] == -1).all()
+
+
 def test_root_info_without_roots(dsb):
     p = np.tile(np.array([[0.04, 1.0e4, 3.0e7]]), (40, 1))
     solver = dsb.OdeBuilder().rhs_implicit("robertson_ode").p(p).rtol(1e-4).atol([1e-8, 1e-14, 1e-6]).build().bdf()

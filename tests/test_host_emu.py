@@ -208,3 +208,17 @@ def test_reset_in_the_band_kernels_on_host(oracle, method):
     v = r["ys"][:, :, 0]
     assert (np.diff(v, axis=1) > 0.3).sum(axis=1).min() >= 1          # every instance was recharged at least once
     assert v.min() > 3.0 and v.max() < 4.2
+
+
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
+def test_harness_loop_ignores_roots_on_host(oracle, method):
+    """The step()/interpolate() loop of the reference's harness (ode_solver/mod.rs:132-141) does not look at the stop
+    reason: with a root function the solver reports RootFound and the loop steps on.  step_and_interpolate does the same."""
+    pts = np.arange(0.0, 10.0)
+    desc = oracle.make_desc("exp_decay_root", method=method, powmode=1)
+    rc, ys_o, stats_o, fin = oracle.harness(desc, [0.1, 1.0], pts)
+    assert rc == 0
+    r = emu.solve(oracle.MODELS["exp_decay_root"], 2, 2, [[0.1, 1.0]], pts, method=method, free_running=True)
+    assert r["status"][0] == 0 and np.array_equal(r["ys"][0], ys_o)
+    assert {n: int(r["stats"][0, i]) for i, n in enumerate(oracle.S_NAMES)} == stats_o
+    assert r["fin"][0, 0] == fin["t"] and fin["t"] >= 9.0
