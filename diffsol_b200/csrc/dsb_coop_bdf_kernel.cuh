@@ -1,5 +1,7 @@
-// dsb_coop_bdf_kernel.cuh -- the BDF path for systems too large for one thread per instance (n > 16):
-// ONE THREAD BLOCK per instance, one thread per state component.  Control flow is uniform over the block
+// dsb_coop_bdf_kernel.cuh -- the path for systems too large for one thread per instance (n > 16) that are not banded:
+// ONE THREAD BLOCK per instance, one thread per state component.  One kernel, two instantiations over the same
+// cooperative pieces: Bdf::step (RK = false; the file's name is from when it was the only one) and Sdirk::step
+// (RK = true: TR-BDF2 / ESDIRK34 from the tableau in pa.rk).  Control flow is uniform over the block
 // (every thread carries the controller scalars and takes the same decisions from the same shared-memory
 // data), so the reference's nested loops are kept as they are; what is parallel is every vector / matrix
 // operation inside them.  Vectors (the difference array D, y, predictor, Newton iterate, ...) live in shared
@@ -11,8 +13,9 @@
 // (squared_norm: nalgebra_serial.rs:395-408; LU; substitutions) is summed in the same order here (the norm's
 // terms are computed in parallel and added up by one thread).
 //
-// Restated functions: the same list as dsb_bdf_kernel.cuh and dsb_init_kernel.cuh (Bdf::_new, Bdf::step and
-// everything it calls, new_and_consistent with InitOp, set_step_size, solve_dense), paths relative to
+// Restated functions: the same lists as dsb_bdf_kernel.cuh, dsb_sdirk_kernel.cuh and dsb_init_kernel.cuh (Bdf::_new,
+// Bdf::step / Rk::_new, Sdirk::step and everything they call, new_and_consistent with InitOp, set_step_size,
+// solve_dense with its RootFound / reset branches, dense_write_out with an output function), paths relative to
 // /root/reference/crates/diffsol/src.
 #pragma once
 #include <type_traits>
