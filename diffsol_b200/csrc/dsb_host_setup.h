@@ -93,6 +93,25 @@ inline void build_tableau(int method, DsbSdirkTableau* t) {
     }
 }
 
+// coloring.rs:27-47 (nonzeros2graph: columns that share a row are adjacent) + greedy_coloring.rs:14-34
+// (color_graph_greedy): colour (1-based) of every column
+inline std::vector<int> greedy_coloring(const std::vector<std::pair<int, int>>& non_zeros, int N) {
+    std::vector<std::vector<int>> cols_by_rows(N), adj(N);
+    for (auto& ij : non_zeros) cols_by_rows[ij.first].push_back(ij.second);
+    for (auto& ij : non_zeros)
+        for (int next_col : cols_by_rows[ij.first])
+            if (next_col < ij.second) { adj[ij.second].push_back(next_col); adj[next_col].push_back(ij.second); }
+    std::vector<int> result(N, 0);
+    if (N > 0) result[0] = 1;
+    std::vector<char> available(N, 0);
+    for (int ii = 1; ii < N; ++ii) {
+        for (int j : adj[ii]) if (result[j] != 0) available[result[j] - 1] = 1;
+        for (int i = 0; i < N; ++i) if (!available[i]) { result[ii] = i + 1; break; }
+        std::fill(available.begin(), available.end(), 0);
+    }
+    return result;
+}
+
 // jacobian/mod.rs:16-48 (NaN probe), coloring.rs:27-47 (graph), greedy_coloring.rs:14-34.
 // The pattern is a property of the equations, not of the instance ("assume every batch has the same
 // non-zeros", jacobian/mod.rs:32), so it is found once on the host with the model's own functor.
@@ -117,19 +136,7 @@ struct ColoringOf {
             v[j] = 0.0;
         }
         *probes = N;
-        std::vector<std::vector<int>> cols_by_rows(N), adj(N);
-        for (auto& ij : non_zeros) cols_by_rows[ij.first].push_back(ij.second);
-        for (auto& ij : non_zeros)
-            for (int next_col : cols_by_rows[ij.first])
-                if (next_col < ij.second) { adj[ij.second].push_back(next_col); adj[next_col].push_back(ij.second); }
-        std::vector<int> result(N, 0);
-        if (N > 0) result[0] = 1;
-        std::vector<char> available(N, 0);
-        for (int ii = 1; ii < N; ++ii) {
-            for (int j : adj[ii]) if (result[j] != 0) available[result[j] - 1] = 1;
-            for (int i = 0; i < N; ++i) if (!available[i]) { result[ii] = i + 1; break; }
-            std::fill(available.begin(), available.end(), 0);
-        }
+        const std::vector<int> result = greedy_coloring(non_zeros, N);
         int max_color = 0;
         for (int c : result) if (c > max_color) max_color = c;
         pa->ncolors = max_color;

@@ -107,6 +107,7 @@ Model make_model() {
     return m;
 }
 bool model_by_id(int id, Model* out);
+std::vector<int> greedy_coloring(const std::vector<std::pair<int, int>>& non_zeros, int n);   // 1-based colour per column
 
 // ---- OdeSolverOptions / InitialConditionSolverOptions (ode_solver/problem.rs:15-152) -----------
 struct Options {

@@ -180,6 +180,15 @@ int orc_harness_tstop(const orc_problem_desc* d, const double* p, int np, const 
     return err;
 }
 
+// nonzeros2graph + color_graph_greedy on a given pattern (the reference's build_coloring test, jacobian/mod.rs:483-513)
+int orc_greedy_coloring(const int32_t* rows, const int32_t* cols, int nnz, int n, int32_t* colors) {
+    std::vector<std::pair<int, int>> nz;
+    for (int k = 0; k < nnz; ++k) nz.push_back({rows[k], cols[k]});
+    const std::vector<int> r = greedy_coloring(nz, n);
+    for (int j = 0; j < n; ++j) colors[j] = r[j];
+    return ST_OK;
+}
+
 // The reference's residual-operator unit tests (op/bdf.rs:317-360, op/sdirk.rs:338-388): F(x) and the iteration matrix of
 // the method's callable with its scalars and vector set directly.  F is n, A is n x n column-major.
 int orc_residual_known_answer(const orc_problem_desc* d, const double* p, int np, double c, double h, const double* vec,

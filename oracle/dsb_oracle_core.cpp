@@ -32,6 +32,26 @@ double squared_norm(const double* x, const double* y, const double* atol, double
 
 // ---- Problem -------------------------------------------------------------------------------------
 
+// jacobian/coloring.rs:27-47 (nonzeros2graph: columns that share a row are adjacent) + jacobian/greedy_coloring.rs:14-34
+// (color_graph_greedy): colour (1-based) of every column
+std::vector<int> greedy_coloring(const std::vector<std::pair<int, int>>& non_zeros, int nn) {
+    std::vector<std::vector<int>> cols_by_rows(nn);
+    for (auto& ij : non_zeros) cols_by_rows[ij.first].push_back(ij.second);
+    std::vector<std::vector<int>> adj(nn);
+    for (auto& ij : non_zeros)
+        for (int next_col : cols_by_rows[ij.first])
+            if (next_col < ij.second) { adj[ij.second].push_back(next_col); adj[next_col].push_back(ij.second); }
+    std::vector<int> result(nn, 0);
+    if (nn > 0) result[0] = 1;
+    std::vector<char> available(nn, 0);
+    for (int ii = 1; ii < nn; ++ii) {
+        for (int j : adj[ii]) if (result[j] != 0) available[result[j] - 1] = 1;
+        for (int i = 0; i < nn; ++i) if (!available[i]) { result[ii] = i + 1; break; }
+        std::fill(available.begin(), available.end(), 0);
+    }
+    return result;
+}
+
 // jacobian/mod.rs:16-48 (NaN probe, one jac_mul per column, counted in OpStatistics),
 // jacobian/coloring.rs:27-47 (graph), jacobian/greedy_coloring.rs:14-34, jacobian/mod.rs:178-214
 void Problem::build_coloring() {
@@ -47,21 +67,7 @@ void Problem::build_coloring() {
         std::fill(col.begin(), col.end(), 0.0);
         v[j] = 0.0;
     }
-    // graph: columns that share a row are adjacent
-    std::vector<std::vector<int>> cols_by_rows(nn);
-    for (auto& ij : non_zeros) cols_by_rows[ij.first].push_back(ij.second);
-    std::vector<std::vector<int>> adj(nn);
-    for (auto& ij : non_zeros)
-        for (int next_col : cols_by_rows[ij.first])
-            if (next_col < ij.second) { adj[ij.second].push_back(next_col); adj[next_col].push_back(ij.second); }
-    std::vector<int> result(nn, 0);
-    if (nn > 0) result[0] = 1;
-    std::vector<char> available(nn, 0);
-    for (int ii = 1; ii < nn; ++ii) {
-        for (int j : adj[ii]) if (result[j] != 0) available[result[j] - 1] = 1;
-        for (int i = 0; i < nn; ++i) if (!available[i]) { result[ii] = i + 1; break; }
-        std::fill(available.begin(), available.end(), 0);
-    }
+    const std::vector<int> result = greedy_coloring(non_zeros, nn);
     int max_color = 0;
     for (int c : result) max_color = std::max(max_color, c);
     color_inputs.clear(); color_entries.clear();

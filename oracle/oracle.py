@@ -210,6 +210,17 @@ def harness(desc, p, t_points, use_tstop=False):
     return _run(lib().orc_harness_tstop if use_tstop else lib().orc_harness, desc, p, t_points)
 
 
+def greedy_coloring(non_zeros, n):
+    """nonzeros2graph + color_graph_greedy -> 1-based colour of every column."""
+    rows = np.ascontiguousarray([ij[0] for ij in non_zeros], dtype=np.int32)
+    cols = np.ascontiguousarray([ij[1] for ij in non_zeros], dtype=np.int32)
+    out = np.zeros(n, dtype=np.int32)
+    ip = ctypes.POINTER(ctypes.c_int32)
+    rc = lib().orc_greedy_coloring(rows.ctypes.data_as(ip), cols.ctypes.data_as(ip), len(rows), int(n), out.ctypes.data_as(ip))
+    assert rc == 0
+    return out.tolist()
+
+
 def residual_known_answer(desc, p, c, h, vec, x, t=0.0):
     """BdfCallable / SdirkCallable with c, (h) and psi - y0 / phi set directly -> (rc, F(x)[n], A[n, n])."""
     n, np_, _ = _dims_by_id(desc.model_id)

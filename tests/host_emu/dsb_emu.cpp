@@ -116,6 +116,15 @@ int emu_solve(int model, int method, int kernel, double rtol, const double* atol
     return call.rc;
 }
 
+// the product's host-side greedy colouring (dsb_host_setup.h) on a given pattern
+int emu_greedy_coloring(const int32_t* rows, const int32_t* cols, int nnz, int n, int32_t* colors) {
+    std::vector<std::pair<int, int>> nz;
+    for (int k = 0; k < nnz; ++k) nz.push_back({rows[k], cols[k]});
+    const std::vector<int> r = dsb_host::greedy_coloring(nz, n);
+    for (int j = 0; j < n; ++j) colors[j] = r[j];
+    return DSB_OK;
+}
+
 void dsb_options_default(dsb_options* o) {
     std::memset(o, 0, sizeof(*o));
     o->max_nonlinear_solver_iterations = 10; o->max_error_test_failures = 40; o->max_nonlinear_solver_failures = 50;

@@ -110,3 +110,14 @@ def solve(model_id, n, np_, params, t_eval, method="bdf", kernel="lane", rtol=1e
     if rc != 0:
         raise RuntimeError("emu_solve: rc = %d (kernel %r not available for this model / method?)" % (rc, kernel))
     return dict(ys=ys, stats=stats, status=status, fin=fin, root_idx=root_idx, ncols=ncols)
+
+
+def greedy_coloring(non_zeros, n):
+    """The product's host-side colouring (csrc/dsb_host_setup.h: greedy_coloring) -> 1-based colour of every column."""
+    rows = np.ascontiguousarray([ij[0] for ij in non_zeros], dtype=np.int32)
+    cols = np.ascontiguousarray([ij[1] for ij in non_zeros], dtype=np.int32)
+    out = np.zeros(n, dtype=np.int32)
+    ip = ctypes.POINTER(ctypes.c_int32)
+    rc = lib().emu_greedy_coloring(rows.ctypes.data_as(ip), cols.ctypes.data_as(ip), len(rows), int(n), out.ctypes.data_as(ip))
+    assert rc == 0
+    return out.tolist()

@@ -222,3 +222,39 @@ def test_harness_loop_ignores_roots_on_host(oracle, method):
     assert r["status"][0] == 0 and np.array_equal(r["ys"][0], ys_o)
     assert {n: int(r["stats"][0, i]) for i, n in enumerate(oracle.S_NAMES)} == stats_o
     assert r["fin"][0, 0] == fin["t"] and fin["t"] >= 9.0
+
+
+COLORING_CASES = [      # jacobian/mod.rs:483-513 build_coloring: (row, col) patterns of 2 x 2 operators and their colourings
+    ([(0, 0), (1, 1)], [1, 1]),
+    ([(0, 0), (0, 1), (1, 1)], [1, 2]),
+    ([(1, 1)], [1, 1]),
+    ([(0, 0), (1, 0), (0, 1), (1, 1)], [1, 2]),
+]
+
+
+@pytest.mark.parametrize("non_zeros,expected", COLORING_CASES)
+def test_greedy_coloring_known_answers(oracle, non_zeros, expected):
+    """nonzeros2graph + color_graph_greedy (jacobian/coloring.rs:27-47, greedy_coloring.rs:14-34) with the reference's own
+    expected colourings, for the oracle's restatement and for the product's host-side one (csrc/dsb_host_setup.h)."""
+    assert oracle.greedy_coloring(non_zeros, 2) == expected
+    assert emu.greedy_coloring(non_zeros, 2) == expected
+
+
+def test_greedy_coloring_band_patterns(oracle):
+    """Tridiagonal and pentadiagonal patterns need 3 and 5 colours; an arrow pattern (dense first row) n; both restatements
+    agree on every pattern."""
+    rng = np.random.default_rng(3)
+    for n, half in ((12, 1), (12, 2)):
+        nz = [(i, j) for j in range(n) for i in range(n) if abs(i - j) <= half]
+        assert max(oracle.greedy_coloring(nz, n)) == 2 * half + 1
+        assert emu.greedy_coloring(nz, n) == oracle.greedy_coloring(nz, n)
+    arrow = [(0, j) for j in range(8)] + [(j, j) for j in range(1, 8)]
+    assert oracle.greedy_coloring(arrow, 8) == list(range(1, 9)) == emu.greedy_coloring(arrow, 8)
+    for _ in range(20):
+        n = int(rng.integers(2, 15))
+        nz = sorted({(int(rng.integers(0, n)), int(rng.integers(0, n))) for _ in range(3 * n)}, key=lambda ij: (ij[1], ij[0]))
+        a, b = oracle.greedy_coloring(nz, n), emu.greedy_coloring(nz, n)
+        assert a == b
+        for (i, j) in nz:                                  # structurally orthogonal: no two columns of a colour share a row
+            for (i2, j2) in nz:
+                assert not (i == i2 and j != j2 and a[j] == a[j2])
