@@ -102,3 +102,29 @@ def test_c_abi_library_exports_every_declared_symbol():
     if capi.device_count() == 0:
         with pytest.raises(diffsol_b200.DiffsolB200Error):
             prob.bdf()
+
+
+def test_c_abi_argument_errors_are_reported_not_swallowed():
+    """Host-only entry points of the C ABI: bad arguments come back as DSB_BAD_ARG (-2) with a message in the thread-local
+    dsb_last_error(), the conventions of diffsol-c (c_api_utils.rs:3-5, error_c.rs:12-46); no GPU needed."""
+    import ctypes
+    sys.path.insert(0, ROOT)
+    from diffsol_b200 import capi
+    L = capi.lib()
+    h = ctypes.c_void_p()
+    assert L.dsb_problem_new(10_000, ctypes.byref(h)) == -2 and b"unknown model" in L.dsb_last_error()
+    assert L.dsb_problem_new(capi.MODELS["robertson_dae"], None) == -2
+    assert L.dsb_problem_new(capi.MODELS["robertson_dae"], ctypes.byref(h)) == 0
+    two = (ctypes.c_double * 2)(1e-6, 1e-6)
+    assert L.dsb_problem_set_atol(h, two, 2) == -2 and b"atol" in L.dsb_last_error()     # 1 or nstates entries
+    three = (ctypes.c_double * 3)(1e-8, 1e-6, 1e-6)
+    assert L.dsb_problem_set_atol(h, three, 3) == 0 and L.dsb_problem_set_atol(h, two, 1) == 0
+    assert L.dsb_problem_set_h0(h, ctypes.c_double(0.0)) == -2 and L.dsb_problem_set_h0(h, ctypes.c_double(-1.0)) == 0
+    nout = ctypes.c_int32(-1)
+    assert L.dsb_problem_nout(h, ctypes.byref(nout)) == 0 and nout.value == 3             # no output function: the states
+    assert L.dsb_problem_free(h) == 0
+    h2 = ctypes.c_void_p()
+    assert L.dsb_problem_new(capi.MODELS["spm_stop"], ctypes.byref(h2)) == 0
+    assert L.dsb_problem_nout(h2, ctypes.byref(nout)) == 0 and nout.value == 1            # terminal voltage
+    assert L.dsb_problem_free(h2) == 0
+    assert L.dsb_version().decode()
