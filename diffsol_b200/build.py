@@ -43,6 +43,18 @@ def _sources_digest():
     return h.hexdigest()
 
 
+def have_nvcc():
+    import shutil
+    cand = _nvcc()
+    return os.path.exists(cand) if os.path.isabs(cand) else shutil.which(cand) is not None
+
+
+def is_current():
+    """True when the library on disk was built from the sources as they are now."""
+    stamp = os.path.join(OUT_DIR, "build.sha256")
+    return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == _sources_digest()
+
+
 def _run(cmd):
     r = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:

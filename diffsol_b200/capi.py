@@ -126,12 +126,18 @@ def library_path():
 
 
 def lib():
-    """Load (building first if the sources changed and nvcc is present) the C-ABI library."""
+    """Load the C-ABI library, building it first when it is missing or when the sources changed since it was built
+    (build() compares a digest of csrc/ with the stamp of the last build and returns at once when they agree).  Without
+    nvcc a stale or missing library is an error, not a silent fallback."""
     global _lib
     if _lib is None:
         path = _build.LIB
-        if not os.path.exists(path) or os.environ.get("DSB_REBUILD"):
-            path = _build.build()
+        if _build.have_nvcc():
+            path = _build.build(force=bool(os.environ.get("DSB_REBUILD")))
+        elif not os.path.exists(path):
+            raise DiffsolB200Error("libdiffsol_b200.so is not built and nvcc is not available (python -m diffsol_b200.build)")
+        elif not _build.is_current():
+            raise DiffsolB200Error("libdiffsol_b200.so is older than diffsol_b200/csrc and nvcc is not available to rebuild it")
         L = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             f = getattr(L, name)          # AttributeError here = header and library disagree

@@ -47,7 +47,8 @@ struct DsbProblemArgs {
     int32_t free_running;      // 1: no stop time; step until t passes each point, then interpolate (the
                                // `while t < t_k { step() }; interpolate(t_k)` loop of ode_solver/mod.rs:132-141)
     int32_t quorum;            // warp scheduler: lanes that make a heavy block worth running (dsb_bdf_kernel.cuh)
-    int32_t coop_dense_only, reserved1;   // 1: the block-per-instance path always uses the blocked dense LU (test hook)
+    int32_t coop_dense_only, reserved1;   // 1: the block-per-instance path always uses the blocked dense LU (test hook);
+                                          // reserved1 != 0: the warp-per-instance banded kernel redoes every solve through its exact path (test hook)
     int32_t ncolors;
     int32_t color_of_col[DSB_MAX_STATES];      // colour index of every column
     uint64_t nz_rows_of_col[DSB_MAX_STATES];   // bit i set <=> (i, col) is in the sparsity pattern

@@ -563,7 +563,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
             if constexpr (NR > 0) {
                 // check for a root within the accepted step (bdf.rs:1566-1579), after the step-size update and before the
                 // stop time is handled; the interpolated state of the secant iteration goes to the (free) Newton residual
-                if (!first && !free_running) {   // the step()/interpolate() loop of the reference's harness (free_running) ignores RootFound: it steps on
+                if (!first) {   // also in the step()/interpolate() loop of the reference's harness (free_running), which returns interpolate(t_root) and ends (ode_solver/mod.rs:134-141)
                     double t_root = t;
                     stopped_on_root = rf.check_root(t, [&](double (&gv)[NR]) { M::root(vY, pl, t, gv); },
                                                     [&](double t_mid, double (&gv)[NR]) {
@@ -574,7 +574,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                         // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root)
                         // (bdf.rs:1228-1262), then -- without a reset function -- the state at the root in the next column
                         // (method.rs:493-503) and the end of the solve
-                        while (col < nt && bb.t_eval[col] <= t_root) {
+                        while (!free_running && col < nt && bb.t_eval[col] <= t_root) {
                             write_column(bb.t_eval[col], col);
                             ++col;
                         }
@@ -600,7 +600,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                                 write_column(t_root, col);
                                 ++col;
                             }
-                            t = t_root;
+                            if (!free_running) t = t_root;      // state_mut_back; the harness loop leaves the state at the end of the step
                             finish(DSB_STATUS_OK);
                         }
                     }

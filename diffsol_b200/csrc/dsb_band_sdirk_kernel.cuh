@@ -467,7 +467,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
             if constexpr (NR > 0) {
                 // check for a root within the accepted step (runge_kutta.rs:935-948), before the stop time is handled;
                 // the interpolated state of the secant iteration goes to the (free) Newton residual
-                if (!first && !free_running) {   // the step()/interpolate() loop of the reference's harness (free_running) ignores RootFound: it steps on
+                if (!first) {   // also in the step()/interpolate() loop of the reference's harness (free_running), which returns interpolate(t_root) and ends (ode_solver/mod.rs:134-141)
                     double t_root = t;
                     stopped_on_root = rf.check_root(t, [&](double (&gv)[NR]) { M::root(vY, pl, t, gv); },
                                                     [&](double t_mid, double (&gv)[NR]) {
@@ -477,7 +477,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                     if (stopped_on_root) {
                         // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root)
                         // (runge_kutta.rs:396-434), then the state at the root in the next column (method.rs:493-503)
-                        while (col < nt && bb.t_eval[col] <= t_root) {
+                        while (!free_running && col < nt && bb.t_eval[col] <= t_root) {
                             write_column(bb.t_eval[col], col);
                             ++col;
                         }
@@ -514,7 +514,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                                 write_column(t_root, col);
                                 ++col;
                             }
-                            t = t_root;
+                            if (!free_running) t = t_root;      // state_mut_back; the harness loop leaves the state at the end of the step
                             finish(DSB_STATUS_OK);
                         }
                     }

@@ -466,7 +466,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                 // check for a root within the accepted step (bdf.rs:1566-1579), after the step-size update and before
                 // the stop time is handled; RootFinder::check_root (root.rs:60-160) with Vector::root_finding
                 // (diffsol-la/src/vector/nalgebra_serial.rs:484-504)
-                if (!first && !free_running) {   // the step()/interpolate() loop of the reference's harness (free_running) ignores RootFound: it steps on
+                if (!first) {   // also in the step()/interpolate() loop of the reference's harness (free_running), which returns interpolate(t_root) and ends (ode_solver/mod.rs:134-141)
                     double pl[NP > 0 ? NP : 1], ys[N];
 #pragma unroll
                     for (int j = 0; j < NP; ++j) pl[j] = SP(j);
@@ -484,14 +484,14 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                         // (bdf.rs:1228-1262), then -- without a reset function -- the state at the root in the next column
                         // (method.rs:493-503) and the end of the solve
                         double yo[N];
-                        while (col < nt && bb.t_eval[col] <= t_root) {
+                        while (!free_running && col < nt && bb.t_eval[col] <= t_root) {
                             interpolate(bb.t_eval[col], yo);
 #pragma unroll
                             for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
                             ++col;
                         }
                         interpolate(t_root, yo);
-                        t = t_root;
+                        if (!free_running) t = t_root;      // state_mut_back; the harness loop leaves the state at the end of the step
                         bool ended = true;
                         if constexpr (dsb_model_has_reset<M>::value) {
                             if (!free_running) {

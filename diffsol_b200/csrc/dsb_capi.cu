@@ -55,7 +55,7 @@ struct dsb_batch {
     int last_launches = 0;
     bool have_timing = false;
     int sparsity_probe_jac_muls = 0;
-    DsbCoopState coop = {0, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, 0};
+    DsbCoopState coop = {0, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, nullptr};
 };
 
 namespace {
@@ -96,6 +96,22 @@ __global__ void dsb_to_instance_major_kernel(const double* __restrict__ src, dou
     for (int r = ty; r < 32; r += blockDim.y) {
         const int64_t b = b0 + r; const int j = j0 + tx;
         if (j < m && b < B) dst[b * m + j] = tile[tx][r];
+    }
+}
+__global__ void dsb_im_to_batch_major_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t B, int m) {
+    __shared__ double tile[32][33];
+    // src [B][m] -> dst [m][B], 32x32 tiles through shared memory so both sides are coalesced
+    const int64_t b0 = (int64_t)blockIdx.x * 32;
+    const int j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int r = ty; r < 32; r += blockDim.y) {
+        const int64_t b = b0 + r; const int j = j0 + tx;
+        if (j < m && b < B) tile[r][tx] = src[b * m + j];
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += blockDim.y) {
+        const int j = j0 + r; const int64_t b = b0 + tx;
+        if (j < m && b < B) dst[(int64_t)j * B + b] = tile[tx][r];
     }
 }
 __global__ void dsb_stats_to_host_layout_kernel(const int32_t* __restrict__ src, int64_t* __restrict__ dst, int64_t B,
@@ -270,7 +286,7 @@ int dsb_batch_free(dsb_batch* b) {
     cudaSetDevice(b->device);
     cudaFree(b->params); cudaFree(b->y0); cudaFree(b->dy0); cudaFree(b->h0);
     cudaFree(b->fin_t); cudaFree(b->fin_h); cudaFree(b->fin_order); cudaFree(b->root_idx); cudaFree(b->ncols);
-    cudaFree(b->stats); cudaFree(b->status); cudaFree(b->work_counter); cudaFree(b->coop.ws_mem); cudaFree(b->coop.atol_dev); cudaFree(b->coop.color_dev); cudaFree(b->t_eval); cudaFree(b->ys_own); cudaFree(b->stage);
+    cudaFree(b->stats); cudaFree(b->status); cudaFree(b->work_counter); cudaFree(b->coop.ws_mem); cudaFree(b->coop.atol_dev); cudaFree(b->coop.color_dev); cudaFree(b->coop.wb_mem); cudaFree(b->coop.ys_im_own); cudaFree(b->t_eval); cudaFree(b->ys_own); cudaFree(b->stage);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->ev_mid) cudaEventDestroy(b->ev_mid);
@@ -304,8 +320,10 @@ int dsb_batch_set_params_host(dsb_batch* b, const double* params, int64_t nbatch
     return DSB_OK;
 }
 
+// ys_im: instance-major buffer offered to kernels that write that layout (NULL: they use their own and the result is
+// re-laid out into ys_dev); *wrote_im (may be NULL) reports that the result is in ys_im and ys_dev was NOT written
 static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_t nt, double* ys_dev, void* stream_,
-                      int free_running) {
+                      int free_running, double* ys_im = nullptr, int* wrote_im = nullptr) {
     if (!b || !t_eval || nt < 1 || !ys_dev) return fail(DSB_BAD_ARG, "bad argument to dsb_batch_solve_dense");
     if (method != DSB_METHOD_BDF && method != DSB_METHOD_TR_BDF2 && method != DSB_METHOD_ESDIRK34)
         return fail(DSB_BAD_ARG, "unknown method");
@@ -332,6 +350,7 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     build_tableau(method, &pa.rk);
     pa.quorum = DSB_DEFAULT_QUORUM;
     if (const char* q = getenv("DSB_COOP_DENSE_ONLY")) pa.coop_dense_only = atoi(q);
+    if (const char* q = getenv("DSB_WBAND_FORCE_REDO")) pa.reserved1 = atoi(q);      // test hook (dsb_wband_bdf_kernel.cuh)
     if (const char* q = getenv("DSB_QUORUM")) { int v = atoi(q); if (v >= 1 && v <= 33) pa.quorum = v; }   // tuning knob
     DsbBatchBuffers bb;
     bb.params = b->params; bb.t_eval = b->t_eval; bb.y0 = b->y0; bb.dy0 = b->dy0; bb.h0 = b->h0;
@@ -351,10 +370,24 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     if (const char* q = getenv("DSB_EXEC_MODE")) b->coop.exec_mode = atoi(q);
     b->coop.color_host = color_full.empty() ? nullptr : color_full.data();
     b->coop.nz_host = nz_full.empty() ? nullptr : nz_full.data();      // test hook: 1 = lane kernels, 2 = cooperative
+    b->coop.ys_im = ys_im; b->coop.ys_im_used = nullptr;
+    if (wrote_im) *wrote_im = 0;
     cudaError_t lerr = g_launch_table[b->prob.model](&pa, &bb, method, stream, b->ev_mid, b->work_counter, &b->coop,
                                                      atol_full.data(), &b->last_launches);
-    if (lerr == cudaErrorNotSupported) return fail(DSB_ERR, "this method / execution mode is not available for this equation set (block-per-instance path: BDF only; banded path: BDF, banded ODE systems; root functions: BDF lane kernel only)");
+    if (lerr == cudaErrorNotSupported) return fail(DSB_ERR, "this execution mode is not available for this equation set and method (thread per instance: n <= 16; banded thread per instance: component-wise equations with a declared band, n > 16; banded warp per instance: the same, BDF, no reset function; block per instance: n <= 512)");
     if (lerr != cudaSuccess) return fail(DSB_ERR, std::string("kernel launch: ") + cudaGetErrorString(lerr));
+    if (b->coop.ys_im_used) {
+        // the kernel wrote the instance-major layout (warp-per-instance banded kernel)
+        if (ys_im && b->coop.ys_im_used == ys_im && wrote_im) {
+            *wrote_im = 1;
+        } else {
+            const int m = nt * b->prob.nout;
+            dim3 grid((unsigned)((b->B + 31) / 32), (unsigned)((m + 31) / 32)), block(32, 8);
+            dsb_im_to_batch_major_kernel<<<grid, block, 0, stream>>>(b->coop.ys_im_used, ys_dev, b->B, m);
+            DSB_CUDA(cudaGetLastError());
+            b->last_launches += 1;
+        }
+    }
     DSB_CUDA(cudaEventRecord(b->ev1, stream));
     b->have_timing = true;
     return DSB_OK;
@@ -369,13 +402,14 @@ int dsb_batch_step_and_interpolate(dsb_batch* b, int32_t method, const double* t
 }
 
 int dsb_batch_set_execution(dsb_batch* b, int32_t mode) {
-    if (!b || mode < 0 || mode > 3) return fail(DSB_BAD_ARG, "mode must be 0 (automatic), 1 (thread per instance), 2 (block per instance) or 3 (thread per instance, banded, state in global memory)");
+    if (!b || mode < 0 || mode > 4) return fail(DSB_BAD_ARG, "mode must be 0 (automatic), 1 (thread per instance), 2 (block per instance), 3 (thread per instance, banded, state in global memory) or 4 (warp per instance, banded, state in shared memory)");
     b->coop.exec_mode = mode;
     return DSB_OK;
 }
 
 int dsb_batch_get_stats_device(dsb_batch* b, int64_t* stats_dev, void* stream) {
     if (!b || !stats_dev) return fail(DSB_BAD_ARG, "NULL argument");
+    DSB_CUDA(cudaSetDevice(b->device));
     const int64_t total = b->B * DSB_NSTATS;
     dsb_stats_to_host_layout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         b->stats, stats_dev, b->B, b->sparsity_probe_jac_muls);
@@ -471,6 +505,9 @@ static int solve_host_impl(dsb_batch* b, int32_t method, const double* params_ho
                            const double* t_eval, int32_t nt, double* ys_host, int64_t* stats_host,
                            int32_t* status_host, int free_running) {
     if (!b || !ys_host) return fail(DSB_BAD_ARG, "NULL argument");
+    if (!t_eval || nt < 1) return fail(DSB_BAD_ARG, "t_eval must hold at least one time");
+    if (method != DSB_METHOD_BDF && method != DSB_METHOD_TR_BDF2 && method != DSB_METHOD_ESDIRK34)
+        return fail(DSB_BAD_ARG, "unknown method");
     DSB_CUDA(cudaSetDevice(b->device));
     const int n = b->prob.nout;                       // rows of a result column
     const size_t ys_bytes = (size_t)nt * n * b->B * 8;
@@ -491,9 +528,12 @@ static int solve_host_impl(dsb_batch* b, int32_t method, const double* params_ho
         if (rc != DSB_OK) return rc;
         ++extra;
     }
-    int rc = solve_impl(b, method, t_eval, nt, b->ys_own, nullptr, free_running);
+    int wrote_im = 0;
+    int rc = solve_impl(b, method, t_eval, nt, b->ys_own, nullptr, free_running, (double*)b->stage, &wrote_im);
     if (rc != DSB_OK) return rc;
-    {
+    if (wrote_im) {
+        DSB_CUDA(cudaMemcpyAsync(ys_host, b->stage, ys_bytes, cudaMemcpyDeviceToHost, 0));
+    } else {
         const int m = nt * n;
         dim3 grid((unsigned)((b->B + 31) / 32), (unsigned)((m + 31) / 32)), block(32, 8);
         dsb_to_instance_major_kernel<<<grid, block>>>(b->ys_own, (double*)b->stage, b->B, m);

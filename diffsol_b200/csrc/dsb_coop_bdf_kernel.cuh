@@ -764,7 +764,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                 t = t + hs;
                 h = new_h;
                 st.v[DSB_STAT_STEPS] += 1;
-                if constexpr (NR > 0) if (!free_running) {   // the step()/interpolate() loop of the reference's harness (free_running) ignores RootFound: it steps on
+                if constexpr (NR > 0) {   // also in the step()/interpolate() loop of the reference's harness (free_running), which returns interpolate(t_root) and ends (ode_solver/mod.rs:134-141)
                     // check for a root within the accepted step (runge_kutta.rs:935-948), before the stop time is handled
                     double t_root = t;
                     const bool stopped_on_root = rf.check_root(t, [&](double (&gv)[NR]) { M::root(ys, p, t, gv); },
@@ -775,7 +775,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                     if (stopped_on_root) {
                         // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root),
                         // then the state at the root in the next column (method.rs:493-503)
-                        while (col < nt && bb.t_eval[col] <= t_root) {
+                        while (!free_running && col < nt && bb.t_eval[col] <= t_root) {
                             (void)interpolate_and_write(bb.t_eval[col], col);
                             ++col;
                         }
@@ -811,7 +811,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                                 ++col;
                             }
                             __syncthreads();
-                            t = t_root;
+                            if (!free_running) t = t_root;      // state_mut_back; the harness loop leaves the state at the end of the step
                             step_result = 2;
                         }
                     }
@@ -1144,7 +1144,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                         jacobian_updates(new_h * pa.tab.alpha[order], DSB_STEP_SUCCESS);
                     }
                 }
-                if constexpr (NR > 0) if (!free_running) {   // the step()/interpolate() loop of the reference's harness (free_running) ignores RootFound: it steps on
+                if constexpr (NR > 0) {   // also in the step()/interpolate() loop of the reference's harness (free_running), which returns interpolate(t_root) and ends (ode_solver/mod.rs:134-141)
                     // check for a root within the accepted step (bdf.rs:1566-1579), after the step-size update and before
                     // the stop time is handled; the interpolated state of the secant iteration goes to the (free) vector yc
                     double t_root = t;
@@ -1158,7 +1158,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                         // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root)
                         // (bdf.rs:1228-1262), then -- without a reset function -- the state at the root in the next column
                         // (method.rs:493-503) and the end of the solve
-                        while (col < nt && bb.t_eval[col] <= t_root) {
+                        while (!free_running && col < nt && bb.t_eval[col] <= t_root) {
                             (void)interpolate_and_write(bb.t_eval[col], col);
                             ++col;
                         }
@@ -1204,7 +1204,7 @@ dsb_coop_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const
                                 ++col;
                             }
                             __syncthreads();
-                            t = t_root;
+                            if (!free_running) t = t_root;      // state_mut_back; the harness loop leaves the state at the end of the step
                             step_result = 2;
                         }
                     }

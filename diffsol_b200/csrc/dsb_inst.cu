@@ -14,6 +14,7 @@
 #include "dsb_launch.h"
 #include "dsb_models.h"
 #include "dsb_sdirk_kernel.cuh"
+#include "dsb_wband_bdf_kernel.cuh"
 
 #ifndef DSB_INST
 #error "compile with -DDSB_INST=<model id>"
@@ -201,6 +202,113 @@ template <class M> struct BandLauncher<M, true> {
     }
 };
 
+// warp-per-instance banded kernel (dsb_wband_bdf_kernel.cuh): BDF, band-capable equations without a reset function
+template <class M, bool BAND> struct WBandCapable : std::false_type {};
+template <class M> struct WBandCapable<M, true> : std::bool_constant<!dsb_model_has_reset<M>::value && WBandLayout<M>::FITS> {};
+constexpr bool kWBandCapable = WBandCapable<InstModel, kBandCapable>::value;
+
+template <class M, bool OK> struct WBandLauncher {
+    static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, cudaStream_t, cudaEvent_t, unsigned long long*, DsbCoopState*,
+                           const double*, int*) {
+        return cudaErrorNotSupported;
+    }
+};
+template <class M> struct WBandLauncher<M, true> {
+    static cudaError_t run(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, cudaStream_t stream, cudaEvent_t mid,
+                           unsigned long long* work_counter, DsbCoopState* coop, const double* atol_host, int* launches) {
+        typedef WBandLayout<M> Lay;
+        constexpr int N = M::N;
+        std::vector<int32_t> colmeta;
+        if (pa->use_coloring && !coop->color_host) return cudaErrorInvalidValue;
+        if (!dsb_host::band_column_meta<M>(pa->t0, pa->use_coloring != 0, coop->color_host, Lay::KL, Lay::KU, &colmeta))
+            return cudaErrorNotSupported;
+        cudaError_t e;
+        if (coop->atol_n < N) {
+            if (coop->atol_dev) cudaFree(coop->atol_dev);
+            coop->atol_dev = nullptr; coop->atol_n = 0;
+            e = cudaMalloc((void**)&coop->atol_dev, (size_t)N * sizeof(double));
+            if (e != cudaSuccess) return e;
+            coop->atol_n = N;
+        }
+        if (coop->color_bytes < (size_t)N * sizeof(int32_t)) {
+            if (coop->color_dev) cudaFree(coop->color_dev);
+            coop->color_dev = nullptr; coop->color_bytes = 0;
+            e = cudaMalloc(&coop->color_dev, (size_t)N * sizeof(int32_t));
+            if (e != cudaSuccess) return e;
+            coop->color_bytes = (size_t)N * sizeof(int32_t);
+        }
+        e = cudaMemcpyAsync(coop->atol_dev, atol_host, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(coop->color_dev, colmeta.data(), (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(stream);              // the host vectors die with this frame
+        if (e != cudaSuccess) return e;
+        const DsbBandMeta meta{coop->atol_dev, (const int32_t*)coop->color_dev};
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaMemsetAsync(work_counter, 0, 32 * sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return e;
+        if constexpr (M::HAS_MASS) {
+            // consistent initialisation of the DAE (state.rs:84-162) by the one-lane-per-instance kernel, which hands y, dy,
+            // the counters and the status over through the batch-major state arrays
+            constexpr int T = DSB_BAND_THREADS_SMALL;
+            typedef BandSdirkLayout<M, T> LayS;
+            const int64_t want = (pa->nbatch + T - 1) / T;
+            const unsigned igrid = (unsigned)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+            const size_t need = (size_t)LayS::WORDS * igrid * T * sizeof(double);
+            if (coop->ws_bytes < need) {
+                if (coop->ws_mem) cudaFree(coop->ws_mem);
+                coop->ws_mem = nullptr; coop->ws_bytes = 0;
+                e = cudaMalloc(&coop->ws_mem, need);
+                if (e != cudaSuccess) return e;
+                coop->ws_bytes = need;
+            }
+            dsb_band_init_kernel<M, T><<<igrid, T, 0, stream>>>(*pa, *bb, meta, (double*)coop->ws_mem);
+            *launches += 1;
+        }
+        const void* kernel = (const void*)dsb_wband_bdf_solve_dense_kernel<M>;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, Lay::THREADS, Lay::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        const int64_t want = (pa->nbatch + Lay::WARPS - 1) / Lay::WARPS;
+        const int64_t resident = (int64_t)sms * per_sm;
+        const unsigned grid = (unsigned)(want < resident ? want : resident);
+        const size_t need = (size_t)Lay::G_WORDS * grid * Lay::WARPS * sizeof(double) + 256;
+        if (coop->wb_bytes < need) {
+            if (coop->wb_mem) cudaFree(coop->wb_mem);
+            coop->wb_mem = nullptr; coop->wb_bytes = 0;
+            e = cudaMalloc(&coop->wb_mem, need);
+            if (e != cudaSuccess) return e;
+            coop->wb_bytes = need;
+        }
+        // the instance-major result block: the caller's, or our own
+        const size_t ys_bytes = (size_t)pa->nt * dsb_model_nout<M>::value * (size_t)pa->nbatch * sizeof(double);
+        double* ys_im = coop->ys_im;
+        if (!ys_im) {
+            if (coop->ys_im_own_bytes < ys_bytes) {
+                if (coop->ys_im_own) cudaFree(coop->ys_im_own);
+                coop->ys_im_own = nullptr; coop->ys_im_own_bytes = 0;
+                e = cudaMalloc((void**)&coop->ys_im_own, ys_bytes);
+                if (e != cudaSuccess) return e;
+                coop->ys_im_own_bytes = ys_bytes;
+            }
+            ys_im = coop->ys_im_own;
+        }
+        e = cudaMemsetAsync(ys_im, 0xFF, ys_bytes, stream);      // outputs never reached stay NaN
+        if (e != cudaSuccess) return e;
+        if (mid) cudaEventRecord(mid, stream);
+        dsb_wband_bdf_solve_dense_kernel<M><<<grid, Lay::THREADS, Lay::SMEM_BYTES, stream>>>(*pa, *bb, meta, (double*)coop->wb_mem, ys_im,
+                                                                                              work_counter);
+        *launches += 1;
+        coop->ys_im_used = ys_im;
+        return cudaGetLastError();
+    }
+};
+
 // lane kernels (one thread per instance): only instantiated for n <= 16
 template <class M, bool LANE> struct LaneLauncher {
     static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, int, cudaStream_t, cudaEvent_t, unsigned long long*, int*) {
@@ -216,8 +324,10 @@ template <class M> struct LaneLauncher<M, true> {
         const int threads = BdfLayout<M>::THREADS;
         const unsigned blocks = (unsigned)((pa->nbatch + threads - 1) / threads);
         const size_t smem = (size_t)BdfLayout<M>::WORDS * threads * sizeof(double);
-        static int resident_blocks = 0;      // persistent grid: as many blocks as fit on the device at once
-        if (resident_blocks == 0) {
+        // persistent grid: as many blocks as fit on THIS device at once.  Function attributes and occupancy are per
+        // device / context, and a process may drive several GPUs, so both are set and queried on every launch.
+        int resident_blocks = 0;
+        {
             cudaError_t e = cudaFuncSetAttribute(dsb_bdf_solve_dense_kernel<M>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
@@ -241,8 +351,8 @@ template <class M> struct LaneLauncher<M, true> {
         const int threads = SdirkLayout<M>::THREADS;
         const unsigned blocks = (unsigned)((pa->nbatch + threads - 1) / threads);
         const size_t smem = (size_t)SdirkLayout<M>::WORDS * threads * sizeof(double);
-        static int resident_blocks = 0;
-        if (resident_blocks == 0) {
+        int resident_blocks = 0;            // per launch, as above
+        {
             cudaError_t e = cudaFuncSetAttribute(dsb_sdirk_solve_dense_kernel<M>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
@@ -269,6 +379,14 @@ template <class M> struct LaneLauncher<M, true> {
 cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method,
                                                  cudaStream_t stream, cudaEvent_t mid, unsigned long long* work_counter,
                                                  DsbCoopState* coop, const double* atol_host, int* launches) {
+    coop->ys_im_used = nullptr;
+    // exec_mode 4 / automatic: the warp-per-instance banded kernel (BDF, no reset function)
+    if (kWBandCapable && method == DSB_METHOD_BDF && (coop->exec_mode == 4 || coop->exec_mode == 0)) {
+        const cudaError_t e = WBandLauncher<InstModel, kWBandCapable>::run(pa, bb, stream, mid, work_counter, coop, atol_host, launches);
+        if (e != cudaErrorNotSupported || coop->exec_mode == 4) return e;
+    } else if (coop->exec_mode == 4) {
+        return cudaErrorNotSupported;
+    }
     // exec_mode 3 / automatic: the banded lane kernels where the model qualifies (BDF and (E)SDIRK)
     if (kBandCapable && (coop->exec_mode == 3 || coop->exec_mode == 0)) {
         const cudaError_t e = BandLauncher<InstModel, kBandCapable>::run(pa, bb, method, stream, mid, work_counter, coop, atol_host, launches);

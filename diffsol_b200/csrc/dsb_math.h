@@ -102,6 +102,47 @@ struct DsbDivInline { static __device__ __forceinline__ double div(double a, dou
 DSB_HD double dsb_abs(double a) { return dsb_from_bits(dsb_bits(a) & 0x7fffffffffffffffULL); }
 DSB_HD bool dsb_isnan(double a) { return a != a; }
 
+// ---- reciprocal-reuse division: a / d from a stored r = RN(1 / d), bit-identical to the IEEE quotient -------------
+// The LU back-substitutions divide by the same diagonal in every Newton iteration between two factorisations, and the
+// factorisation already forms RN(1 / diag) (nalgebra scales the sub-column by it).  Given that reciprocal the
+// correctly rounded quotient takes 5 dependent operations instead of the ~10 (+ special-case test) of the full
+// routine -- what matters in the band substitutions, whose recurrences are pure dependency chains:
+//     q0 = RN(a r)                    relative error <= 2^-52 (two roundings)
+//     e0 = RN(a - q0 d)  (fma)        the residual, itself with relative error <= 2^-53 if it needs 54 bits
+//     q1 = RN(q0 + e0 r) (fma)        = RN(a/d + (a/d - q0) eps_r + ...): within 1/2 ulp + 2^-104 |a/d| of a/d, hence a
+//                                     FAITHFUL rounding of a/d
+//     e1 = a - q1 d      (fma)        exact: a faithful quotient's residual is representable
+//     q  = RN(q1 + e1 r) (fma)        = RN(a / d) by Markstein's theorem (P. Markstein, IBM J. R&D 34 (1990); Muller et
+//                                     al., Handbook of Floating-Point Arithmetic, section on division with an FMA):
+//                                     a faithful q1 and r = RN(1/d) give the correctly rounded quotient in any binade
+// The theorem needs every intermediate to stay normal: dsb_rcp() returns NaN unless |exponent(d)| <= 500, and
+// dsb_div_rcp() falls back to the plain division unless |exponent(a)| <= 500 (zero, subnormal, infinite and NaN
+// numerators take that path too, which also keeps the sign of a zero quotient) or when r is that NaN.  Checked against
+// `/` on random and adversarial operands on the host (tests/test_oracle_golden.py::test_div_rcp_bit_exact) and on the
+// device (tools/fp64_peak.cu).
+DSB_HD double dsb_rcp(double d) {
+    const uint32_t e = (uint32_t)(dsb_bits(d) >> 52) & 0x7ffu;
+    const double r = 1.0 / d;
+    return (e - (1023u - 500u) <= 1000u) ? r : dsb_from_bits(0x7ff8000000000000ULL);
+}
+// the fall-back is a real call so that the compiler cannot evaluate the full division speculatively and select
+DSB_HD_NOINLINE double dsb_div_full(double a, double d) { return a / d; }
+DSB_HD double dsb_div_rcp(double a, double d, double r) {
+    const uint32_t e = (uint32_t)(dsb_bits(a) >> 52) & 0x7ffu;
+    const double q0 = a * r;
+    const double e0 = dsb_fma(-q0, d, a);
+    const double q1 = dsb_fma(e0, r, q0);
+    const double e1 = dsb_fma(-q1, d, a);
+    const double q = dsb_fma(e1, r, q1);
+    if (!(e - (1023u - 500u) <= 1000u && q == q)) return dsb_div_full(a, d);
+    return q;
+}
+// r as dsb_rcp(d) would return it, from an already computed inv = 1.0 / d
+DSB_HD double dsb_rcp_from(double d, double inv) {
+    const uint32_t e = (uint32_t)(dsb_bits(d) >> 52) & 0x7ffu;
+    return (e - (1023u - 500u) <= 1000u) ? inv : dsb_from_bits(0x7ff8000000000000ULL);
+}
+
 // Core of dsb_pow for a positive, finite, NORMAL x (bits ix) and finite y: exp(y * log(x)) with log(x) as
 // a double-double (table of 128 sub-intervals, Tang-style) and a 128-entry 2^(j/128) table for exp.
 DSB_HD double dsb_pow_core(uint64_t ix, int sub, double y) {

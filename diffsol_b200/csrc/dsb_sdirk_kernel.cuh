@@ -390,7 +390,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
             bool reset_now = false;            // a reset was applied at a root: the stop time is set again, then R_STEP
             if constexpr (NR > 0) {
                 // check for a root within the accepted step (runge_kutta.rs:935-948), before the stop time is handled
-                if (!first && !free_running) {   // the step()/interpolate() loop of the reference's harness (free_running) ignores RootFound: it steps on
+                if (!first) {   // also in the step()/interpolate() loop of the reference's harness (free_running), which returns interpolate(t_root) and ends (ode_solver/mod.rs:134-141)
                     double pl[NP > 0 ? NP : 1], ys[N];
 #pragma unroll
                     for (int j = 0; j < NP; ++j) pl[j] = SP(j);
@@ -407,14 +407,14 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                         // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root)
                         // (runge_kutta.rs:396-434), then the state at the root in the next column (method.rs:493-503)
                         double yo[N];
-                        while (col < nt && bb.t_eval[col] <= t_root) {
+                        while (!free_running && col < nt && bb.t_eval[col] <= t_root) {
                             interpolate(bb.t_eval[col], yo);
 #pragma unroll
                             for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
                             ++col;
                         }
                         interpolate(t_root, yo);
-                        t = t_root;
+                        if (!free_running) t = t_root;      // state_mut_back; the harness loop leaves the state at the end of the step
                         bool ended = true;
                         if constexpr (dsb_model_has_reset<M>::value) {
                             if (!free_running) {

@@ -203,8 +203,9 @@ class BatchedSolver:
 
     def set_execution(self, mode):
         """'auto' | 'lane' (one thread per instance, n <= 16) | 'block' (one thread block per instance) |
-        'band' (one thread per instance, banded models of 16 < n <= 64, state in global memory)."""
-        capi.check(capi.lib().dsb_batch_set_execution(self._b, {"auto": 0, "lane": 1, "block": 2, "band": 3}[mode]))
+        'band' (one thread per instance, banded models of n > 16, state in global memory) |
+        'warp' (one warp per instance, banded models of n > 16, BDF, state in shared memory)."""
+        capi.check(capi.lib().dsb_batch_set_execution(self._b, {"auto": 0, "lane": 1, "block": 2, "band": 3, "warp": 4}[mode]))
         return self
 
     def set_params(self):

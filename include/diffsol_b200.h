@@ -135,10 +135,11 @@ int dsb_batch_new(const dsb_problem* p, int64_t nbatch, int32_t device, dsb_batc
 int dsb_batch_free(dsb_batch* b);
 int64_t dsb_batch_size(const dsb_batch* b);
 
-/* Execution model of the integrator kernels: 0 = automatic (one thread per instance for n <= 16; above, one thread
- * per instance with the state in global memory for banded models (ODE or singular-mass DAE, BDF or SDIRK), else one thread
- * block per instance), 1 = thread per instance, 2 = block per instance, 3 = banded thread per instance.  Results
- * are identical. */
+/* Execution model of the integrator kernels: 0 = automatic (one thread per instance for n <= 16; above, for banded
+ * models (ODE or singular-mass DAE), one WARP per instance with the state in shared memory for BDF and one thread per
+ * instance with the state in global memory for (E)SDIRK and for equations with a reset function; else one thread
+ * block per instance), 1 = thread per instance, 2 = block per instance, 3 = banded thread per instance, 4 = banded
+ * warp per instance.  Results are identical. */
 int dsb_batch_set_execution(dsb_batch* b, int32_t mode);
 
 /* Parameters, instance-major: params[b*nparams + j], exactly how the reference concatenates batched

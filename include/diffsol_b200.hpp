@@ -225,7 +225,7 @@ public:
     BatchedSolver(BatchedSolver&& o) noexcept : problem_(o.problem_), method_(o.method_), batch_(o.batch_) { o.batch_ = nullptr; }
     ~BatchedSolver() { if (batch_) dsb_batch_free(batch_); }
 
-    // 0 automatic, 1 one thread per instance (state on chip), 2 one block per instance, 3 banded lane kernels
+    // 0 automatic, 1 one thread per instance (state on chip), 2 one block per instance, 3 banded lane kernels, 4 banded warp-per-instance kernel
     BatchedSolver& set_execution(int32_t mode) { detail::check(dsb_batch_set_execution(batch_, mode), "dsb_batch_set_execution"); return *this; }
 
     // OdeSolverMethod::solve_dense (ode_solver/method.rs:721-848): tstop = t_eval.back(), dense output at every t_eval;
@@ -241,7 +241,7 @@ public:
     // The loop of the reference's test harness (ode_solver/mod.rs:104-194): step while |t| < |t_point|, interpolate
     DenseBlocks step_and_interpolate(const std::vector<double>& t_points) {
         if (t_points.empty()) throw DiffsolError(DSB_BAD_ARG, "step_and_interpolate: t_points is empty");
-        DenseBlocks ys(problem_->nbatch_, problem_->nstates_, (int32_t)t_points.size());
+        DenseBlocks ys(problem_->nbatch_, problem_->nout_, (int32_t)t_points.size());   // rows = outputs, as solve_dense
         detail::check(dsb_batch_step_and_interpolate_host(batch_, method_, problem_->params_.empty() ? nullptr : problem_->params_.data(),
                                                           problem_->nparams_, t_points.data(), (int32_t)t_points.size(), ys.data(), nullptr, nullptr),
                       "dsb_batch_step_and_interpolate_host");

@@ -133,7 +133,8 @@ int orc_solve_dense(const orc_problem_desc* d, const double* p, int np, const do
 }
 
 // The reference's test harness `test_ode_solver(.., use_tstop = false)` (ode_solver/mod.rs:104-194):
-// for each point: step while |t| < |t_point|, then interpolate(t_point).  out is n x npts.
+// for each point: step while |t| < |t_point|, then interpolate(t_point); a step that reports RootFound ends the loop with
+// interpolate(t_root) in that point's column (the later columns keep what the caller put there).  out is n x npts.
 int orc_harness(const orc_problem_desc* d, const double* p, int np, const double* t_points, int npts,
                 double* out, int64_t* stats, double* fin) {
     Problem pr;
@@ -142,12 +143,20 @@ int orc_harness(const orc_problem_desc* d, const double* p, int np, const double
     std::unique_ptr<Method> m(make_method(pr, d->method, &err));
     if (!m) { export_stats(pr, nullptr, stats); return err; }
     const int n = pr.n();
-    for (int k = 0; k < npts && !err; ++k) {
+    bool ended_on_root = false;
+    for (int k = 0; k < npts && !err && !ended_on_root; ++k) {
         while (std::fabs(m->t()) < std::fabs(t_points[k])) {
             StopReason r = m->step(&err);
             if (r == STEP_ERROR) break;
+            if (r == ROOT_FOUND) {
+                // `if let RootFound(t, _) = method.step() { return method.interpolate(t) }` (ode_solver/mod.rs:134-141):
+                // the state at the root takes the place of the point the loop was stepping towards, and the test ends
+                err = m->interpolate(m->root_t(), out + (size_t)k * n);
+                ended_on_root = true;
+                break;
+            }
         }
-        if (err) break;
+        if (err || ended_on_root) break;
         err = m->interpolate(t_points[k], out + (size_t)k * n);
     }
     export_stats(pr, m.get(), stats);

@@ -88,9 +88,11 @@ class ProblemDesc(ctypes.Structure):
 
 
 def build(force=False):
-    """Compile the oracle with the recipe committed in oracle/Makefile."""
-    if force or not os.path.exists(_LIB_PATH):
-        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []))
+    """Compile the oracle with the recipe committed in oracle/Makefile (make rebuilds only when a source is newer than
+    the library, so a stale library never outlives an edit of the restatement)."""
+    import shutil
+    if force or not os.path.exists(_LIB_PATH) or shutil.which("make"):
+        subprocess.check_call(["make", "-s", "-C", _HERE] + (["-B"] if force else []))
     return _LIB_PATH
 
 

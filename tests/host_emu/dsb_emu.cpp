@@ -15,6 +15,7 @@
 #include "../../diffsol_b200/csrc/dsb_bdf_kernel.cuh"
 #include "../../diffsol_b200/csrc/dsb_init_kernel.cuh"
 #include "../../diffsol_b200/csrc/dsb_sdirk_kernel.cuh"
+#include "../../diffsol_b200/csrc/dsb_wband_bdf_kernel.cuh"
 
 double dsb_lane_smem[1 << 20];      // the "shared memory" of the emulated block (word w of lane 0 at w * THREADS)
 
@@ -37,6 +38,7 @@ struct EmuCall {
         pa.free_running = free_running;
         dsb_host::build_tableau(method, &pa.rk);
         pa.quorum = DSB_DEFAULT_QUORUM;
+        if (const char* q = getenv("DSB_WBAND_FORCE_REDO")) pa.reserved1 = atoi(q);
         std::vector<double> atol_full(N);
         for (int i = 0; i < N; ++i) atol_full[i] = pr->atol.size() == 1 ? pr->atol[0] : pr->atol[i];
         constexpr int NOUT = dsb_model_nout<M>::value;
@@ -81,6 +83,29 @@ struct EmuCall {
                     else dsb_band_sdirk_solve_dense_kernel<M, T>(pa, bb, meta, ws.data(), &work_counter);
                     ran = true;
                 }
+            } else if (kernel == 4) {
+                // warp-per-instance banded kernel with ONE lane per warp (DSB_WLANES = 1 on the host): same source, same
+                // arithmetic; with one instance the instance-major result block is the batch-major one
+                if constexpr (dsb_declares_band<M>::value && dsb_is_componentwise<M>::value && N > 16 && !dsb_model_has_reset<M>::value) {
+                    typedef WBandLayout<M> LayW;
+                    if (method == DSB_METHOD_BDF) {
+                        std::vector<int32_t> colmeta;
+                        if (!dsb_host::band_column_meta<M>(pa.t0, pa.use_coloring != 0, color_full.empty() ? nullptr : color_full.data(),
+                                                           LayW::KL, LayW::KU, &colmeta)) { rc = DSB_ERR; return; }
+                        const DsbBandMeta meta{atol_full.data(), colmeta.data()};
+                        if constexpr (M::HAS_MASS) {
+                            constexpr int T = DSB_BAND_THREADS_SMALL;
+                            typedef BandSdirkLayout<M, T> Lay;
+                            blockDim.x = Lay::THREADS;
+                            std::vector<double> ws((size_t)Lay::WORDS * Lay::THREADS);
+                            dsb_band_init_kernel<M, T>(pa, bb, meta, ws.data());
+                        }
+                        blockDim.x = LayW::THREADS;
+                        std::vector<double> slots((size_t)LayW::G_WORDS * LayW::WARPS + 16);
+                        dsb_wband_bdf_solve_dense_kernel<M>(pa, bb, meta, slots.data(), bb.ys, &work_counter);
+                        ran = true;
+                    }
+                }
             }
             if (!ran) { rc = DSB_ERR; return; }
             for (int k = 0; k < nt; ++k)
@@ -96,11 +121,31 @@ struct EmuCall {
 
 }  // namespace
 
+// SmemBandLU (dsb_wband_bdf_kernel.cuh) on a dense column-major n x n matrix whose entries outside the band (kl, ku) are
+// ignored: band storage, factor, then solve b in place.  mode 0: the fast back substitution (the interchange-free
+// forward sweep when the factorisation did not interchange), 1: the exact form.  Returns 0 for a zero pivot, else what
+// solve() returned (1, or 2 = a quotient could not be vouched for); *nswaps = row interchanges.
+template <int N, int KL, int KU>
+static int emu_band_lu_run(const double* A, double* b, int mode, int* nswaps) {
+    constexpr int NS = (N + 1) & ~1, KV = KL + KU, LDAB = 2 * KL + KU + 1;
+    typedef SmemBandLU<N, NS, KL, KU> BLU;
+    std::vector<double> ab((size_t)LDAB * NS, 0.0), rcp(NS, 0.0);
+    std::vector<int> piv(NS, 0);
+    for (int j = 0; j < N; ++j)
+        for (int i = 0; i < N; ++i)
+            if (i - j <= KL && j - i <= KU) ab[(size_t)(KV + i - j) * NS + j] = A[(size_t)j * N + i];
+    const int nzero = BLU::factor(ab.data(), piv.data(), rcp.data(), nswaps);
+    if (nzero) return 0;
+    if (mode == 1) return BLU::template solve<true, true>(ab.data(), piv.data(), rcp.data(), b);
+    return *nswaps ? BLU::template solve<false, true>(ab.data(), piv.data(), rcp.data(), b)
+                   : BLU::template solve<false, false>(ab.data(), piv.data(), rcp.data(), b);
+}
+
 extern "C" {
 
 void dsb_options_default(dsb_options* o);   // defined below (the same defaults as dsb_capi.cu, problem.rs:132-152)
 
-// kernel: 1 = on-chip lane kernels (n <= 16), 3 = banded lane kernels
+// kernel: 1 = on-chip lane kernels (n <= 16), 3 = banded lane kernels, 4 = banded warp-per-instance kernel (one lane per warp)
 int emu_solve(int model, int method, int kernel, double rtol, const double* atol, int natol, double t0, double h0,
               int use_coloring, const dsb_options* opt, const double* params, int64_t B, const double* t_eval, int nt,
               int free_running, double* ys, int64_t* stats, int32_t* status, double* fin, int32_t* root_idx, int32_t* ncols) {
@@ -114,6 +159,16 @@ int emu_solve(int model, int method, int kernel, double rtol, const double* atol
     EmuCall call{&pr, method, kernel, free_running, params, B, t_eval, nt, ys, stats, status, fin, root_idx, ncols, DSB_ERR};
     dsb_dispatch_model(model, call);
     return call.rc;
+}
+
+int emu_smem_band_lu(int n, int kl, int ku, const double* A, double* b, int mode, int* nswaps) {
+    if (n == 24 && kl == 1 && ku == 1) return emu_band_lu_run<24, 1, 1>(A, b, mode, nswaps);
+    if (n == 24 && kl == 2 && ku == 1) return emu_band_lu_run<24, 2, 1>(A, b, mode, nswaps);
+    if (n == 24 && kl == 1 && ku == 2) return emu_band_lu_run<24, 1, 2>(A, b, mode, nswaps);
+    if (n == 24 && kl == 2 && ku == 2) return emu_band_lu_run<24, 2, 2>(A, b, mode, nswaps);
+    if (n == 7 && kl == 2 && ku == 2) return emu_band_lu_run<7, 2, 2>(A, b, mode, nswaps);
+    if (n == 41 && kl == 1 && ku == 1) return emu_band_lu_run<41, 1, 1>(A, b, mode, nswaps);
+    return -1;
 }
 
 // the product's host-side greedy colouring (dsb_host_setup.h) on a given pattern

@@ -18,7 +18,7 @@ _OUT = os.path.join(_HERE, "_build")
 _LIB = os.path.join(_OUT, "libdsb_emu.so")
 NSTATS = 16
 METHODS = {"bdf": 0, "tr_bdf2": 1, "esdirk34": 2}
-KERNELS = {"lane": 1, "band": 3}
+KERNELS = {"lane": 1, "band": 3, "warp": 4}
 
 
 class Options(ctypes.Structure):
@@ -73,6 +73,8 @@ def lib():
                                 ctypes.POINTER(ctypes.c_int32), dp, ctypes.POINTER(ctypes.c_int32),
                                 ctypes.POINTER(ctypes.c_int32)]
         L.dsb_options_default.argtypes = [ctypes.POINTER(Options)]
+        L.emu_smem_band_lu.restype = ctypes.c_int
+        L.emu_smem_band_lu.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
         _lib = L
     return _lib
 
@@ -121,3 +123,13 @@ def greedy_coloring(non_zeros, n):
     rc = lib().emu_greedy_coloring(rows.ctypes.data_as(ip), cols.ctypes.data_as(ip), len(rows), int(n), out.ctypes.data_as(ip))
     assert rc == 0
     return out.tolist()
+
+
+def smem_band_lu(A, kl, ku, b, exact=False):
+    """SmemBandLU (the warp-per-instance kernel's band LU) on the band (kl, ku) of the dense matrix A -> (rc, x, nswaps)."""
+    n = A.shape[0]
+    Af = np.asfortranarray(A, dtype=np.float64)
+    x = np.array(b, dtype=np.float64)
+    nsw = ctypes.c_int(0)
+    rc = lib().emu_smem_band_lu(n, kl, ku, _dp(Af), _dp(x), 1 if exact else 0, ctypes.byref(nsw))
+    return rc, x, nsw.value

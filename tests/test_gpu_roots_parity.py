@@ -243,18 +243,25 @@ def test_battery_cycling_with_resets_bit_exact(dsb, oracle, method, execution):
 
 @pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
 @pytest.mark.parametrize("execution", ["lane", "block"])
-def test_harness_loop_ignores_roots(dsb, oracle, method, execution):
-    """The step()/interpolate() loop of the reference's harness (ode_solver/mod.rs:132-141) does not look at the stop
-    reason: with a root function the loop steps on past the root.  step_and_interpolate does the same."""
+def test_harness_loop_stops_at_the_root(dsb, oracle, method, execution):
+    """The step()/interpolate() loop of the reference's harness (ode_solver/mod.rs:132-141): `if let RootFound(t, _) =
+    method.step() { return method.interpolate(t) }` -- the state at the root takes the place of the point the loop was
+    stepping towards and the loop ends (the solver's own state stays at the end of that step).  step_and_interpolate does
+    the same: the later columns stay NaN, root_info() says which root and how many columns."""
     pts = np.arange(0.0, 10.0)
-    solver = getattr(dsb.OdeBuilder().rhs_implicit("exp_decay_root").p([[0.1, 1.0], [0.2, 1.5]]).build(), method)().set_execution(execution)
+    params = [[0.1, 1.0], [0.2, 1.5], [0.01, 1.0]]          # the last one does not reach its root before t = 9
+    solver = getattr(dsb.OdeBuilder().rhs_implicit("exp_decay_root").p(params).build(), method)().set_execution(execution)
     ys = solver.step_and_interpolate(pts)
+    root_idx, ncols = solver.root_info()
     desc = oracle.make_desc("exp_decay_root", method=method, powmode=1)
-    for b, p in enumerate([[0.1, 1.0], [0.2, 1.5]]):
+    for b, p in enumerate(params):
         rc, ys_o, stats_o, fin = oracle.harness(desc, p, pts)
         assert rc == 0 and solver.status()[b] == 0
-        assert np.array_equal(ys[b], ys_o) and solver.get_statistics(b) == stats_o
-    assert (solver.root_info()[0] == -1).all()
+        assert np.array_equal(ys[b], ys_o, equal_nan=True) and solver.get_statistics(b) == stats_o
+        assert solver.final_state()[0][b] == fin["t"]
+        written = int(np.isfinite(ys_o[:, 0]).sum())
+        assert ncols[b] == written and (root_idx[b] >= 0) == (written < len(pts))
+    assert list(root_idx >= 0) == [True, True, False]
 
 
 def test_root_info_without_roots(dsb):

@@ -123,6 +123,80 @@ def test_battery_voltage_cut_off_in_the_band_kernels_on_host(oracle, model, meth
     assert stopped.sum() > 0
 
 
+# ---- the warp-per-instance banded kernel (dsb_wband_bdf_kernel.cuh), built with one lane per warp ------------------------
+@pytest.mark.parametrize("model,B,coloring", [("spm", 12, False), ("spm", 12, True), ("spm99", 3, True)])
+def test_warp_band_bdf_kernel_on_host(oracle, model, B, coloring):
+    r, *o = run_both(oracle, model, spm_currents(B), np.arange(1, 7) * 600.0, kernel="warp", use_coloring=coloring)
+    assert (o[2] == 0).all()
+    assert_same(r, *o)
+
+
+@pytest.mark.parametrize("model,B,coloring", [("heat1d_dae_32", 10, False), ("heat1d_dae_32", 10, True), ("heat1d_dae_256", 2, True),
+                                               ("heat1d_dae_32_bc", 6, True)])
+def test_warp_band_dae_kernel_on_host(oracle, model, B, coloring):
+    r, *o = run_both(oracle, model, heat_params(B), np.arange(1, 101) / 100.0 * 0.99, kernel="warp", use_coloring=coloring,
+                     rtol=1e-6, atol=1e-6)
+    assert (o[2] == 0).all()
+    assert_same(r, *o)
+
+
+@pytest.mark.parametrize("n,kl,ku", [(24, 1, 1), (24, 2, 1), (24, 1, 2), (24, 2, 2), (7, 2, 2), (41, 1, 1)])
+def test_smem_band_lu_matches_the_dense_restatement(oracle, n, kl, ku):
+    """The band LU of the warp-per-instance kernel (row-per-diagonal band storage, one-lane recurrences, reciprocal-reuse back
+    substitution) against the oracle's dense nalgebra LU on random banded matrices that DO interchange rows, on diagonally
+    dominant ones that do not (the interchange-free forward sweep), with right-hand sides that span the whole exponent range
+    (the in-place plain division for numerators outside the fast quotient's proven range, signed zeros), and singular ones."""
+    import ctypes
+    rng = np.random.default_rng(1000 * n + 10 * kl + ku)
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    seen_swaps = seen_noswaps = 0
+    for trial in range(300):
+        A = np.zeros((n, n))
+        for i in range(n):
+            for j in range(max(0, i - kl), min(n, i + ku + 1)):
+                A[i, j] = rng.standard_normal() * 10.0 ** rng.integers(-3, 4)
+        if trial % 3 == 0:
+            A[np.arange(n), np.arange(n)] += 1e5                      # no interchanges
+        b = rng.standard_normal(n) * 10.0 ** rng.integers(-8, 9, n)
+        if trial % 4 == 1:
+            b = b * 10.0 ** rng.choice([-310.0, -250.0, -160.0, 0.0, 120.0, 250.0, 290.0], n)
+            b[rng.integers(0, n, 3)] = [0.0, -0.0, 5e-324]
+        if trial % 50 == 49:
+            A[:, n // 2] = 0.0                                          # a zero column: LuSolveFailed
+        Af = np.asfortranarray(A)
+        x_o = b.copy()
+        with np.errstate(all="ignore"):
+            rc_o = oracle.lib().orc_lu_solve(dp(Af), n, dp(x_o))
+        for exact in (False, True):
+            rc, x, nsw = emu.smem_band_lu(A, kl, ku, b, exact=exact)
+            if rc_o != 0:
+                assert rc == 0
+                continue
+            assert rc in (1, 2)
+            if rc == 1:
+                assert np.array_equal(x.view(np.int64), x_o.view(np.int64)), (trial, exact)
+            assert not (exact and rc == 2)
+            seen_swaps += nsw > 0
+            seen_noswaps += nsw == 0
+    assert seen_swaps > 100 and seen_noswaps > 100
+
+
+def test_warp_band_exact_solve_path_on_host(oracle, monkeypatch):
+    """The back substitution's fall-back (right-hand side rebuilt, plain IEEE divisions) forced on every Newton iteration."""
+    monkeypatch.setenv("DSB_WBAND_FORCE_REDO", "1")
+    r, *o = run_both(oracle, "heat1d_dae_32", heat_params(6), np.arange(1, 101) / 100.0 * 0.99, kernel="warp", rtol=1e-6, atol=1e-6)
+    assert_same(r, *o)
+    r, *o = run_both(oracle, "spm", spm_currents(6), np.arange(1, 7) * 600.0, kernel="warp", use_coloring=True)
+    assert_same(r, *o)
+
+
+@pytest.mark.parametrize("model,B", [("spm_stop", 24), ("spm99_stop", 3)])
+def test_battery_voltage_cut_off_in_the_warp_band_kernel_on_host(oracle, model, B):
+    r, o = run_both_roots(oracle, model, spm_currents(B), np.arange(1, 121) * 30.0, method="bdf", kernel="warp", use_coloring=True)
+    stopped = assert_same_roots(r, o)
+    assert stopped.sum() > 0
+
+
 @pytest.mark.parametrize("method", ["bdf", "tr_bdf2"])
 @pytest.mark.parametrize("coloring", [False, True])
 def test_band_dae_inconsistent_initial_values_on_host(oracle, method, coloring):
@@ -211,17 +285,21 @@ def test_reset_in_the_band_kernels_on_host(oracle, method):
 
 
 @pytest.mark.parametrize("method", ["bdf", "tr_bdf2", "esdirk34"])
-def test_harness_loop_ignores_roots_on_host(oracle, method):
-    """The step()/interpolate() loop of the reference's harness (ode_solver/mod.rs:132-141) does not look at the stop
-    reason: with a root function the solver reports RootFound and the loop steps on.  step_and_interpolate does the same."""
+def test_harness_loop_stops_at_the_root_on_host(oracle, method):
+    """The step()/interpolate() loop of the reference's harness (ode_solver/mod.rs:132-141) returns interpolate(t_root) for
+    the point it was stepping towards when a step reports RootFound, and ends; without a root before the last point it
+    runs through.  step_and_interpolate does the same."""
     pts = np.arange(0.0, 10.0)
     desc = oracle.make_desc("exp_decay_root", method=method, powmode=1)
-    rc, ys_o, stats_o, fin = oracle.harness(desc, [0.1, 1.0], pts)
-    assert rc == 0
-    r = emu.solve(oracle.MODELS["exp_decay_root"], 2, 2, [[0.1, 1.0]], pts, method=method, free_running=True)
-    assert r["status"][0] == 0 and np.array_equal(r["ys"][0], ys_o)
-    assert {n: int(r["stats"][0, i]) for i, n in enumerate(oracle.S_NAMES)} == stats_o
-    assert r["fin"][0, 0] == fin["t"] and fin["t"] >= 9.0
+    for p, stops in (([0.1, 1.0], True), ([0.01, 1.0], False)):
+        rc, ys_o, stats_o, fin = oracle.harness(desc, p, pts)
+        assert rc == 0
+        r = emu.solve(oracle.MODELS["exp_decay_root"], 2, 2, [p], pts, method=method, free_running=True)
+        assert r["status"][0] == 0 and np.array_equal(r["ys"][0], ys_o, equal_nan=True)
+        assert {n: int(r["stats"][0, i]) for i, n in enumerate(oracle.S_NAMES)} == stats_o
+        assert r["fin"][0, 0] == fin["t"]
+        written = int(np.isfinite(ys_o[:, 0]).sum())
+        assert (written < len(pts)) == stops and r["ncols"][0] == written and (r["root_idx"][0] >= 0) == stops
 
 
 COLORING_CASES = [      # jacobian/mod.rs:483-513 build_coloring: (row, col) patterns of 2 x 2 operators and their colourings

@@ -58,6 +58,7 @@ for it in range(3):
     t0 = time.perf_counter()
     ys = solver.solve_dense(t_eval)
     times.append((time.perf_counter() - t0, solver.last_kernel_ms()))
+integ_ms = solver.last_integrator_ms()
 st = solver.statistics_array()
 status = solver.status()
 kms = min(k for _, k in times[1:])
@@ -74,7 +75,7 @@ if which.startswith("spm") or which.startswith("heat"):
     band_mass = ldj * n if which.startswith("heat") else 0
     band = (nli * 8 * (ldab * n + n + 4 * n + npar) + setups * 8 * (ldj * n + band_mass + ldab * n + n)
             + me * 8 * (ldj * n + n + npar) + attempts * 8 * 19 * n + B * nt * 8 * prob.nout)
-print(json.dumps({"config": which, "n": n, "batch": B, "kernel_ms": kms, "e2e_ms": min(t for t, _ in times[1:]) * 1e3,
+print(json.dumps({"config": which, "n": n, "batch": B, "kernel_ms": kms, "integrator_ms": integ_ms, "e2e_ms": min(t for t, _ in times[1:]) * 1e3,
                   "instances_per_s": B / kms * 1e3, "newton_iters_per_s": nli / kms * 1e3,
                   "steps_mean": float(st[:, 6].mean()), "nli_mean": float(st[:, 8].mean()), "setups_mean": float(st[:, 0].mean()),
                   "failed": int((status != 0).sum()), "stopped_on_root": int((solver.root_info()[0] >= 0).sum()), "algorithmic_GB": alg / 1e9,
