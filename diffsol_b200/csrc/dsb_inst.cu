@@ -206,6 +206,13 @@ template <class M> struct BandLauncher<M, true> {
 template <class M, bool BAND> struct WBandCapable : std::false_type {};
 template <class M> struct WBandCapable<M, true> : std::bool_constant<!dsb_model_has_reset<M>::value && WBandLayout<M>::FITS> {};
 constexpr bool kWBandCapable = WBandCapable<InstModel, kBandCapable>::value;
+// automatic selection: the warp-per-instance kernel for the larger systems (difference array in its global-memory slot,
+// n >~ 100), where shared memory buys it what the lane-per-instance kernel loses to global-memory latency; small
+// systems (n = 42: 16 resident warps of a 100 KB kernel, instruction-fetch bound) stay with one lane per instance
+// (measured on B200, 250 000 instances: n = 42 288 vs 230 ms, n = 200 828 vs 1113 ms, n = 256 DAE 107 vs 374 ms)
+template <class M, bool OK> struct WBandPreferred : std::false_type {};
+template <class M> struct WBandPreferred<M, true> : std::bool_constant<!WBandLayout<M>::D_SHARED> {};
+constexpr bool kWBandPreferred = WBandPreferred<InstModel, kWBandCapable>::value;
 
 template <class M, bool OK> struct WBandLauncher {
     static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, cudaStream_t, cudaEvent_t, unsigned long long*, DsbCoopState*,
@@ -381,7 +388,7 @@ cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const
                                                  DsbCoopState* coop, const double* atol_host, int* launches) {
     coop->ys_im_used = nullptr;
     // exec_mode 4 / automatic: the warp-per-instance banded kernel (BDF, no reset function)
-    if (kWBandCapable && method == DSB_METHOD_BDF && (coop->exec_mode == 4 || coop->exec_mode == 0)) {
+    if (kWBandCapable && method == DSB_METHOD_BDF && (coop->exec_mode == 4 || (coop->exec_mode == 0 && kWBandPreferred))) {
         const cudaError_t e = WBandLauncher<InstModel, kWBandCapable>::run(pa, bb, stream, mid, work_counter, coop, atol_host, launches);
         if (e != cudaErrorNotSupported || coop->exec_mode == 4) return e;
     } else if (coop->exec_mode == 4) {

@@ -142,6 +142,29 @@ DSB_HD double dsb_rcp_from(double d, double inv) {
     const uint32_t e = (uint32_t)(dsb_bits(d) >> 52) & 0x7ffu;
     return (e - (1023u - 500u) <= 1000u) ? inv : dsb_from_bits(0x7ff8000000000000ULL);
 }
+// The band back substitution of the warp-per-instance kernel (dsb_wband_bdf_kernel.cuh) splits the exponent budget
+// unevenly -- pivots are O(1)-ish, right-hand sides span the far field of diffusion fronts: |exponent(d)| <= 100 and
+// exponent(a) in [-920, 900] keep the quotient normal (>= -1020) and the residual a - q d exact (its last bit is
+// 2^(exponent(a) - 104) >= 2^-1074).
+DSB_HD double dsb_rcp_from_narrow(double d, double inv) {
+    const uint32_t e = (uint32_t)(dsb_bits(d) >> 52) & 0x7ffu;
+    return (e - (1023u - 100u) <= 200u) ? inv : dsb_from_bits(0x7ff8000000000000ULL);
+}
+// |q| with the sign bit of (a ^ d): one logic operation on the high word (the compiler would otherwise take |q| on the
+// FP64 pipe, 8 cycles on the dependency chain)
+DSB_HD double dsb_quotient_sign(double q, double a, double d) {
+#if defined(__CUDA_ARCH__)
+    const int sgn = (__double2hiint(a) ^ __double2hiint(d)) & (int)0x80000000;
+    return __hiloint2double((__double2hiint(q) & 0x7fffffff) | sgn, __double2loint(q));
+#else
+    const uint64_t sgn = (dsb_bits(a) ^ dsb_bits(d)) & 0x8000000000000000ULL;
+    return dsb_from_bits((dsb_bits(q) & 0x7fffffffffffffffULL) | sgn);
+#endif
+}
+DSB_HD bool dsb_numerator_in_wide_range(double a) {         // exponent(a) in [-920, 900]: zero, subnormals, infinities, NaNs are out
+    const uint32_t hi = (uint32_t)(dsb_bits(a) >> 32) & 0x7ff00000u;
+    return hi - ((1023u - 920u) << 20) <= ((920u + 900u) << 20);
+}
 
 // Core of dsb_pow for a positive, finite, NORMAL x (bits ix) and finite y: exp(y * log(x)) with log(x) as
 // a double-double (table of 128 sub-intervals, Tang-style) and a 128-entry 2^(j/128) table for exp.
@@ -276,11 +299,14 @@ DSB_HD double dsb_powi(double a, int b) {
 }
 
 // ---- exp / log / tanh / asinh for model output and event functions (the battery model's terminal voltage) ----------
+// Real calls on the device (one copy each): the voltage expression uses ~20 of them and is evaluated from several places
+// of an integrator kernel; inlined everywhere the warp-per-instance kernel grew to 27 k SASS instructions and spent 85 %
+// of its stall samples waiting for instruction fetch (profiles/r2_wband_spm_stop_inlined_math_hotspots.txt).
 // Same tables and the same IEEE-only operation sequences as dsb_pow_core, so host and device agree bit for bit.  They
 // are NOT correctly rounded (exp and log: below 1 ulp; tanh and asinh: absolute error of a few 1e-16, relative error
 // that grows for |x| << 1), which is all an event threshold on a voltage needs; parity with the reference's libm
 // values is a tolerance, parity between the oracle and the kernels is exact.
-DSB_HD double dsb_exp(double x) {
+DSB_HD_NOINLINE double dsb_exp(double x) {
     const double inf = dsb_from_bits(0x7ff0000000000000ULL);
     if (x != x) return x;
     if (x > 709.8) return inf;
@@ -308,7 +334,7 @@ DSB_HD double dsb_exp(double x) {
 }
 // natural logarithm of a positive, finite, normal x (anything else: NaN for x < 0 or NaN, -inf for 0, x for +inf;
 // subnormals are scaled first)
-DSB_HD double dsb_log(double x) {
+DSB_HD_NOINLINE double dsb_log(double x) {
     const double inf = dsb_from_bits(0x7ff0000000000000ULL);
     if (x != x || x < 0.0) return dsb_from_bits(0x7ff8000000000000ULL);
     if (x == 0.0) return -inf;
@@ -359,7 +385,7 @@ DSB_HD double dsb_log(double x) {
     lo = lo + tail;
     return t3 + lo;
 }
-DSB_HD double dsb_tanh(double x) {
+DSB_HD_NOINLINE double dsb_tanh(double x) {
     if (x != x) return x;
     const double a = dsb_abs(x);
     if (a < 1e-8) return x;
@@ -367,7 +393,7 @@ DSB_HD double dsb_tanh(double x) {
     if (a < 20.0) r = 1.0 - 2.0 / (dsb_exp(2.0 * a) + 1.0);
     return x < 0.0 ? -r : r;
 }
-DSB_HD double dsb_asinh(double x) {
+DSB_HD_NOINLINE double dsb_asinh(double x) {
     if (x != x) return x;
     const double a = dsb_abs(x);
     if (a < 1e-8) return x;

@@ -433,6 +433,7 @@ struct ModelSpmT {
     static constexpr bool HAS_MASS = false;
     static constexpr bool COMPONENTWISE = true;
     static constexpr int BAND_KL = 1, BAND_KU = 1;      // df/dy is tridiagonal (checked against the probed pattern at launch)
+    static constexpr int WBAND_MAX_WARPS = 8;           // warp-per-instance kernel: 255 registers per lane (dsb_wband_bdf_kernel.cuh)
     template <class X>
     DSB_HD static double diffusion_i(int i, const X& x) {        // i in 2 .. N - 1
         const bool neg = i < 2 + NR;

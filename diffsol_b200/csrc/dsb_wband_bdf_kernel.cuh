@@ -5,30 +5,37 @@
 // Why (round-1 profiles of the one-lane-per-instance kernel dsb_band_bdf_kernel.cuh, profiles/r1_s4_band_*): with the
 // state in global memory every component of every vector operation was a global round trip (long-scoreboard stalls of
 // 9-24 cycles per issue at 6-24 % resident warps, 1.4-2.5x the algorithmic DRAM traffic).  Here
-//   * the difference array D (n x 8), the five Newton work vectors, the band factors, their pivots and RN(1 / U_jj) live
-//     in the warp's shared-memory slice for the whole integration of the instance (18.5 n words for a tridiagonal system:
-//     6 instances per SM at n = 256, 7 at n = 200, 16 at n = 42); HBM sees the parameters, the initial state and the
-//     result columns, nothing else;
-//   * df/dy (and M for DAEs) are only needed when the iteration matrix is rebuilt: they are PARKED in a per-warp
-//     global-memory slot (L2-resident: 3 n words written per Jacobian evaluation) and brought back by one bulk-async copy
-//     (cp.async.bulk + mbarrier, the 1-D TMA path) straight into the band rows where A = M - c J is assembled;
+//   * the Newton work vectors, the band factors, their pivots and RN(1 / U_jj) live in the warp's shared-memory slice
+//     for the whole integration of the instance (10.5 n words for a tridiagonal system); HBM sees the parameters, the
+//     initial state and the result columns, nothing else;
+//   * the difference array D (n x 8) joins them in shared memory where that still leaves 8 instances per SM (n = 42);
+//     for larger systems it lives in a per-warp global-memory slot that stays in L2 (the resident warps' slots are a few
+//     tens of MB), is read in chunks with L1 bypassed, and costs one L2 round trip per chunk in the ~5 passes a step
+//     makes over it -- which buys 10 instead of 6 instances per SM at n = 256 (measured 1.55x);
+//   * df/dy (and M for DAEs) are only needed when the iteration matrix is rebuilt: they are PARKED in the same slot (3 n
+//     words written per Jacobian evaluation) and df/dy comes back by one bulk-async copy (cp.async.bulk + mbarrier, the
+//     1-D TMA path) straight into the band rows where A = M - c J is assembled;
 //   * every vector operation is lane-parallel (component i on lane i mod 32, stride-1 shared-memory rows: conflict-free);
 //   * the inherently sequential recurrences -- band LU, forward / back substitution, the in-order sum of a weighted
 //     norm (the reference adds its terms sequentially, vector/nalgebra_serial.rs:395-408) -- run on one lane out of
-//     shared memory with the running entries in a register window; their cost is a pure FP64 dependency chain, so the
-//     back substitution divides through the stored reciprocal (dsb_math.h: dsb_div_rcp, 5 dependent operations instead
-//     of ~13 for the IEEE routine, bit-identical quotient);
+//     shared memory with the running entries in a register window.  Their cost is a pure FP64 dependency chain (8.2
+//     cycles per DADD / DMUL / DFMA on B200, an IEEE division 110: tools/fp64_peak.cu), so the back substitution divides
+//     through the stored reciprocal -- 3 dependent operations, proven correct behind the chain (SmemBandLU::solve) --, its
+//     rows are branch-free, and the forward sweep walks interchange-free segments between the few rows that pivoted;
 //   * result columns are staged in a dead work vector and leave through a bulk-async store (cp.async.bulk
 //     shared -> global) that drains while the warp integrates on; outputs are written INSTANCE-major (the reference's
 //     host layout), which makes every column one contiguous run.  Equations with an output function and declared
 //     dependencies (the battery model's terminal voltage) evaluate up to 32 pending columns at once, one per lane.
 // Control flow is uniform over the warp, so the per-lane state machine of dsb_band_bdf_kernel.cuh is kept block by block
-// (same restated functions, same expression order, bit-identical results: tests/test_gpu_band_parity.py) without its
-// warp scheduler.  Warps are persistent and draw instances from a global work counter.
+// (same restated functions, same expression order, bit-identical results: tests/test_gpu_warp_band_parity.py) without
+// its warp scheduler.  Warps are persistent and draw instances from a global work counter.
+// What bounds it (profiles/r2_wband_*): the dependency chains of the one-lane sections at 8-12 resident warps per SM
+// (issue slots 33 % busy, `wait` = fixed-latency dependency is the dominant stall); the number of resident warps is set by
+// shared memory (n >= 200) or registers.
 //
 // Restated functions: the list of dsb_bdf_kernel.cuh plus new_without_initialise / set_step_size
 // (ode_solver/state.rs:1086-1124, 1209-1277).  Not built here (the launcher falls back to the one-lane-per-instance
-// kernel): reset functions.
+// kernel): reset functions, (E)SDIRK.
 #pragma once
 #include "dsb_band_bdf_kernel.cuh"
 
@@ -37,10 +44,24 @@
 #else
 #define DSB_WLANES 1                // tests/host_emu: the same source, one lane per warp
 #endif
+// Warps per block.  Registers are allotted per scheduler (4 x 16384): 16 warps leave 128 registers per lane, 9-12 leave
+// 168, 8 or fewer 255.
 #ifndef DSB_WBAND_MAX_WARPS
-#define DSB_WBAND_MAX_WARPS 16      // 128 registers per lane; small systems are limited by this, large ones by shared memory
+#define DSB_WBAND_MAX_WARPS 16              // small systems, D in shared memory
+#endif
+#ifndef DSB_WBAND_MAX_WARPS_D_GLOBAL
+#define DSB_WBAND_MAX_WARPS_D_GLOBAL 12     // larger systems, D in the global-memory slot
+#endif
+#ifndef DSB_WBAND_MIN_WARPS_D_SHARED
+#define DSB_WBAND_MIN_WARPS_D_SHARED 8
+#endif
+#ifndef DSB_WBAND_CHUNK
+#define DSB_WBAND_CHUNK 2           // components per lane whose difference-array loads go out together (dsb_warp_for)
 #endif
 #define DSB_WBAND_SMEM_BYTES (227 * 1024)
+
+template <class M, class = void> struct dsb_wband_max_warps { static constexpr int value = 64; };
+template <class M> struct dsb_wband_max_warps<M, decltype((void)M::WBAND_MAX_WARPS)> { static constexpr int value = M::WBAND_MAX_WARPS; };
 
 template <class M>
 struct WBandLayout {
@@ -51,8 +72,17 @@ struct WBandLayout {
     static constexpr int NS = (N + 1) & ~1;                         // row stride: even, so every row is 16-byte aligned
     // shared-memory words of one warp; a band row r holds one diagonal: entry (i, j) of row KV + i - j (factors) or
     // KU + i - j (df/dy, M) sits at column j
-    static constexpr int O_D = 0;                                   // D[DSB_NDIFF][NS]
-    static constexpr int O_Y = O_D + DSB_NDIFF * NS;                // state.y
+    // The difference array D (n x 8) takes 8 of the 18.5 n words of an instance.  Where the whole set still lets
+    // DSB_WBAND_MIN_WARPS_D_SHARED instances share an SM (n = 42: 16), D stays in shared memory; for larger systems it
+    // moves to the warp's global-memory slot (L2-resident, loaded in chunks, L1 bypassed), which nearly doubles the
+    // instances per SM (n = 256: 6 -> 10; n = 200: 7 -> 12) at the price of one L2 round trip per chunk in the five or so
+    // passes over D that a step makes.
+    static constexpr int WORDS_NO_D = 5 * NS + LDAB * NS + NS + NS / 2 + 26 + 1 + 5;
+    static constexpr int BLOCK_WORDS = (NS + 15) / 16 * 16;         // shared by the block's warps: the absolute tolerances
+    static constexpr int FIT_D_SHARED = (DSB_WBAND_SMEM_BYTES - BLOCK_WORDS * 8) / (((WORDS_NO_D + DSB_NDIFF * NS + 15) / 16 * 16) * 8);
+    static constexpr bool D_SHARED = FIT_D_SHARED >= DSB_WBAND_MIN_WARPS_D_SHARED;
+    static constexpr int O_D = 0;                                   // D[DSB_NDIFF][NS] (when D_SHARED)
+    static constexpr int O_Y = D_SHARED ? DSB_NDIFF * NS : 0;       // state.y
     static constexpr int O_YP = O_Y + NS;                           // y_predict
     static constexpr int O_YC = O_YP + NS;                          // Newton iterate
     static constexpr int O_PSI = O_YC + NS;                         // psi - y_predict
@@ -62,15 +92,24 @@ struct WBandLayout {
     static constexpr int O_PIV = O_RCP + NS;                        // int32 pivot offsets (row j interchanged with row j + piv[j])
     static constexpr int O_RU = O_PIV + NS / 2;                     // rows / columns 1..5 of R U (rescale)
     static constexpr int O_BAR = O_RU + 26;                         // mbarrier of the bulk-async loads
-    static constexpr int O_FLAG = O_BAR + 1;                        // 2 x int32: zero pivots met by the last factorisation, its row interchanges
-    static constexpr int WORDS = (O_FLAG + 1 + 15) / 16 * 16;       // slices start on 128-byte boundaries
-    static constexpr int FIT = DSB_WBAND_SMEM_BYTES / (WORDS * 8);
-    static constexpr int WARPS = FIT < 1 ? 1 : (FIT < DSB_WBAND_MAX_WARPS ? FIT : DSB_WBAND_MAX_WARPS);
+    static constexpr int O_FLAG = O_BAR + 1;                        // int32: zero pivots met by the last factorisation, its row
+                                                                    // interchanges, the rows of the first 8 of them
+    static constexpr int WORDS = (O_FLAG + 5 + 15) / 16 * 16;       // slices start on 128-byte boundaries
+    static constexpr int FIT = (DSB_WBAND_SMEM_BYTES - BLOCK_WORDS * 8) / (WORDS * 8);
+    // equations whose right-hand side needs many registers (coefficient tables: the battery model) cap the warps at 8
+    // (255 registers per lane) through M::WBAND_MAX_WARPS: at 12 warps (168 registers) they spill ~1 KB per lane into a
+    // local-memory footprint that no longer fits L1 (measured: n = 200, 976 ms at 12 warps, 828 ms at 8)
+    static constexpr int MAXW_MODEL = dsb_wband_max_warps<M>::value;
+    static constexpr int MAXW_KIND = D_SHARED ? DSB_WBAND_MAX_WARPS : DSB_WBAND_MAX_WARPS_D_GLOBAL;
+    static constexpr int MAXW = MAXW_MODEL < MAXW_KIND ? MAXW_MODEL : MAXW_KIND;
+    static constexpr int WARPS = FIT < 1 ? 1 : (FIT < MAXW ? FIT : MAXW);
     static constexpr int THREADS = WARPS * DSB_WLANES;
-    static constexpr size_t SMEM_BYTES = (size_t)WORDS * 8 * WARPS;
+    static constexpr size_t SMEM_BYTES = (size_t)(BLOCK_WORDS + WORDS * WARPS) * 8;
     static constexpr bool FITS = FIT >= 1;
-    // global-memory slot of one warp: df/dy band [LDJ][NS], then M band [LDJ][NS] (DAEs)
-    static constexpr int G_J = 0;
+    // global-memory slot of one warp (L2-resident: the resident warps' slots are a few tens of MB): the difference array
+    // D[DSB_NDIFF][NS] (unless D_SHARED), df/dy band [LDJ][NS], then M band [LDJ][NS] (DAEs)
+    static constexpr int G_D = 0;
+    static constexpr int G_J = G_D + (D_SHARED ? 0 : DSB_NDIFF * NS);
     static constexpr int G_M = G_J + LDJ * NS;
     static constexpr int G_WORDS = G_M + (M::HAS_MASS ? LDJ * NS : 0);
     static_assert(KL >= 1 && KL <= 2 && KU >= 1 && KU <= 2, "register windows are sized for kl, ku <= 2");
@@ -189,6 +228,41 @@ struct WDepVec {
     }
 };
 
+// The difference array, df/dy and M live in the warp's global-memory slot and stay in L2: their loads and stores bypass
+// L1 (ld.global.cg / st.global.cg), which -- next to 200+ KB of shared memory -- is only a few tens of KB and holds the
+// equations' coefficient tables and the column metadata (streaming D through it evicted them: 1.45x slower on n = 200).
+DSB_DEV double dsb_ld_l2(const double* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+DSB_DEV void dsb_st_l2(double* p, double v) {
+#if defined(__CUDA_ARCH__)
+    __stcg(p, v);
+#else
+    *p = v;
+#endif
+}
+
+// Lane-strided component loop in chunks: load(i) for U components of the lane first, then use(i, value) for each.  The
+// difference array lives in the warp's global-memory slot (L2): with the loads of a chunk issued back to back a pass over
+// it costs about one L2 round trip per chunk instead of one per component.  load() must not read what use() writes for
+// another component.
+template <int U, class R, class L, class F>
+DSB_DEV void dsb_warp_for(const int lane, const int n, L&& load, F&& use) {
+#pragma unroll 1
+    for (int i0 = lane; i0 < n; i0 += U * DSB_WLANES) {
+        R r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int i = i0 + u * DSB_WLANES; if (i < n) r[u] = load(i); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int i = i0 + u * DSB_WLANES; if (i < n) use(i, r[u]); }
+    }
+}
+struct WCols { double v[DSB_MAX_ORDER + 2]; };
+
 // ---- band LU on a shared-memory band, ONE lane ----------------------------------------------------------------------------
 // The arithmetic of dsb_band_lu.cuh (= nalgebra 0.35 `DMatrix::lu()` / `LU::solve_mut`, only operations with an exactly
 // zero operand skipped) on the row-per-diagonal layout: entry (i, j) at ab[(KV + i - j) * NS + j].
@@ -197,8 +271,9 @@ struct SmemBandLU {
     static constexpr int KV = KL + KU, LDAB = 2 * KL + KU + 1;
 #define AB_(j, r) ab[(r) * NS + (j)]
     // returns the number of exactly zero pivots (the factors are then unusable: LaError::LuSolveFailed at the next solve);
-    // *nswaps = number of row interchanges (none: the forward sweep runs its interchange-free form)
-    static DSB_DEV int factor(double* __restrict__ ab, int* __restrict__ piv, double* __restrict__ rcp, int* __restrict__ nswaps) {
+    // *nswaps = number of row interchanges, swaprow[0 .. min(nswaps, 8)) their rows (see solve(): FWD)
+    static DSB_DEV int factor(double* __restrict__ ab, int* __restrict__ piv, double* __restrict__ rcp, int* __restrict__ nswaps,
+                              int* __restrict__ swaprow) {
         int nzero = 0, nsw = 0;
         int jlast = 0;                                   // last column touched by the fill-in so far
 #pragma unroll 1
@@ -222,6 +297,7 @@ struct SmemBandLU {
             piv[j] = jp;
             { const int cand = (j + KU + jp < N - 1) ? (j + KU + jp) : (N - 1); if (cand > jlast) jlast = cand; }
             if (jp != 0) {
+                if (nsw < 8) swaprow[nsw] = j;               // the first MAXSW interchange rows, for the forward sweep
                 ++nsw;
 #pragma unroll
                 for (int q = 0; q <= KV; ++q) {              // columns j .. jlast (at most kv + 1 of them)
@@ -238,7 +314,7 @@ struct SmemBandLU {
                 }
             }
             const double inv_diag = 1.0 / colv[0];
-            rcp[j] = dsb_rcp_from(colv[0], inv_diag);
+            rcp[j] = dsb_rcp_from_narrow(colv[0], inv_diag);
             if (km > 0) {
 #pragma unroll
                 for (int d = 1; d <= KL; ++d) if (d <= km) { colv[d] *= inv_diag; AB_(j, KV + d) = colv[d]; }
@@ -271,20 +347,24 @@ struct SmemBandLU {
     //     stored RN(1 / U_ii) (3 dependent operations).  q1 is within half an ulp + 2^-104 of the quotient, i.e. it IS
     //     RN(w / U_ii) unless the quotient lies that close to a rounding boundary; one more residual step
     //     q2 = RN(q1 + RN(w - q1 U_ii) r) is the correctly rounded quotient (dsb_math.h: dsb_div_rcp), so q2 == q1 proves
-    //     q1 right.  That test runs BEHIND the chain (nothing waits for it); a refuted quotient (or a NaN reciprocal from
-    //     dsb_rcp) only raises a flag that is looked at once per solve.  A numerator outside the proof's range (|exponent
-    //     of w| > 500: the far field of a diffusion front, infinities, NaNs) takes the plain division in place; an exactly
-    //     zero w takes q0, which carries the quotient's sign.
-    template <bool EXACT, bool SWAPS>
+    //     q1 right.  That test runs BEHIND the chain (nothing waits for it); a refuted quotient, a NaN reciprocal
+    //     (dsb_rcp_from_narrow: |exponent of U_ii| > 100) or a non-zero numerator outside the proof's range (dsb_math.h:
+    //     dsb_numerator_in_wide_range -- subnormals and the last 30 decades above them, infinities, NaNs) only raise a
+    //     flag that is looked at once per solve.
+    // FWD: how the forward sweep meets row interchanges -- 0: the factorisation made none; 1: a few (at most MAXSW, their
+    // rows listed in ascending order in swaprow[0 .. nsw)): interchange-free segments between them, so no select sits on
+    // the chain; 2: any number, tested row by row (selects).
+    static constexpr int MAXSW = 8;
+    template <bool EXACT, int FWD>
     static DSB_DEV int solve(const double* __restrict__ ab, const int* __restrict__ piv, const double* __restrict__ rcp,
-                             double* __restrict__ b) {
+                             double* __restrict__ b, const int* __restrict__ swaprow, const int nsw) {
         {
             double w[KL + 1];
 #pragma unroll
             for (int d = 0; d <= KL; ++d) w[d] = b[d];
             // one row of the forward sweep: interchange, b[j] leaves the window, the kl multipliers of column j act
-            auto fwd_row = [&](const int jp, const double (&lm_)[KL], const double bin) -> double {
-                if constexpr (SWAPS) {
+            auto fwd_row = [&](auto SW, const int jp, const double (&lm_)[KL], const double bin) -> double {
+                if constexpr (decltype(SW)::value) {
                     if (jp != 0) {
                         const double a = w[0];
 #pragma unroll
@@ -300,39 +380,62 @@ struct SmemBandLU {
                 w[KL] = bin;
                 return bj;
             };
-            int j0 = 0;
-#pragma unroll 1
-            for (; j0 + U <= N - 1 - KL; j0 += U) {             // rows whose multipliers and incoming entry all exist
-                int jp[U];
-                double lm_[U][KL], bin[U], out[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    jp[u] = SWAPS ? piv[j0 + u] : 0;
-#pragma unroll
-                    for (int d = 1; d <= KL; ++d) lm_[u][d - 1] = AB_(j0 + u, KV + d);
-                    bin[u] = b[j0 + u + 1 + KL];
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) out[u] = fwd_row(jp[u], lm_[u], bin[u]);
-#pragma unroll
-                for (int u = 0; u < U; ++u) b[j0 + u] = out[u];
-            }
-#pragma unroll 1
-            for (int j = j0; j + 1 < N; ++j) {                  // tail: multipliers below the matrix are exact zeros
+            // one row with its bounds tests (multipliers below the matrix are exact zeros)
+            auto fwd_single = [&](auto SW, const int j) {
                 double lm_[KL];
 #pragma unroll
                 for (int d = 1; d <= KL; ++d) lm_[d - 1] = (j + d < N) ? AB_(j, KV + d) : 0.0;
                 const double bin = (j + 1 + KL < N) ? b[j + 1 + KL] : 0.0;
-                b[j] = fwd_row(SWAPS ? piv[j] : 0, lm_, bin);
+                b[j] = fwd_row(SW, decltype(SW)::value ? piv[j] : 0, lm_, bin);
+            };
+            // rows [j0, j1), j1 <= N - 1: blocks of U rows whose multipliers and incoming entry all exist, then single rows
+            auto fwd_range = [&](auto SW, int j0, const int j1) {
+                const int safe = (j1 < N - 1 - KL) ? j1 : (N - 1 - KL);
+#pragma unroll 1
+                for (; j0 + U <= safe; j0 += U) {
+                    int jp[U];
+                    double lm_[U][KL], bin[U], out[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        jp[u] = decltype(SW)::value ? piv[j0 + u] : 0;
+#pragma unroll
+                        for (int d = 1; d <= KL; ++d) lm_[u][d - 1] = AB_(j0 + u, KV + d);
+                        bin[u] = b[j0 + u + 1 + KL];
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) out[u] = fwd_row(SW, jp[u], lm_[u], bin[u]);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) b[j0 + u] = out[u];
+                }
+#pragma unroll 1
+                for (; j0 < j1; ++j0) fwd_single(SW, j0);
+            };
+            if constexpr (FWD == 0) {
+                fwd_range(std::false_type{}, 0, N - 1);
+            } else if constexpr (FWD == 1) {
+                int j = 0;
+#pragma unroll 1
+                for (int k = 0; k < nsw; ++k) {
+                    const int r = swaprow[k];
+                    fwd_range(std::false_type{}, j, r);
+                    fwd_single(std::true_type{}, r);
+                    j = r + 1;
+                }
+                fwd_range(std::false_type{}, j, N - 1);
+            } else {
+                fwd_range(std::true_type{}, 0, N - 1);
             }
             b[N - 1] = w[0];
         }
-        bool bad = false;
+        int bad = 0;
         {
             double w[KV + 1];
 #pragma unroll
             for (int e = 0; e <= KV; ++e) w[e] = b[N - 1 - e];
             // one row of the backward sweep: x_i = w[0] / U_ii, then column i of U acts on the kv entries above
+            // The fast form is branch-free: the sign of a zero quotient is put in by a bit operation (sign(a) ^ sign(U_ii) is
+            // the sign of every correctly rounded quotient), and what cannot be vouched for -- q2 != q1, a numerator outside
+            // the proof's range -- only accumulates into `bad`, behind the chain.
             auto bwd_row = [&](const double (&up)[KV + 1], const double rc, const double bin) -> double {
                 const double a = w[0], diag = up[0];
                 double x;
@@ -342,15 +445,10 @@ struct SmemBandLU {
                     const double q0 = a * rc;
                     const double e0 = dsb_fma(-q0, diag, a);
                     const double q1 = dsb_fma(e0, rc, q0);
-                    x = q1;
-                    // behind the chain: the proof that q1 is the correctly rounded quotient (a NaN reciprocal fails it too)
+                    x = dsb_quotient_sign(q1, a, diag);
                     const double e1 = dsb_fma(-q1, diag, a);
                     const double q2 = dsb_fma(e1, rc, q1);
-                    bad = bad || !(q2 == q1);
-                    // numerators outside the proof's range (zero, subnormal, |exponent| > 500, infinite, NaN) take the plain
-                    // division at once; the test only needs the numerator, so the branch resolves before q1 is there
-                    const uint32_t ex = (uint32_t)(dsb_bits(a) >> 52) & 0x7ffu;
-                    if (!(ex - (1023u - 500u) <= 1000u)) x = (a == 0.0) ? q0 : dsb_div_full(a, diag);
+                    bad |= (int)!(q2 == q1) | ((int)(a != 0.0) & (int)!dsb_numerator_in_wide_range(a));    // no short circuits: no branches
                 }
                 const double nx = -x;
 #pragma unroll
@@ -403,9 +501,11 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
     extern __shared__ double dsb_lane_smem[];
     const int lane = dsb_wlane();
     const int warp = (int)(threadIdx.x / LANES);
-    double* const sm = dsb_lane_smem + (size_t)warp * Lay::WORDS;
+    double* const satol = dsb_lane_smem;                             // [N], one copy per block
+    double* const sm = dsb_lane_smem + Lay::BLOCK_WORDS + (size_t)warp * Lay::WORDS;
     double* const gslot = ws + ((size_t)blockIdx.x * Lay::WARPS + warp) * Lay::G_WORDS;
-#define SD(j, i) sm[Lay::O_D + (j) * NS + (i)]
+#define SD_LD(j, i) (Lay::D_SHARED ? sm[Lay::O_D + (j) * NS + (i)] : dsb_ld_l2(&gslot[Lay::G_D + (j) * NS + (i)]))
+#define SD_ST(j, i, v) do { if (Lay::D_SHARED) sm[Lay::O_D + (j) * NS + (i)] = (v); else dsb_st_l2(&gslot[Lay::G_D + (j) * NS + (i)], (v)); } while (0)
 #define SY(i) sm[Lay::O_Y + (i)]
 #define SYP(i) sm[Lay::O_YP + (i)]
 #define SYC(i) sm[Lay::O_YC + (i)]
@@ -432,8 +532,13 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
     constexpr int NR = dsb_model_nroots<M>::value;
     constexpr bool BULK_OUT = !dsb_model_nout<M>::has_out && (N % 2 == 0);
 
+#if defined(__CUDA_ARCH__)
+    for (int i = (int)threadIdx.x; i < N; i += (int)blockDim.x) satol[i] = meta.atol[i];
     if (lane == 0) dsb_mbar_init(sbar);
-    dsb_wsync();
+    __syncthreads();                    // the only block-wide synchronisation: the warps are independent from here on
+#else
+    for (int i = 0; i < N; ++i) satol[i] = meta.atol[i];
+#endif
     unsigned bar_parity = 0;
 
     // ---- controller (uniform over the warp: every lane holds the same values) -----------------------------------------
@@ -510,11 +615,13 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
         return DSB_DIV(acc, (double)N);
     };
     // ||x||^2_w(ref): the terms lane-parallel into DL (x may be DL itself), then the in-order sum
-    auto weighted_norm = [&](const double* x, const double* ref) -> double {
-        WFOR(i) {
-            const double term = DSB_DIV(x[i], dsb_abs(ref[i]) * pa.rtol + meta.atol[i]);
+    auto dcol = [&](int j) -> const double* { return Lay::D_SHARED ? sm + Lay::O_D + j * NS : gslot + Lay::G_D + j * NS; };
+    // x: a shared-memory vector, or (GLOBAL_X) a column of the difference array in the warp's global-memory slot
+    auto weighted_norm = [&](auto GLOBAL_X, const double* x, const double* ref) -> double {
+        dsb_warp_for<DSB_WBAND_CHUNK, double>(lane, N, [&](int i) { return decltype(GLOBAL_X)::value ? dsb_ld_l2(x + i) : x[i]; }, [&](int i, double xi) {
+            const double term = DSB_DIV(xi, dsb_abs(ref[i]) * pa.rtol + satol[i]);
             SDL(i) = term * term;
-        }
+        });
         return sum_terms();
     };
     // the time factors of interpolate (bdf.rs:767-782, 1080-1106)
@@ -529,17 +636,25 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
             tf[j] = time_factor;
         }
     };
-    auto interpolate_i = [&](int i, const double (&tf)[DSB_MAX_ORDER]) -> double {
-        double yo = SD(0, i);
+    // columns 0 .. order of the difference array for component i (the loads of one chunk go out together)
+    auto load_cols = [&](int i) -> WCols {
+        WCols c;
 #pragma unroll
-        for (int j = 0; j < DSB_MAX_ORDER; ++j) if (j < order) yo = tf[j] * SD(j + 1, i) + yo;
+        for (int j = 0; j <= DSB_MAX_ORDER; ++j) c.v[j] = (j <= order) ? SD_LD(j, i) : 0.0;
+        return c;
+    };
+    auto interpolate_cols = [&](const WCols& c, const double (&tf)[DSB_MAX_ORDER]) -> double {
+        double yo = c.v[0];
+#pragma unroll
+        for (int j = 0; j < DSB_MAX_ORDER; ++j) if (j < order) yo = tf[j] * c.v[j + 1] + yo;
         return yo;
     };
+    auto interpolate_i = [&](int i, const double (&tf)[DSB_MAX_ORDER]) -> double { return interpolate_cols(load_cols(i), tf); };
     // interpolate(tq) into a shared-memory vector, one component per lane
     auto interpolate_to = [&](double tq, double* dst) {
         double tf[DSB_MAX_ORDER];
         time_factors(tq, tf);
-        WFOR(i) dst[i] = interpolate_i(i, tf);
+        dsb_warp_for<DSB_WBAND_CHUNK, WCols>(lane, N, load_cols, [&](int i, const WCols& c) { dst[i] = interpolate_cols(c, tf); });
         dsb_wsync();
     };
     // the same for the output and root functions: only the components they read when the equations declare them
@@ -586,7 +701,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
         } else {
             double tf[DSB_MAX_ORDER];
             time_factors(tq, tf);
-            WFOR(i) dst[i] = interpolate_i(i, tf);
+            dsb_warp_for<DSB_WBAND_CHUNK, WCols>(lane, N, load_cols, [&](int i, const WCols& c) { dst[i] = interpolate_cols(c, tf); });
         }
     };
 
@@ -623,28 +738,28 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
                     // (state.rs:84-162)
 #pragma unroll
                     for (int k = 0; k < DSB_NSTATS; ++k) st.v[k] = bb.stats[(int64_t)k * B + inst];
-                    WFOR(i) { SY(i) = bb.y0[(int64_t)i * B + inst]; SD(1, i) = bb.dy0[(int64_t)i * B + inst]; }
+                    WFOR(i) { SY(i) = bb.y0[(int64_t)i * B + inst]; SD_ST(1, i, bb.dy0[(int64_t)i * B + inst]); }
                     dsb_wsync();
                 } else {
                     // y = init(p, t0); dy = f(y, t0)     (state.rs:1086-1124); dy is kept in D[1] until h is known
                     WFOR(i) SY(i) = M::init_i(i, pl, pa.t0);
                     dsb_wsync();
-                    WFOR(i) SD(1, i) = M::rhs_i(i, vY, pl, pa.t0);
+                    WFOR(i) SD_ST(1, i, M::rhs_i(i, vY, pl, pa.t0));
                     dsb_wsync();
                     st.v[DSB_STAT_RHS_CALLS] += 1;
                 }
                 // set_step_size (state.rs:1209-1277), solver order 1
                 {
                     const bool is_neg_h = pa.h0 < 0.0;
-                    const double d0 = dsb_sqrt(weighted_norm(sm + Lay::O_Y, sm + Lay::O_Y));
-                    const double d1 = dsb_sqrt(weighted_norm(sm + Lay::O_D + NS, sm + Lay::O_Y));
+                    const double d0 = dsb_sqrt(weighted_norm(std::false_type{}, sm + Lay::O_Y, sm + Lay::O_Y));
+                    const double d1 = dsb_sqrt(weighted_norm(std::bool_constant<!Lay::D_SHARED>{}, dcol(1), sm + Lay::O_Y));
                     const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * DSB_DIV(d0, d1);
-                    WFOR(i) SYC(i) = is_neg_h ? (SD(1, i) * (-h0) + SY(i)) : (SD(1, i) * h0 + SY(i));
+                    WFOR(i) { const double dy = SD_LD(1, i); SYC(i) = is_neg_h ? (dy * (-h0) + SY(i)) : (dy * h0 + SY(i)); }
                     dsb_wsync();
                     const double t1 = is_neg_h ? pa.t0 - h0 : pa.t0 + h0;
-                    WFOR(i) SDL(i) = M::rhs_i(i, vYC, pl, t1) - SD(1, i);
+                    WFOR(i) SDL(i) = M::rhs_i(i, vYC, pl, t1) - SD_LD(1, i);
                     st.v[DSB_STAT_RHS_CALLS] += 1;
-                    const double d2 = DSB_DIV(dsb_sqrt(weighted_norm(sm + Lay::O_DL, sm + Lay::O_Y)), dsb_abs(h0));
+                    const double d2 = DSB_DIV(dsb_sqrt(weighted_norm(std::false_type{}, sm + Lay::O_DL, sm + Lay::O_Y)), dsb_abs(h0));
                     double max_d = d2;
                     if (max_d < d1) max_d = d1;
                     double h1;
@@ -656,9 +771,9 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
                 }
                 // state.set_problem (bdf_state.rs:72-78): D[:, 0] = y, D[:, 1] = h dy, the rest zero
                 WFOR(i) {
-                    SD(0, i) = SY(i); SD(1, i) = SD(1, i) * h;
+                    SD_ST(0, i, SY(i)); SD_ST(1, i, SD_LD(1, i) * h);
 #pragma unroll
-                    for (int j = 2; j < DSB_NDIFF; ++j) SD(j, i) = 0.0;
+                    for (int j = 2; j < DSB_NDIFF; ++j) SD_ST(j, i, 0.0);
                 }
                 dsb_wsync();
                 order = 1; n_equal_steps = 0;
@@ -690,7 +805,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
                     if (q != 1) {
                         err = inf;
                         if ((q == 0) ? (ord > 1) : (ord < DSB_MAX_ORDER)) {
-                            const double e = weighted_norm(sm + Lay::O_D + (ord + q) * NS, sm + Lay::O_Y) * pa.tab.error_const2[ord - 1 + q];
+                            const double e = weighted_norm(std::bool_constant<!Lay::D_SHARED>{}, dcol(ord + q), sm + Lay::O_Y) * pa.tab.error_const2[ord - 1 + q];
                             err = (0.0 < e) ? e : 0.0;
                         }
                     }
@@ -752,19 +867,21 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
                 }
             }
             dsb_wsync();
-            WFOR(s) {
+            dsb_warp_for<DSB_WBAND_CHUNK, WCols>(lane, N, load_cols, [&](int s, const WCols& dc) {
                 double nd[DSB_MAX_ORDER + 1];
 #pragma unroll
                 for (int j = 1; j <= DSB_MAX_ORDER; ++j) nd[j] = -0.0;      // (-0.0) + x == x: the first term is assigned
-#pragma unroll 1
-                for (int i = 1; i <= k; ++i) {
-                    const double di = SD(i, s);
 #pragma unroll
-                    for (int j = 1; j <= DSB_MAX_ORDER; ++j) nd[j] = di * SRU(i, j) + nd[j];
+                for (int i = 1; i <= DSB_MAX_ORDER; ++i) {
+                    if (i <= k) {
+                        const double di = dc.v[i];
+#pragma unroll
+                        for (int j = 1; j <= DSB_MAX_ORDER; ++j) nd[j] = di * SRU(i, j) + nd[j];
+                    }
                 }
 #pragma unroll
-                for (int j = 1; j <= DSB_MAX_ORDER; ++j) if (j <= k) SD(j, s) = nd[j];
-            }
+                for (int j = 1; j <= DSB_MAX_ORDER; ++j) if (j <= k) SD_ST(j, s, nd[j]);
+            });
             dsb_wsync();
             c = new_h * pa.tab.alpha[k];
             h = new_h;
@@ -800,7 +917,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
                     // colouring the host supplies one colour per column: op/nonlinear_op.rs:211-220), scattered through
                     // the sparsity pattern into the band rows of the warp's global-memory slot
                     st.v[DSB_STAT_RHS_MATRIX_EVALS] += 1;
-                    for (int e = lane; e < LDJ * NS; e += LANES) gslot[Lay::G_J + e] = 0.0;
+                    for (int e = lane; e < LDJ * NS; e += LANES) dsb_st_l2(&gslot[Lay::G_J + e], 0.0);
                     dsb_wsync();
                     const bool one_colour_per_column = pa.ncolors == N;
 #pragma unroll 1
@@ -817,7 +934,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
                                 const int j = i + d;
                                 if (j >= 0 && j < N) {
                                     const int32_t m = meta.colmeta[j];
-                                    if ((m & 0xffff) == cc && ((m >> (16 + KU - d)) & 1)) GJ(j, KU - d) = val;
+                                    if ((m & 0xffff) == cc && ((m >> (16 + KU - d)) & 1)) dsb_st_l2(&GJ(j, KU - d), val);
                                 }
                             }
                         }
@@ -829,7 +946,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
 #pragma unroll
                             for (int r = 0; r < LDJ; ++r) {
                                 const int i = j + r - KU;
-                                GM(j, r) = (i >= 0 && i < N) ? M::mass_i(i, ej, pl, t, 0.0, 0.0) : 0.0;
+                                dsb_st_l2(&GM(j, r), (i >= 0 && i < N) ? M::mass_i(i, ej, pl, t, 0.0, 0.0) : 0.0);
                             }
                         }
                     }
@@ -848,7 +965,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
 #pragma unroll
                         for (int q = 0; q < (N + LANES - 1) / LANES; ++q) {
                             const int j = lane + q * LANES;
-                            mrow[r][q] = (j < N) ? GM(j, r) : 0.0;
+                            mrow[r][q] = (j < N) ? dsb_ld_l2(&GM(j, r)) : 0.0;
                         }
                 }
                 dsb_mbar_wait(sbar, bar_parity);
@@ -871,7 +988,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
                 }
                 dsb_wsync();
                 // band LU, dgbtf2 convention, one lane
-                if (lane == 0) sflag[0] = BLU::factor(sm + Lay::O_AB, spiv, sm + Lay::O_RCP, sflag + 1);
+                if (lane == 0) sflag[0] = BLU::factor(sm + Lay::O_AB, spiv, sm + Lay::O_RCP, sflag + 1, sflag + 2);
                 dsb_wsync();
             }
             state = after_jac;
@@ -1004,13 +1121,13 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
             if (repredict) {
                 const int ord = order;
                 const double a = pa.tab.alpha[ord];
-                WFOR(i) {
+                dsb_warp_for<DSB_WBAND_CHUNK, WCols>(lane, N, load_cols, [&](int i, const WCols& dc) {
                     double yp = 0.0;
                     double ps = 0.0;
 #pragma unroll
                     for (int j = 0; j <= DSB_MAX_ORDER; ++j) {
                         if (j <= ord) {
-                            const double d = SD(j, i);
+                            const double d = dc.v[j];
                             yp += d;
                             if (j == 1) ps = pa.tab.gamma[1] * d;
                             else if (j >= 2) ps = pa.tab.gamma[j] * d + ps;
@@ -1019,7 +1136,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
                     ps *= a;
                     ps -= yp;
                     SYP(i) = yp; SPSI(i) = ps; SYC(i) = yp;
-                }
+                });
                 t_predict = t + h;
             } else {
                 WFOR(i) SYC(i) = SYP(i);
@@ -1052,10 +1169,12 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
             const bool ok = sflag[0] == 0;                      // else LaError::LuSolveFailed: the factors hold a zero pivot
             if (ok) {
                 int rc = 1;
-                const bool swaps = sflag[1] != 0;
+                const int nsw = sflag[1];
                 if (lane == 0) {
-                    rc = swaps ? BLU::template solve<false, true>(sm + Lay::O_AB, spiv, sm + Lay::O_RCP, sm + Lay::O_DL)
-                               : BLU::template solve<false, false>(sm + Lay::O_AB, spiv, sm + Lay::O_RCP, sm + Lay::O_DL);
+                    double* const ab = sm + Lay::O_AB; double* const rc_ = sm + Lay::O_RCP; double* const rhs = sm + Lay::O_DL;
+                    rc = nsw == 0 ? BLU::template solve<false, 0>(ab, spiv, rc_, rhs, sflag + 2, 0)
+                       : nsw <= BLU::MAXSW ? BLU::template solve<false, 1>(ab, spiv, rc_, rhs, sflag + 2, nsw)
+                                           : BLU::template solve<false, 2>(ab, spiv, rc_, rhs, sflag + 2, nsw);
                 }
                 dsb_wsync();
                 rc = dsb_wbcast(rc, 0);
@@ -1063,7 +1182,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
                     // a quotient of the fast back substitution could not be vouched for (or the test hook asks for this path):
                     // the same right-hand side again, through the plain IEEE divisions
                     residual();
-                    if (lane == 0) BLU::template solve<true, true>(sm + Lay::O_AB, spiv, sm + Lay::O_RCP, sm + Lay::O_DL);
+                    if (lane == 0) BLU::template solve<true, 2>(sm + Lay::O_AB, spiv, sm + Lay::O_RCP, sm + Lay::O_DL, sflag + 2, nsw);
                     dsb_wsync();
                 }
             }
@@ -1074,7 +1193,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
                     const double dl = SDL(i);
                     SYC(i) = SYC(i) - dl;
                     // Newton norm weights use the PREDICTOR (line_search.rs:67, convergence.rs:64-66)
-                    const double term = DSB_DIV(dl, dsb_abs(SYP(i)) * pa.rtol + meta.atol[i]);
+                    const double term = DSB_DIV(dl, dsb_abs(SYP(i)) * pa.rtol + satol[i]);
                     SDL(i) = term * term;
                 }
                 const double norm = dsb_sqrt(sum_terms());
@@ -1108,7 +1227,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
                 {   // error_control: ||d||^2_w(state.y) * error_const2[order - 1], d = y - y_predict
                     WFOR(i) {
                         const double d = SYC(i) - SYP(i);
-                        const double term = DSB_DIV(d, dsb_abs(SY(i)) * pa.rtol + meta.atol[i]);
+                        const double term = DSB_DIV(d, dsb_abs(SY(i)) * pa.rtol + satol[i]);
                         SDL(i) = term * term;
                     }
                     const double err = sum_terms() * pa.tab.error_const2[ord - 1];
@@ -1119,21 +1238,25 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
                 safety = DSB_DIV(0.9 * (2.0 * maxiter + 1.0), 2.0 * maxiter + niter);
                 if (error_norm <= 1.0) {
                     // ---- accepted: _update_diff, state.y <- PREDICTOR (quirk Q1) ----
-                    WFOR(i) {
+                    dsb_warp_for<DSB_WBAND_CHUNK, WCols>(lane, N, [&](int i) {
+                        WCols dc = load_cols(i);
+                        dc.v[DSB_MAX_ORDER + 1] = SD_LD(ord + 1, i);        // the old D[:, ord + 1]
+                        return dc;
+                    }, [&](int i, const WCols& dc) {
                         const double yp = SYP(i);
                         const double d = SYC(i) - yp;
                         double above = d;                                   // the new D[:, ord + 1]
-                        SD(ord + 2, i) = d - SD(ord + 1, i);
-                        SD(ord + 1, i) = d;
+                        SD_ST(ord + 2, i, d - dc.v[DSB_MAX_ORDER + 1]);
+                        SD_ST(ord + 1, i, d);
 #pragma unroll
                         for (int j = DSB_MAX_ORDER; j >= 0; --j) {
                             if (j <= ord) {
-                                above = SD(j, i) + 1.0 * above;
-                                SD(j, i) = above;
+                                above = dc.v[j] + 1.0 * above;
+                                SD_ST(j, i, above);
                             }
                         }
                         SY(i) = yp;
-                    }
+                    });
                     dsb_wsync();
                     t = t_predict;
                     st.v[DSB_STAT_STEPS] += 1;
@@ -1165,7 +1288,8 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
             }
         }
     }
-#undef SD
+#undef SD_LD
+#undef SD_ST
 #undef SY
 #undef SYP
 #undef SYC

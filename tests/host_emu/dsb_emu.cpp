@@ -134,11 +134,15 @@ static int emu_band_lu_run(const double* A, double* b, int mode, int* nswaps) {
     for (int j = 0; j < N; ++j)
         for (int i = 0; i < N; ++i)
             if (i - j <= KL && j - i <= KU) ab[(size_t)(KV + i - j) * NS + j] = A[(size_t)j * N + i];
-    const int nzero = BLU::factor(ab.data(), piv.data(), rcp.data(), nswaps);
+    int swaprow[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int nzero = BLU::factor(ab.data(), piv.data(), rcp.data(), nswaps, swaprow);
     if (nzero) return 0;
-    if (mode == 1) return BLU::template solve<true, true>(ab.data(), piv.data(), rcp.data(), b);
-    return *nswaps ? BLU::template solve<false, true>(ab.data(), piv.data(), rcp.data(), b)
-                   : BLU::template solve<false, false>(ab.data(), piv.data(), rcp.data(), b);
+    const int nsw = *nswaps;
+    if (mode == 1) return BLU::template solve<true, 2>(ab.data(), piv.data(), rcp.data(), b, swaprow, nsw);
+    if (mode == 2) return BLU::template solve<false, 2>(ab.data(), piv.data(), rcp.data(), b, swaprow, nsw);      // selects on every row
+    return nsw == 0 ? BLU::template solve<false, 0>(ab.data(), piv.data(), rcp.data(), b, swaprow, 0)
+         : nsw <= BLU::MAXSW ? BLU::template solve<false, 1>(ab.data(), piv.data(), rcp.data(), b, swaprow, nsw)
+                             : BLU::template solve<false, 2>(ab.data(), piv.data(), rcp.data(), b, swaprow, nsw);
 }
 
 extern "C" {

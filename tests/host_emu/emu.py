@@ -125,11 +125,11 @@ def greedy_coloring(non_zeros, n):
     return out.tolist()
 
 
-def smem_band_lu(A, kl, ku, b, exact=False):
+def smem_band_lu(A, kl, ku, b, exact=False, mode=None):
     """SmemBandLU (the warp-per-instance kernel's band LU) on the band (kl, ku) of the dense matrix A -> (rc, x, nswaps)."""
     n = A.shape[0]
     Af = np.asfortranarray(A, dtype=np.float64)
     x = np.array(b, dtype=np.float64)
     nsw = ctypes.c_int(0)
-    rc = lib().emu_smem_band_lu(n, kl, ku, _dp(Af), _dp(x), 1 if exact else 0, ctypes.byref(nsw))
+    rc = lib().emu_smem_band_lu(n, kl, ku, _dp(Af), _dp(x), mode if mode is not None else (1 if exact else 0), ctypes.byref(nsw))
     return rc, x, nsw.value

@@ -145,9 +145,11 @@ def test_heat_dae_band_equals_block_per_instance_and_is_default(dsb):
     ya, yb = a.solve_dense(HEAT_T_EVAL), b.solve_dense(HEAT_T_EVAL)
     assert np.array_equal(ya, yb)
     assert np.array_equal(a.statistics_array(), b.statistics_array())
+    # automatic selection: the banded warp-per-instance kernel for BDF (tests/test_gpu_warp_band_parity.py), same bits
     c = prob.bdf()
-    assert np.array_equal(c.solve_dense(HEAT_T_EVAL), ya)
-    assert c.last_launch_count() == a.last_launch_count()
+    w = prob.bdf().set_execution("warp")
+    assert np.array_equal(c.solve_dense(HEAT_T_EVAL), ya) and np.array_equal(w.solve_dense(HEAT_T_EVAL), ya)
+    assert c.last_launch_count() == w.last_launch_count()
 
 
 @pytest.mark.parametrize("method", ["tr_bdf2", "esdirk34"])

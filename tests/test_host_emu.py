@@ -149,7 +149,7 @@ def test_smem_band_lu_matches_the_dense_restatement(oracle, n, kl, ku):
     import ctypes
     rng = np.random.default_rng(1000 * n + 10 * kl + ku)
     dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
-    seen_swaps = seen_noswaps = 0
+    seen_swaps = seen_noswaps = seen_few = 0
     for trial in range(300):
         A = np.zeros((n, n))
         for i in range(n):
@@ -157,6 +157,10 @@ def test_smem_band_lu_matches_the_dense_restatement(oracle, n, kl, ku):
                 A[i, j] = rng.standard_normal() * 10.0 ** rng.integers(-3, 4)
         if trial % 3 == 0:
             A[np.arange(n), np.arange(n)] += 1e5                      # no interchanges
+        if trial % 3 == 1:                                            # only a few interchanges: the segmented forward sweep
+            A[np.arange(n), np.arange(n)] += 1e5
+            for r in rng.integers(0, n - 1, 3):
+                A[r, r] = 1e-3
         b = rng.standard_normal(n) * 10.0 ** rng.integers(-8, 9, n)
         if trial % 4 == 1:
             b = b * 10.0 ** rng.choice([-310.0, -250.0, -160.0, 0.0, 120.0, 250.0, 290.0], n)
@@ -167,8 +171,9 @@ def test_smem_band_lu_matches_the_dense_restatement(oracle, n, kl, ku):
         x_o = b.copy()
         with np.errstate(all="ignore"):
             rc_o = oracle.lib().orc_lu_solve(dp(Af), n, dp(x_o))
-        for exact in (False, True):
-            rc, x, nsw = emu.smem_band_lu(A, kl, ku, b, exact=exact)
+        for mode in (0, 1, 2):                                          # fast (forward sweep by interchange count), exact, fast with selects
+            exact = mode == 1
+            rc, x, nsw = emu.smem_band_lu(A, kl, ku, b, mode=mode)
             if rc_o != 0:
                 assert rc == 0
                 continue
@@ -176,9 +181,10 @@ def test_smem_band_lu_matches_the_dense_restatement(oracle, n, kl, ku):
             if rc == 1:
                 assert np.array_equal(x.view(np.int64), x_o.view(np.int64)), (trial, exact)
             assert not (exact and rc == 2)
-            seen_swaps += nsw > 0
+            seen_swaps += nsw > 8
+            seen_few += 0 < nsw <= 8
             seen_noswaps += nsw == 0
-    assert seen_swaps > 100 and seen_noswaps > 100
+    assert (seen_swaps > 100 or n <= 8) and seen_noswaps > 100 and seen_few > 100
 
 
 def test_warp_band_exact_solve_path_on_host(oracle, monkeypatch):

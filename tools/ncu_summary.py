@@ -1,43 +1,26 @@
-#!/usr/bin/env python3
-"""Summarise an ncu report exported with `--page raw --csv` and `--page source --csv`:
-headline metrics, opcode mix, and executed instructions / active lanes / stall samples per SASS chunk."""
-import collections
+#!/usr/bin/env python
+"""Text summary of one kernel of an ncu report for profiles/: key launch / throughput / stall metrics (the raw page) plus
+the source-line hot spots (tools/ncu_hotspots.py).   python tools/ncu_summary.py <report.ncu-rep> <cubin> <kernel substring>"""
 import csv
-import re
+import io
+import subprocess
 import sys
 
-raw, src = sys.argv[1], sys.argv[2]
-chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 250
-rows = list(csv.reader(open(raw)))
-hdr, units, vals = rows[0], rows[1], rows[2]
-want = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
-        'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__thread_inst_executed_per_inst_executed.ratio',
-        'smsp__inst_executed.sum', 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
-        'smsp__issue_active.avg.pct', 'smsp__average_warps_issue_stalled', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
-        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'sm__inst_executed_pipe_alu.sum.pct',
-        'sm__inst_executed_pipe_fma.sum.pct', 'sm__inst_executed_pipe_fp64.sum.pct', 'launch__occupancy_limit']
-for h, u, v in zip(hdr, units, vals):
-    if any(w in h for w in want) and 'per_second' not in h and 'pct_of_peak_sustained_elapsed' not in h:
-        print("%-90s %-14s %s" % (h, u, v))
-rows = list(csv.reader(open(src)))
-hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
-ix = {h: i for i, h in enumerate(rows[hi])}
-data = rows[hi + 1:]
-f = lambda r, k: float(r[ix[k]] or 0)
-tot = sum(f(r, "Instructions Executed") for r in data)
-thr = sum(f(r, "Thread Instructions Executed") for r in data)
-print("\nSASS rows %d, warp instructions %.4g, thread instructions %.4g, lanes/instr %.2f" % (len(data), tot, thr, thr / tot))
-op = collections.Counter()
-for r in data:
-    m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[ix["Source"]])
-    op[m.group(2).split('.')[0] if m else '?'] += f(r, "Instructions Executed")
-print("opcode mix: " + ", ".join("%s %.1f%%" % (o, 100 * c / tot) for o, c in op.most_common(16)))
-print("\nchunk        warp-inst   share  lanes  samples  no_inst  wait  short_sb  long_sb  math  branch")
-for k in range(0, len(data), chunk):
-    seg = data[k:k + chunk]
-    ie = sum(f(r, "Instructions Executed") for r in seg)
-    te = sum(f(r, "Thread Instructions Executed") for r in seg)
-    g = lambda name: int(sum(f(r, name) for r in seg))
-    print("%5d-%5d  %10.4g  %5.1f%%  %5.1f  %7d  %7d  %5d  %7d  %7d  %5d  %5d" % (
-        k, k + chunk, ie, 100 * ie / tot, te / max(ie, 1), g("# Samples"), g("stall_no_inst"), g("stall_wait"),
-        g("stall_short_sb"), g("stall_long_sb"), g("stall_math"), g("stall_branch_resolving")))
+rep, cubin, kernel = sys.argv[1:4]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+head, units = rows[0], rows[1]
+vals = next(r for r in rows[2:] if kernel in ",".join(r))
+want = ("Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "launch__shared_mem_per_block_dynamic",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.sum.pct_of_peak_sustained_active",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum")
+for i, k in enumerate(head):
+    if k in want or (k.startswith("smsp__average_warps_issue_stalled") and k.endswith("per_issue_active.ratio")):
+        print("%-86s %-16s %s" % (k, units[i], vals[i]))
+print()
+sys.stdout.flush()
+subprocess.run([sys.executable, __file__.replace("ncu_summary.py", "ncu_hotspots.py"), rep, cubin, kernel, "30"])
