@@ -95,6 +95,8 @@ SIGNATURES = {
     "dsb_batch_free": (ctypes.c_int, [_vp]),
     "dsb_batch_size": (_i64, [_vp]),
     "dsb_batch_set_execution": (ctypes.c_int, [_vp, _i32]),
+    "dsb_model_library_build": (ctypes.c_int, [ctypes.c_char_p, _i32, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]),
+    "dsb_model_library_load": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int32)]),
     "dsb_batch_set_params_host": (ctypes.c_int, [_vp, _vp, _i64, _i32]),
     "dsb_batch_set_params_device": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "dsb_batch_solve_dense": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
@@ -144,6 +146,38 @@ def lib():
             f.restype, f.argtypes = res, args
         _lib = L
     return _lib
+
+
+MODEL_SOURCE_KINDS = {"functor": 0, "diffsl": 1}
+CSRC_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+
+
+def load_model_source(source, kind="functor", struct="UserModel", cache_dir=None):
+    """Compile a user equation set (source text, see include/diffsol_b200.h: dsb_model_library_build) into a model plugin
+    -- cached by the digest of the text and of csrc/ -- load it and return its registered name for
+    OdeBuilder.rhs_implicit().  Compilation runs nvcc (about a minute for a small system); a cached plugin loads at once."""
+    import hashlib
+    L = lib()
+    h = hashlib.sha256()
+    h.update((kind + "\0" + struct + "\0" + source + "\0" + _build._sources_digest()).encode())
+    digest = h.hexdigest()[:20]
+    name = "user_" + digest
+    if name in MODELS:
+        return name
+    cache_dir = cache_dir or os.path.join(os.path.dirname(_build.LIB), "plugins")
+    os.makedirs(cache_dir, exist_ok=True)
+    src = os.path.join(cache_dir, name + ".h")
+    so = os.path.join(cache_dir, name + ".so")
+    if not os.path.exists(so):
+        with open(src, "w") as f:
+            f.write(source)
+        tmp = so + ".tmp.%d" % os.getpid()
+        check(L.dsb_model_library_build(src.encode(), MODEL_SOURCE_KINDS[kind], struct.encode(), CSRC_DIR.encode(), tmp.encode()))
+        os.replace(tmp, so)
+    mid = ctypes.c_int32()
+    check(L.dsb_model_library_load(so.encode(), ctypes.byref(mid)))
+    MODELS[name] = mid.value
+    return name
 
 
 def check(rc):

@@ -30,6 +30,12 @@ struct DsbBdfTables {
     double eta_reset;              // 20^1.25   convergence.rs:36-38
     double eta_reset_timestep;     // 100^1.25  convergence.rs:40-42
     double ic_steptol;             // eps^(2/3) line_search.rs:126
+    // Quotients of the step loop whose operands only take a handful of values, formed once on the host with the same
+    // IEEE division the reference executes at every use (the kernels then read them instead of dividing):
+    double inv_int[32];            // 1.0 / k: the exponent 1 / (niter - 1) of the convergence rate (convergence.rs:77) and
+                                   // RN(1 / i) for the divisions by the row index in Bdf::_compute_r (bdf.rs:433-463)
+    double safety[32];             // 0.9 (2 m + 1) / (2 m + niter), m = max_nonlinear_solver_iterations (bdf.rs:1351-1353)
+    double pi_ki[DSB_MAX_ORDER + 2], pi_kp[DSB_MAX_ORDER + 2];   // pi_control_* / order (runge_kutta.rs:1313-1335)
 };
 
 // Butcher tableau of an (E)SDIRK method (ode_solver/tableau.rs:41-159), evaluated on the host

@@ -46,6 +46,7 @@
 #include "dsb_lane.cuh"
 #include "dsb_roots.cuh"
 
+#define DSB_NSTATS_USED 13      // counters the kernels maintain (the C ABI rows have DSB_NSTATS = 16 slots)
 enum dsb_lane_state {
     L_FETCH = 0, L_POST, L_SELECT, L_RESCALE, L_JAC, L_TSTOP, L_OUTPUT, L_PREDICT, L_NEWTON, L_FINISH, L_IDLE,
     L_REINIT            // equations with a reset function: the is_state_modified branch of Bdf::step after a reset
@@ -59,11 +60,16 @@ struct BdfLayout {
     static constexpr int O_J = O_D + DSB_NDIFF * N;                 // rhs_jac[col][row]
     static constexpr int O_M = O_J + N * N;                         // mass_jac[col][row] (DAE only)
     static constexpr int O_LU = O_M + (M::HAS_MASS ? N * N : 0);    // LU factors [col][row]
+#ifdef DSB_LANE_LU_RCP
+    static constexpr int O_RCP = O_LU + N * N;                      // RN(1 / U_ii) for the back substitution (dsb_div_rcp)
+    static constexpr int O_Y = O_RCP + N;                           // state.y
+#else
     static constexpr int O_Y = O_LU + N * N;                        // state.y
+#endif
     static constexpr int O_YP = O_Y + N;                            // y_predict
     static constexpr int O_P = O_YP + N;                            // parameters
     static constexpr int O_ST = O_P + (NP > 0 ? NP : 1);            // statistics, two int32 per word
-    static constexpr int WORDS = O_ST + (DSB_NSTATS + 1) / 2;
+    static constexpr int WORDS = O_ST + (DSB_NSTATS_USED + 1) / 2;
     static constexpr int THREADS = LaneBlockShape<WORDS, N>::THREADS;
     static constexpr int MAXNREG = LaneBlockShape<WORDS, N>::MAXNREG;
 };
@@ -80,6 +86,15 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
     double* const sm = dsb_lane_smem + threadIdx.x;
 #define SM(w) sm[(w) * Lay::THREADS]
 #define DSB_DIV(a, b) DsbDivShared::div((a), (b))      // one shared division routine (code size, dsb_math.h)
+    // x / N (the mean of a weighted norm's squared terms) through the compile-time RN(1 / N): the same quotient in 5
+    // operations (dsb_math.h: dsb_div_rcp)
+    // (tried and rejected: x / N and the x / i of the rescale rows through dsb_div_rcp with constant reciprocals -- fewer
+    // operations, but ten more inline expansions: 59.4 -> 67.9 ms, the loop body no longer fits the instruction cache)
+#ifdef DSB_OPT_DIVN
+#define DSB_DIV_N(x) dsb_div_rcp((x), (double)N, 1.0 / (double)N)
+#else
+#define DSB_DIV_N(x) DSB_DIV((x), (double)N)
+#endif
 #ifndef DSB_NEWTON_DIV
 #define DSB_NEWTON_DIV DsbDivShared               // tuning experiment: inline expansion at the six hottest sites
 #endif
@@ -147,6 +162,23 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
             for (int i = 0; i < N; ++i) yo[i] = time_factor * SD(j + 1, i) + yo[i];
         }
     };
+    // one column of the solve_dense result (dense_write_out, method.rs:822-848): the state, or -- for equations with an
+    // output function (OdeEquations::out) -- out(y(tq), tq)
+    auto write_column = [&](int column, double tq, const double (&yo)[N]) {
+        if constexpr (dsb_model_nout<M>::has_out) {
+            constexpr int NOUT = dsb_model_nout<M>::value;
+            double pl_[NP > 0 ? NP : 1], o[NOUT];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) pl_[j] = SP(j);
+            M::out(yo, pl_, tq, o);
+#pragma unroll
+            for (int k = 0; k < NOUT; ++k) bb.ys[((int64_t)column * NOUT + k) * B + inst] = o[k];
+        } else {
+            (void)tq;
+#pragma unroll
+            for (int i = 0; i < N; ++i) bb.ys[((int64_t)column * N + i) * B + inst] = yo[i];
+        }
+    };
     // bdf.rs:694-731.  0 = nothing, 1 = TstopReached, 2 = step size must be clipped (rescale_factor set), < 0 = -status
     auto handle_tstop = [&](double ts) -> int {
         const double troundoff = 100.0 * eps * (dsb_abs(t) + dsb_abs(h));
@@ -163,10 +195,16 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
     };
     // runge_kutta.rs:1313-1335
     auto pi_controller_raw = [&](double err, int eff_order) -> double {
+#ifndef DSB_NO_HOST_TABLES     // A/B switch: 61.5 -> 59.4 ms per 10^6 Robertson instances (profiles/r2_lane_kernel_ab.log)
+        const double ki = pa.tab.pi_ki[eff_order];                 // pi_control_integral / order, divided on the host
+        const bool p_only = pa.opt.pi_control_proportional == 0.0 || !has_prev_error;
+        const double kp = p_only ? 0.0 : pa.tab.pi_kp[eff_order];
+#else
         const double order_f = (double)eff_order;
         const double ki = DSB_DIV(pa.opt.pi_control_integral, order_f);
         const bool p_only = pa.opt.pi_control_proportional == 0.0 || !has_prev_error;
         const double kp = p_only ? 0.0 : DSB_DIV(pa.opt.pi_control_proportional, order_f);
+#endif
         double v = dsb_pow(err, p_only ? -ki : -(ki + kp));
         if (!p_only) v = v * dsb_pow(prev_error_norm, kp);
         return v;
@@ -179,7 +217,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
             const double term = DSB_DIV(SD(j, i), dsb_abs(SY(i)) * pa.rtol + pa.atol[i]);
             acc += term * term;
         }
-        return DSB_DIV(acc, (double)N);
+        return DSB_DIV_N(acc);
     };
 
 #ifdef DSB_LANE_PROFILE          // warp-scheduler occupancy counters (warp-uniform values, lane 0 publishes them)
@@ -225,7 +263,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
             bb.ncols[inst] = col;
             if (NR > 0) bb.root_idx[inst] = root_found;
 #pragma unroll
-            for (int k = 0; k < DSB_NSTATS; ++k) bb.stats[(int64_t)k * B + inst] = st.v[k];
+            for (int k = 0; k < DSB_NSTATS_USED; ++k) bb.stats[(int64_t)k * B + inst] = st.v[k];
             state = L_FETCH;
         }
         // ================= FETCH: next instance from the work counter; Bdf::_new part 1 ==================
@@ -237,7 +275,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #pragma unroll
                 for (int j = 0; j < NP; ++j) SP(j) = bb.params[(int64_t)j * B + inst];
 #pragma unroll
-                for (int k = 0; k < DSB_NSTATS; ++k) st.v[k] = bb.stats[(int64_t)k * B + inst];
+                for (int k = 0; k < DSB_NSTATS_USED; ++k) st.v[k] = bb.stats[(int64_t)k * B + inst];
                 order = 1; n_equal_steps = 0;
                 t = pa.t0; h = bb.h0[inst];
                 conv.eta = pa.tab.eta_reset; conv.old_norm = 0.0; conv.reset();
@@ -369,7 +407,11 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
             for (int i = 1; i <= k; ++i) {
                 const double i_t = (double)i;
 #pragma unroll
+#ifdef DSB_OPT_RESCALE_RCP
+                for (int l = 1; l <= DSB_MAX_ORDER; ++l) rrow[l] = dsb_div_rcp(rrow[l] * (i_t - 1.0 - factor * (double)l), i_t, pa.tab.inv_int[i]);
+#else
                 for (int l = 1; l <= DSB_MAX_ORDER; ++l) rrow[l] = DSB_DIV(rrow[l] * (i_t - 1.0 - factor * (double)l), i_t);
+#endif
                 double di[N];
 #pragma unroll
                 for (int s = 0; s < N; ++s) di[s] = SD(i, s);
@@ -453,6 +495,9 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                     piv_packed |= (unsigned long long)lu.piv[j] << (4 * j);
 #pragma unroll
                     for (int i = 0; i < N; ++i) SLU(j, i) = lu.a[j][i];
+#ifdef DSB_LANE_LU_RCP
+                    SM(Lay::O_RCP + j) = lu.rinv[j];
+#endif
                 }
             }
             state = after_jac;
@@ -486,8 +531,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                         double yo[N];
                         while (!free_running && col < nt && bb.t_eval[col] <= t_root) {
                             interpolate(bb.t_eval[col], yo);
-#pragma unroll
-                            for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
+                            write_column(col, bb.t_eval[col], yo);
                             ++col;
                         }
                         interpolate(t_root, yo);
@@ -511,8 +555,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                         }
                         if (ended) {
                             if (col < nt) {
-#pragma unroll
-                                for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
+                                write_column(col, t_root, yo);
                                 ++col;
                             }
                             finish(DSB_STATUS_OK);
@@ -564,8 +607,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                 if ((is_forward && tq > t) || (!is_forward && tq < t)) { status = DSB_STATUS_INTERPOLATION_TIME_AFTER_CURRENT; break; }
                 double yo[N];
                 interpolate(tq, yo);
-#pragma unroll
-                for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
+                write_column(col, tq, yo);
                 ++col;
             }
             if (status != DSB_STATUS_OK) finish(status);
@@ -645,8 +687,15 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                 lu.piv[j] = (int)((piv_packed >> (4 * j)) & 15ull);
 #pragma unroll
                 for (int i = 0; i < N; ++i) lu.a[j][i] = SLU(j, i);
+#ifdef DSB_LANE_LU_RCP
+                lu.rinv[j] = SM(Lay::O_RCP + j);
+#endif
             }
+#ifdef DSB_LANE_LU_RCP
+            if (!lu.template solve<true>(delta)) {
+#else
             if (!lu.solve(delta)) {
+#endif
                 newton_ok = false; state = L_POST;              // LuSolveFailed
             } else {
                 double acc = 0.0;
@@ -657,12 +706,16 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                     const double term = DSB_NEWTON_DIV::div(delta[i], dsb_abs(SYP(i)) * pa.rtol + pa.atol[i]);
                     acc += term * term;
                 }
-                const double norm = dsb_sqrt(DSB_DIV(acc, (double)N));
+                const double norm = dsb_sqrt(DSB_DIV_N(acc));
                 // Convergence::check_new_iteration (convergence.rs:68-139) with its pow() hoisted to one call site
                 conv.niter += 1;
                 const bool have_rate = conv.has_old_norm;
                 double px, py;
+#ifndef DSB_NO_HOST_TABLES     // A/B switch: 61.5 -> 59.4 ms per 10^6 Robertson instances (profiles/r2_lane_kernel_ab.log)
+                if (have_rate) { px = DSB_DIV(norm, conv.old_norm); py = conv.niter <= 32 ? pa.tab.inv_int[(conv.niter - 1) & 31] : DSB_DIV(1.0, (double)(conv.niter - 1)); }
+#else
                 if (have_rate) { px = DSB_DIV(norm, conv.old_norm); py = DSB_DIV(1.0, (double)(conv.niter - 1)); }
+#endif
                 else { const double min_eta = 1e4 * eps; px = (conv.eta < min_eta) ? min_eta : conv.eta; py = 0.8; }
                 const double pw = dsb_pow(px, py);
                 int s = LANE_CONTINUE;
@@ -696,12 +749,19 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                         const double term = DSB_DIV(d[i], dsb_abs(SY(i)) * pa.rtol + pa.atol[i]);
                         acc += term * term;
                     }
-                    const double err = DSB_DIV(acc, (double)N) * pa.tab.error_const2[ord - 1];
+                    const double err = DSB_DIV_N(acc) * pa.tab.error_const2[ord - 1];
                     error_norm = (0.0 < err) ? err : 0.0;
                 }
-                const double maxiter = (double)conv.max_iter;
-                const double niter = (double)conv.niter;
-                safety = DSB_DIV(0.9 * (2.0 * maxiter + 1.0), 2.0 * maxiter + niter);
+#ifndef DSB_NO_HOST_TABLES     // A/B switch: 61.5 -> 59.4 ms per 10^6 Robertson instances (profiles/r2_lane_kernel_ab.log)
+                if (conv.niter < 32) {
+                    safety = pa.tab.safety[conv.niter];             // 0.9 (2 m + 1) / (2 m + niter), divided on the host
+                } else
+#endif
+                {
+                    const double maxiter = (double)conv.max_iter;
+                    const double niter = (double)conv.niter;
+                    safety = DSB_DIV(0.9 * (2.0 * maxiter + 1.0), 2.0 * maxiter + niter);
+                }
                 if (error_norm <= 1.0) {
                     // ---- accepted: _update_diff, state.y <- PREDICTOR (quirk Q1) ----
 #pragma unroll
@@ -756,6 +816,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #undef DSB_PROF_BLOCK
 #undef SM
 #undef DSB_DIV
+#undef DSB_DIV_N
 #undef SD
 #undef SJ
 #undef SMM

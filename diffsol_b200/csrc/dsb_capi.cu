@@ -5,6 +5,7 @@
 // host<->device copies of the `*_host` entry points.  There is NO CPU fallback: every solve runs
 // the sm_100a kernels; without a CUDA device the calls fail with DSB_ERR.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cmath>
 #include <cstdio>
@@ -59,6 +60,28 @@ struct dsb_batch {
 };
 
 namespace {
+
+// ---- equation sets loaded at run time (model plugins: dsb_inst.cu compiled for a user's source) -----------------------------
+struct PluginModel {
+    void* handle;
+    dsb_launch_fn launch;
+    void (*dims)(int*, int*, int*, int*);
+    int (*coloring)(double, DsbProblemArgs*, int*, int32_t*, uint8_t*);
+    std::string path;
+};
+std::vector<PluginModel>& plugins() { static std::vector<PluginModel> v; return v; }
+const PluginModel* plugin_of(int model) {
+    const int k = model - DSB_MODEL_PLUGIN_ID0;
+    return (k >= 0 && k < (int)plugins().size()) ? &plugins()[(size_t)k] : nullptr;
+}
+// fill_problem_args (dsb_host_setup.h) asks here for the sparsity pattern and colouring of a plugin model
+int plugin_coloring_hook(const dsb_problem& pr, DsbProblemArgs* pa, int* probes, std::vector<int32_t>* color_full, std::vector<uint8_t>* nz_full) {
+    const PluginModel* pm = plugin_of(pr.model);
+    if (!pm) return DSB_BAD_ARG;
+    color_full->assign((size_t)pr.n, 0); nz_full->assign((size_t)pr.n * pr.n, 0);
+    pm->coloring(pr.t0, pa, probes, color_full->data(), nz_full->data());
+    return DSB_OK;
+}
 
 struct DimsOf {
     int *n, *np, *hm, *nout;
@@ -192,7 +215,8 @@ int dsb_problem_new(int model, dsb_problem** out) {
     if (!out) return fail(DSB_BAD_ARG, "out is NULL");
     int n = 0, np = 0, hm = 0, nout = 0;
     DimsOf f{&n, &np, &hm, &nout};
-    if (!dsb_dispatch_model(model, f)) return fail(DSB_BAD_ARG, "unknown model id");
+    if (const PluginModel* pm = plugin_of(model)) pm->dims(&n, &np, &hm, &nout);
+    else if (!dsb_dispatch_model(model, f)) return fail(DSB_BAD_ARG, "unknown model id");
     dsb_problem* p = new (std::nothrow) dsb_problem();
     if (!p) return fail(DSB_ERR, "out of memory");
     p->model = model; p->n = n; p->np = np; p->has_mass = hm; p->nout = nout;
@@ -239,6 +263,55 @@ int dsb_problem_set_options(dsb_problem* p, const dsb_options* opt) {
 int dsb_problem_get_options(const dsb_problem* p, dsb_options* opt) {
     if (!p || !opt) return fail(DSB_BAD_ARG, "NULL argument");
     *opt = p->opt; return DSB_OK;
+}
+
+// ---- user equation sets ("DiffSL modules drop in") -------------------------------------------------------
+// The source is compiled by nvcc for sm_100a into ONE instantiation of the kernel families (csrc/dsb_inst.cu with the
+// user's text in place of a built-in functor) and linked into a shared object that this library loads; the kernels that
+// integrate a user model are therefore the same hand-written kernels, specialised by the compiler for its size and
+// functions -- no interpreter, no enum entry, no rebuild of this library.
+int dsb_model_library_build(const char* source_path, int32_t kind, const char* struct_name, const char* csrc_dir,
+                            const char* out_path) {
+    if (!source_path || !csrc_dir || !out_path) return fail(DSB_BAD_ARG, "NULL argument");
+    if (kind != DSB_MODEL_SOURCE_FUNCTOR && kind != DSB_MODEL_SOURCE_DIFFSL) return fail(DSB_BAD_ARG, "unknown source kind");
+    if (kind == DSB_MODEL_SOURCE_FUNCTOR && (!struct_name || !*struct_name)) return fail(DSB_BAD_ARG, "struct_name is required for a functor source");
+    for (const char* q : {source_path, csrc_dir, out_path, struct_name ? struct_name : ""})
+        for (const char* c = q; *c; ++c)
+            if (*c == '"' || *c == '\'' || *c == '`' || *c == '$' || *c == ';' || *c == '\n') return fail(DSB_BAD_ARG, "unsupported character in a path or name");
+    const char* nvcc = getenv("NVCC");
+    std::string cmd = std::string(nvcc && *nvcc ? nvcc : "nvcc") +
+        " -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --fmad=false -std=c++17 -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math"
+        " -diag-suppress 128 -shared -I'" + csrc_dir + "' -DDSB_USER_MODEL_SOURCE='\"" + source_path + "\"'";
+    if (kind == DSB_MODEL_SOURCE_DIFFSL) cmd += " -DDSB_USER_DIFFSL";
+    else cmd += std::string(" -DDSB_USER_MODEL=") + struct_name;
+    cmd += std::string(" '") + csrc_dir + "/dsb_inst.cu' -o '" + out_path + "' 2>&1";
+    FILE* pipe = popen(cmd.c_str(), "r");
+    if (!pipe) return fail(DSB_ERR, "cannot run nvcc");
+    std::string log; char buf[512];
+    while (fgets(buf, sizeof(buf), pipe)) log += buf;
+    const int rc = pclose(pipe);
+    if (rc != 0) return fail(DSB_ERR, "nvcc failed on the model source:\n" + log.substr(0, 4000));
+    return DSB_OK;
+}
+
+int dsb_model_library_load(const char* library_path, int32_t* model_out) {
+    if (!library_path || !model_out) return fail(DSB_BAD_ARG, "NULL argument");
+    for (size_t k = 0; k < plugins().size(); ++k)
+        if (plugins()[k].path == library_path) { *model_out = DSB_MODEL_PLUGIN_ID0 + (int)k; return DSB_OK; }
+    void* h = dlopen(library_path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) return fail(DSB_ERR, std::string("dlopen: ") + dlerror());
+    PluginModel pm;
+    pm.handle = h; pm.path = library_path;
+    int (*abi)(void) = (int (*)(void))dlsym(h, "dsb_plugin_abi");
+    pm.launch = (dsb_launch_fn)dlsym(h, "dsb_plugin_launch");
+    pm.dims = (void (*)(int*, int*, int*, int*))dlsym(h, "dsb_plugin_dims");
+    pm.coloring = (int (*)(double, DsbProblemArgs*, int*, int32_t*, uint8_t*))dlsym(h, "dsb_plugin_coloring");
+    if (!abi || !pm.launch || !pm.dims || !pm.coloring) { dlclose(h); return fail(DSB_ERR, "not a diffsol_b200 model library (symbols missing)"); }
+    if (abi() != 2) { dlclose(h); return fail(DSB_ERR, "model library built against another version of csrc/ (rebuild it)"); }
+    plugins().push_back(pm);
+    dsb_host::plugin_coloring() = &plugin_coloring_hook;
+    *model_out = DSB_MODEL_PLUGIN_ID0 + (int)plugins().size() - 1;
+    return DSB_OK;
 }
 
 int dsb_batch_new(const dsb_problem* p, int64_t nbatch, int32_t device, dsb_batch** out) {
@@ -364,7 +437,8 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     DSB_CUDA(cudaMemsetAsync(ys_dev, 0xFF, (size_t)nt * b->prob.nout * b->B * 8, stream));
     b->last_launches = 0;
     DSB_CUDA(cudaEventRecord(b->ev0, stream));
-    if (b->prob.model < 0 || b->prob.model >= DSB_MODEL_COUNT) return fail(DSB_BAD_ARG, "unknown model id");
+    const PluginModel* pm = plugin_of(b->prob.model);
+    if (!pm && (b->prob.model < 0 || b->prob.model >= DSB_MODEL_COUNT)) return fail(DSB_BAD_ARG, "unknown model id");
     std::vector<double> atol_full((size_t)b->prob.n);
     for (int i = 0; i < b->prob.n; ++i) atol_full[i] = b->prob.atol.size() == 1 ? b->prob.atol[0] : b->prob.atol[i];
     if (const char* q = getenv("DSB_EXEC_MODE")) b->coop.exec_mode = atoi(q);
@@ -372,8 +446,8 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     b->coop.nz_host = nz_full.empty() ? nullptr : nz_full.data();      // test hook: 1 = lane kernels, 2 = cooperative
     b->coop.ys_im = ys_im; b->coop.ys_im_used = nullptr;
     if (wrote_im) *wrote_im = 0;
-    cudaError_t lerr = g_launch_table[b->prob.model](&pa, &bb, method, stream, b->ev_mid, b->work_counter, &b->coop,
-                                                     atol_full.data(), &b->last_launches);
+    const dsb_launch_fn launch = pm ? pm->launch : g_launch_table[b->prob.model];
+    cudaError_t lerr = launch(&pa, &bb, method, stream, b->ev_mid, b->work_counter, &b->coop, atol_full.data(), &b->last_launches);
     if (lerr == cudaErrorNotSupported) return fail(DSB_ERR, "this execution mode is not available for this equation set and method (thread per instance: n <= 16; banded thread per instance: component-wise equations with a declared band, n > 16; banded warp per instance: the same, BDF, no reset function; block per instance: n <= 512)");
     if (lerr != cudaSuccess) return fail(DSB_ERR, std::string("kernel launch: ") + cudaGetErrorString(lerr));
     if (b->coop.ys_im_used) {

@@ -31,7 +31,7 @@ namespace dsb_host {
 // bdf.rs:253-276 (kappa, gamma, alpha, error_const2), bdf.rs:433-463 (U = R(order, 1)),
 // convergence.rs:36-42 (eta resets), line_search.rs:126 (steptol).  Host code of this file is compiled
 // with -ffp-contract=off so these are the same doubles the oracle computes.
-inline void build_tables(DsbBdfTables* tb) {
+inline void build_tables(DsbBdfTables* tb, const dsb_options* opt = nullptr) {
     const double kappa[6] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
     tb->alpha[0] = 0.0; tb->gamma[0] = 0.0; tb->error_const2[0] = 1.0;
     for (int i = 1; i <= DSB_MAX_ORDER; ++i) {
@@ -60,6 +60,19 @@ inline void build_tables(DsbBdfTables* tb) {
     tb->eta_reset = dsb_pow(20.0, 1.25);
     tb->eta_reset_timestep = dsb_pow(100.0, 1.25);
     tb->ic_steptol = dsb_pow(std::numeric_limits<double>::epsilon(), 2.0 / 3.0);
+    for (int k = 0; k < 32; ++k) {
+        tb->inv_int[k] = k > 0 ? 1.0 / (double)k : 0.0;
+        tb->safety[k] = 0.0;
+    }
+    for (int o = 0; o < DSB_MAX_ORDER + 2; ++o) { tb->pi_ki[o] = 0.0; tb->pi_kp[o] = 0.0; }
+    if (opt) {
+        const double maxiter = (double)opt->max_nonlinear_solver_iterations;
+        for (int k = 0; k < 32; ++k) tb->safety[k] = 0.9 * (2.0 * maxiter + 1.0) / (2.0 * maxiter + (double)k);
+        for (int o = 1; o < DSB_MAX_ORDER + 2; ++o) {
+            tb->pi_ki[o] = opt->pi_control_integral / (double)o;
+            tb->pi_kp[o] = opt->pi_control_proportional / (double)o;
+        }
+    }
 }
 
 // ode_solver/tableau.rs:41-97 (tr_bdf2) and :101-159 (esdirk34); same expressions as the reference
@@ -151,6 +164,10 @@ struct ColoringOf {
     }
 };
 
+// set by dsb_capi.cu when a model plugin is loaded: pattern + colouring of a model that is not in the built-in registry
+typedef int (*plugin_coloring_fn)(const dsb_problem&, DsbProblemArgs*, int*, std::vector<int32_t>*, std::vector<uint8_t>*);
+inline plugin_coloring_fn& plugin_coloring() { static plugin_coloring_fn f = nullptr; return f; }
+
 inline int fill_problem_args(const dsb_problem& pr, int64_t B, int nt, DsbProblemArgs* pa, int* probes,
                       std::vector<int32_t>* color_full, std::vector<uint8_t>* nz_full) {
     std::memset(pa, 0, sizeof(*pa));
@@ -158,12 +175,14 @@ inline int fill_problem_args(const dsb_problem& pr, int64_t B, int nt, DsbProble
     pa->rtol = pr.rtol; pa->t0 = pr.t0; pa->h0 = pr.h0;
     for (int i = 0; i < pr.n && i < DSB_MAX_STATES; ++i) pa->atol[i] = pr.atol.size() == 1 ? pr.atol[0] : pr.atol[i];
     pa->opt = pr.opt;
-    build_tables(&pa->tab);
+    build_tables(&pa->tab, &pr.opt);
     pa->use_coloring = pr.use_coloring;
     *probes = 0;
     if (pr.use_coloring) {
         ColoringOf f{&pr, pa, probes, color_full, nz_full};
-        if (!dsb_dispatch_model(pr.model, f)) return DSB_BAD_ARG;
+        if (pr.model >= DSB_MODEL_PLUGIN_ID0) {
+            if (!plugin_coloring() || plugin_coloring()(pr, pa, probes, color_full, nz_full) != DSB_OK) return DSB_BAD_ARG;
+        } else if (!dsb_dispatch_model(pr.model, f)) return DSB_BAD_ARG;
     } else {
         // dense assembly (op/nonlinear_op.rs:211-220) expressed as one colour per column with a full pattern, so
         // that the lane kernels carry a single assembly loop (dsb_lane.cuh:lane_jacobian_to; the banded kernel

@@ -1,4 +1,8 @@
-// dsb_inst.cu -- instantiates the lane kernels for ONE equation set: compile with -DDSB_INST=<model id>.
+// dsb_inst.cu -- instantiates the kernel families for ONE equation set.
+//   built-in equation sets: compile with -DDSB_INST=<model id> (one translation unit per model, diffsol_b200/build.py);
+//   USER equation sets, at run time (dsb_capi.cu: dsb_model_library_build): -DDSB_USER_MODEL_SOURCE="<file>" plus either
+//   -DDSB_USER_MODEL=<struct name> (a functor with the interface of dsb_models.h) or -DDSB_USER_DIFFSL (the DiffSL symbol
+//   table, dsb_diffsl_adapter.h) -- the same kernels, exported from a plugin shared object as dsb_plugin_* (bottom).
 #include <cmath>
 #include <cstdlib>
 #include <limits>
@@ -16,13 +20,25 @@
 #include "dsb_sdirk_kernel.cuh"
 #include "dsb_wband_bdf_kernel.cuh"
 
-#ifndef DSB_INST
-#error "compile with -DDSB_INST=<model id>"
-#endif
 #define DSB_CAT_(a, b) a##b
 #define DSB_CAT(a, b) DSB_CAT_(a, b)
 
+#if defined(DSB_USER_MODEL_SOURCE)
+#include DSB_USER_MODEL_SOURCE
+#if defined(DSB_USER_DIFFSL)
+#include "dsb_diffsl_adapter.h"
+typedef DsbDiffslModel InstModel;
+#else
+typedef DSB_USER_MODEL InstModel;
+#endif
+#define DSB_LAUNCH_SYMBOL dsb_plugin_launch
+#else
+#ifndef DSB_INST
+#error "compile with -DDSB_INST=<model id>"
+#endif
 typedef dsb_model_by_id<DSB_INST>::type InstModel;
+#define DSB_LAUNCH_SYMBOL DSB_CAT(dsb_launch_model_, DSB_INST)
+#endif
 
 constexpr bool kLaneCapable = InstModel::N <= 16;
 
@@ -103,6 +119,26 @@ static cudaError_t launch_coop_bdf(const DsbProblemArgs* pa, const DsbBatchBuffe
     *launches += 1;
     return cudaGetLastError();
 }
+
+// A model plugin of a small system (n <= 16) carries the on-chip lane kernels only: the block-per-instance kernel is the
+// largest of the families and would double the run-time compilation for a path such a model never takes by default.
+#if defined(DSB_USER_MODEL_SOURCE)
+constexpr bool kCoopBuilt = !kLaneCapable;
+#else
+constexpr bool kCoopBuilt = true;
+#endif
+template <class M, bool BUILT> struct CoopLauncher {
+    static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, cudaStream_t, cudaEvent_t, unsigned long long*, DsbCoopState*,
+                           const double*, int*, bool) {
+        return cudaErrorNotSupported;
+    }
+};
+template <class M> struct CoopLauncher<M, true> {
+    static cudaError_t run(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, cudaStream_t stream, cudaEvent_t mid,
+                           unsigned long long* work_counter, DsbCoopState* coop, const double* atol_host, int* launches, bool rk) {
+        return launch_coop_bdf<M>(pa, bb, stream, mid, work_counter, coop, atol_host, launches, rk);
+    }
+};
 
 // banded lane kernel (one thread per instance, state in global memory): component-wise models without a mass
 // matrix that declare a band, n > 16
@@ -383,7 +419,10 @@ template <class M> struct LaneLauncher<M, true> {
     }
 };
 
-cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method,
+#if defined(DSB_USER_MODEL_SOURCE)
+extern "C"
+#endif
+cudaError_t DSB_LAUNCH_SYMBOL(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method,
                                                  cudaStream_t stream, cudaEvent_t mid, unsigned long long* work_counter,
                                                  DsbCoopState* coop, const double* atol_host, int* launches) {
     coop->ys_im_used = nullptr;
@@ -401,15 +440,35 @@ cudaError_t DSB_CAT(dsb_launch_model_, DSB_INST)(const DsbProblemArgs* pa, const
     } else if (coop->exec_mode == 3) {
         return cudaErrorNotSupported;
     }
-    // root functions (events) are built into every kernel family; output functions into the banded lane kernels and the
-    // block-per-instance kernel (the on-chip lane kernels hold n <= 16 states and return them all)
+    // root functions (events) and output functions (OdeEquations::out) are built into every kernel family
     // reset functions (re-initialisation after an event) are built into the on-chip lane kernels (BDF and SDIRK) and the
     // block-per-instance kernel, not into the banded lane kernels
     const bool use_coop = coop->exec_mode == 2 || (coop->exec_mode == 0 && !kLaneCapable);
     if (use_coop) {
         // block-per-instance kernel: Bdf, or Sdirk (TR-BDF2 / ESDIRK34)
-        return launch_coop_bdf<InstModel>(pa, bb, stream, mid, work_counter, coop, atol_host, launches, method != DSB_METHOD_BDF);
+        return CoopLauncher<InstModel, kCoopBuilt>::run(pa, bb, stream, mid, work_counter, coop, atol_host, launches, method != DSB_METHOD_BDF);
     }
-    if (dsb_model_nout<InstModel>::has_out) return cudaErrorNotSupported;
     return LaneLauncher<InstModel, kLaneCapable>::run(pa, bb, method, stream, mid, work_counter, launches);
 }
+
+#if defined(DSB_USER_MODEL_SOURCE)
+// ---- what a model plugin exports besides its launcher (dsb_capi.cu: dsb_model_library_load) ----------------------------------
+extern "C" {
+int dsb_plugin_abi(void) { return 2; }
+void dsb_plugin_dims(int* n, int* np, int* has_mass, int* nout) {
+    *n = InstModel::N; *np = InstModel::NP; *has_mass = InstModel::HAS_MASS ? 1 : 0; *nout = dsb_model_nout<InstModel>::value;
+}
+// sparsity pattern by NaN probe + greedy colouring with the model's own functor on the host (dsb_host_setup.h: ColoringOf);
+// color_full [n], nz_full [n * n] (column-major pattern bytes)
+int dsb_plugin_coloring(double t0, DsbProblemArgs* pa, int* probes, int32_t* color_full, uint8_t* nz_full) {
+    dsb_problem pr;
+    pr.t0 = t0;
+    std::vector<int32_t> cf; std::vector<uint8_t> nz;
+    dsb_host::ColoringOf f{&pr, pa, probes, &cf, &nz};
+    f.template operator()<InstModel>();
+    for (size_t k = 0; k < cf.size(); ++k) color_full[k] = cf[k];
+    for (size_t k = 0; k < nz.size(); ++k) nz_full[k] = nz[k];
+    return (int)cf.size();
+}
+}
+#endif

@@ -76,6 +76,7 @@ template <int N, class Div = DsbDivInline>
 struct LaneLU {
     double a[N][N];
     int piv[N];          // row i was swapped with row piv[i] (piv[i] == i: no swap)
+    double rinv[N];      // RN(1 / U_ii) as dsb_rcp() would return it (NaN outside its proven range); filled by factor()
 
     // a must already hold the matrix to factor.
     DSB_DEV void factor() {
@@ -94,6 +95,7 @@ struct LaneLU {
                 diag = (p == r) ? a[i][r] : diag;
             });
             piv[i] = (diag == 0.0) ? i : p;
+            rinv[i] = 0.0;
             if (diag != 0.0) {                              // else: no non-zero entries on this column
                 // row swap i <-> p written as selects so that every register index stays static
                 dsb_static_for<i + 1, N>([&](auto R_) {
@@ -107,6 +109,7 @@ struct LaneLU {
                     });
                 });
                 const double inv_diag = 1.0 / diag;
+                rinv[i] = dsb_rcp_from(diag, inv_diag);
 #pragma unroll
                 for (int r = i + 1; r < N; ++r) a[i][r] *= inv_diag;
 #pragma unroll
@@ -119,7 +122,9 @@ struct LaneLU {
         });
     }
 
-    // false <=> zero on U's diagonal (LaError::LuSolveFailed)
+    // false <=> zero on U's diagonal (LaError::LuSolveFailed).  RCP: divide through the stored reciprocals (rinv must hold
+    // what factor() left there): the same quotients in 5 operations each (dsb_math.h: dsb_div_rcp)
+    template <bool RCP = false>
     DSB_DEV bool solve(double (&b)[N]) const {
         dsb_static_for<0, N>([&](auto I_) {
             constexpr int i = decltype(I_)::value;
@@ -143,7 +148,7 @@ struct LaneLU {
             const double diag = a[i][i];
             if (diag == 0.0) ok = false;
             if (ok) {
-                const double coeff = Div::div(b[i], diag);
+                const double coeff = RCP ? dsb_div_rcp(b[i], diag, rinv[i]) : Div::div(b[i], diag);
                 b[i] = coeff;
                 const double mc = -coeff;
 #pragma unroll

@@ -20,9 +20,11 @@
 #if defined(__CUDACC__)
 #define DSB_HD __host__ __device__ __forceinline__
 #define DSB_HD_NOINLINE static __host__ __device__ __noinline__
+#define DSB_SYMBOL extern "C" __host__ __device__      // a function of a DiffSL symbol table (dsb_diffsl_adapter.h)
 #else
 #define DSB_HD inline
 #define DSB_HD_NOINLINE inline
+#define DSB_SYMBOL extern "C"
 #endif
 
 #include "dsb_pow_tables.inc"

@@ -110,6 +110,23 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
     int root_found = -1;
 #pragma unroll
     for (int r = 0; r < (NR > 0 ? NR : 1); ++r) rf.g0[r] = 0.0;
+    // one column of the solve_dense result (dense_write_out, method.rs:822-848): the state, or -- for equations with an
+    // output function (OdeEquations::out) -- out(y(tq), tq)
+    auto write_column = [&](int column, double tq, const double (&yo)[N]) {
+        if constexpr (dsb_model_nout<M>::has_out) {
+            constexpr int NOUT = dsb_model_nout<M>::value;
+            double pl_[NP > 0 ? NP : 1], o[NOUT];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) pl_[j] = SP(j);
+            M::out(yo, pl_, tq, o);
+#pragma unroll
+            for (int k = 0; k < NOUT; ++k) bb.ys[((int64_t)column * NOUT + k) * B + inst] = o[k];
+        } else {
+            (void)tq;
+#pragma unroll
+            for (int i = 0; i < N; ++i) bb.ys[((int64_t)column * N + i) * B + inst] = yo[i];
+        }
+    };
     // interpolate_inplace (runge_kutta.rs:1080-1127; :962-981 beta dense output, :1004-1024 Hermite) on [old_t, t]
     auto interpolate = [&](double tq, double (&yo)[N]) {
         const double dt = t - old_t;
@@ -409,8 +426,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                         double yo[N];
                         while (!free_running && col < nt && bb.t_eval[col] <= t_root) {
                             interpolate(bb.t_eval[col], yo);
-#pragma unroll
-                            for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
+                            write_column(col, bb.t_eval[col], yo);
                             ++col;
                         }
                         interpolate(t_root, yo);
@@ -450,8 +466,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                         }
                         if (ended) {
                             if (col < nt) {
-#pragma unroll
-                                for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
+                                write_column(col, t_root, yo);
                                 ++col;
                             }
                             finish(DSB_STATUS_OK);
@@ -489,8 +504,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                 }
                 double yo[N];
                 interpolate(tq, yo);
-#pragma unroll
-                for (int i = 0; i < N; ++i) bb.ys[((int64_t)col * N + i) * B + inst] = yo[i];
+                write_column(col, tq, yo);
                 ++col;
             }
             if (status != DSB_STATUS_OK) finish(status);

@@ -72,6 +72,14 @@ class OdeBuilder:
         self._model = model
         return self
 
+    def rhs_implicit_source(self, source, kind="functor", struct="UserModel"):
+        """User equations as SOURCE TEXT (the counterpart of OdeBuilder::rhs_implicit with closures, builder.rs:192-200, and
+        of a DiffSL module, ode_equations/diffsl.rs): kind "functor" = a struct `struct` with the closure signatures as
+        DSB_HD static functions (csrc/dsb_models.h), kind "diffsl" = the DiffSL symbol table as C (csrc/dsb_diffsl_adapter.h).
+        nvcc compiles it for sm_100a at run time into the library's own kernel families (capi.load_model_source)."""
+        self._model = capi.load_model_source(source, kind=kind, struct=struct)
+        return self
+
     def p(self, p):
         self._p = np.asarray(p, dtype=np.float64)
         return self

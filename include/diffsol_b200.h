@@ -127,6 +127,26 @@ int dsb_problem_set_use_coloring(dsb_problem* p, int32_t use_coloring);      /* 
 int dsb_problem_set_options(dsb_problem* p, const dsb_options* opt);        /* OdeBuilder::ode_options / ic_options */
 int dsb_problem_get_options(const dsb_problem* p, dsb_options* opt);
 
+/* ---- user equation sets: "user RHS closures and DiffSL-JIT modules drop in" -------------------------------------------------
+ * The reference takes equations as Rust closures (builder.rs:192-200) or as a compiled DiffSL module consumed through its
+ * symbol table (crates/diffsol/src/ode_equations/diffsl.rs:1072-1098, 1221-1232; the table:
+ * crates/diffsol-c/tests/external-dynamic-logistic/src/lib.rs:15-600).  Neither can run inside a kernel as it is, so the
+ * equations cross this boundary as SOURCE TEXT that nvcc compiles for sm_100a at run time into one instantiation of the
+ * library's kernel families:
+ *   DSB_MODEL_SOURCE_DIFFSL   the DiffSL symbol table as C: set_u0 / rhs / rhs_grad / set_inputs [/ mass / calc_out /
+ *                             calc_stop], every definition prefixed with DSB_SYMBOL, dimensions as #define
+ *                             DSB_DIFFSL_STATES / _INPUTS / _DATA / _OUTPUTS / _STOP / _HAS_MASS (csrc/dsb_diffsl_adapter.h)
+ *   DSB_MODEL_SOURCE_FUNCTOR  a struct with the closure signatures (x, p, t, y), (x, p, t, v, y), (x, p, t, beta, y), (p, t, y)
+ *                             of builder.rs:192-200 as DSB_HD static member functions (csrc/dsb_models.h shows 22 of them)
+ * dsb_model_library_build writes a shared object; dsb_model_library_load registers it and returns a model id that
+ * dsb_problem_new accepts like a built-in one.  `csrc_dir` = the directory of this library's kernel sources
+ * (diffsol_b200/csrc).  Build needs nvcc on PATH (or $NVCC); loading a built library does not. */
+enum { DSB_MODEL_SOURCE_FUNCTOR = 0, DSB_MODEL_SOURCE_DIFFSL = 1 };
+#define DSB_MODEL_PLUGIN_ID0 1000
+int dsb_model_library_build(const char* source_path, int32_t kind, const char* struct_name, const char* csrc_dir,
+                            const char* out_path);
+int dsb_model_library_load(const char* library_path, int32_t* model_out);
+
 /* ---- batch = Context::nbatch (diffsol-la/src/context/mod.rs:27) + per-instance parameters + all
  * device state of the batched solver, resident on ONE GPU.  Not thread-safe; all work is enqueued on
  * the stream given to the solve call; only the get_* / *_host calls synchronise. */

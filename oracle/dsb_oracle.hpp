@@ -107,6 +107,11 @@ Model make_model() {
     return m;
 }
 bool model_by_id(int id, Model* out);
+// Equation sets that are not compiled into the oracle: a shared object built from the USER'S source (the same text the
+// CUDA library compiles for the device, oracle/oracle.py: load_user_model) exports `void orc_plugin_model(orc::Model*)`;
+// its Model is registered under an id >= ORC_PLUGIN_ID0.
+constexpr int ORC_PLUGIN_ID0 = 1000;
+int register_plugin_model(const Model& m);
 std::vector<int> greedy_coloring(const std::vector<std::pair<int, int>>& non_zeros, int n);   // 1-based colour per column
 
 // ---- OdeSolverOptions / InitialConditionSolverOptions (ode_solver/problem.rs:15-152) -----------

@@ -1,6 +1,8 @@
 // oracle/dsb_oracle_capi.cpp -- TEST INFRASTRUCTURE (see dsb_oracle.hpp).
 // extern "C" entry points used through ctypes by tests/, __graft_entry__.smoke() and
 // bench.py's cpu_baseline / --impl reference legs.
+#include <dlfcn.h>
+
 #include "dsb_oracle.hpp"
 
 #include <atomic>
@@ -292,6 +294,18 @@ int orc_batch_solve_dense_roots(const orc_problem_desc* d, const double* params,
         for (auto& th : pool) th.join();
     }
     return ST_OK;
+}
+
+// dlopen a model plugin (built by oracle/oracle.py: load_user_model from the user's source) -> model id, or -1
+int orc_load_model_plugin(const char* path) {
+    void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) return -1;
+    typedef void (*fn_t)(orc::Model*);
+    fn_t fn = (fn_t)dlsym(h, "orc_plugin_model");
+    if (!fn) return -1;
+    orc::Model m;
+    fn(&m);
+    return orc::register_plugin_model(m);
 }
 
 int orc_num_threads() { return (int)std::thread::hardware_concurrency(); }

@@ -15,7 +15,17 @@ struct ModelMaker {
 };
 }  // namespace
 
+// user equation sets loaded at run time (orc_load_model_plugin, dsb_oracle_capi.cpp): ids ORC_PLUGIN_ID0, +1, ...
+static std::vector<Model>& plugin_models() { static std::vector<Model> v; return v; }
+int register_plugin_model(const Model& m) { plugin_models().push_back(m); return ORC_PLUGIN_ID0 + (int)plugin_models().size() - 1; }
+
 bool model_by_id(int id, Model* out) {
+    if (id >= ORC_PLUGIN_ID0) {
+        const size_t k = (size_t)(id - ORC_PLUGIN_ID0);
+        if (k >= plugin_models().size()) return false;
+        *out = plugin_models()[k];
+        return true;
+    }
     ModelMaker f{out};
     return dsb_dispatch_model(id, f);
 }

@@ -123,6 +123,8 @@ def lib():
         L.orc_powi.argtypes = [ctypes.c_double, ctypes.c_int]
         L.orc_squared_norm.restype = ctypes.c_double
         L.orc_squared_norm.argtypes = [dp, dp, dp, ctypes.c_double, ctypes.c_int]
+        L.orc_load_model_plugin.restype = ctypes.c_int
+        L.orc_load_model_plugin.argtypes = [ctypes.c_char_p]
         L.orc_lu_solve.argtypes = [dp, ctypes.c_int, dp]
         L.orc_lu_factor.argtypes = [dp, ctypes.c_int, dp, ctypes.POINTER(ctypes.c_int32)]
         L.orc_num_threads.restype = ctypes.c_int
@@ -286,6 +288,38 @@ def batch_solve_dense_roots(desc, params, t_eval, nthreads=0):
         status.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _dp(roots))
     assert rc == 0
     return out, stats, status, roots[:, 0].copy(), roots[:, 1].astype(np.int32), roots[:, 2].astype(np.int32)
+
+
+def load_user_model(source, kind="functor", struct="UserModel", name=None):
+    """Compile a USER equation set for the host and register it with the oracle -> model name usable with make_desc().
+    `source` is the same text the CUDA library compiles for the device (diffsol_b200.OdeBuilder.rhs_implicit_source):
+    kind "functor": a struct `struct` with the interface of csrc/dsb_models.h; kind "diffsl": the DiffSL symbol table
+    (csrc/dsb_diffsl_adapter.h).  TEST INFRASTRUCTURE: the oracle stays the checker of the CUDA path."""
+    import hashlib
+    build()
+    digest = hashlib.sha256((kind + "\0" + struct + "\0" + source).encode()).hexdigest()[:16]
+    name = name or "user_" + digest
+    if name in MODELS:
+        return name
+    out_dir = os.path.join(_HERE, "_ref", "plugins")
+    os.makedirs(out_dir, exist_ok=True)
+    src = os.path.join(out_dir, "m_%s.cpp" % digest)
+    so = os.path.join(out_dir, "m_%s.so" % digest)
+    csrc = os.path.join(os.path.dirname(_HERE), "diffsol_b200", "csrc")
+    if kind == "diffsl":
+        body = '#include "%s/dsb_math.h"\n%s\n#include "%s/dsb_diffsl_adapter.h"\ntypedef DsbDiffslModel OrcUserModel;\n' % (csrc, source, csrc)
+    else:
+        body = '#include "%s/dsb_math.h"\n%s\ntypedef %s OrcUserModel;\n' % (csrc, source, struct)
+    with open(src, "w") as f:
+        f.write('#include "%s/dsb_oracle.hpp"\n%s\nextern "C" void orc_plugin_model(orc::Model* m) { *m = orc::make_model<OrcUserModel>(); }\n'
+                % (_HERE, body))
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-mfma",
+                               "-shared", src, "-o", so])
+    mid = lib().orc_load_model_plugin(so.encode())
+    assert mid >= 1000, "oracle model plugin failed to load: " + so
+    MODELS[name] = mid
+    return name
 
 
 def num_threads():

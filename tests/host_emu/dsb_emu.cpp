@@ -56,7 +56,7 @@ struct EmuCall {
             unsigned long long work_counter = 0;
             bool ran = false;
             if (kernel == 1) {
-                if constexpr (N <= 16 && !dsb_model_nout<M>::has_out) {
+                if constexpr (N <= 16) {
                     if (method == DSB_METHOD_BDF) {
                         blockDim.x = BdfLayout<M>::THREADS;
                         dsb_init_kernel<M>(pa, bb, 1);
