@@ -86,12 +86,19 @@ def test_robertson_sweep_bit_exact(dsb, oracle, model, tol):
     assert (status_o == 0).all()
     assert np.array_equal(solver.statistics_array()[:, :13], stats_o[:, :13])
     assert np.array_equal(ys, ys_o)
-    # against the reference-literal libm pow: counters may differ for a small fraction of instances
+    # against the reference-literal libm pow (what diffsol's own powf calls): a last-ulp difference in pow very occasionally
+    # flips a step-size decision -- measured 1e-4 of the instances; the bound is 1e-3, on a sample big enough
+    # to resolve it
+    B2 = 20000
+    p2 = sweeps.robertson_sweep(np.arange(B2))
+    s2 = _build(dsb, case, p=p2).bdf()
+    ys2 = s2.solve_dense(sweeps.ROBERTSON_T_EVAL)
     desc0 = oracle.make_desc(model, powmode=0, **tolkw)
-    ys_0, stats_0, _ = oracle.batch_solve_dense(desc0, p, sweeps.ROBERTSON_T_EVAL)
-    frac = np.mean((solver.statistics_array()[:, :13] != stats_0[:, :13]).any(axis=1))
-    print("fraction of instances whose counters differ from the libm-pow oracle: %.4f" % frac)
-    assert frac < 0.25
+    ys_0, stats_0, _ = oracle.batch_solve_dense(desc0, p2, sweeps.ROBERTSON_T_EVAL)
+    frac = np.mean((s2.statistics_array()[:, :13] != stats_0[:, :13]).any(axis=1))
+    print("fraction of instances whose counters differ from the libm-pow oracle: %.5f" % frac)
+    assert frac <= 1e-3
+    ys, ys_0 = ys2, ys_0
     w = np.abs(ys_0) * tolkw["rtol"] + np.array(tolkw["atol"])
     assert (np.abs(ys - ys_0) <= 20 * w).all()
     # device-side reduction of a statistic agrees with the per-instance array
