@@ -56,6 +56,9 @@ struct dsb_batch {
     int last_launches = 0;
     bool have_timing = false;
     int sparsity_probe_jac_muls = 0;
+    // the *_host entry points split big batches into chunks that run as child batches on their own streams, so that the
+    // host -> device copy of one chunk's parameters and the device -> host copy of another's results overlap the kernels
+    std::vector<dsb_batch*> chunks; std::vector<cudaStream_t> chunk_streams; std::vector<cudaEvent_t> chunk_done;
     DsbCoopState coop = {0, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, nullptr};
 };
 
@@ -357,6 +360,9 @@ int dsb_batch_new(const dsb_problem* p, int64_t nbatch, int32_t device, dsb_batc
 int dsb_batch_free(dsb_batch* b) {
     if (!b) return DSB_OK;
     cudaSetDevice(b->device);
+    for (dsb_batch* c : b->chunks) dsb_batch_free(c);
+    for (cudaStream_t st : b->chunk_streams) cudaStreamDestroy(st);
+    for (cudaEvent_t ev : b->chunk_done) cudaEventDestroy(ev);
     cudaFree(b->params); cudaFree(b->y0); cudaFree(b->dy0); cudaFree(b->h0);
     cudaFree(b->fin_t); cudaFree(b->fin_h); cudaFree(b->fin_order); cudaFree(b->root_idx); cudaFree(b->ncols);
     cudaFree(b->stats); cudaFree(b->status); cudaFree(b->work_counter); cudaFree(b->coop.ws_mem); cudaFree(b->coop.atol_dev); cudaFree(b->coop.color_dev); cudaFree(b->coop.wb_mem); cudaFree(b->coop.ys_im_own); cudaFree(b->t_eval); cudaFree(b->ys_own); cudaFree(b->stage);
@@ -575,18 +581,15 @@ int dsb_batch_debug_words(dsb_batch* b, uint64_t* words_host) {
     return DSB_OK;
 }
 
-static int solve_host_impl(dsb_batch* b, int32_t method, const double* params_host, int32_t nparams,
-                           const double* t_eval, int32_t nt, double* ys_host, int64_t* stats_host,
-                           int32_t* status_host, int free_running) {
-    if (!b || !ys_host) return fail(DSB_BAD_ARG, "NULL argument");
-    if (!t_eval || nt < 1) return fail(DSB_BAD_ARG, "t_eval must hold at least one time");
-    if (method != DSB_METHOD_BDF && method != DSB_METHOD_TR_BDF2 && method != DSB_METHOD_ESDIRK34)
-        return fail(DSB_BAD_ARG, "unknown method");
-    DSB_CUDA(cudaSetDevice(b->device));
+// One chunk (or the whole batch) of a *_host call on `stream`: parameters up, kernels, results down.  Nothing here waits
+// for the device; the caller synchronises.  The instance-major staging block doubles as the kernels' result block when
+// they write that layout (warp-per-instance banded kernel).
+static int solve_host_enqueue(dsb_batch* b, int32_t method, const double* params_host, int32_t nparams, const double* t_eval,
+                              int32_t nt, double* ys_host, int64_t* stats_host, int32_t* status_host, int free_running,
+                              cudaStream_t stream) {
     const int n = b->prob.nout;                       // rows of a result column
     const size_t ys_bytes = (size_t)nt * n * b->B * 8;
-    size_t stage_need = ys_bytes;
-    if ((size_t)b->B * DSB_NSTATS * 8 > stage_need) stage_need = (size_t)b->B * DSB_NSTATS * 8;
+    size_t stage_need = ys_bytes + (size_t)b->B * DSB_NSTATS * 8;
     if ((size_t)b->B * (nparams > 0 ? nparams : 1) * 8 > stage_need) stage_need = (size_t)b->B * nparams * 8;
     if (ensure_stage(b, stage_need) != DSB_OK) return DSB_ERR;
     if (b->ys_own_bytes < ys_bytes) {
@@ -596,33 +599,106 @@ static int solve_host_impl(dsb_batch* b, int32_t method, const double* params_ho
     }
     int extra = 0;
     if (nparams > 0) {
-        if (!params_host || nparams != b->prob.np) return fail(DSB_BAD_ARG, "parameter shape mismatch");
-        DSB_CUDA(cudaMemcpyAsync(b->stage, params_host, (size_t)b->B * nparams * 8, cudaMemcpyHostToDevice, 0));
-        int rc = dsb_batch_set_params_device(b, (const double*)b->stage, b->B, nparams, nullptr);
+        DSB_CUDA(cudaMemcpyAsync(b->stage, params_host, (size_t)b->B * nparams * 8, cudaMemcpyHostToDevice, stream));
+        int rc = dsb_batch_set_params_device(b, (const double*)b->stage, b->B, nparams, stream);
         if (rc != DSB_OK) return rc;
         ++extra;
     }
     int wrote_im = 0;
-    int rc = solve_impl(b, method, t_eval, nt, b->ys_own, nullptr, free_running, (double*)b->stage, &wrote_im);
+    int rc = solve_impl(b, method, t_eval, nt, b->ys_own, stream, free_running, (double*)b->stage, &wrote_im);
     if (rc != DSB_OK) return rc;
-    if (wrote_im) {
-        DSB_CUDA(cudaMemcpyAsync(ys_host, b->stage, ys_bytes, cudaMemcpyDeviceToHost, 0));
-    } else {
+    if (!wrote_im) {
         const int m = nt * n;
         dim3 grid((unsigned)((b->B + 31) / 32), (unsigned)((m + 31) / 32)), block(32, 8);
-        dsb_to_instance_major_kernel<<<grid, block>>>(b->ys_own, (double*)b->stage, b->B, m);
+        dsb_to_instance_major_kernel<<<grid, block, 0, stream>>>(b->ys_own, (double*)b->stage, b->B, m);
         DSB_CUDA(cudaGetLastError());
         ++extra;
-        DSB_CUDA(cudaMemcpyAsync(ys_host, b->stage, ys_bytes, cudaMemcpyDeviceToHost, 0));
     }
+    DSB_CUDA(cudaMemcpyAsync(ys_host, b->stage, ys_bytes, cudaMemcpyDeviceToHost, stream));
     if (stats_host) {
-        if (dsb_batch_get_stats_device(b, (int64_t*)b->stage, nullptr) != DSB_OK) return DSB_ERR;
+        int64_t* stats_stage = (int64_t*)((char*)b->stage + ys_bytes);
+        if (dsb_batch_get_stats_device(b, stats_stage, stream) != DSB_OK) return DSB_ERR;
         ++extra;
-        DSB_CUDA(cudaMemcpyAsync(stats_host, b->stage, (size_t)b->B * DSB_NSTATS * 8, cudaMemcpyDeviceToHost, 0));
+        DSB_CUDA(cudaMemcpyAsync(stats_host, stats_stage, (size_t)b->B * DSB_NSTATS * 8, cudaMemcpyDeviceToHost, stream));
     }
-    if (status_host) DSB_CUDA(cudaMemcpyAsync(status_host, b->status, (size_t)b->B * 4, cudaMemcpyDeviceToHost, 0));
-    DSB_CUDA(cudaStreamSynchronize(0));
+    if (status_host) DSB_CUDA(cudaMemcpyAsync(status_host, b->status, (size_t)b->B * 4, cudaMemcpyDeviceToHost, stream));
     b->last_launches += extra;
+    return DSB_OK;
+}
+
+static int solve_host_impl(dsb_batch* b, int32_t method, const double* params_host, int32_t nparams,
+                           const double* t_eval, int32_t nt, double* ys_host, int64_t* stats_host,
+                           int32_t* status_host, int free_running) {
+    if (!b || !ys_host) return fail(DSB_BAD_ARG, "NULL argument");
+    if (!t_eval || nt < 1) return fail(DSB_BAD_ARG, "t_eval must hold at least one time");
+    if (method != DSB_METHOD_BDF && method != DSB_METHOD_TR_BDF2 && method != DSB_METHOD_ESDIRK34)
+        return fail(DSB_BAD_ARG, "unknown method");
+    if (nparams > 0 && (!params_host || nparams != b->prob.np)) return fail(DSB_BAD_ARG, "parameter shape mismatch");
+    DSB_CUDA(cudaSetDevice(b->device));
+    // OPTIONAL pipelining (DSB_HOST_CHUNKS = 2..16, default off): the batch runs as child batches on their own streams --
+    // the persistent kernels of consecutive chunks hand the SMs over as their work counters run out, and the copies of
+    // the other chunks run underneath (host buffers should be pinned for that).  Measured on one B200, 10^6 Robertson
+    // instances (24 MB up, 148 MB down, pinned): 62.4 ms direct, 65.1 ms in 4 chunks -- each chunk's kernel pays its own
+    // tail of late-finishing instances, which costs more than the 3 ms of copies it hides -- hence off by default; it is
+    // there for hosts whose device -> host path is slow or shared (8 ranks on one PCIe root).
+    int nchunks = 1;
+    if (const char* q = getenv("DSB_HOST_CHUNKS")) nchunks = atoi(q);
+    if (nchunks > 16) nchunks = 16;
+    if (nchunks < 2 || b->B < (int64_t)nchunks * 65536) {
+        int rc = solve_host_enqueue(b, method, params_host, nparams, t_eval, nt, ys_host, stats_host, status_host, free_running, 0);
+        if (rc != DSB_OK) return rc;
+        DSB_CUDA(cudaStreamSynchronize(0));
+        return DSB_OK;
+    }
+    const int n = b->prob.nout;
+    if ((int)b->chunks.size() != nchunks) {
+        for (dsb_batch* c : b->chunks) dsb_batch_free(c);
+        for (cudaStream_t st : b->chunk_streams) cudaStreamDestroy(st);
+        for (cudaEvent_t ev : b->chunk_done) cudaEventDestroy(ev);
+        b->chunks.clear(); b->chunk_streams.clear(); b->chunk_done.clear();
+        for (int k = 0; k < nchunks; ++k) {
+            const int64_t k0 = b->B * k / nchunks, k1 = b->B * (k + 1) / nchunks;
+            dsb_batch* c = nullptr;
+            if (dsb_batch_new(&b->prob, k1 - k0, b->device, &c) != DSB_OK) return DSB_ERR;
+            b->chunks.push_back(c);
+            cudaStream_t st; cudaEvent_t ev;
+            DSB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            DSB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            b->chunk_streams.push_back(st); b->chunk_done.push_back(ev);
+        }
+    }
+    DSB_CUDA(cudaEventRecord(b->ev0, 0));
+    DSB_CUDA(cudaEventRecord(b->ev_mid, 0));
+    b->last_launches = 0;
+    for (int k = 0; k < nchunks; ++k) {
+        dsb_batch* c = b->chunks[(size_t)k];
+        cudaStream_t st = b->chunk_streams[(size_t)k];
+        const int64_t k0 = b->B * k / nchunks;
+        c->prob = b->prob; c->coop.exec_mode = b->coop.exec_mode;
+        DSB_CUDA(cudaStreamWaitEvent(st, b->ev0, 0));
+        if (nparams == 0 && b->prob.np > 0)        // parameters set earlier on the parent: hand the chunk its columns
+            for (int j = 0; j < b->prob.np; ++j)
+                DSB_CUDA(cudaMemcpyAsync(c->params + (size_t)j * c->B, b->params + (size_t)j * b->B + k0, (size_t)c->B * 8, cudaMemcpyDeviceToDevice, st));
+        int rc = solve_host_enqueue(c, method, params_host ? params_host + (size_t)k0 * nparams : nullptr, nparams, t_eval, nt,
+                                    ys_host + (size_t)k0 * nt * n, stats_host ? stats_host + (size_t)k0 * DSB_NSTATS : nullptr,
+                                    status_host ? status_host + k0 : nullptr, free_running, st);
+        if (rc != DSB_OK) return rc;
+        // the parent's per-instance arrays (read by the getters after the call) take the chunk's rows
+        DSB_CUDA(cudaMemcpy2DAsync(b->stats + k0, (size_t)b->B * 4, c->stats, (size_t)c->B * 4, (size_t)c->B * 4, DSB_NSTATS, cudaMemcpyDeviceToDevice, st));
+        DSB_CUDA(cudaMemcpyAsync(b->status + k0, c->status, (size_t)c->B * 4, cudaMemcpyDeviceToDevice, st));
+        DSB_CUDA(cudaMemcpyAsync(b->fin_t + k0, c->fin_t, (size_t)c->B * 8, cudaMemcpyDeviceToDevice, st));
+        DSB_CUDA(cudaMemcpyAsync(b->fin_h + k0, c->fin_h, (size_t)c->B * 8, cudaMemcpyDeviceToDevice, st));
+        DSB_CUDA(cudaMemcpyAsync(b->fin_order + k0, c->fin_order, (size_t)c->B * 4, cudaMemcpyDeviceToDevice, st));
+        DSB_CUDA(cudaMemcpyAsync(b->root_idx + k0, c->root_idx, (size_t)c->B * 4, cudaMemcpyDeviceToDevice, st));
+        DSB_CUDA(cudaMemcpyAsync(b->ncols + k0, c->ncols, (size_t)c->B * 4, cudaMemcpyDeviceToDevice, st));
+        DSB_CUDA(cudaEventRecord(b->chunk_done[(size_t)k], st));
+        DSB_CUDA(cudaStreamWaitEvent(0, b->chunk_done[(size_t)k], 0));
+        b->last_launches += c->last_launches;
+        b->sparsity_probe_jac_muls = c->sparsity_probe_jac_muls;
+    }
+    DSB_CUDA(cudaEventRecord(b->ev1, 0));
+    b->have_timing = true;
+    DSB_CUDA(cudaStreamSynchronize(0));
     return DSB_OK;
 }
 

@@ -426,6 +426,14 @@ struct SpmTables99 {
 #endif
     }
 };
+// tuning of the warp-per-instance kernel for this model (measured, n = 200, 250 000 instances: 8 warps x chunk 2 (255 registers)
+// 832 ms; 12 warps x chunk 1 (160 registers, no spills) 616 ms; 12 warps x chunk 2 spills 1 KB per lane: 976 ms)
+#ifndef DSB_SPM_WBAND_WARPS
+#define DSB_SPM_WBAND_WARPS 12
+#endif
+#ifndef DSB_SPM_WBAND_CHUNK
+#define DSB_SPM_WBAND_CHUNK 1
+#endif
 template <class Tab>
 struct ModelSpmT {
     static constexpr int NR = Tab::NR;
@@ -433,7 +441,8 @@ struct ModelSpmT {
     static constexpr bool HAS_MASS = false;
     static constexpr bool COMPONENTWISE = true;
     static constexpr int BAND_KL = 1, BAND_KU = 1;      // df/dy is tridiagonal (checked against the probed pattern at launch)
-    static constexpr int WBAND_MAX_WARPS = 8;           // warp-per-instance kernel: 255 registers per lane (dsb_wband_bdf_kernel.cuh)
+    static constexpr int WBAND_MAX_WARPS = DSB_SPM_WBAND_WARPS;   // warp-per-instance kernel (dsb_wband_bdf_kernel.cuh): warps per SM and
+    static constexpr int WBAND_CHUNK = DSB_SPM_WBAND_CHUNK;       // components per chunk of its passes over the difference array
     template <class X>
     DSB_HD static double diffusion_i(int i, const X& x) {        // i in 2 .. N - 1
         const bool neg = i < 2 + NR;

@@ -63,6 +63,9 @@
 template <class M, class = void> struct dsb_wband_max_warps { static constexpr int value = 64; };
 template <class M> struct dsb_wband_max_warps<M, decltype((void)M::WBAND_MAX_WARPS)> { static constexpr int value = M::WBAND_MAX_WARPS; };
 
+template <class M, class = void> struct dsb_wband_chunk { static constexpr int value = DSB_WBAND_CHUNK; };
+template <class M> struct dsb_wband_chunk<M, decltype((void)M::WBAND_CHUNK)> { static constexpr int value = M::WBAND_CHUNK; };
+
 template <class M>
 struct WBandLayout {
     static constexpr int N = M::N, NP = M::NP;
@@ -83,11 +86,20 @@ struct WBandLayout {
     static constexpr bool D_SHARED = FIT_D_SHARED >= DSB_WBAND_MIN_WARPS_D_SHARED;
     static constexpr int O_D = 0;                                   // D[DSB_NDIFF][NS] (when D_SHARED)
     static constexpr int O_Y = D_SHARED ? DSB_NDIFF * NS : 0;       // state.y
-    static constexpr int O_YP = O_Y + NS;                           // y_predict
-    static constexpr int O_YC = O_YP + NS;                          // Newton iterate
-    static constexpr int O_PSI = O_YC + NS;                         // psi - y_predict
-    static constexpr int O_DL = O_PSI + NS;                         // Newton residual / update, norm terms, output staging
-    static constexpr int O_AB = O_DL + NS;                          // factors [LDAB][NS]
+    // the predictor and psi - y_predict are only ever read component by component: for the larger systems they follow D
+    // into the global-memory slot (two more L2 passes per Newton iteration, 12 instead of 10 instances per SM at n = 256)
+    static constexpr int O_YC = O_Y + NS;                           // Newton iterate
+    static constexpr int O_DL = O_YC + NS;                          // Newton residual / update, norm terms, output staging
+    // ... unless the warps are capped below what shared memory would hold anyway (M::WBAND_MAX_WARPS: the battery model)
+    static constexpr int MAXW_MODEL = dsb_wband_max_warps<M>::value;
+    static constexpr int MAXW_KIND = D_SHARED ? DSB_WBAND_MAX_WARPS : DSB_WBAND_MAX_WARPS_D_GLOBAL;
+    static constexpr int MAXW = MAXW_MODEL < MAXW_KIND ? MAXW_MODEL : MAXW_KIND;
+    static constexpr int FIT_VEC_SHARED = (DSB_WBAND_SMEM_BYTES - BLOCK_WORDS * 8) / (((WORDS_NO_D + 15) / 16 * 16) * 8);
+    static constexpr bool VEC_SHARED = D_SHARED || FIT_VEC_SHARED >= MAXW;
+    static constexpr int O_YP = O_DL + NS;                          // y_predict (when VEC_SHARED)
+    static constexpr int O_PSI = O_YP + NS;                         // psi - y_predict (when VEC_SHARED)
+    static constexpr int O_VEC_END = VEC_SHARED ? O_PSI + NS : O_DL + NS;
+    static constexpr int O_AB = O_VEC_END;                          // factors [LDAB][NS]
     static constexpr int O_RCP = O_AB + LDAB * NS;                  // RN(1 / U_jj) (dsb_math.h: dsb_rcp)
     static constexpr int O_PIV = O_RCP + NS;                        // int32 pivot offsets (row j interchanged with row j + piv[j])
     static constexpr int O_RU = O_PIV + NS / 2;                     // rows / columns 1..5 of R U (rescale)
@@ -96,12 +108,10 @@ struct WBandLayout {
                                                                     // interchanges, the rows of the first 8 of them
     static constexpr int WORDS = (O_FLAG + 5 + 15) / 16 * 16;       // slices start on 128-byte boundaries
     static constexpr int FIT = (DSB_WBAND_SMEM_BYTES - BLOCK_WORDS * 8) / (WORDS * 8);
-    // equations whose right-hand side needs many registers (coefficient tables: the battery model) cap the warps at 8
-    // (255 registers per lane) through M::WBAND_MAX_WARPS: at 12 warps (168 registers) they spill ~1 KB per lane into a
-    // local-memory footprint that no longer fits L1 (measured: n = 200, 976 ms at 12 warps, 828 ms at 8)
-    static constexpr int MAXW_MODEL = dsb_wband_max_warps<M>::value;
-    static constexpr int MAXW_KIND = D_SHARED ? DSB_WBAND_MAX_WARPS : DSB_WBAND_MAX_WARPS_D_GLOBAL;
-    static constexpr int MAXW = MAXW_MODEL < MAXW_KIND ? MAXW_MODEL : MAXW_KIND;
+    // (MAXW and the chunk size of the passes over D can be set per equation set, M::WBAND_MAX_WARPS / M::WBAND_CHUNK: what
+    // matters is that the kernel stays inside the registers the warp count leaves -- 168 per lane at 9-12 warps -- because
+    // a spilled kernel's local-memory footprint does not fit the few KB of L1 next to 200+ KB of shared memory; see the
+    // battery model's figures in dsb_models.h)
     static constexpr int WARPS = FIT < 1 ? 1 : (FIT < MAXW ? FIT : MAXW);
     static constexpr int THREADS = WARPS * DSB_WLANES;
     static constexpr size_t SMEM_BYTES = (size_t)(BLOCK_WORDS + WORDS * WARPS) * 8;
@@ -109,7 +119,9 @@ struct WBandLayout {
     // global-memory slot of one warp (L2-resident: the resident warps' slots are a few tens of MB): the difference array
     // D[DSB_NDIFF][NS] (unless D_SHARED), df/dy band [LDJ][NS], then M band [LDJ][NS] (DAEs)
     static constexpr int G_D = 0;
-    static constexpr int G_J = G_D + (D_SHARED ? 0 : DSB_NDIFF * NS);
+    static constexpr int G_YP = G_D + (D_SHARED ? 0 : DSB_NDIFF * NS);
+    static constexpr int G_PSI = G_YP + (VEC_SHARED ? 0 : NS);
+    static constexpr int G_J = G_PSI + (VEC_SHARED ? 0 : NS);
     static constexpr int G_M = G_J + LDJ * NS;
     static constexpr int G_WORDS = G_M + (M::HAS_MASS ? LDJ * NS : 0);
     static_assert(KL >= 1 && KL <= 2 && KU >= 1 && KU <= 2, "register windows are sized for kl, ku <= 2");
@@ -206,28 +218,6 @@ DSB_DEV void dsb_mbar_wait(double* bar, unsigned parity) {
 #endif
 }
 
-// indexable view of a shared-memory vector (what the component-wise equations read)
-struct WVec {
-    const double* base;
-    __device__ __forceinline__ double operator[](int k) const { return base[k]; }
-};
-// y + (psi - y0), the argument of the mass matrix in the BDF residual (op/bdf.rs:240-256), formed on the fly
-struct WSumVec {
-    const double* a; const double* b;
-    __device__ __forceinline__ double operator[](int k) const { return a[k] + b[k]; }
-};
-// the NDEP state components an output / root function declares, held in registers
-template <class M, int NDEP>
-struct WDepVec {
-    double v[NDEP > 0 ? NDEP : 1];
-    __device__ __forceinline__ double operator[](int k) const {
-        double r = v[0];
-#pragma unroll
-        for (int q = 1; q < NDEP; ++q) r = (k == M::dep(q)) ? v[q] : r;
-        return r;
-    }
-};
-
 // The difference array, df/dy and M live in the warp's global-memory slot and stay in L2: their loads and stores bypass
 // L1 (ld.global.cg / st.global.cg), which -- next to 200+ KB of shared memory -- is only a few tens of KB and holds the
 // equations' coefficient tables and the column metadata (streaming D through it evicted them: 1.45x slower on n = 200).
@@ -246,6 +236,29 @@ DSB_DEV void dsb_st_l2(double* p, double v) {
 #endif
 }
 
+// indexable view of a shared-memory vector (what the component-wise equations read)
+struct WVec {
+    const double* base;
+    __device__ __forceinline__ double operator[](int k) const { return base[k]; }
+};
+// y + (psi - y0), the argument of the mass matrix in the BDF residual (op/bdf.rs:240-256), formed on the fly
+template <bool B_GLOBAL>
+struct WSumVec {
+    const double* a; const double* b;            // a in shared memory; b in shared memory or (B_GLOBAL) in the warp's global slot
+    __device__ __forceinline__ double operator[](int k) const { return a[k] + (B_GLOBAL ? dsb_ld_l2(b + k) : b[k]); }
+};
+// the NDEP state components an output / root function declares, held in registers
+template <class M, int NDEP>
+struct WDepVec {
+    double v[NDEP > 0 ? NDEP : 1];
+    __device__ __forceinline__ double operator[](int k) const {
+        double r = v[0];
+#pragma unroll
+        for (int q = 1; q < NDEP; ++q) r = (k == M::dep(q)) ? v[q] : r;
+        return r;
+    }
+};
+
 // Lane-strided component loop in chunks: load(i) for U components of the lane first, then use(i, value) for each.  The
 // difference array lives in the warp's global-memory slot (L2): with the loads of a chunk issued back to back a pass over
 // it costs about one L2 round trip per chunk instead of one per component.  load() must not read what use() writes for
@@ -262,6 +275,7 @@ DSB_DEV void dsb_warp_for(const int lane, const int n, L&& load, F&& use) {
     }
 }
 struct WCols { double v[DSB_MAX_ORDER + 2]; };
+struct WColsYp { WCols c; double yp; };
 
 // ---- band LU on a shared-memory band, ONE lane ----------------------------------------------------------------------------
 // The arithmetic of dsb_band_lu.cuh (= nalgebra 0.35 `DMatrix::lu()` / `LU::solve_mut`, only operations with an exactly
@@ -507,9 +521,11 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
 #define SD_LD(j, i) (Lay::D_SHARED ? sm[Lay::O_D + (j) * NS + (i)] : dsb_ld_l2(&gslot[Lay::G_D + (j) * NS + (i)]))
 #define SD_ST(j, i, v) do { if (Lay::D_SHARED) sm[Lay::O_D + (j) * NS + (i)] = (v); else dsb_st_l2(&gslot[Lay::G_D + (j) * NS + (i)], (v)); } while (0)
 #define SY(i) sm[Lay::O_Y + (i)]
-#define SYP(i) sm[Lay::O_YP + (i)]
+#define SYP_LD(i) (Lay::VEC_SHARED ? sm[Lay::O_YP + (i)] : dsb_ld_l2(&gslot[Lay::G_YP + (i)]))
+#define SYP_ST(i, v) do { if (Lay::VEC_SHARED) sm[Lay::O_YP + (i)] = (v); else dsb_st_l2(&gslot[Lay::G_YP + (i)], (v)); } while (0)
 #define SYC(i) sm[Lay::O_YC + (i)]
-#define SPSI(i) sm[Lay::O_PSI + (i)]
+#define SPSI_LD(i) (Lay::VEC_SHARED ? sm[Lay::O_PSI + (i)] : dsb_ld_l2(&gslot[Lay::G_PSI + (i)]))
+#define SPSI_ST(i, v) do { if (Lay::VEC_SHARED) sm[Lay::O_PSI + (i)] = (v); else dsb_st_l2(&gslot[Lay::G_PSI + (i)], (v)); } while (0)
 #define SDL(i) sm[Lay::O_DL + (i)]
 #define SAB(j, r) sm[Lay::O_AB + (r) * NS + (j)]
 #define SRU(i, j) sm[Lay::O_RU + ((i) - 1) * 5 + ((j) - 1)]
@@ -521,7 +537,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
     int* const sflag = reinterpret_cast<int*>(sm + Lay::O_FLAG);
     double* const sbar = sm + Lay::O_BAR;
     const WVec vY{sm + Lay::O_Y}, vYC{sm + Lay::O_YC}, vDL{sm + Lay::O_DL};
-    const WSumVec vTMP{sm + Lay::O_YC, sm + Lay::O_PSI};
+    const WSumVec<!Lay::VEC_SHARED> vTMP{sm + Lay::O_YC, Lay::VEC_SHARED ? sm + Lay::O_PSI : gslot + Lay::G_PSI};
 
     const int64_t B = pa.nbatch;
     const int nt = pa.nt;
@@ -530,6 +546,8 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
     constexpr int NOUT = dsb_model_nout<M>::value;
     constexpr int NDEP = dsb_model_ndep<M>::value;
     constexpr int NR = dsb_model_nroots<M>::value;
+    constexpr int DCHUNK = dsb_wband_chunk<M>::value;                      // passes over the difference array (global loads unless D_SHARED)
+    constexpr int VCHUNK = Lay::VEC_SHARED ? 1 : 2 * DCHUNK;     // predictor / psi passes: chunked only when they are global loads
     constexpr bool BULK_OUT = !dsb_model_nout<M>::has_out && (N % 2 == 0);
 
 #if defined(__CUDA_ARCH__)
@@ -564,7 +582,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
     double rescale_factor = 1.0;
     int fin_status = DSB_STATUS_OK;
     int stores_in_flight = 0;           // bulk-async stores whose shared-memory source may still be read (lane 0's groups)
-    int stage_next = 0;                 // output staging rotates over the dead work vectors DL, YC, PSI
+    int stage_next = 0;                 // output staging alternates between the dead work vectors DL and YC
     auto finish = [&](int status) { fin_status = status; state = L_FINISH; };
     // the output staging vectors are about to be written by the integrator again
     auto drain_stores = [&]() {
@@ -618,7 +636,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
     auto dcol = [&](int j) -> const double* { return Lay::D_SHARED ? sm + Lay::O_D + j * NS : gslot + Lay::G_D + j * NS; };
     // x: a shared-memory vector, or (GLOBAL_X) a column of the difference array in the warp's global-memory slot
     auto weighted_norm = [&](auto GLOBAL_X, const double* x, const double* ref) -> double {
-        dsb_warp_for<DSB_WBAND_CHUNK, double>(lane, N, [&](int i) { return decltype(GLOBAL_X)::value ? dsb_ld_l2(x + i) : x[i]; }, [&](int i, double xi) {
+        dsb_warp_for<DCHUNK, double>(lane, N, [&](int i) { return decltype(GLOBAL_X)::value ? dsb_ld_l2(x + i) : x[i]; }, [&](int i, double xi) {
             const double term = DSB_DIV(xi, dsb_abs(ref[i]) * pa.rtol + satol[i]);
             SDL(i) = term * term;
         });
@@ -654,7 +672,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
     auto interpolate_to = [&](double tq, double* dst) {
         double tf[DSB_MAX_ORDER];
         time_factors(tq, tf);
-        dsb_warp_for<DSB_WBAND_CHUNK, WCols>(lane, N, load_cols, [&](int i, const WCols& c) { dst[i] = interpolate_cols(c, tf); });
+        dsb_warp_for<DCHUNK, WCols>(lane, N, load_cols, [&](int i, const WCols& c) { dst[i] = interpolate_cols(c, tf); });
         dsb_wsync();
     };
     // the same for the output and root functions: only the components they read when the equations declare them
@@ -688,20 +706,20 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
             dsb_wsync();                // DL is read by every lane above and rewritten by the next column
         } else if constexpr (BULK_OUT) {
             // stage the column in a dead work vector; it leaves through a bulk-async store while the warp goes on
-            if (stores_in_flight >= 3) {
-                if (lane == 0) dsb_bulk_store_wait_read<2>();
+            if (stores_in_flight >= 2) {
+                if (lane == 0) dsb_bulk_store_wait_read<1>();
                 dsb_wsync();
-                stores_in_flight = 2;
+                stores_in_flight = 1;
             }
-            double* const stage = sm + (stage_next == 0 ? Lay::O_DL : stage_next == 1 ? Lay::O_YC : Lay::O_PSI);
-            stage_next = stage_next == 2 ? 0 : stage_next + 1;
+            double* const stage = sm + (stage_next == 0 ? Lay::O_DL : Lay::O_YC);
+            stage_next = stage_next == 1 ? 0 : stage_next + 1;
             interpolate_to(tq, stage);
             if (lane == 0) dsb_bulk_store(dst, stage, N);
             stores_in_flight += 1;
         } else {
             double tf[DSB_MAX_ORDER];
             time_factors(tq, tf);
-            dsb_warp_for<DSB_WBAND_CHUNK, WCols>(lane, N, load_cols, [&](int i, const WCols& c) { dst[i] = interpolate_cols(c, tf); });
+            dsb_warp_for<DCHUNK, WCols>(lane, N, load_cols, [&](int i, const WCols& c) { dst[i] = interpolate_cols(c, tf); });
         }
     };
 
@@ -867,7 +885,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
                 }
             }
             dsb_wsync();
-            dsb_warp_for<DSB_WBAND_CHUNK, WCols>(lane, N, load_cols, [&](int s, const WCols& dc) {
+            dsb_warp_for<DCHUNK, WCols>(lane, N, load_cols, [&](int s, const WCols& dc) {
                 double nd[DSB_MAX_ORDER + 1];
 #pragma unroll
                 for (int j = 1; j <= DSB_MAX_ORDER; ++j) nd[j] = -0.0;      // (-0.0) + x == x: the first term is assigned
@@ -1121,7 +1139,7 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
             if (repredict) {
                 const int ord = order;
                 const double a = pa.tab.alpha[ord];
-                dsb_warp_for<DSB_WBAND_CHUNK, WCols>(lane, N, load_cols, [&](int i, const WCols& dc) {
+                dsb_warp_for<DCHUNK, WCols>(lane, N, load_cols, [&](int i, const WCols& dc) {
                     double yp = 0.0;
                     double ps = 0.0;
 #pragma unroll
@@ -1135,11 +1153,11 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
                     }
                     ps *= a;
                     ps -= yp;
-                    SYP(i) = yp; SPSI(i) = ps; SYC(i) = yp;
+                    SYP_ST(i, yp); SPSI_ST(i, ps); SYC(i) = yp;
                 });
                 t_predict = t + h;
             } else {
-                WFOR(i) SYC(i) = SYP(i);
+                dsb_warp_for<VCHUNK, double>(lane, N, [&](int i) { return SYP_LD(i); }, [&](int i, double v) { SYC(i) = v; });
             }
             dsb_wsync();
             state = L_NEWTON;
@@ -1157,11 +1175,11 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
             // delta = F(y) = M (y + psi - y0) - c f(t, y)   (op/bdf.rs:240-256)
             const double mc = -c;
             auto residual = [&]() {
-                WFOR(i) {
+                dsb_warp_for<VCHUNK, double>(lane, N, [&](int i) { return M::HAS_MASS ? 0.0 : SPSI_LD(i); }, [&](int i, double psi) {
                     const double f = M::rhs_i(i, vYC, pl, t_predict);
                     if constexpr (M::HAS_MASS) SDL(i) = M::mass_i(i, vTMP, pl, t_predict, mc, f);    // gemv_inplace(x, t, beta, y): y = M x + beta y
-                    else SDL(i) = (SYC(i) + SPSI(i)) + mc * f;
-                }
+                    else SDL(i) = (SYC(i) + psi) + mc * f;
+                });
                 dsb_wsync();
             };
             residual();
@@ -1189,13 +1207,13 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
             if (!ok) {
                 newton_ok = false; state = L_POST;              // LuSolveFailed
             } else {
-                WFOR(i) {
+                dsb_warp_for<VCHUNK, double>(lane, N, [&](int i) { return SYP_LD(i); }, [&](int i, double yp) {
                     const double dl = SDL(i);
                     SYC(i) = SYC(i) - dl;
                     // Newton norm weights use the PREDICTOR (line_search.rs:67, convergence.rs:64-66)
-                    const double term = DSB_DIV(dl, dsb_abs(SYP(i)) * pa.rtol + satol[i]);
+                    const double term = DSB_DIV(dl, dsb_abs(yp) * pa.rtol + satol[i]);
                     SDL(i) = term * term;
-                }
+                });
                 const double norm = dsb_sqrt(sum_terms());
                 // Convergence::check_new_iteration (convergence.rs:68-139)
                 conv.niter += 1;
@@ -1225,11 +1243,11 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
             if (newton_ok) {
                 const int ord = order;
                 {   // error_control: ||d||^2_w(state.y) * error_const2[order - 1], d = y - y_predict
-                    WFOR(i) {
-                        const double d = SYC(i) - SYP(i);
+                    dsb_warp_for<VCHUNK, double>(lane, N, [&](int i) { return SYP_LD(i); }, [&](int i, double yp) {
+                        const double d = SYC(i) - yp;
                         const double term = DSB_DIV(d, dsb_abs(SY(i)) * pa.rtol + satol[i]);
                         SDL(i) = term * term;
-                    }
+                    });
                     const double err = sum_terms() * pa.tab.error_const2[ord - 1];
                     error_norm = (0.0 < err) ? err : 0.0;
                 }
@@ -1238,12 +1256,15 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
                 safety = DSB_DIV(0.9 * (2.0 * maxiter + 1.0), 2.0 * maxiter + niter);
                 if (error_norm <= 1.0) {
                     // ---- accepted: _update_diff, state.y <- PREDICTOR (quirk Q1) ----
-                    dsb_warp_for<DSB_WBAND_CHUNK, WCols>(lane, N, [&](int i) {
-                        WCols dc = load_cols(i);
-                        dc.v[DSB_MAX_ORDER + 1] = SD_LD(ord + 1, i);        // the old D[:, ord + 1]
-                        return dc;
-                    }, [&](int i, const WCols& dc) {
-                        const double yp = SYP(i);
+                    dsb_warp_for<DCHUNK, WColsYp>(lane, N, [&](int i) {
+                        WColsYp r;
+                        r.c = load_cols(i);
+                        r.c.v[DSB_MAX_ORDER + 1] = SD_LD(ord + 1, i);       // the old D[:, ord + 1]
+                        r.yp = SYP_LD(i);
+                        return r;
+                    }, [&](int i, const WColsYp& r) {
+                        const WCols& dc = r.c;
+                        const double yp = r.yp;
                         const double d = SYC(i) - yp;
                         double above = d;                                   // the new D[:, ord + 1]
                         SD_ST(ord + 2, i, d - dc.v[DSB_MAX_ORDER + 1]);
@@ -1291,9 +1312,11 @@ dsb_wband_bdf_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, cons
 #undef SD_LD
 #undef SD_ST
 #undef SY
-#undef SYP
+#undef SYP_LD
+#undef SYP_ST
 #undef SYC
-#undef SPSI
+#undef SPSI_LD
+#undef SPSI_ST
 #undef SDL
 #undef SAB
 #undef SRU

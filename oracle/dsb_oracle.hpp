@@ -174,6 +174,7 @@ struct Problem {
 double squared_norm(const double* x, const double* y, const double* atol, double rtol, int n);
 
 // ---- nalgebra 0.35 LU (restated; call sites diffsol-la/src/linear_solver/nalgebra/lu.rs:36,50) --
+extern int g_fused_lu_updates;            // experiment switch, see dsb_oracle_core.cpp
 struct DenseLU {
     int n = 0;
     Vec lu;                                  // col-major

@@ -308,6 +308,9 @@ int orc_load_model_plugin(const char* path) {
     return orc::register_plugin_model(m);
 }
 
+// experiment switch (tools/dmma_rounding_check.py): fused multiply-adds in the LU trailing updates; returns the old value
+int orc_set_fused_lu_updates(int on) { const int old = orc::g_fused_lu_updates; orc::g_fused_lu_updates = on; return old; }
+
 int orc_num_threads() { return (int)std::thread::hardware_concurrency(); }
 
 double orc_pow(double x, double y, int powmode) { Math m; m.powmode = powmode; return m.pow(x, y); }

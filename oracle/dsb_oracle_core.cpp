@@ -136,6 +136,10 @@ void Problem::mass_matrix(double t, double* M) const {
 // nalgebra-0.35 src/linalg/lu.rs `LU::new`, `gauss_step`, `gauss_step_swap`; pivot = icamax (first
 // strict maximum of |.|); sub-column scaled by the RECIPROCAL of the pivot; rank-1 update column by
 // column as axpy(-pivot_row[k], coeffs, 1).
+// EXPERIMENT SWITCH (tools/dmma_rounding_check.py): the trailing updates of the factorisation with a FUSED multiply-add,
+// i.e. the arithmetic an FP64 tensor-core (DMMA) trailing update would perform.  The reference path is unfused.
+int g_fused_lu_updates = 0;
+
 void DenseLU::factor(const double* A, int n_) {
     n = n_;
     lu.assign(A, A + (size_t)n * n);
@@ -156,14 +160,16 @@ void DenseLU::factor(const double* A, int n_) {
             for (int k = i + 1; k < n; ++k) {
                 std::swap(at(i, k), at(piv, k));
                 double mpk = -at(i, k);
-                for (int r = i + 1; r < n; ++r) at(r, k) = mpk * at(r, i) + at(r, k);
+                if (g_fused_lu_updates) { for (int r = i + 1; r < n; ++r) at(r, k) = __builtin_fma(mpk, at(r, i), at(r, k)); }
+                else for (int r = i + 1; r < n; ++r) at(r, k) = mpk * at(r, i) + at(r, k);
             }
         } else {
             double inv_diag = 1.0 / diag;
             for (int r = i + 1; r < n; ++r) at(r, i) *= inv_diag;
             for (int k = i + 1; k < n; ++k) {
                 double mpk = -at(i, k);
-                for (int r = i + 1; r < n; ++r) at(r, k) = mpk * at(r, i) + at(r, k);
+                if (g_fused_lu_updates) { for (int r = i + 1; r < n; ++r) at(r, k) = __builtin_fma(mpk, at(r, i), at(r, k)); }
+                else for (int r = i + 1; r < n; ++r) at(r, k) = mpk * at(r, i) + at(r, k);
             }
         }
     }

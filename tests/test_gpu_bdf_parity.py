@@ -105,6 +105,26 @@ def test_robertson_sweep_bit_exact(dsb, oracle, model, tol):
     assert solver.sum_statistic("number_of_nonlinear_solver_iterations") == int(stats_o[:, 8].sum())
 
 
+def test_host_entry_point_pipelines_big_batches_in_chunks(dsb, monkeypatch):
+    """dsb_batch_solve_dense_host splits big batches into child batches on their own streams (copies of one chunk under the
+    kernels of another): same trajectories, counters, status and getters as the direct path."""
+    from diffsol_b200 import sweeps
+    B = 4 * 65536 + 1237
+    p = sweeps.robertson_sweep(np.arange(B))
+    case = dict(model="robertson_ode", coloring=False, **sweeps.ROBERTSON_ODE_TOL)
+    monkeypatch.setenv("DSB_HOST_CHUNKS", "1")
+    a = _build(dsb, case, p=p).bdf()
+    ya = a.solve_dense(sweeps.ROBERTSON_T_EVAL)
+    sa, sta, fa = a.statistics_array().copy(), a.status().copy(), a.final_state()
+    monkeypatch.setenv("DSB_HOST_CHUNKS", "4")
+    b = _build(dsb, case, p=p).bdf()
+    yb = b.solve_dense(sweeps.ROBERTSON_T_EVAL)
+    assert np.array_equal(ya, yb) and np.array_equal(sa, b.statistics_array()) and np.array_equal(sta, b.status())
+    assert all(np.array_equal(u, v) for u, v in zip(fa, b.final_state()))
+    assert b.sum_statistic("number_of_steps") == int(sa[:, 6].sum())
+    assert b.last_kernel_ms() > 0.0
+
+
 def test_failed_instances_keep_status(dsb, oracle):
     """An instance that fails does not abort the batch: same status code as the oracle, NaN outputs
     past the failure, neighbours unaffected."""

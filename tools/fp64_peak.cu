@@ -1,6 +1,7 @@
 // fp64_peak.cu -- FP64 micro-benchmarks on the box the bench runs on (VERDICT r1 item 2c / SURVEY section 8d: an FP64
 // denominator has to be MEASURED before any flop statement).  Prints one JSON object:
 //   dfma_tflops            unfused-equivalent peak: 2 flop per DFMA, every SM saturated with independent chains
+//   dmma_m8n8k4_tflops     the FP64 tensor-core rate (mma.sync m8n8k4 f64), for the question whether DMMA trailing updates would pay
 //   dmul_dadd_tflops       the same with the unfused pair (DMUL then DADD) the bit-exact kernels have to issue (--fmad=false)
 //   lat_*_cycles           dependent-issue latency of DFMA / DADD / DMUL, of an IEEE division `a / b`, and of the
 //                          reciprocal-reuse division (dsb_math.h: dsb_div_rcp, 5 dependent operations)
@@ -30,6 +31,25 @@ __global__ void __launch_bounds__(256) throughput_kernel(double* out, int iters,
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == 12345.678) out[0] = s;
+}
+
+// FP64 tensor-core path: mma.sync m8n8k4 f64 (DMMA), 8 independent accumulator pairs per thread.  512 flop per warp
+// instruction; every multiply-add of it is FUSED (one rounding), which is why the bit-exact LU cannot use it.
+__global__ void __launch_bounds__(256) dmma_kernel(double* out, int iters, double seed) {
+    double c0[8], c1[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { c0[k] = seed + k; c1[k] = seed - k; }
+    const double a = 1.0000001 + threadIdx.x * 1e-12, b = 0.9999999;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                         : "+d"(c0[k]), "+d"(c1[k]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += c0[k] + c1[k];
     if (s == 12345.678) out[0] = s;
 }
 
@@ -111,6 +131,19 @@ int main() {
         }
         tf[mode] = 2.0 * 8.0 * iters * 256.0 * blocks / (best * 1e-3) / 1e12;
     }
+    double dmma_tf = 0.0;
+    {
+        float best = 1e30f;
+        const int diters = 1 << 13;
+        for (int rep = 0; rep < 6; ++rep) {
+            cudaEventRecord(e0);
+            dmma_kernel<<<blocks, 256>>>(out, diters, 1.0);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            const float ms = time_ms(e0, e1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        dmma_tf = 512.0 * 8.0 * diters * (256.0 / 32.0) * blocks / (best * 1e-3) / 1e12;
+    }
     double lat[6];
     const int liters = 1 << 14;
     for (int mode = 0; mode < 6; ++mode) {
@@ -137,11 +170,11 @@ int main() {
     cudaMemcpy(&bad, mism, 8, cudaMemcpyDeviceToHost);
     const cudaError_t err = cudaGetLastError();
     cudaDeviceProp prop; cudaGetDeviceProperties(&prop, dev);
-    printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz_attr\": %d, \"dfma_tflops\": %.3f, \"dmul_dadd_tflops\": %.3f, "
+    printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz_attr\": %d, \"dfma_tflops\": %.3f, \"dmul_dadd_tflops\": %.3f, \"dmma_m8n8k4_tflops\": %.3f, "
            "\"lat_dfma_cycles\": %.2f, \"lat_dadd_cycles\": %.2f, \"lat_dmul_cycles\": %.2f, \"lat_ieee_div_cycles\": %.2f, "
            "\"lat_rcp_div_cycles\": %.2f, \"lds_chain_cycles\": %.2f, \"rcp_div_trials\": %llu, \"rcp_div_mismatches\": %llu, "
            "\"cuda_error\": \"%s\"}\n",
-           prop.name, sms, clk, tf[0], tf[1], lat[0], lat[1], lat[2], lat[3], lat[4], lat[5],
+           prop.name, sms, clk, tf[0], tf[1], dmma_tf, lat[0], lat[1], lat[2], lat[3], lat[4], lat[5],
            (unsigned long long)sms * 16ull * 256ull * per_thread, bad, cudaGetErrorString(err));
     return err == cudaSuccess ? 0 : 1;
 }
