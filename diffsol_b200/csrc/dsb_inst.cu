@@ -242,12 +242,15 @@ template <class M> struct BandLauncher<M, true> {
 template <class M, bool BAND> struct WBandCapable : std::false_type {};
 template <class M> struct WBandCapable<M, true> : std::bool_constant<!dsb_model_has_reset<M>::value && WBandLayout<M>::FITS> {};
 constexpr bool kWBandCapable = WBandCapable<InstModel, kBandCapable>::value;
-// automatic selection: the warp-per-instance kernel for the larger systems (difference array in its global-memory slot,
-// n >~ 100), where shared memory buys it what the lane-per-instance kernel loses to global-memory latency; small
-// systems (n = 42: 16 resident warps of a 100 KB kernel, instruction-fetch bound) stay with one lane per instance
-// (measured on B200, 250 000 instances: n = 42 288 vs 230 ms, n = 200 828 vs 1113 ms, n = 256 DAE 107 vs 374 ms)
+// automatic selection between the two banded kernel families, from measurements on one B200 (250 000 instances, BDF; ms
+// warp-per-instance vs lane-per-instance): n = 256 DAE 100 vs 374; n = 200 616 vs 1113, with out / stop functions 1180 vs
+// 1556; n = 42 182 vs 231, but with out / stop functions 731 vs 514 -- a warp evaluates its instance's output and root
+// functions once per step at the issue cost of 32 lanes, which a small system cannot amortise.  Hence: the warp kernel
+// for every larger system (difference array in its global-memory slot) and for small systems without output / root
+// functions; one lane per instance for small systems that have them.
 template <class M, bool OK> struct WBandPreferred : std::false_type {};
-template <class M> struct WBandPreferred<M, true> : std::bool_constant<!WBandLayout<M>::D_SHARED> {};
+template <class M> struct WBandPreferred<M, true>
+    : std::bool_constant<!WBandLayout<M>::D_SHARED || (dsb_model_nroots<M>::value == 0 && !dsb_model_nout<M>::has_out)> {};
 constexpr bool kWBandPreferred = WBandPreferred<InstModel, kWBandCapable>::value;
 
 template <class M, bool OK> struct WBandLauncher {
