@@ -500,9 +500,9 @@ def main():
             "gpu_launches": c[8],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
-                         # (profiles/r1_v10_bdf_kernel_ncu_summary.txt: 161.1 + 187.5 MB for a 10^6-instance launch),
+                         # (profiles/r2_bdf_kernel_ncu_summary.txt: 149.5 + 179.3 MB for a 10^6-instance launch),
                          # per instance: mostly the trajectories, counters and status it writes
-                         "traffic": 348.6 * B, "traffic_source": "ncu capture profiles/r1_v10 (348.6 B/instance), scaled to this launch",
+                         "traffic": 328.8 * B, "traffic_source": "ncu capture profiles/r2_bdf_kernel_ncu_summary.txt (328.8 B/instance), scaled to this launch",
                          "kernel": "dsb_bdf_solve_dense_kernel<ModelRobertsonOde<1>>",
                          "kernel_ms": integ_mean_ms, "algorithmic_bytes_per_launch": alg,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",

@@ -210,14 +210,32 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
         return v;
     };
     // ||D[:, j]||^2_w(state.y) (vector/nalgebra_serial.rs:395-408)
-    auto diff_col_norm = [&](int j) -> double {
+    // x_i / (|ref_i| rtol + atol_i), i = 0 .. N-1, squared and summed in index order (vector/nalgebra_serial.rs:395-408)
+    auto weighted_sum = [&](const double (&x)[N], const double (&ref)[N]) -> double {
+#ifdef DSB_DIV_VEC
+        DsbVecN<N> a, b;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { a.v[i] = x[i]; b.v[i] = dsb_abs(ref[i]) * pa.rtol + pa.atol[i]; }
+        const DsbVecN<N> q = dsb_div_vec_fn<N>(a, b);
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc += q.v[i] * q.v[i];
+        return acc;
+#else
         double acc = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double term = DSB_DIV(SD(j, i), dsb_abs(SY(i)) * pa.rtol + pa.atol[i]);
+            const double term = DSB_DIV(x[i], dsb_abs(ref[i]) * pa.rtol + pa.atol[i]);
             acc += term * term;
         }
-        return DSB_DIV_N(acc);
+        return acc;
+#endif
+    };
+    auto diff_col_norm = [&](int j) -> double {
+        double x[N], ref[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) { x[i] = SD(j, i); ref[i] = SY(i); }
+        return DSB_DIV_N(weighted_sum(x, ref));
     };
 
 #ifdef DSB_LANE_PROFILE          // warp-scheduler occupancy counters (warp-uniform values, lane 0 publishes them)
@@ -698,14 +716,11 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #endif
                 newton_ok = false; state = L_POST;              // LuSolveFailed
             } else {
-                double acc = 0.0;
+                double ypl[N];
 #pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    y_cur[i] -= delta[i];
-                    // Newton norm weights use the PREDICTOR (line_search.rs:67, convergence.rs:64-66)
-                    const double term = DSB_NEWTON_DIV::div(delta[i], dsb_abs(SYP(i)) * pa.rtol + pa.atol[i]);
-                    acc += term * term;
-                }
+                for (int i = 0; i < N; ++i) { y_cur[i] -= delta[i]; ypl[i] = SYP(i); }
+                // Newton norm weights use the PREDICTOR (line_search.rs:67, convergence.rs:64-66)
+                const double acc = weighted_sum(delta, ypl);
                 const double norm = dsb_sqrt(DSB_DIV_N(acc));
                 // Convergence::check_new_iteration (convergence.rs:68-139) with its pow() hoisted to one call site
                 conv.niter += 1;
@@ -743,12 +758,10 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #pragma unroll
                 for (int i = 0; i < N; ++i) d[i] = y_cur[i] - SYP(i);
                 {   // error_control: ||d||^2_w(state.y) * error_const2[order - 1]
-                    double acc = 0.0;
+                    double yl[N];
 #pragma unroll
-                    for (int i = 0; i < N; ++i) {
-                        const double term = DSB_DIV(d[i], dsb_abs(SY(i)) * pa.rtol + pa.atol[i]);
-                        acc += term * term;
-                    }
+                    for (int i = 0; i < N; ++i) yl[i] = SY(i);
+                    const double acc = weighted_sum(d, yl);
                     const double err = DSB_DIV_N(acc) * pa.tab.error_const2[ord - 1];
                     error_norm = (0.0 < err) ? err : 0.0;
                 }

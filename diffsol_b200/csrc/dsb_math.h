@@ -100,6 +100,17 @@ DSB_HD double dsb_sqrt(double a) {
 static __device__ __noinline__ double dsb_div_fn(double a, double b) { return a / b; }
 struct DsbDivShared { static __device__ __forceinline__ double div(double a, double b) { return dsb_div_fn(a, b); } };
 struct DsbDivInline { static __device__ __forceinline__ double div(double a, double b) { return a / b; } };
+// N independent quotients in ONE call: the same IEEE divisions, but the N dependency chains (reciprocal seed, two Newton
+// steps, quotient, residual correction: ~10 dependent operations each) interleave inside the routine instead of running
+// one after the other through N calls.  The weighted norms divide N components at a time.
+template <int N> struct DsbVecN { double v[N]; };
+template <int N>
+static __device__ __noinline__ DsbVecN<N> dsb_div_vec_fn(DsbVecN<N> a, DsbVecN<N> b) {
+    DsbVecN<N> q;
+#pragma unroll
+    for (int i = 0; i < N; ++i) q.v[i] = a.v[i] / b.v[i];
+    return q;
+}
 #endif
 DSB_HD double dsb_abs(double a) { return dsb_from_bits(dsb_bits(a) & 0x7fffffffffffffffULL); }
 DSB_HD bool dsb_isnan(double a) { return a != a; }
