@@ -46,6 +46,10 @@ template <class M> struct dsb_model_ndep<M, decltype((void)M::NDEP)> { static co
 // reset function of an equation set (OdeEquations::reset: the state map applied at a root): declared by M::HAS_RESET
 template <class M, class = void> struct dsb_model_has_reset { static constexpr bool value = false; };
 template <class M> struct dsb_model_has_reset<M, decltype((void)M::HAS_RESET)> { static constexpr bool value = M::HAS_RESET; };
+// forward sensitivities (OdeEquationsImplicitSens, ode_equations/mod.rs): M::HAS_SENS, M::sens_mul(x, p, t, v, y) = f_p(x, p, t) v
+// and M::init_sens(p, t, v, y) = (d y0 / d p) v
+template <class M, class = void> struct dsb_model_has_sens { static constexpr bool value = false; };
+template <class M> struct dsb_model_has_sens<M, decltype((void)M::HAS_SENS)> { static constexpr bool value = M::HAS_SENS; };
 
 struct dsb_log_row { double invc, logc_hi, logc_lo; };
 struct dsb_exp_row { double hi, lo; };

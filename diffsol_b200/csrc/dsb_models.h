@@ -58,6 +58,16 @@ struct ModelExpDecay {
     DSB_HD static void init(const double* p, double, double* y) {
         for (int i = 0; i < N; ++i) y[i] = p[1];
     }
+    // forward sensitivities: exponential_decay_sens / exponential_decay_init_sens (test_models/exponential_decay.rs:
+    // f_p v = x * (-v[0]), (d y0 / d p) v = [v[1], v[1]]), the problem of exponential_decay_problem_sens (:703-742)
+    static constexpr bool HAS_SENS = true;
+    DSB_HD static void sens_mul(const double* x, const double*, double, const double* v, double* y) {
+        const double mv = -v[0];
+        for (int i = 0; i < N; ++i) y[i] = x[i] * mv;
+    }
+    DSB_HD static void init_sens(const double*, double, const double* v, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = v[1];
+    }
 };
 
 // The same equations with the root function of the reference's event tests
@@ -181,6 +191,19 @@ struct ModelRobertsonOde {
     }
     DSB_HD static void init(const double*, double, double* y) {
         for (int ig = 0; ig < NG; ++ig) { y[3 * ig] = 1.0; y[3 * ig + 1] = 0.0; y[3 * ig + 2] = 0.0; }
+    }
+    // forward sensitivities: the closures of robertson_ode_with_sens (test_models/robertson_ode_with_sens.rs:38-50)
+    static constexpr bool HAS_SENS = true;
+    DSB_HD static void sens_mul(const double* x, const double*, double, const double* v, double* y) {
+        for (int ig = 0; ig < NG; ++ig) {
+            const int i = ig * 3;
+            y[i] = -v[0] * x[i] + v[1] * x[i + 1] * x[i + 2];
+            y[i + 1] = v[0] * x[i] - v[1] * x[i + 1] * x[i + 2] - v[2] * x[i + 1] * x[i + 1];
+            y[i + 2] = v[2] * x[i + 1] * x[i + 1];
+        }
+    }
+    DSB_HD static void init_sens(const double*, double, const double*, double* y) {
+        for (int i = 0; i < N; ++i) y[i] = 0.0;
     }
 };
 

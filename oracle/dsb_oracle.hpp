@@ -77,6 +77,9 @@ struct Model {
     void (*out)(const double*, const double*, double, double*) = nullptr;
     int ncols_out() const { return nout > 0 ? nout : n; }                 // rows of the solve_dense result
     void (*reset)(const double*, const double*, double, double*) = nullptr;   // OdeEquations::reset: y <- reset(y, t) at a root
+    // OdeEquationsImplicitSens: f_p(x, p, t) v and (d y0 / d p) v (op/closure_with_sens.rs:181-183, op/constant_closure_with_sens.rs)
+    void (*sens_mul)(const double*, const double*, double, const double*, double*) = nullptr;
+    void (*init_sens)(const double*, double, const double*, double*) = nullptr;
 };
 template <class M, int NR = dsb_model_nroots<M>::value> struct RootOf {
     static void set(Model& m) {          // M::root may be a template over the state accessor (component-wise models)
@@ -96,6 +99,10 @@ template <class M, bool HAS = dsb_model_has_reset<M>::value> struct ResetOf {
     static void set(Model& m) { m.reset = [](const double* x, const double* p, double t, double* y) { M::reset(x, p, t, y); }; }
 };
 template <class M> struct ResetOf<M, false> { static void set(Model&) {} };
+template <class M, bool HAS = dsb_model_has_sens<M>::value> struct SensOf {
+    static void set(Model& m) { m.sens_mul = &M::sens_mul; m.init_sens = &M::init_sens; }
+};
+template <class M> struct SensOf<M, false> { static void set(Model&) {} };
 template <class M>
 Model make_model() {
     Model m;
@@ -104,6 +111,7 @@ Model make_model() {
     RootOf<M>::set(m);
     OutOf<M>::set(m);
     ResetOf<M>::set(m);
+    SensOf<M>::set(m);
     return m;
 }
 bool model_by_id(int id, Model* out);
@@ -148,6 +156,12 @@ struct Problem {
     Vec atol;                  // length n
     double t0 = 0.0, h0 = 1.0;
     bool use_coloring = false;
+    // forward sensitivities (problem.bdf_sens(), ode_solver/problem.rs:819-830): one sensitivity vector per parameter;
+    // sens_rtol / sens_atol (builder.rs:1682-1716; per state, param_scales = 1) put them into the error test
+    bool sens = false;
+    bool sens_error_control = false;
+    double sens_rtol = 0.0;
+    Vec sens_atol;             // length n
     Options opt;
     Math math;
     // colouring data (jacobian/mod.rs:178-214), built by build_coloring()
@@ -257,6 +271,8 @@ struct Method {
     virtual int cur_order() const = 0;
     virtual const double* y() const = 0;
     virtual const Stats& stats() const = 0;
+    // OdeSolverMethod::interpolate_sens (bdf.rs:1162-1190): one vector per parameter, out is n x np (parameter-major)
+    virtual int interpolate_sens(double, double*) const { return ST_BAD_ARG; }
     // RootFound(t, index) of the last step() that returned ROOT_FOUND
     virtual double root_t() const { return 0.0; }
     virtual int root_index() const { return -1; }

@@ -42,6 +42,13 @@ struct Bdf : Method {
     RootFinder root_finder;
     double root_t_ = 0.0; int root_idx_ = -1;
     bool is_state_modified = false;                        // bdf.rs:1223-1226: set by state_mut() / state_mut_back()
+    // forward sensitivities (Bdf<.., SensEquations>, bdf.rs:128-141): one difference array per parameter, all rescaled
+    // through the ONE diff_tmp ping-pong buffer (bdf.rs:539-541); the sensitivity residual keeps its OWN c, which stays 0
+    // until the first step-size update (op/bdf.rs:61 new_no_jacobian, bdf.rs:551-553)
+    int ns = 0;
+    std::vector<Vec> s_, ds_, sdiff, s_deltas;
+    Vec s_predict, sens_S, sens_y, psi_s;                  // sens_S = f_p at the predictor, n x np col-major (SensRhs::update_state)
+    double c_sens = 0.0;
 
     explicit Bdf(const Problem& p) : pr(p), n(p.n()) {}
 
@@ -83,7 +90,74 @@ struct Bdf : Method {
         u = compute_r(order, 1.0);
         statistics.v[S_SETUPS] = 1; statistics.v[S_SETUPS_CHECKPOINT] = 1;
         jacobian_update.init(pr.opt, 1.0);             // jacobian_update.rs:27 -- h_at_last starts at ONE
+        if (pr.sens) {
+            // state.rs:1158-1180 initialise_augmented_state (s_i = (d y0 / d p) e_i), :178-189 set_consistent_augmented without
+            // algebraic rows (ds_i = J(y0) s_i + f_p e_i), bdf_state.rs:88-98 initialise_sdiff_to_first_order
+            if (!pr.model.sens_mul || !pr.model.init_sens || pr.model.has_mass) return ST_BAD_ARG;
+            ns = pr.model.np;
+            s_.assign(ns, Vec(n, 0.0)); ds_ = s_; s_deltas = s_;
+            sdiff.assign(ns, Vec((size_t)n * NCOLS, 0.0));
+            s_predict.assign(n, 0.0); psi_s.assign(n, 0.0); sens_y.assign(n, 0.0); sens_S.assign((size_t)n * ns, 0.0);
+            Vec e(ns, 0.0);
+            for (int i = 0; i < ns; ++i) {
+                e[i] = 1.0;
+                pr.model.init_sens(pr.p.data(), pr.t0, e.data(), s_[i].data());
+                e[i] = 0.0;
+            }
+            update_rhs_out_state(y_.data(), t_);
+            for (int i = 0; i < ns; ++i) sens_rhs(i, s_[i].data(), t_, ds_[i].data());
+            for (int i = 0; i < ns; ++i)
+                for (int k = 0; k < n; ++k) { sdiff[i][k] = s_[i][k]; sdiff[i][(size_t)n + k] = ds_[i][k] * h_; }
+        }
         return ST_OK;
+    }
+
+    // SensRhs::update_state (sens_equations.rs:129-134) through _default_sens_inplace (op/nonlinear_op.rs:72-81)
+    void update_rhs_out_state(const double* y, double t) {
+        Vec v(ns, 0.0);
+        for (int j = 0; j < ns; ++j) {
+            v[j] = 1.0;
+            pr.model.sens_mul(y, pr.p.data(), t, v.data(), sens_S.data() + (size_t)j * n);
+            v[j] = 0.0;
+        }
+        for (int k = 0; k < n; ++k) sens_y[k] = y[k];
+    }
+    // SensRhs::call_inplace (sens_equations.rs:168-174): J(y stored) x + S[:, index]
+    void sens_rhs(int index, const double* x, double t, double* out) const {
+        pr.jac_mul(sens_y.data(), t, x, out);
+        const double* col = sens_S.data() + (size_t)index * n;
+        for (int k = 0; k < n; ++k) out[k] += col[k];
+    }
+    // BdfCallable<SensEquations>::call_inplace (op/bdf.rs:240-256) with its own psi and c
+    void callable_sens(int index, const double* x, double t, double* out) {
+        sens_rhs(index, x, t, out);
+        for (int k = 0; k < n; ++k) tmp[k] = x[k] + psi_s[k];
+        const double mc = -c_sens;
+        for (int k = 0; k < n; ++k) out[k] = tmp[k] + mc * out[k];
+    }
+    // bdf.rs:934-989.  false <=> a sensitivity solve failed (the iterations of the failed solve are NOT counted: the `?`
+    // returns before the statistics line)
+    bool sensitivity_solve(double t_new) {
+        update_rhs_out_state(y_predict.data(), t_new);
+        for (int i = 0; i < ns; ++i) {
+            const double* d = sdiff[i].data();
+            for (int k = 0; k < n; ++k) s_predict[k] = 0.0;
+            for (int j = 0; j <= order; ++j)
+                for (int k = 0; k < n; ++k) s_predict[k] += d[(size_t)j * n + k];
+            for (int k = 0; k < n; ++k) psi_s[k] = gamma[1] * d[(size_t)n + k];
+            for (int j = 2; j <= order; ++j)
+                for (int k = 0; k < n; ++k) psi_s[k] = gamma[j] * d[(size_t)j * n + k] + psi_s[k];
+            for (int k = 0; k < n; ++k) psi_s[k] *= alpha[order];
+            for (int k = 0; k < n; ++k) psi_s[k] -= s_predict[k];
+            s_[i] = s_predict;
+            const bool ok = newton_solve_with([this, i](const double* x, double t, double* out) { callable_sens(i, x, t, out); },
+                                              s_[i], t_new, s_predict);
+            if (!ok) return false;
+            statistics.v[S_NL_ITERS] += convergence.niter;
+            for (int k = 0; k < n; ++k) s_deltas[i][k] = s_[i][k];
+            for (int k = 0; k < n; ++k) s_deltas[i][k] -= s_predict[k];
+        }
+        return true;
     }
 
     void set_c(double h, double a) { c = h * a; }       // op/bdf.rs:179-181
@@ -153,18 +227,23 @@ struct Bdf : Method {
                     else ru[ij] = r[(size_t)l * nr + i] * ulj + ru[ij];
                 }
             }
-        for (int j = 0; j < nr; ++j)
-            for (int l = 0; l < nr; ++l) {
-                double rulj = ru[(size_t)j * nr + l];
-                const double* dl = D(l);
-                double* out = diff_tmp.data() + (size_t)j * n;
-                for (int i = 0; i < n; ++i) {
-                    if (l == 0) out[i] = dl[i] * rulj;
-                    else out[i] = dl[i] * rulj + out[i];
+        auto rescale = [&](Vec& dd) {                       // _update_diff_for_step_size (bdf.rs:567-577)
+            for (int j = 0; j < nr; ++j)
+                for (int l = 0; l < nr; ++l) {
+                    double rulj = ru[(size_t)j * nr + l];
+                    const double* dl = dd.data() + (size_t)l * n;
+                    double* out = diff_tmp.data() + (size_t)j * n;
+                    for (int i = 0; i < n; ++i) {
+                        if (l == 0) out[i] = dl[i] * rulj;
+                        else out[i] = dl[i] * rulj + out[i];
+                    }
                 }
-            }
-        std::swap(diff, diff_tmp);
+            std::swap(dd, diff_tmp);
+        };
+        rescale(diff);
+        for (int i = 0; i < ns; ++i) rescale(sdiff[i]);     // bdf.rs:539-541: the same diff_tmp, so the buffers rotate
         set_c(new_h, alpha[order]);
+        if (ns > 0) c_sens = new_h * alpha[order];          // bdf.rs:551-553
         h_ = new_h;
         convergence.reset_eta_timestep_change();
         if (new_h_out) *new_h_out = new_h;
@@ -173,11 +252,13 @@ struct Bdf : Method {
     }
 
     // bdf.rs:646-664
-    void update_diff(int ord, const Vec& d) {
-        for (int i = 0; i < n; ++i) D(ord + 2)[i] = d[i] - D(ord + 1)[i];
-        for (int i = 0; i < n; ++i) D(ord + 1)[i] = d[i];
+    void update_diff(int ord, const Vec& d) { update_diff_of(diff, ord, d); }
+    void update_diff_of(Vec& dd, int ord, const Vec& d) {
+        auto C = [&](int j) { return dd.data() + (size_t)j * n; };
+        for (int i = 0; i < n; ++i) C(ord + 2)[i] = d[i] - C(ord + 1)[i];
+        for (int i = 0; i < n; ++i) C(ord + 1)[i] = d[i];
         for (int j = ord; j >= 0; --j)
-            for (int i = 0; i < n; ++i) D(j)[i] = D(j)[i] + 1.0 * D(j + 1)[i];
+            for (int i = 0; i < n; ++i) C(j)[i] = C(j)[i] + 1.0 * C(j + 1)[i];
     }
 
     // bdf.rs:667-692 + op/bdf.rs:182-210
@@ -205,9 +286,13 @@ struct Bdf : Method {
 
     // newton_iteration + NoLineSearch::take_optimal_step.  Returns true on convergence.
     bool newton_solve(Vec& xn, double t, const Vec& error_y) {
+        return newton_solve_with([this](const double* x, double tt, double* out) { callable(x, tt, out); }, xn, t, error_y);
+    }
+    template <class F>
+    bool newton_solve_with(F&& residual, Vec& xn, double t, const Vec& error_y) {
         convergence.reset();
         for (int it = 0; it < convergence.max_iter; ++it) {
-            callable(xn.data(), t, newton_tmp.data());
+            residual(xn.data(), t, newton_tmp.data());
             if (!lu.solve(newton_tmp.data())) return false;     // LuSolveFailed
             for (int i = 0; i < n; ++i) xn[i] -= newton_tmp[i];
             double norm = convergence.norm(newton_tmp.data(), error_y.data());
@@ -236,12 +321,21 @@ struct Bdf : Method {
     // bdf.rs:812-869 (state part only): NB error_const2[order - 1]
     double error_control() const {
         double err = squared_norm(y_delta.data(), y_.data(), pr.atol.data(), pr.rtol, n) * error_const2[order - 1];
-        return std::max(0.0, err);
+        err = std::max(0.0, err);
+        if (pr.sens_error_control)                          // NB error_const2[order] for the sensitivities (bdf.rs:844-858)
+            for (int i = 0; i < ns; ++i)
+                err = std::max(err, squared_norm(s_deltas[i].data(), s_[i].data(), pr.sens_atol.data(), pr.sens_rtol, n) * error_const2[order]);
+        return err;
     }
     // bdf.rs:871-932
     double predict_error_control(int ord) const {
         double err = squared_norm(D(ord + 1), y_.data(), pr.atol.data(), pr.rtol, n) * error_const2[ord];
-        return std::max(0.0, err);
+        err = std::max(0.0, err);
+        if (pr.sens_error_control)                          // bdf.rs:908-919
+            for (int i = 0; i < ns; ++i)
+                err = std::max(err, squared_norm(sdiff[i].data() + (size_t)(ord + 1) * n, s_[i].data(), pr.sens_atol.data(), pr.sens_rtol, n)
+                                        * error_const2[ord]);
+        return err;
     }
     // runge_kutta.rs:1313-1335
     double pi_controller_raw(double error_norm, int eff_order) const {
@@ -267,6 +361,7 @@ struct Bdf : Method {
             for (int i = 0; i < n; ++i) { D(0)[i] = y_[i]; D(1)[i] = dy_[i] * h_; }
             u = compute_r(1, 1.0);
             is_state_modified = false;
+            if (ns > 0) { *err = ST_BAD_ARG; return STEP_ERROR; }   // resets with sensitivities (bdf.rs:1022-1078) are not restated
             const double c_new = h_ * alpha[order];
             set_c(h_, alpha[order]);
             jacobian_updates(c_new, STEP_SUCCESS);
@@ -284,7 +379,9 @@ struct Bdf : Method {
             statistics.v[S_NL_ITERS] += convergence.niter;
             if (ok) {
                 for (int i = 0; i < n; ++i) y_delta[i] -= y_predict[i];
-            } else {
+                if (ns > 0 && !sensitivity_solve(t_predict)) ok = false;     // SensitivitySolveFailed (bdf.rs:1355-1361)
+            }
+            if (!ok) {
                 statistics.v[S_NL_FAILS] += 1;
                 if (statistics.v[S_NL_FAILS] > pr.opt.max_nonlinear_solver_failures) {
                     *err = ST_TOO_MANY_NONLINEAR_FAILURES; return STEP_ERROR;
@@ -322,6 +419,7 @@ struct Bdf : Method {
         }
         // accepted
         update_diff(order, y_delta);
+        for (int i = 0; i < ns; ++i) update_diff_of(sdiff[i], order, s_deltas[i]);   // bdf.rs:629-633
         for (int i = 0; i < n; ++i) y_[i] = y_predict[i];       // Q1: the PREDICTOR
         t_ = t_predict;
         {
@@ -391,6 +489,25 @@ struct Bdf : Method {
             double j_t = (double)j;
             time_factor *= (t - (t_ - h_ * j_t)) / (h_ * (1.0 + j_t));
             for (int i = 0; i < n; ++i) y[i] = time_factor * D(j + 1)[i] + y[i];
+        }
+        return ST_OK;
+    }
+
+    // bdf.rs:1162-1215: interpolate_from_diff on every sdiff
+    int interpolate_sens(double t, double* out) const override {
+        if (ns == 0) return ST_BAD_ARG;
+        bool is_forward = h_ > 0.0;
+        if ((is_forward && t > t_) || (!is_forward && t < t_)) return ST_INTERPOLATION_TIME_AFTER_CURRENT;
+        for (int q = 0; q < ns; ++q) {
+            const double* d = sdiff[q].data();
+            double* y = out + (size_t)q * n;
+            double time_factor = 1.0;
+            for (int i = 0; i < n; ++i) y[i] = d[i];
+            for (int j = 0; j < order; ++j) {
+                double j_t = (double)j;
+                time_factor *= (t - (t_ - h_ * j_t)) / (h_ * (1.0 + j_t));
+                for (int i = 0; i < n; ++i) y[i] = time_factor * d[(size_t)(j + 1) * n + i] + y[i];
+            }
         }
         return ST_OK;
     }

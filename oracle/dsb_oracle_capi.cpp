@@ -29,6 +29,11 @@ struct orc_problem_desc {
     double max_timestep_growth, min_timestep_growth, max_timestep_shrink, min_timestep_shrink;
     double threshold_to_update_jacobian, threshold_to_update_rhs_jacobian;
     double pi_control_proportional, pi_control_integral;
+    // forward sensitivities (problem.bdf_sens()): sens != 0 integrates one sensitivity vector per parameter; sens_natol = 0
+    // leaves them out of the error test (builder.rs turn_off_sensitivities_error_control), 1 broadcasts, else == n
+    int32_t sens, sens_natol;
+    double sens_rtol;
+    double sens_atol[64];
 };
 
 static int build_problem(const orc_problem_desc* d, const double* p, int np, Problem* pr) {
@@ -60,6 +65,16 @@ static int build_problem(const orc_problem_desc* d, const double* p, int np, Pro
     }
     pr->use_coloring = d->use_coloring != 0;
     if (pr->use_coloring) pr->build_coloring();
+    pr->sens = d->sens != 0;
+    if (pr->sens) {
+        if (!pr->model.sens_mul || d->method != 0) return ST_BAD_ARG;     // the BDF restatement only
+        pr->sens_error_control = d->sens_natol != 0;
+        pr->sens_rtol = d->sens_rtol;
+        pr->sens_atol.assign(n, 0.0);
+        if (d->sens_natol == 1) for (int i = 0; i < n; ++i) pr->sens_atol[i] = d->sens_atol[0];
+        else if (d->sens_natol == n && n <= 64) for (int i = 0; i < n; ++i) pr->sens_atol[i] = d->sens_atol[i];
+        else if (d->sens_natol != 0) return ST_BAD_ARG;
+    }
     return ST_OK;
 }
 
@@ -164,6 +179,84 @@ int orc_harness(const orc_problem_desc* d, const double* p, int np, const double
     export_stats(pr, m.get(), stats);
     if (fin) { fin[0] = m->t(); fin[1] = m->h(); fin[2] = (double)m->cur_order(); }
     return err;
+}
+
+// test_ode_solver(.., solve_for_sensitivities = true) (ode_solver/mod.rs:104-194): the same loop, plus interpolate_sens at
+// every point.  out is n x npts, sens_out is n x np x npts (point-major, then parameter).
+int orc_harness_sens(const orc_problem_desc* d, const double* p, int np, const double* t_points, int npts,
+                     double* out, double* sens_out, int64_t* stats, double* fin) {
+    Problem pr;
+    int err = build_problem(d, p, np, &pr);
+    if (err) return err;
+    if (!pr.sens) return ST_BAD_ARG;
+    std::unique_ptr<Method> m(make_method(pr, d->method, &err));
+    if (!m) { export_stats(pr, nullptr, stats); return err; }
+    const int n = pr.n();
+    for (int k = 0; k < npts && !err; ++k) {
+        while (std::fabs(m->t()) < std::fabs(t_points[k])) {
+            StopReason r = m->step(&err);
+            if (r == STEP_ERROR) break;
+        }
+        if (err) break;
+        err = m->interpolate(t_points[k], out + (size_t)k * n);
+        if (!err) err = m->interpolate_sens(t_points[k], sens_out + (size_t)k * n * np);
+    }
+    export_stats(pr, m.get(), stats);
+    if (fin) { fin[0] = m->t(); fin[1] = m->h(); fin[2] = (double)m->cur_order(); }
+    return err;
+}
+
+// fn solve_dense_sensitivities (ode_solver/sensitivities.rs:205-262) + dense_write_out_sensitivities (:360-397) for equations
+// without output or root functions: a stop time at t_eval[nt - 1], step(), interpolate + interpolate_sens at every point
+// passed.  out is n x nt, sens_out is n x np x nt (point-major, then parameter).
+static int solve_dense_sens_one(const orc_problem_desc* d, const double* p, int np, const double* t_eval, int nt,
+                                double* out, double* sens_out, int64_t* stats) {
+    Problem pr;
+    int err = build_problem(d, p, np, &pr);
+    if (err) return err;
+    if (!pr.sens || pr.model.nroots > 0 || pr.model.nout > 0) return ST_BAD_ARG;
+    std::unique_ptr<Method> m(make_method(pr, d->method, &err));
+    if (!m) { export_stats(pr, nullptr, stats); return err; }
+    const int n = pr.n();
+    err = m->set_stop_time(t_eval[nt - 1]);
+    int col = 0;
+    while (!err) {
+        StopReason r = m->step(&err);
+        if (r == STEP_ERROR) break;
+        while (col < nt && t_eval[col] <= m->t() && !err) {
+            err = m->interpolate(t_eval[col], out + (size_t)col * n);
+            if (!err) err = m->interpolate_sens(t_eval[col], sens_out + (size_t)col * n * np);
+            ++col;
+        }
+        if (r == TSTOP_REACHED) break;
+    }
+    export_stats(pr, m.get(), stats);
+    return err;
+}
+// instance b: params[b * np ..), out[b] n x nt, sens_out[b] n x np x nt, stats[b] the 16 counters, status[b] the error code
+int orc_batch_solve_dense_sens(const orc_problem_desc* d, const double* params, int np, int64_t nbatch, const double* t_eval, int nt,
+                               int nthreads, double* out, double* sens_out, int64_t* stats, int32_t* status) {
+    Model mm;
+    if (!model_by_id(d->model_id, &mm)) return ST_BAD_ARG;
+    const int n = mm.n;
+    int nt_use = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
+    if (nt_use < 1) nt_use = 1;
+    std::atomic<int64_t> next(0);
+    auto worker = [&]() {
+        while (true) {
+            const int64_t b0 = next.fetch_add(16);
+            if (b0 >= nbatch) break;
+            const int64_t b1 = b0 + 16 < nbatch ? b0 + 16 : nbatch;
+            for (int64_t b = b0; b < b1; ++b)
+                status[b] = solve_dense_sens_one(d, params + (size_t)b * np, np, t_eval, nt, out + (size_t)b * n * nt,
+                                                 sens_out + (size_t)b * n * np * nt, stats + (size_t)b * S_COUNT);
+        }
+    };
+    if (nt_use == 1) { worker(); return ST_OK; }
+    std::vector<std::thread> pool;
+    for (int k = 0; k < nt_use; ++k) pool.emplace_back(worker);
+    for (auto& th : pool) th.join();
+    return ST_OK;
 }
 
 // The same with `use_tstop = true`: set_stop_time(point) then step until TstopReached; the solution

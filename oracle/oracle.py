@@ -84,6 +84,10 @@ class ProblemDesc(ctypes.Structure):
         ("threshold_to_update_rhs_jacobian", ctypes.c_double),
         ("pi_control_proportional", ctypes.c_double),
         ("pi_control_integral", ctypes.c_double),
+        ("sens", ctypes.c_int32),
+        ("sens_natol", ctypes.c_int32),
+        ("sens_rtol", ctypes.c_double),
+        ("sens_atol", ctypes.c_double * 64),
     ]
 
 
@@ -110,6 +114,11 @@ def lib():
             f = getattr(L, name)
             f.restype = ctypes.c_int
             f.argtypes = [ctypes.POINTER(ProblemDesc), dp, ctypes.c_int, dp, ctypes.c_int, dp, ip, dp]
+        L.orc_harness_sens.restype = ctypes.c_int
+        L.orc_harness_sens.argtypes = [ctypes.POINTER(ProblemDesc), dp, ctypes.c_int, dp, ctypes.c_int, dp, dp, ip, dp]
+        L.orc_batch_solve_dense_sens.restype = ctypes.c_int
+        L.orc_batch_solve_dense_sens.argtypes = [ctypes.POINTER(ProblemDesc), dp, ctypes.c_int, ctypes.c_int64, dp, ctypes.c_int,
+                                                 ctypes.c_int, dp, dp, ip, ctypes.POINTER(ctypes.c_int32)]
         L.orc_batch_solve_dense.restype = ctypes.c_int
         L.orc_batch_solve_dense.argtypes = [
             ctypes.POINTER(ProblemDesc), dp, ctypes.c_int, ctypes.c_int64, dp, ctypes.c_int, ctypes.c_int,
@@ -153,7 +162,7 @@ def model_dims(model):
 
 
 def make_desc(model, method="bdf", rtol=1e-6, atol=1e-6, t0=0.0, h0=1.0, use_coloring=False,
-              powmode=0, options=None):
+              powmode=0, options=None, sens=False, sens_rtol=None, sens_atol=None):
     d = ProblemDesc()
     d.model_id = MODELS[model] if isinstance(model, str) else int(model)
     d.method = METHODS[method] if isinstance(method, str) else int(method)
@@ -164,6 +173,12 @@ def make_desc(model, method="bdf", rtol=1e-6, atol=1e-6, t0=0.0, h0=1.0, use_col
     d.natol = len(atol)
     for i, a in enumerate(atol):
         d.atol[i] = a
+    d.sens = int(bool(sens))
+    if sens and sens_rtol is not None and sens_atol is not None:
+        sa = np.atleast_1d(np.asarray(sens_atol, dtype=np.float64))
+        d.sens_natol, d.sens_rtol = len(sa), float(sens_rtol)
+        for i, a in enumerate(sa):
+            d.sens_atol[i] = a
     if options:
         d.has_options = 1
         defaults = dict(
@@ -212,6 +227,37 @@ def solve_dense(desc, p, t_eval):
 def harness(desc, p, t_points, use_tstop=False):
     """The reference's test_ode_solver() loop -> (rc, ys[npts, n], stats, final)"""
     return _run(lib().orc_harness_tstop if use_tstop else lib().orc_harness, desc, p, t_points)
+
+
+def harness_sens(desc, p, t_points):
+    """test_ode_solver(.., solve_for_sensitivities=True) -> (rc, ys[npts, n], sens[npts, np, n], stats, final)"""
+    n, np_, _ = _dims_by_id(desc.model_id)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    ts = np.ascontiguousarray(t_points, dtype=np.float64)
+    out = np.full((len(ts), n), np.nan)
+    sens = np.full((len(ts), np_, n), np.nan)
+    stats = np.zeros(S_COUNT, dtype=np.int64)
+    fin = np.zeros(3)
+    rc = lib().orc_harness_sens(ctypes.byref(desc), _dp(p), int(p.size), _dp(ts), len(ts), _dp(out), _dp(sens),
+                                stats.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _dp(fin))
+    return rc, out, sens, _stats_dict(stats), dict(t=fin[0], h=fin[1], order=int(fin[2]))
+
+
+def batch_solve_dense_sens(desc, params, t_eval, nthreads=0):
+    """solve_dense_sensitivities for every row of params -> (ys[B, nt, n], sens[B, nt, np, n], stats[B, 16], status[B])"""
+    n, np_, _ = _dims_by_id(desc.model_id)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    B = params.shape[0]
+    ts = np.ascontiguousarray(t_eval, dtype=np.float64)
+    ys = np.full((B, len(ts), n), np.nan)
+    sens = np.full((B, len(ts), np_, n), np.nan)
+    stats = np.zeros((B, S_COUNT), dtype=np.int64)
+    status = np.zeros(B, dtype=np.int32)
+    rc = lib().orc_batch_solve_dense_sens(ctypes.byref(desc), _dp(params), np_, B, _dp(ts), len(ts), int(nthreads), _dp(ys), _dp(sens),
+                                          stats.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                          status.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    assert rc == 0
+    return ys, sens, stats, status
 
 
 def greedy_coloring(non_zeros, n):
