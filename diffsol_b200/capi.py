@@ -91,6 +91,7 @@ SIGNATURES = {
     "dsb_problem_set_use_coloring": (ctypes.c_int, [_vp, _i32]),
     "dsb_problem_set_options": (ctypes.c_int, [_vp, ctypes.POINTER(Options)]),
     "dsb_problem_get_options": (ctypes.c_int, [_vp, ctypes.POINTER(Options)]),
+    "dsb_problem_set_sensitivities": (ctypes.c_int, [_vp, _i32, _dbl, _vp, _i32]),
     "dsb_batch_new": (ctypes.c_int, [_vp, _i64, _i32, ctypes.POINTER(_vp)]),
     "dsb_batch_free": (ctypes.c_int, [_vp]),
     "dsb_batch_size": (_i64, [_vp]),
@@ -103,6 +104,10 @@ SIGNATURES = {
     "dsb_batch_solve_dense_host": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp]),
     "dsb_batch_step_and_interpolate": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "dsb_batch_step_and_interpolate_host": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "dsb_batch_solve_dense_sensitivities": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "dsb_batch_step_and_interpolate_sensitivities": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "dsb_batch_solve_dense_sensitivities_host": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "dsb_batch_step_and_interpolate_sensitivities_host": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "dsb_batch_get_stats": (ctypes.c_int, [_vp, _vp]),
     "dsb_batch_get_stats_device": (ctypes.c_int, [_vp, _vp, _vp]),
     "dsb_batch_get_status": (ctypes.c_int, [_vp, _vp]),

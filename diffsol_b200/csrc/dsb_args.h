@@ -64,6 +64,11 @@ struct DsbProblemArgs {
     dsb_options opt;
     DsbBdfTables tab;
     DsbSdirkTableau rk;
+    // forward sensitivities (problem.bdf_sens(), ode_solver/problem.rs:819-830; builder.rs:1682-1716): sens != 0 integrates
+    // one sensitivity vector per parameter; sens_error_control puts them into the error test with sens_rtol / sens_atol
+    int32_t sens, sens_error_control;
+    double sens_rtol;
+    double sens_atol[DSB_MAX_STATES];
 };
 
 // Device buffers of one batch, all batch-major (instance index fastest) so that a warp's 32 lanes
@@ -82,4 +87,5 @@ struct DsbBatchBuffers {
     int32_t* fin_order;      // [B]
     int32_t* root_idx;       // [B]   index of the root function that stopped the instance, -1: none (OdeSolverStopReason::RootFound)
     int32_t* ncols;          // [B]   solve_dense columns written (nt unless a root or an error stopped the instance)
+    double* ss;              // [nt][np][n][B]  solve_dense_sensitivities output (NULL without sensitivities)
 };

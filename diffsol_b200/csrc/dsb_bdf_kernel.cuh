@@ -69,7 +69,16 @@ struct BdfLayout {
     static constexpr int O_YP = O_Y + N;                            // y_predict
     static constexpr int O_P = O_YP + N;                            // parameters
     static constexpr int O_ST = O_P + (NP > 0 ? NP : 1);            // statistics, two int32 per word
-    static constexpr int WORDS = O_ST + (DSB_NSTATS_USED + 1) / 2;
+    // forward sensitivities (DsbWithSens<M> only): per parameter a difference array, state.s, s_delta and the column of
+    // f_p at the predictor; the predictor of the sensitivity being solved; the parked solution of the main Newton solve
+    static constexpr bool SENS = dsb_model_sens_on<M>::value;
+    static constexpr int O_SDF = O_ST + (DSB_NSTATS_USED + 1) / 2;  // sdiff[NP][DSB_NDIFF][N]
+    static constexpr int O_SS = O_SDF + NP * DSB_NDIFF * N;         // state.s[NP][N]
+    static constexpr int O_SDL = O_SS + NP * N;                     // s_deltas[NP][N]
+    static constexpr int O_SFP = O_SDL + NP * N;                    // f_p e_q at (y_predict, t_predict) [NP][N]
+    static constexpr int O_SPR = O_SFP + NP * N;                    // s_predict[N]
+    static constexpr int O_SYC = O_SPR + N;                         // the main solve's y while the sensitivities are solved
+    static constexpr int WORDS = SENS ? O_SYC + N : O_SDF;
     static constexpr int THREADS = LaneBlockShape<WORDS, N>::THREADS;
     static constexpr int MAXNREG = LaneBlockShape<WORDS, N>::MAXNREG;
 };
@@ -105,6 +114,16 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #define SY(i) SM(Lay::O_Y + (i))
 #define SYP(i) SM(Lay::O_YP + (i))
 #define SP(i) SM(Lay::O_P + (i))
+#define SDF(q, j, i) SM(Lay::O_SDF + ((q) * DSB_NDIFF + (j)) * N + (i))
+#define SSS(q, i) SM(Lay::O_SS + (q) * N + (i))
+#define SDL(q, i) SM(Lay::O_SDL + (q) * N + (i))
+#define SFP(q, i) SM(Lay::O_SFP + (q) * N + (i))
+#define SPR(i) SM(Lay::O_SPR + (i))
+#define SYC(i) SM(Lay::O_SYC + (i))
+    constexpr bool SENS = Lay::SENS;
+    static_assert(!SENS || (dsb_model_has_sens<M>::value && !M::HAS_MASS && dsb_model_nroots<M>::value == 0 &&
+                            !dsb_model_nout<M>::has_out && !dsb_model_has_reset<M>::value),
+                  "sensitivities: ODEs with sens_mul / init_sens, no root / output / reset functions");
 
     const int64_t B = pa.nbatch;
     const int nt = pa.nt;
@@ -139,6 +158,10 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
     // pending control transfers
     int after_rescale = L_JAC, after_jac = L_TSTOP, jac_kind = DSB_CHECKPOINT;
     double rescale_factor = 1.0;
+    // sensitivities: which equation the Newton block is solving (0 = the state, q + 1 = the sensitivity to parameter q)
+    // and the sensitivity residual's OWN c, which stays 0 until the first step-size update (op/bdf.rs:61, bdf.rs:551-553)
+    int eq = 0;
+    double c_sens = 0.0;
 
     int fin_status = DSB_STATUS_OK;
     auto finish = [&](int status) { fin_status = status; state = L_FINISH; };
@@ -237,6 +260,62 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
         for (int i = 0; i < N; ++i) { x[i] = SD(j, i); ref[i] = SY(i); }
         return DSB_DIV_N(weighted_sum(x, ref));
     };
+    // ---- sensitivities (only instantiated for DsbWithSens<M>) ----
+    // squared_norm(x, ref, sens_atol, sens_rtol) (bdf.rs:844-858, 908-919)
+    auto sens_weighted_norm = [&](const double (&x)[N], const double (&ref)[N]) -> double {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double term = DSB_DIV(x[i], dsb_abs(ref[i]) * pa.sens_rtol + pa.sens_atol[i]);
+            acc += term * term;
+        }
+        return DSB_DIV_N(acc);
+    };
+    // f_p e_q at (x, tq) for every parameter: SensRhs::update_state through _default_sens_inplace
+    // (sens_equations.rs:129-134, op/nonlinear_op.rs:72-81)
+    auto sens_update_state = [&](const double (&x)[N], double tq) {
+        if constexpr (SENS) {
+        double pl_[NP > 0 ? NP : 1], e[NP > 0 ? NP : 1], colv[N];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) { pl_[j] = SP(j); e[j] = 0.0; }
+#pragma unroll 1
+        for (int q = 0; q < NP; ++q) {
+#pragma unroll
+            for (int j = 0; j < NP; ++j) e[j] = (j == q) ? 1.0 : 0.0;
+            M::sens_mul(x, pl_, tq, e, colv);
+#pragma unroll
+            for (int i = 0; i < N; ++i) SFP(q, i) = colv[i];
+        }
+        }
+    };
+    // the start of the Newton solve for sensitivity q (bdf.rs:948-968): predictor and psi from sdiff[q], s_new <- s_predict
+    auto sens_setup = [&](int q) {
+        double sp[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) sp[i] = 0.0;
+#pragma unroll 1
+        for (int j = 0; j <= order; ++j) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) sp[i] += SDF(q, j, i);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) psi_neg_y0[i] = pa.tab.gamma[1] * SDF(q, 1, i);
+#pragma unroll 1
+        for (int j = 2; j <= order; ++j) {
+            const double g = pa.tab.gamma[j];
+#pragma unroll
+            for (int i = 0; i < N; ++i) psi_neg_y0[i] = g * SDF(q, j, i) + psi_neg_y0[i];
+        }
+        const double a = pa.tab.alpha[order];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            psi_neg_y0[i] *= a;
+            psi_neg_y0[i] -= sp[i];
+            SPR(i) = sp[i];
+            y_cur[i] = sp[i];
+        }
+        conv.reset();
+    };
 
 #ifdef DSB_LANE_PROFILE          // warp-scheduler occupancy counters (warp-uniform values, lane 0 publishes them)
     unsigned long long prof[12];
@@ -315,6 +394,35 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                     M::root(y0l, pl0, t, rf.g0);
                     rf.t0 = t; root_found = -1;
                 }
+                if constexpr (SENS) {
+                    // state.rs:1158-1180 (s_q = (d y0 / d p) e_q), :178-189 (ds_q = J(y0) s_q + f_p e_q), bdf_state.rs:88-98
+                    // (sdiff[q][:, 0] = s_q, [:, 1] = h ds_q)
+                    double y0l[N], pl0[NP > 0 ? NP : 1], e[NP > 0 ? NP : 1], sq[N], dsq[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) y0l[i] = SY(i);
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) { pl0[j] = SP(j); e[j] = 0.0; }
+                    sens_update_state(y0l, t);
+#pragma unroll 1
+                    for (int q = 0; q < NP; ++q) {
+#pragma unroll
+                        for (int j = 0; j < NP; ++j) e[j] = (j == q) ? 1.0 : 0.0;
+                        M::init_sens(pl0, pa.t0, e, sq);
+                        M::jac_mul(y0l, pl0, t, sq, dsq);
+                        st.v[DSB_STAT_RHS_JAC_MULS] += 1;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            dsq[i] += SFP(q, i);
+                            SSS(q, i) = sq[i]; SDL(q, i) = 0.0;
+                            SDF(q, 0, i) = sq[i]; SDF(q, 1, i) = dsq[i] * h;
+                        }
+#pragma unroll 1
+                        for (int j = 2; j < DSB_NDIFF; ++j)
+#pragma unroll
+                            for (int i = 0; i < N; ++i) SDF(q, j, i) = 0.0;
+                    }
+                    eq = 0; c_sens = 0.0;
+                }
                 c = h * pa.tab.alpha[1];
                 jacobian_is_stale = true;
                 ju.init(1.0);                                   // jacobian_update.rs:27 -- h_at_last starts at ONE
@@ -366,6 +474,18 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                         if ((q == 0) ? (ord > 1) : (ord < DSB_MAX_ORDER)) {
                             const double e = diff_col_norm(ord + q) * pa.tab.error_const2[ord - 1 + q];
                             err = (0.0 < e) ? e : 0.0;
+                            if constexpr (SENS) {               // predict_error_control's sensitivity terms (bdf.rs:908-919)
+                                if (pa.sens_error_control) {
+#pragma unroll 1
+                                    for (int qs = 0; qs < NP; ++qs) {
+                                        double x[N], ref[N];
+#pragma unroll
+                                        for (int i = 0; i < N; ++i) { x[i] = SDF(qs, ord + q, i); ref[i] = SSS(qs, i); }
+                                        const double es = sens_weighted_norm(x, ref) * pa.tab.error_const2[ord - 1 + q];
+                                        err = (err < es) ? es : err;
+                                    }
+                                }
+                            }
                         }
                     }
                     const double v = pi_controller_raw(err, ord + q);
@@ -448,6 +568,44 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #pragma unroll
                     for (int s = 0; s < N; ++s) SD(j, s) = nd[j][s];
                 }
+            }
+            if constexpr (SENS) {
+                // the same RU on every sdiff (bdf.rs:539-541); the reference's shared ping-pong buffer only moves columns
+                // above the order around, which are rewritten before anything reads them
+#pragma unroll 1
+                for (int qs = 0; qs < NP; ++qs) {
+#pragma unroll
+                    for (int l = 1; l <= DSB_MAX_ORDER; ++l) {
+                        rrow[l] = 1.0;
+#pragma unroll
+                        for (int s = 0; s < N; ++s) nd[l][s] = -0.0;
+                    }
+#pragma unroll 1
+                    for (int i = 1; i <= k; ++i) {
+                        const double i_t = (double)i;
+#pragma unroll
+                        for (int l = 1; l <= DSB_MAX_ORDER; ++l) rrow[l] = DSB_DIV(rrow[l] * (i_t - 1.0 - factor * (double)l), i_t);
+                        double di[N];
+#pragma unroll
+                        for (int s = 0; s < N; ++s) di[s] = SDF(qs, i, s);
+#pragma unroll
+                        for (int j = 1; j <= DSB_MAX_ORDER; ++j) {
+                            double ru_ij = rrow[1] * u[j * 6 + 1];
+#pragma unroll
+                            for (int l = 2; l <= j; ++l) ru_ij = rrow[l] * u[j * 6 + l] + ru_ij;
+#pragma unroll
+                            for (int s = 0; s < N; ++s) nd[j][s] = di[s] * ru_ij + nd[j][s];
+                        }
+                    }
+#pragma unroll
+                    for (int j = 1; j <= DSB_MAX_ORDER; ++j) {
+                        if (j <= k) {
+#pragma unroll
+                            for (int s = 0; s < N; ++s) SDF(qs, j, s) = nd[j][s];
+                        }
+                    }
+                }
+                c_sens = new_h * pa.tab.alpha[k];
             }
             c = new_h * pa.tab.alpha[k];
             h = new_h;
@@ -626,6 +784,23 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                 double yo[N];
                 interpolate(tq, yo);
                 write_column(col, tq, yo);
+                if constexpr (SENS) {                   // interpolate_sens (bdf.rs:1162-1215): interpolate_from_diff on every sdiff
+#pragma unroll 1
+                    for (int qs = 0; qs < NP; ++qs) {
+                        double time_factor = 1.0;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) yo[i] = SDF(qs, 0, i);
+#pragma unroll 1
+                        for (int j = 0; j < order; ++j) {
+                            const double j_t = (double)j;
+                            time_factor *= DSB_DIV(tq - (t - h * j_t), h * (1.0 + j_t));
+#pragma unroll
+                            for (int i = 0; i < N; ++i) yo[i] = time_factor * SDF(qs, j + 1, i) + yo[i];
+                        }
+#pragma unroll
+                        for (int i = 0; i < N; ++i) bb.ss[(((int64_t)col * NP + qs) * N + i) * B + inst] = yo[i];
+                    }
+                }
                 ++col;
             }
             if (status != DSB_STATUS_OK) finish(status);
@@ -640,7 +815,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
         // ================= PREDICT: _predict_forward + start of a Newton solve ============================
         DSB_PROF_BLOCK(5, state == L_PREDICT)
         if (__any_sync(0xffffffffu, state == L_PREDICT) && state == L_PREDICT) {
-            if (repredict) {
+            if (repredict || SENS) {        // (sensitivities: psi_neg_y0 was reused by the sensitivity solves; the same values again)
                 double yp[N];
 #pragma unroll
                 for (int i = 0; i < N; ++i) yp[i] = 0.0;
@@ -685,6 +860,26 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #pragma unroll
             for (int j = 0; j < NP; ++j) pl[j] = SP(j);
             double delta[N];
+            bool sens_eq = false;
+            if constexpr (SENS) sens_eq = eq > 0;
+            if (sens_eq) {
+                if constexpr (SENS) {
+                    // BdfCallable<SensEquations>::call_inplace (op/bdf.rs:240-256) on SensRhs::call_inplace
+                    // (sens_equations.rs:168-174): J(y_predict) s + f_p e_q, with the sensitivity residual's own c
+                    double ypl_[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) ypl_[i] = SYP(i);
+                    M::jac_mul(ypl_, pl, t_predict, y_cur, delta);
+                    st.v[DSB_STAT_RHS_JAC_MULS] += 1;
+                    const double mc = -c_sens;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        delta[i] += SFP(eq - 1, i);
+                        const double tmp = y_cur[i] + psi_neg_y0[i];
+                        delta[i] = tmp + mc * delta[i];
+                    }
+                }
+            } else {
             M::rhs(y_cur, pl, t_predict, delta);
             st.v[DSB_STAT_RHS_CALLS] += 1;
             {
@@ -698,6 +893,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #pragma unroll
                     for (int i = 0; i < N; ++i) delta[i] = tmp[i] + mc * delta[i];
                 }
+            }
             }
             LaneLU<N, DSB_NEWTON_DIV> lu;
 #pragma unroll
@@ -718,7 +914,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
             } else {
                 double ypl[N];
 #pragma unroll
-                for (int i = 0; i < N; ++i) { y_cur[i] -= delta[i]; ypl[i] = SYP(i); }
+                for (int i = 0; i < N; ++i) { y_cur[i] -= delta[i]; ypl[i] = sens_eq ? SPR(i) : SYP(i); }
                 // Newton norm weights use the PREDICTOR (line_search.rs:67, convergence.rs:64-66)
                 const double acc = weighted_sum(delta, ypl);
                 const double norm = dsb_sqrt(DSB_DIV_N(acc));
@@ -751,8 +947,46 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
         // ================= POST: a Newton solve ended (bdf.rs:1338-1563) ==================================
         DSB_PROF_BLOCK(9, state == L_POST)
         if (__any_sync(0xffffffffu, state == L_POST) && state == L_POST) {
-            st.v[DSB_STAT_NONLINEAR_SOLVER_ITERATIONS] += conv.niter;
-            if (newton_ok) {
+            bool run_main = true;
+            if constexpr (SENS) {
+                // sensitivity_solve (bdf.rs:934-989) after a successful main solve: one Newton solve per parameter on the
+                // same LU and the same Convergence; a failed sensitivity solve is a failed step whose iterations are NOT counted
+                // (the `?` returns before the statistics line)
+                if (eq == 0 || newton_ok) st.v[DSB_STAT_NONLINEAR_SOLVER_ITERATIONS] += conv.niter;
+                if (newton_ok) {
+                    if (eq == 0) {
+                        double ypl_[N];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) { SYC(i) = y_cur[i]; ypl_[i] = SYP(i); }
+                        sens_update_state(ypl_, t_predict);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            SSS(eq - 1, i) = y_cur[i];
+                            double dl = y_cur[i];
+                            dl -= SPR(i);
+                            SDL(eq - 1, i) = dl;
+                        }
+                    }
+                    if (eq < NP) {
+                        sens_setup(eq);
+                        eq += 1;
+                        state = L_NEWTON;
+                        run_main = false;
+                    } else {
+                        eq = 0;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) y_cur[i] = SYC(i);
+                    }
+                } else {
+                    eq = 0;
+                }
+            } else {
+                st.v[DSB_STAT_NONLINEAR_SOLVER_ITERATIONS] += conv.niter;
+            }
+            if (!run_main) {
+                // on to the next sensitivity solve
+            } else if (newton_ok) {
                 const int ord = order;
                 double d[N];
 #pragma unroll
@@ -764,6 +998,18 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                     const double acc = weighted_sum(d, yl);
                     const double err = DSB_DIV_N(acc) * pa.tab.error_const2[ord - 1];
                     error_norm = (0.0 < err) ? err : 0.0;
+                }
+                if constexpr (SENS) {               // NB error_const2[order] for the sensitivities (bdf.rs:844-858)
+                    if (pa.sens_error_control) {
+#pragma unroll 1
+                        for (int qs = 0; qs < NP; ++qs) {
+                            double x[N], ref[N];
+#pragma unroll
+                            for (int i = 0; i < N; ++i) { x[i] = SDL(qs, i); ref[i] = SSS(qs, i); }
+                            const double es = sens_weighted_norm(x, ref) * pa.tab.error_const2[ord];
+                            error_norm = (error_norm < es) ? es : error_norm;
+                        }
+                    }
                 }
 #ifndef DSB_NO_HOST_TABLES     // A/B switch: 61.5 -> 59.4 ms per 10^6 Robertson instances (profiles/r2_lane_kernel_ab.log)
                 if (conv.niter < 32) {
@@ -786,6 +1032,22 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                     for (int j = ord; j >= 0; --j) {
 #pragma unroll
                         for (int i = 0; i < N; ++i) SD(j, i) = SD(j, i) + 1.0 * SD(j + 1, i);
+                    }
+                    if constexpr (SENS) {           // _update_diff on every sdiff (bdf.rs:629-633)
+#pragma unroll 1
+                        for (int qs = 0; qs < NP; ++qs) {
+#pragma unroll
+                            for (int i = 0; i < N; ++i) {
+                                const double dl = SDL(qs, i);
+                                SDF(qs, ord + 2, i) = dl - SDF(qs, ord + 1, i);
+                                SDF(qs, ord + 1, i) = dl;
+                            }
+#pragma unroll 1
+                            for (int j = ord; j >= 0; --j) {
+#pragma unroll
+                                for (int i = 0; i < N; ++i) SDF(qs, j, i) = SDF(qs, j, i) + 1.0 * SDF(qs, j + 1, i);
+                            }
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < N; ++i) SY(i) = SYP(i);
@@ -837,4 +1099,10 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #undef SY
 #undef SYP
 #undef SP
+#undef SDF
+#undef SSS
+#undef SDL
+#undef SFP
+#undef SPR
+#undef SYC
 }

@@ -51,6 +51,7 @@ struct dsb_batch {
     unsigned long long* work_counter = nullptr;
     double* t_eval = nullptr; int t_eval_cap = 0;
     double* ys_own = nullptr; size_t ys_own_bytes = 0;       // used by the *_host entry point
+    double* sens_own = nullptr; size_t sens_own_bytes = 0;   // batch-major sensitivities of the *_sensitivities_host entry points
     void* stage = nullptr; size_t stage_bytes = 0;           // instance-major staging for host copies
     cudaEvent_t ev0 = nullptr, ev_mid = nullptr, ev1 = nullptr;
     int last_launches = 0;
@@ -263,6 +264,16 @@ int dsb_problem_set_options(dsb_problem* p, const dsb_options* opt) {
     if (opt->max_nonlinear_solver_iterations < 1) return fail(DSB_BAD_ARG, "max_nonlinear_solver_iterations < 1");
     p->opt = *opt; return DSB_OK;
 }
+int dsb_problem_set_sensitivities(dsb_problem* p, int32_t enable, double sens_rtol, const double* sens_atol, int32_t natol) {
+    if (!p) return fail(DSB_BAD_ARG, "problem is NULL");
+    if (!enable) { p->sens = 0; p->sens_atol.clear(); p->sens_rtol = 0.0; return DSB_OK; }
+    if (natol != 0 && natol != 1 && natol != p->n) return fail(DSB_BAD_ARG, "sens_atol must have 0, 1 or nstates entries");
+    if (natol > 0 && (!sens_atol || !(sens_rtol >= 0.0))) return fail(DSB_BAD_ARG, "sens_atol is NULL or sens_rtol is negative");
+    p->sens = 1;
+    p->sens_rtol = sens_rtol;
+    p->sens_atol.assign(sens_atol, sens_atol + (natol > 0 ? natol : 0));
+    return DSB_OK;
+}
 int dsb_problem_get_options(const dsb_problem* p, dsb_options* opt) {
     if (!p || !opt) return fail(DSB_BAD_ARG, "NULL argument");
     *opt = p->opt; return DSB_OK;
@@ -365,7 +376,7 @@ int dsb_batch_free(dsb_batch* b) {
     for (cudaEvent_t ev : b->chunk_done) cudaEventDestroy(ev);
     cudaFree(b->params); cudaFree(b->y0); cudaFree(b->dy0); cudaFree(b->h0);
     cudaFree(b->fin_t); cudaFree(b->fin_h); cudaFree(b->fin_order); cudaFree(b->root_idx); cudaFree(b->ncols);
-    cudaFree(b->stats); cudaFree(b->status); cudaFree(b->work_counter); cudaFree(b->coop.ws_mem); cudaFree(b->coop.atol_dev); cudaFree(b->coop.color_dev); cudaFree(b->coop.wb_mem); cudaFree(b->coop.ys_im_own); cudaFree(b->t_eval); cudaFree(b->ys_own); cudaFree(b->stage);
+    cudaFree(b->stats); cudaFree(b->status); cudaFree(b->work_counter); cudaFree(b->coop.ws_mem); cudaFree(b->coop.atol_dev); cudaFree(b->coop.color_dev); cudaFree(b->coop.wb_mem); cudaFree(b->coop.ys_im_own); cudaFree(b->t_eval); cudaFree(b->ys_own); cudaFree(b->sens_own); cudaFree(b->stage);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->ev_mid) cudaEventDestroy(b->ev_mid);
@@ -402,8 +413,10 @@ int dsb_batch_set_params_host(dsb_batch* b, const double* params, int64_t nbatch
 // ys_im: instance-major buffer offered to kernels that write that layout (NULL: they use their own and the result is
 // re-laid out into ys_dev); *wrote_im (may be NULL) reports that the result is in ys_im and ys_dev was NOT written
 static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_t nt, double* ys_dev, void* stream_,
-                      int free_running, double* ys_im = nullptr, int* wrote_im = nullptr) {
+                      int free_running, double* ys_im = nullptr, int* wrote_im = nullptr, double* sens_dev = nullptr) {
     if (!b || !t_eval || nt < 1 || !ys_dev) return fail(DSB_BAD_ARG, "bad argument to dsb_batch_solve_dense");
+    if (sens_dev && !b->prob.sens) return fail(DSB_BAD_ARG, "the problem has no sensitivities enabled (dsb_problem_set_sensitivities)");
+    if (!sens_dev && b->prob.sens) return fail(DSB_BAD_ARG, "a problem with sensitivities is solved through dsb_batch_solve_dense_sensitivities");
     if (method != DSB_METHOD_BDF && method != DSB_METHOD_TR_BDF2 && method != DSB_METHOD_ESDIRK34)
         return fail(DSB_BAD_ARG, "unknown method");
     // solve_dense walks forward through t_eval (method.rs:761-764); the free-running loop steps while |t| < |t_k|
@@ -436,6 +449,8 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     bb.ys = ys_dev; bb.stats = b->stats; bb.status = b->status;
     bb.fin_t = b->fin_t; bb.fin_h = b->fin_h; bb.fin_order = b->fin_order;
     bb.root_idx = b->root_idx; bb.ncols = b->ncols;
+    bb.ss = sens_dev;
+    if (sens_dev) DSB_CUDA(cudaMemsetAsync(sens_dev, 0xFF, (size_t)nt * b->prob.np * b->prob.n * b->B * 8, stream));
     // kernels without root finding leave these alone: no root, every column
     DSB_CUDA(cudaMemsetAsync(b->root_idx, 0xFF, (size_t)b->B * 4, stream));
     dsb_fill_i32_kernel<<<(unsigned)((b->B + 255) / 256), 256, 0, stream>>>(b->ncols, b->B, nt);
@@ -454,6 +469,8 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     if (wrote_im) *wrote_im = 0;
     const dsb_launch_fn launch = pm ? pm->launch : g_launch_table[b->prob.model];
     cudaError_t lerr = launch(&pa, &bb, method, stream, b->ev_mid, b->work_counter, &b->coop, atol_full.data(), &b->last_launches);
+    if (lerr == cudaErrorNotSupported && b->prob.sens)
+        return fail(DSB_ERR, "forward sensitivities are built for BDF on equation sets with sens_mul / init_sens, no mass matrix, no root / output / reset function and n <= 16");
     if (lerr == cudaErrorNotSupported) return fail(DSB_ERR, "this execution mode is not available for this equation set and method (thread per instance: n <= 16; banded thread per instance: component-wise equations with a declared band, n > 16; banded warp per instance: the same, BDF, no reset function; block per instance: n <= 512)");
     if (lerr != cudaSuccess) return fail(DSB_ERR, std::string("kernel launch: ") + cudaGetErrorString(lerr));
     if (b->coop.ys_im_used) {
@@ -479,6 +496,17 @@ int dsb_batch_solve_dense(dsb_batch* b, int32_t method, const double* t_eval, in
 int dsb_batch_step_and_interpolate(dsb_batch* b, int32_t method, const double* t_points, int32_t npts, double* ys_dev,
                                    void* stream) {
     return solve_impl(b, method, t_points, npts, ys_dev, stream, 1);
+}
+
+int dsb_batch_solve_dense_sensitivities(dsb_batch* b, int32_t method, const double* t_eval, int32_t nt, double* ys_dev, double* sens_dev,
+                                        void* stream) {
+    if (!sens_dev) return fail(DSB_BAD_ARG, "sens_dev is NULL");
+    return solve_impl(b, method, t_eval, nt, ys_dev, stream, 0, nullptr, nullptr, sens_dev);
+}
+int dsb_batch_step_and_interpolate_sensitivities(dsb_batch* b, int32_t method, const double* t_points, int32_t npts, double* ys_dev,
+                                                 double* sens_dev, void* stream) {
+    if (!sens_dev) return fail(DSB_BAD_ARG, "sens_dev is NULL");
+    return solve_impl(b, method, t_points, npts, ys_dev, stream, 1, nullptr, nullptr, sens_dev);
 }
 
 int dsb_batch_set_execution(dsb_batch* b, int32_t mode) {
@@ -700,6 +728,74 @@ static int solve_host_impl(dsb_batch* b, int32_t method, const double* params_ho
     b->have_timing = true;
     DSB_CUDA(cudaStreamSynchronize(0));
     return DSB_OK;
+}
+
+// Sensitivities with HOST buffers: parameters up, solve, the states and the sensitivities transposed to instance-major
+// through the staging block (one after the other on the default stream), counters and status down, synchronise.
+static int solve_sens_host_impl(dsb_batch* b, int32_t method, const double* params_host, int32_t nparams, const double* t_eval,
+                                int32_t nt, double* ys_host, double* sens_host, int64_t* stats_host, int32_t* status_host, int free_running) {
+    if (!b || !ys_host || !sens_host) return fail(DSB_BAD_ARG, "NULL argument");
+    if (!t_eval || nt < 1) return fail(DSB_BAD_ARG, "t_eval must hold at least one time");
+    if (nparams < 1 || !params_host || nparams != b->prob.np) return fail(DSB_BAD_ARG, "parameter shape mismatch");
+    if (!b->prob.sens) return fail(DSB_BAD_ARG, "the problem has no sensitivities enabled (dsb_problem_set_sensitivities)");
+    DSB_CUDA(cudaSetDevice(b->device));
+    cudaStream_t stream = 0;
+    const int n = b->prob.n;
+    const size_t ys_bytes = (size_t)nt * n * b->B * 8, sens_bytes = ys_bytes * (size_t)nparams;
+    size_t stage_need = sens_bytes;
+    if ((size_t)b->B * DSB_NSTATS * 8 > stage_need) stage_need = (size_t)b->B * DSB_NSTATS * 8;
+    if ((size_t)b->B * nparams * 8 > stage_need) stage_need = (size_t)b->B * nparams * 8;
+    if (ensure_stage(b, stage_need) != DSB_OK) return DSB_ERR;
+    if (b->ys_own_bytes < ys_bytes) {
+        cudaFree(b->ys_own); b->ys_own = nullptr; b->ys_own_bytes = 0;
+        DSB_CUDA(cudaMalloc((void**)&b->ys_own, ys_bytes));
+        b->ys_own_bytes = ys_bytes;
+    }
+    if (b->sens_own_bytes < sens_bytes) {
+        cudaFree(b->sens_own); b->sens_own = nullptr; b->sens_own_bytes = 0;
+        DSB_CUDA(cudaMalloc((void**)&b->sens_own, sens_bytes));
+        b->sens_own_bytes = sens_bytes;
+    }
+    DSB_CUDA(cudaMemcpyAsync(b->stage, params_host, (size_t)b->B * nparams * 8, cudaMemcpyHostToDevice, stream));
+    int rc = dsb_batch_set_params_device(b, (const double*)b->stage, b->B, nparams, stream);
+    if (rc != DSB_OK) return rc;
+    rc = solve_impl(b, method, t_eval, nt, b->ys_own, stream, free_running, nullptr, nullptr, b->sens_own);
+    if (rc != DSB_OK) return rc;
+    dim3 block(32, 8);
+    {
+        const int m = nt * n;
+        dim3 grid((unsigned)((b->B + 31) / 32), (unsigned)((m + 31) / 32));
+        dsb_to_instance_major_kernel<<<grid, block, 0, stream>>>(b->ys_own, (double*)b->stage, b->B, m);
+        DSB_CUDA(cudaGetLastError());
+        DSB_CUDA(cudaMemcpyAsync(ys_host, b->stage, ys_bytes, cudaMemcpyDeviceToHost, stream));
+    }
+    {
+        const int m = nt * nparams * n;
+        dim3 grid((unsigned)((b->B + 31) / 32), (unsigned)((m + 31) / 32));
+        dsb_to_instance_major_kernel<<<grid, block, 0, stream>>>(b->sens_own, (double*)b->stage, b->B, m);
+        DSB_CUDA(cudaGetLastError());
+        DSB_CUDA(cudaMemcpyAsync(sens_host, b->stage, sens_bytes, cudaMemcpyDeviceToHost, stream));
+    }
+    int extra = 3;
+    if (stats_host) {
+        if (dsb_batch_get_stats_device(b, (int64_t*)b->stage, stream) != DSB_OK) return DSB_ERR;
+        ++extra;
+        DSB_CUDA(cudaMemcpyAsync(stats_host, b->stage, (size_t)b->B * DSB_NSTATS * 8, cudaMemcpyDeviceToHost, stream));
+    }
+    if (status_host) DSB_CUDA(cudaMemcpyAsync(status_host, b->status, (size_t)b->B * 4, cudaMemcpyDeviceToHost, stream));
+    b->last_launches += extra;
+    DSB_CUDA(cudaStreamSynchronize(stream));
+    return DSB_OK;
+}
+
+int dsb_batch_solve_dense_sensitivities_host(dsb_batch* b, int32_t method, const double* params_host, int32_t nparams, const double* t_eval,
+                                             int32_t nt, double* ys_host, double* sens_host, int64_t* stats_host, int32_t* status_host) {
+    return solve_sens_host_impl(b, method, params_host, nparams, t_eval, nt, ys_host, sens_host, stats_host, status_host, 0);
+}
+int dsb_batch_step_and_interpolate_sensitivities_host(dsb_batch* b, int32_t method, const double* params_host, int32_t nparams,
+                                                      const double* t_points, int32_t npts, double* ys_host, double* sens_host,
+                                                      int64_t* stats_host, int32_t* status_host) {
+    return solve_sens_host_impl(b, method, params_host, nparams, t_points, npts, ys_host, sens_host, stats_host, status_host, 1);
 }
 
 int dsb_batch_solve_dense_host(dsb_batch* b, int32_t method, const double* params_host, int32_t nparams,

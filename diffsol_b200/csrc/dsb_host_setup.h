@@ -24,6 +24,9 @@ struct dsb_problem {
     double t0, h0;
     int use_coloring;
     dsb_options opt;
+    int sens = 0;               // forward sensitivities (dsb_problem_set_sensitivities)
+    double sens_rtol = 0.0;
+    std::vector<double> sens_atol;   // empty: not in the error test; 1 entry broadcasts
 };
 
 namespace dsb_host {
@@ -177,6 +180,11 @@ inline int fill_problem_args(const dsb_problem& pr, int64_t B, int nt, DsbProble
     pa->opt = pr.opt;
     build_tables(&pa->tab, &pr.opt);
     pa->use_coloring = pr.use_coloring;
+    pa->sens = pr.sens;
+    pa->sens_error_control = pr.sens && !pr.sens_atol.empty();
+    pa->sens_rtol = pr.sens_rtol;
+    for (int i = 0; i < pr.n && i < DSB_MAX_STATES && !pr.sens_atol.empty(); ++i)
+        pa->sens_atol[i] = pr.sens_atol.size() == 1 ? pr.sens_atol[0] : pr.sens_atol[i];
     *probes = 0;
     if (pr.use_coloring) {
         ColoringOf f{&pr, pa, probes, color_full, nz_full};

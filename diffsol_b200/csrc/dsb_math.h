@@ -50,6 +50,11 @@ template <class M> struct dsb_model_has_reset<M, decltype((void)M::HAS_RESET)> {
 // and M::init_sens(p, t, v, y) = (d y0 / d p) v
 template <class M, class = void> struct dsb_model_has_sens { static constexpr bool value = false; };
 template <class M> struct dsb_model_has_sens<M, decltype((void)M::HAS_SENS)> { static constexpr bool value = M::HAS_SENS; };
+// DsbWithSens<M>: the equation set M with the sensitivity equations switched ON -- the kernels integrate one sensitivity
+// vector per parameter beside the state (Bdf<.., SensEquations>, ode_solver/bdf.rs:934-989) only in this instantiation
+template <class M, class = void> struct dsb_model_sens_on { static constexpr bool value = false; };
+template <class M> struct dsb_model_sens_on<M, decltype((void)M::SENS_ON)> { static constexpr bool value = M::SENS_ON; };
+template <class M> struct DsbWithSens : M { static constexpr bool SENS_ON = true; };
 
 struct dsb_log_row { double invc, logc_hi, logc_lo; };
 struct dsb_exp_row { double hi, lo; };

@@ -138,6 +138,15 @@ struct ModelExpDecayAlgebraic {
     DSB_HD static void init(const double*, double, double* y) {
         y[0] = 1.0; y[1] = 1.0; y[2] = 0.0;
     }
+    // forward sensitivities (oracle pin only, see ModelRobertsonDae): exponential_decay_with_algebraic_sens / _init_sens
+    // (test_models/exponential_decay_with_algebraic.rs:32-43, 128-135), the problem of ..._problem_sens (:418-453)
+    static constexpr bool HAS_SENS = true;
+    DSB_HD static void sens_mul(const double* x, const double*, double, const double* v, double* y) {
+        const double mv = -v[0];
+        for (int i = 0; i < N; ++i) y[i] = x[i] * mv;
+        y[N - 1] = 0.0;
+    }
+    DSB_HD static void init_sens(const double*, double, const double*, double* y) { for (int i = 0; i < N; ++i) y[i] = 0.0; }
 };
 
 // Robertson chemical kinetics as an index-1 DAE, p = [k1, k2, k3]
@@ -162,6 +171,16 @@ struct ModelRobertsonDae {
     DSB_HD static void init(const double*, double, double* y) {
         y[0] = 1.0; y[1] = 0.0; y[2] = 0.0;
     }
+    // forward sensitivities: robertson_sens_mul / robertson_init_sens (test_models/robertson.rs:73-77, 91-93), the problem of
+    // robertson_sens (:151-201).  The kernels integrate sensitivities for ODEs only; the oracle restates the DAE case too
+    // (consistent initialisation of the sensitivities, state.rs:167-238) to pin itself against bdf.rs:2248-2271.
+    static constexpr bool HAS_SENS = true;
+    DSB_HD static void sens_mul(const double* x, const double*, double, const double* v, double* y) {
+        y[0] = -v[0] * x[0] + v[1] * x[1] * x[2];
+        y[1] = v[0] * x[0] - v[1] * x[1] * x[2] - v[2] * x[1] * x[1];
+        y[2] = 0.0;
+    }
+    DSB_HD static void init_sens(const double*, double, const double*, double* y) { y[0] = 0.0; y[1] = 0.0; y[2] = 0.0; }
 };
 
 // Robertson as a pure ODE, NG decoupled copies (robertson_ode.rs `ngroups`)

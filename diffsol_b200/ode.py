@@ -35,6 +35,7 @@ class OdeSolverProblem:
         self.nbatch = nbatch
         self.p = params
         self.device = device
+        self.has_sens = False
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -53,6 +54,13 @@ class OdeSolverProblem:
     def esdirk34(self):
         return self._solver("esdirk34")
 
+    def bdf_sens(self):
+        """`problem.bdf_sens::<LS>()` (ode_solver/problem.rs:819-830): BDF with one forward sensitivity per parameter.  The
+        builder must have been given sens_rtol / sens_atol or sensitivities(True)."""
+        if not self.has_sens:
+            raise ValueError("build the problem with OdeBuilder.sens_rtol(..).sens_atol(..) or .sensitivities()")
+        return self._solver("bdf")
+
 
 class OdeBuilder:
     """Fluent builder; defaults are the reference's (builder.rs:112-140): t0=0, h0=1, rtol=1e-6, atol=[1e-6]."""
@@ -65,6 +73,7 @@ class OdeBuilder:
         self._nbatch = None
         self._device = 0
         self._opts = {}
+        self._sens, self._sens_rtol, self._sens_atol = False, None, None
 
     def rhs_implicit(self, model):
         if model not in capi.MODELS:
@@ -99,6 +108,18 @@ class OdeBuilder:
     def use_coloring(self, v):
         self._coloring = bool(v); return self
 
+    def sens_rtol(self, v):
+        """OdeBuilder::sens_rtol (builder.rs:1454-1464); with sens_atol the sensitivities join the error test."""
+        self._sens, self._sens_rtol = True, float(v); return self
+
+    def sens_atol(self, v):
+        """OdeBuilder::sens_atol (builder.rs:1466-1477): one entry broadcasts, else one per state."""
+        self._sens, self._sens_atol = True, [float(x) for x in np.atleast_1d(v)]; return self
+
+    def sensitivities(self, on=True):
+        """Integrate the sensitivities without putting them into the error test (turn_off_sensitivities_error_control)."""
+        self._sens = bool(on); return self
+
     def nbatch(self, b):
         self._nbatch = int(b); return self
 
@@ -126,6 +147,11 @@ class OdeBuilder:
             capi.check(L.dsb_problem_set_t0(h, self._t0))
             capi.check(L.dsb_problem_set_h0(h, self._h0))
             capi.check(L.dsb_problem_set_use_coloring(h, int(self._coloring)))
+            if self._sens:
+                if (self._sens_rtol is None) != (self._sens_atol is None):
+                    raise ValueError("sens_rtol and sens_atol go together")
+                sa = np.asarray(self._sens_atol or [], dtype=np.float64)
+                capi.check(L.dsb_problem_set_sensitivities(h, 1, self._sens_rtol or 0.0, _ptr(sa) if len(sa) else None, len(sa)))
             if self._opts:
                 o = capi.Options()
                 capi.check(L.dsb_problem_get_options(h, ctypes.byref(o)))
@@ -151,8 +177,10 @@ class OdeBuilder:
         except Exception:
             L.dsb_problem_free(h)
             raise
-        return OdeSolverProblem(h, self._model, n.value, npar.value, bool(hm.value), p.shape[0],
+        prob = OdeSolverProblem(h, self._model, n.value, npar.value, bool(hm.value), p.shape[0],
                                 np.ascontiguousarray(p), self._device, nout=nout.value)
+        prob.has_sens = self._sens
+        return prob
 
 
 class BatchedSolver:
@@ -196,6 +224,23 @@ class BatchedSolver:
             _ptr(ys), _ptr(stats), _ptr(status)))
         self._stats, self._status = stats, status
         return ys
+
+    def solve_dense_sensitivities(self, t_eval, free_running=False):
+        """`solve_dense_sensitivities(t_eval)` (ode_solver/sensitivities.rs:114-262) -> (ys[nbatch, nt, nstates],
+        sens[nbatch, nt, nparams, nstates]); free_running = the step()/interpolate()/interpolate_sens() loop of the
+        reference's tests instead (ode_solver/mod.rs:104-194)."""
+        pr = self.problem
+        t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
+        nt = len(t_eval)
+        ys = np.empty((pr.nbatch, nt, pr.nstates))
+        sens = np.empty((pr.nbatch, nt, pr.nparams, pr.nstates))
+        stats = np.empty((pr.nbatch, capi.DSB_NSTATS), dtype=np.int64)
+        status = np.empty(pr.nbatch, dtype=np.int32)
+        entry = "dsb_batch_step_and_interpolate_sensitivities_host" if free_running else "dsb_batch_solve_dense_sensitivities_host"
+        capi.check(getattr(capi.lib(), entry)(self._b, self.method, _ptr(pr.p), pr.nparams, _ptr(t_eval), nt,
+                                              _ptr(ys), _ptr(sens), _ptr(stats), _ptr(status)))
+        self._stats, self._status = stats, status
+        return ys, sens
 
     def solve_dense_device(self, t_eval, ys_dev_ptr, stream=None, params_dev_ptr=None):
         """Device-resident variant: ys_dev_ptr -> [nt][nout][nbatch] doubles (batch-major), asynchronous."""

@@ -126,6 +126,14 @@ int dsb_problem_set_h0(dsb_problem* p, double h0);                          /* O
 int dsb_problem_set_use_coloring(dsb_problem* p, int32_t use_coloring);      /* OdeBuilder::use_coloring  builder.rs:1852-1857 */
 int dsb_problem_set_options(dsb_problem* p, const dsb_options* opt);        /* OdeBuilder::ode_options / ic_options */
 int dsb_problem_get_options(const dsb_problem* p, dsb_options* opt);
+/* Forward sensitivities: OdeBuilder::sens_rtol / sens_atol (builder.rs:1466-1477, 1682-1716) and the choice of
+ * `problem.bdf_sens::<LS>()` over `problem.bdf::<LS>()` (ode_solver/problem.rs:819-830).  enable != 0: the batch integrates
+ * one sensitivity vector d y / d p_q per parameter beside the state (Bdf::sensitivity_solve, ode_solver/bdf.rs:934-989).
+ * natol == 0 keeps the sensitivities out of the error test (OdeBuilder::turn_off_sensitivities_error_control); natol == 1
+ * broadcasts sens_atol[0], natol == nstates gives it per state (param_scales = 1).  Equation sets qualify when they provide
+ * sens_mul / init_sens (OdeEquationsImplicitSens), have no mass matrix, no root / output / reset function and
+ * nstates <= 16; the method must be DSB_METHOD_BDF.  Anything else: DSB_ERR from the solve call. */
+int dsb_problem_set_sensitivities(dsb_problem* p, int32_t enable, double sens_rtol, const double* sens_atol, int32_t natol);
 
 /* ---- user equation sets: "user RHS closures and DiffSL-JIT modules drop in" -------------------------------------------------
  * The reference takes equations as Rust closures (builder.rs:192-200) or as a compiled DiffSL module consumed through its
@@ -179,6 +187,25 @@ int dsb_batch_solve_dense(dsb_batch* b, int32_t method, const double* t_eval, in
  * i.e. OdeSolverMethod::step (method.rs:99) + interpolate (method.rs:106) with NO stop time.  Same
  * layouts as dsb_batch_solve_dense.  This is the call that reproduces the reference's statistics snapshots. */
 int dsb_batch_step_and_interpolate(dsb_batch* b, int32_t method, const double* t_points, int32_t npts, double* ys_dev, void* stream);
+
+/* `problem.bdf_sens::<LS>()?.solve_dense_sensitivities(t_eval)` for every instance (ode_solver/sensitivities.rs:114-262,
+ * dense_write_out_sensitivities :360-397): the states as dsb_batch_solve_dense writes them, and
+ * sens_dev: DEVICE buffer of nt*nparams*nstates*nbatch doubles, sens[((k*nparams + q)*nstates + i)*nbatch + b] =
+ * d y_i / d p_q of instance b at t_eval[k].  The problem must have sensitivities enabled (dsb_problem_set_sensitivities).
+ * dsb_batch_step_and_interpolate_sensitivities is the free-running loop of the reference's tests with interpolate_sens
+ * at every point (test_ode_solver(.., solve_for_sensitivities = true), ode_solver/mod.rs:104-194). */
+int dsb_batch_solve_dense_sensitivities(dsb_batch* b, int32_t method, const double* t_eval, int32_t nt, double* ys_dev, double* sens_dev,
+                                        void* stream);
+int dsb_batch_step_and_interpolate_sensitivities(dsb_batch* b, int32_t method, const double* t_points, int32_t npts, double* ys_dev,
+                                                 double* sens_dev, void* stream);
+/* The same two calls with HOST buffers (parameters in, results back, synchronised): ys_host instance-major
+ * [nbatch][nt][nstates]; sens_host [nbatch][nt][nparams][nstates] -- instance b's block holds, for every time, the nparams
+ * sensitivity vectors one after the other (the Vec of matrices solve_dense_sensitivities returns, interleaved by time). */
+int dsb_batch_solve_dense_sensitivities_host(dsb_batch* b, int32_t method, const double* params_host, int32_t nparams, const double* t_eval,
+                                             int32_t nt, double* ys_host, double* sens_host, int64_t* stats_host, int32_t* status_host);
+int dsb_batch_step_and_interpolate_sensitivities_host(dsb_batch* b, int32_t method, const double* params_host, int32_t nparams,
+                                                      const double* t_points, int32_t npts, double* ys_host, double* sens_host,
+                                                      int64_t* stats_host, int32_t* status_host);
 
 /* Same call with HOST buffers: copies parameters in, runs, copies results back, synchronises.
  * ys_host layout is instance-major [nbatch][nt][nstates] (each instance's block is the column-major

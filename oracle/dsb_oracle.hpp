@@ -242,6 +242,11 @@ struct InitialState {
     Vec y, dy; double t = 0, h = 0;
 };
 int new_and_consistent(const Problem& pr, int solver_order, InitialState* st);
+// InitOp + Newton with the backtracking line search for the algebraic rows (state.rs:84-162 for the state, :167-238 for a
+// sensitivity vector); a no-op without a singular mass matrix
+int consistent_solve(const Problem& pr, const std::function<void(const double*, double, double*)>& eq_rhs,
+                     const std::function<void(const double*, double, double*)>& eq_jacobian, Vec& y_state, Vec& dy_state,
+                     Convergence* shared_conv, bool zero_dv);
 
 enum StopReason { INTERNAL_TIMESTEP = 0, TSTOP_REACHED = 1, STEP_ERROR = 2, ROOT_FOUND = 3 };
 

@@ -93,7 +93,7 @@ struct Bdf : Method {
         if (pr.sens) {
             // state.rs:1158-1180 initialise_augmented_state (s_i = (d y0 / d p) e_i), :178-189 set_consistent_augmented without
             // algebraic rows (ds_i = J(y0) s_i + f_p e_i), bdf_state.rs:88-98 initialise_sdiff_to_first_order
-            if (!pr.model.sens_mul || !pr.model.init_sens || pr.model.has_mass) return ST_BAD_ARG;
+            if (!pr.model.sens_mul || !pr.model.init_sens) return ST_BAD_ARG;
             ns = pr.model.np;
             s_.assign(ns, Vec(n, 0.0)); ds_ = s_; s_deltas = s_;
             sdiff.assign(ns, Vec((size_t)n * NCOLS, 0.0));
@@ -106,6 +106,18 @@ struct Bdf : Method {
             }
             update_rhs_out_state(y_.data(), t_);
             for (int i = 0; i < ns; ++i) sens_rhs(i, s_[i].data(), t_, ds_[i].data());
+            if (pr.model.has_mass) {
+                // set_consistent_augmented's algebraic part (state.rs:191-237): one Convergence for every parameter
+                Convergence ic_conv;
+                ic_conv.init(pr.rtol, pr.atol.data(), n, pr.opt.nonlinear_solver_tolerance, &pr.math);
+                ic_conv.max_iter = pr.opt.ic_max_newton_iterations;
+                for (int i = 0; i < ns; ++i) {
+                    int e = consistent_solve(pr, [this, i](const double* x, double tt, double* out) { sens_rhs(i, x, tt, out); },
+                                             [this](const double*, double tt, double* J) { pr.jacobian(sens_y.data(), tt, J); },
+                                             s_[i], ds_[i], &ic_conv, false);
+                    if (e) return e;
+                }
+            }
             for (int i = 0; i < ns; ++i)
                 for (int k = 0; k < n; ++k) { sdiff[i][k] = s_[i][k]; sdiff[i][(size_t)n + k] = ds_[i][k] * h_; }
         }
@@ -133,7 +145,8 @@ struct Bdf : Method {
         sens_rhs(index, x, t, out);
         for (int k = 0; k < n; ++k) tmp[k] = x[k] + psi_s[k];
         const double mc = -c_sens;
-        for (int k = 0; k < n; ++k) out[k] = tmp[k] + mc * out[k];
+        if (pr.model.has_mass) pr.mass_gemv(tmp.data(), t, mc, out);
+        else for (int k = 0; k < n; ++k) out[k] = tmp[k] + mc * out[k];
     }
     // bdf.rs:934-989.  false <=> a sensitivity solve failed (the iterations of the failed solve are NOT counted: the `?`
     // returns before the statistics line)

@@ -268,7 +268,13 @@ void Stats::record_linear_solver_setup(SolverState s) {
 // ---- consistent initialisation (ode_solver/state.rs:84-162, op/init.rs:14-131) -------------------
 // Newton with BacktrackingLineSearch (diffsol-nl/src/line_search.rs:115-201) on
 //   F(du, v) = -M_u du + f(u, v) ; g(u, v)      unknown x = (du at differential idx, v at algebraic idx)
-static int set_consistent(const Problem& pr, InitialState* st) {
+// The same solve serves the state (set_consistent, state.rs:84-162: eq_rhs / eq_jacobian = the equations' own, a fresh
+// Convergence, dy zeroed at the algebraic rows afterwards) and every sensitivity vector (set_consistent_augmented,
+// state.rs:167-238: eq_rhs = SensRhs::call, eq_jacobian = SensRhs::jacobian_inplace, ONE Convergence for all parameters,
+// ds kept at the algebraic rows).
+int consistent_solve(const Problem& pr, const std::function<void(const double*, double, double*)>& eq_rhs,
+                     const std::function<void(const double*, double, double*)>& eq_jacobian, Vec& y_state, Vec& dy_state,
+                     Convergence* shared_conv, bool zero_dv) {
     const int n = pr.n();
     if (!pr.model.has_mass) return ST_OK;
     Vec M((size_t)n * n);
@@ -277,10 +283,12 @@ static int set_consistent(const Problem& pr, InitialState* st) {
     int nalg = 0;
     for (int i = 0; i < n; ++i) if (M[(size_t)i * n + i] == 0.0) { is_alg[i] = 1; ++nalg; }
     if (nalg == 0) return ST_OK;
+    struct { Vec& y; Vec& dy; } state{y_state, dy_state};
+    auto* st = &state;
 
     // InitOp::new: rhs_jac at (y0, t0); jac = (-M_u | df/dv ; 0 | dg/dv); neg_mass = (-M_u | 0 ; 0 | 0)
     Vec rhs_jac((size_t)n * n), jac((size_t)n * n, 0.0), neg_mass((size_t)n * n, 0.0);
-    pr.jacobian(st->y.data(), pr.t0, rhs_jac.data());
+    eq_jacobian(st->y.data(), pr.t0, rhs_jac.data());
     for (int j = 0; j < n; ++j)
         for (int i = 0; i < n; ++i) {
             size_t ij = (size_t)j * n + i;
@@ -293,7 +301,7 @@ static int set_consistent(const Problem& pr, InitialState* st) {
     Vec y0 = st->y;   // InitOp.y0
     auto fun = [&](const Vec& x, Vec& out) {
         for (int i = 0; i < n; ++i) if (is_alg[i]) y0[i] = x[i];
-        pr.rhs(y0.data(), pr.t0, out.data());
+        eq_rhs(y0.data(), pr.t0, out.data());
         // neg_mass.gemv(1, x, 1, out): column sweep, out = (1 * col_j) * x_j + out
         for (int j = 0; j < n; ++j)
             for (int i = 0; i < n; ++i) out[i] = neg_mass[(size_t)j * n + i] * x[j] + out[i];
@@ -302,9 +310,12 @@ static int set_consistent(const Problem& pr, InitialState* st) {
     Vec y_tmp = st->dy;
     for (int i = 0; i < n; ++i) if (is_alg[i]) y_tmp[i] = st->y[i];
     Vec yerr = y_tmp;
-    Convergence conv;
-    conv.init(pr.rtol, pr.atol.data(), n, pr.opt.nonlinear_solver_tolerance, &pr.math);
-    conv.max_iter = pr.opt.ic_max_newton_iterations;
+    Convergence own_conv;
+    if (!shared_conv) {
+        own_conv.init(pr.rtol, pr.atol.data(), n, pr.opt.nonlinear_solver_tolerance, &pr.math);
+        own_conv.max_iter = pr.opt.ic_max_newton_iterations;
+    }
+    Convergence& conv = shared_conv ? *shared_conv : own_conv;
 
     const double tau = pr.opt.ic_step_reduction_factor, c_armijo = pr.opt.ic_armijo_constant;
     const double steptol = pr.math.pow(std::numeric_limits<double>::epsilon(), 2.0 / 3.0);
@@ -371,12 +382,16 @@ static int set_consistent(const Problem& pr, InitialState* st) {
         yerr = y_tmp;
     }
     if (!ok) return ST_INITIAL_CONDITION_DID_NOT_CONVERGE;
-    // InitOp::scatter_soln + zero dv (state.rs:155-160)
+    // InitOp::scatter_soln (op/init.rs:77-82) [+ zero dv for the state (state.rs:155-160)]
     for (int i = 0; i < n; ++i) {
-        if (is_alg[i]) { st->y[i] = y_tmp[i]; st->dy[i] = 0.0; }
+        if (is_alg[i]) { st->y[i] = y_tmp[i]; if (zero_dv) st->dy[i] = 0.0; }
         else st->dy[i] = y_tmp[i];
     }
     return ST_OK;
+}
+static int set_consistent(const Problem& pr, InitialState* st) {
+    return consistent_solve(pr, [&pr](const double* x, double t, double* out) { pr.rhs(x, t, out); },
+                            [&pr](const double* x, double t, double* J) { pr.jacobian(x, t, J); }, st->y, st->dy, nullptr, true);
 }
 
 // ode_solver/state.rs:1209-1277 (Hairer/Norsett/Wanner II.4.2)

@@ -119,6 +119,52 @@ struct EmuCall {
     }
 };
 
+// forward sensitivities: the on-chip BDF lane kernel instantiated for DsbWithSens<M> (dsb_inst.cu: SensLauncher)
+struct EmuSensCall {
+    const dsb_problem* pr; int free_running;
+    const double* params; int64_t B; const double* t_eval; int nt;
+    double* ys; double* sens; int64_t* stats; int32_t* status;
+    int rc;
+    template <class M> void operator()() {
+        constexpr int N = M::N, NP = M::NP;
+        if constexpr (N <= 16 && dsb_model_has_sens<M>::value && !M::HAS_MASS && dsb_model_nroots<M>::value == 0 &&
+                      !dsb_model_nout<M>::has_out && !dsb_model_has_reset<M>::value) {
+            typedef DsbWithSens<M> MS;
+            DsbProblemArgs pa;
+            int probes = 0;
+            std::vector<int32_t> color_full; std::vector<uint8_t> nz_full;
+            if (dsb_host::fill_problem_args(*pr, 1, nt, &pa, &probes, &color_full, &nz_full) != DSB_OK) { rc = DSB_BAD_ARG; return; }
+            pa.free_running = free_running;
+            dsb_host::build_tableau(DSB_METHOD_BDF, &pa.rk);
+            pa.quorum = DSB_DEFAULT_QUORUM;
+            std::vector<double> y0(N), dy0(N), h0(1), ysb((size_t)nt * N), ssb((size_t)nt * NP * N), fin_t(1), fin_h(1);
+            std::vector<int32_t> st(DSB_NSTATS), status1(1), fin_order(1), ridx(1), nc(1);
+            for (int64_t b = 0; b < B; ++b) {
+                DsbBatchBuffers bb;
+                bb.params = params + b * NP; bb.t_eval = t_eval; bb.y0 = y0.data(); bb.dy0 = dy0.data(); bb.h0 = h0.data();
+                bb.ys = ysb.data(); bb.ss = ssb.data(); bb.stats = st.data(); bb.status = status1.data();
+                bb.fin_t = fin_t.data(); bb.fin_h = fin_h.data(); bb.fin_order = fin_order.data();
+                bb.root_idx = ridx.data(); bb.ncols = nc.data();
+                for (auto& v : ysb) v = dsb_from_bits(~0ull);
+                for (auto& v : ssb) v = dsb_from_bits(~0ull);
+                for (auto& v : st) v = 0;
+                status1[0] = -1;
+                unsigned long long work_counter = 0;
+                blockDim.x = BdfLayout<MS>::THREADS;
+                dsb_init_kernel<M>(pa, bb, 1);
+                dsb_bdf_solve_dense_kernel<MS>(pa, bb, &work_counter);
+                for (size_t k = 0; k < ysb.size(); ++k) ys[b * ysb.size() + k] = ysb[k];
+                for (size_t k = 0; k < ssb.size(); ++k) sens[b * ssb.size() + k] = ssb[k];
+                for (int s = 0; s < DSB_NSTATS; ++s) stats[b * DSB_NSTATS + s] = st[s] + (s == DSB_STAT_RHS_JAC_MULS ? probes : 0);
+                status[b] = status1[0];
+            }
+            rc = DSB_OK;
+        } else {
+            rc = DSB_ERR;
+        }
+    }
+};
+
 }  // namespace
 
 // SmemBandLU (dsb_wband_bdf_kernel.cuh) on a dense column-major n x n matrix whose entries outside the band (kl, ku) are
@@ -161,6 +207,24 @@ int emu_solve(int model, int method, int kernel, double rtol, const double* atol
     if (!dsb_dispatch_model(model, dims)) return DSB_BAD_ARG;
     if (natol != 1 && natol != pr.n) return DSB_BAD_ARG;
     EmuCall call{&pr, method, kernel, free_running, params, B, t_eval, nt, ys, stats, status, fin, root_idx, ncols, DSB_ERR};
+    dsb_dispatch_model(model, call);
+    return call.rc;
+}
+
+// solve_dense_sensitivities (or, free_running, the step / interpolate / interpolate_sens loop) through the sensitivity
+// instantiation of the on-chip BDF lane kernel; ys [B][nt][n], sens [B][nt][np][n].  sens_natol = 0: not in the error test.
+int emu_solve_sens(int model, double rtol, const double* atol, int natol, double t0, double h0, const dsb_options* opt,
+                   double sens_rtol, const double* sens_atol, int sens_natol, const double* params, int64_t B,
+                   const double* t_eval, int nt, int free_running, double* ys, double* sens, int64_t* stats, int32_t* status) {
+    dsb_problem pr;
+    pr.model = model; pr.n = 0; pr.np = 0; pr.has_mass = 0;
+    pr.rtol = rtol; pr.atol.assign(atol, atol + natol); pr.t0 = t0; pr.h0 = h0; pr.use_coloring = 0;
+    if (opt) pr.opt = *opt; else dsb_options_default(&pr.opt);
+    EmuDims dims{&pr};
+    if (!dsb_dispatch_model(model, dims)) return DSB_BAD_ARG;
+    if (natol != 1 && natol != pr.n) return DSB_BAD_ARG;
+    pr.sens = 1; pr.sens_rtol = sens_rtol; pr.sens_atol.assign(sens_atol, sens_atol + sens_natol);
+    EmuSensCall call{&pr, free_running, params, B, t_eval, nt, ys, sens, stats, status, DSB_ERR};
     dsb_dispatch_model(model, call);
     return call.rc;
 }

@@ -1,0 +1,352 @@
+"""Forward sensitivities: `problem.bdf_sens::<LS>()` -- Bdf::sensitivity_solve
+(/root/reference/crates/diffsol/src/ode_solver/bdf.rs:934-989), the sensitivity terms of the error test (:844-858, 908-919),
+interpolate_sens (:1162-1215) and solve_dense_sensitivities (ode_solver/sensitivities.rs:205-262).
+
+CPU tests pin the ORACLE: every counter of THREE of the reference's sensitivity snapshots (bdf_test_nalgebra_exponential_
+decay_sens, bdf.rs:1812-1834; test_bdf_nalgebra_exponential_decay_algebraic_sens, :2118-2140; test_bdf_nalgebra_robertson_sens,
+:2248-2271 -- the last with 28 failed Newton solves), the reference's acceptance measures for the state (< 20) and
+the sensitivities (< 29, ode_solver/mod.rs:164-187) against the analytic solution, and the kernel SOURCE (host emulation of
+the DsbWithSens<M> instantiation of the on-chip BDF lane kernel) bit for bit against the oracle.
+GPU tests: the CUDA path through the C ABI (dsb_batch_solve_dense_sensitivities_host) bit-identical to the oracle.
+
+The reference's fourth BDF sensitivity snapshot (test_bdf_nalgebra_robertson_ode_sens, bdf.rs:2324-2345) is NOT reproduced
+(851 steps here, 840 there): that run is chaotic at the level of one unit in the last place (a relative change of 1e-15 in
+rtol moves it between 821 and 997 steps, while the same perturbation leaves the counters of the run WITHOUT sensitivities --
+which the oracle does reproduce -- unchanged), so it cannot pin a restatement whose third-party arithmetic (nalgebra's gemm
+/ LU evaluation order) is itself restated; test_robertson_ode_sens_snapshot_lies_within_the_one_ulp_scatter records that."""
+import json
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+with open(os.path.join(HERE, "golden", "reference_snapshots.json")) as f:
+    GOLD = json.load(f)
+
+# bdf.rs:1812-1834, in the order of oracle.S_NAMES
+EXP_DECAY_SENS_SNAPSHOT = [14, 1, 0, 0, 1, 12, 56, 1, 175, 0, 60, 123, 2]
+# bdf.rs:2324-2345
+ROBERTSON_ODE_SENS_SNAPSHOT = [364, 1, 18, 0, 226, 119, 840, 226, 5099, 18, 1357, 3859, 28]
+
+
+def exp_decay_sens_desc(oracle, powmode):
+    # exponential_decay_problem_sens (test_models/exponential_decay.rs:703-742): p = [0.1, 1], sens_rtol 1e-6, sens_atol 1e-6
+    return oracle.make_desc("exp_decay", sens=True, sens_rtol=1e-6, sens_atol=[1e-6, 1e-6], powmode=powmode)
+
+
+@pytest.mark.parametrize("powmode", [0, 1], ids=["libm_pow", "dsb_pow"])
+def test_exponential_decay_sens_snapshot(oracle, powmode):
+    t = np.arange(10.0)
+    rc, ys, sens, stats, fin = oracle.harness_sens(exp_decay_sens_desc(oracle, powmode), [0.1, 1.0], t)
+    assert rc == 0
+    assert list(stats.values())[:13] == EXP_DECAY_SENS_SNAPSHOT
+    # the solution table of the test problem: y = y0 e^{-k t}, dy/dk = -t y0 e^{-k t}, dy/dy0 = e^{-k t}
+    y = np.exp(-0.1 * t)
+    want = [np.stack([y, y], axis=1), np.stack([-t * y] * 2, axis=1), np.stack([y, y], axis=1)]
+    got = [ys, sens[:, 0, :], sens[:, 1, :]]
+    for k in range(len(t)):
+        for j, (g, w) in enumerate(zip(got, want)):
+            err = math.sqrt(np.mean(((g[k] - w[k]) / (np.abs(w[k]) * 1e-6 + 1e-6)) ** 2))
+            assert err < (20.0 if j == 0 else 29.0), (k, j, err)
+
+
+# test_bdf_nalgebra_exponential_decay_algebraic_sens (bdf.rs:2118-2140) and test_bdf_nalgebra_robertson_sens (bdf.rs:2248-2271):
+# DAEs, whose sensitivities are made consistent first (set_consistent_augmented, state.rs:167-238); the second runs with the
+# sensitivities outside the error test and max_nonlinear_solver_failures = 70, and 28 of its steps fail inside a Newton solve
+EXP_DECAY_ALGEBRAIC_SENS_SNAPSHOT = [24, 1, 0, 0, 8, 15, 45, 8, 115, 0, 66, 64, 3]
+ROBERTSON_DAE_SENS_SNAPSHOT = [92, 1, 26, 2, 4, 59, 319, 4, 1941, 28, 575, 1522, 31]
+
+
+@pytest.mark.parametrize("powmode", [0, 1], ids=["libm_pow", "dsb_pow"])
+def test_dae_sens_snapshots(oracle, powmode):
+    t = np.arange(10) / 10.0
+    d = oracle.make_desc("exp_decay_algebraic", sens=True, sens_rtol=1e-6, sens_atol=[1e-6] * 3, powmode=powmode)
+    rc, ys, sens, stats, fin = oracle.harness_sens(d, [0.1], t)
+    assert rc == 0 and list(stats.values())[:13] == EXP_DECAY_ALGEBRAIC_SENS_SNAPSHOT
+    y = np.exp(-0.1 * t)
+    for k in range(len(t)):                          # the problem's solution table: y = e^{-k t}, dy/dk = -t e^{-k t} in every row
+        for got, want, bound in ((ys[k], np.full(3, y[k]), 20.0), (sens[k, 0], np.full(3, -t[k] * y[k]), 29.0)):
+            assert math.sqrt(np.mean(((got - want) / (np.abs(want) * 1e-6 + 1e-6)) ** 2)) < bound
+    g = GOLD["robertson_dae_points"]
+    t, ystar = np.array(g["t"]), np.array(g["y"])
+    d = oracle.make_desc("robertson_dae", rtol=1e-4, atol=[1e-8, 1e-6, 1e-6], sens=True, powmode=powmode,
+                         options=dict(max_nonlinear_solver_failures=70))
+    rc, ys, sens, stats, fin = oracle.harness_sens(d, [0.04, 1e4, 3e7], t)
+    assert rc == 0 and list(stats.values())[:13] == ROBERTSON_DAE_SENS_SNAPSHOT
+    for k in range(len(t)):
+        w = np.abs(ystar[k]) * 1e-4 + np.array([1e-8, 1e-6, 1e-6])
+        assert math.sqrt(np.mean(((ys[k] - ystar[k]) / w) ** 2)) < 20.0
+    assert np.abs(sens.sum(axis=-1)).max() < 1e-6 * np.abs(sens).max()      # the constraint y1 + y2 + y3 = 1, differentiated
+
+
+def test_sensitivities_without_error_control_follow_the_plain_run(oracle):
+    """turn_off_sensitivities_error_control: the sensitivities are integrated beside the state but stay out of the error test.
+    The sensitivity residual's c is 0 until the first step-size update (op/bdf.rs:61, bdf.rs:551-553), so the step sequence
+    is the plain run's.  The first step's sensitivities are then solved with c = 0 -- i.e. held at their predictor -- and
+    nothing rejects that step, so an error of the size of that first step (1e-3 here) stays in d y / d k: the reference's
+    behaviour, restated as it is."""
+    t = np.arange(10.0)
+    rc0, ys0, stats0, fin0 = oracle.harness(oracle.make_desc("exp_decay"), [0.1, 1.0], t)
+    rc, ys, sens, stats, fin = oracle.harness_sens(oracle.make_desc("exp_decay", sens=True), [0.1, 1.0], t)
+    assert rc == 0 and rc0 == 0
+    assert stats["number_of_steps"] == stats0["number_of_steps"] and np.array_equal(ys, ys0)
+    assert 1e-4 < np.abs(sens[:, 0, 0] + t * np.exp(-0.1 * t)).max() < 2e-3
+
+
+def test_robertson_ode_sens_snapshot_lies_within_the_one_ulp_scatter(oracle):
+    g = GOLD["robertson_ode_points"]
+    t, ystar = np.array(g["t"]), np.array(g["y"])
+    rows = []
+    for eps in (0.0, 1e-15, 1e-14, 1e-13, 1e-12):
+        d = oracle.make_desc("robertson_ode", rtol=1e-4 * (1.0 + eps), atol=[1e-8, 1e-6, 1e-6], sens=True, sens_rtol=1e-6, sens_atol=[1e-6] * 3)
+        rc, ys, sens, stats, fin = oracle.harness_sens(d, [0.04, 1e4, 3e7], t)
+        assert rc == 0
+        rows.append(list(stats.values())[:13])
+        if eps == 0.0:                       # the state passes the reference's acceptance test (the table has no sensitivities)
+            for k in range(len(t)):
+                w = np.abs(ystar[k]) * 1e-4 + np.array([1e-8, 1e-6, 1e-6])
+                assert math.sqrt(np.mean(((ys[k] - ystar[k]) / w) ** 2)) < 20.0
+    rows = np.array(rows)
+    assert len({tuple(r) for r in rows}) >= 4                   # chaotic: (nearly) every perturbation gives another trajectory
+    for name, idx in (("setups", 0), ("steps", 6), ("error test failures", 7), ("newton iterations", 8), ("rhs calls", 10), ("jac_muls", 11)):
+        assert rows[:, idx].min() <= ROBERTSON_ODE_SENS_SNAPSHOT[idx] <= rows[:, idx].max(), name
+    # the same perturbations leave the run WITHOUT sensitivities (reproduced exactly, tests/test_oracle_golden.py) unchanged
+    plain = []
+    for eps in (0.0, 1e-15, 1e-13):
+        rc, ys, stats, fin = oracle.harness(oracle.make_desc("robertson_ode", rtol=1e-4 * (1.0 + eps), atol=[1e-8, 1e-6, 1e-6]), [0.04, 1e4, 3e7], t)
+        plain.append(tuple(stats.values()))
+    assert len(set(plain)) == 1
+
+
+# ---- the kernel source on the host (no GPU) ---------------------------------------------------------------------------------
+def exp_sweep(B):
+    from diffsol_b200 import sweeps
+    i = np.arange(B)
+    return np.stack([0.02 * 100.0 ** sweeps.uniform(i, 0), 0.5 + 1.5 * sweeps.uniform(i, 1)], axis=1)
+
+
+def robertson_sweep(B):
+    from diffsol_b200 import sweeps
+    return sweeps.robertson_sweep(np.arange(B))
+
+
+@pytest.mark.parametrize("sens_atol", [[1e-6, 1e-6], None], ids=["error_control", "no_error_control"])
+@pytest.mark.parametrize("free_running", [False, True], ids=["solve_dense", "step_loop"])
+def test_kernel_source_equals_oracle_exponential_decay(oracle, sens_atol, free_running):
+    from host_emu import emu
+    p = exp_sweep(48)
+    t = np.linspace(0.5, 10.0, 20)
+    d = oracle.make_desc("exp_decay", sens=True, sens_rtol=1e-6 if sens_atol else None, sens_atol=sens_atol, powmode=1)
+    if free_running:
+        res = [oracle.harness_sens(d, p[k], t) for k in range(len(p))]
+        assert all(r[0] == 0 for r in res)
+        ys, se = np.array([r[1] for r in res]), np.array([r[2] for r in res])
+        st = np.array([list(r[3].values())[:13] for r in res])
+    else:
+        ys, se, st, status = oracle.batch_solve_dense_sens(d, p, t)
+        assert (status == 0).all()
+        st = st[:, :13]
+    r = emu.solve_sens(0, 2, 2, p, t, sens_rtol=1e-6 if sens_atol else None, sens_atol=sens_atol, free_running=free_running)
+    assert (r["status"] == 0).all()
+    assert np.array_equal(r["stats"][:, :13], st)
+    assert np.array_equal(r["ys"], ys) and np.array_equal(r["sens"], se)
+
+
+def test_kernel_source_equals_oracle_robertson(oracle):
+    """Newton failures inside the sensitivity solves, Jacobian re-evaluations, orders up to 5 -- on the run that amplifies a
+    one-ulp difference into other counters, the kernel source and the oracle agree bit for bit."""
+    from host_emu import emu
+    p = robertson_sweep(6)
+    t = np.array([0.4, 4.0, 40.0, 400.0, 4000.0])
+    tol = dict(rtol=1e-4, atol=[1e-8, 1e-6, 1e-6])
+    ys, se, st, status = oracle.batch_solve_dense_sens(oracle.make_desc("robertson_ode", sens=True, sens_rtol=1e-6, sens_atol=[1e-6] * 3, powmode=1, **tol), p, t)
+    r = emu.solve_sens(3, 3, 3, p, t, sens_rtol=1e-6, sens_atol=[1e-6] * 3, **tol)
+    assert np.array_equal(r["status"], status) and (status == 0).all()
+    assert np.array_equal(r["stats"][:, :13], st[:, :13]) and st[:, 9].sum() > 0          # Newton failures were exercised
+    assert np.array_equal(r["ys"], ys) and np.array_equal(r["sens"], se)
+
+
+def test_sensitivity_arguments_are_checked_without_a_gpu():
+    """dsb_problem_set_sensitivities: argument errors come back as DSB_BAD_ARG with a message (no device needed)."""
+    import ctypes
+    from diffsol_b200 import capi
+    L = capi.lib()
+    h = ctypes.c_void_p()
+    capi.check(L.dsb_problem_new(capi.MODELS["exp_decay"], ctypes.byref(h)))
+    a = np.array([1e-6, 1e-6, 1e-6])
+    ptr = ctypes.c_void_p(a.ctypes.data)
+    try:
+        assert L.dsb_problem_set_sensitivities(h, 1, 1e-6, ptr, 3) != 0 and b"sens_atol" in L.dsb_last_error()
+        assert L.dsb_problem_set_sensitivities(h, 1, 1e-6, None, 2) != 0
+        assert L.dsb_problem_set_sensitivities(h, 1, -1.0, ptr, 2) != 0
+        assert L.dsb_problem_set_sensitivities(h, 1, 1e-6, ptr, 2) == 0
+        assert L.dsb_problem_set_sensitivities(h, 1, 0.0, None, 0) == 0
+        assert L.dsb_problem_set_sensitivities(h, 0, 0.0, None, 0) == 0
+        assert L.dsb_problem_set_sensitivities(None, 1, 0.0, None, 0) != 0
+    finally:
+        L.dsb_problem_free(h)
+
+
+# ---- the CUDA path -------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def dsb():
+    import diffsol_b200
+    from diffsol_b200 import capi
+    capi.require_device()
+    return diffsol_b200
+
+
+@pytest.mark.gpu
+def test_gpu_reference_snapshot_exponential_decay_sens(dsb):
+    """The reference's own test on the GPU: the step / interpolate / interpolate_sens loop over t = 0 .. 9 at p = [0.1, 1]
+    gives every counter of bdf.rs:1812-1834 (sparsity probes excluded as everywhere: no colouring here)."""
+    solver = dsb.OdeBuilder().rhs_implicit("exp_decay").p(np.array([[0.1, 1.0]] * 64)).sens_rtol(1e-6).sens_atol([1e-6, 1e-6]).build().bdf_sens()
+    t = np.arange(10.0)
+    ys, sens = solver.solve_dense_sensitivities(t, free_running=True)
+    assert (solver.status() == 0).all()
+    assert (solver.statistics_array()[:, :13] == np.array(EXP_DECAY_SENS_SNAPSHOT)).all()
+    y = np.exp(-0.1 * t)
+    assert np.abs(ys[:, :, 0] - y).max() < 1e-5 and np.abs(sens[:, :, 0, 0] + t * y).max() < 1e-5 and np.abs(sens[:, :, 1, 1] - y).max() < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sens_atol", [[1e-6, 1e-6], None], ids=["error_control", "no_error_control"])
+@pytest.mark.parametrize("free_running", [False, True], ids=["solve_dense", "step_loop"])
+def test_gpu_sensitivities_bit_exact_exponential_decay(dsb, oracle, sens_atol, free_running):
+    B = 4000 if not free_running else 300
+    p = exp_sweep(B)
+    t = np.linspace(0.5, 10.0, 20)
+    b = dsb.OdeBuilder().rhs_implicit("exp_decay").p(p)
+    b = b.sens_rtol(1e-6).sens_atol(sens_atol) if sens_atol else b.sensitivities()
+    solver = b.build().bdf_sens()
+    ys, sens = solver.solve_dense_sensitivities(t, free_running=free_running)
+    d = oracle.make_desc("exp_decay", sens=True, sens_rtol=1e-6 if sens_atol else None, sens_atol=sens_atol, powmode=1)
+    if free_running:
+        res = [oracle.harness_sens(d, p[k], t) for k in range(B)]
+        ys_o, se_o = np.array([r[1] for r in res]), np.array([r[2] for r in res])
+        st_o = np.array([list(r[3].values())[:13] for r in res])
+        status_o = np.array([r[0] for r in res])
+    else:
+        ys_o, se_o, st_o, status_o = oracle.batch_solve_dense_sens(d, p, t)
+        st_o = st_o[:, :13]
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(solver.statistics_array()[:, :13], st_o)
+    assert np.array_equal(ys, ys_o) and np.array_equal(sens, se_o)
+    # and the analytic sensitivities
+    ex = p[:, 1, None] * np.exp(-p[:, 0, None] * t[None, :])
+    if sens_atol:
+        assert np.abs(sens[:, :, 0, 0] + t[None, :] * ex).max() < 2e-4 and np.abs(sens[:, :, 1, 0] - ex / p[:, 1, None]).max() < 2e-4
+
+
+@pytest.mark.gpu
+def test_gpu_sensitivities_bit_exact_robertson(dsb, oracle):
+    """The stiff case: Newton failures inside sensitivity solves, hundreds of rejected steps, orders up to 5."""
+    B = 2000
+    p = robertson_sweep(B)
+    t = np.array([0.4, 4.0, 40.0, 400.0, 4000.0])
+    tol = dict(rtol=1e-4, atol=[1e-8, 1e-6, 1e-6])
+    solver = (dsb.OdeBuilder().rhs_implicit("robertson_ode").p(p).rtol(tol["rtol"]).atol(tol["atol"])
+              .sens_rtol(1e-6).sens_atol([1e-6] * 3).build().bdf_sens())
+    ys, sens = solver.solve_dense_sensitivities(t)
+    ys_o, se_o, st_o, status_o = oracle.batch_solve_dense_sens(
+        oracle.make_desc("robertson_ode", sens=True, sens_rtol=1e-6, sens_atol=[1e-6] * 3, powmode=1, **tol), p, t)
+    assert np.array_equal(solver.status(), status_o)
+    assert np.array_equal(solver.statistics_array()[:, :13], st_o[:, :13]) and st_o[:, 9].sum() > 0
+    assert np.array_equal(ys, ys_o, equal_nan=True) and np.array_equal(sens, se_o, equal_nan=True)
+    # mass conservation differentiated: sum_i d y_i / d p_q = 0 for every parameter
+    ok = status_o == 0
+    assert ok.mean() > 0.99
+    assert np.abs(sens[ok].sum(axis=-1)).max() < 1e-3 * max(1.0, np.abs(sens[ok]).max())
+
+
+@pytest.mark.gpu
+def test_gpu_sensitivities_against_finite_differences(dsb):
+    """Independent of the oracle: d y / d p from the sensitivity equations against central differences of two plain solves."""
+    B = 256
+    p = robertson_sweep(B)
+    t = np.array([0.4, 4.0, 40.0])
+    def plain(pp):
+        return dsb.OdeBuilder().rhs_implicit("robertson_ode").p(pp).rtol(1e-10).atol([1e-14, 1e-14, 1e-14]).build().bdf().solve_dense(t)
+    solver = (dsb.OdeBuilder().rhs_implicit("robertson_ode").p(p).rtol(1e-8).atol([1e-12] * 3).sens_rtol(1e-8).sens_atol([1e-12] * 3)
+              .build().bdf_sens())
+    ys, sens = solver.solve_dense_sensitivities(t)
+    assert (solver.status() == 0).all()
+    for q in range(3):
+        dp = np.zeros_like(p)
+        dp[:, q] = 1e-3 * p[:, q]
+        fd = (plain(p + dp) - plain(p - dp)) / (2.0 * dp[:, q])[:, None, None]
+        scale = np.abs(fd).max(axis=(1, 2), keepdims=True)
+        assert (np.abs(sens[:, :, q, :] - fd) / scale).max() < 5e-3, q     # the difference quotient of two 1e-10 solves is the limit
+
+
+@pytest.mark.gpu
+def test_gpu_sensitivity_errors(dsb):
+    from diffsol_b200 import capi
+    p = exp_sweep(8)
+    t = np.array([1.0, 2.0])
+    # an equation set without sens_mul / init_sens
+    pv = np.array([[1.0]] * 4)
+    with pytest.raises(capi.DiffsolB200Error, match="sensitivities"):
+        dsb.OdeBuilder().rhs_implicit("van_der_pol").p(pv).sensitivities().build().bdf_sens().solve_dense_sensitivities(t)
+    # SDIRK with sensitivities is not built
+    prob = dsb.OdeBuilder().rhs_implicit("exp_decay").p(p).sensitivities().build()
+    with pytest.raises(capi.DiffsolB200Error, match="sensitivities"):
+        prob.tr_bdf2().solve_dense_sensitivities(t)
+    # a problem with sensitivities goes through the sensitivity entry point, one without cannot
+    with pytest.raises(capi.DiffsolB200Error, match="sensitivities"):
+        prob.bdf().solve_dense(t)
+    plain = dsb.OdeBuilder().rhs_implicit("exp_decay").p(p).build()
+    with pytest.raises(ValueError):
+        plain.bdf_sens()
+    with pytest.raises(capi.DiffsolB200Error, match="sensitivities"):
+        plain.bdf().solve_dense_sensitivities(t)
+
+
+SENS_FUNCTOR = r"""
+struct LogisticSens {
+    static constexpr int N = 1, NP = 2;
+    static constexpr bool HAS_MASS = false;
+    static constexpr bool HAS_SENS = true;
+    // x' = r x (1 - x / K), p = [r, K], x(0) = 0.1
+    DSB_HD static void rhs(const double* x, const double* p, double, double* y) { y[0] = p[0] * x[0] * (1.0 - x[0] / p[1]); }
+    DSB_HD static void jac_mul(const double* x, const double* p, double, const double* v, double* y) { y[0] = p[0] * (1.0 - 2.0 * x[0] / p[1]) * v[0]; }
+    DSB_HD static void mass(const double* x, const double*, double, double beta, double* y) { y[0] = x[0] + beta * y[0]; }
+    DSB_HD static void init(const double*, double, double* y) { y[0] = 0.1; }
+    DSB_HD static void sens_mul(const double* x, const double* p, double, const double* v, double* y) {
+        y[0] = x[0] * (1.0 - x[0] / p[1]) * v[0] + p[0] * x[0] * x[0] / (p[1] * p[1]) * v[1];
+    }
+    DSB_HD static void init_sens(const double*, double, const double*, double* y) { y[0] = 0.0; }
+};
+"""
+
+
+@pytest.mark.gpu
+def test_gpu_sensitivities_of_a_user_functor(dsb, oracle):
+    """A closure-style functor with sens_mul / init_sens (builder.rs rhs_sens_implicit / init_sens) compiled at run time:
+    bit-identical to the oracle (which compiled the same text), and the analytic d x / d r, d x / d K of logistic growth."""
+    from diffsol_b200 import sweeps
+    B = 1500
+    i = np.arange(B)
+    p = np.stack([0.5 + 2.0 * sweeps.uniform(i, 0), 0.8 + 0.7 * sweeps.uniform(i, 1)], axis=1)
+    t = np.linspace(0.25, 4.0, 16)
+    solver = (dsb.OdeBuilder().rhs_implicit_source(SENS_FUNCTOR, kind="functor", struct="LogisticSens").p(p).rtol(1e-8).atol(1e-10)
+              .sens_rtol(1e-8).sens_atol(1e-10).build().bdf_sens())
+    ys, sens = solver.solve_dense_sensitivities(t)
+    name = oracle.load_user_model(SENS_FUNCTOR, kind="functor", struct="LogisticSens")
+    ys_o, se_o, st_o, status_o = oracle.batch_solve_dense_sens(
+        oracle.make_desc(name, rtol=1e-8, atol=1e-10, sens=True, sens_rtol=1e-8, sens_atol=1e-10, powmode=1), p, t)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(solver.statistics_array()[:, :13], st_o[:, :13])
+    assert np.array_equal(ys, ys_o) and np.array_equal(sens, se_o)
+    r, K, x0 = p[:, 0, None], p[:, 1, None], 0.1
+    A = (K - x0) / x0
+    e = np.exp(-r * t[None, :])
+    x = K / (1.0 + A * e)
+    dx_dr = K * A * t[None, :] * e / (1.0 + A * e) ** 2
+    dx_dK = 1.0 / (1.0 + A * e) - K * (e / x0) / (1.0 + A * e) ** 2
+    assert np.abs(ys[:, :, 0] - x).max() < 1e-6
+    assert np.abs(sens[:, :, 0, 0] - dx_dr).max() < 1e-5 and np.abs(sens[:, :, 1, 0] - dx_dK).max() < 1e-5
