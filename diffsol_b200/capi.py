@@ -105,6 +105,10 @@ SIGNATURES = {
     "dsb_batch_step_and_interpolate": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "dsb_batch_step_and_interpolate_host": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp]),
     "dsb_batch_solve_dense_sensitivities": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "dsb_batch_solve_count": (ctypes.c_int, [_vp, _i32, _dbl, _vp]),
+    "dsb_batch_solve_offsets": (ctypes.c_int, [_vp, _vp]),
+    "dsb_batch_solve_write": (ctypes.c_int, [_vp, _i32, _dbl, _vp, _vp, _vp]),
+    "dsb_batch_solve_write_host": (ctypes.c_int, [_vp, _i32, _dbl, _vp, _vp]),
     "dsb_batch_step_and_interpolate_sensitivities": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp]),
     "dsb_batch_solve_dense_sensitivities_host": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "dsb_batch_step_and_interpolate_sensitivities_host": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),

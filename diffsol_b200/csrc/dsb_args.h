@@ -66,6 +66,7 @@ struct DsbProblemArgs {
     DsbSdirkTableau rk;
     // forward sensitivities (problem.bdf_sens(), ode_solver/problem.rs:819-830; builder.rs:1682-1716): sens != 0 integrates
     // one sensitivity vector per parameter; sens_error_control puts them into the error test with sens_rtol / sens_atol
+    int32_t ragged, reserved2;     // solve(final_time) form (DsbRagged<M> kernels): 1 = count the columns, 2 = write them
     int32_t sens, sens_error_control;
     double sens_rtol;
     double sens_atol[DSB_MAX_STATES];
@@ -88,4 +89,8 @@ struct DsbBatchBuffers {
     int32_t* root_idx;       // [B]   index of the root function that stopped the instance, -1: none (OdeSolverStopReason::RootFound)
     int32_t* ncols;          // [B]   solve_dense columns written (nt unless a root or an error stopped the instance)
     double* ss;              // [nt][np][n][B]  solve_dense_sensitivities output (NULL without sensitivities)
+    // solve(final_time), writing pass: instance b's column k at rag_ts[rag_off[b] + k], rag_ys[(rag_off[b] + k) * nout + i]
+    const int64_t* rag_off;  // [B + 1]
+    double* rag_ts;
+    double* rag_ys;
 };

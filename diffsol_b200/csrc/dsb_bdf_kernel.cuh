@@ -187,6 +187,10 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
     };
     // one column of the solve_dense result (dense_write_out, method.rs:822-848): the state, or -- for equations with an
     // output function (OdeEquations::out) -- out(y(tq), tq)
+    // In the solve(final_time) form (DsbRagged<M>; write_out, method.rs:965-1000) the column goes, with its time, to the
+    // instance's own run of the ragged result (writing pass only).
+    constexpr bool RAG = dsb_model_ragged_on<M>::value;
+    static_assert(!RAG || !dsb_model_has_reset<M>::value, "solve(final_time) form: no reset functions");
     auto write_column = [&](int column, double tq, const double (&yo)[N]) {
         if constexpr (dsb_model_nout<M>::has_out) {
             constexpr int NOUT = dsb_model_nout<M>::value;
@@ -194,12 +198,30 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #pragma unroll
             for (int j = 0; j < NP; ++j) pl_[j] = SP(j);
             M::out(yo, pl_, tq, o);
+            if constexpr (RAG) {
+                if (pa.ragged == 2) {
+                    const int64_t at = bb.rag_off[inst] + column;
+                    bb.rag_ts[at] = tq;
+#pragma unroll
+                    for (int k = 0; k < NOUT; ++k) bb.rag_ys[at * NOUT + k] = o[k];
+                }
+            } else {
 #pragma unroll
             for (int k = 0; k < NOUT; ++k) bb.ys[((int64_t)column * NOUT + k) * B + inst] = o[k];
+            }
         } else {
             (void)tq;
+            if constexpr (RAG) {
+                if (pa.ragged == 2) {
+                    const int64_t at = bb.rag_off[inst] + column;
+                    bb.rag_ts[at] = tq;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) bb.rag_ys[at * N + i] = yo[i];
+                }
+            } else {
 #pragma unroll
             for (int i = 0; i < N; ++i) bb.ys[((int64_t)column * N + i) * B + inst] = yo[i];
+            }
         }
     };
     // bdf.rs:694-731.  0 = nothing, 1 = TstopReached, 2 = step size must be clipped (rescale_factor set), < 0 = -status
@@ -681,6 +703,15 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 
         // ================= TSTOP: set_stop_time (first) / handle_tstop after an accepted step =============
         if (__any_sync(0xffffffffu, state == L_TSTOP) && state == L_TSTOP) {
+            if constexpr (RAG) {                    // solve(final_time): the initial column, before the stop time is set (method.rs:900-901)
+                if (first) {
+                    double y0c[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) y0c[i] = SY(i);
+                    write_column(0, t, y0c);
+                    col = 1;
+                }
+            }
             bool stopped_on_root = false;
             bool reset_now = false;             // a reset was applied at a root: set_stop_time again, then L_REINIT
             if constexpr (NR > 0) {
@@ -705,7 +736,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                         // (bdf.rs:1228-1262), then -- without a reset function -- the state at the root in the next column
                         // (method.rs:493-503) and the end of the solve
                         double yo[N];
-                        while (!free_running && col < nt && bb.t_eval[col] <= t_root) {
+                        while (!RAG && !free_running && col < nt && bb.t_eval[col] <= t_root) {
                             interpolate(bb.t_eval[col], yo);
                             write_column(col, bb.t_eval[col], yo);
                             ++col;
@@ -730,7 +761,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                             }
                         }
                         if (ended) {
-                            if (col < nt) {
+                            if (RAG || col < nt) {
                                 write_column(col, t_root, yo);
                                 ++col;
                             }
@@ -775,7 +806,14 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
         // ================= OUTPUT: dense output at every t_eval passed (method.rs:761-764, 822-848) =======
         if (__any_sync(0xffffffffu, state == L_OUTPUT) && state == L_OUTPUT) {
             int status = DSB_STATUS_OK;
-            while (col < nt) {
+            if constexpr (RAG) {                    // solve(final_time): (state.t, state.y) after every step (method.rs:907-921)
+                double yc[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) yc[i] = SY(i);
+                write_column(col, t, yc);
+                ++col;
+            }
+            while (!RAG && col < nt) {
                 const double tq = bb.t_eval[col];
                 if (free_running ? (dsb_abs(t) < dsb_abs(tq)) : !(tq <= t)) break;
                 // interpolate (bdf.rs:767-782, 1080-1106)

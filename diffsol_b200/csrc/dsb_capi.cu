@@ -52,6 +52,8 @@ struct dsb_batch {
     double* t_eval = nullptr; int t_eval_cap = 0;
     double* ys_own = nullptr; size_t ys_own_bytes = 0;       // used by the *_host entry point
     double* sens_own = nullptr; size_t sens_own_bytes = 0;   // batch-major sensitivities of the *_sensitivities_host entry points
+    int64_t* rag_off = nullptr;                              // [B + 1] column offsets of the last dsb_batch_solve_count
+    int64_t rag_total = -1; int32_t rag_method = -1; double rag_final_time = 0.0;
     void* stage = nullptr; size_t stage_bytes = 0;           // instance-major staging for host copies
     cudaEvent_t ev0 = nullptr, ev_mid = nullptr, ev1 = nullptr;
     int last_launches = 0;
@@ -376,7 +378,7 @@ int dsb_batch_free(dsb_batch* b) {
     for (cudaEvent_t ev : b->chunk_done) cudaEventDestroy(ev);
     cudaFree(b->params); cudaFree(b->y0); cudaFree(b->dy0); cudaFree(b->h0);
     cudaFree(b->fin_t); cudaFree(b->fin_h); cudaFree(b->fin_order); cudaFree(b->root_idx); cudaFree(b->ncols);
-    cudaFree(b->stats); cudaFree(b->status); cudaFree(b->work_counter); cudaFree(b->coop.ws_mem); cudaFree(b->coop.atol_dev); cudaFree(b->coop.color_dev); cudaFree(b->coop.wb_mem); cudaFree(b->coop.ys_im_own); cudaFree(b->t_eval); cudaFree(b->ys_own); cudaFree(b->sens_own); cudaFree(b->stage);
+    cudaFree(b->stats); cudaFree(b->status); cudaFree(b->work_counter); cudaFree(b->coop.ws_mem); cudaFree(b->coop.atol_dev); cudaFree(b->coop.color_dev); cudaFree(b->coop.wb_mem); cudaFree(b->coop.ys_im_own); cudaFree(b->t_eval); cudaFree(b->ys_own); cudaFree(b->sens_own); cudaFree(b->rag_off); cudaFree(b->stage);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->ev_mid) cudaEventDestroy(b->ev_mid);
@@ -412,8 +414,15 @@ int dsb_batch_set_params_host(dsb_batch* b, const double* params, int64_t nbatch
 
 // ys_im: instance-major buffer offered to kernels that write that layout (NULL: they use their own and the result is
 // re-laid out into ys_dev); *wrote_im (may be NULL) reports that the result is in ys_im and ys_dev was NOT written
+// what the sensitivity and solve(final_time) entry points add to a solve
+struct SolveExtras {
+    double* sens_dev = nullptr;                     // solve_dense_sensitivities: [nt][np][n][B]
+    int ragged = 0;                                 // solve(final_time): 1 = counting pass, 2 = writing pass
+    const int64_t* rag_off = nullptr; double* rag_ts = nullptr; double* rag_ys = nullptr;
+};
 static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_t nt, double* ys_dev, void* stream_,
-                      int free_running, double* ys_im = nullptr, int* wrote_im = nullptr, double* sens_dev = nullptr) {
+                      int free_running, double* ys_im = nullptr, int* wrote_im = nullptr, const SolveExtras* ex = nullptr) {
+    double* const sens_dev = ex ? ex->sens_dev : nullptr;
     if (!b || !t_eval || nt < 1 || !ys_dev) return fail(DSB_BAD_ARG, "bad argument to dsb_batch_solve_dense");
     if (sens_dev && !b->prob.sens) return fail(DSB_BAD_ARG, "the problem has no sensitivities enabled (dsb_problem_set_sensitivities)");
     if (!sens_dev && b->prob.sens) return fail(DSB_BAD_ARG, "a problem with sensitivities is solved through dsb_batch_solve_dense_sensitivities");
@@ -450,6 +459,8 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     bb.fin_t = b->fin_t; bb.fin_h = b->fin_h; bb.fin_order = b->fin_order;
     bb.root_idx = b->root_idx; bb.ncols = b->ncols;
     bb.ss = sens_dev;
+    bb.rag_off = ex ? ex->rag_off : nullptr; bb.rag_ts = ex ? ex->rag_ts : nullptr; bb.rag_ys = ex ? ex->rag_ys : nullptr;
+    pa.ragged = ex ? ex->ragged : 0;
     if (sens_dev) DSB_CUDA(cudaMemsetAsync(sens_dev, 0xFF, (size_t)nt * b->prob.np * b->prob.n * b->B * 8, stream));
     // kernels without root finding leave these alone: no root, every column
     DSB_CUDA(cudaMemsetAsync(b->root_idx, 0xFF, (size_t)b->B * 4, stream));
@@ -469,6 +480,8 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     if (wrote_im) *wrote_im = 0;
     const dsb_launch_fn launch = pm ? pm->launch : g_launch_table[b->prob.model];
     cudaError_t lerr = launch(&pa, &bb, method, stream, b->ev_mid, b->work_counter, &b->coop, atol_full.data(), &b->last_launches);
+    if (lerr == cudaErrorNotSupported && pa.ragged)
+        return fail(DSB_ERR, "solve(final_time) is built for the thread-per-instance kernels: n <= 16, no reset function, no sensitivities");
     if (lerr == cudaErrorNotSupported && b->prob.sens)
         return fail(DSB_ERR, "forward sensitivities are built for BDF on equation sets with sens_mul / init_sens, no mass matrix, no root / output / reset function and n <= 16");
     if (lerr == cudaErrorNotSupported) return fail(DSB_ERR, "this execution mode is not available for this equation set and method (thread per instance: n <= 16; banded thread per instance: component-wise equations with a declared band, n > 16; banded warp per instance: the same, BDF, no reset function; block per instance: n <= 512)");
@@ -501,12 +514,72 @@ int dsb_batch_step_and_interpolate(dsb_batch* b, int32_t method, const double* t
 int dsb_batch_solve_dense_sensitivities(dsb_batch* b, int32_t method, const double* t_eval, int32_t nt, double* ys_dev, double* sens_dev,
                                         void* stream) {
     if (!sens_dev) return fail(DSB_BAD_ARG, "sens_dev is NULL");
-    return solve_impl(b, method, t_eval, nt, ys_dev, stream, 0, nullptr, nullptr, sens_dev);
+    SolveExtras ex; ex.sens_dev = sens_dev;
+    return solve_impl(b, method, t_eval, nt, ys_dev, stream, 0, nullptr, nullptr, &ex);
 }
 int dsb_batch_step_and_interpolate_sensitivities(dsb_batch* b, int32_t method, const double* t_points, int32_t npts, double* ys_dev,
                                                  double* sens_dev, void* stream) {
     if (!sens_dev) return fail(DSB_BAD_ARG, "sens_dev is NULL");
-    return solve_impl(b, method, t_points, npts, ys_dev, stream, 1, nullptr, nullptr, sens_dev);
+    SolveExtras ex; ex.sens_dev = sens_dev;
+    return solve_impl(b, method, t_points, npts, ys_dev, stream, 1, nullptr, nullptr, &ex);
+}
+
+// ---- OdeSolverMethod::solve(final_time): ragged results in two passes -------------------------------------------------------
+static int ragged_pass(dsb_batch* b, int32_t method, double final_time, const SolveExtras& ex, cudaStream_t stream) {
+    const size_t dummy = (size_t)b->prob.nout * b->B * 8;           // the dense result block of a one-point solve: unused
+    if (b->ys_own_bytes < dummy) {
+        cudaFree(b->ys_own); b->ys_own = nullptr; b->ys_own_bytes = 0;
+        DSB_CUDA(cudaMalloc((void**)&b->ys_own, dummy));
+        b->ys_own_bytes = dummy;
+    }
+    return solve_impl(b, method, &final_time, 1, b->ys_own, stream, 0, nullptr, nullptr, &ex);
+}
+int dsb_batch_solve_count(dsb_batch* b, int32_t method, double final_time, int64_t* total_columns) {
+    if (!b || !total_columns) return fail(DSB_BAD_ARG, "NULL argument");
+    if (b->prob.sens) return fail(DSB_BAD_ARG, "solve(final_time) is not built for problems with sensitivities");
+    DSB_CUDA(cudaSetDevice(b->device));
+    SolveExtras ex; ex.ragged = 1;
+    int rc = ragged_pass(b, method, final_time, ex, 0);
+    if (rc != DSB_OK) return rc;
+    std::vector<int32_t> nc((size_t)b->B);
+    DSB_CUDA(cudaMemcpy(nc.data(), b->ncols, (size_t)b->B * 4, cudaMemcpyDeviceToHost));
+    std::vector<int64_t> off((size_t)b->B + 1);
+    off[0] = 0;
+    for (int64_t k = 0; k < b->B; ++k) off[(size_t)k + 1] = off[(size_t)k] + nc[(size_t)k];
+    if (!b->rag_off) DSB_CUDA(cudaMalloc((void**)&b->rag_off, ((size_t)b->B + 1) * 8));
+    DSB_CUDA(cudaMemcpy(b->rag_off, off.data(), ((size_t)b->B + 1) * 8, cudaMemcpyHostToDevice));
+    b->rag_total = off[(size_t)b->B]; b->rag_method = method; b->rag_final_time = final_time;
+    *total_columns = b->rag_total;
+    return DSB_OK;
+}
+int dsb_batch_solve_offsets(dsb_batch* b, int64_t* offsets_host) {
+    if (!b || !offsets_host) return fail(DSB_BAD_ARG, "NULL argument");
+    if (b->rag_total < 0) return fail(DSB_BAD_ARG, "dsb_batch_solve_count has not run on this batch");
+    DSB_CUDA(cudaSetDevice(b->device));
+    DSB_CUDA(cudaMemcpy(offsets_host, b->rag_off, ((size_t)b->B + 1) * 8, cudaMemcpyDeviceToHost));
+    return DSB_OK;
+}
+int dsb_batch_solve_write(dsb_batch* b, int32_t method, double final_time, double* ts_dev, double* ys_dev, void* stream) {
+    if (!b || !ts_dev || !ys_dev) return fail(DSB_BAD_ARG, "NULL argument");
+    if (b->rag_total < 0 || b->rag_method != method || b->rag_final_time != final_time)
+        return fail(DSB_BAD_ARG, "dsb_batch_solve_write follows a dsb_batch_solve_count with the same method and final time");
+    DSB_CUDA(cudaSetDevice(b->device));
+    SolveExtras ex; ex.ragged = 2; ex.rag_off = b->rag_off; ex.rag_ts = ts_dev; ex.rag_ys = ys_dev;
+    return ragged_pass(b, method, final_time, ex, (cudaStream_t)stream);
+}
+int dsb_batch_solve_write_host(dsb_batch* b, int32_t method, double final_time, double* ts_host, double* ys_host) {
+    if (!b || !ts_host || !ys_host) return fail(DSB_BAD_ARG, "NULL argument");
+    if (b->rag_total < 0) return fail(DSB_BAD_ARG, "dsb_batch_solve_count has not run on this batch");
+    DSB_CUDA(cudaSetDevice(b->device));
+    const size_t tb = (size_t)(b->rag_total > 0 ? b->rag_total : 1) * 8, yb = tb * (size_t)b->prob.nout;
+    if (ensure_stage(b, tb + yb) != DSB_OK) return DSB_ERR;
+    double* ts_dev = (double*)b->stage;
+    double* ys_dev = (double*)((char*)b->stage + tb);
+    int rc = dsb_batch_solve_write(b, method, final_time, ts_dev, ys_dev, nullptr);
+    if (rc != DSB_OK) return rc;
+    DSB_CUDA(cudaMemcpy(ts_host, ts_dev, (size_t)b->rag_total * 8, cudaMemcpyDeviceToHost));
+    DSB_CUDA(cudaMemcpy(ys_host, ys_dev, (size_t)b->rag_total * 8 * (size_t)b->prob.nout, cudaMemcpyDeviceToHost));
+    return DSB_OK;
 }
 
 int dsb_batch_set_execution(dsb_batch* b, int32_t mode) {
@@ -759,7 +832,8 @@ static int solve_sens_host_impl(dsb_batch* b, int32_t method, const double* para
     DSB_CUDA(cudaMemcpyAsync(b->stage, params_host, (size_t)b->B * nparams * 8, cudaMemcpyHostToDevice, stream));
     int rc = dsb_batch_set_params_device(b, (const double*)b->stage, b->B, nparams, stream);
     if (rc != DSB_OK) return rc;
-    rc = solve_impl(b, method, t_eval, nt, b->ys_own, stream, free_running, nullptr, nullptr, b->sens_own);
+    SolveExtras ex; ex.sens_dev = b->sens_own;
+    rc = solve_impl(b, method, t_eval, nt, b->ys_own, stream, free_running, nullptr, nullptr, &ex);
     if (rc != DSB_OK) return rc;
     dim3 block(32, 8);
     {

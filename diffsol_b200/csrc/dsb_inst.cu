@@ -461,6 +461,46 @@ template <class M> struct SensLauncher<M, true> {
     }
 };
 
+// solve(final_time) form (OdeSolverMethod::solve): the on-chip lane kernels instantiated for DsbRagged<M>, equations
+// without a reset function
+template <class M, bool LANE> struct RaggedCapable : std::false_type {};
+template <class M> struct RaggedCapable<M, true> : std::bool_constant<!dsb_model_has_reset<M>::value> {};
+constexpr bool kRaggedCapable = RaggedCapable<InstModel, kLaneCapable>::value;
+template <class M, bool OK> struct RaggedLauncher {
+    static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, int, cudaStream_t, cudaEvent_t, unsigned long long*, int*) {
+        return cudaErrorNotSupported;
+    }
+};
+template <class M> struct RaggedLauncher<M, true> {
+    static cudaError_t run(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method, cudaStream_t stream, cudaEvent_t mid,
+                           unsigned long long* work_counter, int* launches) {
+        typedef DsbRagged<M> MR;
+        const bool bdf = method == DSB_METHOD_BDF;
+        const int threads = bdf ? BdfLayout<MR>::THREADS : SdirkLayout<MR>::THREADS;
+        const size_t smem = (size_t)(bdf ? BdfLayout<MR>::WORDS : SdirkLayout<MR>::WORDS) * threads * sizeof(double);
+        const void* kernel = bdf ? (const void*)dsb_bdf_solve_dense_kernel<MR> : (const void*)dsb_sdirk_solve_dense_kernel<MR>;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        e = cudaMemsetAsync(work_counter, 0, 32 * sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return e;
+        const unsigned init_blocks = (unsigned)((pa->nbatch + DSB_LANE_THREADS - 1) / DSB_LANE_THREADS);
+        dsb_init_kernel<M><<<init_blocks, DSB_LANE_THREADS, 0, stream>>>(*pa, *bb, bdf ? 1 : pa->rk.order);
+        if (mid) cudaEventRecord(mid, stream);
+        const unsigned blocks = (unsigned)((pa->nbatch + threads - 1) / threads);
+        const unsigned grid = blocks < (unsigned)(sms * per_sm) ? blocks : (unsigned)(sms * per_sm);
+        if (bdf) dsb_bdf_solve_dense_kernel<MR><<<grid, threads, smem, stream>>>(*pa, *bb, work_counter);
+        else dsb_sdirk_solve_dense_kernel<MR><<<grid, threads, smem, stream>>>(*pa, *bb, work_counter);
+        *launches += 2;
+        return cudaGetLastError();
+    }
+};
+
 #if defined(DSB_USER_MODEL_SOURCE)
 extern "C"
 #endif
@@ -468,6 +508,10 @@ cudaError_t DSB_LAUNCH_SYMBOL(const DsbProblemArgs* pa, const DsbBatchBuffers* b
                                                  cudaStream_t stream, cudaEvent_t mid, unsigned long long* work_counter,
                                                  DsbCoopState* coop, const double* atol_host, int* launches) {
     coop->ys_im_used = nullptr;
+    if (pa->ragged) {
+        if (pa->sens) return cudaErrorNotSupported;
+        return RaggedLauncher<InstModel, kRaggedCapable>::run(pa, bb, method, stream, mid, work_counter, launches);
+    }
     if (pa->sens) {
         if (method != DSB_METHOD_BDF || !bb->ss) return cudaErrorNotSupported;
         return SensLauncher<InstModel, kSensCapable>::run(pa, bb, stream, mid, work_counter, launches);

@@ -55,6 +55,12 @@ template <class M> struct dsb_model_has_sens<M, decltype((void)M::HAS_SENS)> { s
 template <class M, class = void> struct dsb_model_sens_on { static constexpr bool value = false; };
 template <class M> struct dsb_model_sens_on<M, decltype((void)M::SENS_ON)> { static constexpr bool value = M::SENS_ON; };
 template <class M> struct DsbWithSens : M { static constexpr bool SENS_ON = true; };
+// DsbRagged<M>: the kernels in `solve(final_time)` form (OdeSolverMethod::solve, ode_solver/method.rs:227-258, 881-961) -- one
+// result column per internal step, per instance as many as it takes, written at an offset the caller got from a counting
+// pass.  A separate instantiation, so that the solve_dense kernels carry none of it.
+template <class M, class = void> struct dsb_model_ragged_on { static constexpr bool value = false; };
+template <class M> struct dsb_model_ragged_on<M, decltype((void)M::RAGGED_ON)> { static constexpr bool value = M::RAGGED_ON; };
+template <class M> struct DsbRagged : M { static constexpr bool RAGGED_ON = true; };
 
 struct dsb_log_row { double invc, logc_hi, logc_lo; };
 struct dsb_exp_row { double hi, lo; };

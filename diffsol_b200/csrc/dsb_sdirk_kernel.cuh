@@ -112,6 +112,10 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
     for (int r = 0; r < (NR > 0 ? NR : 1); ++r) rf.g0[r] = 0.0;
     // one column of the solve_dense result (dense_write_out, method.rs:822-848): the state, or -- for equations with an
     // output function (OdeEquations::out) -- out(y(tq), tq)
+    // In the solve(final_time) form (DsbRagged<M>; write_out, method.rs:965-1000) the column goes, with its time, to the
+    // instance's own run of the ragged result (writing pass only).
+    constexpr bool RAG = dsb_model_ragged_on<M>::value;
+    static_assert(!RAG || !dsb_model_has_reset<M>::value, "solve(final_time) form: no reset functions");
     auto write_column = [&](int column, double tq, const double (&yo)[N]) {
         if constexpr (dsb_model_nout<M>::has_out) {
             constexpr int NOUT = dsb_model_nout<M>::value;
@@ -119,12 +123,30 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
 #pragma unroll
             for (int j = 0; j < NP; ++j) pl_[j] = SP(j);
             M::out(yo, pl_, tq, o);
+            if constexpr (RAG) {
+                if (pa.ragged == 2) {
+                    const int64_t at = bb.rag_off[inst] + column;
+                    bb.rag_ts[at] = tq;
+#pragma unroll
+                    for (int k = 0; k < NOUT; ++k) bb.rag_ys[at * NOUT + k] = o[k];
+                }
+            } else {
 #pragma unroll
             for (int k = 0; k < NOUT; ++k) bb.ys[((int64_t)column * NOUT + k) * B + inst] = o[k];
+            }
         } else {
             (void)tq;
+            if constexpr (RAG) {
+                if (pa.ragged == 2) {
+                    const int64_t at = bb.rag_off[inst] + column;
+                    bb.rag_ts[at] = tq;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) bb.rag_ys[at * N + i] = yo[i];
+                }
+            } else {
 #pragma unroll
             for (int i = 0; i < N; ++i) bb.ys[((int64_t)column * N + i) * B + inst] = yo[i];
+            }
         }
     };
     // interpolate_inplace (runge_kutta.rs:1080-1127; :962-981 beta dense output, :1004-1024 Hermite) on [old_t, t]
@@ -185,7 +207,8 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
             bb.fin_t[inst] = t; bb.fin_h[inst] = h_state; bb.fin_order[inst] = pa.rk.order;
 #pragma unroll
             for (int k = 0; k < DSB_NSTATS; ++k) bb.stats[(int64_t)k * B + inst] = st.v[k];
-            if (NR > 0) { bb.ncols[inst] = col; bb.root_idx[inst] = root_found; }
+            if (NR > 0 || RAG) bb.ncols[inst] = col;
+            if (NR > 0) bb.root_idx[inst] = root_found;
             state = R_FETCH;
         }
         // ================= FETCH: next instance; Rk::_new + Sdirk::_new =========================================
@@ -401,6 +424,15 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
 
         // ================= TSTOP: set_stop_time (first) / handle_tstop after an accepted step ===================
         if (__any_sync(0xffffffffu, state == R_TSTOP) && state == R_TSTOP) {
+            if constexpr (RAG) {                    // solve(final_time): the initial column, before the stop time is set (method.rs:900-901)
+                if (first) {
+                    double y0c[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) y0c[i] = SY(i);
+                    write_column(0, t, y0c);
+                    col = 1;
+                }
+            }
             int r = 0;
             int next = first ? R_STEP : R_OUTPUT;
             bool stopped_on_root = false;
@@ -424,7 +456,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                         // fn solve_dense, RootFound (method.rs:774-805): the points up to the root, state_mut_back(t_root)
                         // (runge_kutta.rs:396-434), then the state at the root in the next column (method.rs:493-503)
                         double yo[N];
-                        while (!free_running && col < nt && bb.t_eval[col] <= t_root) {
+                        while (!RAG && !free_running && col < nt && bb.t_eval[col] <= t_root) {
                             interpolate(bb.t_eval[col], yo);
                             write_column(col, bb.t_eval[col], yo);
                             ++col;
@@ -465,7 +497,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                             }
                         }
                         if (ended) {
-                            if (col < nt) {
+                            if (RAG || col < nt) {
                                 write_column(col, t_root, yo);
                                 ++col;
                             }
@@ -495,7 +527,14 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
         // ================= OUTPUT: dense output (method.rs:761-764, 822-848; runge_kutta.rs:1080-1127) ==========
         if (__any_sync(0xffffffffu, state == R_OUTPUT) && state == R_OUTPUT) {
             int status = DSB_STATUS_OK;
-            while (col < nt) {
+            if constexpr (RAG) {                    // solve(final_time): (state.t, state.y) after every step (method.rs:907-921)
+                double yc[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) yc[i] = SY(i);
+                write_column(col, t, yc);
+                ++col;
+            }
+            while (!RAG && col < nt) {
                 const double tq = bb.t_eval[col];
                 if (free_running ? (dsb_abs(t) < dsb_abs(tq)) : !(tq <= t)) break;
                 const bool is_forward = h_state > 0.0;

@@ -225,6 +225,23 @@ class BatchedSolver:
         self._stats, self._status = stats, status
         return ys
 
+    def solve(self, final_time):
+        """`solve(final_time)` (ode_solver/method.rs:227-258): every internal step of every instance.  -> (ys[total, nout],
+        ts[total], offsets[nbatch + 1]): instance b's columns are rows offsets[b] : offsets[b + 1].  Two passes on the device
+        (count, then write: dsb_batch_solve_count / dsb_batch_solve_write_host)."""
+        pr = self.problem
+        L = capi.lib()
+        self.set_params()
+        total = ctypes.c_int64()
+        capi.check(L.dsb_batch_solve_count(self._b, self.method, float(final_time), ctypes.byref(total)))
+        offsets = np.empty(pr.nbatch + 1, dtype=np.int64)
+        capi.check(L.dsb_batch_solve_offsets(self._b, _ptr(offsets)))
+        ts = np.empty(total.value)
+        ys = np.empty((total.value, pr.nout))
+        capi.check(L.dsb_batch_solve_write_host(self._b, self.method, float(final_time), _ptr(ts), _ptr(ys)))
+        self._stats = self._status = None
+        return ys, ts, offsets
+
     def solve_dense_sensitivities(self, t_eval, free_running=False):
         """`solve_dense_sensitivities(t_eval)` (ode_solver/sensitivities.rs:114-262) -> (ys[nbatch, nt, nstates],
         sens[nbatch, nt, nparams, nstates]); free_running = the step()/interpolate()/interpolate_sens() loop of the
@@ -241,6 +258,13 @@ class BatchedSolver:
                                               _ptr(ys), _ptr(sens), _ptr(stats), _ptr(status)))
         self._stats, self._status = stats, status
         return ys, sens
+
+    def solve_dense_sensitivities_device(self, t_eval, ys_dev_ptr, sens_dev_ptr, stream=None):
+        """Device-resident variant: ys -> [nt][nstates][nbatch], sens -> [nt][nparams][nstates][nbatch] doubles, asynchronous."""
+        t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
+        capi.check(capi.lib().dsb_batch_solve_dense_sensitivities(self._b, self.method, _ptr(t_eval), len(t_eval), ctypes.c_void_p(ys_dev_ptr),
+                                                                  ctypes.c_void_p(sens_dev_ptr), ctypes.c_void_p(stream or 0)))
+        self._stats = self._status = None
 
     def solve_dense_device(self, t_eval, ys_dev_ptr, stream=None, params_dev_ptr=None):
         """Device-resident variant: ys_dev_ptr -> [nt][nout][nbatch] doubles (batch-major), asynchronous."""

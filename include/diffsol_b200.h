@@ -198,6 +198,24 @@ int dsb_batch_solve_dense_sensitivities(dsb_batch* b, int32_t method, const doub
                                         void* stream);
 int dsb_batch_step_and_interpolate_sensitivities(dsb_batch* b, int32_t method, const double* t_points, int32_t npts, double* ys_dev,
                                                  double* sens_dev, void* stream);
+/* `problem.<method>::<LS>()?.solve(final_time)` for every instance (OdeSolverMethod::solve, ode_solver/method.rs:227-258; fn solve
+ * :881-961, write_out :965-1000): one column per INTERNAL step -- (state.t, state.y), or out(state.y, state.t) for equations
+ * with an output function -- after the initial one; a root ends an instance's solve with the state at the root in its last
+ * column.  Every instance takes its own number of steps, so the result is ragged and comes in two passes:
+ *   dsb_batch_solve_count   integrates once, writes nothing, and leaves per-instance column counts (dsb_batch_get_root_info's
+ *                           ncols) and their exclusive prefix sums in the batch; *total_columns = their sum.  Synchronous.
+ *   dsb_batch_solve_offsets copies the nbatch + 1 offsets to the host.
+ *   dsb_batch_solve_write   integrates again (the integration is deterministic: same steps) and writes instance b's column k
+ *                           at ts_dev[off[b] + k] and ys_dev[(off[b] + k) * nout + i]; asynchronous on `stream`.  Must follow a
+ *                           count with the same method and final_time (and unchanged parameters).
+ *   dsb_batch_solve_write_host  the same into host arrays of total_columns (x nout) doubles, synchronous.
+ * Parameters are set beforehand (dsb_batch_set_params_host / _device).  Built for the thread-per-instance kernels: n <= 16,
+ * BDF / TR-BDF2 / ESDIRK34, equations without a reset function. */
+int dsb_batch_solve_count(dsb_batch* b, int32_t method, double final_time, int64_t* total_columns);
+int dsb_batch_solve_offsets(dsb_batch* b, int64_t* offsets_host);
+int dsb_batch_solve_write(dsb_batch* b, int32_t method, double final_time, double* ts_dev, double* ys_dev, void* stream);
+int dsb_batch_solve_write_host(dsb_batch* b, int32_t method, double final_time, double* ts_host, double* ys_host);
+
 /* The same two calls with HOST buffers (parameters in, results back, synchronised): ys_host instance-major
  * [nbatch][nt][nstates]; sens_host [nbatch][nt][nparams][nstates] -- instance b's block holds, for every time, the nparams
  * sensitivity vectors one after the other (the Vec of matrices solve_dense_sensitivities returns, interleaved by time). */

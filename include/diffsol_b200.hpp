@@ -172,6 +172,11 @@ public:
     OdeBuilder& t0(double v) { t0_ = v; return *this; }
     OdeBuilder& h0(double v) { h0_ = v; return *this; }
     OdeBuilder& use_coloring(bool v) { use_coloring_ = v; return *this; }
+    // OdeBuilder::sens_rtol / sens_atol (builder.rs:1454-1477): forward sensitivities in the error test;
+    // sensitivities(true) alone integrates them outside it (turn_off_sensitivities_error_control)
+    OdeBuilder& sens_rtol(double v) { sens_ = true; sens_rtol_ = v; return *this; }
+    OdeBuilder& sens_atol(std::vector<double> v) { sens_ = true; sens_atol_ = std::move(v); return *this; }
+    OdeBuilder& sensitivities(bool on) { sens_ = on; return *this; }
     // parameters of the whole batch, instance-major: nbatch x nparams values
     OdeBuilder& p(std::vector<double> v) { p_ = std::move(v); return *this; }
     OdeBuilder& device(int32_t d) { device_ = d; return *this; }
@@ -201,6 +206,9 @@ public:
         detail::check(dsb_problem_set_h0(pr.handle_, h0_), "dsb_problem_set_h0");
         detail::check(dsb_problem_set_use_coloring(pr.handle_, use_coloring_ ? 1 : 0), "dsb_problem_set_use_coloring");
         detail::check(dsb_problem_set_options(pr.handle_, &opt_), "dsb_problem_set_options");
+        if (sens_)
+            detail::check(dsb_problem_set_sensitivities(pr.handle_, 1, sens_rtol_, sens_atol_.empty() ? nullptr : sens_atol_.data(),
+                                                        (int32_t)sens_atol_.size()), "dsb_problem_set_sensitivities");
         return pr;
     }
 
@@ -209,6 +217,9 @@ private:
     double rtol_ = 1e-6, t0_ = 0.0, h0_ = 1.0;
     std::vector<double> atol_ = {1e-6};
     bool use_coloring_ = false;
+    bool sens_ = false;
+    double sens_rtol_ = 0.0;
+    std::vector<double> sens_atol_;
     std::vector<double> p_;
     int32_t device_ = 0;
     dsb_options opt_;
@@ -237,6 +248,19 @@ public:
                                                  problem_->nparams_, t_eval.data(), (int32_t)t_eval.size(), ys.data(), nullptr, nullptr),
                       "dsb_batch_solve_dense_host");
         return ys;
+    }
+    // solve_dense_sensitivities (ode_solver/sensitivities.rs:114-262) on a problem built with sens_rtol / sens_atol /
+    // sensitivities(true), solver = problem.bdf(): the states, and per instance nt x nparams sensitivity vectors
+    // (sens block b, time k, parameter q at rows [q * nstates, (q + 1) * nstates) of column k)
+    std::pair<DenseBlocks, DenseBlocks> solve_dense_sensitivities(const std::vector<double>& t_eval) {
+        if (t_eval.empty()) throw DiffsolError(DSB_BAD_ARG, "solve_dense_sensitivities: t_eval is empty");
+        DenseBlocks ys(problem_->nbatch_, problem_->nstates_, (int32_t)t_eval.size());
+        DenseBlocks sens(problem_->nbatch_, problem_->nstates_ * problem_->nparams_, (int32_t)t_eval.size());
+        detail::check(dsb_batch_solve_dense_sensitivities_host(batch_, method_, problem_->params_.empty() ? nullptr : problem_->params_.data(),
+                                                               problem_->nparams_, t_eval.data(), (int32_t)t_eval.size(), ys.data(), sens.data(),
+                                                               nullptr, nullptr),
+                      "dsb_batch_solve_dense_sensitivities_host");
+        return {std::move(ys), std::move(sens)};
     }
     // The loop of the reference's test harness (ode_solver/mod.rs:104-194): step while |t| < |t_point|, interpolate
     DenseBlocks step_and_interpolate(const std::vector<double>& t_points) {

@@ -304,5 +304,7 @@ Method* new_sdirk(const Problem& pr, int tableau /*0 = tr_bdf2, 1 = esdirk34*/, 
 // (nout values) instead of the n states; `pr` supplies it (may be NULL: states).
 int solve_dense(Method& s, const double* t_eval, int nt, int n, double* out /* n*nt (or nout*nt) col-major */,
                 int* ncols = nullptr, double* root_t = nullptr, int* root_idx = nullptr, const Problem* pr = nullptr);
+int solve_ragged(Method& s, double final_time, int n, const Problem* pr, int max_cols, double* ts, double* ys, int* ncols,
+                 double* root_t, int* root_idx);
 
 }  // namespace orc

@@ -206,6 +206,42 @@ int orc_harness_sens(const orc_problem_desc* d, const double* p, int np, const d
     return err;
 }
 
+// OdeSolverMethod::solve(final_time) for every row of params (instance-major): instance b's columns at ts[b * max_cols ..),
+// ys[b * max_cols * nrow ..) (nrow = the out function's outputs, else n), their number in ncols[b]; roots[b] = (t_root, index)
+int orc_batch_solve_ragged(const orc_problem_desc* d, const double* params, int np, int64_t nbatch, double final_time, int max_cols,
+                           int nthreads, double* ts, double* ys, int32_t* ncols, int64_t* stats, int32_t* status, double* roots) {
+    Model mm;
+    if (!model_by_id(d->model_id, &mm)) return ST_BAD_ARG;
+    const int nrow = mm.ncols_out();
+    int nt_use = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
+    if (nt_use < 1) nt_use = 1;
+    std::atomic<int64_t> next(0);
+    auto worker = [&]() {
+        while (true) {
+            const int64_t b0 = next.fetch_add(16);
+            if (b0 >= nbatch) break;
+            const int64_t b1 = b0 + 16 < nbatch ? b0 + 16 : nbatch;
+            for (int64_t b = b0; b < b1; ++b) {
+                Problem pr;
+                int err = build_problem(d, params + (size_t)b * np, np, &pr);
+                int nc = 0, ridx = -1; double rt = 0.0;
+                std::unique_ptr<Method> m;
+                if (!err) m.reset(make_method(pr, d->method, &err));
+                if (m) err = solve_ragged(*m, final_time, pr.n(), &pr, max_cols, ts + (size_t)b * max_cols, ys + (size_t)b * max_cols * nrow,
+                                          &nc, &rt, &ridx);
+                export_stats(pr, m.get(), stats + (size_t)b * S_COUNT);
+                ncols[b] = nc; status[b] = err;
+                if (roots) { roots[b * 2] = rt; roots[b * 2 + 1] = (double)ridx; }
+            }
+        }
+    };
+    if (nt_use == 1) { worker(); return ST_OK; }
+    std::vector<std::thread> pool;
+    for (int k = 0; k < nt_use; ++k) pool.emplace_back(worker);
+    for (auto& th : pool) th.join();
+    return ST_OK;
+}
+
 // fn solve_dense_sensitivities (ode_solver/sensitivities.rs:205-262) + dense_write_out_sensitivities (:360-397) for equations
 // without output or root functions: a stop time at t_eval[nt - 1], step(), interpolate + interpolate_sens at every point
 // passed.  out is n x nt, sens_out is n x np x nt (point-major, then parameter).

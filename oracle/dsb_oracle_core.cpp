@@ -591,4 +591,43 @@ int solve_dense(Method& s, const double* t_eval, int nt, int n, double* out, int
     return ST_OK;
 }
 
+// fn solve (ode_solver/method.rs:881-961) + write_out (:965-1000) behind OdeSolverMethod::solve(final_time) (:227-258): one
+// column per internal step -- (state.t, state.y), or out(state.y, state.t) for equations with an output function -- after
+// the initial one; a root ends the solve with the state moved back to the root (no reset function here).
+// ST_BAD_ARG when max_cols columns do not hold the run.
+int solve_ragged(Method& s, double final_time, int n, const Problem* pr, int max_cols, double* ts, double* ys, int* ncols,
+                 double* root_t, int* root_idx) {
+    const bool has_out = pr && pr->model.nout > 0;
+    const int nrow = has_out ? pr->model.nout : n;
+    int col = 0;
+    auto write_out = [&]() -> bool {
+        if (col >= max_cols) return false;
+        ts[col] = s.t();
+        if (has_out) pr->model.out(s.y(), pr->p.data(), s.t(), ys + (size_t)col * nrow);
+        else for (int i = 0; i < n; ++i) ys[(size_t)col * nrow + i] = s.y()[i];
+        ++col;
+        return true;
+    };
+    if (root_idx) *root_idx = -1;
+    if (pr && pr->model.reset) return ST_BAD_ARG;
+    if (!write_out()) return ST_BAD_ARG;
+    int err = s.set_stop_time(final_time);
+    while (!err) {
+        StopReason r = s.step(&err);
+        if (r == STEP_ERROR) break;
+        if (r == ROOT_FOUND) {
+            const double tr = s.root_t();
+            err = s.state_mut_back(tr);
+            if (!err && !write_out()) err = ST_BAD_ARG;
+            if (root_t) *root_t = tr;
+            if (root_idx) *root_idx = s.root_index();
+            break;
+        }
+        if (!write_out()) { err = ST_BAD_ARG; break; }
+        if (r == TSTOP_REACHED) break;
+    }
+    if (ncols) *ncols = col;
+    return err;
+}
+
 }  // namespace orc

@@ -119,6 +119,9 @@ def lib():
         L.orc_batch_solve_dense_sens.restype = ctypes.c_int
         L.orc_batch_solve_dense_sens.argtypes = [ctypes.POINTER(ProblemDesc), dp, ctypes.c_int, ctypes.c_int64, dp, ctypes.c_int,
                                                  ctypes.c_int, dp, dp, ip, ctypes.POINTER(ctypes.c_int32)]
+        L.orc_batch_solve_ragged.restype = ctypes.c_int
+        L.orc_batch_solve_ragged.argtypes = [ctypes.POINTER(ProblemDesc), dp, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_int,
+                                             ctypes.c_int, dp, dp, ctypes.POINTER(ctypes.c_int32), ip, ctypes.POINTER(ctypes.c_int32), dp]
         L.orc_batch_solve_dense.restype = ctypes.c_int
         L.orc_batch_solve_dense.argtypes = [
             ctypes.POINTER(ProblemDesc), dp, ctypes.c_int, ctypes.c_int64, dp, ctypes.c_int, ctypes.c_int,
@@ -258,6 +261,27 @@ def batch_solve_dense_sens(desc, params, t_eval, nthreads=0):
                                           status.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
     assert rc == 0
     return ys, sens, stats, status
+
+
+def batch_solve_ragged(desc, params, final_time, max_cols=4096, nthreads=0):
+    """OdeSolverMethod::solve(final_time) for every row of params -> (ts[B, max_cols], ys[B, max_cols, nrow], ncols[B],
+    stats[B, 16], status[B], roots[B, 2] = (t_root, root index)); instance b's columns are the first ncols[b]."""
+    n, np_, _ = _dims_by_id(desc.model_id)
+    nrow = lib().orc_model_nout(int(desc.model_id)) or n
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, max(np_, 1))
+    B = params.shape[0]
+    ts = np.full((B, max_cols), np.nan)
+    ys = np.full((B, max_cols, nrow), np.nan)
+    ncols = np.zeros(B, dtype=np.int32)
+    stats = np.zeros((B, S_COUNT), dtype=np.int64)
+    status = np.zeros(B, dtype=np.int32)
+    roots = np.zeros((B, 2))
+    ip32 = ctypes.POINTER(ctypes.c_int32)
+    rc = lib().orc_batch_solve_ragged(ctypes.byref(desc), _dp(params), np_, B, float(final_time), int(max_cols), int(nthreads), _dp(ts),
+                                      _dp(ys), ncols.ctypes.data_as(ip32), stats.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                      status.ctypes.data_as(ip32), _dp(roots))
+    assert rc == 0
+    return ts, ys, ncols, stats, status, roots
 
 
 def greedy_coloring(non_zeros, n):

@@ -2,7 +2,7 @@
 // API (ode_solver/bdf.rs:2175-2197 test_bdf_nalgebra_robertson; examples/*): OdeBuilder -> problem.bdf() ->
 // solve_dense -> get_statistics.  Prints one line per instance: status, the 13 counters, the last column.
 // Without a CUDA device the solver construction throws DiffsolError (no CPU fallback): exit code 3.
-//   usage: robertson_cpp <method: bdf|tr_bdf2|esdirk34> <nbatch>
+//   usage: robertson_cpp <method: bdf|tr_bdf2|esdirk34|sens> <nbatch>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -23,6 +23,25 @@ int main(int argc, char** argv) {
         return 12;
     } catch (const DiffsolError& e) { if (e.code() != DSB_BAD_ARG) return 13; }
 
+    if (method == "sens") {
+        // problem.bdf_sens()?.solve_dense_sensitivities(t_eval) on the reference's exponential-decay sensitivity problem
+        // (test_models/exponential_decay.rs:703-742), k swept over the batch: prints y0, dy0/dk, dy0/dy0 at the last time
+        std::vector<double> ps;
+        for (int b = 0; b < nbatch; ++b) { ps.push_back(0.1 * (1.0 + 0.25 * b)); ps.push_back(1.0); }
+        OdeSolverProblem pr = OdeBuilder().rhs_implicit("exp_decay").p(ps).sens_rtol(1e-6).sens_atol({1e-6, 1e-6}).build();
+        try {
+            BatchedSolver solver = pr.bdf();
+            const std::vector<double> t_eval = {1.0, 2.0, 5.0};
+            auto res = solver.solve_dense_sensitivities(t_eval);
+            std::vector<int32_t> status = solver.status();
+            for (int b = 0; b < nbatch; ++b)
+                std::printf("%d %d %.17g %.17g %.17g\n", b, status[b], res.first(b, 0, 2), res.second(b, 0, 2), res.second(b, 2, 2));
+        } catch (const DiffsolError& e) {
+            std::fprintf(stderr, "DiffsolError(%d): %s\n", e.code(), e.what());
+            return 3;
+        }
+        return 0;
+    }
     std::vector<double> p;
     for (int b = 0; b < nbatch; ++b) { p.push_back(0.04 * (1.0 + 0.125 * b)); p.push_back(1.0e4); p.push_back(3.0e7); }
     OdeSolverProblem problem = OdeBuilder().rhs_implicit("robertson_dae").p(p).rtol(1e-4).atol({1e-8, 1e-6, 1e-6}).build();

@@ -165,6 +165,57 @@ struct EmuSensCall {
     }
 };
 
+// solve(final_time): the on-chip lane kernels instantiated for DsbRagged<M> (dsb_inst.cu: RaggedLauncher), writing pass with
+// the instance's run at offset 0 of a max_cols-column block
+struct EmuRaggedCall {
+    const dsb_problem* pr; int method;
+    const double* params; int64_t B; double final_time; int max_cols;
+    double* ts; double* ys; int32_t* ncols; int64_t* stats; int32_t* status; int32_t* root_idx;
+    int rc;
+    template <class M> void operator()() {
+        constexpr int N = M::N, NP = M::NP;
+        if constexpr (N <= 16 && !dsb_model_has_reset<M>::value) {
+            typedef DsbRagged<M> MR;
+            constexpr int NOUT = dsb_model_nout<M>::value;
+            DsbProblemArgs pa;
+            int probes = 0;
+            std::vector<int32_t> color_full; std::vector<uint8_t> nz_full;
+            if (dsb_host::fill_problem_args(*pr, 1, 1, &pa, &probes, &color_full, &nz_full) != DSB_OK) { rc = DSB_BAD_ARG; return; }
+            pa.free_running = 0; pa.ragged = 2;
+            dsb_host::build_tableau(method, &pa.rk);
+            pa.quorum = DSB_DEFAULT_QUORUM;
+            std::vector<double> y0(N), dy0(N), h0(1), ysb(NOUT), fin_t(1), fin_h(1);
+            std::vector<int32_t> st(DSB_NSTATS), status1(1), fin_order(1), ridx(1), nc(1);
+            const int64_t off[2] = {0, 0};
+            for (int64_t b = 0; b < B; ++b) {
+                DsbBatchBuffers bb;
+                bb.params = params + b * NP; bb.t_eval = &final_time; bb.y0 = y0.data(); bb.dy0 = dy0.data(); bb.h0 = h0.data();
+                bb.ys = ysb.data(); bb.ss = nullptr; bb.stats = st.data(); bb.status = status1.data();
+                bb.fin_t = fin_t.data(); bb.fin_h = fin_h.data(); bb.fin_order = fin_order.data();
+                bb.root_idx = ridx.data(); bb.ncols = nc.data();
+                bb.rag_off = off; bb.rag_ts = ts + b * max_cols; bb.rag_ys = ys + b * max_cols * NOUT;
+                for (auto& v : st) v = 0;
+                status1[0] = -1; ridx[0] = -1; nc[0] = 0;
+                unsigned long long work_counter = 0;
+                if (method == DSB_METHOD_BDF) {
+                    blockDim.x = BdfLayout<MR>::THREADS;
+                    dsb_init_kernel<M>(pa, bb, 1);
+                    dsb_bdf_solve_dense_kernel<MR>(pa, bb, &work_counter);
+                } else {
+                    blockDim.x = SdirkLayout<MR>::THREADS;
+                    dsb_init_kernel<M>(pa, bb, pa.rk.order);
+                    dsb_sdirk_solve_dense_kernel<MR>(pa, bb, &work_counter);
+                }
+                for (int s = 0; s < DSB_NSTATS; ++s) stats[b * DSB_NSTATS + s] = st[s] + (s == DSB_STAT_RHS_JAC_MULS ? probes : 0);
+                status[b] = status1[0]; ncols[b] = nc[0]; root_idx[b] = ridx[0];
+            }
+            rc = DSB_OK;
+        } else {
+            rc = DSB_ERR;
+        }
+    }
+};
+
 }  // namespace
 
 // SmemBandLU (dsb_wband_bdf_kernel.cuh) on a dense column-major n x n matrix whose entries outside the band (kl, ku) are
@@ -225,6 +276,23 @@ int emu_solve_sens(int model, double rtol, const double* atol, int natol, double
     if (natol != 1 && natol != pr.n) return DSB_BAD_ARG;
     pr.sens = 1; pr.sens_rtol = sens_rtol; pr.sens_atol.assign(sens_atol, sens_atol + sens_natol);
     EmuSensCall call{&pr, free_running, params, B, t_eval, nt, ys, sens, stats, status, DSB_ERR};
+    dsb_dispatch_model(model, call);
+    return call.rc;
+}
+
+// OdeSolverMethod::solve(final_time) through the DsbRagged<M> instantiation of the on-chip lane kernels; instance b's columns
+// at ts[b * max_cols ..), ys[b * max_cols * nout ..) -- max_cols must hold the longest run (the emulation does not check)
+int emu_solve_ragged(int model, int method, double rtol, const double* atol, int natol, double t0, double h0, const dsb_options* opt,
+                     const double* params, int64_t B, double final_time, int max_cols, double* ts, double* ys, int32_t* ncols,
+                     int64_t* stats, int32_t* status, int32_t* root_idx) {
+    dsb_problem pr;
+    pr.model = model; pr.n = 0; pr.np = 0; pr.has_mass = 0;
+    pr.rtol = rtol; pr.atol.assign(atol, atol + natol); pr.t0 = t0; pr.h0 = h0; pr.use_coloring = 0;
+    if (opt) pr.opt = *opt; else dsb_options_default(&pr.opt);
+    EmuDims dims{&pr};
+    if (!dsb_dispatch_model(model, dims)) return DSB_BAD_ARG;
+    if (natol != 1 && natol != pr.n) return DSB_BAD_ARG;
+    EmuRaggedCall call{&pr, method, params, B, final_time, max_cols, ts, ys, ncols, stats, status, root_idx, DSB_ERR};
     dsb_dispatch_model(model, call);
     return call.rc;
 }

@@ -73,6 +73,11 @@ def lib():
                                 ctypes.POINTER(ctypes.c_int32), dp, ctypes.POINTER(ctypes.c_int32),
                                 ctypes.POINTER(ctypes.c_int32)]
         L.dsb_options_default.argtypes = [ctypes.POINTER(Options)]
+        L.emu_solve_ragged.restype = ctypes.c_int
+        L.emu_solve_ragged.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, dp, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                       ctypes.POINTER(Options), dp, ctypes.c_int64, ctypes.c_double, ctypes.c_int, dp, dp,
+                                       ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32),
+                                       ctypes.POINTER(ctypes.c_int32)]
         L.emu_solve_sens.restype = ctypes.c_int
         L.emu_solve_sens.argtypes = [ctypes.c_int, ctypes.c_double, dp, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                      ctypes.POINTER(Options), ctypes.c_double, dp, ctypes.c_int, dp, ctypes.c_int64, dp, ctypes.c_int,
@@ -145,6 +150,27 @@ def solve_sens(model_id, n, np_, params, t_eval, rtol=1e-6, atol=1e-6, t0=0.0, h
     if rc != 0:
         raise RuntimeError("emu_solve_sens: rc = %d" % rc)
     return dict(ys=ys, sens=sens, stats=stats, status=status)
+
+
+def solve_ragged(model_id, n, np_, params, final_time, method="bdf", rtol=1e-6, atol=1e-6, t0=0.0, h0=1.0, nout=None, max_cols=4096):
+    """OdeSolverMethod::solve(final_time) through the DsbRagged<M> instantiation of the on-chip lane kernels ->
+    dict(ts[B, max_cols], ys[B, max_cols, nout], ncols[B], stats[B, 16], status[B], root_idx[B])."""
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, max(np_, 1))
+    B = params.shape[0]
+    atol = np.ascontiguousarray(np.atleast_1d(np.asarray(atol, dtype=np.float64)))
+    ts = np.full((B, max_cols), np.nan)
+    ys = np.full((B, max_cols, nout or n), np.nan)
+    ncols = np.zeros(B, dtype=np.int32)
+    stats = np.zeros((B, NSTATS), dtype=np.int64)
+    status = np.zeros(B, dtype=np.int32)
+    root_idx = np.zeros(B, dtype=np.int32)
+    ip32 = ctypes.POINTER(ctypes.c_int32)
+    rc = lib().emu_solve_ragged(int(model_id), METHODS[method], float(rtol), _dp(atol), len(atol), float(t0), float(h0), None, _dp(params), B,
+                                float(final_time), int(max_cols), _dp(ts), _dp(ys), ncols.ctypes.data_as(ip32),
+                                stats.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), status.ctypes.data_as(ip32), root_idx.ctypes.data_as(ip32))
+    if rc != 0:
+        raise RuntimeError("emu_solve_ragged: rc = %d" % rc)
+    return dict(ts=ts, ys=ys, ncols=ncols, stats=stats, status=status, root_idx=root_idx)
 
 
 def greedy_coloring(non_zeros, n):

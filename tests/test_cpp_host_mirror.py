@@ -56,3 +56,20 @@ def test_cpp_mirror_equals_python_mirror(cpp_binary, method):
         assert [int(x) for x in row[2:15]] == stats[b, :13].tolist()
         assert [float(x) for x in row[15:18]] == ys[b, 5].tolist()
         assert float(row[18]) == 40000.0 and int(row[19]) == -1
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_sensitivities_equal_python_mirror(cpp_binary):
+    """OdeBuilder().sens_rtol().sens_atol() ... solve_dense_sensitivities through the C++ header, against the Python mirror."""
+    import diffsol_b200 as dsb
+    B = 5
+    r = subprocess.run([cpp_binary, "sens", str(B)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = [line.split() for line in r.stdout.strip().splitlines()]
+    p = np.array([[0.1 * (1.0 + 0.25 * b), 1.0] for b in range(B)])
+    solver = dsb.OdeBuilder().rhs_implicit("exp_decay").p(p).sens_rtol(1e-6).sens_atol([1e-6, 1e-6]).build().bdf_sens()
+    ys, sens = solver.solve_dense_sensitivities([1.0, 2.0, 5.0])
+    for b, row in enumerate(rows):
+        assert int(row[0]) == b and int(row[1]) == 0
+        assert [float(x) for x in row[2:5]] == [ys[b, 2, 0], sens[b, 2, 0, 0], sens[b, 2, 1, 0]]
+        assert abs(float(row[3]) + 5.0 * np.exp(-5.0 * p[b, 0])) < 1e-5
