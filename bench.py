@@ -329,6 +329,30 @@ def fp64_peak():
         return {"unavailable": str(e)[:120]}
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Multi-GPU runs: restrict this rank to the CPUs NVML reports as local to its GPU BEFORE the pinned host buffers are
+    allocated and first touched, so that the host <-> device copies of the end-to-end leg do not cross the socket
+    interconnect.  Returns the number of CPUs the rank is bound to (0: left alone)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(local_rank)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(props.uuid)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (max(os.cpu_count() or 64, 64) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        local = {w * 64 + k for w, word in enumerate(mask) for k in range(64) if (int(word) >> k) & 1}
+        cpus = sorted(local & os.sched_getaffinity(0))
+        if not cpus or len(cpus) == len(os.sched_getaffinity(0)):
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -355,6 +379,7 @@ def main():
     capi.require_device()                       # fail loudly: there is no CPU fallback
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -530,7 +555,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "instances_per_gpu": B, "instances_total": B * world,
                        "parallelism": "instances sharded i mod G, one all-gather of trajectories" if world > 1 else "single GPU",
-                       "l2": "256 MiB buffer rewritten between timed steps", "failed_instances": c[7]},
+                       "l2": "256 MiB buffer rewritten between timed steps", "failed_instances": c[7],
+                       "rank0_bound_to_gpu_local_cpus": numa_cpus},
             "instances_per_sec": B * world * args.steps / (total_ms * 1e-3),
             "newton_iters_per_step": nli_all,
             "e2e": {"value": c[6] / (e2e_ms * 1e-3), "unit": UNIT,

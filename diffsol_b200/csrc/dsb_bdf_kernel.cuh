@@ -44,6 +44,7 @@
 //   fn solve_dense               ode_solver/method.rs:721-848
 #pragma once
 #include "dsb_lane.cuh"
+#include "dsb_init_kernel.cuh"      // lane_consistent_solve: consistent sensitivities of a DAE
 #include "dsb_roots.cuh"
 
 #define DSB_NSTATS_USED 13      // counters the kernels maintain (the C ABI rows have DSB_NSTATS = 16 slots)
@@ -121,9 +122,9 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #define SPR(i) SM(Lay::O_SPR + (i))
 #define SYC(i) SM(Lay::O_SYC + (i))
     constexpr bool SENS = Lay::SENS;
-    static_assert(!SENS || (dsb_model_has_sens<M>::value && !M::HAS_MASS && dsb_model_nroots<M>::value == 0 &&
+    static_assert(!SENS || (dsb_model_has_sens<M>::value && dsb_model_nroots<M>::value == 0 &&
                             !dsb_model_nout<M>::has_out && !dsb_model_has_reset<M>::value),
-                  "sensitivities: ODEs with sens_mul / init_sens, no root / output / reset functions");
+                  "sensitivities: equations with sens_mul / init_sens, no root / output / reset functions");
 
     const int64_t B = pa.nbatch;
     const int nt = pa.nt;
@@ -435,13 +436,42 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #pragma unroll
                         for (int i = 0; i < N; ++i) {
                             dsq[i] += SFP(q, i);
-                            SSS(q, i) = sq[i]; SDL(q, i) = 0.0;
+                            SSS(q, i) = sq[i]; SDL(q, i) = M::HAS_MASS ? dsq[i] : 0.0;      // (a DAE's ds_q is parked for the solve below)
                             SDF(q, 0, i) = sq[i]; SDF(q, 1, i) = dsq[i] * h;
                         }
 #pragma unroll 1
                         for (int j = 2; j < DSB_NDIFF; ++j)
 #pragma unroll
                             for (int i = 0; i < N; ++i) SDF(q, j, i) = 0.0;
+                    }
+                    if constexpr (M::HAS_MASS) {
+                        // set_consistent_augmented's algebraic part (state.rs:191-237): after every ds_q is formed, each
+                        // sensitivity vector goes through the InitOp solve on SensRhs (J(y0) x + f_p e_q; its Jacobian is
+                        // df/dy at y0, evaluated per parameter), with ONE Convergence for all of them
+                        LaneConvergence ic_conv;
+                        ic_conv.tol = pa.opt.nonlinear_solver_tolerance;
+                        ic_conv.eta = pa.tab.eta_reset;
+                        ic_conv.max_iter = pa.opt.ic_max_newton_iterations;
+                        ic_conv.reset();
+                        int ic_status = DSB_STATUS_OK;
+#pragma unroll 1
+                        for (int q = 0; q < NP && ic_status == DSB_STATUS_OK; ++q) {
+#pragma unroll
+                            for (int i = 0; i < N; ++i) { sq[i] = SSS(q, i); dsq[i] = SDL(q, i); SDL(q, i) = 0.0; }
+                            ic_status = lane_consistent_solve<M>(pa, pl0, sq, dsq,
+                                [&](const double (&x)[N], double (&out)[N]) {
+                                    M::jac_mul(y0l, pl0, t, x, out);
+                                    st.v[DSB_STAT_RHS_JAC_MULS] += 1;
+#pragma unroll
+                                    for (int i = 0; i < N; ++i) out[i] += SFP(q, i);
+                                },
+                                [&](double (&J)[N][N]) {
+                                    lane_jacobian_to<M>(pa, y0l, pl0, t, st, [&](int j, int i, double val) { J[j][i] = val; });
+                                }, ic_conv, false);
+#pragma unroll
+                            for (int i = 0; i < N; ++i) { SSS(q, i) = sq[i]; SDF(q, 0, i) = sq[i]; SDF(q, 1, i) = dsq[i] * h; }
+                        }
+                        if (ic_status != DSB_STATUS_OK) finish(ic_status);
                     }
                     eq = 0; c_sens = 0.0;
                 }
@@ -452,7 +482,8 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                 convergence_fail = false; first = true; reached = false; pending_etf = false; col = 0;
                 t_predict = t;
                 jac_kind = DSB_KIND_CONSTRUCT;
-                state = L_JAC;
+                if constexpr (SENS && M::HAS_MASS) { if (state != L_FINISH) state = L_JAC; }      // (the sensitivities' consistency solve may fail)
+                else state = L_JAC;
             }
         }
         // ================= REINIT: Bdf::step finds the state modified by a reset (bdf.rs:1291-1318) ==========
@@ -910,11 +941,17 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                     M::jac_mul(ypl_, pl, t_predict, y_cur, delta);
                     st.v[DSB_STAT_RHS_JAC_MULS] += 1;
                     const double mc = -c_sens;
+                    double tmp[N];
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
                         delta[i] += SFP(eq - 1, i);
-                        const double tmp = y_cur[i] + psi_neg_y0[i];
-                        delta[i] = tmp + mc * delta[i];
+                        tmp[i] = y_cur[i] + psi_neg_y0[i];
+                    }
+                    if (M::HAS_MASS) {
+                        M::mass(tmp, pl, t_predict, mc, delta);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) delta[i] = tmp[i] + mc * delta[i];
                     }
                 }
             } else {

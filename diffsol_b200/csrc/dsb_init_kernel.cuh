@@ -11,9 +11,13 @@
 #pragma once
 #include "dsb_lane.cuh"
 
-template <class M>
-DSB_DEV int lane_set_consistent(const DsbProblemArgs& pa, const double* p, double (&y)[M::N], double (&dy)[M::N],
-                                LaneStats& st) {
+// The solve is shared by the state (set_consistent, state.rs:84-162: eq_rhs / eq_jac = the equations' own, a fresh
+// Convergence, dy zeroed at the algebraic rows) and the sensitivity vectors of a DAE (set_consistent_augmented,
+// state.rs:167-238: eq_rhs = SensRhs::call, eq_jac = SensRhs::jacobian_inplace, ONE Convergence for every parameter, ds kept
+// at the algebraic rows).  eq_rhs(x, out) and eq_jac(J) do their own counting.
+template <class M, class RhsFn, class JacFn>
+DSB_DEV int lane_consistent_solve(const DsbProblemArgs& pa, const double* p, double (&y)[M::N], double (&dy)[M::N],
+                                  RhsFn&& eq_rhs, JacFn&& eq_jac, LaneConvergence& conv, bool zero_dv) {
     constexpr int N = M::N;
     if (!M::HAS_MASS) return DSB_STATUS_OK;
     const double t0 = pa.t0;
@@ -28,7 +32,7 @@ DSB_DEV int lane_set_consistent(const DsbProblemArgs& pa, const double* p, doubl
         // InitOp::new (op/init.rs:22-76): jac = (-M_u | f_v ; 0 | g_v), neg_mass = (-M_u | 0 ; 0 | 0)
         // is built below from Mm; keep Mm alive through the block.
         double rhs_jac[N][N];
-        lane_jacobian<M>(pa, y, p, t0, rhs_jac, st);
+        eq_jac(rhs_jac);
         LaneLU<N> lu;
         double neg_mass[N][N];
 #pragma unroll
@@ -55,8 +59,7 @@ DSB_DEV int lane_set_consistent(const DsbProblemArgs& pa, const double* p, doubl
         auto fun = [&](const double (&x)[N], double (&out)[N]) {
 #pragma unroll
             for (int i = 0; i < N; ++i) if (is_alg[i]) y0w[i] = x[i];
-            M::rhs(y0w, p, t0, out);
-            st.v[DSB_STAT_RHS_CALLS] += 1;
+            eq_rhs(y0w, out);
 #pragma unroll
             for (int j = 0; j < N; ++j)
 #pragma unroll
@@ -65,11 +68,6 @@ DSB_DEV int lane_set_consistent(const DsbProblemArgs& pa, const double* p, doubl
         double y_tmp[N], yerr[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) { y_tmp[i] = is_alg[i] ? y[i] : dy[i]; yerr[i] = y_tmp[i]; }
-        LaneConvergence conv;
-        conv.tol = pa.opt.nonlinear_solver_tolerance;
-        conv.eta = pa.tab.eta_reset;
-        conv.max_iter = pa.opt.ic_max_newton_iterations;
-        conv.reset();
         const double tau = pa.opt.ic_step_reduction_factor, c_armijo = pa.opt.ic_armijo_constant;
         const double steptol = pa.tab.ic_steptol;
         const int ls_max_iter = pa.opt.ic_max_linesearch_iterations;
@@ -147,11 +145,27 @@ DSB_DEV int lane_set_consistent(const DsbProblemArgs& pa, const double* p, doubl
         if (!ok) return DSB_STATUS_INITIAL_CONDITION_DID_NOT_CONVERGE;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            if (is_alg[i]) { y[i] = y_tmp[i]; dy[i] = 0.0; }
+            if (is_alg[i]) { y[i] = y_tmp[i]; if (zero_dv) dy[i] = 0.0; }
             else dy[i] = y_tmp[i];
         }
     }
     return DSB_STATUS_OK;
+}
+
+template <class M>
+DSB_DEV int lane_set_consistent(const DsbProblemArgs& pa, const double* p, double (&y)[M::N], double (&dy)[M::N],
+                                LaneStats& st) {
+    constexpr int N = M::N;
+    if (!M::HAS_MASS) return DSB_STATUS_OK;
+    LaneConvergence conv;
+    conv.tol = pa.opt.nonlinear_solver_tolerance;
+    conv.eta = pa.tab.eta_reset;
+    conv.max_iter = pa.opt.ic_max_newton_iterations;
+    conv.reset();
+    const double t0 = pa.t0;
+    return lane_consistent_solve<M>(pa, p, y, dy,
+                                    [&](const double (&x)[N], double (&out)[N]) { M::rhs(x, p, t0, out); st.v[DSB_STAT_RHS_CALLS] += 1; },
+                                    [&](double (&J)[N][N]) { lane_jacobian<M>(pa, y, p, t0, J, st); }, conv, true);
 }
 
 template <class M>

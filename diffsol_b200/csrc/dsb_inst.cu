@@ -423,10 +423,10 @@ template <class M> struct LaneLauncher<M, true> {
 };
 
 // forward sensitivities (problem.bdf_sens(), solve_dense_sensitivities): the on-chip BDF lane kernel instantiated for
-// DsbWithSens<M> -- ODEs of n <= 16 that provide sens_mul / init_sens and have no root / output / reset functions
+// DsbWithSens<M> -- ODEs and DAEs of n <= 16 that provide sens_mul / init_sens and have no root / output / reset functions
 template <class M, bool LANE> struct SensCapable : std::false_type {};
 template <class M> struct SensCapable<M, true>
-    : std::bool_constant<dsb_model_has_sens<M>::value && !M::HAS_MASS && dsb_model_nroots<M>::value == 0 &&
+    : std::bool_constant<dsb_model_has_sens<M>::value && dsb_model_nroots<M>::value == 0 &&
                          !dsb_model_nout<M>::has_out && !dsb_model_has_reset<M>::value> {};
 constexpr bool kSensCapable = SensCapable<InstModel, kLaneCapable>::value;
 template <class M, bool OK> struct SensLauncher {

@@ -138,7 +138,7 @@ struct ModelExpDecayAlgebraic {
     DSB_HD static void init(const double*, double, double* y) {
         y[0] = 1.0; y[1] = 1.0; y[2] = 0.0;
     }
-    // forward sensitivities (oracle pin only, see ModelRobertsonDae): exponential_decay_with_algebraic_sens / _init_sens
+    // forward sensitivities: exponential_decay_with_algebraic_sens / _init_sens
     // (test_models/exponential_decay_with_algebraic.rs:32-43, 128-135), the problem of ..._problem_sens (:418-453)
     static constexpr bool HAS_SENS = true;
     DSB_HD static void sens_mul(const double* x, const double*, double, const double* v, double* y) {
@@ -172,8 +172,8 @@ struct ModelRobertsonDae {
         y[0] = 1.0; y[1] = 0.0; y[2] = 0.0;
     }
     // forward sensitivities: robertson_sens_mul / robertson_init_sens (test_models/robertson.rs:73-77, 91-93), the problem of
-    // robertson_sens (:151-201).  The kernels integrate sensitivities for ODEs only; the oracle restates the DAE case too
-    // (consistent initialisation of the sensitivities, state.rs:167-238) to pin itself against bdf.rs:2248-2271.
+    // robertson_sens (:151-201): a DAE, so the sensitivities are made consistent first (state.rs:167-238); the run of
+    // bdf.rs:2248-2271 (28 failed Newton solves) pins the oracle and is reproduced by the kernel.
     static constexpr bool HAS_SENS = true;
     DSB_HD static void sens_mul(const double* x, const double*, double, const double* v, double* y) {
         y[0] = -v[0] * x[0] + v[1] * x[1] * x[2];

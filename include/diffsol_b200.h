@@ -131,8 +131,9 @@ int dsb_problem_get_options(const dsb_problem* p, dsb_options* opt);
  * one sensitivity vector d y / d p_q per parameter beside the state (Bdf::sensitivity_solve, ode_solver/bdf.rs:934-989).
  * natol == 0 keeps the sensitivities out of the error test (OdeBuilder::turn_off_sensitivities_error_control); natol == 1
  * broadcasts sens_atol[0], natol == nstates gives it per state (param_scales = 1).  Equation sets qualify when they provide
- * sens_mul / init_sens (OdeEquationsImplicitSens), have no mass matrix, no root / output / reset function and
- * nstates <= 16; the method must be DSB_METHOD_BDF.  Anything else: DSB_ERR from the solve call. */
+ * sens_mul / init_sens (OdeEquationsImplicitSens), have no root / output / reset function and nstates <= 16 (ODEs, and
+ * singular-mass DAEs, whose sensitivities are made consistent first: set_consistent_augmented, state.rs:167-238); the method
+ * must be DSB_METHOD_BDF.  Anything else: DSB_ERR from the solve call. */
 int dsb_problem_set_sensitivities(dsb_problem* p, int32_t enable, double sens_rtol, const double* sens_atol, int32_t natol);
 
 /* ---- user equation sets: "user RHS closures and DiffSL-JIT modules drop in" -------------------------------------------------

@@ -127,7 +127,7 @@ struct EmuSensCall {
     int rc;
     template <class M> void operator()() {
         constexpr int N = M::N, NP = M::NP;
-        if constexpr (N <= 16 && dsb_model_has_sens<M>::value && !M::HAS_MASS && dsb_model_nroots<M>::value == 0 &&
+        if constexpr (N <= 16 && dsb_model_has_sens<M>::value && dsb_model_nroots<M>::value == 0 &&
                       !dsb_model_nout<M>::has_out && !dsb_model_has_reset<M>::value) {
             typedef DsbWithSens<M> MS;
             DsbProblemArgs pa;

@@ -170,6 +170,28 @@ def test_kernel_source_equals_oracle_robertson(oracle):
     assert np.array_equal(r["ys"], ys) and np.array_equal(r["sens"], se)
 
 
+def test_kernel_source_reproduces_the_dae_sens_snapshots(oracle):
+    """The DAE form in the kernel: consistent sensitivities (the InitOp solve on SensRhs inside FETCH), the mass matrix in the
+    sensitivity residual.  Through the free-running loop the kernel SOURCE gives every counter of bdf.rs:2118-2140 and
+    bdf.rs:2248-2271 (28 failed Newton solves), and on a Robertson DAE sweep with the sensitivities in the error test it equals
+    the oracle bit for bit."""
+    from host_emu import emu
+    t = np.array(GOLD["robertson_dae_points"]["t"])
+    r = emu.solve_sens(2, 3, 3, np.array([[0.04, 1e4, 3e7]]), t, rtol=1e-4, atol=[1e-8, 1e-6, 1e-6], free_running=True,
+                       options=dict(max_nonlinear_solver_failures=70))
+    assert r["status"][0] == 0 and r["stats"][0, :13].tolist() == ROBERTSON_DAE_SENS_SNAPSHOT
+    r = emu.solve_sens(1, 3, 1, np.array([[0.1]]), np.arange(10) / 10.0, sens_rtol=1e-6, sens_atol=[1e-6] * 3, free_running=True)
+    assert r["status"][0] == 0 and r["stats"][0, :13].tolist() == EXP_DECAY_ALGEBRAIC_SENS_SNAPSHOT
+    p = robertson_sweep(6)
+    te = np.array([0.4, 4.0, 40.0, 400.0])
+    tol = dict(rtol=1e-4, atol=[1e-8, 1e-6, 1e-6])
+    ys, se, st, status = oracle.batch_solve_dense_sens(
+        oracle.make_desc("robertson_dae", sens=True, sens_rtol=1e-5, sens_atol=[1e-7] * 3, powmode=1, **tol), p, te)
+    r = emu.solve_sens(2, 3, 3, p, te, sens_rtol=1e-5, sens_atol=[1e-7] * 3, **tol)
+    assert np.array_equal(r["status"], status) and (status == 0).all() and np.array_equal(r["stats"][:, :13], st[:, :13])
+    assert np.array_equal(r["ys"], ys) and np.array_equal(r["sens"], se)
+
+
 def test_sensitivity_arguments_are_checked_without_a_gpu():
     """dsb_problem_set_sensitivities: argument errors come back as DSB_BAD_ARG with a message (no device needed)."""
     import ctypes
@@ -261,6 +283,45 @@ def test_gpu_sensitivities_bit_exact_robertson(dsb, oracle):
     ok = status_o == 0
     assert ok.mean() > 0.99
     assert np.abs(sens[ok].sum(axis=-1)).max() < 1e-3 * max(1.0, np.abs(sens[ok]).max())
+
+
+@pytest.mark.gpu
+def test_gpu_reference_snapshots_dae_sens(dsb):
+    """The reference's two DAE sensitivity tests on the GPU (free-running loop): every counter of bdf.rs:2118-2140 and
+    bdf.rs:2248-2271."""
+    t = np.array(GOLD["robertson_dae_points"]["t"])
+    solver = (dsb.OdeBuilder().rhs_implicit("robertson_dae").p(np.array([[0.04, 1e4, 3e7]] * 40)).rtol(1e-4).atol([1e-8, 1e-6, 1e-6])
+              .sensitivities().ode_options(max_nonlinear_solver_failures=70).build().bdf_sens())
+    ys, sens = solver.solve_dense_sensitivities(t, free_running=True)
+    assert (solver.status() == 0).all()
+    assert (solver.statistics_array()[:, :13] == np.array(ROBERTSON_DAE_SENS_SNAPSHOT)).all()
+    ystar = np.array(GOLD["robertson_dae_points"]["y"])
+    assert (np.sqrt(np.mean(((ys[0] - ystar) / (np.abs(ystar) * 1e-4 + np.array([1e-8, 1e-6, 1e-6]))) ** 2, axis=1)) < 20.0).all()
+    t2 = np.arange(10) / 10.0
+    solver = dsb.OdeBuilder().rhs_implicit("exp_decay_algebraic").p(np.array([[0.1]] * 40)).sens_rtol(1e-6).sens_atol([1e-6] * 3).build().bdf_sens()
+    ys, sens = solver.solve_dense_sensitivities(t2, free_running=True)
+    assert (solver.status() == 0).all()
+    assert (solver.statistics_array()[:, :13] == np.array(EXP_DECAY_ALGEBRAIC_SENS_SNAPSHOT)).all()
+    assert np.abs(sens[:, :, 0, :] + (t2 * np.exp(-0.1 * t2))[None, :, None]).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_gpu_sensitivities_bit_exact_robertson_dae(dsb, oracle):
+    B = 1500
+    p = robertson_sweep(B)
+    te = np.array([0.4, 4.0, 40.0, 400.0, 4000.0])
+    tol = dict(rtol=1e-4, atol=[1e-8, 1e-6, 1e-6])
+    solver = (dsb.OdeBuilder().rhs_implicit("robertson_dae").p(p).rtol(tol["rtol"]).atol(tol["atol"]).sens_rtol(1e-5).sens_atol([1e-7] * 3)
+              .build().bdf_sens())
+    ys, sens = solver.solve_dense_sensitivities(te)
+    ys_o, se_o, st_o, status_o = oracle.batch_solve_dense_sens(
+        oracle.make_desc("robertson_dae", sens=True, sens_rtol=1e-5, sens_atol=[1e-7] * 3, powmode=1, **tol), p, te)
+    assert np.array_equal(solver.status(), status_o)
+    assert np.array_equal(solver.statistics_array()[:, :13], st_o[:, :13])
+    assert np.array_equal(ys, ys_o, equal_nan=True) and np.array_equal(sens, se_o, equal_nan=True)
+    ok = status_o == 0
+    assert ok.mean() > 0.99
+    assert np.abs(sens[ok].sum(axis=-1)).max() < 1e-6 * max(1.0, np.abs(sens[ok]).max())      # y1 + y2 + y3 = 1, differentiated
 
 
 @pytest.mark.gpu
