@@ -71,7 +71,10 @@ struct BdfLayout {
     static constexpr int O_P = O_YP + N;                            // parameters
     static constexpr int O_ST = O_P + (NP > 0 ? NP : 1);            // statistics, two int32 per word
     // forward sensitivities (DsbWithSens<M> only): per parameter a difference array, state.s, s_delta and the column of
-    // f_p at the predictor; the predictor of the sensitivity being solved; the parked solution of the main Newton solve
+    // f_p at the predictor; the predictor of the sensitivity being solved; the parked solution of the main Newton solve.
+    // (Tried and rejected: the difference arrays sdiff in a lane-interleaved global-memory slot, touched once per step --
+    // 166 -> 94 words of shared memory per lane, 5 -> 9 warps per SM for Robertson -- 760 -> 1166 ms per 10^6 instances:
+    // the blocks that touch sdiff run with ~3 active lanes per warp, and their L2 round trips are not hidden.)
     static constexpr bool SENS = dsb_model_sens_on<M>::value;
     static constexpr int O_SDF = O_ST + (DSB_NSTATS_USED + 1) / 2;  // sdiff[NP][DSB_NDIFF][N]
     static constexpr int O_SS = O_SDF + NP * DSB_NDIFF * N;         // state.s[NP][N]
@@ -313,21 +316,17 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
     };
     // the start of the Newton solve for sensitivity q (bdf.rs:948-968): predictor and psi from sdiff[q], s_new <- s_predict
     auto sens_setup = [&](int q) {
+        // (one pass over the columns: each accumulator sees its terms in the reference's order)
         double sp[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) sp[i] = 0.0;
-#pragma unroll 1
-        for (int j = 0; j <= order; ++j) {
+        for (int i = 0; i < N; ++i) { const double d0 = SDF(q, 0, i); sp[i] = 0.0; sp[i] += d0; }
 #pragma unroll
-            for (int i = 0; i < N; ++i) sp[i] += SDF(q, j, i);
-        }
-#pragma unroll
-        for (int i = 0; i < N; ++i) psi_neg_y0[i] = pa.tab.gamma[1] * SDF(q, 1, i);
+        for (int i = 0; i < N; ++i) { const double d1 = SDF(q, 1, i); sp[i] += d1; psi_neg_y0[i] = pa.tab.gamma[1] * d1; }
 #pragma unroll 1
         for (int j = 2; j <= order; ++j) {
             const double g = pa.tab.gamma[j];
 #pragma unroll
-            for (int i = 0; i < N; ++i) psi_neg_y0[i] = g * SDF(q, j, i) + psi_neg_y0[i];
+            for (int i = 0; i < N; ++i) { const double dj = SDF(q, j, i); sp[i] += dj; psi_neg_y0[i] = g * dj + psi_neg_y0[i]; }
         }
         const double a = pa.tab.alpha[order];
 #pragma unroll
@@ -1112,15 +1111,18 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #pragma unroll 1
                         for (int qs = 0; qs < NP; ++qs) {
 #pragma unroll
+                            double prev[N];
+#pragma unroll
                             for (int i = 0; i < N; ++i) {
                                 const double dl = SDL(qs, i);
                                 SDF(qs, ord + 2, i) = dl - SDF(qs, ord + 1, i);
                                 SDF(qs, ord + 1, i) = dl;
+                                prev[i] = dl;
                             }
 #pragma unroll 1
                             for (int j = ord; j >= 0; --j) {
 #pragma unroll
-                                for (int i = 0; i < N; ++i) SDF(qs, j, i) = SDF(qs, j, i) + 1.0 * SDF(qs, j + 1, i);
+                                for (int i = 0; i < N; ++i) { prev[i] = SDF(qs, j, i) + 1.0 * prev[i]; SDF(qs, j, i) = prev[i]; }
                             }
                         }
                     }

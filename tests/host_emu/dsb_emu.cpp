@@ -45,7 +45,7 @@ struct EmuCall {
         std::vector<double> y0(N), dy0(N), h0(1), ysb((size_t)nt * NOUT), fin_t(1), fin_h(1);
         std::vector<int32_t> st(DSB_NSTATS), status1(1), fin_order(1), ridx(1), nc(1);
         for (int64_t b = 0; b < B; ++b) {
-            DsbBatchBuffers bb;
+            DsbBatchBuffers bb{};
             bb.params = params + b * NP; bb.t_eval = t_eval; bb.y0 = y0.data(); bb.dy0 = dy0.data(); bb.h0 = h0.data();
             bb.ys = ysb.data(); bb.stats = st.data(); bb.status = status1.data();
             bb.fin_t = fin_t.data(); bb.fin_h = fin_h.data(); bb.fin_order = fin_order.data();
@@ -140,7 +140,7 @@ struct EmuSensCall {
             std::vector<double> y0(N), dy0(N), h0(1), ysb((size_t)nt * N), ssb((size_t)nt * NP * N), fin_t(1), fin_h(1);
             std::vector<int32_t> st(DSB_NSTATS), status1(1), fin_order(1), ridx(1), nc(1);
             for (int64_t b = 0; b < B; ++b) {
-                DsbBatchBuffers bb;
+                DsbBatchBuffers bb{};
                 bb.params = params + b * NP; bb.t_eval = t_eval; bb.y0 = y0.data(); bb.dy0 = dy0.data(); bb.h0 = h0.data();
                 bb.ys = ysb.data(); bb.ss = ssb.data(); bb.stats = st.data(); bb.status = status1.data();
                 bb.fin_t = fin_t.data(); bb.fin_h = fin_h.data(); bb.fin_order = fin_order.data();
@@ -188,7 +188,7 @@ struct EmuRaggedCall {
             std::vector<int32_t> st(DSB_NSTATS), status1(1), fin_order(1), ridx(1), nc(1);
             const int64_t off[2] = {0, 0};
             for (int64_t b = 0; b < B; ++b) {
-                DsbBatchBuffers bb;
+                DsbBatchBuffers bb{};
                 bb.params = params + b * NP; bb.t_eval = &final_time; bb.y0 = y0.data(); bb.dy0 = dy0.data(); bb.h0 = h0.data();
                 bb.ys = ysb.data(); bb.ss = nullptr; bb.stats = st.data(); bb.status = status1.data();
                 bb.fin_t = fin_t.data(); bb.fin_h = fin_h.data(); bb.fin_order = fin_order.data();
