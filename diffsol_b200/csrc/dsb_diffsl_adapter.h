@@ -11,7 +11,7 @@
 //
 // The module's dimensions, which the reference reads through get_dims(), have to be compile-time constants for the
 // kernels' register arrays; the source states them as
-//     #define DSB_DIFFSL_STATES / _INPUTS / _OUTPUTS / _DATA / _STOP / _HAS_MASS
+//     #define DSB_DIFFSL_STATES / _INPUTS / _OUTPUTS / _DATA / _STOP / _HAS_MASS / _HAS_SENS
 // and get_dims() (optional) must agree: the loader calls it on the host build and checks.
 //
 // `data` -- the module's scratch block (inputs first, then whatever intermediates it keeps) -- is per solver in the
@@ -35,6 +35,9 @@
 #ifndef DSB_DIFFSL_DATA
 #define DSB_DIFFSL_DATA DSB_DIFFSL_INPUTS
 #endif
+#ifndef DSB_DIFFSL_HAS_SENS          // the module provides rhs_sgrad / set_u0_sgrad: forward sensitivities to its inputs
+#define DSB_DIFFSL_HAS_SENS 0
+#endif
 
 // the symbol table (signatures of external-dynamic-logistic/src/lib.rs; u32 = unsigned)
 DSB_SYMBOL void set_u0(double* u, double* data, unsigned thread_id, unsigned thread_dim);
@@ -50,6 +53,12 @@ DSB_SYMBOL void calc_out(double t, const double* u, double* data, double* out, u
 #endif
 #if DSB_DIFFSL_STOP > 0
 DSB_SYMBOL void calc_stop(double t, const double* u, double* data, double* root, unsigned thread_id, unsigned thread_dim);
+#endif
+#if DSB_DIFFSL_HAS_SENS
+// forward-mode derivatives with respect to the inputs (external-dynamic-logistic/src/lib.rs:189 rhs_sgrad, :292 set_u0_sgrad)
+DSB_SYMBOL void rhs_sgrad(double t, const double* u, const double* data, double* ddata, const double* rr, double* drr,
+                          unsigned thread_id, unsigned thread_dim);
+DSB_SYMBOL void set_u0_sgrad(const double* u, double* du, const double* data, double* ddata, unsigned thread_id, unsigned thread_dim);
 #endif
 
 struct DsbDiffslModel {
@@ -100,6 +109,35 @@ struct DsbDiffslModel {
         for (int i = 0; i < N; ++i) y[i] = x[i] + beta * y[i];
 #endif
     }
+#if DSB_DIFFSL_HAS_SENS
+    static constexpr bool HAS_SENS = true;
+    // DiffSlRhs::sens_mul_inplace (diffsl.rs:1152-1168): the direction v goes into the sensitivity data block through
+    // set_inputs, then rhs_sgrad(t, x, data, sens_data, tmp, y) with tmp = the rhs scratch for this x
+    DSB_HD static void sens_mul(const double* x, const double* p, double t, const double* v, double* y) {
+        double data[NDATA], sdata[NDATA], tmp[N];
+        prepare(p, data);
+        ::rhs(t, x, data, tmp, 0u, 1u);
+#pragma unroll
+        for (int k = 0; k < NDATA; ++k) sdata[k] = 0.0;
+        ::set_inputs(v, sdata, 0u);
+#pragma unroll
+        for (int i = 0; i < N; ++i) y[i] = 0.0;
+        ::rhs_sgrad(t, x, data, sdata, tmp, y, 0u, 1u);
+    }
+    // DiffSlInit::sens_mul_inplace (diffsl.rs:737-750): set_inputs(v -> sens_data), set_u0_sgrad(u0, y, data, sens_data) into
+    // a zeroed y (ConstantOp::call allocates it with zeros)
+    DSB_HD static void init_sens(const double* p, double, const double* v, double* y) {
+        double data[NDATA], sdata[NDATA], u0[N];
+#pragma unroll
+        for (int k = 0; k < NDATA; ++k) { data[k] = 0.0; sdata[k] = 0.0; }
+        ::set_inputs(p, data, 0u);
+        ::set_u0(u0, data, 0u, 1u);
+        ::set_inputs(v, sdata, 0u);
+#pragma unroll
+        for (int i = 0; i < N; ++i) y[i] = 0.0;
+        ::set_u0_sgrad(u0, y, data, sdata, 0u, 1u);
+    }
+#endif
 #if DSB_DIFFSL_STOP > 0
     static constexpr int NROOTS = DSB_DIFFSL_STOP;
     template <class X>

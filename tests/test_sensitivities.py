@@ -411,3 +411,69 @@ def test_gpu_sensitivities_of_a_user_functor(dsb, oracle):
     dx_dK = 1.0 / (1.0 + A * e) - K * (e / x0) / (1.0 + A * e) ** 2
     assert np.abs(ys[:, :, 0] - x).max() < 1e-6
     assert np.abs(sens[:, :, 0, 0] - dx_dr).max() < 1e-5 and np.abs(sens[:, :, 1, 0] - dx_dK).max() < 1e-5
+
+
+# the reference's external logistic module (crates/diffsol-c/tests/external-dynamic-logistic/src/lib.rs) with its forward-mode
+# symbols: rhs_sgrad (:189-208) and set_u0_sgrad (:292-301, empty: u0 does not depend on the input), no out / stop functions
+LOGISTIC_DIFFSL_SENS = r"""
+#define DSB_DIFFSL_STATES 1
+#define DSB_DIFFSL_INPUTS 1
+#define DSB_DIFFSL_DATA 1
+#define DSB_DIFFSL_HAS_SENS 1
+DSB_SYMBOL void set_u0(double* u, double* data, unsigned thread_id, unsigned thread_dim) { if (u) *u = 0.1; }
+DSB_SYMBOL void rhs(double t, const double* u, double* data, double* rr, unsigned thread_id, unsigned thread_dim) {
+    if (!u || !data || !rr) return;
+    const double x = *u, r = *data;
+    *rr = r * x * (1.0 - x);
+}
+DSB_SYMBOL void rhs_grad(double t, const double* u, const double* du, const double* data, double* ddata, const double* rr,
+                         double* drr, unsigned thread_id, unsigned thread_dim) {
+    if (!u || !du || !data || !ddata || !drr) return;
+    const double x = *u, dx = *du, r = *data;
+    *drr = r * (1.0 - 2.0 * x) * dx;
+    *ddata = x * (1.0 - x);
+}
+DSB_SYMBOL void rhs_sgrad(double t, const double* u, const double* data, double* ddata, const double* rr, double* drr,
+                          unsigned thread_id, unsigned thread_dim) {
+    if (!u || !data || !ddata || !drr) return;
+    const double x = *u;
+    *drr = x * (1.0 - x) * *ddata;              // the module of the reference hard-codes d r = 1; here the seeded direction
+}
+DSB_SYMBOL void set_u0_sgrad(const double* u, double* du, const double* data, double* ddata, unsigned thread_id, unsigned thread_dim) {}
+DSB_SYMBOL void set_inputs(const double* inputs, double* data, unsigned model_index) { if (inputs && data) *data = *inputs; }
+"""
+
+
+@pytest.mark.gpu
+def test_gpu_sensitivities_of_a_diffsl_symbol_table(dsb, oracle):
+    """A DiffSL module with its forward-mode symbols (rhs_sgrad / set_u0_sgrad) as source text: DiffSlRhs::sens_mul_inplace and
+    DiffSlInit::sens_mul_inplace (ode_equations/diffsl.rs:1152-1168, 737-750) through csrc/dsb_diffsl_adapter.h.  Bit-identical
+    to the oracle (same text), and d x / d r of logistic growth."""
+    from diffsol_b200 import sweeps
+    B = 1200
+    r = (0.5 + 2.0 * sweeps.uniform(np.arange(B), 0)).reshape(-1, 1)
+    t = np.linspace(0.25, 4.0, 16)
+    solver = (dsb.OdeBuilder().rhs_implicit_source(LOGISTIC_DIFFSL_SENS, kind="diffsl").p(r).rtol(1e-8).atol(1e-10)
+              .sens_rtol(1e-8).sens_atol(1e-10).build().bdf_sens())
+    ys, sens = solver.solve_dense_sensitivities(t)
+    name = oracle.load_user_model(LOGISTIC_DIFFSL_SENS, kind="diffsl")
+    ys_o, se_o, st_o, status_o = oracle.batch_solve_dense_sens(
+        oracle.make_desc(name, rtol=1e-8, atol=1e-10, sens=True, sens_rtol=1e-8, sens_atol=1e-10, powmode=1), r, t)
+    assert np.array_equal(solver.status(), status_o) and (status_o == 0).all()
+    assert np.array_equal(solver.statistics_array()[:, :13], st_o[:, :13])
+    assert np.array_equal(ys, ys_o) and np.array_equal(sens, se_o)
+    A, e = 9.0, np.exp(-r * t[None, :])
+    assert np.abs(sens[:, :, 0, 0] - A * t[None, :] * e / (1.0 + A * e) ** 2).max() < 1e-5
+
+
+def test_oracle_sensitivities_of_a_diffsl_symbol_table(oracle):
+    """The same module on the oracle (CPU): the analytic d x / d r."""
+    name = oracle.load_user_model(LOGISTIC_DIFFSL_SENS, kind="diffsl")
+    r = np.linspace(0.5, 2.5, 9).reshape(-1, 1)
+    t = np.linspace(0.25, 4.0, 16)
+    ys, se, st, status = oracle.batch_solve_dense_sens(
+        oracle.make_desc(name, rtol=1e-8, atol=1e-10, sens=True, sens_rtol=1e-8, sens_atol=1e-10), r, t)
+    assert (status == 0).all()
+    A, e = 9.0, np.exp(-r * t[None, :])
+    assert np.abs(ys[:, :, 0] - 1.0 / (1.0 + A * e)).max() < 1e-6
+    assert np.abs(se[:, :, 0, 0] - A * t[None, :] * e / (1.0 + A * e) ** 2).max() < 1e-5
