@@ -165,12 +165,13 @@ __global__ void __launch_bounds__(128, 4) dsb_lu_solve_coop_kernel(const double*
     extern __shared__ unsigned char dsb_coop_smem[];
     CoopScratch sc;                                      // no panel here: [b (n doubles) | reduction scratch]
     sc.panel = (double*)dsb_coop_smem;
+    sc.utile = nullptr;
     sc.redv = sc.panel + n; sc.redi = (int*)(sc.redv + 32); sc.bcast = sc.redi + 32;
     double* bs = sc.panel;
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) bs[i] = rhs[(size_t)b * n + i];
         __syncthreads();
-        const bool ok = coop_lu_solve(a + (size_t)b * n * n, n, piv + (size_t)b * n, bs, sc);
+        const bool ok = coop_lu_solve(a + (size_t)b * n * n, n, piv + (size_t)b * n, bs, sc, false);     // no panel scratch in this kernel
         for (int i = threadIdx.x; i < n; i += blockDim.x) rhs[(size_t)b * n + i] = bs[i];
         if (threadIdx.x == 0) info[b] = ok ? 0 : 1;
         __syncthreads();
@@ -208,7 +209,7 @@ inline cudaError_t dsb_launch_lu_solve_im(const double* a, const int32_t* piv, d
                                           cudaStream_t s) {
     if (n > DSB_COOP_MAX_N) return cudaErrorInvalidValue;
     const int threads = dsb_coop_threads(n);
-    const size_t smem = coop_lu_smem_bytes_host(n) - (size_t)n * (DSB_COOP_NB - 1) * sizeof(double);   // only b, no panel
+    const size_t smem = coop_lu_smem_bytes_host(n) - ((size_t)n * (DSB_COOP_NB - 1) + DSB_COOP_UT_WORDS) * sizeof(double);   // only b: no panel, no U tiles
     unsigned grid = 1;
     cudaError_t e = dsb_coop_grid((const void*)dsb_lu_solve_coop_kernel, threads, smem, B, &grid);
     if (e != cudaSuccess) return e;
