@@ -67,7 +67,7 @@ static int build_problem(const orc_problem_desc* d, const double* p, int np, Pro
     if (pr->use_coloring) pr->build_coloring();
     pr->sens = d->sens != 0;
     if (pr->sens) {
-        if (!pr->model.sens_mul || d->method != 0) return ST_BAD_ARG;     // the BDF restatement only
+        if (!pr->model.sens_mul) return ST_BAD_ARG;
         pr->sens_error_control = d->sens_natol != 0;
         pr->sens_rtol = d->sens_rtol;
         pr->sens_atol.assign(n, 0.0);

@@ -87,6 +87,12 @@ struct Sdirk : Method {
     RootFinder root_finder;
     double root_t_ = 0.0; int root_idx_ = -1;
     bool is_state_mutated = false;                         // runge_kutta.rs:50: set by state_mut() (:391-394)
+    // forward sensitivities (Sdirk<.., SensEquations>, sdirk.rs:222-255; Rk: runge_kutta.rs:46, 518-523, 691-745, 812-822,
+    // 917-920, 1237-1310): per parameter a stage-increment array, state.s / ds and their old_state twins; the sensitivity
+    // residual SdirkCallable<SensEquations> has its own phi, shares c and h with the main one
+    int ns = 0;
+    std::vector<Vec> s_, ds_, os_, ods_, sdiff;
+    Vec phi_s, sens_S, sens_y, sens_error;
 
     Sdirk(const Problem& p, const Tableau& t) : pr(p), n(p.n()), tab(t) {}
 
@@ -118,7 +124,61 @@ struct Sdirk : Method {
         if (!pr.model.has_mass) pr.mass_matrix(t_, mass_jac.data());     // identity
         jacobian_is_stale = true;
         is_jacobian_set = false;
+        if (pr.sens) {
+            // RkState::new_with_sensitivities_and_consistent (state.rs:1032-1080): as for Bdf; Sdirk::new_augmented ends with
+            // jacobian_updates(h, Checkpoint) (sdirk.rs:252), so the first LU is NOT the lazy one of the first stage
+            if (!pr.model.sens_mul || !pr.model.init_sens) return ST_BAD_ARG;
+            ns = pr.model.np;
+            s_.assign(ns, Vec(n, 0.0)); ds_ = s_; os_ = s_; ods_ = s_;
+            sdiff.assign(ns, Vec((size_t)n * tab.s, 0.0));
+            phi_s.assign(n, 0.0); sens_y.assign(n, 0.0); sens_S.assign((size_t)n * ns, 0.0); sens_error.assign(n, 0.0);
+            Vec e(ns, 0.0);
+            for (int j = 0; j < ns; ++j) {
+                e[j] = 1.0;
+                pr.model.init_sens(pr.p.data(), pr.t0, e.data(), s_[j].data());
+                e[j] = 0.0;
+            }
+            update_rhs_out_state(y_.data(), t_);
+            for (int j = 0; j < ns; ++j) sens_rhs(j, s_[j].data(), t_, ds_[j].data());
+            if (pr.model.has_mass) {
+                Convergence ic_conv;
+                ic_conv.init(pr.rtol, pr.atol.data(), n, pr.opt.nonlinear_solver_tolerance, &pr.math);
+                ic_conv.max_iter = pr.opt.ic_max_newton_iterations;
+                for (int j = 0; j < ns; ++j) {
+                    int e2 = consistent_solve(pr, [this, j](const double* x, double tt, double* out) { sens_rhs(j, x, tt, out); },
+                                              [this](const double*, double tt, double* J) { pr.jacobian(sens_y.data(), tt, J); },
+                                              s_[j], ds_[j], &ic_conv, false);
+                    if (e2) return e2;
+                }
+            }
+            os_ = s_; ods_ = ds_;                              // old_state = state.clone()
+            jacobian_updates(h_, CHECKPOINT);
+        }
         return ST_OK;
+    }
+
+    // SensRhs::update_state / call_inplace (ode_equations/sens_equations.rs:129-134, 168-174), as in the Bdf restatement
+    void update_rhs_out_state(const double* y, double t) {
+        Vec v(ns, 0.0);
+        for (int j = 0; j < ns; ++j) {
+            v[j] = 1.0;
+            pr.model.sens_mul(y, pr.p.data(), t, v.data(), sens_S.data() + (size_t)j * n);
+            v[j] = 0.0;
+        }
+        for (int k = 0; k < n; ++k) sens_y[k] = y[k];
+    }
+    void sens_rhs(int index, const double* x, double t, double* out) const {
+        pr.jac_mul(sens_y.data(), t, x, out);
+        const double* col = sens_S.data() + (size_t)index * n;
+        for (int k = 0; k < n; ++k) out[k] += col[k];
+    }
+    // SdirkCallable<SensEquations>::call_inplace (op/sdirk.rs:231-245): F(x) = M x - h rhs_s(phi_s + c x)
+    void callable_sens(int index, const double* x, double t, double* out) {
+        for (int i = 0; i < n; ++i) tmp[i] = c * x[i] + phi_s[i];
+        sens_rhs(index, tmp.data(), t, out);
+        const double beta = -op_h;
+        if (pr.model.has_mass) pr.mass_gemv(x, t, beta, out);
+        else for (int i = 0; i < n; ++i) out[i] = x[i] + beta * out[i];
     }
 
     // SdirkCallable::jacobian_inplace (op/sdirk.rs:257-292) + NalgebraLU::set_linearisation
@@ -163,10 +223,11 @@ struct Sdirk : Method {
         else for (int i = 0; i < n; ++i) out[i] = x[i] + beta * out[i];     // y.axpy(1, x, beta): 1*x*1 + beta*y
     }
 
-    bool newton_solve(Vec& xn, double t, const Vec& error_y) {
+    bool newton_solve(Vec& xn, double t, const Vec& error_y, int sens_index = -1) {
         convergence.reset();
         for (int it = 0; it < convergence.max_iter; ++it) {
-            callable(xn.data(), t, newton_tmp.data());
+            if (sens_index >= 0) callable_sens(sens_index, xn.data(), t, newton_tmp.data());
+            else callable(xn.data(), t, newton_tmp.data());
             if (!lu.solve(newton_tmp.data())) return false;
             for (int i = 0; i < n; ++i) xn[i] -= newton_tmp[i];
             double norm = convergence.norm(newton_tmp.data(), error_y.data());
@@ -207,6 +268,34 @@ struct Sdirk : Method {
         // get_f_eval: y_stage = phi + c x
         for (int k = 0; k < n; ++k) oy_[k] = c * ody_[k] + phi[k];
         for (int k = 0; k < n; ++k) DC(i)[k] = ody_[k];
+        // the sensitivity equations of the stage (runge_kutta.rs:691-745): f_p at the stage value, then per parameter the
+        // same set_phi / predict / Newton solve / get_f_eval on sdiff[j], state.s[j], state.ds[j]; the iterations of a failed
+        // solve ARE counted here (the statistics line precedes the `?`)
+        if (ns > 0) {
+            update_rhs_out_state(oy_.data(), t);
+            for (int j = 0; j < ns; ++j) {
+                double* sd = sdiff[j].data();
+                for (int k = 0; k < n; ++k) phi_s[k] = s_[j][k];
+                for (int q = 0; q < i; ++q) {
+                    const double aiq = tab.A(i, q);
+                    for (int k = 0; k < n; ++k) phi_s[k] = sd[(size_t)q * n + k] * aiq + phi_s[k];
+                }
+                if (i == 0) {
+                    for (int k = 0; k < n; ++k) ods_[j][k] = h * ds_[j][k];
+                } else if (i == 1) {
+                    for (int k = 0; k < n; ++k) ods_[j][k] = sd[k];
+                } else {
+                    const double cc = (tab.c[i] - tab.c[i - 2]) / (tab.c[i - 1] - tab.c[i - 2]);
+                    const double al = -cc, be = 1.0 + cc;
+                    for (int k = 0; k < n; ++k) ods_[j][k] = al * sd[(size_t)(i - 2) * n + k] + be * sd[(size_t)(i - 1) * n + k];
+                }
+                const bool oks = newton_solve(ods_[j], t, s_[j], j);
+                statistics.v[S_NL_ITERS] += convergence.niter;
+                if (!oks) return false;
+                for (int k = 0; k < n; ++k) os_[j][k] = c * ods_[j][k] + phi_s[k];
+                for (int k = 0; k < n; ++k) sd[(size_t)i * n + k] = ods_[j][k];
+            }
+        }
         return true;
     }
 
@@ -258,7 +347,11 @@ struct Sdirk : Method {
         const int start = (tab.A(0, 0) == 0.0) ? 1 : 0;
         double factor = 1.0, error_norm = 0.0;
         while (true) {
-            if (start == 1) for (int k = 0; k < n; ++k) DC(0)[k] = h * dy_[k];     // start_step_attempt
+            if (start == 1) {                                                      // start_step_attempt
+                for (int k = 0; k < n; ++k) DC(0)[k] = h * dy_[k];
+                for (int j = 0; j < ns; ++j)
+                    for (int k = 0; k < n; ++k) sdiff[j][k] = h * ds_[j][k];
+            }
             bool failed = false;
             for (int i = start; i < tab.s; ++i) {
                 if (!do_stage(i, h)) { failed = true; break; }
@@ -297,6 +390,16 @@ struct Sdirk : Method {
                 double e = squared_norm(error.data(), y_.data(), pr.atol.data(), pr.rtol, n);
                 error_norm = (0.0 < e) ? e : 0.0;             // 0.max(err)
             }
+            if (pr.sens_error_control) {                      // sdiff[j] . d, NOT filtered through the LU (runge_kutta.rs:812-822)
+                for (int j = 0; j < ns; ++j) {
+                    const double* sd = sdiff[j].data();
+                    for (int k = 0; k < n; ++k) sens_error[k] = sd[k] * tab.d[0];
+                    for (int q = 1; q < tab.s; ++q)
+                        for (int k = 0; k < n; ++k) sens_error[k] = sd[(size_t)q * n + k] * tab.d[q] + sens_error[k];
+                    const double es = squared_norm(sens_error.data(), s_[j].data(), pr.sens_atol.data(), pr.sens_rtol, n);
+                    error_norm = (error_norm < es) ? es : error_norm;
+                }
+            }
             const double maxiter = (double)convergence.max_iter;
             const double niter = (double)convergence.niter;
             const double safety_factor = (2.0 * maxiter + 1.0) / (2.0 * maxiter + niter);
@@ -326,8 +429,11 @@ struct Sdirk : Method {
         {
             const double inv_h = 1.0 / h;
             for (int k = 0; k < n; ++k) ody_[k] *= inv_h;
+            for (int j = 0; j < ns; ++j)
+                for (int k = 0; k < n; ++k) ods_[j][k] *= inv_h;
         }
         std::swap(y_, oy_); std::swap(dy_, ody_); std::swap(t_, ot_); std::swap(h_, oh_);
+        std::swap(s_, os_); std::swap(ds_, ods_);
         statistics.v[S_STEPS] += 1;
         // check for a root within the accepted step (runge_kutta.rs:935-948)
         if (pr.model.nroots > 0) {
@@ -387,6 +493,46 @@ struct Sdirk : Method {
                 for (int k = 0; k < n; ++k) y[k] = al * oy_[k] + be * y[k];
             }
             for (int k = 0; k < n; ++k) y[k] = theta * y_[k] + y[k];
+        }
+        return ST_OK;
+    }
+
+    // runge_kutta.rs:1237-1310: the same dense output on (old_state.s[j], state.s[j], sdiff[j])
+    int interpolate_sens(double t, double* out) const override {
+        if (ns == 0 || is_state_mutated) return ST_BAD_ARG;
+        const bool is_forward = h_ > 0.0;
+        if ((is_forward && (t > t_ || t < ot_)) || (!is_forward && (t < t_ || t > ot_)))
+            return ST_INTERPOLATION_TIME_AFTER_CURRENT;
+        const double dt = t_ - ot_;
+        const double theta = (dt == 0.0) ? 1.0 : (t - ot_) / dt;
+        for (int j = 0; j < ns; ++j) {
+            double* y = out + (size_t)j * n;
+            const double* sd = sdiff[j].data();
+            if (tab.has_beta) {
+                const int s = tab.s;
+                const double th1 = theta, th2 = theta * theta;
+                Vec beta_f(s);
+                for (int k = 0; k < s; ++k) beta_f[k] = tab.beta[k] * th1;
+                for (int k = 0; k < s; ++k) beta_f[k] = tab.beta[(size_t)s + k] * th2 + beta_f[k];
+                for (int k = 0; k < n; ++k) y[k] = os_[j][k];
+                for (int q = 0; q < s; ++q)
+                    for (int k = 0; k < n; ++k) y[k] = sd[(size_t)q * n + k] * beta_f[q] + y[k];
+            } else {
+                const double* f0 = sd;
+                const double* f1 = sd + (size_t)(tab.s - 1) * n;
+                for (int k = 0; k < n; ++k) y[k] = s_[j][k];
+                for (int k = 0; k < n; ++k) y[k] -= os_[j][k];
+                {
+                    const double al = theta - 1.0, be = 1.0 - 2.0 * theta;
+                    for (int k = 0; k < n; ++k) y[k] = al * f0[k] + be * y[k];
+                }
+                for (int k = 0; k < n; ++k) y[k] = theta * f1[k] + y[k];
+                {
+                    const double al = 1.0 - theta, be = theta * (theta - 1.0);
+                    for (int k = 0; k < n; ++k) y[k] = al * os_[j][k] + be * y[k];
+                }
+                for (int k = 0; k < n; ++k) y[k] = theta * s_[j][k] + y[k];
+            }
         }
         return ST_OK;
     }

@@ -2,9 +2,10 @@
 (/root/reference/crates/diffsol/src/ode_solver/bdf.rs:934-989), the sensitivity terms of the error test (:844-858, 908-919),
 interpolate_sens (:1162-1215) and solve_dense_sensitivities (ode_solver/sensitivities.rs:205-262).
 
-CPU tests pin the ORACLE: every counter of THREE of the reference's sensitivity snapshots (bdf_test_nalgebra_exponential_
-decay_sens, bdf.rs:1812-1834; test_bdf_nalgebra_exponential_decay_algebraic_sens, :2118-2140; test_bdf_nalgebra_robertson_sens,
-:2248-2271 -- the last with 28 failed Newton solves), the reference's acceptance measures for the state (< 20) and
+CPU tests pin the ORACLE: every counter of SEVEN of the reference's eight nalgebra sensitivity snapshots -- BDF: bdf_test_
+nalgebra_exponential_decay_sens (bdf.rs:1812-1834), test_bdf_nalgebra_exponential_decay_algebraic_sens (:2118-2140),
+test_bdf_nalgebra_robertson_sens (:2248-2271, 28 failed Newton solves); TR-BDF2 and ESDIRK34: exponential decay and the
+Robertson DAE (sdirk.rs:708-730, 783-805, 895-918, 946-969) -- the reference's acceptance measures for the state (< 20) and
 the sensitivities (< 29, ode_solver/mod.rs:164-187) against the analytic solution, and the kernel SOURCE (host emulation of
 the DsbWithSens<M> instantiation of the on-chip BDF lane kernel) bit for bit against the oracle.
 GPU tests: the CUDA path through the C ABI (dsb_batch_solve_dense_sensitivities_host) bit-identical to the oracle.
@@ -81,6 +82,38 @@ def test_dae_sens_snapshots(oracle, powmode):
         w = np.abs(ystar[k]) * 1e-4 + np.array([1e-8, 1e-6, 1e-6])
         assert math.sqrt(np.mean(((ys[k] - ystar[k]) / w) ** 2)) < 20.0
     assert np.abs(sens.sum(axis=-1)).max() < 1e-6 * np.abs(sens).max()      # the constraint y1 + y2 + y3 = 1, differentiated
+
+
+# (E)SDIRK (Rk::do_stage_sdirk's sensitivity part, runge_kutta.rs:691-745; the sensitivity error, :812-822): sdirk.rs:708-730,
+# 783-805 (exponential decay, sensitivities in the error test) and :895-918, 946-969 (Robertson DAE, 30 resp. 10 failed solves)
+SDIRK_SENS_SNAPSHOTS = {
+    ("tr_bdf2", "exp_decay"): [10, 1, 0, 0, 0, 9, 90, 0, 620, 0, 207, 421, 2],
+    ("esdirk34", "exp_decay"): [6, 1, 0, 0, 0, 5, 33, 0, 347, 0, 107, 246, 1],
+    ("tr_bdf2", "robertson_dae"): [77, 1, 29, 1, 0, 46, 286, 0, 4146, 30, 1303, 2954, 34],
+    ("esdirk34", "robertson_dae"): [68, 1, 8, 2, 0, 57, 333, 0, 6856, 10, 2272, 4644, 17],
+}
+
+
+def sdirk_sens_case(oracle, method, model, powmode):
+    if model == "exp_decay":
+        d = oracle.make_desc("exp_decay", method=method, sens=True, sens_rtol=1e-6, sens_atol=[1e-6, 1e-6], powmode=powmode)
+        return d, [0.1, 1.0], np.arange(10.0)
+    opts = dict(max_nonlinear_solver_iterations=10) if method == "tr_bdf2" else None
+    d = oracle.make_desc("robertson_dae", method=method, rtol=1e-4, atol=[1e-8, 1e-6, 1e-6], sens=True, powmode=powmode, options=opts)
+    return d, [0.04, 1e4, 3e7], np.array(GOLD["robertson_dae_points"]["t"])
+
+
+@pytest.mark.parametrize("powmode", [0, 1], ids=["libm_pow", "dsb_pow"])
+@pytest.mark.parametrize("method,model", sorted(SDIRK_SENS_SNAPSHOTS))
+def test_sdirk_sens_snapshots(oracle, method, model, powmode):
+    d, p, t = sdirk_sens_case(oracle, method, model, powmode)
+    rc, ys, sens, stats, fin = oracle.harness_sens(d, p, t)
+    assert rc == 0 and list(stats.values())[:13] == SDIRK_SENS_SNAPSHOTS[(method, model)]
+    if model == "exp_decay":
+        y = np.exp(-0.1 * t)
+        for k in range(len(t)):
+            for got, want, bound in ((ys[k], np.full(2, y[k]), 20.0), (sens[k, 0], np.full(2, -t[k] * y[k]), 29.0), (sens[k, 1], np.full(2, y[k]), 29.0)):
+                assert math.sqrt(np.mean(((got - want) / (np.abs(want) * 1e-6 + 1e-6)) ** 2)) < bound
 
 
 def test_sensitivities_without_error_control_follow_the_plain_run(oracle):
