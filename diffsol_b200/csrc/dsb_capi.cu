@@ -483,7 +483,7 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     if (lerr == cudaErrorNotSupported && pa.ragged)
         return fail(DSB_ERR, "solve(final_time) is built for the thread-per-instance kernels: n <= 16, no reset function, no sensitivities");
     if (lerr == cudaErrorNotSupported && b->prob.sens)
-        return fail(DSB_ERR, "forward sensitivities are built for BDF on equation sets with sens_mul / init_sens, no root / output / reset function and n <= 16");
+        return fail(DSB_ERR, "forward sensitivities are built for equation sets with sens_mul / init_sens, no root / output / reset function and n <= 16");
     if (lerr == cudaErrorNotSupported) return fail(DSB_ERR, "this execution mode is not available for this equation set and method (thread per instance: n <= 16; banded thread per instance: component-wise equations with a declared band, n > 16; banded warp per instance: the same, BDF, no reset function; block per instance: n <= 512)");
     if (lerr != cudaSuccess) return fail(DSB_ERR, std::string("kernel launch: ") + cudaGetErrorString(lerr));
     if (b->coop.ys_im_used) {

@@ -422,7 +422,7 @@ template <class M> struct LaneLauncher<M, true> {
     }
 };
 
-// forward sensitivities (problem.bdf_sens(), solve_dense_sensitivities): the on-chip BDF lane kernel instantiated for
+// forward sensitivities (problem.bdf_sens() / tr_bdf2_sens() / esdirk34_sens(), solve_dense_sensitivities): the on-chip lane kernels instantiated for
 // DsbWithSens<M> -- ODEs and DAEs of n <= 16 that provide sens_mul / init_sens and have no root / output / reset functions
 template <class M, bool LANE> struct SensCapable : std::false_type {};
 template <class M> struct SensCapable<M, true>
@@ -430,32 +430,35 @@ template <class M> struct SensCapable<M, true>
                          !dsb_model_nout<M>::has_out && !dsb_model_has_reset<M>::value> {};
 constexpr bool kSensCapable = SensCapable<InstModel, kLaneCapable>::value;
 template <class M, bool OK> struct SensLauncher {
-    static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, cudaStream_t, cudaEvent_t, unsigned long long*, int*) {
+    static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, int, cudaStream_t, cudaEvent_t, unsigned long long*, int*) {
         return cudaErrorNotSupported;
     }
 };
 template <class M> struct SensLauncher<M, true> {
-    static cudaError_t run(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, cudaStream_t stream, cudaEvent_t mid,
+    static cudaError_t run(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method, cudaStream_t stream, cudaEvent_t mid,
                            unsigned long long* work_counter, int* launches) {
         typedef DsbWithSens<M> MS;
-        const int threads = BdfLayout<MS>::THREADS;
-        const size_t smem = (size_t)BdfLayout<MS>::WORDS * threads * sizeof(double);
-        cudaError_t e = cudaFuncSetAttribute(dsb_bdf_solve_dense_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const bool bdf = method == DSB_METHOD_BDF;
+        const int threads = bdf ? BdfLayout<MS>::THREADS : SdirkLayout<MS>::THREADS;
+        const size_t smem = (size_t)(bdf ? BdfLayout<MS>::WORDS : SdirkLayout<MS>::WORDS) * threads * sizeof(double);
+        const void* kernel = bdf ? (const void*)dsb_bdf_solve_dense_kernel<MS> : (const void*)dsb_sdirk_solve_dense_kernel<MS>;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dsb_bdf_solve_dense_kernel<MS>, threads, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         e = cudaMemsetAsync(work_counter, 0, 32 * sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return e;
         const unsigned init_blocks = (unsigned)((pa->nbatch + DSB_LANE_THREADS - 1) / DSB_LANE_THREADS);
-        dsb_init_kernel<M><<<init_blocks, DSB_LANE_THREADS, 0, stream>>>(*pa, *bb, 1);
+        dsb_init_kernel<M><<<init_blocks, DSB_LANE_THREADS, 0, stream>>>(*pa, *bb, bdf ? 1 : pa->rk.order);
         if (mid) cudaEventRecord(mid, stream);
         const unsigned blocks = (unsigned)((pa->nbatch + threads - 1) / threads);
         const unsigned grid = blocks < (unsigned)(sms * per_sm) ? blocks : (unsigned)(sms * per_sm);
-        dsb_bdf_solve_dense_kernel<MS><<<grid, threads, smem, stream>>>(*pa, *bb, work_counter);
+        if (bdf) dsb_bdf_solve_dense_kernel<MS><<<grid, threads, smem, stream>>>(*pa, *bb, work_counter);
+        else dsb_sdirk_solve_dense_kernel<MS><<<grid, threads, smem, stream>>>(*pa, *bb, work_counter);
         *launches += 2;
         return cudaGetLastError();
     }
@@ -513,8 +516,8 @@ cudaError_t DSB_LAUNCH_SYMBOL(const DsbProblemArgs* pa, const DsbBatchBuffers* b
         return RaggedLauncher<InstModel, kRaggedCapable>::run(pa, bb, method, stream, mid, work_counter, launches);
     }
     if (pa->sens) {
-        if (method != DSB_METHOD_BDF || !bb->ss) return cudaErrorNotSupported;
-        return SensLauncher<InstModel, kSensCapable>::run(pa, bb, stream, mid, work_counter, launches);
+        if (!bb->ss) return cudaErrorNotSupported;
+        return SensLauncher<InstModel, kSensCapable>::run(pa, bb, method, stream, mid, work_counter, launches);
     }
     // exec_mode 4 / automatic: the warp-per-instance banded kernel (BDF, no reset function)
     if (kWBandCapable && method == DSB_METHOD_BDF && (coop->exec_mode == 4 || (coop->exec_mode == 0 && kWBandPreferred))) {

@@ -22,6 +22,7 @@
 // Newton iteration count of the last stage only; the error estimate is filtered through the LU.
 #pragma once
 #include "dsb_lane.cuh"
+#include "dsb_init_kernel.cuh"      // lane_consistent_solve: consistent sensitivities of a DAE
 #include "dsb_roots.cuh"
 
 enum dsb_rk_lane_state {
@@ -43,7 +44,17 @@ struct SdirkLayout {
     static constexpr int O_PHI = O_OY + N;                          // SdirkCallable.phi
     static constexpr int O_P = O_PHI + N;                           // parameters
     static constexpr int O_ST = O_P + (NP > 0 ? NP : 1);            // statistics, two int32 per word
-    static constexpr int WORDS = O_ST + (DSB_NSTATS + 1) / 2;
+    // forward sensitivities (DsbWithSens<M> only; Rk: runge_kutta.rs:46, 518-523, 691-745, 812-822, 917-920): per parameter the
+    // stage increments, state.s / state.ds, old_state.s (the stage value, then the previous step's s) and the column of f_p at
+    // the stage value; phi of the sensitivity residual
+    static constexpr bool SENS = dsb_model_sens_on<M>::value;
+    static constexpr int O_SSD = O_ST + (DSB_NSTATS + 1) / 2;       // sdiff[NP][DSB_RK_MAX_STAGES][N]
+    static constexpr int O_SS = O_SSD + NP * DSB_RK_MAX_STAGES * N; // state.s[NP][N]
+    static constexpr int O_SDS = O_SS + NP * N;                     // state.ds[NP][N]
+    static constexpr int O_SOS = O_SDS + NP * N;                    // old_state.s[NP][N]
+    static constexpr int O_SFP = O_SOS + NP * N;                    // f_p e_q at the stage value [NP][N]
+    static constexpr int O_SPH = O_SFP + NP * N;                    // phi of SdirkCallable<SensEquations>
+    static constexpr int WORDS = SENS ? O_SPH + N : O_SSD;
     static constexpr int THREADS = LaneBlockShape<WORDS, N>::THREADS;
     static constexpr int MAXNREG = LaneBlockShape<WORDS, N>::MAXNREG;
 };
@@ -69,6 +80,17 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
 #define SOY(i) SM(Lay::O_OY + (i))
 #define SPHI(i) SM(Lay::O_PHI + (i))
 #define SP(i) SM(Lay::O_P + (i))
+#define SSD(q, j, i) SM(Lay::O_SSD + ((q) * DSB_RK_MAX_STAGES + (j)) * N + (i))
+#define SSS(q, i) SM(Lay::O_SS + (q) * N + (i))
+#define SDS(q, i) SM(Lay::O_SDS + (q) * N + (i))
+#define SOS(q, i) SM(Lay::O_SOS + (q) * N + (i))
+#define SFP(q, i) SM(Lay::O_SFP + (q) * N + (i))
+#define SPHS(i) SM(Lay::O_SPH + (i))
+    constexpr bool SENS = Lay::SENS;
+    static_assert(!SENS || (dsb_model_has_sens<M>::value && dsb_model_nroots<M>::value == 0 &&
+                            !dsb_model_nout<M>::has_out && !dsb_model_has_reset<M>::value),
+                  "sensitivities: equations with sens_mul / init_sens, no root / output / reset functions");
+    int eq = 0;            // sensitivities: which equation the Newton block is solving (0 = the state, q + 1 = sensitivity q)
 
     const int64_t B = pa.nbatch;
     const int nt = pa.nt;
@@ -192,6 +214,52 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
         }
         return 0;
     };
+    // ---- sensitivities (only instantiated for DsbWithSens<M>) ----
+    // f_p e_q at (x, tq) for every parameter: SensRhs::update_state (sens_equations.rs:129-134)
+    auto sens_update_state = [&](const double (&x)[N], double tq) {
+        if constexpr (SENS) {
+            double pl_[NP > 0 ? NP : 1], e[NP > 0 ? NP : 1], colv[N];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) { pl_[j] = SP(j); e[j] = 0.0; }
+#pragma unroll 1
+            for (int q = 0; q < NP; ++q) {
+#pragma unroll
+                for (int j = 0; j < NP; ++j) e[j] = (j == q) ? 1.0 : 0.0;
+                M::sens_mul(x, pl_, tq, e, colv);
+#pragma unroll
+                for (int i = 0; i < N; ++i) SFP(q, i) = colv[i];
+            }
+        }
+    };
+    // the start of stage `stage`'s Newton solve for sensitivity q (runge_kutta.rs:698-716): set_phi on sdiff[q] / state.s[q],
+    // predict_stage_sdirk on state.ds[q] / sdiff[q]
+    auto sens_stage_setup = [&](int q) {
+        const int i = stage;
+        double ph[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) ph[k] = SSS(q, k);
+#pragma unroll 1
+        for (int j = 0; j < i; ++j) {
+            const double aij = pa.rk.a[j * ns + i];
+#pragma unroll
+            for (int k = 0; k < N; ++k) ph[k] = SSD(q, j, k) * aij + ph[k];
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) SPHS(k) = ph[k];
+        if (i == 0) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) x_cur[k] = h * SDS(q, k);
+        } else if (i == 1) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) x_cur[k] = SSD(q, 0, k);
+        } else {
+            const double cc = DSB_DIV(pa.rk.c[i] - pa.rk.c[i - 2], pa.rk.c[i - 1] - pa.rk.c[i - 2]);
+            const double al = -cc, be = 1.0 + cc;
+#pragma unroll
+            for (int k = 0; k < N; ++k) x_cur[k] = al * SSD(q, i - 2, k) + be * SSD(q, i - 1, k);
+        }
+        conv.reset();
+    };
 
     while (true) {
         // ---- warp-level block scheduler (see dsb_bdf_kernel.cuh) ------------------------------------------
@@ -250,6 +318,63 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                     rf.t0 = t; root_found = -1;
                 }
                 state = R_TSTOP;
+                if constexpr (SENS) {
+                    // RkState::new_with_sensitivities_and_consistent (state.rs:1032-1080) as in the Bdf kernel: s_q = (d y0 / d p)
+                    // e_q, ds_q = J(y0) s_q + f_p e_q, for a DAE the InitOp solve on SensRhs; then Sdirk::new_augmented's
+                    // jacobian_updates(h, Checkpoint) (sdirk.rs:252): the first LU is NOT the lazy one of the first stage
+                    double y0l[N], pl0[NP > 0 ? NP : 1], e[NP > 0 ? NP : 1], sq[N], dsq[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) y0l[i] = SY(i);
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) { pl0[j] = SP(j); e[j] = 0.0; }
+                    sens_update_state(y0l, t);
+#pragma unroll 1
+                    for (int q = 0; q < NP; ++q) {
+#pragma unroll
+                        for (int j = 0; j < NP; ++j) e[j] = (j == q) ? 1.0 : 0.0;
+                        M::init_sens(pl0, pa.t0, e, sq);
+                        M::jac_mul(y0l, pl0, t, sq, dsq);
+                        st.v[DSB_STAT_RHS_JAC_MULS] += 1;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) { dsq[i] += SFP(q, i); SSS(q, i) = sq[i]; SDS(q, i) = dsq[i]; }
+#pragma unroll 1
+                        for (int j = 0; j < DSB_RK_MAX_STAGES; ++j)
+#pragma unroll
+                            for (int i = 0; i < N; ++i) SSD(q, j, i) = 0.0;
+                    }
+                    int ic_status = DSB_STATUS_OK;
+                    if constexpr (M::HAS_MASS) {
+                        LaneConvergence ic_conv;
+                        ic_conv.tol = pa.opt.nonlinear_solver_tolerance;
+                        ic_conv.eta = pa.tab.eta_reset;
+                        ic_conv.max_iter = pa.opt.ic_max_newton_iterations;
+                        ic_conv.reset();
+#pragma unroll 1
+                        for (int q = 0; q < NP && ic_status == DSB_STATUS_OK; ++q) {
+#pragma unroll
+                            for (int i = 0; i < N; ++i) { sq[i] = SSS(q, i); dsq[i] = SDS(q, i); }
+                            ic_status = lane_consistent_solve<M>(pa, pl0, sq, dsq,
+                                [&](const double (&x)[N], double (&out)[N]) {
+                                    M::jac_mul(y0l, pl0, t, x, out);
+                                    st.v[DSB_STAT_RHS_JAC_MULS] += 1;
+#pragma unroll
+                                    for (int i = 0; i < N; ++i) out[i] += SFP(q, i);
+                                },
+                                [&](double (&J)[N][N]) {
+                                    lane_jacobian_to<M>(pa, y0l, pl0, t, st, [&](int j, int i, double val) { J[j][i] = val; });
+                                }, ic_conv, false);
+#pragma unroll
+                            for (int i = 0; i < N; ++i) { SSS(q, i) = sq[i]; SDS(q, i) = dsq[i]; }
+                        }
+                    }
+#pragma unroll 1
+                    for (int q = 0; q < NP; ++q)
+#pragma unroll
+                        for (int i = 0; i < N; ++i) SOS(q, i) = SSS(q, i);          // old_state = state.clone()
+                    eq = 0;
+                    if (ic_status != DSB_STATUS_OK) finish(ic_status);
+                    else { jac_kind = DSB_CHECKPOINT; jac_h = h_state; after_jac = R_TSTOP; state = R_JAC; }
+                }
             }
         }
 
@@ -294,6 +419,30 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                 }
                 const double e = DSB_DIV(acc, (double)N);
                 error_norm = (0.0 < e) ? e : 0.0;
+                if constexpr (SENS) {               // sdiff[q] . d, NOT filtered through the LU (runge_kutta.rs:812-822)
+                    if (pa.sens_error_control) {
+#pragma unroll 1
+                        for (int q = 0; q < NP; ++q) {
+                            double es[N];
+#pragma unroll
+                            for (int k = 0; k < N; ++k) es[k] = SSD(q, 0, k) * pa.rk.d[0];
+#pragma unroll 1
+                            for (int j = 1; j < ns; ++j) {
+                                const double dj = pa.rk.d[j];
+#pragma unroll
+                                for (int k = 0; k < N; ++k) es[k] = SSD(q, j, k) * dj + es[k];
+                            }
+                            double accs = 0.0;
+#pragma unroll
+                            for (int i = 0; i < N; ++i) {
+                                const double term = DSB_DIV(es[i], dsb_abs(SSS(q, i)) * pa.sens_rtol + pa.sens_atol[i]);
+                                accs += term * term;
+                            }
+                            const double en = DSB_DIV(accs, (double)N);
+                            error_norm = (error_norm < en) ? en : error_norm;
+                        }
+                    }
+                }
                 const double maxiter = (double)conv.max_iter;
                 const double niter = (double)conv.niter;
                 const double safety_factor = DSB_DIV(2.0 * maxiter + 1.0, 2.0 * maxiter + niter);
@@ -384,7 +533,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                 is_jacobian_set = true;
             }
             state = after_jac;
-            if (jac_kind != DSB_KIND_LAZY && jac_kind != DSB_STEP_SUCCESS) {
+            if (jac_kind != DSB_KIND_LAZY && jac_kind != DSB_STEP_SUCCESS && jac_kind != DSB_CHECKPOINT) {
                 // the failure paths continue after jacobian_updates (sdirk.rs:464-471, 524-529)
                 has_prev_error = false;
                 if (jac_kind == DSB_ERROR_TEST_FAIL) {
@@ -415,8 +564,21 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                 const double y_new = SOY(i);                 // old_state.y held the last stage value
                 SOY(i) = SY(i);                              // swap: old_state <- previous state
                 SY(i) = y_new;
-                SDY(i) = x_cur[i] * inv_h;                   // old_state.dy *= 1/h, then swapped in
+                // old_state.dy *= 1/h, then swapped in (the last stage's increment; with sensitivities x_cur has moved on)
+                SDY(i) = (SENS ? SDF(ns - 1, i) : x_cur[i]) * inv_h;
                 wt[i] = dsb_abs(y_new) * pa.rtol + pa.atol[i];
+            }
+            if constexpr (SENS) {
+#pragma unroll 1
+                for (int q = 0; q < NP; ++q) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const double s_new = SOS(q, i);          // old_state.s held the last stage value
+                        SOS(q, i) = SSS(q, i);
+                        SSS(q, i) = s_new;
+                        SDS(q, i) = SSD(q, ns - 1, i) * inv_h;
+                    }
+                }
             }
             st.v[DSB_STAT_STEPS] += 1;
             state = R_TSTOP;
@@ -544,6 +706,41 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                 double yo[N];
                 interpolate(tq, yo);
                 write_column(col, tq, yo);
+                if constexpr (SENS) {               // interpolate_sens (runge_kutta.rs:1237-1310) on (old_state.s, state.s, sdiff)
+                    const double dt = t - old_t;
+                    const double theta = (dt == 0.0) ? 1.0 : DSB_DIV(tq - old_t, dt);
+#pragma unroll 1
+                    for (int q = 0; q < NP; ++q) {
+                        if (pa.rk.has_beta) {
+                            const double th2 = theta * theta;
+#pragma unroll
+                            for (int i = 0; i < N; ++i) yo[i] = SOS(q, i);
+#pragma unroll 1
+                            for (int j = 0; j < ns; ++j) {
+                                double bf = pa.rk.beta[j] * theta;
+                                bf = pa.rk.beta[ns + j] * th2 + bf;
+#pragma unroll
+                                for (int i = 0; i < N; ++i) yo[i] = SSD(q, j, i) * bf + yo[i];
+                            }
+                        } else {
+                            const double al1 = theta - 1.0, be1 = 1.0 - 2.0 * theta;
+                            const double al2 = 1.0 - theta, be2 = theta * (theta - 1.0);
+#pragma unroll
+                            for (int i = 0; i < N; ++i) {
+                                const double u0 = SOS(q, i), u1 = SSS(q, i);
+                                double v = u1;
+                                v -= u0;
+                                v = al1 * SSD(q, 0, i) + be1 * v;
+                                v = theta * SSD(q, ns - 1, i) + v;
+                                v = al2 * u0 + be2 * v;
+                                v = theta * u1 + v;
+                                yo[i] = v;
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < N; ++i) bb.ss[(((int64_t)col * NP + q) * N + i) * B + inst] = yo[i];
+                    }
+                }
                 ++col;
             }
             if (status != DSB_STATUS_OK) finish(status);
@@ -566,8 +763,15 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
             if (start == 1) {
 #pragma unroll
                 for (int k = 0; k < N; ++k) SDF(0, k) = h * SDY(k);
+                if constexpr (SENS) {
+#pragma unroll 1
+                    for (int q = 0; q < NP; ++q)
+#pragma unroll
+                        for (int k = 0; k < N; ++k) SSD(q, 0, k) = h * SDS(q, k);
+                }
             }
             stage = start;
+            eq = 0;
             state = R_STAGE;
         }
         // ================= STAGE: set_phi + predict_stage_sdirk (runge_kutta.rs:645-665) ========================
@@ -608,12 +812,27 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
 #pragma unroll
             for (int j = 0; j < NP; ++j) pl[j] = SP(j);
             double delta[N];
+            bool sens_eq = false;
+            if constexpr (SENS) sens_eq = eq > 0;
             {
                 double tmpv[N];
+                if (sens_eq) {
+                    if constexpr (SENS) {
+                        // SdirkCallable<SensEquations>::call_inplace on SensRhs::call_inplace: J(stage value) (phi_s + c x) + f_p e_q
+                        double ysv[N];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) { tmpv[i] = cg * x_cur[i] + SPHS(i); ysv[i] = SOY(i); }
+                        M::jac_mul(ysv, pl, t_stage, tmpv, delta);
+                        st.v[DSB_STAT_RHS_JAC_MULS] += 1;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) delta[i] += SFP(eq - 1, i);
+                    }
+                } else {
 #pragma unroll
                 for (int i = 0; i < N; ++i) tmpv[i] = cg * x_cur[i] + SPHI(i);
                 M::rhs(tmpv, pl, t_stage, delta);
                 st.v[DSB_STAT_RHS_CALLS] += 1;
+                }
                 const double beta = -op_h;
                 if (M::HAS_MASS) {
                     M::mass(x_cur, pl, t_stage, beta, delta);
@@ -636,7 +855,9 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     x_cur[i] -= delta[i];
-                    const double term = DSB_DIV(delta[i], wt[i]);
+                    double w = wt[i];
+                    if constexpr (SENS) { if (sens_eq) w = dsb_abs(SSS(eq - 1, i)) * pa.rtol + pa.atol[i]; }   // error_y = state.s[q]
+                    const double term = DSB_DIV(delta[i], w);
                     acc += term * term;
                 }
                 const double norm = dsb_sqrt(DSB_DIV(acc, (double)N));
@@ -664,8 +885,45 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
 
         // ================= POST: a stage's Newton solve ended (runge_kutta.rs:674-679, sdirk.rs:436-472) ========
         if (__any_sync(0xffffffffu, state == R_POST) && state == R_POST) {
-            st.v[DSB_STAT_NONLINEAR_SOLVER_ITERATIONS] += conv.niter;
-            if (newton_ok) {
+            st.v[DSB_STAT_NONLINEAR_SOLVER_ITERATIONS] += conv.niter;      // (sensitivity solves too, failed ones included)
+            bool stage_done = true;
+            if constexpr (SENS) {
+                if (newton_ok) {
+                    const int i = stage;
+                    if (eq == 0) {
+                        double ysv[N];
+#pragma unroll
+                        for (int k = 0; k < N; ++k) {
+                            ysv[k] = cg * x_cur[k] + SPHI(k);
+                            SOY(k) = ysv[k];
+                            SDF(i, k) = x_cur[k];
+                        }
+                        sens_update_state(ysv, t_stage);            // f_p at the stage value (runge_kutta.rs:693-695)
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < N; ++k) {
+                            SOS(eq - 1, k) = cg * x_cur[k] + SPHS(k);
+                            SSD(eq - 1, i, k) = x_cur[k];
+                        }
+                    }
+                    if (eq < NP) {
+                        sens_stage_setup(eq);
+                        eq += 1;
+                        state = R_NEWTON;
+                        stage_done = false;
+                    } else {
+                        eq = 0;
+                        stage = i + 1;
+                        state = (stage < ns) ? R_STAGE : R_ERRTEST;
+                        stage_done = false;
+                    }
+                } else {
+                    eq = 0;
+                }
+            }
+            if (!stage_done) {
+                // handled above
+            } else if (newton_ok) {
                 const int i = stage;
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
@@ -700,4 +958,10 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
 #undef SOY
 #undef SPHI
 #undef SP
+#undef SSD
+#undef SSS
+#undef SDS
+#undef SOS
+#undef SFP
+#undef SPHS
 }

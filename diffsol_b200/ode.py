@@ -61,6 +61,18 @@ class OdeSolverProblem:
             raise ValueError("build the problem with OdeBuilder.sens_rtol(..).sens_atol(..) or .sensitivities()")
         return self._solver("bdf")
 
+    def tr_bdf2_sens(self):
+        """`problem.tr_bdf2_sens::<LS>()` (ode_solver/problem.rs): TR-BDF2 with forward sensitivities."""
+        if not self.has_sens:
+            raise ValueError("build the problem with OdeBuilder.sens_rtol(..).sens_atol(..) or .sensitivities()")
+        return self._solver("tr_bdf2")
+
+    def esdirk34_sens(self):
+        """`problem.esdirk34_sens::<LS>()`: ESDIRK34 with forward sensitivities."""
+        if not self.has_sens:
+            raise ValueError("build the problem with OdeBuilder.sens_rtol(..).sens_atol(..) or .sensitivities()")
+        return self._solver("esdirk34")
+
 
 class OdeBuilder:
     """Fluent builder; defaults are the reference's (builder.rs:112-140): t0=0, h0=1, rtol=1e-6, atol=[1e-6]."""

@@ -128,12 +128,13 @@ int dsb_problem_set_options(dsb_problem* p, const dsb_options* opt);        /* O
 int dsb_problem_get_options(const dsb_problem* p, dsb_options* opt);
 /* Forward sensitivities: OdeBuilder::sens_rtol / sens_atol (builder.rs:1466-1477, 1682-1716) and the choice of
  * `problem.bdf_sens::<LS>()` over `problem.bdf::<LS>()` (ode_solver/problem.rs:819-830).  enable != 0: the batch integrates
- * one sensitivity vector d y / d p_q per parameter beside the state (Bdf::sensitivity_solve, ode_solver/bdf.rs:934-989).
+ * one sensitivity vector d y / d p_q per parameter beside the state (Bdf::sensitivity_solve, ode_solver/bdf.rs:934-989; Sdirk).
  * natol == 0 keeps the sensitivities out of the error test (OdeBuilder::turn_off_sensitivities_error_control); natol == 1
  * broadcasts sens_atol[0], natol == nstates gives it per state (param_scales = 1).  Equation sets qualify when they provide
  * sens_mul / init_sens (OdeEquationsImplicitSens), have no root / output / reset function and nstates <= 16 (ODEs, and
- * singular-mass DAEs, whose sensitivities are made consistent first: set_consistent_augmented, state.rs:167-238); the method
- * must be DSB_METHOD_BDF.  Anything else: DSB_ERR from the solve call. */
+ * singular-mass DAEs, whose sensitivities are made consistent first: set_consistent_augmented, state.rs:167-238); every
+ * method (Bdf::sensitivity_solve; Rk::do_stage_sdirk's sensitivity part, runge_kutta.rs:691-745).  Anything else: DSB_ERR
+ * from the solve call. */
 int dsb_problem_set_sensitivities(dsb_problem* p, int32_t enable, double sens_rtol, const double* sens_atol, int32_t natol);
 
 /* ---- user equation sets: "user RHS closures and DiffSL-JIT modules drop in" -------------------------------------------------

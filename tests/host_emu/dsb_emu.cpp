@@ -121,7 +121,7 @@ struct EmuCall {
 
 // forward sensitivities: the on-chip BDF lane kernel instantiated for DsbWithSens<M> (dsb_inst.cu: SensLauncher)
 struct EmuSensCall {
-    const dsb_problem* pr; int free_running;
+    const dsb_problem* pr; int method; int free_running;
     const double* params; int64_t B; const double* t_eval; int nt;
     double* ys; double* sens; int64_t* stats; int32_t* status;
     int rc;
@@ -135,7 +135,7 @@ struct EmuSensCall {
             std::vector<int32_t> color_full; std::vector<uint8_t> nz_full;
             if (dsb_host::fill_problem_args(*pr, 1, nt, &pa, &probes, &color_full, &nz_full) != DSB_OK) { rc = DSB_BAD_ARG; return; }
             pa.free_running = free_running;
-            dsb_host::build_tableau(DSB_METHOD_BDF, &pa.rk);
+            dsb_host::build_tableau(method, &pa.rk);
             pa.quorum = DSB_DEFAULT_QUORUM;
             std::vector<double> y0(N), dy0(N), h0(1), ysb((size_t)nt * N), ssb((size_t)nt * NP * N), fin_t(1), fin_h(1);
             std::vector<int32_t> st(DSB_NSTATS), status1(1), fin_order(1), ridx(1), nc(1);
@@ -150,9 +150,15 @@ struct EmuSensCall {
                 for (auto& v : st) v = 0;
                 status1[0] = -1;
                 unsigned long long work_counter = 0;
-                blockDim.x = BdfLayout<MS>::THREADS;
-                dsb_init_kernel<M>(pa, bb, 1);
-                dsb_bdf_solve_dense_kernel<MS>(pa, bb, &work_counter);
+                if (method == DSB_METHOD_BDF) {
+                    blockDim.x = BdfLayout<MS>::THREADS;
+                    dsb_init_kernel<M>(pa, bb, 1);
+                    dsb_bdf_solve_dense_kernel<MS>(pa, bb, &work_counter);
+                } else {
+                    blockDim.x = SdirkLayout<MS>::THREADS;
+                    dsb_init_kernel<M>(pa, bb, pa.rk.order);
+                    dsb_sdirk_solve_dense_kernel<MS>(pa, bb, &work_counter);
+                }
                 for (size_t k = 0; k < ysb.size(); ++k) ys[b * ysb.size() + k] = ysb[k];
                 for (size_t k = 0; k < ssb.size(); ++k) sens[b * ssb.size() + k] = ssb[k];
                 for (int s = 0; s < DSB_NSTATS; ++s) stats[b * DSB_NSTATS + s] = st[s] + (s == DSB_STAT_RHS_JAC_MULS ? probes : 0);
@@ -264,7 +270,7 @@ int emu_solve(int model, int method, int kernel, double rtol, const double* atol
 
 // solve_dense_sensitivities (or, free_running, the step / interpolate / interpolate_sens loop) through the sensitivity
 // instantiation of the on-chip BDF lane kernel; ys [B][nt][n], sens [B][nt][np][n].  sens_natol = 0: not in the error test.
-int emu_solve_sens(int model, double rtol, const double* atol, int natol, double t0, double h0, const dsb_options* opt,
+int emu_solve_sens(int model, int method, double rtol, const double* atol, int natol, double t0, double h0, const dsb_options* opt,
                    double sens_rtol, const double* sens_atol, int sens_natol, const double* params, int64_t B,
                    const double* t_eval, int nt, int free_running, double* ys, double* sens, int64_t* stats, int32_t* status) {
     dsb_problem pr;
@@ -275,7 +281,7 @@ int emu_solve_sens(int model, double rtol, const double* atol, int natol, double
     if (!dsb_dispatch_model(model, dims)) return DSB_BAD_ARG;
     if (natol != 1 && natol != pr.n) return DSB_BAD_ARG;
     pr.sens = 1; pr.sens_rtol = sens_rtol; pr.sens_atol.assign(sens_atol, sens_atol + sens_natol);
-    EmuSensCall call{&pr, free_running, params, B, t_eval, nt, ys, sens, stats, status, DSB_ERR};
+    EmuSensCall call{&pr, method, free_running, params, B, t_eval, nt, ys, sens, stats, status, DSB_ERR};
     dsb_dispatch_model(model, call);
     return call.rc;
 }

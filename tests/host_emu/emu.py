@@ -79,7 +79,7 @@ def lib():
                                        ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32),
                                        ctypes.POINTER(ctypes.c_int32)]
         L.emu_solve_sens.restype = ctypes.c_int
-        L.emu_solve_sens.argtypes = [ctypes.c_int, ctypes.c_double, dp, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+        L.emu_solve_sens.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, dp, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                      ctypes.POINTER(Options), ctypes.c_double, dp, ctypes.c_int, dp, ctypes.c_int64, dp, ctypes.c_int,
                                      ctypes.c_int, dp, dp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32)]
         L.emu_smem_band_lu.restype = ctypes.c_int
@@ -123,7 +123,7 @@ def solve(model_id, n, np_, params, t_eval, method="bdf", kernel="lane", rtol=1e
     return dict(ys=ys, stats=stats, status=status, fin=fin, root_idx=root_idx, ncols=ncols)
 
 
-def solve_sens(model_id, n, np_, params, t_eval, rtol=1e-6, atol=1e-6, t0=0.0, h0=1.0, sens_rtol=None, sens_atol=None,
+def solve_sens(model_id, n, np_, params, t_eval, method="bdf", rtol=1e-6, atol=1e-6, t0=0.0, h0=1.0, sens_rtol=None, sens_atol=None,
                options=None, free_running=False):
     """The sensitivity instantiation of the on-chip BDF lane kernel (DsbWithSens<M>) -> dict(ys[B, nt, n],
     sens[B, nt, np, n], stats[B, 16], status[B])."""
@@ -143,7 +143,7 @@ def solve_sens(model_id, n, np_, params, t_eval, rtol=1e-6, atol=1e-6, t0=0.0, h
         lib().dsb_options_default(ctypes.byref(opt))
         for k, v in options.items():
             setattr(opt, k, v)
-    rc = lib().emu_solve_sens(int(model_id), float(rtol), _dp(atol), len(atol), float(t0), float(h0),
+    rc = lib().emu_solve_sens(int(model_id), METHODS[method], float(rtol), _dp(atol), len(atol), float(t0), float(h0),
                               ctypes.byref(opt) if opt is not None else None, float(sens_rtol or 0.0), _dp(sa), len(sa), _dp(params), B,
                               _dp(t_eval), nt, int(free_running), _dp(ys), _dp(sens),
                               stats.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), status.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))

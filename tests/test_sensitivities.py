@@ -225,6 +225,32 @@ def test_kernel_source_reproduces_the_dae_sens_snapshots(oracle):
     assert np.array_equal(r["ys"], ys) and np.array_equal(r["sens"], se)
 
 
+@pytest.mark.parametrize("method", ["tr_bdf2", "esdirk34"])
+def test_sdirk_kernel_source_reproduces_the_sens_snapshots(oracle, method):
+    """The (E)SDIRK lane kernel's sensitivity instantiation on the host: every counter of the reference's four TR-BDF2 /
+    ESDIRK34 sensitivity snapshots through the free-running loop, and bit-identical to the oracle on Robertson ODE and DAE
+    sweeps with the sensitivities in the error test."""
+    from host_emu import emu
+    r = emu.solve_sens(0, 2, 2, np.array([[0.1, 1.0]]), np.arange(10.0), method=method, sens_rtol=1e-6, sens_atol=[1e-6, 1e-6], free_running=True)
+    assert r["status"][0] == 0 and r["stats"][0, :13].tolist() == SDIRK_SENS_SNAPSHOTS[(method, "exp_decay")]
+    opts = dict(max_nonlinear_solver_iterations=10) if method == "tr_bdf2" else None
+    r = emu.solve_sens(2, 3, 3, np.array([[0.04, 1e4, 3e7]]), np.array(GOLD["robertson_dae_points"]["t"]), method=method, rtol=1e-4,
+                       atol=[1e-8, 1e-6, 1e-6], free_running=True, options=opts)
+    assert r["status"][0] == 0 and r["stats"][0, :13].tolist() == SDIRK_SENS_SNAPSHOTS[(method, "robertson_dae")]
+    p = robertson_sweep(6)
+    te = np.array([0.4, 4.0, 40.0, 400.0])
+    tol = dict(rtol=1e-4, atol=[1e-8, 1e-6, 1e-6])
+    # (TR-BDF2 with the sensitivities in the error test takes millions of steps on this problem -- see the GPU test; short horizon)
+    if method == "tr_bdf2":
+        te = np.array([0.01, 0.02, 0.04])
+    for model, model_id in (("robertson_ode", 3), ("robertson_dae", 2)):
+        ys, se, st, status = oracle.batch_solve_dense_sens(
+            oracle.make_desc(model, method=method, sens=True, sens_rtol=1e-5, sens_atol=[1e-7] * 3, powmode=1, **tol), p, te)
+        r = emu.solve_sens(model_id, 3, 3, p, te, method=method, sens_rtol=1e-5, sens_atol=[1e-7] * 3, **tol)
+        assert np.array_equal(r["status"], status) and (status == 0).all() and np.array_equal(r["stats"][:, :13], st[:, :13])
+        assert np.array_equal(r["ys"], ys) and np.array_equal(r["sens"], se)
+
+
 def test_sensitivity_arguments_are_checked_without_a_gpu():
     """dsb_problem_set_sensitivities: argument errors come back as DSB_BAD_ARG with a message (no device needed)."""
     import ctypes
@@ -358,6 +384,51 @@ def test_gpu_sensitivities_bit_exact_robertson_dae(dsb, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("method", ["tr_bdf2", "esdirk34"])
+def test_gpu_sdirk_sensitivities(dsb, oracle, method):
+    """problem.tr_bdf2_sens() / esdirk34_sens(): the reference's four (E)SDIRK sensitivity snapshots on the GPU, and sweeps
+    (exponential decay, Robertson ODE and DAE) bit-identical to the oracle."""
+    prob = dsb.OdeBuilder().rhs_implicit("exp_decay").p(np.array([[0.1, 1.0]] * 40)).sens_rtol(1e-6).sens_atol([1e-6, 1e-6]).build()
+    solver = getattr(prob, method + "_sens")()
+    ys, sens = solver.solve_dense_sensitivities(np.arange(10.0), free_running=True)
+    assert (solver.status() == 0).all()
+    assert (solver.statistics_array()[:, :13] == np.array(SDIRK_SENS_SNAPSHOTS[(method, "exp_decay")])).all()
+    b = (dsb.OdeBuilder().rhs_implicit("robertson_dae").p(np.array([[0.04, 1e4, 3e7]] * 40)).rtol(1e-4).atol([1e-8, 1e-6, 1e-6]).sensitivities())
+    if method == "tr_bdf2":
+        b = b.ode_options(max_nonlinear_solver_iterations=10)
+    solver = getattr(b.build(), method + "_sens")()
+    ys, sens = solver.solve_dense_sensitivities(np.array(GOLD["robertson_dae_points"]["t"]), free_running=True)
+    assert (solver.status() == 0).all()
+    assert (solver.statistics_array()[:, :13] == np.array(SDIRK_SENS_SNAPSHOTS[(method, "robertson_dae")])).all()
+    te = np.array([0.4, 4.0, 40.0, 400.0, 4000.0])
+    tol = dict(rtol=1e-4, atol=[1e-8, 1e-6, 1e-6])
+    # TR-BDF2's sensitivity error estimate is not filtered through the iteration matrix (runge_kutta.rs:812-822), which on
+    # this stiff problem drives the step size down to 2.6 MILLION steps per instance (restated as it is, measured on the
+    # oracle); the reference's own Robertson test keeps the sensitivities out of the error test, and so does this sweep
+    sens_tol = dict(sens_rtol=1e-5, sens_atol=[1e-7] * 3) if method == "esdirk34" else dict(sens_rtol=None, sens_atol=None)
+    for model, B in (("robertson_ode", 1200), ("robertson_dae", 1200)):
+        p = robertson_sweep(B)
+        b = dsb.OdeBuilder().rhs_implicit(model).p(p).rtol(tol["rtol"]).atol(tol["atol"])
+        b = b.sens_rtol(1e-5).sens_atol([1e-7] * 3) if method == "esdirk34" else b.sensitivities()
+        solver = getattr(b.build(), method + "_sens")()
+        ys, sens = solver.solve_dense_sensitivities(te)
+        ys_o, se_o, st_o, status_o = oracle.batch_solve_dense_sens(
+            oracle.make_desc(model, method=method, sens=True, powmode=1, **sens_tol, **tol), p, te)
+        assert np.array_equal(solver.status(), status_o)
+        assert np.array_equal(solver.statistics_array()[:, :13], st_o[:, :13])
+        assert np.array_equal(ys, ys_o, equal_nan=True) and np.array_equal(sens, se_o, equal_nan=True)
+    p = exp_sweep(2000)
+    t = np.linspace(0.5, 10.0, 20)
+    solver = getattr(dsb.OdeBuilder().rhs_implicit("exp_decay").p(p).sens_rtol(1e-6).sens_atol([1e-6, 1e-6]).build(), method + "_sens")()
+    ys, sens = solver.solve_dense_sensitivities(t)
+    ys_o, se_o, st_o, status_o = oracle.batch_solve_dense_sens(
+        oracle.make_desc("exp_decay", method=method, sens=True, sens_rtol=1e-6, sens_atol=[1e-6, 1e-6], powmode=1), p, t)
+    assert np.array_equal(solver.statistics_array()[:, :13], st_o[:, :13]) and np.array_equal(ys, ys_o) and np.array_equal(sens, se_o)
+    ex = p[:, 1, None] * np.exp(-p[:, 0, None] * t[None, :])
+    assert np.abs(sens[:, :, 0, 0] + t[None, :] * ex).max() < 2e-4
+
+
+@pytest.mark.gpu
 def test_gpu_sensitivities_against_finite_differences(dsb):
     """Independent of the oracle: d y / d p from the sensitivity equations against central differences of two plain solves."""
     B = 256
@@ -386,10 +457,7 @@ def test_gpu_sensitivity_errors(dsb):
     pv = np.array([[1.0]] * 4)
     with pytest.raises(capi.DiffsolB200Error, match="sensitivities"):
         dsb.OdeBuilder().rhs_implicit("van_der_pol").p(pv).sensitivities().build().bdf_sens().solve_dense_sensitivities(t)
-    # SDIRK with sensitivities is not built
     prob = dsb.OdeBuilder().rhs_implicit("exp_decay").p(p).sensitivities().build()
-    with pytest.raises(capi.DiffsolB200Error, match="sensitivities"):
-        prob.tr_bdf2().solve_dense_sensitivities(t)
     # a problem with sensitivities goes through the sensitivity entry point, one without cannot
     with pytest.raises(capi.DiffsolB200Error, match="sensitivities"):
         prob.bdf().solve_dense(t)
