@@ -3,14 +3,14 @@
 TooManyNonlinearSolverFailures an artefact of integrating in scaled time tau = t / T (model van_der_pol_scaled, which lets
 one t_eval grid serve every instance)?  The same instances are integrated by the oracle in PHYSICAL time with their own
 t_final (model van_der_pol, p = [mu], one solve per instance) and the per-instance outcomes are compared.
-   python tools/config3_scaling_check.py [sample] > profiles/r2_config3_scaling_check.json"""
+   python tests/diagnostics/config3_scaling_check.py [sample] > profiles/r2_config3_scaling_check.json"""
 import json
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import oracle as orc  # noqa: E402
 from diffsol_b200 import sweeps  # noqa: E402

@@ -4,14 +4,14 @@ the reference (nalgebra's LU) rounds the product and the sum separately.  The or
 reference arithmetic, and with fused multiply-adds in the trailing updates of every LU factorisation -- and the outcomes are
 compared: instances whose 13 integer counters differ, and the largest weighted state difference.  (CPU experiment; the
 speed side of the question is tools/fp64_peak.cu: dmma_tflops vs dfma_tflops.)
-   python tools/dmma_rounding_check.py > profiles/r2_dmma_rounding_check.json"""
+   python tests/diagnostics/dmma_rounding_check.py > profiles/r2_dmma_rounding_check.json"""
 import json
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import oracle as orc  # noqa: E402
 from diffsol_b200 import sweeps  # noqa: E402
