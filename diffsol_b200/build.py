@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 _TAG = os.environ.get("DSB_LIB_TAG", "")
 OUT_DIR = os.path.join(HERE, "_lib" + ("_" + _TAG if _TAG else ""))
 LIB = os.path.join(OUT_DIR, "libdiffsol_b200.so")
-N_MODELS = 22
+N_MODELS = 23
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",

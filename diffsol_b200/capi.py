@@ -15,7 +15,7 @@ METHODS = {"bdf": 0, "tr_bdf2": 1, "esdirk34": 2}
 MODELS = {
     "exp_decay": 0, "exp_decay_algebraic": 1, "robertson_dae": 2, "robertson_ode": 3,
     "robertson_ode_g3": 4, "dydt_y2": 5, "gaussian_decay": 6, "van_der_pol": 7, "van_der_pol_scaled": 8,
-    "heat1d_dae_256": 9, "heat1d_dae_32": 10, "spm": 11, "spm99": 12, "exp_decay_root": 13, "spm_stop": 14, "spm99_stop": 15, "heat1d_dae_32_bc": 16, "exp_decay_reset": 17, "heat2d_10": 18, "ball_bounce": 19, "exp_decay_two_roots": 20, "spm_cycle": 21,
+    "heat1d_dae_256": 9, "heat1d_dae_32": 10, "spm": 11, "spm99": 12, "exp_decay_root": 13, "spm_stop": 14, "spm99_stop": 15, "heat1d_dae_32_bc": 16, "exp_decay_reset": 17, "heat2d_10": 18, "ball_bounce": 19, "exp_decay_two_roots": 20, "spm_cycle": 21, "exp_decay_algebraic_reset": 22,
 }
 STAT_NAMES = [
     "number_of_linear_solver_setups",

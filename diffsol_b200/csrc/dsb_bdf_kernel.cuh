@@ -466,7 +466,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                                 },
                                 [&](double (&J)[N][N]) {
                                     lane_jacobian_to<M>(pa, y0l, pl0, t, st, [&](int j, int i, double val) { J[j][i] = val; });
-                                }, ic_conv, false);
+                                }, ic_conv, false, pa.opt.ic_use_linesearch != 0);
 #pragma unroll
                             for (int i = 0; i < N; ++i) { SSS(q, i) = sq[i]; SDF(q, 0, i) = sq[i]; SDF(q, 1, i) = dsq[i] * h; }
                         }
@@ -772,6 +772,24 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                             ++col;
                         }
                         interpolate(t_root, yo);
+                        double dyg[N];                      // a DAE's reset: state_mut_back also interpolates dy (bdf.rs:1245-1252, 788-810)
+                        if constexpr (dsb_model_has_reset<M>::value && M::HAS_MASS) {
+                            double pi = 1.0, d_pi = 0.0;
+#pragma unroll
+                            for (int i = 0; i < N; ++i) dyg[i] = 0.0;
+#pragma unroll 1
+                            for (int j = 0; j < order; ++j) {
+                                const double j_t = (double)j;
+                                const double denom = h * (1.0 + j_t);
+                                const double w = DSB_DIV(t_root - (t - h * j_t), denom);
+                                const double dw = DSB_DIV(1.0, denom);
+                                const double new_d_pi = d_pi * w + pi * dw;
+                                pi *= w;
+                                d_pi = new_d_pi;
+#pragma unroll
+                                for (int i = 0; i < N; ++i) dyg[i] = d_pi * SD(j + 1, i) + dyg[i];
+                            }
+                        }
                         if (!free_running) t = t_root;      // state_mut_back; the harness loop leaves the state at the end of the step
                         bool ended = true;
                         if constexpr (dsb_model_has_reset<M>::value) {
@@ -780,12 +798,32 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                                 // dy <- f(y, t)), then a new stop time and on with the integration -- or TstopReached
                                 double yr[N], dyr[N];
                                 M::reset(yo, pl, t, yr);
-                                M::rhs(yr, pl, t, dyr);
-                                st.v[DSB_STAT_RHS_CALLS] += 1;
+                                int reset_status = DSB_STATUS_OK;
+                                if constexpr (M::HAS_MASS) {
+                                    // state.apply_reset_with_mass (state.rs:279-306): set_consistent with a Newton solver WITHOUT
+                                    // line search, from the reset y and the dy interpolated at the root; InitOp and the mass
+                                    // matrix are evaluated at problem.t0 (state.rs:114-119)
+                                    LaneConvergence ic_conv;
+                                    ic_conv.tol = pa.opt.nonlinear_solver_tolerance;
+                                    ic_conv.eta = pa.tab.eta_reset;
+                                    ic_conv.max_iter = pa.opt.ic_max_newton_iterations;
+                                    ic_conv.reset();
+#pragma unroll
+                                    for (int i = 0; i < N; ++i) dyr[i] = dyg[i];
+                                    reset_status = lane_consistent_solve<M>(pa, pl, yr, dyr,
+                                        [&](const double (&x)[N], double (&out)[N]) { M::rhs(x, pl, pa.t0, out); st.v[DSB_STAT_RHS_CALLS] += 1; },
+                                        [&](double (&J)[N][N]) {
+                                            lane_jacobian_to<M>(pa, yr, pl, pa.t0, st, [&](int j, int i, double val) { J[j][i] = val; });
+                                        }, ic_conv, true, false);
+                                } else {
+                                    M::rhs(yr, pl, t, dyr);
+                                    st.v[DSB_STAT_RHS_CALLS] += 1;
+                                }
 #pragma unroll
                                 for (int i = 0; i < N; ++i) { SY(i) = yr[i]; SYP(i) = dyr[i]; }
                                 root_found = -1;
-                                if (t < bb.t_eval[nt - 1]) { reset_now = true; stopped_on_root = false; }
+                                if (reset_status != DSB_STATUS_OK) finish(reset_status);
+                                else if (t < bb.t_eval[nt - 1]) { reset_now = true; stopped_on_root = false; }
                                 else finish(DSB_STATUS_OK);                        // TstopReached
                                 ended = false;
                             }

@@ -100,7 +100,7 @@ const dsb_launch_fn g_launch_table[DSB_MODEL_COUNT] = {
     dsb_launch_model_0, dsb_launch_model_1, dsb_launch_model_2, dsb_launch_model_3,
     dsb_launch_model_4, dsb_launch_model_5, dsb_launch_model_6, dsb_launch_model_7,
     dsb_launch_model_8, dsb_launch_model_9, dsb_launch_model_10, dsb_launch_model_11,
-    dsb_launch_model_12, dsb_launch_model_13, dsb_launch_model_14, dsb_launch_model_15, dsb_launch_model_16, dsb_launch_model_17, dsb_launch_model_18, dsb_launch_model_19, dsb_launch_model_20, dsb_launch_model_21,
+    dsb_launch_model_12, dsb_launch_model_13, dsb_launch_model_14, dsb_launch_model_15, dsb_launch_model_16, dsb_launch_model_17, dsb_launch_model_18, dsb_launch_model_19, dsb_launch_model_20, dsb_launch_model_21, dsb_launch_model_22,
 };
 
 // instance-major <-> batch-major re-layout on the device (the host-facing layouts follow the

@@ -17,7 +17,7 @@
 // at the algebraic rows).  eq_rhs(x, out) and eq_jac(J) do their own counting.
 template <class M, class RhsFn, class JacFn>
 DSB_DEV int lane_consistent_solve(const DsbProblemArgs& pa, const double* p, double (&y)[M::N], double (&dy)[M::N],
-                                  RhsFn&& eq_rhs, JacFn&& eq_jac, LaneConvergence& conv, bool zero_dv) {
+                                  RhsFn&& eq_rhs, JacFn&& eq_jac, LaneConvergence& conv, bool zero_dv, bool use_linesearch) {
     constexpr int N = M::N;
     if (!M::HAS_MASS) return DSB_STATUS_OK;
     const double t0 = pa.t0;
@@ -88,7 +88,7 @@ DSB_DEV int lane_consistent_solve(const DsbProblemArgs& pa, const double* p, dou
             for (int it = 0; it < conv.max_iter && result < 0; ++it) {
                 int res = LANE_CONTINUE;
                 bool have_res = false;
-                if (pa.opt.ic_use_linesearch) {
+                if (use_linesearch) {
                     if (conv.niter == 0) {
                         fun(y_tmp, delta);
                         if (!lu.solve(delta)) { result = 2; break; }
@@ -165,7 +165,7 @@ DSB_DEV int lane_set_consistent(const DsbProblemArgs& pa, const double* p, doubl
     const double t0 = pa.t0;
     return lane_consistent_solve<M>(pa, p, y, dy,
                                     [&](const double (&x)[N], double (&out)[N]) { M::rhs(x, p, t0, out); st.v[DSB_STAT_RHS_CALLS] += 1; },
-                                    [&](double (&J)[N][N]) { lane_jacobian<M>(pa, y, p, t0, J, st); }, conv, true);
+                                    [&](double (&J)[N][N]) { lane_jacobian<M>(pa, y, p, t0, J, st); }, conv, true, pa.opt.ic_use_linesearch != 0);
 }
 
 template <class M>

@@ -511,6 +511,10 @@ cudaError_t DSB_LAUNCH_SYMBOL(const DsbProblemArgs* pa, const DsbBatchBuffers* b
                                                  cudaStream_t stream, cudaEvent_t mid, unsigned long long* work_counter,
                                                  DsbCoopState* coop, const double* atol_host, int* launches) {
     coop->ys_im_used = nullptr;
+    // a reset on a DAE (state.apply_reset_with_mass, state.rs:279-306) is built into the on-chip BDF lane kernel only
+    if (InstModel::HAS_MASS && dsb_model_has_reset<InstModel>::value &&
+        (method != DSB_METHOD_BDF || !kLaneCapable || coop->exec_mode > 1 || pa->ragged || pa->sens))
+        return cudaErrorNotSupported;
     if (pa->ragged) {
         if (pa->sens) return cudaErrorNotSupported;
         return RaggedLauncher<InstModel, kRaggedCapable>::run(pa, bb, method, stream, mid, work_counter, launches);

@@ -34,5 +34,5 @@ DSB_DECLARE_LAUNCH(0) DSB_DECLARE_LAUNCH(1) DSB_DECLARE_LAUNCH(2) DSB_DECLARE_LA
 DSB_DECLARE_LAUNCH(4) DSB_DECLARE_LAUNCH(5) DSB_DECLARE_LAUNCH(6) DSB_DECLARE_LAUNCH(7)
 DSB_DECLARE_LAUNCH(8) DSB_DECLARE_LAUNCH(9) DSB_DECLARE_LAUNCH(10) DSB_DECLARE_LAUNCH(11)
 DSB_DECLARE_LAUNCH(12) DSB_DECLARE_LAUNCH(13) DSB_DECLARE_LAUNCH(14) DSB_DECLARE_LAUNCH(15)
-DSB_DECLARE_LAUNCH(16) DSB_DECLARE_LAUNCH(17) DSB_DECLARE_LAUNCH(18) DSB_DECLARE_LAUNCH(19) DSB_DECLARE_LAUNCH(20) DSB_DECLARE_LAUNCH(21)
+DSB_DECLARE_LAUNCH(16) DSB_DECLARE_LAUNCH(17) DSB_DECLARE_LAUNCH(18) DSB_DECLARE_LAUNCH(19) DSB_DECLARE_LAUNCH(20) DSB_DECLARE_LAUNCH(21) DSB_DECLARE_LAUNCH(22)
 #undef DSB_DECLARE_LAUNCH

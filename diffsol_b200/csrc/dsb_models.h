@@ -37,6 +37,7 @@ enum dsb_model_id {
     DSB_MODEL_BALL_BOUNCE = 19,         // n=2  np=3   bouncing ball x' = v, v' = -g with the root x and the reset v -> -e v (ode_solver/mod.rs:1001-1080)
     DSB_MODEL_EXP_DECAY_TWO_ROOTS = 20, // n=2  np=2   exp_decay with the roots y[0] - 0.6, y[0] - 0.3 and no reset (exponential_decay.rs:827-832, 890-912)
     DSB_MODEL_SPM_CYCLE = 21,           // n=42 np=1   spm_stop with a reset: at a voltage cut-off the cell goes back to its initial (charged) state
+    DSB_MODEL_EXP_DECAY_ALGEBRAIC_RESET = 22,  // n=3 np=2  exp_decay_algebraic with p = [k, y0], the roots y[0] - 0.6, y[0] - 2 and the reset y -> y + 2 (a DAE with a reset: apply_reset_with_mass)
     DSB_MODEL_COUNT
 };
 
@@ -147,6 +148,20 @@ struct ModelExpDecayAlgebraic {
         y[N - 1] = 0.0;
     }
     DSB_HD static void init_sens(const double*, double, const double*, double* y) { for (int i = 0; i < N; ++i) y[i] = 0.0; }
+};
+
+// The DAE of the reference's reset-with-mass problem (test_models/exponential_decay_with_algebraic.rs:501-560,
+// exponential_decay_with_algebraic_with_reset_problem_sens, without its sensitivities): p = [k, y0], every state starts at y0,
+// roots y[0] - 0.6 and y[0] - 2.0 (exponential_decay_root_0_6_and_2_0), reset y -> y + 2 (exponential_decay_reset_y_plus_2).
+// A reset on a DAE goes through state.apply_reset_with_mass (ode_solver/state.rs:279-306): reset, then set_consistent.
+struct ModelExpDecayAlgebraicReset : ModelExpDecayAlgebraic {
+    static constexpr int NP = 2;
+    static constexpr int NROOTS = 2;
+    static constexpr bool HAS_RESET = true;
+    static constexpr bool HAS_SENS = false;
+    DSB_HD static void init(const double* p, double, double* y) { for (int i = 0; i < N; ++i) y[i] = p[1]; }
+    DSB_HD static void root(const double* x, const double*, double, double* g) { g[0] = x[0] - 0.6; g[1] = x[0] - 2.0; }
+    DSB_HD static void reset(const double* x, const double*, double, double* y) { for (int i = 0; i < N; ++i) y[i] = x[i] + 2.0; }
 };
 
 // Robertson chemical kinetics as an index-1 DAE, p = [k1, k2, k3]
@@ -627,6 +642,7 @@ template <> struct dsb_model_by_id<DSB_MODEL_HEAT2D_10> { typedef ModelHeat2d<10
 template <> struct dsb_model_by_id<DSB_MODEL_BALL_BOUNCE> { typedef ModelBallBounce type; };
 template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY_TWO_ROOTS> { typedef ModelExpDecayTwoRoots type; };
 template <> struct dsb_model_by_id<DSB_MODEL_SPM_CYCLE> { typedef ModelSpmCycle type; };
+template <> struct dsb_model_by_id<DSB_MODEL_EXP_DECAY_ALGEBRAIC_RESET> { typedef ModelExpDecayAlgebraicReset type; };
 
 // traits of an equation set: written component-wise (`*_i` functions), declares a band for df/dy
 template <class M, class = void> struct dsb_is_componentwise : std::false_type {};
@@ -660,6 +676,7 @@ inline bool dsb_dispatch_model(int id, F&& f) {
         case DSB_MODEL_BALL_BOUNCE: f.template operator()<ModelBallBounce>(); return true;
         case DSB_MODEL_EXP_DECAY_TWO_ROOTS: f.template operator()<ModelExpDecayTwoRoots>(); return true;
         case DSB_MODEL_SPM_CYCLE: f.template operator()<ModelSpmCycle>(); return true;
+        case DSB_MODEL_EXP_DECAY_ALGEBRAIC_RESET: f.template operator()<ModelExpDecayAlgebraicReset>(); return true;
         default: return false;
     }
 }

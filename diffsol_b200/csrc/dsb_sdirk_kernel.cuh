@@ -362,7 +362,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                                 },
                                 [&](double (&J)[N][N]) {
                                     lane_jacobian_to<M>(pa, y0l, pl0, t, st, [&](int j, int i, double val) { J[j][i] = val; });
-                                }, ic_conv, false);
+                                }, ic_conv, false, pa.opt.ic_use_linesearch != 0);
 #pragma unroll
                             for (int i = 0; i < N; ++i) { SSS(q, i) = sq[i]; SDS(q, i) = dsq[i]; }
                         }

@@ -54,7 +54,8 @@ enum dsb_model {
     DSB_ROBERTSON_ODE_G3 = 4, DSB_DYDT_Y2 = 5, DSB_GAUSSIAN_DECAY = 6, DSB_VAN_DER_POL = 7,
     DSB_VAN_DER_POL_SCALED = 8, DSB_HEAT1D_DAE_256 = 9, DSB_HEAT1D_DAE_32 = 10, DSB_SPM = 11, DSB_SPM99 = 12,
     DSB_EXP_DECAY_ROOT = 13, DSB_SPM_STOP = 14, DSB_SPM99_STOP = 15,
-    DSB_HEAT1D_DAE_32_BC = 16, DSB_EXP_DECAY_RESET = 17, DSB_HEAT2D_10 = 18, DSB_BALL_BOUNCE = 19, DSB_EXP_DECAY_TWO_ROOTS = 20, DSB_SPM_CYCLE = 21
+    DSB_HEAT1D_DAE_32_BC = 16, DSB_EXP_DECAY_RESET = 17, DSB_HEAT2D_10 = 18, DSB_BALL_BOUNCE = 19, DSB_EXP_DECAY_TWO_ROOTS = 20, DSB_SPM_CYCLE = 21,
+    DSB_EXP_DECAY_ALGEBRAIC_RESET = 22
 };
 
 /* ---- statistics: one row of DSB_NSTATS int64 per instance.  Indices 0-9 are the fields of

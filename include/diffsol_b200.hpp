@@ -156,7 +156,8 @@ public:
             {"spm99", DSB_SPM99}, {"exp_decay_root", DSB_EXP_DECAY_ROOT}, {"spm_stop", DSB_SPM_STOP},
             {"spm99_stop", DSB_SPM99_STOP}, {"heat1d_dae_32_bc", DSB_HEAT1D_DAE_32_BC},
             {"exp_decay_reset", DSB_EXP_DECAY_RESET}, {"heat2d_10", DSB_HEAT2D_10}, {"ball_bounce", DSB_BALL_BOUNCE},
-            {"exp_decay_two_roots", DSB_EXP_DECAY_TWO_ROOTS}, {"spm_cycle", DSB_SPM_CYCLE}};
+            {"exp_decay_two_roots", DSB_EXP_DECAY_TWO_ROOTS}, {"spm_cycle", DSB_SPM_CYCLE},
+            {"exp_decay_algebraic_reset", DSB_EXP_DECAY_ALGEBRAIC_RESET}};
         return m;
     }
     // .rhs_implicit(f, jac) + .init / .mass / .root / .reset / .out of the reference: one built-in device functor

@@ -246,7 +246,7 @@ int new_and_consistent(const Problem& pr, int solver_order, InitialState* st);
 // sensitivity vector); a no-op without a singular mass matrix
 int consistent_solve(const Problem& pr, const std::function<void(const double*, double, double*)>& eq_rhs,
                      const std::function<void(const double*, double, double*)>& eq_jacobian, Vec& y_state, Vec& dy_state,
-                     Convergence* shared_conv, bool zero_dv);
+                     Convergence* shared_conv, bool zero_dv, int use_linesearch = -1 /* -1: ic_options.use_linesearch */);
 
 enum StopReason { INTERNAL_TIMESTEP = 0, TSTOP_REACHED = 1, STEP_ERROR = 2, ROOT_FOUND = 3 };
 

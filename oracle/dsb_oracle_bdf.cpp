@@ -535,18 +535,39 @@ struct Bdf : Method {
         Vec ynew(n);
         int e = interpolate(t, ynew.data());
         if (e) return e;
-        y_ = ynew;                          // dy is interpolated as well in the reference; apply_reset overwrites it
+        y_ = ynew;
+        // interpolate_derivative_from_diff (bdf.rs:788-810): the guess apply_reset_with_mass's set_consistent starts from
+        {
+            double pi = 1.0, d_pi = 0.0;
+            for (int i = 0; i < n; ++i) dy_[i] = 0.0;
+            for (int j = 0; j < order; ++j) {
+                const double j_t = (double)j;
+                const double denom = h_ * (1.0 + j_t);
+                const double w = (t - (t_ - h_ * j_t)) / denom;
+                const double dw = 1.0 / denom;
+                const double new_d_pi = d_pi * w + pi * dw;
+                pi *= w;
+                d_pi = new_d_pi;
+                for (int i = 0; i < n; ++i) dy_[i] = d_pi * D(j + 1)[i] + dy_[i];
+            }
+        }
         t_ = t;
         is_state_modified = true;
         return ST_OK;
     }
     // method.rs:175-181 -> state.rs:246-270 through state_mut() (no mass matrix: dy = f(y, t))
     int apply_reset() override {
-        if (!pr.model.reset || pr.model.has_mass) return ST_BAD_ARG;
+        if (!pr.model.reset) return ST_BAD_ARG;
         is_state_modified = true;
         Vec ynew(n);
         pr.model.reset(y_.data(), pr.p.data(), t_, ynew.data());
         y_ = ynew;
+        if (pr.model.has_mass) {
+            // state.apply_reset_with_mass (state.rs:279-306): set_consistent with a Newton solver WITHOUT line search, from the
+            // reset y and the dy interpolated at the root; InitOp and the mass matrix are evaluated at problem.t0 (state.rs:114-119)
+            return consistent_solve(pr, [this](const double* x, double t, double* out) { pr.rhs(x, t, out); },
+                                    [this](const double* x, double t, double* J) { pr.jacobian(x, t, J); }, y_, dy_, nullptr, true, 0);
+        }
         pr.rhs(y_.data(), t_, dy_.data());
         return ST_OK;
     }

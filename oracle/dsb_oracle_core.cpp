@@ -274,7 +274,8 @@ void Stats::record_linear_solver_setup(SolverState s) {
 // ds kept at the algebraic rows).
 int consistent_solve(const Problem& pr, const std::function<void(const double*, double, double*)>& eq_rhs,
                      const std::function<void(const double*, double, double*)>& eq_jacobian, Vec& y_state, Vec& dy_state,
-                     Convergence* shared_conv, bool zero_dv) {
+                     Convergence* shared_conv, bool zero_dv, int use_linesearch) {
+    const bool linesearch = use_linesearch < 0 ? pr.opt.ic_use_linesearch : use_linesearch != 0;
     const int n = pr.n();
     if (!pr.model.has_mass) return ST_OK;
     Vec M((size_t)n * n);
@@ -332,7 +333,7 @@ int consistent_solve(const Problem& pr, const std::function<void(const double*, 
         for (int it = 0; it < conv.max_iter && result < 0; ++it) {
             ConvStatus res = CONTINUE;
             bool have_res = false;
-            if (pr.opt.ic_use_linesearch) {
+            if (linesearch) {
                 if (conv.niter == 0) {
                     fun(y_tmp, delta);
                     if (!lu.solve(delta.data())) { result = 2; break; }

@@ -53,6 +53,7 @@ MODELS = {
     "ball_bounce": 19,
     "exp_decay_two_roots": 20,
     "spm_cycle": 21,
+    "exp_decay_algebraic_reset": 22,
 }
 
 
