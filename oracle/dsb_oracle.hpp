@@ -8,7 +8,8 @@
 // The reference is Rust and cannot be compiled in this image (no rustc/cargo, no vendored crates),
 // so this is a restatement, written from the reference sources cited on every function
 // (paths relative to /root/reference/crates).  It is PINNED against the reference's own inline
-// `insta` statistics snapshots and golden solution tables (tests/test_oracle_golden.py):
+// `insta` statistics snapshots and golden solution tables (tests/test_oracle_golden.py; forward sensitivities:
+// tests/test_sensitivities.py, 7 of the reference's 8 nalgebra snapshots; `solve(final_time)`: tests/test_solve_ragged.py):
 // every integer of OdeSolverStatistics / OpStatistics must match.
 //
 // Third-party arithmetic the reference delegates to and that is restated here from the published
