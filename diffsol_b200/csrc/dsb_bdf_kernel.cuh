@@ -1058,7 +1058,19 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
         }
         // ================= POST: a Newton solve ended (bdf.rs:1338-1563) ==================================
         DSB_PROF_BLOCK(9, state == L_POST)
-        if (__any_sync(0xffffffffu, state == L_POST) && state == L_POST) {
+        // Sensitivities: a lane passes through NEWTON (1 + np) x (iterations) times per step and through the END of POST (error
+        // test, _update_diff on every difference array, then TSTOP / OUTPUT / PREDICT) once; left alone those blocks run on
+        // every trip with ~3 lanes (ncu, profiles/r2_sens_kernel_ncu_summary.txt).  A lane whose last sensitivity solve has
+        // converged therefore WAITS in front of POST until a quorum (or half of the active lanes) is there too -- waiting
+        // changes when a lane runs, never its arithmetic; with two waiting groups (this one and the slow pool) that each
+        // release at half of the active lanes, all lanes can never wait at once.
+        bool hold_post = false;
+        if constexpr (SENS) {
+            const bool at_end = state == L_POST && newton_ok && eq == NP;
+            const int n_end = __popc(__ballot_sync(0xffffffffu, at_end));
+            hold_post = at_end && !(n_end >= quorum || 2 * n_end >= n_active);
+        }
+        if (__any_sync(0xffffffffu, state == L_POST && !hold_post) && state == L_POST && !hold_post) {
             bool run_main = true;
             if constexpr (SENS) {
                 // sensitivity_solve (bdf.rs:934-989) after a successful main solve: one Newton solve per parameter on the
