@@ -12,6 +12,7 @@
 #define DSB_MAX_STATES 64      // register/local-memory lane kernels; larger n uses the block-cooperative path
 #define DSB_MAX_ORDER 5        // bdf_state.rs:44
 #define DSB_NDIFF (DSB_MAX_ORDER + 3)
+#define DSB_DEFAULT_NEWTON_PASSES 3   // Newton iterations a warp may run per trip of its state machine (dsb_bdf_kernel.cuh, NEWTON block)
 #define DSB_DEFAULT_QUORUM 16     // lanes of a warp that make a heavy block worth running (see dsb_bdf_kernel.cuh)
 #define DSB_LANE_THREADS 128   // block size of the one-thread-per-instance kernels
 
@@ -66,7 +67,8 @@ struct DsbProblemArgs {
     DsbSdirkTableau rk;
     // forward sensitivities (problem.bdf_sens(), ode_solver/problem.rs:819-830; builder.rs:1682-1716): sens != 0 integrates
     // one sensitivity vector per parameter; sens_error_control puts them into the error test with sens_rtol / sens_atol
-    int32_t ragged, reserved2;     // solve(final_time) form (DsbRagged<M> kernels): 1 = count the columns, 2 = write them
+    int32_t ragged;                // solve(final_time) form (DsbRagged<M> kernels): 1 = count the columns, 2 = write them
+    int32_t newton_passes;         // lane kernels: Newton iterations a warp may run per trip of its state machine (< 1 reads as 1)
     int32_t sens, sens_error_control;
     double sens_rtol;
     double sens_atol[DSB_MAX_STATES];

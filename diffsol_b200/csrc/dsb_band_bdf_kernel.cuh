@@ -139,6 +139,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
     const int nt = pa.nt;
     const bool free_running = pa.free_running != 0;
     const int quorum = pa.quorum;
+    const int newton_passes = pa.newton_passes < 1 ? 1 : pa.newton_passes;       // see dsb_bdf_kernel.cuh (NEWTON block)
     const double eps = 2.220446049250313e-16;
 
     // ---- per-lane registers (the controller of dsb_bdf_kernel.cuh) ----------------------------------------
@@ -695,7 +696,10 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
         }
 
         // ================= NEWTON: one iteration (newton.rs:13-36, line_search.rs:48-69) =====================================
-        if (__any_sync(0xffffffffu, state == L_NEWTON) && state == L_NEWTON) {
+#pragma unroll 1
+        for (int pass = 0; pass < newton_passes; ++pass) {
+        if (!__any_sync(0xffffffffu, state == L_NEWTON)) break;
+        if (state == L_NEWTON) {
             // delta = F(y) = M (y + psi - y0) - c f(t, y)   (op/bdf.rs:240-256)
             const double mc = -c;
             if constexpr (M::HAS_MASS) {
@@ -743,6 +747,7 @@ __global__ void __maxnreg__((BandBdfLayout<M, T>::MAXNREG)) dsb_band_bdf_solve_d
                 if (s == LANE_CONVERGED) { newton_ok = true; state = L_POST; }
                 else if (s == LANE_DIVERGED || conv.niter >= conv.max_iter) { newton_ok = false; state = L_POST; }
             }
+        }
         }
         // ================= POST: a Newton solve ended (bdf.rs:1338-1563) =====================================================
         if (__any_sync(0xffffffffu, state == L_POST) && state == L_POST) {

@@ -74,6 +74,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
     const int nt = pa.nt;
     const bool free_running = pa.free_running != 0;
     const int quorum = pa.quorum;
+    const int newton_passes = pa.newton_passes < 1 ? 1 : pa.newton_passes;       // see dsb_bdf_kernel.cuh (NEWTON block)
     const double eps = 2.220446049250313e-16;
     const int ns = pa.rk.s;
     const int start = (pa.rk.a[0] == 0.0) ? 1 : 0;        // skip_first_stage (runge_kutta.rs:286-288)
@@ -602,7 +603,10 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
         }
 
         // ================= NEWTON: one iteration on F(x) = M x - h f(phi + c x) =================================
-        if (__any_sync(0xffffffffu, state == R_NEWTON) && state == R_NEWTON) {
+#pragma unroll 1
+        for (int pass = 0; pass < newton_passes; ++pass) {
+        if (!__any_sync(0xffffffffu, state == R_NEWTON)) break;
+        if (state == R_NEWTON) {
             band_for<U4, double>(N, [&](int i) { return cg * GX(i) + GPHI(i); }, [&](int i, double r) { GTMP(i) = r; });
             const double beta = -op_h;
             band_for<U2, double>(N, [&](int i) {
@@ -640,6 +644,7 @@ __global__ void __maxnreg__((BandSdirkLayout<M, T>::MAXNREG)) dsb_band_sdirk_sol
                 if (s == LANE_CONVERGED) { newton_ok = true; state = R_POST; }
                 else if (s == LANE_DIVERGED || conv.niter >= conv.max_iter) { newton_ok = false; state = R_POST; }
             }
+        }
         }
 
         // ================= POST: a stage's Newton solve ended (runge_kutta.rs:674-679, sdirk.rs:436-472) ========

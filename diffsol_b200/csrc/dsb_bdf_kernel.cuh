@@ -133,6 +133,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
     const int nt = pa.nt;
     const bool free_running = pa.free_running != 0;
     const int quorum = pa.quorum;
+    const int newton_passes = pa.newton_passes < 1 ? 1 : pa.newton_passes;
     const double eps = 2.220446049250313e-16;
 
     // ---- per-lane registers -----------------------------------------------------------------------
@@ -960,8 +961,14 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
         }
 
         // ================= NEWTON: one iteration (newton.rs:13-36, line_search.rs:48-69) ==================
+        // A lane that needs another iteration takes it in the same trip (up to newton_passes of them): the trip's other blocks
+        // -- the per-step chain is the larger part of the loop body -- then run once per STEP of most lanes, not once per
+        // iteration, with correspondingly more lanes each time.  The loop is rolled: one copy of the block in the code.
+#pragma unroll 1
+        for (int pass = 0; pass < newton_passes; ++pass) {
         DSB_PROF_BLOCK(7, state == L_NEWTON)
-        if (__any_sync(0xffffffffu, state == L_NEWTON) && state == L_NEWTON) {
+        if (!__any_sync(0xffffffffu, state == L_NEWTON)) break;
+        if (state == L_NEWTON) {
             double pl[NP > 0 ? NP : 1];
 #pragma unroll
             for (int j = 0; j < NP; ++j) pl[j] = SP(j);
@@ -1055,6 +1062,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                 if (s == LANE_CONVERGED) { newton_ok = true; state = L_POST; }
                 else if (s == LANE_DIVERGED || conv.niter >= conv.max_iter) { newton_ok = false; state = L_POST; }
             }
+        }
         }
         // ================= POST: a Newton solve ended (bdf.rs:1338-1563) ==================================
         DSB_PROF_BLOCK(9, state == L_POST)

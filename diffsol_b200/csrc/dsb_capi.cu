@@ -450,6 +450,8 @@ static int solve_impl(dsb_batch* b, int32_t method, const double* t_eval, int32_
     pa.free_running = free_running;
     build_tableau(method, &pa.rk);
     pa.quorum = DSB_DEFAULT_QUORUM;
+    pa.newton_passes = DSB_DEFAULT_NEWTON_PASSES;
+    if (const char* q = getenv("DSB_NEWTON_PASSES")) { int v = atoi(q); if (v >= 1 && v <= 16) pa.newton_passes = v; }   // tuning knob
     if (const char* q = getenv("DSB_COOP_DENSE_ONLY")) pa.coop_dense_only = atoi(q);
     if (const char* q = getenv("DSB_WBAND_FORCE_REDO")) pa.reserved1 = atoi(q);      // test hook (dsb_wband_bdf_kernel.cuh)
     if (const char* q = getenv("DSB_QUORUM")) { int v = atoi(q); if (v >= 1 && v <= 33) pa.quorum = v; }   // tuning knob

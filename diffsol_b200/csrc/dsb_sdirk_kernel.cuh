@@ -96,6 +96,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
     const int nt = pa.nt;
     const bool free_running = pa.free_running != 0;
     const int quorum = pa.quorum;
+    const int newton_passes = pa.newton_passes < 1 ? 1 : pa.newton_passes;
     const double eps = 2.220446049250313e-16;
     const int ns = pa.rk.s;
     const int start = (pa.rk.a[0] == 0.0) ? 1 : 0;        // skip_first_stage (runge_kutta.rs:286-288)
@@ -807,7 +808,11 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
         }
 
         // ================= NEWTON: one iteration on F(x) = M x - h f(phi + c x) =================================
-        if (__any_sync(0xffffffffu, state == R_NEWTON) && state == R_NEWTON) {
+        // (up to newton_passes iterations per trip, rolled: see dsb_bdf_kernel.cuh)
+#pragma unroll 1
+        for (int pass = 0; pass < newton_passes; ++pass) {
+        if (!__any_sync(0xffffffffu, state == R_NEWTON)) break;
+        if (state == R_NEWTON) {
             double pl[NP > 0 ? NP : 1];
 #pragma unroll
             for (int j = 0; j < NP; ++j) pl[j] = SP(j);
@@ -881,6 +886,7 @@ dsb_sdirk_solve_dense_kernel(const __grid_constant__ DsbProblemArgs pa, const __
                 if (s == LANE_CONVERGED) { newton_ok = true; state = R_POST; }
                 else if (s == LANE_DIVERGED || conv.niter >= conv.max_iter) { newton_ok = false; state = R_POST; }
             }
+        }
         }
 
         // ================= POST: a stage's Newton solve ended (runge_kutta.rs:674-679, sdirk.rs:436-472) ========

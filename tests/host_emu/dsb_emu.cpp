@@ -37,7 +37,7 @@ struct EmuCall {
         if (dsb_host::fill_problem_args(*pr, 1, nt, &pa, &probes, &color_full, &nz_full) != DSB_OK) { rc = DSB_BAD_ARG; return; }
         pa.free_running = free_running;
         dsb_host::build_tableau(method, &pa.rk);
-        pa.quorum = DSB_DEFAULT_QUORUM;
+        pa.quorum = DSB_DEFAULT_QUORUM; pa.newton_passes = DSB_DEFAULT_NEWTON_PASSES;
         if (const char* q = getenv("DSB_WBAND_FORCE_REDO")) pa.reserved1 = atoi(q);
         std::vector<double> atol_full(N);
         for (int i = 0; i < N; ++i) atol_full[i] = pr->atol.size() == 1 ? pr->atol[0] : pr->atol[i];
@@ -136,7 +136,7 @@ struct EmuSensCall {
             if (dsb_host::fill_problem_args(*pr, 1, nt, &pa, &probes, &color_full, &nz_full) != DSB_OK) { rc = DSB_BAD_ARG; return; }
             pa.free_running = free_running;
             dsb_host::build_tableau(method, &pa.rk);
-            pa.quorum = DSB_DEFAULT_QUORUM;
+            pa.quorum = DSB_DEFAULT_QUORUM; pa.newton_passes = DSB_DEFAULT_NEWTON_PASSES;
             std::vector<double> y0(N), dy0(N), h0(1), ysb((size_t)nt * N), ssb((size_t)nt * NP * N), fin_t(1), fin_h(1);
             std::vector<int32_t> st(DSB_NSTATS), status1(1), fin_order(1), ridx(1), nc(1);
             for (int64_t b = 0; b < B; ++b) {
@@ -189,7 +189,7 @@ struct EmuRaggedCall {
             if (dsb_host::fill_problem_args(*pr, 1, 1, &pa, &probes, &color_full, &nz_full) != DSB_OK) { rc = DSB_BAD_ARG; return; }
             pa.free_running = 0; pa.ragged = 2;
             dsb_host::build_tableau(method, &pa.rk);
-            pa.quorum = DSB_DEFAULT_QUORUM;
+            pa.quorum = DSB_DEFAULT_QUORUM; pa.newton_passes = DSB_DEFAULT_NEWTON_PASSES;
             std::vector<double> y0(N), dy0(N), h0(1), ysb(NOUT), fin_t(1), fin_h(1);
             std::vector<int32_t> st(DSB_NSTATS), status1(1), fin_order(1), ridx(1), nc(1);
             const int64_t off[2] = {0, 0};
