@@ -95,4 +95,7 @@ struct DsbBatchBuffers {
     const int64_t* rag_off;  // [B + 1]
     double* rag_ts;
     double* rag_ys;
+    // sensitivity BDF lane kernel built with DSB_SENS_SDIFF_GLOBAL: the difference arrays of the sensitivities, one word of
+    // every RESIDENT lane side by side ([np * 8 * n][grid * threads]); set by the launcher
+    double* sens_ws;
 };

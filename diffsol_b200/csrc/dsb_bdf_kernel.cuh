@@ -76,12 +76,22 @@ struct BdfLayout {
     // 166 -> 94 words of shared memory per lane, 5 -> 9 warps per SM for Robertson -- 760 -> 1166 ms per 10^6 instances:
     // the blocks that touch sdiff run with ~3 active lanes per warp, and their L2 round trips are not hidden.)
     static constexpr bool SENS = dsb_model_sens_on<M>::value;
+    // SDIFF_GLOBAL: the difference arrays of the sensitivities live in a lane-interleaved global-memory slot (L2-resident:
+    // 148 blocks x THREADS x NP x 8 x N words) and every predictor / psi pair is formed in PREDICT, where the lanes arrive in
+    // groups (end-of-step hold, slow pool), and kept in shared memory for the NP solves of the attempt.
+#ifdef DSB_SENS_SDIFF_GLOBAL
+    static constexpr bool SDIFF_GLOBAL = SENS;
+#else
+    static constexpr bool SDIFF_GLOBAL = false;
+#endif
+    static constexpr int SDIFF_WORDS = NP * DSB_NDIFF * N;          // per lane, shared or global
     static constexpr int O_SDF = O_ST + (DSB_NSTATS_USED + 1) / 2;  // sdiff[NP][DSB_NDIFF][N]
-    static constexpr int O_SS = O_SDF + NP * DSB_NDIFF * N;         // state.s[NP][N]
+    static constexpr int O_SS = O_SDF + (SDIFF_GLOBAL ? 0 : SDIFF_WORDS);   // state.s[NP][N]
     static constexpr int O_SDL = O_SS + NP * N;                     // s_deltas[NP][N]
     static constexpr int O_SFP = O_SDL + NP * N;                    // f_p e_q at (y_predict, t_predict) [NP][N]
-    static constexpr int O_SPR = O_SFP + NP * N;                    // s_predict[N]
-    static constexpr int O_SYC = O_SPR + N;                         // the main solve's y while the sensitivities are solved
+    static constexpr int O_SPR = O_SFP + NP * N;                    // s_predict[N] (SDIFF_GLOBAL: [NP][N])
+    static constexpr int O_SPS = O_SPR + (SDIFF_GLOBAL ? NP * N : N);       // SDIFF_GLOBAL: psi - s_predict of every sensitivity [NP][N]
+    static constexpr int O_SYC = O_SPS + (SDIFF_GLOBAL ? NP * N : 0);       // the main solve's y while the sensitivities are solved
     static constexpr int WORDS = SENS ? O_SYC + N : O_SDF;
     static constexpr int THREADS = LaneBlockShape<WORDS, N>::THREADS;
     static constexpr int MAXNREG = LaneBlockShape<WORDS, N>::MAXNREG;
@@ -118,13 +128,16 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #define SY(i) SM(Lay::O_Y + (i))
 #define SYP(i) SM(Lay::O_YP + (i))
 #define SP(i) SM(Lay::O_P + (i))
-#define SDF(q, j, i) SM(Lay::O_SDF + ((q) * DSB_NDIFF + (j)) * N + (i))
+#define SDF(q, j, i) (*(Lay::SDIFF_GLOBAL ? sdf_g + (size_t)(((q) * DSB_NDIFF + (j)) * N + (i)) * sdf_stride : &SM(Lay::O_SDF + ((q) * DSB_NDIFF + (j)) * N + (i))))
 #define SSS(q, i) SM(Lay::O_SS + (q) * N + (i))
 #define SDL(q, i) SM(Lay::O_SDL + (q) * N + (i))
 #define SFP(q, i) SM(Lay::O_SFP + (q) * N + (i))
-#define SPR(i) SM(Lay::O_SPR + (i))
+#define SPR(q, i) SM(Lay::O_SPR + (Lay::SDIFF_GLOBAL ? (q) * N : 0) + (i))
+#define SPS(q, i) SM(Lay::O_SPS + (q) * N + (i))
 #define SYC(i) SM(Lay::O_SYC + (i))
     constexpr bool SENS = Lay::SENS;
+    const size_t sdf_stride = (size_t)gridDim.x * Lay::THREADS;
+    double* const sdf_g = Lay::SDIFF_GLOBAL ? bb.sens_ws + ((size_t)blockIdx.x * Lay::THREADS + threadIdx.x) : nullptr;
     static_assert(!SENS || (dsb_model_has_sens<M>::value && dsb_model_nroots<M>::value == 0 &&
                             !dsb_model_nout<M>::has_out && !dsb_model_has_reset<M>::value),
                   "sensitivities: equations with sens_mul / init_sens, no root / output / reset functions");
@@ -317,6 +330,12 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
     };
     // the start of the Newton solve for sensitivity q (bdf.rs:948-968): predictor and psi from sdiff[q], s_new <- s_predict
     auto sens_setup = [&](int q) {
+        if constexpr (Lay::SDIFF_GLOBAL) {          // formed by sens_predict_all() in PREDICT
+#pragma unroll
+            for (int i = 0; i < N; ++i) { psi_neg_y0[i] = SPS(q, i); y_cur[i] = SPR(q, i); }
+            conv.reset();
+            return;
+        }
         // (one pass over the columns: each accumulator sees its terms in the reference's order)
         double sp[N];
 #pragma unroll
@@ -334,10 +353,45 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
         for (int i = 0; i < N; ++i) {
             psi_neg_y0[i] *= a;
             psi_neg_y0[i] -= sp[i];
-            SPR(i) = sp[i];
+            SPR(q, i) = sp[i];
             y_cur[i] = sp[i];
         }
         conv.reset();
+    };
+    // SDIFF_GLOBAL: the same sums for every sensitivity at once, the column loop unrolled under a predicate so that the
+    // loads of all columns are in flight together (each accumulator still sees its terms in the reference's order)
+    auto sens_predict_all = [&]() {
+        if constexpr (Lay::SDIFF_GLOBAL) {
+            double sp[NP > 0 ? NP : 1][N], ps[NP > 0 ? NP : 1][N];
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+#pragma unroll
+                for (int i = 0; i < N; ++i) { const double d0 = SDF(q, 0, i); sp[q][i] = 0.0; sp[q][i] += d0; }
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+#pragma unroll
+                for (int i = 0; i < N; ++i) { const double d1 = SDF(q, 1, i); sp[q][i] += d1; ps[q][i] = pa.tab.gamma[1] * d1; }
+#pragma unroll
+            for (int j = 2; j <= DSB_MAX_ORDER; ++j) {
+                if (j <= order) {
+                    const double g = pa.tab.gamma[j];
+#pragma unroll
+                    for (int q = 0; q < NP; ++q)
+#pragma unroll
+                        for (int i = 0; i < N; ++i) { const double dj = SDF(q, j, i); sp[q][i] += dj; ps[q][i] = g * dj + ps[q][i]; }
+                }
+            }
+            const double a = pa.tab.alpha[order];
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    ps[q][i] *= a;
+                    ps[q][i] -= sp[q][i];
+                    SPR(q, i) = sp[q][i];
+                    SPS(q, i) = ps[q][i];
+                }
+        }
     };
 
 #ifdef DSB_LANE_PROFILE          // warp-scheduler occupancy counters (warp-uniform values, lane 0 publishes them)
@@ -947,6 +1001,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                     SYP(i) = yp[i];
                 }
                 t_predict = t + h;
+                sens_predict_all();
             }
             state = L_NEWTON;
             if (pending_etf) {
@@ -1033,7 +1088,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
             } else {
                 double ypl[N];
 #pragma unroll
-                for (int i = 0; i < N; ++i) { y_cur[i] -= delta[i]; ypl[i] = sens_eq ? SPR(i) : SYP(i); }
+                for (int i = 0; i < N; ++i) { y_cur[i] -= delta[i]; ypl[i] = sens_eq ? SPR(eq - 1, i) : SYP(i); }
                 // Newton norm weights use the PREDICTOR (line_search.rs:67, convergence.rs:64-66)
                 const double acc = weighted_sum(delta, ypl);
                 const double norm = dsb_sqrt(DSB_DIV_N(acc));
@@ -1096,7 +1151,7 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                         for (int i = 0; i < N; ++i) {
                             SSS(eq - 1, i) = y_cur[i];
                             double dl = y_cur[i];
-                            dl -= SPR(i);
+                            dl -= SPR(eq - 1, i);
                             SDL(eq - 1, i) = dl;
                         }
                     }
@@ -1165,7 +1220,33 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #pragma unroll
                         for (int i = 0; i < N; ++i) SD(j, i) = SD(j, i) + 1.0 * SD(j + 1, i);
                     }
-                    if constexpr (SENS) {           // _update_diff on every sdiff (bdf.rs:629-633)
+                    if constexpr (Lay::SDIFF_GLOBAL) {      // the same update with one array's columns loaded together (global slot)
+#pragma unroll 1
+                        for (int qs = 0; qs < NP; ++qs) {
+                            double col[DSB_MAX_ORDER + 1][N], o1[N], prev[N];
+#pragma unroll
+                            for (int j = 0; j <= DSB_MAX_ORDER; ++j)
+                                if (j <= ord) {
+#pragma unroll
+                                    for (int i = 0; i < N; ++i) col[j][i] = SDF(qs, j, i);
+                                }
+#pragma unroll
+                            for (int i = 0; i < N; ++i) o1[i] = SDF(qs, ord + 1, i);
+#pragma unroll
+                            for (int i = 0; i < N; ++i) {
+                                const double dl = SDL(qs, i);
+                                SDF(qs, ord + 2, i) = dl - o1[i];
+                                SDF(qs, ord + 1, i) = dl;
+                                prev[i] = dl;
+                            }
+#pragma unroll
+                            for (int j = DSB_MAX_ORDER; j >= 0; --j)
+                                if (j <= ord) {
+#pragma unroll
+                                    for (int i = 0; i < N; ++i) { prev[i] = col[j][i] + 1.0 * prev[i]; SDF(qs, j, i) = prev[i]; }
+                                }
+                        }
+                    } else if constexpr (SENS) {           // _update_diff on every sdiff (bdf.rs:629-633)
 #pragma unroll 1
                         for (int qs = 0; qs < NP; ++qs) {
 #pragma unroll
@@ -1239,5 +1320,6 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #undef SDL
 #undef SFP
 #undef SPR
+#undef SPS
 #undef SYC
 }

@@ -430,13 +430,13 @@ template <class M> struct SensCapable<M, true>
                          !dsb_model_nout<M>::has_out && !dsb_model_has_reset<M>::value> {};
 constexpr bool kSensCapable = SensCapable<InstModel, kLaneCapable>::value;
 template <class M, bool OK> struct SensLauncher {
-    static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, int, cudaStream_t, cudaEvent_t, unsigned long long*, int*) {
+    static cudaError_t run(const DsbProblemArgs*, const DsbBatchBuffers*, int, cudaStream_t, cudaEvent_t, unsigned long long*, DsbCoopState*, int*) {
         return cudaErrorNotSupported;
     }
 };
 template <class M> struct SensLauncher<M, true> {
     static cudaError_t run(const DsbProblemArgs* pa, const DsbBatchBuffers* bb, int method, cudaStream_t stream, cudaEvent_t mid,
-                           unsigned long long* work_counter, int* launches) {
+                           unsigned long long* work_counter, DsbCoopState* coop, int* launches) {
         typedef DsbWithSens<M> MS;
         const bool bdf = method == DSB_METHOD_BDF;
         const int threads = bdf ? BdfLayout<MS>::THREADS : SdirkLayout<MS>::THREADS;
@@ -457,7 +457,20 @@ template <class M> struct SensLauncher<M, true> {
         if (mid) cudaEventRecord(mid, stream);
         const unsigned blocks = (unsigned)((pa->nbatch + threads - 1) / threads);
         const unsigned grid = blocks < (unsigned)(sms * per_sm) ? blocks : (unsigned)(sms * per_sm);
-        if (bdf) dsb_bdf_solve_dense_kernel<MS><<<grid, threads, smem, stream>>>(*pa, *bb, work_counter);
+        DsbBatchBuffers bbs = *bb;
+        bbs.sens_ws = nullptr;
+        if (bdf && BdfLayout<MS>::SDIFF_GLOBAL) {        // the sensitivities' difference arrays: one column per resident lane
+            const size_t need = (size_t)BdfLayout<MS>::SDIFF_WORDS * grid * threads * sizeof(double);
+            if (coop->ws_bytes < need) {
+                if (coop->ws_mem) cudaFree(coop->ws_mem);
+                coop->ws_mem = nullptr; coop->ws_bytes = 0;
+                e = cudaMalloc(&coop->ws_mem, need);
+                if (e != cudaSuccess) return e;
+                coop->ws_bytes = need;
+            }
+            bbs.sens_ws = (double*)coop->ws_mem;
+        }
+        if (bdf) dsb_bdf_solve_dense_kernel<MS><<<grid, threads, smem, stream>>>(*pa, bbs, work_counter);
         else dsb_sdirk_solve_dense_kernel<MS><<<grid, threads, smem, stream>>>(*pa, *bb, work_counter);
         *launches += 2;
         return cudaGetLastError();
@@ -521,7 +534,7 @@ cudaError_t DSB_LAUNCH_SYMBOL(const DsbProblemArgs* pa, const DsbBatchBuffers* b
     }
     if (pa->sens) {
         if (!bb->ss) return cudaErrorNotSupported;
-        return SensLauncher<InstModel, kSensCapable>::run(pa, bb, method, stream, mid, work_counter, launches);
+        return SensLauncher<InstModel, kSensCapable>::run(pa, bb, method, stream, mid, work_counter, coop, launches);
     }
     // exec_mode 4 / automatic: the warp-per-instance banded kernel (BDF, no reset function)
     if (kWBandCapable && method == DSB_METHOD_BDF && (coop->exec_mode == 4 || (coop->exec_mode == 0 && kWBandPreferred))) {

@@ -152,6 +152,8 @@ struct EmuSensCall {
                 unsigned long long work_counter = 0;
                 if (method == DSB_METHOD_BDF) {
                     blockDim.x = BdfLayout<MS>::THREADS;
+                    std::vector<double> sens_ws((size_t)BdfLayout<MS>::SDIFF_WORDS * BdfLayout<MS>::THREADS);
+                    bb.sens_ws = sens_ws.data();
                     dsb_init_kernel<M>(pa, bb, 1);
                     dsb_bdf_solve_dense_kernel<MS>(pa, bb, &work_counter);
                 } else {
