@@ -293,3 +293,50 @@ def test_backward_integration(dsb, oracle, method):
     assert tf[0] == fin["t"] and hf[0] == fin["h"] and hf[0] < 0
     with pytest.raises(dsb.DiffsolB200Error):
         solver.solve_dense(pts[1:])                  # decreasing t_eval: rejected
+
+
+@pytest.mark.parametrize("method", ["bdf", "tr_bdf2"])
+def test_warp_scheduling_knobs_never_change_results(dsb, method, monkeypatch):
+    """The lane kernels' warp scheduler (quorum of the slow pool, Newton iterations per trip: dsb_bdf_kernel.cuh) decides
+    WHEN a lane runs a block, never what it computes: counters, states and status are bitwise the same for every setting."""
+    from diffsol_b200 import sweeps
+    nb = 3000
+    p = sweeps.robertson_sweep(np.arange(nb))
+    tol = sweeps.ROBERTSON_ODE_TOL
+
+    def run():
+        solver = getattr(dsb.OdeBuilder().rhs_implicit("robertson_ode").p(p).rtol(tol["rtol"]).atol(tol["atol"]).build(), method)()
+        ys = solver.solve_dense(sweeps.ROBERTSON_T_EVAL)
+        return ys.copy(), solver.statistics_array().copy(), solver.status().copy()
+
+    ys0, st0, status0 = run()
+    assert (status0 == 0).all()
+    for passes, quorum in ((1, 16), (2, 8), (5, 24), (16, 33)):
+        monkeypatch.setenv("DSB_NEWTON_PASSES", str(passes))
+        monkeypatch.setenv("DSB_QUORUM", str(quorum))
+        ys, st, status = run()
+        assert np.array_equal(ys.view(np.uint64), ys0.view(np.uint64)), (passes, quorum)
+        assert np.array_equal(st, st0) and np.array_equal(status, status0), (passes, quorum)
+
+
+def test_sensitivity_hold_is_scheduling_only(dsb, monkeypatch):
+    """The end-of-step hold of the sensitivity instantiation (lanes wait for a quorum in front of POST) likewise."""
+    from diffsol_b200 import sweeps
+    nb = 1500
+    p = sweeps.robertson_sweep(np.arange(nb))
+    tol = sweeps.ROBERTSON_ODE_TOL
+
+    def run():
+        solver = (dsb.OdeBuilder().rhs_implicit("robertson_ode").p(p).rtol(tol["rtol"]).atol(tol["atol"])
+                  .sens_rtol(tol["rtol"]).sens_atol([1e-6] * 3).build().bdf_sens())
+        ys, ss = solver.solve_dense_sensitivities(sweeps.ROBERTSON_T_EVAL)
+        return ys.copy(), ss.copy(), solver.statistics_array().copy()
+
+    ys0, ss0, st0 = run()
+    for passes, quorum in ((1, 1), (3, 33), (4, 6)):
+        monkeypatch.setenv("DSB_NEWTON_PASSES", str(passes))
+        monkeypatch.setenv("DSB_QUORUM", str(quorum))
+        ys, ss, st = run()
+        assert np.array_equal(ys.view(np.uint64), ys0.view(np.uint64)), (passes, quorum)
+        assert np.array_equal(ss.view(np.uint64), ss0.view(np.uint64)), (passes, quorum)
+        assert np.array_equal(st, st0), (passes, quorum)
