@@ -583,11 +583,30 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
                             err = (0.0 < e) ? e : 0.0;
                             if constexpr (SENS) {               // predict_error_control's sensitivity terms (bdf.rs:908-919)
                                 if (pa.sens_error_control) {
+                                    double xa[Lay::SDIFF_GLOBAL ? (NP > 0 ? NP : 1) : 1][N];
+                                    if constexpr (Lay::SDIFF_GLOBAL) {      // the NP columns' loads in flight together (global slot)
+#pragma unroll
+                                        for (int qs = 0; qs < NP; ++qs)
+#pragma unroll
+                                            for (int i = 0; i < N; ++i) xa[qs][i] = SDF(qs, ord + q, i);
+                                    }
 #pragma unroll 1
                                     for (int qs = 0; qs < NP; ++qs) {
                                         double x[N], ref[N];
+                                        if constexpr (Lay::SDIFF_GLOBAL) {
+                                            dsb_static_for<0, (NP > 0 ? NP : 1)>([&](auto Q) {
+                                                constexpr int QC = decltype(Q)::value;
+                                                if (QC == qs) {
 #pragma unroll
-                                        for (int i = 0; i < N; ++i) { x[i] = SDF(qs, ord + q, i); ref[i] = SSS(qs, i); }
+                                                    for (int i = 0; i < N; ++i) x[i] = xa[QC][i];
+                                                }
+                                            });
+                                        } else {
+#pragma unroll
+                                            for (int i = 0; i < N; ++i) x[i] = SDF(qs, ord + q, i);
+                                        }
+#pragma unroll
+                                        for (int i = 0; i < N; ++i) ref[i] = SSS(qs, i);
                                         const double es = sens_weighted_norm(x, ref) * pa.tab.error_const2[ord - 1 + q];
                                         err = (err < es) ? es : err;
                                     }
@@ -690,11 +709,11 @@ __global__ void __maxnreg__(BdfLayout<M>::MAXNREG) dsb_bdf_solve_dense_kernel(co
 #pragma unroll 1
                     for (int i = 1; i <= k; ++i) {
                         const double i_t = (double)i;
-#pragma unroll
-                        for (int l = 1; l <= DSB_MAX_ORDER; ++l) rrow[l] = DSB_DIV(rrow[l] * (i_t - 1.0 - factor * (double)l), i_t);
-                        double di[N];
+                        double di[N];                   // (loaded before the divisions: a global-slot load hides behind them)
 #pragma unroll
                         for (int s = 0; s < N; ++s) di[s] = SDF(qs, i, s);
+#pragma unroll
+                        for (int l = 1; l <= DSB_MAX_ORDER; ++l) rrow[l] = DSB_DIV(rrow[l] * (i_t - 1.0 - factor * (double)l), i_t);
 #pragma unroll
                         for (int j = 1; j <= DSB_MAX_ORDER; ++j) {
                             double ru_ij = rrow[1] * u[j * 6 + 1];
