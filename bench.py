@@ -31,12 +31,14 @@ UNIT = "newton_iters/s"
 WORKLOAD = "robertson_ode n=3 rate-constant sweep, Bdf, t in [0,1e4], 6 t_eval, rtol 1e-4 atol [1e-8,1e-14,1e-6]"
 
 
-def algorithmic_bytes(stats_sum, n, npar, nt, nbatch, mass_words):
-    """bytes an HBM-resident implementation must move, from the counters."""
+def algorithmic_bytes(stats_sum, n, npar, nt, nbatch, mass_words, history_cols=5 + 3):
+    """bytes an HBM-resident implementation must move, from the counters.  `history_cols`: the columns
+    of per-step history read and written by every attempted step -- the BDF difference array (max order + 3), or the s stage
+    derivatives of an (E)SDIRK method."""
     b_nl = 8 * (n * n + 4 * n + npar) + 4 * n
     b_lu = 8 * (n * n + mass_words + n * n) + 4 * n
     b_j = 8 * (n * n + n + npar)
-    b_st = 8 * (2 * (5 + 3) * n + 3 * n)
+    b_st = 8 * (2 * history_cols * n + 3 * n)
     nli, setups, me = stats_sum["nli"], stats_sum["setups"], stats_sum["me"]
     attempts = stats_sum["steps"] + stats_sum["etf"] + stats_sum["nlf"]
     return nli * b_nl + setups * b_lu + me * b_j + attempts * b_st + nbatch * nt * 8 * n
@@ -218,6 +220,13 @@ def other_configs(diffsol_b200, sweeps, orc, rank, world, local_rank, peak):
           "failed_note": "TooManyNonlinearSolverFailures under the reference's default limit of 50 (runge_kutta.rs:869-884)",
           "completed_instances_per_s": float(done.sum()) / ms * 1e3,
           "newton_iters_per_s_of_completed_instances": float(st[done, 8].sum()) / ms * 1e3}
+    # the SURVEY 8(d) byte model with TR-BDF2's three stage derivatives as the per-step history (dense n = 2 storage)
+    ssum = {"nli": int(st[:, 8].sum()), "setups": int(st[:, 0].sum()), "me": int(st[:, 12].sum()), "steps": int(st[:, 6].sum()),
+            "etf": int(st[:, 7].sum()), "nlf": int(st[:, 9].sum())}
+    alg = algorithmic_bytes(ssum, 2, int(p.shape[1]), len(S.VAN_DER_POL_T_EVAL), B, 0, history_cols=3)
+    c3["algorithmic_GB"] = alg / 1e9
+    c3["frac_hbm"] = alg / (ms * 1e-3) / 1e9 / peak
+    c3["kernel"] = "dsb_sdirk_solve_dense_kernel<ModelVanDerPolScaled> (thread per instance, state on chip)"
     nsamp = 4096
     ps = S.van_der_pol_scaled_sweep(np.arange(nsamp))
     ss = diffsol_b200.OdeBuilder().rhs_implicit("van_der_pol_scaled").p(ps).rtol(1e-4).atol([1e-6]).device(local_rank).build().tr_bdf2()
